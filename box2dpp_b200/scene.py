@@ -1,0 +1,309 @@
+"""Scene descriptions (ctypes mirror of include/b2g_scene.h) and the synthetic scenes of BASELINE.json.
+
+A ``Scene`` records the arguments of the reference's scene-construction calls
+(``b2World::CreateBody`` Box2D/Dynamics/b2World.cpp:98-122, ``b2Body::CreateFixture``
+Box2D/Dynamics/b2Body.cpp:168-214) in call order.  The same description feeds the product
+(``box2dpp_b200.batch.WorldBatch``) and the CPU oracles under ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+F32 = np.float32
+
+STATIC_BODY, KINEMATIC_BODY, DYNAMIC_BODY = 0, 1, 2
+SHAPE_CIRCLE, SHAPE_EDGE, SHAPE_POLYGON, SHAPE_CHAIN = 0, 1, 2, 3
+POLY_BOX, POLY_BOX_OFFSET, POLY_SET = 0, 1, 2
+CHAIN_OPEN, CHAIN_LOOP = 0, 1
+BD_ALLOW_SLEEP, BD_AWAKE, BD_FIXED_ROTATION, BD_BULLET, BD_ACTIVE = 1, 2, 4, 8, 16
+BD_DEFAULT = BD_ALLOW_SLEEP | BD_AWAKE | BD_ACTIVE
+WORLD_ALLOW_SLEEP, WORLD_WARM_STARTING, WORLD_CONTINUOUS, WORLD_CLEAR_FORCES = 1, 2, 4, 8
+WORLD_DEFAULT = 15
+
+
+class BodyDef(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("flags", C.c_int32),
+        ("position", C.c_float * 2),
+        ("angle", C.c_float),
+        ("linearVelocity", C.c_float * 2),
+        ("angularVelocity", C.c_float),
+        ("linearDamping", C.c_float),
+        ("angularDamping", C.c_float),
+        ("gravityScale", C.c_float),
+    ]
+
+
+class FixtureDef(C.Structure):
+    _fields_ = [
+        ("body", C.c_int32),
+        ("shapeType", C.c_int32),
+        ("shapeKind", C.c_int32),
+        ("isSensor", C.c_int32),
+        ("friction", C.c_float),
+        ("restitution", C.c_float),
+        ("density", C.c_float),
+        ("categoryBits", C.c_uint16),
+        ("maskBits", C.c_uint16),
+        ("groupIndex", C.c_int16),
+        ("pad0", C.c_int16),
+        ("radius", C.c_float),
+        ("p", C.c_float * 2),
+        ("center", C.c_float * 2),
+        ("angle", C.c_float),
+        ("firstVertex", C.c_int32),
+        ("vertexCount", C.c_int32),
+        ("hasVertex0", C.c_int32),
+        ("hasVertex3", C.c_int32),
+        ("vertex0", C.c_float * 2),
+        ("vertex3", C.c_float * 2),
+    ]
+
+
+class CScene(C.Structure):
+    _fields_ = [
+        ("gravity", C.c_float * 2),
+        ("worldFlags", C.c_int32),
+        ("bodyCount", C.c_int32),
+        ("fixtureCount", C.c_int32),
+        ("vertexCount", C.c_int32),
+        ("bodies", C.POINTER(BodyDef)),
+        ("fixtures", C.POINTER(FixtureDef)),
+        ("vertices", C.POINTER(C.c_float)),
+    ]
+
+
+class Scene:
+    """One world, as built by the user.  Mirrors b2World / b2Body construction calls."""
+
+    def __init__(self, gravity=(0.0, -10.0), flags=WORLD_DEFAULT):
+        self.gravity = (float(gravity[0]), float(gravity[1]))
+        self.flags = int(flags)
+        self.bodies: list[BodyDef] = []
+        self.fixtures: list[FixtureDef] = []
+        self.vertices: list[float] = []
+        self._c = None
+
+    # ---- b2World::CreateBody ----
+    def create_body(self, type=STATIC_BODY, position=(0.0, 0.0), angle=0.0, linear_velocity=(0.0, 0.0),
+                    angular_velocity=0.0, linear_damping=0.0, angular_damping=0.0, gravity_scale=1.0,
+                    flags=BD_DEFAULT) -> int:
+        bd = BodyDef()
+        bd.type = type
+        bd.flags = flags
+        bd.position[0], bd.position[1] = position
+        bd.angle = angle
+        bd.linearVelocity[0], bd.linearVelocity[1] = linear_velocity
+        bd.angularVelocity = angular_velocity
+        bd.linearDamping = linear_damping
+        bd.angularDamping = angular_damping
+        bd.gravityScale = gravity_scale
+        self.bodies.append(bd)
+        self._c = None
+        return len(self.bodies) - 1
+
+    def _fixture(self, body, shape_type, kind, density, friction, restitution, sensor, category, mask, group):
+        fd = FixtureDef()
+        fd.body = body
+        fd.shapeType = shape_type
+        fd.shapeKind = kind
+        fd.isSensor = int(sensor)
+        fd.friction = friction
+        fd.restitution = restitution
+        fd.density = density
+        fd.categoryBits = category
+        fd.maskBits = mask
+        fd.groupIndex = group
+        self.fixtures.append(fd)
+        self._c = None
+        return fd
+
+    _kw = dict(density=0.0, friction=0.2, restitution=0.0, sensor=False, category=1, mask=0xFFFF, group=0)
+
+    # ---- b2Body::CreateFixture with each shape class ----
+    def create_box(self, body, hx, hy, center=None, angle=0.0, **kw):
+        k = {**self._kw, **kw}
+        fd = self._fixture(body, SHAPE_POLYGON, POLY_BOX if center is None else POLY_BOX_OFFSET, k["density"],
+                           k["friction"], k["restitution"], k["sensor"], k["category"], k["mask"], k["group"])
+        fd.p[0], fd.p[1] = hx, hy
+        if center is not None:
+            fd.center[0], fd.center[1] = center
+            fd.angle = angle
+        return len(self.fixtures) - 1
+
+    def create_polygon(self, body, points, **kw):
+        k = {**self._kw, **kw}
+        fd = self._fixture(body, SHAPE_POLYGON, POLY_SET, k["density"], k["friction"], k["restitution"],
+                           k["sensor"], k["category"], k["mask"], k["group"])
+        fd.firstVertex = len(self.vertices) // 2
+        fd.vertexCount = len(points)
+        for x, y in points:
+            self.vertices += [float(x), float(y)]
+        return len(self.fixtures) - 1
+
+    def create_circle(self, body, radius, p=(0.0, 0.0), **kw):
+        k = {**self._kw, **kw}
+        fd = self._fixture(body, SHAPE_CIRCLE, 0, k["density"], k["friction"], k["restitution"], k["sensor"],
+                           k["category"], k["mask"], k["group"])
+        fd.radius = radius
+        fd.p[0], fd.p[1] = p
+        return len(self.fixtures) - 1
+
+    def create_edge(self, body, v1, v2, v0=None, v3=None, **kw):
+        k = {**self._kw, **kw}
+        fd = self._fixture(body, SHAPE_EDGE, 0, k["density"], k["friction"], k["restitution"], k["sensor"],
+                           k["category"], k["mask"], k["group"])
+        fd.firstVertex = len(self.vertices) // 2
+        fd.vertexCount = 2
+        self.vertices += [float(v1[0]), float(v1[1]), float(v2[0]), float(v2[1])]
+        if v0 is not None:
+            fd.hasVertex0 = 1
+            fd.vertex0[0], fd.vertex0[1] = v0
+        if v3 is not None:
+            fd.hasVertex3 = 1
+            fd.vertex3[0], fd.vertex3[1] = v3
+        return len(self.fixtures) - 1
+
+    def create_chain(self, body, points, loop=False, prev=None, next=None, **kw):
+        k = {**self._kw, **kw}
+        fd = self._fixture(body, SHAPE_CHAIN, CHAIN_LOOP if loop else CHAIN_OPEN, k["density"], k["friction"],
+                           k["restitution"], k["sensor"], k["category"], k["mask"], k["group"])
+        fd.firstVertex = len(self.vertices) // 2
+        fd.vertexCount = len(points)
+        for x, y in points:
+            self.vertices += [float(x), float(y)]
+        if prev is not None:
+            fd.hasVertex0 = 1
+            fd.vertex0[0], fd.vertex0[1] = prev
+        if next is not None:
+            fd.hasVertex3 = 1
+            fd.vertex3[0], fd.vertex3[1] = next
+        return len(self.fixtures) - 1
+
+    # ---- export ----
+    @property
+    def body_count(self):
+        return len(self.bodies)
+
+    @property
+    def dynamic_body_count(self):
+        return sum(1 for b in self.bodies if b.type == DYNAMIC_BODY)
+
+    def c_scene(self) -> CScene:
+        if self._c is None:
+            nb, nf, nv = len(self.bodies), len(self.fixtures), len(self.vertices) // 2
+            bodies = (BodyDef * max(nb, 1))(*self.bodies)
+            fixtures = (FixtureDef * max(nf, 1))(*self.fixtures)
+            verts = (C.c_float * max(2 * nv, 2))(*self.vertices)
+            cs = CScene()
+            cs.gravity[0], cs.gravity[1] = self.gravity
+            cs.worldFlags = self.flags
+            cs.bodyCount, cs.fixtureCount, cs.vertexCount = nb, nf, nv
+            cs.bodies = C.cast(bodies, C.POINTER(BodyDef))
+            cs.fixtures = C.cast(fixtures, C.POINTER(FixtureDef))
+            cs.vertices = C.cast(verts, C.POINTER(C.c_float))
+            self._c = (cs, bodies, fixtures, verts)  # keep the arrays alive
+        return self._c[0]
+
+
+def scene_array(scenes):
+    """Pack scenes into a contiguous C array of b2g_scene (keeps the Python objects alive)."""
+    arr = (CScene * len(scenes))()
+    for i, s in enumerate(scenes):
+        cs = s.c_scene()
+        C.memmove(C.byref(arr, i * C.sizeof(CScene)), C.byref(cs), C.sizeof(CScene))
+    arr._keep = list(scenes)
+    return arr
+
+
+# --------------------------------------------------------------------------------------------
+# Deterministic 32-bit LCG used by every randomised scene (documented in DESIGN.md):
+#   state <- state * 1664525 + 1013904223 (mod 2^32);  u = (state >> 8) / 2^24 in [0, 1)
+# --------------------------------------------------------------------------------------------
+class LCG:
+    def __init__(self, seed):
+        self.state = (int(seed) * 2654435761 + 12345) & 0xFFFFFFFF
+
+    def next_u(self) -> float:
+        self.state = (self.state * 1664525 + 1013904223) & 0xFFFFFFFF
+        return (self.state >> 8) / float(1 << 24)
+
+    def uniform(self, lo, hi) -> float:
+        return float(np.float32(lo + (hi - lo) * self.next_u()))
+
+
+def hello_world(flags=WORLD_DEFAULT) -> Scene:
+    """BASELINE config 1 — HelloWorld/HelloWorld.cpp:36-80."""
+    s = Scene((0.0, -10.0), flags)
+    ground = s.create_body(STATIC_BODY, (0.0, -10.0))
+    s.create_box(ground, 50.0, 10.0)  # CreateFixture(&groundBox, 0.0f)
+    body = s.create_body(DYNAMIC_BODY, (0.0, 4.0))
+    s.create_box(body, 1.0, 1.0, density=1.0, friction=0.3)
+    return s
+
+
+def pyramid(rows=20, flags=WORLD_DEFAULT, ground="box", jitter_seed=None, jitter=0.02) -> Scene:
+    """BASELINE configs 2/3/5 — Box2D Testbed "Pyramid" layout restated in SURVEY.md §8(d) C2.
+
+    ground="box": variant A, SetAsBox(50, 10, center (0,-10), 0) on a static body at the origin.
+    ground="edge": variant B, b2EdgeShape (-40,0)-(40,0).
+    jitter_seed: world index w; every box's x gets U(-jitter, jitter) from LCG(w) (C3 "jittered").
+    """
+    s = Scene((0.0, -10.0), flags)
+    g = s.create_body(STATIC_BODY, (0.0, 0.0))
+    if ground == "box":
+        s.create_box(g, 50.0, 10.0, center=(0.0, -10.0), angle=0.0)
+    else:
+        s.create_edge(g, (-40.0, 0.0), (40.0, 0.0))
+    rng = LCG(jitter_seed) if jitter_seed is not None else None
+    f32 = np.float32
+    a = f32(0.5)
+    x = np.array([-7.0, 0.75], dtype=f32)
+    dx = np.array([0.5625, 1.25], dtype=f32)
+    dy = np.array([1.125, 0.0], dtype=f32)
+    for i in range(rows):
+        y = x.copy()
+        for _ in range(i, rows):
+            px = float(y[0])
+            if rng is not None:
+                px = float(f32(px) + f32(rng.uniform(-jitter, jitter)))
+            b = s.create_body(DYNAMIC_BODY, (px, float(y[1])))
+            s.create_box(b, float(a), float(a), density=5.0)
+            y = y + dy
+        x = x + dx
+    return s
+
+
+def mixed(seed: int, flags=WORLD_DEFAULT, bodies=40) -> Scene:
+    """BASELINE config 4 — SURVEY.md §8(d) C4: chain terrain + alternating circles / random convex polygons.
+
+    Static body with b2ChainShape::CreateChain of 33 vertices at x = -16..16, heights U(0,2) (the two end
+    vertices are raised to y = 8 so nothing rolls off); `bodies` dynamic bodies in columns 3 m apart
+    (+U(0,1)) dropped from y in [6, 15]: even k circles r in [0.3,0.8], odd k convex polygons with 3-8 points
+    on a jittered circle r in [0.4,0.9] through b2PolygonShape::Set; density 1.  All randomness from LCG(seed).
+    """
+    rng = LCG(seed)
+    s = Scene((0.0, -10.0), flags)
+    g = s.create_body(STATIC_BODY, (0.0, 0.0))
+    pts = [(float(-16 + i), rng.uniform(0.0, 2.0)) for i in range(33)]
+    pts[0] = (pts[0][0], 8.0)
+    pts[32] = (pts[32][0], 8.0)
+    s.create_chain(g, pts)
+    for k in range(bodies):
+        px = float(F32(-13.5 + 3.0 * (k % 10)) + F32(rng.uniform(0.0, 1.0)))
+        py = float(F32(6.0 + 2.5 * (k // 10)) + F32(rng.uniform(0.0, 1.5)))
+        b = s.create_body(DYNAMIC_BODY, (px, py))
+        if k % 2 == 0:
+            s.create_circle(b, rng.uniform(0.3, 0.8), density=1.0)
+        else:
+            n = 3 + int(rng.next_u() * 6) % 6
+            r = rng.uniform(0.4, 0.9)
+            poly = []
+            for j in range(n):
+                ang = (j + 0.8 * rng.next_u()) * (2.0 * np.pi / n)
+                poly.append((float(F32(r * np.cos(ang))), float(F32(r * np.sin(ang)))))
+            s.create_polygon(b, poly, density=1.0)
+    return s

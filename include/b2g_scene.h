@@ -1,0 +1,113 @@
+/*
+ * b2g_scene.h — flat, plain-C description of ONE world as the user built it:
+ * the arguments of every b2World::CreateBody / b2Body::CreateFixture call, in
+ * call order.  It is the common input of
+ *   - the product's host layer (box2dpp_b200/csrc/b2g_host.cpp), which turns it
+ *     into world-interleaved device arenas, and
+ *   - the test oracles under oracle/ (the vanilla-library harness and the C
+ *     restatement), which rebuild the same world on the CPU.
+ *
+ * Reference interfaces this mirrors (paths relative to /root/reference):
+ *   b2BodyDef      Box2D/Dynamics/b2Body.h:53-125
+ *   b2FixtureDef   Box2D/Dynamics/b2Fixture.h:59-95,  b2Filter :35-57
+ *   b2CircleShape / b2EdgeShape / b2PolygonShape / b2ChainShape
+ *                  Box2D/Collision/Shapes/*.h
+ *   b2World(gravity) + Set* flags   Box2D/Dynamics/b2World.h:48-232
+ */
+#ifndef B2G_SCENE_H
+#define B2G_SCENE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* b2BodyType — Box2D/Dynamics/b2Body.h:41-49 */
+enum { B2G_STATIC_BODY = 0, B2G_KINEMATIC_BODY = 1, B2G_DYNAMIC_BODY = 2 };
+
+/* b2Shape::Type — Box2D/Collision/Shapes/b2Shape.h:47-54 */
+enum { B2G_SHAPE_CIRCLE = 0, B2G_SHAPE_EDGE = 1, B2G_SHAPE_POLYGON = 2, B2G_SHAPE_CHAIN = 3 };
+
+/* How a shape was built by the user (which shape-class method was called). */
+enum {
+    B2G_POLY_BOX        = 0, /* SetAsBox(hx, hy)                       b2PolygonShape.cpp:32-44  */
+    B2G_POLY_BOX_OFFSET = 1, /* SetAsBox(hx, hy, center, angle)        b2PolygonShape.cpp:46-71  */
+    B2G_POLY_SET        = 2, /* Set(points, count) (welding + hull)    b2PolygonShape.cpp:122-245 */
+    B2G_CHAIN_OPEN      = 0, /* CreateChain(vertices, count)           b2ChainShape.cpp:63-79    */
+    B2G_CHAIN_LOOP      = 1  /* CreateLoop(vertices, count)            b2ChainShape.cpp:41-61    */
+};
+
+/* body-def flag bits */
+enum {
+    B2G_BD_ALLOW_SLEEP    = 1,
+    B2G_BD_AWAKE          = 2,
+    B2G_BD_FIXED_ROTATION = 4,
+    B2G_BD_BULLET         = 8,
+    B2G_BD_ACTIVE         = 16,
+    B2G_BD_DEFAULT_FLAGS  = 1 | 2 | 16
+};
+
+/* world flag bits (b2World::SetAllowSleeping / SetWarmStarting / SetContinuousPhysics /
+ * SetAutoClearForces; b2World.h:146-180,214-217; defaults b2World.cpp:39-52) */
+enum {
+    B2G_WORLD_ALLOW_SLEEP   = 1,
+    B2G_WORLD_WARM_STARTING = 2,
+    B2G_WORLD_CONTINUOUS    = 4, /* TOI: not implemented on the device path */
+    B2G_WORLD_CLEAR_FORCES  = 8,
+    B2G_WORLD_DEFAULT_FLAGS = 1 | 2 | 4 | 8
+};
+
+typedef struct b2g_body_def {
+    int32_t type;            /* B2G_*_BODY */
+    int32_t flags;           /* B2G_BD_* */
+    float position[2];
+    float angle;
+    float linearVelocity[2];
+    float angularVelocity;
+    float linearDamping;
+    float angularDamping;
+    float gravityScale;
+} b2g_body_def;
+
+typedef struct b2g_fixture_def {
+    int32_t body;            /* index into bodies[] (creation order) */
+    int32_t shapeType;       /* B2G_SHAPE_* */
+    int32_t shapeKind;       /* B2G_POLY_* or B2G_CHAIN_* */
+    int32_t isSensor;
+    float friction;          /* default 0.2  */
+    float restitution;       /* default 0    */
+    float density;           /* default 0    */
+    uint16_t categoryBits;   /* default 1      */
+    uint16_t maskBits;       /* default 0xFFFF */
+    int16_t groupIndex;      /* default 0      */
+    int16_t pad0;
+    float radius;            /* circle: m_radius. others: ignored (b2_polygonRadius) */
+    /* circle: p = m_p.  box: p = (hx, hy), center, angle. */
+    float p[2];
+    float center[2];
+    float angle;
+    /* polygon Set / chain / edge: vertices[firstVertex .. firstVertex+vertexCount)
+       edge: 2 vertices (v1, v2).  */
+    int32_t firstVertex;
+    int32_t vertexCount;
+    /* edge: ghost vertices v0 / v3; chain: prev / next vertex (SetPrevVertex/SetNextVertex) */
+    int32_t hasVertex0, hasVertex3;
+    float vertex0[2], vertex3[2];
+} b2g_fixture_def;
+
+typedef struct b2g_scene {
+    float gravity[2];
+    int32_t worldFlags;      /* B2G_WORLD_* */
+    int32_t bodyCount;
+    int32_t fixtureCount;
+    int32_t vertexCount;
+    const b2g_body_def* bodies;       /* creation order */
+    const b2g_fixture_def* fixtures;  /* creation order (global, across bodies) */
+    const float* vertices;            /* xy pairs */
+} b2g_scene;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

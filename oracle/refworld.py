@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE — ctypes wrapper over oracle/_ref/libb2ref.so (the reference's own vanilla
+Box2D 2.3.2 compiled by oracle/Makefile; see oracle/ref_harness.cpp).  Only tests/, bench.py's
+cpu_baseline / --impl reference leg and __graft_entry__.smoke() may import this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from box2dpp_b200.scene import CScene, FixtureDef, Scene, scene_array
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "libb2ref.so")
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(REF_SO)
+        L.ref_world_create.restype = C.c_void_p
+        L.ref_world_create.argtypes = [C.POINTER(CScene)]
+        L.ref_world_destroy.argtypes = [C.c_void_p]
+        L.ref_world_record_events.argtypes = [C.c_void_p, C.c_int]
+        L.ref_world_step.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
+        for f in ("ref_world_body_count", "ref_world_contact_count", "ref_world_proxy_count"):
+            getattr(L, f).argtypes = [C.c_void_p]
+            getattr(L, f).restype = C.c_int
+        L.ref_world_get_bodies.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_world_get_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_world_get_contacts.restype = C.c_int
+        L.ref_world_get_proxies.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_world_get_proxies.restype = C.c_int
+        L.ref_world_get_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_world_get_events.restype = C.c_int
+        L.ref_polygon_build.argtypes = [C.POINTER(FixtureDef), C.c_void_p, C.c_void_p]
+        L.ref_polygon_build.restype = C.c_int
+        for f in ("ref_collide_polygons", "ref_collide_circles", "ref_collide_polygon_circle",
+                  "ref_collide_edge_circle", "ref_collide_edge_polygon"):
+            getattr(L, f).argtypes = [C.c_void_p] * 6
+        L.ref_sincosf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.ref_bench_run.restype = C.c_double
+        L.ref_bench_run.argtypes = [C.POINTER(CScene), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                    C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefWorld:
+    """A vanilla b2World built from a Scene."""
+
+    def __init__(self, scene: Scene, record_events=False):
+        self.scene = scene
+        self.h = lib().ref_world_create(C.byref(scene.c_scene()))
+        if record_events:
+            lib().ref_world_record_events(self.h, 1)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_world_destroy(self.h)
+            self.h = None
+
+    def step(self, dt, vel_iters, pos_iters):
+        lib().ref_world_step(self.h, dt, vel_iters, pos_iters)
+
+    def bodies(self) -> np.ndarray:
+        """[nb,16] float32: xf.p(2) q.s q.c | c(2) a | v(2) w | awake mass I localCenter(2) pad."""
+        nb = lib().ref_world_body_count(self.h)
+        out = np.zeros((nb, 16), np.float32)
+        lib().ref_world_get_bodies(self.h, _p(out))
+        return out
+
+    def contacts(self):
+        """(ints [n,8], floats [n,16]) in world-list order; see ref_harness.cpp."""
+        n = lib().ref_world_contact_count(self.h)
+        ints = np.zeros((max(n, 1), 8), np.int32)
+        fl = np.zeros((max(n, 1), 16), np.float32)
+        lib().ref_world_get_contacts(self.h, _p(ints), _p(fl), n)
+        return ints[:n], fl[:n]
+
+    def proxies(self):
+        n = lib().ref_world_proxy_count(self.h)
+        aabbs = np.zeros((max(n, 1), 4), np.float32)
+        ids = np.zeros(max(n, 1), np.int32)
+        lib().ref_world_get_proxies(self.h, _p(aabbs), _p(ids), n)
+        return aabbs[:n], ids[:n]
+
+    def events(self):
+        cap = 1 << 16
+        ints = np.zeros((cap, 6), np.int32)
+        fl = np.zeros((cap, 4), np.float32)
+        n = lib().ref_world_get_events(self.h, _p(ints), _p(fl), cap)
+        return ints[:n], fl[:n]
+
+
+def polygon_build(fd: FixtureDef, verts: np.ndarray):
+    out = np.zeros(38, np.float32)
+    v = np.ascontiguousarray(verts, np.float32)
+    n = lib().ref_polygon_build(C.byref(fd), _p(v), _p(out))
+    return n, out
+
+
+def _collide(fn, a, xa, b, xb):
+    ints = np.zeros(4, np.int32)
+    fl = np.zeros(8, np.float32)
+    a, xa, b, xb = (np.ascontiguousarray(t, np.float32) for t in (a, xa, b, xb))
+    getattr(lib(), fn)(_p(a), _p(xa), _p(b), _p(xb), _p(ints), _p(fl))
+    return ints, fl
+
+
+def collide_polygons(pa, xa, pb, xb):
+    return _collide("ref_collide_polygons", pa, xa, pb, xb)
+
+
+def collide_circles(ca, xa, cb, xb):
+    return _collide("ref_collide_circles", ca, xa, cb, xb)
+
+
+def collide_polygon_circle(pa, xa, cb, xb):
+    return _collide("ref_collide_polygon_circle", pa, xa, cb, xb)
+
+
+def collide_edge_circle(ea, xa, cb, xb):
+    return _collide("ref_collide_edge_circle", ea, xa, cb, xb)
+
+
+def collide_edge_polygon(ea, xa, pb, xb):
+    return _collide("ref_collide_edge_polygon", ea, xa, pb, xb)
+
+
+def sincosf(x: np.ndarray):
+    x = np.ascontiguousarray(x, np.float32)
+    s = np.empty_like(x)
+    c = np.empty_like(x)
+    lib().ref_sincosf(_p(x), _p(s), _p(c), x.size)
+    return s, c
+
+
+def bench_run(scenes, worlds_per_thread, threads, steps, warmup, dt, vel_iters, pos_iters):
+    """All-core CPU baseline.  Returns (seconds, checksum)."""
+    arr = scene_array(scenes)
+    chk = C.c_uint64(0)
+    sec = lib().ref_bench_run(arr, len(scenes), worlds_per_thread, threads, steps, warmup, dt, vel_iters,
+                              pos_iters, C.byref(chk))
+    return sec, chk.value
+
+
+# ---- hashes of SURVEY.md Appendix D -------------------------------------------------------------
+def fnv1a64(data: bytes) -> int:
+    h = 0xCBF29CE484222325
+    for b in data:
+        h ^= b
+        h = (h * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def state_hash(bodies: np.ndarray, skip_first=1) -> int:
+    """FNV-1a over bits of x, y, angle, vx, vy, w per body in creation order, ground excluded."""
+    b = bodies[skip_first:]
+    cols = np.stack([b[:, 0], b[:, 1], b[:, 6], b[:, 7], b[:, 8], b[:, 9]], axis=1).astype("<f4")
+    return fnv1a64(cols.tobytes())
+
+
+def contact_order_hash(ints: np.ndarray, fixture_body: np.ndarray) -> int:
+    """FNV-1a over (body index A, body index B, pointCount) as int32 per contact in world-list order."""
+    rows = np.stack([fixture_body[ints[:, 0]], fixture_body[ints[:, 2]], ints[:, 5]], axis=1).astype("<i4")
+    return fnv1a64(rows.tobytes())
