@@ -11,7 +11,7 @@
  *   b2BodyDef      Box2D/Dynamics/b2Body.h:53-125
  *   b2FixtureDef   Box2D/Dynamics/b2Fixture.h:59-95,  b2Filter :35-57
  *   b2CircleShape / b2EdgeShape / b2PolygonShape / b2ChainShape
- *                  Box2D/Collision/Shapes/*.h
+ *                  Box2D/Collision/Shapes/ (all four headers)
  *   b2World(gravity) + Set* flags   Box2D/Dynamics/b2World.h:48-232
  */
 #ifndef B2G_SCENE_H

@@ -1,6 +1,11 @@
-"""TEST INFRASTRUCTURE — ctypes wrapper over oracle/_ref/libb2ref.so (the reference's own vanilla
-Box2D 2.3.2 compiled by oracle/Makefile; see oracle/ref_harness.cpp).  Only tests/, bench.py's
-cpu_baseline / --impl reference leg and __graft_entry__.smoke() may import this module."""
+"""TEST INFRASTRUCTURE — ctypes wrappers over the two CPU oracles:
+
+  * ``RefWorld``  -> oracle/_ref/libb2ref.so: the reference's own vanilla Box2D 2.3.2, compiled from
+    /root/reference by oracle/Makefile behind oracle/ref_harness.cpp ("reference");
+  * ``PortWorld`` -> oracle/libb2oracle.so: the plain-C restatement in oracle/b2o_*.c ("port").
+
+Both expose the same calls and dump formats.  Only tests/, bench.py's cpu_baseline / --impl reference
+leg and __graft_entry__.smoke() may import this module; the product never does."""
 from __future__ import annotations
 
 import ctypes as C
@@ -12,18 +17,33 @@ from box2dpp_b200.scene import CScene, FixtureDef, Scene, scene_array
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libb2ref.so")
+PORT_SO = os.path.join(_HERE, "libb2oracle.so")
 
-_lib = None
-
-
-def available() -> bool:
-    return os.path.exists(REF_SO)
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(REF_SO)
+def available(kind="ref") -> bool:
+    return os.path.exists(REF_SO if kind == "ref" else PORT_SO)
+
+
+class _Prefixed:
+    """Maps L.ref_xxx to the same-named b2o_xxx symbol of the port library."""
+
+    def __init__(self, cdll, prefix):
+        self._cdll, self._prefix = cdll, prefix
+
+    def __getattr__(self, name):
+        if name.startswith("ref_"):
+            name = self._prefix + name[4:]
+        return getattr(self._cdll, name)
+
+
+def lib(kind="ref"):
+    if kind not in _libs:
+        if kind == "ref":
+            L = C.CDLL(REF_SO)
+        else:
+            L = _Prefixed(C.CDLL(PORT_SO), "b2o_")
         L.ref_world_create.restype = C.c_void_p
         L.ref_world_create.argtypes = [C.POINTER(CScene)]
         L.ref_world_destroy.argtypes = [C.c_void_p]
@@ -44,12 +64,13 @@ def lib():
         for f in ("ref_collide_polygons", "ref_collide_circles", "ref_collide_polygon_circle",
                   "ref_collide_edge_circle", "ref_collide_edge_polygon"):
             getattr(L, f).argtypes = [C.c_void_p] * 6
-        L.ref_sincosf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
-        L.ref_bench_run.restype = C.c_double
-        L.ref_bench_run.argtypes = [C.POINTER(CScene), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                    C.c_int, C.c_int, C.POINTER(C.c_uint64)]
-        _lib = L
-    return _lib
+        if kind == "ref":
+            L.ref_sincosf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+            L.ref_bench_run.restype = C.c_double
+            L.ref_bench_run.argtypes = [C.POINTER(CScene), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                        C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        _libs[kind] = L
+    return _libs[kind]
 
 
 def _p(a):
@@ -57,85 +78,100 @@ def _p(a):
 
 
 class RefWorld:
-    """A vanilla b2World built from a Scene."""
+    """A vanilla b2World built from a Scene (KIND "ref"), or the C restatement (PortWorld, KIND "port")."""
+
+    KIND = "ref"
 
     def __init__(self, scene: Scene, record_events=False):
         self.scene = scene
-        self.h = lib().ref_world_create(C.byref(scene.c_scene()))
+        self.L = lib(self.KIND)
+        self.h = self.L.ref_world_create(C.byref(scene.c_scene()))
         if record_events:
-            lib().ref_world_record_events(self.h, 1)
+            self.L.ref_world_record_events(self.h, 1)
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().ref_world_destroy(self.h)
+            self.L.ref_world_destroy(self.h)
             self.h = None
 
     def step(self, dt, vel_iters, pos_iters):
-        lib().ref_world_step(self.h, dt, vel_iters, pos_iters)
+        self.L.ref_world_step(self.h, dt, vel_iters, pos_iters)
 
     def bodies(self) -> np.ndarray:
         """[nb,16] float32: xf.p(2) q.s q.c | c(2) a | v(2) w | awake mass I localCenter(2) pad."""
-        nb = lib().ref_world_body_count(self.h)
+        nb = self.L.ref_world_body_count(self.h)
         out = np.zeros((nb, 16), np.float32)
-        lib().ref_world_get_bodies(self.h, _p(out))
+        self.L.ref_world_get_bodies(self.h, _p(out))
         return out
 
     def contacts(self):
         """(ints [n,8], floats [n,16]) in world-list order; see ref_harness.cpp."""
-        n = lib().ref_world_contact_count(self.h)
+        n = self.L.ref_world_contact_count(self.h)
         ints = np.zeros((max(n, 1), 8), np.int32)
         fl = np.zeros((max(n, 1), 16), np.float32)
-        lib().ref_world_get_contacts(self.h, _p(ints), _p(fl), n)
+        self.L.ref_world_get_contacts(self.h, _p(ints), _p(fl), n)
         return ints[:n], fl[:n]
 
     def proxies(self):
-        n = lib().ref_world_proxy_count(self.h)
+        n = self.L.ref_world_proxy_count(self.h)
         aabbs = np.zeros((max(n, 1), 4), np.float32)
         ids = np.zeros(max(n, 1), np.int32)
-        lib().ref_world_get_proxies(self.h, _p(aabbs), _p(ids), n)
+        self.L.ref_world_get_proxies(self.h, _p(aabbs), _p(ids), n)
         return aabbs[:n], ids[:n]
 
     def events(self):
         cap = 1 << 16
         ints = np.zeros((cap, 6), np.int32)
         fl = np.zeros((cap, 4), np.float32)
-        n = lib().ref_world_get_events(self.h, _p(ints), _p(fl), cap)
+        n = self.L.ref_world_get_events(self.h, _p(ints), _p(fl), cap)
         return ints[:n], fl[:n]
 
 
-def polygon_build(fd: FixtureDef, verts: np.ndarray):
+class PortWorld(RefWorld):
+    KIND = "port"
+
+    def islands(self):
+        """(island count, body order over all islands, contact count) of the last step."""
+        nb = self.L.ref_world_body_count(self.h)
+        bodies = np.zeros(4 * (nb + 1), np.int32)
+        counts = np.zeros(3, np.int32)
+        n = self.L.ref_world_get_islands(self.h, _p(bodies), bodies.size, _p(counts))
+        return int(counts[0]), bodies[:n].copy(), int(counts[2])
+
+
+def polygon_build(fd: FixtureDef, verts: np.ndarray, kind="ref"):
     out = np.zeros(38, np.float32)
     v = np.ascontiguousarray(verts, np.float32)
-    n = lib().ref_polygon_build(C.byref(fd), _p(v), _p(out))
+    n = lib(kind).ref_polygon_build(C.byref(fd), _p(v), _p(out))
     return n, out
 
 
-def _collide(fn, a, xa, b, xb):
+def _collide(fn, a, xa, b, xb, kind="ref"):
     ints = np.zeros(4, np.int32)
     fl = np.zeros(8, np.float32)
     a, xa, b, xb = (np.ascontiguousarray(t, np.float32) for t in (a, xa, b, xb))
-    getattr(lib(), fn)(_p(a), _p(xa), _p(b), _p(xb), _p(ints), _p(fl))
+    getattr(lib(kind), fn)(_p(a), _p(xa), _p(b), _p(xb), _p(ints), _p(fl))
     return ints, fl
 
 
-def collide_polygons(pa, xa, pb, xb):
-    return _collide("ref_collide_polygons", pa, xa, pb, xb)
+def collide_polygons(pa, xa, pb, xb, kind="ref"):
+    return _collide("ref_collide_polygons", pa, xa, pb, xb, kind)
 
 
-def collide_circles(ca, xa, cb, xb):
-    return _collide("ref_collide_circles", ca, xa, cb, xb)
+def collide_circles(ca, xa, cb, xb, kind="ref"):
+    return _collide("ref_collide_circles", ca, xa, cb, xb, kind)
 
 
-def collide_polygon_circle(pa, xa, cb, xb):
-    return _collide("ref_collide_polygon_circle", pa, xa, cb, xb)
+def collide_polygon_circle(pa, xa, cb, xb, kind="ref"):
+    return _collide("ref_collide_polygon_circle", pa, xa, cb, xb, kind)
 
 
-def collide_edge_circle(ea, xa, cb, xb):
-    return _collide("ref_collide_edge_circle", ea, xa, cb, xb)
+def collide_edge_circle(ea, xa, cb, xb, kind="ref"):
+    return _collide("ref_collide_edge_circle", ea, xa, cb, xb, kind)
 
 
-def collide_edge_polygon(ea, xa, pb, xb):
-    return _collide("ref_collide_edge_polygon", ea, xa, pb, xb)
+def collide_edge_polygon(ea, xa, pb, xb, kind="ref"):
+    return _collide("ref_collide_edge_polygon", ea, xa, pb, xb, kind)
 
 
 def sincosf(x: np.ndarray):
