@@ -1,0 +1,247 @@
+"""ctypes binding of libb2gpu.so (include/b2gpu.h) for tests and bench.py.
+
+``WorldBatch`` is the Python face of the C++ ``b2WorldBatch``: a batch of independent worlds built from
+``Scene`` descriptions (the reference's CreateBody / CreateFixture calls) and stepped on one B200 by
+``b2gpu_batch_step`` — the replacement of ``b2World::Step`` (Box2D/Dynamics/b2World.cpp:888-954).
+There is no CPU fallback: construction raises if the CUDA library is missing or no device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .scene import CScene, FixtureDef, Scene, scene_array
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2gpu.so")
+
+# field ids — keep in sync with include/b2gpu.h
+(F_GRAVITY, F_WORLD_FLAGS, F_INV_DT0, F_BODY_COUNT, F_PROXY_COUNT, F_CONTACT_COUNT, F_STATUS, F_EVENT_COUNT,
+ F_ISLAND_COUNT, F_STEP_COUNT, F_BODY_XF, F_BODY_SWEEP, F_BODY_SWEEP0, F_BODY_VEL, F_BODY_FORCE, F_BODY_MASS,
+ F_BODY_DAMP, F_BODY_FLAGS, F_FIXTURE_INFO, F_FIXTURE_SHAPE, F_FIXTURE_MAT, F_FIXTURE_FILTER, F_PROXY_FAT,
+ F_PROXY_INFO, F_PROXY_MOVED, F_SHAPE_WORDS, F_CHAIN_VERTS, F_CONTACT_A, F_CONTACT_K, F_CONTACT_S, F_CONTACT_P0,
+ F_CONTACT_P1, F_CONTACT_N, F_EVENT_A, F_EVENT_B, F_ISLAND_CONTACTS, F_ISLAND_CONTACT_END, F_COUNT) = range(38)
+
+INT_FIELDS = {F_WORLD_FLAGS, F_BODY_COUNT, F_PROXY_COUNT, F_CONTACT_COUNT, F_STATUS, F_EVENT_COUNT, F_ISLAND_COUNT,
+              F_STEP_COUNT, F_BODY_FLAGS, F_FIXTURE_INFO, F_FIXTURE_SHAPE, F_FIXTURE_FILTER, F_PROXY_INFO,
+              F_PROXY_MOVED, F_CONTACT_A, F_CONTACT_K, F_CONTACT_S, F_EVENT_A, F_ISLAND_CONTACTS,
+              F_ISLAND_CONTACT_END}
+
+EVENT_BEGIN, EVENT_END, EVENT_PRESOLVE, EVENT_POSTSOLVE = 0, 1, 2, 3
+EVENT_ALL = 15
+
+EXPORTED_SYMBOLS = [
+    "b2gpu_batch_create", "b2gpu_batch_destroy", "b2gpu_batch_upload_field", "b2gpu_batch_download_field",
+    "b2gpu_batch_field_shape", "b2gpu_batch_step", "b2gpu_batch_step_n", "b2gpu_batch_sync",
+    "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_last_step_ms",
+    "b2gpu_batch_profile_steps", "b2gpu_batch_launch_count", "b2gpu_last_error", "b2gpu_scene_capacities",
+    "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build",
+]
+
+
+class BatchDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "device", "numWorlds", "maxBodies", "maxFixtures", "maxProxies", "maxContacts", "maxShapeWords",
+        "maxChainVerts", "maxEvents", "eventMask", "blockSize", "reserved")]
+
+
+class B2GpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libb2gpu.so.  Raises (never falls back) when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2GpuError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                             "box2dpp_b200 has no CPU path")
+        L = C.CDLL(LIB_PATH)
+        vp, i32 = C.c_void_p, C.c_int32
+        L.b2gpu_batch_create.argtypes = [C.POINTER(BatchDesc), C.POINTER(vp)]
+        L.b2gpu_batch_destroy.argtypes = [vp]
+        L.b2gpu_batch_upload_field.argtypes = [vp, i32, vp, i32, i32]
+        L.b2gpu_batch_download_field.argtypes = [vp, i32, vp, i32, i32]
+        L.b2gpu_batch_field_shape.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.b2gpu_batch_step.argtypes = [vp, C.c_float, i32, i32]
+        L.b2gpu_batch_step_n.argtypes = [vp, C.c_float, i32, i32, i32]
+        L.b2gpu_batch_sync.argtypes = [vp]
+        L.b2gpu_batch_apply_forces.argtypes = [vp, vp]
+        L.b2gpu_batch_read_transforms.argtypes = [vp, vp]
+        L.b2gpu_batch_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b2gpu_batch_profile_steps.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
+        L.b2gpu_batch_launch_count.argtypes = [vp]
+        L.b2gpu_batch_launch_count.restype = C.c_int64
+        L.b2gpu_last_error.restype = C.c_char_p
+        L.b2gpu_scene_capacities.argtypes = [C.POINTER(CScene), i32, C.POINTER(BatchDesc)]
+        L.b2gpu_batch_build_worlds.argtypes = [vp, C.POINTER(CScene), i32, i32, i32]
+        L.b2gpu_host_polygon_build.argtypes = [C.POINTER(FixtureDef), vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise B2GpuError(f"b2gpu error {rc}: {lib().b2gpu_last_error().decode()}")
+
+
+def host_polygon_build(fd: FixtureDef, verts):
+    v = np.ascontiguousarray(verts, np.float32)
+    out = np.zeros(38, np.float32)
+    n = lib().b2gpu_host_polygon_build(C.byref(fd), v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return n, out
+
+
+class WorldBatch:
+    """A batch of independent worlds on one GPU."""
+
+    def __init__(self, scenes, replicate=1, device=0, max_contacts=0, max_events=0, event_mask=0, block_size=0):
+        if isinstance(scenes, Scene):
+            scenes = [scenes]
+        self.scenes = list(scenes)
+        self.num_worlds = len(self.scenes) * replicate
+        L = lib()
+        arr = scene_array(self.scenes)
+        d = BatchDesc()
+        d.device, d.numWorlds = device, self.num_worlds
+        d.maxContacts, d.maxEvents, d.eventMask, d.blockSize = max_contacts, max_events, event_mask, block_size
+        _check(L.b2gpu_scene_capacities(arr, len(self.scenes), C.byref(d)))
+        self.desc = d
+        self.h = C.c_void_p()
+        _check(L.b2gpu_batch_create(C.byref(d), C.byref(self.h)))
+        _check(L.b2gpu_batch_build_worlds(self.h, arr, len(self.scenes), 0, replicate))
+        self.max_bodies = d.maxBodies
+        self._pinned = {}
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            lib().b2gpu_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- b2World::Step ----
+    def step(self, dt, vel_iters, pos_iters):
+        _check(lib().b2gpu_batch_step(self.h, dt, vel_iters, pos_iters))
+
+    def step_n(self, dt, vel_iters, pos_iters, steps):
+        _check(lib().b2gpu_batch_step_n(self.h, dt, vel_iters, pos_iters, steps))
+
+    def sync(self):
+        _check(lib().b2gpu_batch_sync(self.h))
+
+    def last_step_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().b2gpu_batch_last_step_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_steps(self, dt, vel_iters, pos_iters, steps):
+        ms = (C.c_float * 4)()
+        _check(lib().b2gpu_batch_profile_steps(self.h, dt, vel_iters, pos_iters, steps, ms))
+        return dict(zip(("collide", "islands", "solve", "sync_pairs"), [float(x) for x in ms]))
+
+    def launch_count(self) -> int:
+        return int(lib().b2gpu_batch_launch_count(self.h))
+
+    # ---- fields ----
+    def field_shape(self, fid):
+        cap, comps = C.c_int32(), C.c_int32()
+        _check(lib().b2gpu_batch_field_shape(self.h, fid, C.byref(cap), C.byref(comps)))
+        return cap.value, comps.value
+
+    def field(self, fid, first=0, count=None) -> np.ndarray:
+        count = self.num_worlds - first if count is None else count
+        cap, comps = self.field_shape(fid)
+        out = np.zeros((count, cap, comps), np.int32 if fid in INT_FIELDS else np.float32)
+        _check(lib().b2gpu_batch_download_field(self.h, fid, out.ctypes.data_as(C.c_void_p), first, count))
+        return out
+
+    def set_field(self, fid, values, first=0):
+        cap, comps = self.field_shape(fid)
+        v = np.ascontiguousarray(values, np.int32 if fid in INT_FIELDS else np.float32).reshape(-1, cap, comps)
+        _check(lib().b2gpu_batch_upload_field(self.h, fid, v.ctypes.data_as(C.c_void_p), first, v.shape[0]))
+
+    # ---- per-step I/O ----
+    def apply_forces(self, forces: np.ndarray):
+        f = np.ascontiguousarray(forces, np.float32)
+        assert f.size == self.num_worlds * self.max_bodies * 3
+        _check(lib().b2gpu_batch_apply_forces(self.h, f.ctypes.data_as(C.c_void_p)))
+
+    def read_transforms(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.num_worlds, self.max_bodies, 4), np.float32)
+        _check(lib().b2gpu_batch_read_transforms(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # ---- dumps in the oracle's formats (oracle/ref_harness.cpp) for parity tests ----
+    def bodies(self, world) -> np.ndarray:
+        nb = int(self.field(F_BODY_COUNT, world, 1)[0, 0, 0])
+        xf = self.field(F_BODY_XF, world, 1)[0, :nb]
+        sw = self.field(F_BODY_SWEEP, world, 1)[0, :nb]
+        ve = self.field(F_BODY_VEL, world, 1)[0, :nb]
+        ms = self.field(F_BODY_MASS, world, 1)[0, :nb]
+        fl = self.field(F_BODY_FLAGS, world, 1)[0, :nb, 0]
+        out = np.zeros((nb, 16), np.float32)
+        out[:, 0:4] = xf
+        out[:, 4:7] = sw[:, 0:3]
+        out[:, 7:10] = ve[:, 0:3]
+        out[:, 10] = ((fl & 8) != 0).astype(np.float32)
+        with np.errstate(divide="ignore"):
+            out[:, 11] = np.where(ms[:, 0] > 0, np.float32(1.0) / ms[:, 0], 0.0)
+        out[:, 13:15] = ms[:, 2:4]
+        return out
+
+    def contacts(self, world):
+        n = int(self.field(F_CONTACT_COUNT, world, 1)[0, 0, 0])
+        A = self.field(F_CONTACT_A, world, 1)[0, :n][::-1]
+        K = self.field(F_CONTACT_K, world, 1)[0, :n][::-1]
+        P0 = self.field(F_CONTACT_P0, world, 1)[0, :n][::-1]
+        P1 = self.field(F_CONTACT_P1, world, 1)[0, :n][::-1]
+        N = self.field(F_CONTACT_N, world, 1)[0, :n][::-1]
+        pinfo = self.field(F_PROXY_INFO, world, 1)[0, :, 0]
+        ints = np.zeros((n, 8), np.int32)
+        fl = np.zeros((n, 16), np.float32)
+        pa, pb = A[:, 0] & 0xFFFF, (A[:, 0] >> 16) & 0xFFFF
+        ints[:, 0], ints[:, 1] = pinfo[pa] & 0xFFFF, (pinfo[pa] >> 16) & 0xFFFF
+        ints[:, 2], ints[:, 3] = pinfo[pb] & 0xFFFF, (pinfo[pb] >> 16) & 0xFFFF
+        flags = A[:, 2]
+        ints[:, 4] = ((flags & 2) != 0) * 1 + ((flags & 4) != 0) * 2
+        pc = (A[:, 3] >> 8) & 0xFF
+        ints[:, 5] = pc
+        ints[:, 6] = np.where(pc > 0, K[:, 0], 0)
+        ints[:, 7] = np.where(pc > 1, K[:, 1], 0)
+        has = pc > 0
+        fl[:, 0:4] = np.where(has[:, None], N, 0)
+        fl[:, 4] = np.where(has, (A[:, 3] & 0xFF).astype(np.float32), 0)
+        fl[:, 5:9] = np.where(has[:, None], P0, 0)
+        fl[:, 9:13] = np.where((pc > 1)[:, None], P1, 0)
+        fl[:, 13] = K[:, 2].view(np.float32)
+        fl[:, 14] = K[:, 3].view(np.float32)
+        return ints, fl
+
+    def proxies(self, world):
+        n = int(self.field(F_PROXY_COUNT, world, 1)[0, 0, 0])
+        return self.field(F_PROXY_FAT, world, 1)[0, :n]
+
+    def events(self, world):
+        n = int(self.field(F_EVENT_COUNT, world, 1)[0, 0, 0])
+        A = self.field(F_EVENT_A, world, 1)[0, :n]
+        B = self.field(F_EVENT_B, world, 1)[0, :n]
+        ints = np.zeros((n, 6), np.int32)
+        ints[:, 0] = A[:, 0]
+        ints[:, 1], ints[:, 2] = A[:, 1] & 0xFFFF, (A[:, 1] >> 16) & 0xFFFF
+        ints[:, 3], ints[:, 4] = A[:, 2] & 0xFFFF, (A[:, 2] >> 16) & 0xFFFF
+        ints[:, 5] = A[:, 3]
+        return ints, B.copy()
+
+    def status(self):
+        return self.field(F_STATUS)[:, 0, 0]

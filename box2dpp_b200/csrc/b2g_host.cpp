@@ -1,0 +1,596 @@
+// b2g_host.cpp — host layer of libb2gpu.so: turns the user's CreateBody / CreateFixture calls
+// (b2g_scene, include/b2g_scene.h) into world-major arena fields and uploads them through the
+// device-layer C ABI (b2gpu_batch_upload_field).  Everything the reference computes at scene-construction
+// time is computed here with the same float32 expression order:
+//   b2Body::b2Body                 Box2D/Dynamics/b2Body.cpp:27-108
+//   b2Body::CreateFixture          Box2D/Dynamics/b2Body.cpp:168-214
+//   b2Body::ResetMassData          Box2D/Dynamics/b2Body.cpp:283-352
+//   b2Fixture::Create/CreateProxies Box2D/Dynamics/b2Fixture.cpp:43-69, 124-139
+//   b2DynamicTree::CreateProxy     Box2D/Collision/b2DynamicTree.cpp:112-126 (fat AABB, node ids)
+//   b2PolygonShape::Set/SetAsBox/ComputeMass/ComputeAABB  Box2D/Collision/Shapes/b2PolygonShape.cpp
+//   b2CircleShape / b2EdgeShape / b2ChainShape ComputeMass/ComputeAABB
+// Compiled with g++ -O2 -ffp-contract=off (no FMA contraction), never -ffast-math.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b2gpu.h"
+#include "b2g_layout.h"
+#include "b2g_math.cuh"
+
+using namespace b2g;
+
+extern "C" int b2gpu_host_set_error(int code, const char* msg);  // defined below; shares b2gpu_last_error()
+
+namespace {
+
+struct HostShape {
+    int type = 0;
+    float radius = 0.0f;
+    int count = 0;
+    Vec2 verts[kMaxPolygonVertices], normals[kMaxPolygonVertices], centroid;
+    Vec2 p;                    // circle
+    Vec2 v0, v1, v2, v3;       // edge
+    bool has0 = false, has3 = false;
+    std::vector<Vec2> chain;   // chain
+    Vec2 prev, next;
+    bool hasPrev = false, hasNext = false;
+};
+
+// b2PolygonShape::SetAsBox(hx, hy)
+void SetAsBox(HostShape& s, float hx, float hy) {
+    s.type = B2G_SHAPE_POLYGON;
+    s.radius = kPolygonRadius;
+    s.count = 4;
+    s.verts[0] = V2(-hx, -hy);
+    s.verts[1] = V2(hx, -hy);
+    s.verts[2] = V2(hx, hy);
+    s.verts[3] = V2(-hx, hy);
+    s.normals[0] = V2(0.0f, -1.0f);
+    s.normals[1] = V2(1.0f, 0.0f);
+    s.normals[2] = V2(0.0f, 1.0f);
+    s.normals[3] = V2(-1.0f, 0.0f);
+    s.centroid = V2(0.0f, 0.0f);
+}
+
+// b2PolygonShape::SetAsBox(hx, hy, center, angle)
+void SetAsBox(HostShape& s, float hx, float hy, Vec2 center, float angle) {
+    SetAsBox(s, hx, hy);
+    s.centroid = center;
+    Xf xf;
+    xf.p = center;
+    xf.q = MakeRot(angle);
+    for (int i = 0; i < s.count; ++i) {
+        s.verts[i] = Mul(xf, s.verts[i]);
+        s.normals[i] = Mul(xf.q, s.normals[i]);
+    }
+}
+
+// ComputeCentroid (b2PolygonShape.cpp:73-121)
+Vec2 ComputeCentroid(const Vec2* vs, int count) {
+    Vec2 c = V2(0.0f, 0.0f);
+    float area = 0.0f;
+    Vec2 pRef = V2(0.0f, 0.0f);
+    const float inv3 = 1.0f / 3.0f;
+    for (int i = 0; i < count; ++i) {
+        Vec2 p1 = pRef, p2 = vs[i], p3 = i + 1 < count ? vs[i + 1] : vs[0];
+        Vec2 e1 = p2 - p1, e2 = p3 - p1;
+        float D = Cross(e1, e2);
+        float triangleArea = 0.5f * D;
+        area += triangleArea;
+        c = c + (triangleArea * inv3) * (p1 + p2 + p3);
+    }
+    c = (1.0f / area) * c;
+    return c;
+}
+
+// b2PolygonShape::Set: weld, gift-wrap hull, normals, centroid
+void SetPolygon(HostShape& s, const Vec2* vertices, int count) {
+    s.type = B2G_SHAPE_POLYGON;
+    s.radius = kPolygonRadius;
+    if (count < 3) { SetAsBox(s, 1.0f, 1.0f); return; }
+    int n = count < kMaxPolygonVertices ? count : kMaxPolygonVertices;
+    Vec2 ps[kMaxPolygonVertices];
+    int tempCount = 0;
+    for (int i = 0; i < n; ++i) {
+        Vec2 v = vertices[i];
+        bool unique = true;
+        for (int j = 0; j < tempCount; ++j) {
+            if (DistanceSquared(v, ps[j]) < 0.5f * kLinearSlop) { unique = false; break; }
+        }
+        if (unique) ps[tempCount++] = v;
+    }
+    n = tempCount;
+    if (n < 3) { SetAsBox(s, 1.0f, 1.0f); return; }
+    int i0 = 0;
+    float x0 = ps[0].x;
+    for (int i = 1; i < n; ++i) {
+        float x = ps[i].x;
+        if (x > x0 || (x == x0 && ps[i].y < ps[i0].y)) { i0 = i; x0 = x; }
+    }
+    int hull[kMaxPolygonVertices];
+    int m = 0, ih = i0;
+    for (;;) {
+        hull[m] = ih;
+        int ie = 0;
+        for (int j = 1; j < n; ++j) {
+            if (ie == ih) { ie = j; continue; }
+            Vec2 r = ps[ie] - ps[hull[m]];
+            Vec2 v = ps[j] - ps[hull[m]];
+            float c = Cross(r, v);
+            if (c < 0.0f) ie = j;
+            if (c == 0.0f && LengthSquared(v) > LengthSquared(r)) ie = j;
+        }
+        ++m;
+        ih = ie;
+        if (ie == i0) break;
+    }
+    if (m < 3) { SetAsBox(s, 1.0f, 1.0f); return; }
+    s.count = m;
+    for (int i = 0; i < m; ++i) s.verts[i] = ps[hull[i]];
+    for (int i = 0; i < m; ++i) {
+        int i2 = i + 1 < m ? i + 1 : 0;
+        Vec2 edge = s.verts[i2] - s.verts[i];
+        s.normals[i] = Cross(edge, 1.0f);
+        Normalize(s.normals[i]);
+    }
+    s.centroid = ComputeCentroid(s.verts, m);
+}
+
+struct MassData {
+    float mass;
+    Vec2 center;
+    float I;
+};
+
+// b2*Shape::ComputeMass
+MassData ComputeMass(const HostShape& s, float density) {
+    MassData md;
+    if (s.type == B2G_SHAPE_POLYGON) {
+        Vec2 center = V2(0.0f, 0.0f);
+        float area = 0.0f, I = 0.0f;
+        Vec2 sref = V2(0.0f, 0.0f);
+        for (int i = 0; i < s.count; ++i) sref = sref + s.verts[i];
+        sref = (1.0f / s.count) * sref;
+        const float k_inv3 = 1.0f / 3.0f;
+        for (int i = 0; i < s.count; ++i) {
+            Vec2 e1 = s.verts[i] - sref;
+            Vec2 e2 = i + 1 < s.count ? s.verts[i + 1] - sref : s.verts[0] - sref;
+            float D = Cross(e1, e2);
+            float triangleArea = 0.5f * D;
+            area += triangleArea;
+            center = center + (triangleArea * k_inv3) * (e1 + e2);
+            float ex1 = e1.x, ey1 = e1.y, ex2 = e2.x, ey2 = e2.y;
+            float intx2 = ex1 * ex1 + ex2 * ex1 + ex2 * ex2;
+            float inty2 = ey1 * ey1 + ey2 * ey1 + ey2 * ey2;
+            I += (0.25f * k_inv3 * D) * (intx2 + inty2);
+        }
+        md.mass = density * area;
+        center = (1.0f / area) * center;
+        md.center = center + sref;
+        md.I = density * I;
+        md.I += md.mass * (Dot(md.center, md.center) - Dot(center, center));
+    } else if (s.type == B2G_SHAPE_CIRCLE) {
+        md.mass = density * kPi * s.radius * s.radius;
+        md.center = s.p;
+        md.I = md.mass * (0.5f * s.radius * s.radius + Dot(s.p, s.p));
+    } else if (s.type == B2G_SHAPE_EDGE) {
+        md.mass = 0.0f;
+        md.center = 0.5f * (s.v1 + s.v2);
+        md.I = 0.0f;
+    } else {
+        md.mass = 0.0f;
+        md.center = V2(0.0f, 0.0f);
+        md.I = 0.0f;
+    }
+    return md;
+}
+
+// b2*Shape::ComputeAABB
+void ComputeAABB(const HostShape& s, Xf xf, int child, Vec2* lo, Vec2* hi) {
+    if (s.type == B2G_SHAPE_POLYGON) {
+        Vec2 lower = Mul(xf, s.verts[0]);
+        Vec2 upper = lower;
+        for (int i = 1; i < s.count; ++i) {
+            Vec2 v = Mul(xf, s.verts[i]);
+            lower = Min(lower, v);
+            upper = Max(upper, v);
+        }
+        Vec2 r = V2(s.radius, s.radius);
+        *lo = lower - r;
+        *hi = upper + r;
+    } else if (s.type == B2G_SHAPE_CIRCLE) {
+        Vec2 p = xf.p + Mul(xf.q, s.p);
+        *lo = V2(p.x - s.radius, p.y - s.radius);
+        *hi = V2(p.x + s.radius, p.y + s.radius);
+    } else if (s.type == B2G_SHAPE_EDGE) {
+        Vec2 a = Mul(xf, s.v1), b = Mul(xf, s.v2);
+        Vec2 r = V2(s.radius, s.radius);
+        *lo = Min(a, b) - r;
+        *hi = Max(a, b) + r;
+    } else {
+        int i1 = child, i2 = child + 1;
+        if (i2 == (int)s.chain.size()) i2 = 0;
+        Vec2 a = Mul(xf, s.chain[i1]), b = Mul(xf, s.chain[i2]);
+        *lo = Min(a, b);
+        *hi = Max(a, b);
+    }
+}
+
+int BuildShape(HostShape& sh, const b2g_fixture_def& d, const float* V) {
+    switch (d.shapeType) {
+        case B2G_SHAPE_CIRCLE:
+            sh.type = B2G_SHAPE_CIRCLE;
+            sh.radius = d.radius;
+            sh.p = V2(d.p[0], d.p[1]);
+            return 1;
+        case B2G_SHAPE_EDGE:
+            sh.type = B2G_SHAPE_EDGE;
+            sh.radius = kPolygonRadius;
+            sh.v1 = V2(V[2 * d.firstVertex], V[2 * d.firstVertex + 1]);
+            sh.v2 = V2(V[2 * d.firstVertex + 2], V[2 * d.firstVertex + 3]);
+            sh.has0 = d.hasVertex0 != 0;
+            sh.has3 = d.hasVertex3 != 0;
+            sh.v0 = V2(d.vertex0[0], d.vertex0[1]);
+            sh.v3 = V2(d.vertex3[0], d.vertex3[1]);
+            return 1;
+        case B2G_SHAPE_POLYGON:
+            if (d.shapeKind == B2G_POLY_BOX) SetAsBox(sh, d.p[0], d.p[1]);
+            else if (d.shapeKind == B2G_POLY_BOX_OFFSET) SetAsBox(sh, d.p[0], d.p[1], V2(d.center[0], d.center[1]), d.angle);
+            else {
+                Vec2 pts[kMaxPolygonVertices];
+                int n = d.vertexCount < kMaxPolygonVertices ? d.vertexCount : kMaxPolygonVertices;
+                for (int k = 0; k < n; ++k) pts[k] = V2(V[2 * (d.firstVertex + k)], V[2 * (d.firstVertex + k) + 1]);
+                SetPolygon(sh, pts, n);
+            }
+            return 1;
+        case B2G_SHAPE_CHAIN: {
+            sh.type = B2G_SHAPE_CHAIN;
+            sh.radius = kPolygonRadius;
+            for (int k = 0; k < d.vertexCount; ++k) sh.chain.push_back(V2(V[2 * (d.firstVertex + k)], V[2 * (d.firstVertex + k) + 1]));
+            if (d.shapeKind == B2G_CHAIN_LOOP) {  // b2ChainShape::CreateLoop
+                sh.chain.push_back(sh.chain[0]);
+                sh.prev = sh.chain[sh.chain.size() - 2];
+                sh.next = sh.chain[1];
+                sh.hasPrev = sh.hasNext = true;
+            } else {
+                sh.hasPrev = d.hasVertex0 != 0;
+                sh.hasNext = d.hasVertex3 != 0;
+                sh.prev = V2(d.vertex0[0], d.vertex0[1]);
+                sh.next = V2(d.vertex3[0], d.vertex3[1]);
+            }
+            return (int)sh.chain.size() - 1;
+        }
+    }
+    return 0;
+}
+
+inline float IntBits(int v) { float f; memcpy(&f, &v, 4); return f; }
+
+// One world flattened into world-major field arrays of capacity-sized rows.
+struct FlatWorld {
+    std::vector<std::vector<uint32_t>> f;  // per field id, capacity * components words
+};
+
+struct Caps {
+    int NB, NF, NP, NC, NS, NV, NE;
+};
+
+// Shape-table words of one shape (layout in b2g_layout.h).  Chains reference chainVerts at chainOffset.
+std::vector<uint32_t> ShapeWords(const HostShape& sh, int chainOffset) {
+    std::vector<uint32_t> words;
+    auto pushf = [&](float v) { uint32_t u; memcpy(&u, &v, 4); words.push_back(u); };
+    auto pushi = [&](int v) { words.push_back((uint32_t)v); };
+    if (sh.type == B2G_SHAPE_POLYGON) {
+        pushi(sh.count); pushf(sh.radius); pushf(sh.centroid.x); pushf(sh.centroid.y);
+        for (int k = 0; k < sh.count; ++k) { pushf(sh.verts[k].x); pushf(sh.verts[k].y); }
+        for (int k = 0; k < sh.count; ++k) { pushf(sh.normals[k].x); pushf(sh.normals[k].y); }
+    } else if (sh.type == B2G_SHAPE_CIRCLE) {
+        pushf(sh.radius); pushf(sh.p.x); pushf(sh.p.y);
+    } else if (sh.type == B2G_SHAPE_EDGE) {
+        pushf(sh.radius);
+        pushf(sh.v0.x); pushf(sh.v0.y); pushf(sh.v1.x); pushf(sh.v1.y);
+        pushf(sh.v2.x); pushf(sh.v2.y); pushf(sh.v3.x); pushf(sh.v3.y);
+        pushi((sh.has0 ? 1 : 0) | (sh.has3 ? 2 : 0));
+    } else {
+        pushf(sh.radius); pushi(chainOffset); pushi((int)sh.chain.size());
+        pushf(sh.prev.x); pushf(sh.prev.y); pushf(sh.next.x); pushf(sh.next.y);
+        pushi((sh.hasPrev ? 1 : 0) | (sh.hasNext ? 2 : 0));
+    }
+    return words;
+}
+
+// Exact per-world sizes: bodies, fixtures, proxies, shape-table words after deduplication, chain vertices.
+void CountScene(const b2g_scene& s, int* nb, int* nf, int* np, int* ns, int* nv) {
+    *nb = s.bodyCount;
+    *nf = s.fixtureCount;
+    int proxies = 0, words = 0, verts = 0;
+    std::map<std::vector<uint32_t>, int> dedup;
+    for (int i = 0; i < s.fixtureCount; ++i) {
+        HostShape sh;
+        int children = BuildShape(sh, s.fixtures[i], s.vertices);
+        bool active = s.fixtures[i].body >= 0 && s.fixtures[i].body < s.bodyCount &&
+                      (s.bodies[s.fixtures[i].body].flags & B2G_BD_ACTIVE) != 0;
+        if (active) proxies += children;
+        std::vector<uint32_t> w = ShapeWords(sh, verts);
+        if (dedup.find(w) == dedup.end()) {
+            dedup[w] = words;
+            words += (int)w.size();
+        }
+        verts += (int)sh.chain.size();
+    }
+    *np = proxies; *ns = words; *nv = verts;
+}
+
+template <class T>
+void put(std::vector<uint32_t>& dst, size_t wordIndex, T v) {
+    static_assert(sizeof(T) == 4, "32-bit fields only");
+    memcpy(&dst[wordIndex], &v, 4);
+}
+
+int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int, int>>& shapes /*cap, comps per field*/,
+            FlatWorld& out, std::string& err) {
+    if (s.worldFlags & B2G_WORLD_CONTINUOUS) {
+        err = "continuous physics (TOI) is not on the device path: build the world with SetContinuousPhysics(false)";
+        return B2GPU_ERR_UNSUPPORTED;
+    }
+    int nb, nf, np, ns, nv;
+    CountScene(s, &nb, &nf, &np, &ns, &nv);
+    if (nb > cap.NB || nf > cap.NF || np > cap.NP || nv > cap.NV || ns > cap.NS) {
+        err = "scene exceeds the batch capacities (bodies/fixtures/proxies/chain vertices)";
+        return B2GPU_ERR_CAPACITY;
+    }
+    out.f.assign(B2GPU_F_COUNT, {});
+    for (int id = 0; id < B2GPU_F_COUNT; ++id) out.f[id].assign((size_t)shapes[id].first * shapes[id].second, 0u);
+
+    struct HBody {
+        int type, flags;
+        Xf xf;
+        Vec2 localCenter, c0, c;
+        float a0, a;
+        Vec2 v;
+        float w;
+        float mass, invMass, I, invI;
+    };
+    std::vector<HBody> bodies(nb);
+    for (int i = 0; i < nb; ++i) {
+        const b2g_body_def& d = s.bodies[i];
+        HBody& b = bodies[i];
+        b.type = d.type;
+        b.flags = d.type & kBodyTypeMask;
+        if (d.flags & B2G_BD_BULLET) b.flags |= kBodyBullet;
+        if (d.flags & B2G_BD_FIXED_ROTATION) b.flags |= kBodyFixedRotation;
+        if (d.flags & B2G_BD_ALLOW_SLEEP) b.flags |= kBodyAutoSleep;
+        if (d.flags & B2G_BD_AWAKE) b.flags |= kBodyAwake;
+        if (d.flags & B2G_BD_ACTIVE) b.flags |= kBodyActive;
+        b.xf.p = V2(d.position[0], d.position[1]);
+        b.xf.q = MakeRot(d.angle);
+        b.localCenter = V2(0.0f, 0.0f);
+        b.c0 = b.c = b.xf.p;
+        b.a0 = b.a = d.angle;
+        b.v = V2(d.linearVelocity[0], d.linearVelocity[1]);
+        b.w = d.angularVelocity;
+        b.mass = b.invMass = d.type == B2G_DYNAMIC_BODY ? 1.0f : 0.0f;
+        b.I = b.invI = 0.0f;
+    }
+
+    std::vector<HostShape> fshapes(nf);
+    std::map<std::vector<uint32_t>, int> shapeDedup;
+    int shapeWordsUsed = 0, chainUsed = 0, proxyCount = 0;
+    auto& SW = out.f[B2GPU_F_SHAPE_WORDS];
+    auto& CV = out.f[B2GPU_F_CHAIN_VERTS];
+    for (int i = 0; i < nf; ++i) {
+        const b2g_fixture_def& d = s.fixtures[i];
+        if (d.isSensor) { err = "sensor fixtures are not on the device path"; return B2GPU_ERR_UNSUPPORTED; }
+        if (d.body < 0 || d.body >= nb) { err = "fixture references a body that does not exist"; return B2GPU_ERR_INVALID; }
+        HostShape& sh = fshapes[i];
+        int childCount = BuildShape(sh, d, s.vertices);
+        // shape table entry (deduplicated within the world)
+        std::vector<uint32_t> words = ShapeWords(sh, chainUsed);
+        for (const Vec2& v : sh.chain) {
+            put(CV, (size_t)chainUsed * 2, v.x);
+            put(CV, (size_t)chainUsed * 2 + 1, v.y);
+            ++chainUsed;
+        }
+        int offset;
+        auto it = shapeDedup.find(words);
+        if (it != shapeDedup.end()) {
+            offset = it->second;
+        } else {
+            offset = shapeWordsUsed;
+            if (offset + (int)words.size() > cap.NS) { err = "shape table capacity exceeded"; return B2GPU_ERR_CAPACITY; }
+            for (size_t k = 0; k < words.size(); ++k) SW[offset + k] = words[k];
+            shapeWordsUsed += (int)words.size();
+            shapeDedup[words] = offset;
+        }
+        put(out.f[B2GPU_F_FIXTURE_INFO], i, d.body | (sh.type << 16));
+        put(out.f[B2GPU_F_FIXTURE_SHAPE], i, offset);
+        put(out.f[B2GPU_F_FIXTURE_MAT], (size_t)i * 2, d.friction);
+        put(out.f[B2GPU_F_FIXTURE_MAT], (size_t)i * 2 + 1, d.restitution);
+        put(out.f[B2GPU_F_FIXTURE_FILTER], (size_t)i * 2, (int)d.categoryBits | ((int)d.maskBits << 16));
+        put(out.f[B2GPU_F_FIXTURE_FILTER], (size_t)i * 2 + 1, (int)d.groupIndex);
+
+        HBody& b = bodies[d.body];
+        if (b.flags & kBodyActive) {  // b2Fixture::CreateProxies
+            for (int k = 0; k < childCount; ++k) {
+                Vec2 lo, hi;
+                ComputeAABB(sh, b.xf, k, &lo, &hi);
+                Vec2 r = V2(kAabbExtension, kAabbExtension);
+                lo = lo - r;
+                hi = hi + r;
+                size_t p = proxyCount++;
+                put(out.f[B2GPU_F_PROXY_FAT], p * 4 + 0, lo.x);
+                put(out.f[B2GPU_F_PROXY_FAT], p * 4 + 1, lo.y);
+                put(out.f[B2GPU_F_PROXY_FAT], p * 4 + 2, hi.x);
+                put(out.f[B2GPU_F_PROXY_FAT], p * 4 + 3, hi.y);
+                put(out.f[B2GPU_F_PROXY_INFO], p, i | (k << 16));
+                put(out.f[B2GPU_F_PROXY_MOVED], p, 1);  // b2BroadPhase::CreateProxy buffers a move
+            }
+        }
+        if (d.density > 0.0f) {  // b2Body::ResetMassData
+            b.mass = b.invMass = b.I = b.invI = 0.0f;
+            b.localCenter = V2(0.0f, 0.0f);
+            if (b.type == B2G_STATIC_BODY || b.type == B2G_KINEMATIC_BODY) {
+                b.c0 = b.c = b.xf.p;
+                b.a0 = b.a;
+            } else {
+                Vec2 localCenter = V2(0.0f, 0.0f);
+                for (int f = i; f >= 0; --f) {  // fixture list is head-inserted: newest first
+                    if (s.fixtures[f].body != d.body || s.fixtures[f].density == 0.0f) continue;
+                    MassData md = ComputeMass(fshapes[f], s.fixtures[f].density);
+                    b.mass += md.mass;
+                    localCenter = localCenter + md.mass * md.center;
+                    b.I += md.I;
+                }
+                if (b.mass > 0.0f) {
+                    b.invMass = 1.0f / b.mass;
+                    localCenter = b.invMass * localCenter;
+                } else {
+                    b.mass = 1.0f;
+                    b.invMass = 1.0f;
+                }
+                if (b.I > 0.0f && (b.flags & kBodyFixedRotation) == 0) {
+                    b.I -= b.mass * Dot(localCenter, localCenter);
+                    b.invI = 1.0f / b.I;
+                } else {
+                    b.I = 0.0f;
+                    b.invI = 0.0f;
+                }
+                Vec2 oldCenter = b.c;
+                b.localCenter = localCenter;
+                b.c0 = b.c = Mul(b.xf, b.localCenter);
+                b.v = b.v + Cross(b.w, b.c - oldCenter);
+            }
+        }
+    }
+
+    for (int i = 0; i < nb; ++i) {
+        const HBody& b = bodies[i];
+        const b2g_body_def& d = s.bodies[i];
+        size_t o = (size_t)i * 4;
+        auto& XF = out.f[B2GPU_F_BODY_XF];
+        put(XF, o, b.xf.p.x); put(XF, o + 1, b.xf.p.y); put(XF, o + 2, b.xf.q.s); put(XF, o + 3, b.xf.q.c);
+        auto& S1 = out.f[B2GPU_F_BODY_SWEEP];
+        put(S1, o, b.c.x); put(S1, o + 1, b.c.y); put(S1, o + 2, b.a); put(S1, o + 3, 0.0f);
+        auto& S0 = out.f[B2GPU_F_BODY_SWEEP0];
+        put(S0, o, b.c0.x); put(S0, o + 1, b.c0.y); put(S0, o + 2, b.a0); put(S0, o + 3, 0.0f);
+        auto& VE = out.f[B2GPU_F_BODY_VEL];
+        put(VE, o, b.v.x); put(VE, o + 1, b.v.y); put(VE, o + 2, b.w); put(VE, o + 3, 0.0f);
+        auto& MS = out.f[B2GPU_F_BODY_MASS];
+        put(MS, o, b.invMass); put(MS, o + 1, b.invI); put(MS, o + 2, b.localCenter.x); put(MS, o + 3, b.localCenter.y);
+        auto& DP = out.f[B2GPU_F_BODY_DAMP];
+        put(DP, o, d.linearDamping); put(DP, o + 1, d.angularDamping); put(DP, o + 2, d.gravityScale); put(DP, o + 3, 0.0f);
+        put(out.f[B2GPU_F_BODY_FLAGS], i, b.flags);
+    }
+    put(out.f[B2GPU_F_GRAVITY], 0, s.gravity[0]);
+    put(out.f[B2GPU_F_GRAVITY], 1, s.gravity[1]);
+    put(out.f[B2GPU_F_WORLD_FLAGS], 0, s.worldFlags);
+    put(out.f[B2GPU_F_INV_DT0], 0, 0.0f);
+    put(out.f[B2GPU_F_BODY_COUNT], 0, nb);
+    put(out.f[B2GPU_F_PROXY_COUNT], 0, proxyCount);
+    return B2GPU_OK;
+}
+
+// Fields written at scene-construction time, in upload order (the move buffer last: it arms FindNewContacts).
+const int kBuildFields[] = {
+    B2GPU_F_GRAVITY, B2GPU_F_WORLD_FLAGS, B2GPU_F_INV_DT0, B2GPU_F_BODY_COUNT, B2GPU_F_PROXY_COUNT,
+    B2GPU_F_CONTACT_COUNT, B2GPU_F_STATUS, B2GPU_F_EVENT_COUNT, B2GPU_F_STEP_COUNT,
+    B2GPU_F_BODY_XF, B2GPU_F_BODY_SWEEP, B2GPU_F_BODY_SWEEP0, B2GPU_F_BODY_VEL, B2GPU_F_BODY_FORCE, B2GPU_F_BODY_MASS,
+    B2GPU_F_BODY_DAMP, B2GPU_F_BODY_FLAGS, B2GPU_F_FIXTURE_INFO, B2GPU_F_FIXTURE_SHAPE, B2GPU_F_FIXTURE_MAT,
+    B2GPU_F_FIXTURE_FILTER, B2GPU_F_PROXY_FAT, B2GPU_F_PROXY_INFO, B2GPU_F_SHAPE_WORDS, B2GPU_F_CHAIN_VERTS,
+    B2GPU_F_PROXY_MOVED,
+};
+
+}  // namespace
+
+extern "C" {
+
+int b2gpu_scene_capacities(const b2g_scene* scenes, int32_t sceneCount, b2gpu_batch_desc* desc) {
+    if (!scenes || !desc || sceneCount <= 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    int NB = 1, NF = 1, NP = 1, NS = 4, NV = 1;
+    for (int i = 0; i < sceneCount; ++i) {
+        int nb, nf, np, ns, nv;
+        CountScene(scenes[i], &nb, &nf, &np, &ns, &nv);
+        NB = nb > NB ? nb : NB; NF = nf > NF ? nf : NF; NP = np > NP ? np : NP; NS = ns > NS ? ns : NS; NV = nv > NV ? nv : NV;
+    }
+    desc->maxBodies = NB;
+    desc->maxFixtures = NF;
+    desc->maxProxies = NP;
+    desc->maxShapeWords = NS;
+    desc->maxChainVerts = NV;
+    if (desc->maxContacts <= 0) desc->maxContacts = 4 * NP + 32;   // pyramid-20 peaks at 604 for 211 proxies
+    if (desc->maxEvents <= 0) desc->maxEvents = desc->eventMask ? 3 * desc->maxContacts : 1;
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_build_worlds(b2gpu_batch* batch, const b2g_scene* scenes, int32_t sceneCount, int32_t firstWorld,
+                             int32_t replicate) {
+    if (!batch || !scenes || sceneCount <= 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    if (replicate < 1) replicate = 1;
+    if (replicate > 1 && sceneCount != 1) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "replicate needs exactly one scene");
+    std::vector<std::pair<int, int>> shapes(B2GPU_F_COUNT);
+    for (int id = 0; id < B2GPU_F_COUNT; ++id) {
+        int rc = b2gpu_batch_field_shape(batch, id, &shapes[id].first, &shapes[id].second);
+        if (rc != B2GPU_OK) return rc;
+    }
+    Caps cap;
+    cap.NB = shapes[B2GPU_F_BODY_XF].first;
+    cap.NF = shapes[B2GPU_F_FIXTURE_INFO].first;
+    cap.NP = shapes[B2GPU_F_PROXY_FAT].first;
+    cap.NC = shapes[B2GPU_F_CONTACT_A].first;
+    cap.NS = shapes[B2GPU_F_SHAPE_WORDS].first;
+    cap.NV = shapes[B2GPU_F_CHAIN_VERTS].first;
+    cap.NE = shapes[B2GPU_F_EVENT_A].first;
+
+    const int total = sceneCount * replicate;
+    const int chunk = 2048;  // worlds per upload
+    std::string err;
+    FlatWorld replicated;
+    if (replicate > 1) {
+        int rc = Flatten(scenes[0], cap, shapes, replicated, err);
+        if (rc != B2GPU_OK) return b2gpu_host_set_error(rc, err.c_str());
+    }
+    std::vector<std::vector<uint32_t>> staging(B2GPU_F_COUNT);
+    for (int w0 = 0; w0 < total; w0 += chunk) {
+        int n = total - w0 < chunk ? total - w0 : chunk;
+        for (int id : kBuildFields) staging[id].assign((size_t)n * shapes[id].first * shapes[id].second, 0u);
+        for (int i = 0; i < n; ++i) {
+            FlatWorld local;
+            const FlatWorld* fw = &replicated;
+            if (replicate == 1) {
+                int rc = Flatten(scenes[w0 + i], cap, shapes, local, err);
+                if (rc != B2GPU_OK) return b2gpu_host_set_error(rc, err.c_str());
+                fw = &local;
+            }
+            for (int id : kBuildFields) {
+                size_t words = (size_t)shapes[id].first * shapes[id].second;
+                memcpy(&staging[id][(size_t)i * words], fw->f[id].data(), words * 4);
+            }
+        }
+        for (int id : kBuildFields) {
+            int rc = b2gpu_batch_upload_field(batch, id, staging[id].data(), firstWorld + w0, n);
+            if (rc != B2GPU_OK) return rc;
+        }
+    }
+    return B2GPU_OK;
+}
+
+int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, float* out) {
+    HostShape sh;
+    BuildShape(sh, *fd, vertices);
+    for (int i = 0; i < 8; ++i) {
+        out[2 * i] = i < sh.count ? sh.verts[i].x : 0.0f;
+        out[2 * i + 1] = i < sh.count ? sh.verts[i].y : 0.0f;
+        out[16 + 2 * i] = i < sh.count ? sh.normals[i].x : 0.0f;
+        out[16 + 2 * i + 1] = i < sh.count ? sh.normals[i].y : 0.0f;
+    }
+    out[32] = sh.centroid.x;
+    out[33] = sh.centroid.y;
+    MassData md = ComputeMass(sh, fd->density);
+    out[34] = md.mass; out[35] = md.center.x; out[36] = md.center.y; out[37] = md.I;
+    return sh.count;
+}
+
+}  // extern "C"

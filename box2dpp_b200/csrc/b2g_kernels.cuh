@@ -1,0 +1,1168 @@
+// b2g_kernels.cuh — the b2World::Step pipeline as sm_100a kernels.
+//
+// One thread steps one world; the 32 lanes of a warp are the 32 worlds of a tile (b2g_layout.h), so
+// every access `field[item]` is a coalesced 128 B / 512 B segment across the warp and the strictly
+// ordered per-world lists of the reference are walked sequentially by their
+// owner lane — Gauss-Seidel order, contact-list order and island order are the reference's by
+// construction.
+//
+// Kernel -> reference function (paths under /root/reference/Box2D, vanilla twin under
+// Regression/box2d-ref/Box2DRef):
+//   k_collide      b2ContactManager::Collide  Dynamics/b2ContactManager.cpp:110-175
+//                  b2Contact::Update          Dynamics/Contacts/b2Contact.cpp:170-256
+//                  b2ContactManager::Destroy  Dynamics/b2ContactManager.cpp:42-105
+//   k_islands      b2World::Solve (DFS part)  Dynamics/b2World.cpp:381-537
+//   k_solve        b2Island::Solve            Dynamics/b2Island.cpp:182-383
+//                  b2ContactSolver::*         Dynamics/Contacts/b2ContactSolver.cpp:33-744
+//   k_sync_pairs   b2Body::SynchronizeFixtures Dynamics/b2Body.cpp:442-453, b2Fixture::Synchronize
+//                  Dynamics/b2Fixture.cpp:154-177, b2DynamicTree::MoveProxy Collision/b2DynamicTree.cpp:137-181,
+//                  b2BroadPhase::UpdatePairs Collision/b2BroadPhase.h:193-247,
+//                  b2ContactManager::AddPair Dynamics/b2ContactManager.cpp:182-301
+#pragma once
+
+#include "b2g_collide.cuh"
+#include "b2g_layout.h"
+#include "../../include/b2g_scene.h"
+
+namespace b2g {
+
+// Column view of one field for one world: element i lives at p[i * 32].
+template <class T>
+struct Col {
+    T* p;
+    __device__ __forceinline__ T& operator[](int i) const { return p[(size_t)i * kTile]; }
+};
+template <class T>
+__device__ __forceinline__ Col<T> col(T* base, int tile, int cap, int lane) {
+    Col<T> c;
+    c.p = base + ((size_t)tile * (size_t)cap) * kTile + lane;
+    return c;
+}
+
+__device__ __forceinline__ Xf LoadXf(const Col<float4>& c, int i) {
+    float4 v = c[i];
+    Xf xf;
+    xf.p = V2(v.x, v.y);
+    xf.q.s = v.z;
+    xf.q.c = v.w;
+    return xf;
+}
+
+// ---- shape table readers -----------------------------------------------------------------------
+struct DevPoly {
+    const float* w;  // word 0 of the shape for this lane; word k at w[k * 32]
+    int n;
+    __device__ __forceinline__ DevPoly(const float* base) : w(base) { n = __float_as_int(base[0]); }
+    __device__ __forceinline__ int count() const { return n; }
+    __device__ __forceinline__ float radius() const { return w[1 * kTile]; }
+    __device__ __forceinline__ Vec2 centroid() const { return V2(w[2 * kTile], w[3 * kTile]); }
+    __device__ __forceinline__ Vec2 vert(int i) const { return V2(w[(4 + 2 * i) * kTile], w[(5 + 2 * i) * kTile]); }
+    __device__ __forceinline__ Vec2 normal(int i) const {
+        return V2(w[(4 + 2 * n + 2 * i) * kTile], w[(5 + 2 * n + 2 * i) * kTile]);
+    }
+};
+__device__ __forceinline__ CircleData LoadCircle(const float* w) {
+    CircleData c;
+    c.radius = w[0];
+    c.p = V2(w[1 * kTile], w[2 * kTile]);
+    return c;
+}
+__device__ __forceinline__ EdgeData LoadEdge(const float* w) {
+    EdgeData e;
+    e.radius = w[0];
+    e.v0 = V2(w[1 * kTile], w[2 * kTile]);
+    e.v1 = V2(w[3 * kTile], w[4 * kTile]);
+    e.v2 = V2(w[5 * kTile], w[6 * kTile]);
+    e.v3 = V2(w[7 * kTile], w[8 * kTile]);
+    int f = __float_as_int(w[9 * kTile]);
+    e.has0 = (f & 1) != 0;
+    e.has3 = (f & 2) != 0;
+    return e;
+}
+// b2ChainShape::GetChildEdge — Collision/Shapes/b2ChainShape.cpp:111-140
+__device__ __forceinline__ EdgeData LoadChainChild(const float* w, const Col<float2>& verts, int index) {
+    EdgeData e;
+    e.radius = w[0];
+    int first = __float_as_int(w[1 * kTile]);
+    int count = __float_as_int(w[2 * kTile]);
+    int f = __float_as_int(w[7 * kTile]);
+    float2 a = verts[first + index], b = verts[first + index + 1];
+    e.v1 = V2(a.x, a.y);
+    e.v2 = V2(b.x, b.y);
+    if (index > 0) {
+        float2 p = verts[first + index - 1];
+        e.v0 = V2(p.x, p.y);
+        e.has0 = true;
+    } else {
+        e.v0 = V2(w[3 * kTile], w[4 * kTile]);
+        e.has0 = (f & 1) != 0;
+    }
+    if (index < count - 2) {
+        float2 p = verts[first + index + 2];
+        e.v3 = V2(p.x, p.y);
+        e.has3 = true;
+    } else {
+        e.v3 = V2(w[5 * kTile], w[6 * kTile]);
+        e.has3 = (f & 2) != 0;
+    }
+    return e;
+}
+// m_radius of any shape
+__device__ __forceinline__ float ShapeRadius(const float* w, int shapeType) {
+    return shapeType == B2G_SHAPE_POLYGON ? w[1 * kTile] : w[0];
+}
+
+// Shape ComputeAABB: b2PolygonShape.cpp:335-352, b2CircleShape.cpp:85-94, b2EdgeShape.cpp:118-131,
+// b2ChainShape.cpp:169-185 (no radius on chain children)
+__device__ __forceinline__ void ShapeAABB(const float* w, int shapeType, const Col<float2>& chainVerts, int child, Xf xf,
+                                          Vec2* lo, Vec2* hi) {
+    if (shapeType == B2G_SHAPE_POLYGON) {
+        DevPoly p(w);
+        Vec2 lower = Mul(xf, p.vert(0));
+        Vec2 upper = lower;
+        for (int i = 1; i < p.count(); ++i) {
+            Vec2 v = Mul(xf, p.vert(i));
+            lower = Min(lower, v);
+            upper = Max(upper, v);
+        }
+        Vec2 r = V2(p.radius(), p.radius());
+        *lo = lower - r;
+        *hi = upper + r;
+    } else if (shapeType == B2G_SHAPE_CIRCLE) {
+        CircleData c = LoadCircle(w);
+        Vec2 p = xf.p + Mul(xf.q, c.p);
+        *lo = V2(p.x - c.radius, p.y - c.radius);
+        *hi = V2(p.x + c.radius, p.y + c.radius);
+    } else if (shapeType == B2G_SHAPE_EDGE) {
+        EdgeData e = LoadEdge(w);
+        Vec2 v1 = Mul(xf, e.v1);
+        Vec2 v2 = Mul(xf, e.v2);
+        Vec2 lower = Min(v1, v2);
+        Vec2 upper = Max(v1, v2);
+        Vec2 r = V2(e.radius, e.radius);
+        *lo = lower - r;
+        *hi = upper + r;
+    } else {
+        int first = __float_as_int(w[1 * kTile]);
+        int count = __float_as_int(w[2 * kTile]);
+        int i1 = child, i2 = child + 1;
+        if (i2 == count) i2 = 0;
+        float2 a = chainVerts[first + i1], b = chainVerts[first + i2];
+        Vec2 v1 = Mul(xf, V2(a.x, a.y));
+        Vec2 v2 = Mul(xf, V2(b.x, b.y));
+        *lo = Min(v1, v2);
+        *hi = Max(v1, v2);
+    }
+}
+
+__device__ __forceinline__ bool FatOverlap(float4 a, float4 b) {  // b2TestOverlap(AABB, AABB), b2Collision.h:278-291
+    float d1x = b.x - a.z, d1y = b.y - a.w;
+    float d2x = a.x - b.z, d2y = a.y - b.w;
+    if (d1x > 0.0f || d1y > 0.0f) return false;
+    if (d2x > 0.0f || d2y > 0.0f) return false;
+    return true;
+}
+
+// b2Body::SetAwake(true) — Box2D/Dynamics/b2Body.h:634-643
+__device__ __forceinline__ void WakeBody(const Col<int>& bodyFlags, const Col<float4>& bodySweep, int b) {
+    int f = bodyFlags[b];
+    if ((f & kBodyAwake) == 0) {
+        bodyFlags[b] = f | kBodyAwake;
+        float4 s = bodySweep[b];
+        s.w = 0.0f;  // m_sleepTime
+        bodySweep[b] = s;
+    }
+}
+
+struct EventSink {
+    Col<int4> a;
+    Col<float4> b;
+    int* count;
+    int* status;
+    int cap, mask;
+    __device__ __forceinline__ void push(int type, int fixA, int childA, int fixB, int childB, int n, float4 imp) const {
+        if ((mask >> type & 1) == 0) return;
+        int i = *count;
+        if (i < cap) {
+            a[i] = make_int4(type, fixA | (childA << 16), fixB | (childB << 16), n);
+            b[i] = imp;
+        } else {
+            *status |= kStatusEventOverflow;
+        }
+        *count = i + 1;
+    }
+};
+
+struct WorldCtx {
+    int tile, lane;
+    __device__ __forceinline__ size_t s() const { return (size_t)tile * kTile + lane; }  // world-scalar index
+};
+
+// =================================================================================================
+// k_collide
+// =================================================================================================
+__device__ __forceinline__ void EvaluateContact(const Arena& A, int tile, int lane, Manifold* m, int shapeTypes,
+                                                int shapeOffA, int shapeOffB, int proxyA, Xf xfA, Xf xfB) {
+    const float* wA = A.shapeWords + ((size_t)tile * A.NS + shapeOffA) * kTile + lane;
+    const float* wB = A.shapeWords + ((size_t)tile * A.NS + shapeOffB) * kTile + lane;
+    int tA = shapeTypes & 3, tB = (shapeTypes >> 2) & 3;
+    if (tA == B2G_SHAPE_POLYGON && tB == B2G_SHAPE_POLYGON) {
+        CollidePolygons(m, DevPoly(wA), xfA, DevPoly(wB), xfB);
+    } else if (tA == B2G_SHAPE_CIRCLE && tB == B2G_SHAPE_CIRCLE) {
+        CollideCircles(m, LoadCircle(wA), xfA, LoadCircle(wB), xfB);
+    } else if (tA == B2G_SHAPE_POLYGON && tB == B2G_SHAPE_CIRCLE) {
+        CollidePolygonAndCircle(m, DevPoly(wA), xfA, LoadCircle(wB), xfB);
+    } else {
+        EdgeData e;
+        if (tA == B2G_SHAPE_CHAIN) {
+            int child = (col(A.proxyInfo, tile, A.NP, lane)[proxyA] >> 16) & 0xffff;
+            e = LoadChainChild(wA, col(A.chainVerts, tile, A.NV, lane), child);
+        } else {
+            e = LoadEdge(wA);
+        }
+        if (tB == B2G_SHAPE_CIRCLE) CollideEdgeAndCircle(m, e, xfA, LoadCircle(wB), xfB);
+        else CollideEdgeAndPolygon(m, e, xfA, DevPoly(wB), xfB);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_collide(Arena A) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int tile = w >> 5, lane = w & 31;
+    if (tile >= A.numTiles) return;
+    size_t ws = (size_t)tile * kTile + lane;
+    A.eventCount[ws] = 0;
+    int n = A.contactCount[ws];
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    Col<int4> cK = col(A.contactK, tile, A.NC, lane);
+    Col<int2> cS = col(A.contactS, tile, A.NC, lane);
+    Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane);
+    Col<float4> cP1 = col(A.contactP1, tile, A.NC, lane);
+    Col<float4> cN = col(A.contactN, tile, A.NC, lane);
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
+    Col<float4> bodyXf = col(A.bodyXf, tile, A.NB, lane);
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws],
+                 A.NE, A.eventMask};
+    bool anyDead = false;
+    for (int k = n - 1; k >= 0; --k) {
+        int4 a = cA[k];
+        int proxyA = a.x & 0xffff, proxyB = (a.x >> 16) & 0xffff;
+        int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+        int flags = a.z;
+        int pointCountOld = (a.w >> 8) & 0xff;
+        int bfA = bodyFlags[bodyA], bfB = bodyFlags[bodyB];
+        bool activeA = (bfA & kBodyAwake) && (bfA & kBodyTypeMask) != B2G_STATIC_BODY;
+        bool activeB = (bfB & kBodyAwake) && (bfB & kBodyTypeMask) != B2G_STATIC_BODY;
+        if (!activeA && !activeB) continue;
+        if (!FatOverlap(proxyFat[proxyA], proxyFat[proxyB])) {
+            // b2ContactManager::Destroy + b2Contact::Destroy
+            if (flags & kContactTouching) {
+                int pa = proxyInfo[proxyA], pb = proxyInfo[proxyB];
+                ev.push(kEventEnd, pa & 0xffff, (pa >> 16) & 0xffff, pb & 0xffff, (pb >> 16) & 0xffff, pointCountOld,
+                        make_float4(0, 0, 0, 0));
+            }
+            if (pointCountOld > 0) {
+                WakeBody(bodyFlags, bodySweep, bodyA);
+                WakeBody(bodyFlags, bodySweep, bodyB);
+            }
+            a.z = flags | kContactDead;
+            cA[k] = a;
+            anyDead = true;
+            continue;
+        }
+        // b2Contact::Update
+        int4 kk = cK[k];
+        float4 p0 = cP0[k], p1 = cP1[k];
+        uint32_t oldKey0 = (uint32_t)kk.x, oldKey1 = (uint32_t)kk.y;
+        float oldN0 = p0.z, oldT0 = p0.w, oldN1 = p1.z, oldT1 = p1.w;
+        flags |= kContactEnabled;
+        bool wasTouching = (flags & kContactTouching) != 0;
+        Manifold m;
+        m.pointCount = 0;
+        m.type = a.w & 0xff;
+        int2 so = cS[k];
+        EvaluateContact(A, tile, lane, &m, (a.w >> 16) & 0xf, so.x, so.y, proxyA, LoadXf(bodyXf, bodyA),
+                        LoadXf(bodyXf, bodyB));
+        bool touching = m.pointCount > 0;
+        if (m.pointCount > 0) {
+            float nI = 0.0f, tI = 0.0f;
+            if (pointCountOld > 0 && oldKey0 == m.key0) { nI = oldN0; tI = oldT0; }
+            else if (pointCountOld > 1 && oldKey1 == m.key0) { nI = oldN1; tI = oldT1; }
+            cP0[k] = make_float4(m.lp0.x, m.lp0.y, nI, tI);
+            if (m.pointCount > 1) {
+                nI = 0.0f; tI = 0.0f;
+                if (pointCountOld > 0 && oldKey0 == m.key1) { nI = oldN0; tI = oldT0; }
+                else if (pointCountOld > 1 && oldKey1 == m.key1) { nI = oldN1; tI = oldT1; }
+                cP1[k] = make_float4(m.lp1.x, m.lp1.y, nI, tI);
+            }
+            cN[k] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
+            kk.x = (int)m.key0;
+            kk.y = (int)m.key1;
+            cK[k] = kk;
+        }
+        if (touching != wasTouching) {
+            WakeBody(bodyFlags, bodySweep, bodyA);
+            WakeBody(bodyFlags, bodySweep, bodyB);
+        }
+        if (touching) flags |= kContactTouching; else flags &= ~kContactTouching;
+        a.z = flags;
+        a.w = (a.w & 0xffff0000) | (m.type & 0xff) | (m.pointCount << 8);
+        cA[k] = a;
+        if (A.eventMask) {
+            int pa = proxyInfo[proxyA], pb = proxyInfo[proxyB];
+            int fA = pa & 0xffff, chA = (pa >> 16) & 0xffff, fB = pb & 0xffff, chB = (pb >> 16) & 0xffff;
+            if (!wasTouching && touching) ev.push(kEventBegin, fA, chA, fB, chB, m.pointCount, make_float4(0, 0, 0, 0));
+            if (wasTouching && !touching) ev.push(kEventEnd, fA, chA, fB, chB, m.pointCount, make_float4(0, 0, 0, 0));
+            if (touching) ev.push(kEventPreSolve, fA, chA, fB, chB, m.pointCount, make_float4(0, 0, 0, 0));
+        }
+    }
+    if (anyDead) {  // stable erase keeps every list in the reference's order
+        int wpos = 0;
+        for (int k = 0; k < n; ++k) {
+            int4 a = cA[k];
+            if (a.z & kContactDead) continue;
+            if (wpos != k) {
+                cA[wpos] = a;
+                cK[wpos] = cK[k];
+                cS[wpos] = cS[k];
+                cP0[wpos] = cP0[k];
+                cP1[wpos] = cP1[k];
+                cN[wpos] = cN[k];
+            }
+            ++wpos;
+        }
+        A.contactCount[ws] = wpos;
+    }
+}
+
+// =================================================================================================
+// k_islands
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_islands(Arena A) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int tile = w >> 5, lane = w & 31;
+    if (tile >= A.numTiles) return;
+    size_t ws = (size_t)tile * kTile + lane;
+    int nb = A.bodyCount[ws];
+    int nc = A.contactCount[ws];
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
+    Col<int> adjStart = col(A.bodyAdjStart, tile, A.NB + 1, lane);
+    Col<int> adj = col(A.bodyAdj, tile, 2 * A.NC, lane);
+    Col<int> stack = col(A.dfsStack, tile, A.NB, lane);
+    Col<int> iBodies = col(A.islandBodies, tile, A.NB + A.NC, lane);
+    Col<int> iBodyEnd = col(A.islandBodyEnd, tile, A.NB, lane);
+    Col<int> iContacts = col(A.islandContacts, tile, A.NC, lane);
+    Col<int> iContactEnd = col(A.islandContactEnd, tile, A.NB, lane);
+
+    // clear island flags; count contact edges per body
+    for (int b = 0; b < nb; ++b) {
+        bodyFlags[b] &= ~kBodyIsland;
+        adjStart[b] = 0;
+    }
+    for (int k = 0; k < nc; ++k) {
+        int4 a = cA[k];
+        if (a.z & kContactIsland) {
+            a.z &= ~kContactIsland;
+            cA[k] = a;
+        }
+        adjStart[a.y & 0xffff] += 1;
+        adjStart[(a.y >> 16) & 0xffff] += 1;
+    }
+    int run = 0;
+    for (int b = 0; b < nb; ++b) {
+        int c = adjStart[b];
+        adjStart[b] = run;
+        run += c;
+    }
+    // fill newest-first (= the order of b2Body::m_contactList); afterwards adjStart[b] is the END of b
+    for (int k = nc - 1; k >= 0; --k) {
+        int4 a = cA[k];
+        int bA = a.y & 0xffff, bB = (a.y >> 16) & 0xffff;
+        int pA = adjStart[bA];
+        adj[pA] = k;
+        adjStart[bA] = pA + 1;
+        int pB = adjStart[bB];
+        adj[pB] = k;
+        adjStart[bB] = pB + 1;
+    }
+
+    int islands = 0, nBodies = 0, nContacts = 0;
+    for (int seed = nb - 1; seed >= 0; --seed) {  // m_bodyList is head-inserted: newest first
+        int sf = bodyFlags[seed];
+        if (sf & kBodyIsland) continue;
+        if ((sf & kBodyAwake) == 0 || (sf & kBodyActive) == 0) continue;
+        if ((sf & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+        int stackCount = 0;
+        stack[stackCount++] = seed;
+        bodyFlags[seed] = sf | kBodyIsland;
+        while (stackCount > 0) {
+            int b = stack[--stackCount];
+            iBodies[nBodies++] = b;
+            WakeBody(bodyFlags, bodySweep, b);
+            if ((bodyFlags[b] & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+            int e0 = b == 0 ? 0 : adjStart[b - 1], e1 = adjStart[b];
+            for (int e = e0; e < e1; ++e) {
+                int k = adj[e];
+                int4 a = cA[k];
+                if (a.z & kContactIsland) continue;
+                if ((a.z & kContactEnabled) == 0 || (a.z & kContactTouching) == 0) continue;
+                iContacts[nContacts++] = k;
+                a.z |= kContactIsland;
+                cA[k] = a;
+                int bA = a.y & 0xffff, bB = (a.y >> 16) & 0xffff;
+                int other = bA == b ? bB : bA;
+                int of = bodyFlags[other];
+                if (of & kBodyIsland) continue;
+                stack[stackCount++] = other;
+                bodyFlags[other] = of | kBodyIsland;
+            }
+        }
+        // statics may join the next island
+        int b0 = islands == 0 ? 0 : iBodyEnd[islands - 1];
+        for (int i = b0; i < nBodies; ++i) {
+            int b = iBodies[i];
+            int f = bodyFlags[b];
+            if ((f & kBodyTypeMask) == B2G_STATIC_BODY) bodyFlags[b] = f & ~kBodyIsland;
+        }
+        iBodyEnd[islands] = nBodies;
+        iContactEnd[islands] = nContacts;
+        ++islands;
+    }
+    A.islandCount[ws] = islands;
+}
+
+// =================================================================================================
+// k_solve
+// =================================================================================================
+constexpr int kVcStride = 9;  // float4 per b2ContactVelocityConstraint
+
+__global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, int posIters) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int tile = w >> 5, lane = w & 31;
+    if (tile >= A.numTiles) return;
+    size_t ws = (size_t)tile * kTile + lane;
+    const int islands = A.islandCount[ws];
+    const int worldFlags = A.worldFlags[ws];
+    const bool warmStarting = (worldFlags & B2G_WORLD_WARM_STARTING) != 0;
+    const bool allowSleep = (worldFlags & B2G_WORLD_ALLOW_SLEEP) != 0;
+    const bool clearForces = (worldFlags & B2G_WORLD_CLEAR_FORCES) != 0;
+    const float dtRatio = A.invDt0[ws] * h;
+    const float2 g2 = A.gravity[ws];
+    const Vec2 gravity = V2(g2.x, g2.y);
+
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    Col<int4> cK = col(A.contactK, tile, A.NC, lane);
+    Col<int2> cS = col(A.contactS, tile, A.NC, lane);
+    Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane);
+    Col<float4> cP1 = col(A.contactP1, tile, A.NC, lane);
+    Col<float4> cN = col(A.contactN, tile, A.NC, lane);
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    Col<float4> bodyXf = col(A.bodyXf, tile, A.NB, lane);
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
+    Col<float4> bodySweep0 = col(A.bodySweep0, tile, A.NB, lane);
+    Col<float4> bodyVel = col(A.bodyVel, tile, A.NB, lane);
+    Col<float4> bodyForce = col(A.bodyForce, tile, A.NB, lane);
+    Col<float4> bodyMass = col(A.bodyMass, tile, A.NB, lane);
+    Col<float4> bodyDamp = col(A.bodyDamp, tile, A.NB, lane);
+    Col<int> iBodies = col(A.islandBodies, tile, A.NB + A.NC, lane);
+    Col<int> iBodyEnd = col(A.islandBodyEnd, tile, A.NB, lane);
+    Col<int> iContacts = col(A.islandContacts, tile, A.NC, lane);
+    Col<int> iContactEnd = col(A.islandContactEnd, tile, A.NB, lane);
+    Col<float4> vc = col(A.vc, tile, A.NC * kVcStride, lane);
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws],
+                 A.NE, A.eventMask};
+
+    int b0 = 0, c0 = 0;
+    for (int isl = 0; isl < islands; ++isl) {
+        const int b1 = iBodyEnd[isl], c1 = iContactEnd[isl];
+
+        // ---- integrate velocities (b2Island.cpp:190-225); positions/velocities stay in the body arrays ----
+        for (int i = b0; i < b1; ++i) {
+            int b = iBodies[i];
+            int f = bodyFlags[b];
+            if ((f & kBodyTypeMask) == B2G_STATIC_BODY) continue;  // c0 == c already, never integrated
+            float4 sw = bodySweep[b];
+            bodySweep0[b] = make_float4(sw.x, sw.y, sw.z, 0.0f);
+            if ((f & kBodyTypeMask) == B2G_DYNAMIC_BODY) {
+                float4 vel = bodyVel[b];
+                float4 frc = bodyForce[b];
+                float4 ms = bodyMass[b];
+                float4 dp = bodyDamp[b];
+                Vec2 v = V2(vel.x, vel.y);
+                float wv = vel.z;
+                v = v + h * (dp.z * gravity + ms.x * V2(frc.x, frc.y));
+                wv += h * ms.y * frc.z;
+                v = Div(1.0f, 1.0f + h * dp.x) * v;
+                wv *= Div(1.0f, 1.0f + h * dp.y);
+                bodyVel[b] = make_float4(v.x, v.y, wv, 0.0f);
+                if (clearForces && (frc.x != 0.0f || frc.y != 0.0f || frc.z != 0.0f))
+                    bodyForce[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+
+        // ---- b2ContactSolver ctor + InitializeVelocityConstraints (b2ContactSolver.cpp:33-238) ----
+        for (int i = c0; i < c1; ++i) {
+            const int k = iContacts[i];
+            const int4 a = cA[k];
+            const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+            const int mtype = a.w & 0xff;
+            const int pointCount = (a.w >> 8) & 0xff;
+            const int shapeTypes = (a.w >> 16) & 0xf;
+            const int4 kk = cK[k];
+            const int2 so = cS[k];
+            const float friction = __int_as_float(kk.z), restitution = __int_as_float(kk.w);
+            const float radiusA = ShapeRadius(A.shapeWords + ((size_t)tile * A.NS + so.x) * kTile + lane, shapeTypes & 3);
+            const float radiusB = ShapeRadius(A.shapeWords + ((size_t)tile * A.NS + so.y) * kTile + lane, (shapeTypes >> 2) & 3);
+            const float4 msA = bodyMass[bodyA], msB = bodyMass[bodyB];
+            const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
+            const float4 swA = bodySweep[bodyA], swB = bodySweep[bodyB];
+            const float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
+            const Vec2 cAp = V2(swA.x, swA.y), cBp = V2(swB.x, swB.y);
+            const Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
+            const float wA = veA.z, wB = veB.z;
+            Xf xfA, xfB;
+            xfA.q = MakeRot(swA.z);
+            xfB.q = MakeRot(swB.z);
+            xfA.p = cAp - Mul(xfA.q, V2(msA.z, msA.w));
+            xfB.p = cBp - Mul(xfB.q, V2(msB.z, msB.w));
+            const float4 p0 = cP0[k];
+            float4 p1 = make_float4(0, 0, 0, 0);
+            if (pointCount > 1) p1 = cP1[k];
+            const float4 nn = cN[k];
+            // b2WorldManifold::Initialize (b2Collision.cpp:24-87)
+            Vec2 normal, wp0, wp1 = V2(0, 0);
+            if (mtype == kManifoldCircles) {
+                normal = V2(1.0f, 0.0f);
+                Vec2 pointA = Mul(xfA, V2(nn.z, nn.w));
+                Vec2 pointB = Mul(xfB, V2(p0.x, p0.y));
+                if (DistanceSquared(pointA, pointB) > kEpsilon * kEpsilon) {
+                    normal = pointB - pointA;
+                    Normalize(normal);
+                }
+                Vec2 ca = pointA + radiusA * normal;
+                Vec2 cb = pointB - radiusB * normal;
+                wp0 = 0.5f * (ca + cb);
+            } else if (mtype == kManifoldFaceA) {
+                normal = Mul(xfA.q, V2(nn.x, nn.y));
+                Vec2 planePoint = Mul(xfA, V2(nn.z, nn.w));
+                {
+                    Vec2 clipPoint = Mul(xfB, V2(p0.x, p0.y));
+                    Vec2 ca = clipPoint + (radiusA - Dot(clipPoint - planePoint, normal)) * normal;
+                    Vec2 cb = clipPoint - radiusB * normal;
+                    wp0 = 0.5f * (ca + cb);
+                }
+                if (pointCount > 1) {
+                    Vec2 clipPoint = Mul(xfB, V2(p1.x, p1.y));
+                    Vec2 ca = clipPoint + (radiusA - Dot(clipPoint - planePoint, normal)) * normal;
+                    Vec2 cb = clipPoint - radiusB * normal;
+                    wp1 = 0.5f * (ca + cb);
+                }
+            } else {
+                normal = Mul(xfB.q, V2(nn.x, nn.y));
+                Vec2 planePoint = Mul(xfB, V2(nn.z, nn.w));
+                {
+                    Vec2 clipPoint = Mul(xfA, V2(p0.x, p0.y));
+                    Vec2 cb = clipPoint + (radiusB - Dot(clipPoint - planePoint, normal)) * normal;
+                    Vec2 ca = clipPoint - radiusA * normal;
+                    wp0 = 0.5f * (ca + cb);
+                }
+                if (pointCount > 1) {
+                    Vec2 clipPoint = Mul(xfA, V2(p1.x, p1.y));
+                    Vec2 cb = clipPoint + (radiusB - Dot(clipPoint - planePoint, normal)) * normal;
+                    Vec2 ca = clipPoint - radiusA * normal;
+                    wp1 = 0.5f * (ca + cb);
+                }
+                normal = -normal;
+            }
+            const Vec2 tangent = Cross(normal, 1.0f);
+            int vcPointCount = pointCount;
+            float4 q2, q3, q4 = make_float4(0, 0, 0, 0), q5 = make_float4(0, 0, 0, 0);
+            float4 q6 = make_float4(0, 0, 0, 0), q7 = make_float4(0, 0, 0, 0);
+            Vec2 rA0, rB0, rA1 = V2(0, 0), rB1 = V2(0, 0);
+            {
+                rA0 = wp0 - cAp;
+                rB0 = wp0 - cBp;
+                float rnA = Cross(rA0, normal), rnB = Cross(rB0, normal);
+                float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                float normalMass = kNormal > 0.0f ? Div(1.0f, kNormal) : 0.0f;
+                float rtA = Cross(rA0, tangent), rtB = Cross(rB0, tangent);
+                float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+                float tangentMass = kTangent > 0.0f ? Div(1.0f, kTangent) : 0.0f;
+                float velocityBias = 0.0f;
+                float vRel = Dot(normal, vB + Cross(wB, rB0) - vA - Cross(wA, rA0));
+                if (vRel < -kVelocityThreshold) velocityBias = -restitution * vRel;
+                q2 = make_float4(rA0.x, rA0.y, rB0.x, rB0.y);
+                q3 = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
+            }
+            if (pointCount > 1) {
+                rA1 = wp1 - cAp;
+                rB1 = wp1 - cBp;
+                float rnA = Cross(rA1, normal), rnB = Cross(rB1, normal);
+                float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                float normalMass = kNormal > 0.0f ? Div(1.0f, kNormal) : 0.0f;
+                float rtA = Cross(rA1, tangent), rtB = Cross(rB1, tangent);
+                float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+                float tangentMass = kTangent > 0.0f ? Div(1.0f, kTangent) : 0.0f;
+                float velocityBias = 0.0f;
+                float vRel = Dot(normal, vB + Cross(wB, rB1) - vA - Cross(wA, rA1));
+                if (vRel < -kVelocityThreshold) velocityBias = -restitution * vRel;
+                q4 = make_float4(rA1.x, rA1.y, rB1.x, rB1.y);
+                q5 = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
+                // block solver preparation
+                float rn1A = Cross(rA0, normal), rn1B = Cross(rB0, normal);
+                float rn2A = Cross(rA1, normal), rn2B = Cross(rB1, normal);
+                float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+                float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+                float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+                const float k_maxConditionNumber = 1000.0f;
+                if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
+                    // b2Mat22::GetInverse with ex = (k11, k12), ey = (k12, k22)
+                    float ma = k11, mb = k12, mc = k12, md = k22;
+                    float det = ma * md - mb * mc;
+                    if (det != 0.0f) det = Div(1.0f, det);
+                    q6 = make_float4(k11, k12, k22, det * md);        // K, normalMass.ex.x
+                    q7 = make_float4(-det * mc, -det * mb, det * ma, 0.0f);  // nm.ex.y, nm.ey.x, nm.ey.y
+                } else {
+                    vcPointCount = 1;
+                }
+            }
+            float4 imp = make_float4(0, 0, 0, 0);
+            if (warmStarting) imp = make_float4(dtRatio * p0.z, dtRatio * p0.w, dtRatio * p1.z, dtRatio * p1.w);
+            q3.w = __int_as_float(vcPointCount | (pointCount << 8));
+            q5.w = radiusA;
+            q7.w = radiusB;
+            const size_t o = (size_t)i * kVcStride;
+            vc[o + 0] = make_float4(normal.x, normal.y, friction, __int_as_float(a.y));
+            vc[o + 1] = make_float4(mA, iA, mB, iB);
+            vc[o + 2] = q2;
+            vc[o + 3] = q3;
+            vc[o + 4] = q4;
+            vc[o + 5] = q5;
+            vc[o + 6] = q6;
+            vc[o + 7] = q7;
+            vc[o + 8] = imp;
+        }
+
+        // ---- WarmStart (b2ContactSolver.cpp:240-278) ----
+        if (warmStarting) {
+            for (int i = c0; i < c1; ++i) {
+                const size_t o = (size_t)i * kVcStride;
+                const float4 q0 = vc[o + 0], q1 = vc[o + 1], q2 = vc[o + 2], q3 = vc[o + 3], imp = vc[o + 8];
+                const int bodies = __float_as_int(q0.w);
+                const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
+                const int pointCount = __float_as_int(q3.w) & 0xff;
+                const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
+                float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
+                Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
+                float wA = veA.z, wB = veB.z;
+                const Vec2 normal = V2(q0.x, q0.y);
+                const Vec2 tangent = Cross(normal, 1.0f);
+                {
+                    Vec2 P = imp.x * normal + imp.y * tangent;
+                    wA -= iA * Cross(V2(q2.x, q2.y), P);
+                    vA = vA - mA * P;
+                    wB += iB * Cross(V2(q2.z, q2.w), P);
+                    vB = vB + mB * P;
+                }
+                if (pointCount > 1) {
+                    const float4 q4 = vc[o + 4];
+                    Vec2 P = imp.z * normal + imp.w * tangent;
+                    wA -= iA * Cross(V2(q4.x, q4.y), P);
+                    vA = vA - mA * P;
+                    wB += iB * Cross(V2(q4.z, q4.w), P);
+                    vB = vB + mB * P;
+                }
+                bodyVel[bodyA] = make_float4(vA.x, vA.y, wA, 0.0f);
+                bodyVel[bodyB] = make_float4(vB.x, vB.y, wB, 0.0f);
+            }
+        }
+
+        // ---- SolveVelocityConstraints (b2ContactSolver.cpp:280-597) ----
+        for (int it = 0; it < velIters; ++it) {
+            for (int i = c0; i < c1; ++i) {
+                const size_t o = (size_t)i * kVcStride;
+                const float4 q0 = vc[o + 0], q1 = vc[o + 1], q2 = vc[o + 2], q3 = vc[o + 3];
+                float4 imp = vc[o + 8];
+                const int bodies = __float_as_int(q0.w);
+                const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
+                const int pointCount = __float_as_int(q3.w) & 0xff;
+                const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
+                float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
+                Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
+                float wA = veA.z, wB = veB.z;
+                const Vec2 normal = V2(q0.x, q0.y);
+                const Vec2 tangent = Cross(normal, 1.0f);
+                const float friction = q0.z;
+                const Vec2 rA0 = V2(q2.x, q2.y), rB0 = V2(q2.z, q2.w);
+                // tangent constraints first (tangentSpeed is 0: b2Contact::SetTangentSpeed is not exposed)
+                {
+                    Vec2 dv = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
+                    float vt = Dot(dv, tangent) - 0.0f;
+                    float lambda = q3.y * (-vt);
+                    float maxFriction = friction * imp.x;
+                    float newImpulse = Clamp(imp.y + lambda, -maxFriction, maxFriction);
+                    lambda = newImpulse - imp.y;
+                    imp.y = newImpulse;
+                    Vec2 P = lambda * tangent;
+                    vA = vA - mA * P;
+                    wA -= iA * Cross(rA0, P);
+                    vB = vB + mB * P;
+                    wB += iB * Cross(rB0, P);
+                }
+                if (pointCount == 1) {
+                    Vec2 dv = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
+                    float vn = Dot(dv, normal);
+                    float lambda = -q3.x * (vn - q3.z);
+                    float newImpulse = Max(imp.x + lambda, 0.0f);
+                    lambda = newImpulse - imp.x;
+                    imp.x = newImpulse;
+                    Vec2 P = lambda * normal;
+                    vA = vA - mA * P;
+                    wA -= iA * Cross(rA0, P);
+                    vB = vB + mB * P;
+                    wB += iB * Cross(rB0, P);
+                } else {
+                    const float4 q4 = vc[o + 4], q5 = vc[o + 5], q6 = vc[o + 6], q7 = vc[o + 7];
+                    const Vec2 rA1 = V2(q4.x, q4.y), rB1 = V2(q4.z, q4.w);
+                    {
+                        Vec2 dv = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
+                        float vt = Dot(dv, tangent) - 0.0f;
+                        float lambda = q5.y * (-vt);
+                        float maxFriction = friction * imp.z;
+                        float newImpulse = Clamp(imp.w + lambda, -maxFriction, maxFriction);
+                        lambda = newImpulse - imp.w;
+                        imp.w = newImpulse;
+                        Vec2 P = lambda * tangent;
+                        vA = vA - mA * P;
+                        wA -= iA * Cross(rA1, P);
+                        vB = vB + mB * P;
+                        wB += iB * Cross(rB1, P);
+                    }
+                    // block solver
+                    Vec2 a = V2(imp.x, imp.z);
+                    Vec2 dv1 = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
+                    Vec2 dv2 = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
+                    float vn1 = Dot(dv1, normal);
+                    float vn2 = Dot(dv2, normal);
+                    Vec2 b;
+                    b.x = vn1 - q3.z;
+                    b.y = vn2 - q5.z;
+                    const float k11 = q6.x, k12 = q6.y, k22 = q6.z;
+                    // b -= b2Mul(K, a), K.ex = (k11, k12), K.ey = (k12, k22)
+                    b.x -= k11 * a.x + k12 * a.y;
+                    b.y -= k12 * a.x + k22 * a.y;
+                    Vec2 x;
+                    bool solved = false;
+                    // case 1: x = -b2Mul(normalMass, b)
+                    x.x = -(q6.w * b.x + q7.y * b.y);
+                    x.y = -(q7.x * b.x + q7.z * b.y);
+                    if (x.x >= 0.0f && x.y >= 0.0f) solved = true;
+                    if (!solved) {  // case 2
+                        x.x = -q3.x * b.x;
+                        x.y = 0.0f;
+                        vn2 = k12 * x.x + b.y;
+                        if (x.x >= 0.0f && vn2 >= 0.0f) solved = true;
+                    }
+                    if (!solved) {  // case 3
+                        x.x = 0.0f;
+                        x.y = -q5.x * b.y;
+                        vn1 = k12 * x.y + b.x;
+                        if (x.y >= 0.0f && vn1 >= 0.0f) solved = true;
+                    }
+                    if (!solved) {  // case 4
+                        x.x = 0.0f;
+                        x.y = 0.0f;
+                        if (b.x >= 0.0f && b.y >= 0.0f) solved = true;
+                    }
+                    if (solved) {
+                        Vec2 d = x - a;
+                        Vec2 P1 = d.x * normal;
+                        Vec2 P2 = d.y * normal;
+                        vA = vA - mA * (P1 + P2);
+                        wA -= iA * (Cross(rA0, P1) + Cross(rA1, P2));
+                        vB = vB + mB * (P1 + P2);
+                        wB += iB * (Cross(rB0, P1) + Cross(rB1, P2));
+                        imp.x = x.x;
+                        imp.z = x.y;
+                    }
+                }
+                vc[o + 8] = imp;
+                bodyVel[bodyA] = make_float4(vA.x, vA.y, wA, 0.0f);
+                bodyVel[bodyB] = make_float4(vB.x, vB.y, wB, 0.0f);
+            }
+        }
+
+        // ---- StoreImpulses (b2ContactSolver.cpp:599-612) + Report/PostSolve (b2Island.cpp:517-540) ----
+        for (int i = c0; i < c1; ++i) {
+            const size_t o = (size_t)i * kVcStride;
+            const int k = iContacts[i];
+            const float4 imp = vc[o + 8];
+            const int vcPointCount = __float_as_int(vc[o + 3].w) & 0xff;
+            float4 p0 = cP0[k];
+            p0.z = imp.x;
+            p0.w = imp.y;
+            cP0[k] = p0;
+            if (vcPointCount > 1) {
+                float4 p1 = cP1[k];
+                p1.z = imp.z;
+                p1.w = imp.w;
+                cP1[k] = p1;
+            }
+        }
+
+        // ---- integrate positions (b2Island.cpp:276-306) ----
+        for (int i = b0; i < b1; ++i) {
+            int b = iBodies[i];
+            if ((bodyFlags[b] & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+            float4 sw = bodySweep[b];
+            float4 vel = bodyVel[b];
+            Vec2 c = V2(sw.x, sw.y);
+            float a = sw.z;
+            Vec2 v = V2(vel.x, vel.y);
+            float wv = vel.z;
+            Vec2 translation = h * v;
+            if (Dot(translation, translation) > kMaxTranslationSquared) {
+                float ratio = Div(kMaxTranslation, Length(translation));
+                v = ratio * v;
+            }
+            float rotation = h * wv;
+            if (rotation * rotation > kMaxRotationSquared) {
+                float ratio = Div(kMaxRotation, Abs(rotation));
+                wv *= ratio;
+            }
+            c = c + h * v;
+            a += h * wv;
+            bodySweep[b] = make_float4(c.x, c.y, a, sw.w);
+            bodyVel[b] = make_float4(v.x, v.y, wv, 0.0f);
+        }
+
+        // ---- SolvePositionConstraints (b2Island.cpp:308-328, b2ContactSolver.cpp:614-744) ----
+        bool positionSolved = false;
+        for (int it = 0; it < posIters; ++it) {
+            float minSeparation = 0.0f;
+            for (int i = c0; i < c1; ++i) {
+                const size_t o = (size_t)i * kVcStride;
+                const int k = iContacts[i];
+                const float4 q0 = vc[o + 0], q1 = vc[o + 1];
+                const float radiusA = vc[o + 5].w, radiusB = vc[o + 7].w;
+                const int counts = __float_as_int(vc[o + 3].w);
+                const int pointCount = (counts >> 8) & 0xff;  // pc->pointCount is the manifold's
+                const int bodies = __float_as_int(q0.w);
+                const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
+                const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
+                const int mtype = cA[k].w & 0xff;
+                const float4 nn = cN[k];
+                const float4 p0 = cP0[k];
+                const float4 msA = bodyMass[bodyA], msB = bodyMass[bodyB];
+                const Vec2 localCenterA = V2(msA.z, msA.w), localCenterB = V2(msB.z, msB.w);
+                float4 swA = bodySweep[bodyA], swB = bodySweep[bodyB];
+                Vec2 cAp = V2(swA.x, swA.y), cBp = V2(swB.x, swB.y);
+                float aA = swA.z, aB = swB.z;
+                const Vec2 localNormal = V2(nn.x, nn.y), localPoint = V2(nn.z, nn.w);
+                for (int j = 0; j < pointCount; ++j) {
+                    Vec2 lp = V2(p0.x, p0.y);
+                    if (j == 1) {
+                        float4 p1 = cP1[k];
+                        lp = V2(p1.x, p1.y);
+                    }
+                    Xf xfA, xfB;
+                    xfA.q = MakeRot(aA);
+                    xfB.q = MakeRot(aB);
+                    xfA.p = cAp - Mul(xfA.q, localCenterA);
+                    xfB.p = cBp - Mul(xfB.q, localCenterB);
+                    Vec2 normal, point;
+                    float separation;
+                    if (mtype == kManifoldCircles) {
+                        Vec2 pointA = Mul(xfA, localPoint);
+                        Vec2 pointB = Mul(xfB, lp);
+                        normal = pointB - pointA;
+                        Normalize(normal);
+                        point = 0.5f * (pointA + pointB);
+                        separation = Dot(pointB - pointA, normal) - radiusA - radiusB;
+                    } else if (mtype == kManifoldFaceA) {
+                        normal = Mul(xfA.q, localNormal);
+                        Vec2 planePoint = Mul(xfA, localPoint);
+                        Vec2 clipPoint = Mul(xfB, lp);
+                        separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+                        point = clipPoint;
+                    } else {
+                        normal = Mul(xfB.q, localNormal);
+                        Vec2 planePoint = Mul(xfB, localPoint);
+                        Vec2 clipPoint = Mul(xfA, lp);
+                        separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+                        point = clipPoint;
+                        normal = -normal;
+                    }
+                    Vec2 rA = point - cAp;
+                    Vec2 rB = point - cBp;
+                    minSeparation = Min(minSeparation, separation);
+                    float C = Clamp(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+                    float rnA = Cross(rA, normal);
+                    float rnB = Cross(rB, normal);
+                    float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                    float impulse = K > 0.0f ? Div(-C, K) : 0.0f;
+                    Vec2 P = impulse * normal;
+                    cAp = cAp - mA * P;
+                    aA -= iA * Cross(rA, P);
+                    cBp = cBp + mB * P;
+                    aB += iB * Cross(rB, P);
+                }
+                bodySweep[bodyA] = make_float4(cAp.x, cAp.y, aA, swA.w);
+                bodySweep[bodyB] = make_float4(cBp.x, cBp.y, aB, swB.w);
+            }
+            if (minSeparation >= -3.0f * kLinearSlop) {
+                positionSolved = true;
+                break;
+            }
+        }
+
+        // ---- write back: SynchronizeTransform (b2Island.cpp:331-339, b2Body.h:835-839) ----
+        for (int i = b0; i < b1; ++i) {
+            int b = iBodies[i];
+            if ((bodyFlags[b] & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+            float4 sw = bodySweep[b];
+            float4 ms = bodyMass[b];
+            Rot q = MakeRot(sw.z);
+            Vec2 p = V2(sw.x, sw.y) - Mul(q, V2(ms.z, ms.w));
+            bodyXf[b] = make_float4(p.x, p.y, q.s, q.c);
+        }
+
+        // ---- Report: PostSolve ----
+        if (A.eventMask >> kEventPostSolve & 1) {
+            for (int i = c0; i < c1; ++i) {
+                const size_t o = (size_t)i * kVcStride;
+                const int k = iContacts[i];
+                const float4 imp = vc[o + 8];
+                const int vcPointCount = __float_as_int(vc[o + 3].w) & 0xff;
+                const int4 a = cA[k];
+                int pa = proxyInfo[a.x & 0xffff], pb = proxyInfo[(a.x >> 16) & 0xffff];
+                float4 e = make_float4(imp.x, vcPointCount > 1 ? imp.z : 0.0f, imp.y, vcPointCount > 1 ? imp.w : 0.0f);
+                ev.push(kEventPostSolve, pa & 0xffff, (pa >> 16) & 0xffff, pb & 0xffff, (pb >> 16) & 0xffff, vcPointCount, e);
+            }
+        }
+
+        // ---- sleep (b2Island.cpp:345-382) ----
+        if (allowSleep) {
+            float minSleepTime = kMaxFloat;
+            const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
+            const float angTolSqr = kAngularSleepTolerance * kAngularSleepTolerance;
+            for (int i = b0; i < b1; ++i) {
+                int b = iBodies[i];
+                int f = bodyFlags[b];
+                if ((f & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+                float4 vel = bodyVel[b];
+                float4 sw = bodySweep[b];
+                if ((f & kBodyAutoSleep) == 0 || vel.z * vel.z > angTolSqr || Dot(V2(vel.x, vel.y), V2(vel.x, vel.y)) > linTolSqr) {
+                    sw.w = 0.0f;
+                    minSleepTime = 0.0f;
+                } else {
+                    sw.w += h;
+                    minSleepTime = Min(minSleepTime, sw.w);
+                }
+                bodySweep[b] = sw;
+            }
+            if (minSleepTime >= kTimeToSleep && positionSolved) {
+                for (int i = b0; i < b1; ++i) {  // b2Body::SetAwake(false), b2Body.h:644-652
+                    int b = iBodies[i];
+                    bodyFlags[b] &= ~kBodyAwake;
+                    float4 sw = bodySweep[b];
+                    sw.w = 0.0f;
+                    bodySweep[b] = sw;
+                    bodyVel[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    bodyForce[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+            }
+        }
+        b0 = b1;
+        c0 = c1;
+    }
+}
+
+// =================================================================================================
+// k_sync_pairs
+// =================================================================================================
+// b2ContactFilter::ShouldCollide — Dynamics/b2WorldCallbacks.cpp:26-39
+__device__ __forceinline__ bool FilterShouldCollide(int2 fa, int2 fb) {
+    int groupA = fa.y, groupB = fb.y;
+    if (groupA == groupB && groupA != 0) return groupA > 0;
+    int catA = fa.x & 0xffff, maskA = (fa.x >> 16) & 0xffff;
+    int catB = fb.x & 0xffff, maskB = (fb.x >> 16) & 0xffff;
+    return (maskA & catB) != 0 && (catA & maskB) != 0;
+}
+
+// b2Contact::s_registers (b2Contact.cpp:42-76): 0 = no contact class, 1 = primary, 2 = swapped
+__device__ __forceinline__ int ContactRegister(int t1, int t2) {
+    if (t2 == B2G_SHAPE_CIRCLE) return 1;                                   // circle/edge/polygon/chain vs circle
+    if (t2 == B2G_SHAPE_POLYGON) return t1 == B2G_SHAPE_CIRCLE ? 2 : 1;     // polygon, edge, chain vs polygon
+    // t2 is edge or chain
+    if (t1 == B2G_SHAPE_CIRCLE || t1 == B2G_SHAPE_POLYGON) return 2;
+    return 0;
+}
+
+struct PairCtx {
+    const Arena& A;
+    int tile, lane;
+    size_t ws;
+    Col<int4> cA, cK;
+    Col<int2> cS;
+    Col<int> proxyInfo, fixtureInfo, fixtureShape, bodyFlags, adjStart, adj;
+    Col<float2> fixtureMat;
+    Col<int2> fixtureFilter;
+    Col<float4> bodySweep;
+    int nc;          // running contact count
+    int ncAtStart;   // contacts that existed before this UpdatePairs
+    bool useCsr;
+};
+
+// b2ContactManager::AddPair for proxies a < b (ascending tree id)
+__device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB) {
+    int pa = c.proxyInfo[proxyA], pb = c.proxyInfo[proxyB];
+    int fixtureA = pa & 0xffff, fixtureB = pb & 0xffff;
+    int fiA = c.fixtureInfo[fixtureA], fiB = c.fixtureInfo[fixtureB];
+    int bodyA = fiA & 0xffff, bodyB = fiB & 0xffff;
+    if (bodyA == bodyB) return;
+    // does a contact already exist? (walk of bodyB's edge list in the reference)
+    const int key1 = proxyA | (proxyB << 16), key2 = proxyB | (proxyA << 16);
+    if (c.useCsr) {
+        int e0 = bodyB == 0 ? 0 : c.adjStart[bodyB - 1], e1 = c.adjStart[bodyB];
+        for (int e = e0; e < e1; ++e) {
+            int x = c.cA[c.adj[e]].x;
+            if (x == key1 || x == key2) return;
+        }
+    } else {
+        for (int k = 0; k < c.ncAtStart; ++k) {
+            int x = c.cA[k].x;
+            if (x == key1 || x == key2) return;
+        }
+    }
+    int bfA = c.bodyFlags[bodyA], bfB = c.bodyFlags[bodyB];
+    // b2Body::ShouldCollide (no joints): at least one dynamic body
+    if ((bfA & kBodyTypeMask) != B2G_DYNAMIC_BODY && (bfB & kBodyTypeMask) != B2G_DYNAMIC_BODY) return;
+    if (!FilterShouldCollide(c.fixtureFilter[fixtureA], c.fixtureFilter[fixtureB])) return;
+    int tA = (fiA >> 16) & 3, tB = (fiB >> 16) & 3;
+    int reg = ContactRegister(tA, tB);
+    if (reg == 0) return;
+    if (reg == 2) {
+        int t;
+        t = proxyA; proxyA = proxyB; proxyB = t;
+        t = fixtureA; fixtureA = fixtureB; fixtureB = t;
+        t = bodyA; bodyA = bodyB; bodyB = t;
+        t = tA; tA = tB; tB = t;
+    }
+    if (c.nc >= c.A.NC) {
+        c.A.status[c.ws] |= kStatusContactOverflow;
+        return;
+    }
+    float2 matA = c.fixtureMat[fixtureA], matB = c.fixtureMat[fixtureB];
+    float friction = Sqrt(matA.x * matB.x);                      // b2MixFriction
+    float restitution = matA.y > matB.y ? matA.y : matB.y;       // b2MixRestitution
+    int k = c.nc++;
+    c.cA[k] = make_int4(proxyA | (proxyB << 16), bodyA | (bodyB << 16), kContactEnabled, (tA | (tB << 2)) << 16);
+    c.cK[k] = make_int4(0, 0, __float_as_int(friction), __float_as_int(restitution));
+    c.cS[k] = make_int2(c.fixtureShape[fixtureA], c.fixtureShape[fixtureB]);
+    WakeBody(c.bodyFlags, c.bodySweep, bodyA);
+    WakeBody(c.bodyFlags, c.bodySweep, bodyB);
+}
+
+template <bool kSync>
+__global__ void __launch_bounds__(128) k_sync_pairs(Arena A, float dt, int useCsr) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int tile = w >> 5, lane = w & 31;
+    if (tile >= A.numTiles) return;
+    size_t ws = (size_t)tile * kTile + lane;
+    const int np = A.proxyCount[ws];
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+    Col<int> fixtureShape = col(A.fixtureShape, tile, A.NF, lane);
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    Col<float4> bodyXf = col(A.bodyXf, tile, A.NB, lane);
+    Col<float4> bodySweep0 = col(A.bodySweep0, tile, A.NB, lane);
+    Col<float4> bodyMass = col(A.bodyMass, tile, A.NB, lane);
+    Col<float2> chainVerts = col(A.chainVerts, tile, A.NV, lane);
+    Col<int> movedList = col(A.movedList, tile, A.NP, lane);
+
+    if (kSync) {
+        for (int p = 0; p < np; ++p) {
+            int pi = proxyInfo[p];
+            int fixture = pi & 0xffff, child = (pi >> 16) & 0xffff;
+            int fi = fixtureInfo[fixture];
+            int body = fi & 0xffff;
+            int bf = bodyFlags[body];
+            if ((bf & kBodyIsland) == 0) continue;          // not in an island: did not move
+            if ((bf & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+            int shapeType = (fi >> 16) & 3;
+            const float* sw = A.shapeWords + ((size_t)tile * A.NS + fixtureShape[fixture]) * kTile + lane;
+            float4 s0 = bodySweep0[body];
+            float4 ms = bodyMass[body];
+            Xf xf1;
+            xf1.q = MakeRot(s0.z);
+            xf1.p = V2(s0.x, s0.y) - Mul(xf1.q, V2(ms.z, ms.w));
+            Xf xf2 = LoadXf(bodyXf, body);
+            Vec2 lo1, hi1, lo2, hi2;
+            ShapeAABB(sw, shapeType, chainVerts, child, xf1, &lo1, &hi1);
+            ShapeAABB(sw, shapeType, chainVerts, child, xf2, &lo2, &hi2);
+            Vec2 lo = Min(lo1, lo2), hi = Max(hi1, hi2);
+            Vec2 displacement = xf2.p - xf1.p;
+            float4 fat = proxyFat[p];
+            // b2AABB::Contains
+            bool contains = fat.x <= lo.x && fat.y <= lo.y && hi.x <= fat.z && hi.y <= fat.w;
+            if (contains) continue;
+            Vec2 r = V2(kAabbExtension, kAabbExtension);
+            lo = lo - r;
+            hi = hi + r;
+            Vec2 d = kAabbMultiplier * displacement;
+            if (d.x < 0.0f) lo.x += d.x; else hi.x += d.x;
+            if (d.y < 0.0f) lo.y += d.y; else hi.y += d.y;
+            proxyFat[p] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            proxyMoved[p] = 1;
+        }
+    }
+
+    // ---- b2BroadPhase::UpdatePairs: pairs are produced directly in (proxyIdA, proxyIdB) order ----
+    int nMoved = 0;
+    for (int p = 0; p < np; ++p) {
+        if (proxyMoved[p]) {
+            movedList[nMoved++] = p;
+            proxyMoved[p] = 0;
+        }
+    }
+    if (nMoved > 0) {
+        PairCtx c{A, tile, lane, ws,
+                  col(A.contactA, tile, A.NC, lane), col(A.contactK, tile, A.NC, lane), col(A.contactS, tile, A.NC, lane),
+                  proxyInfo, fixtureInfo, fixtureShape, bodyFlags,
+                  col(A.bodyAdjStart, tile, A.NB + 1, lane), col(A.bodyAdj, tile, 2 * A.NC, lane),
+                  col(A.fixtureMat, tile, A.NF, lane), col(A.fixtureFilter, tile, A.NF, lane),
+                  col(A.bodySweep, tile, A.NB, lane), 0, 0, useCsr != 0};
+        c.nc = A.contactCount[ws];
+        c.ncAtStart = c.nc;
+        int mi = 0;  // first moved proxy with index > a
+        for (int a = 0; a < np; ++a) {
+            while (mi < nMoved && movedList[mi] <= a) ++mi;
+            bool aMoved = mi > 0 && movedList[mi - 1] == a;
+            float4 fatA = proxyFat[a];
+            if (aMoved) {
+                for (int b = a + 1; b < np; ++b)
+                    if (FatOverlap(proxyFat[b], fatA)) AddPair(c, a, b);
+            } else {
+                for (int m = mi; m < nMoved; ++m) {
+                    int b = movedList[m];
+                    if (FatOverlap(fatA, proxyFat[b])) AddPair(c, a, b);
+                }
+            }
+        }
+        A.contactCount[ws] = c.nc;
+    }
+    if (kSync) {
+        if (dt > 0.0f) A.invDt0[ws] = Div(1.0f, dt);
+        A.stepCount[ws] += 1;
+    }
+}
+
+}  // namespace b2g

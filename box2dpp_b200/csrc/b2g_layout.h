@@ -1,0 +1,134 @@
+// b2g_layout.h — the world-interleaved SoA arenas that replace the reference's
+// b2BlockAllocator / b2StackAllocator (Box2D/Common/b2BlockAllocator.cpp, b2StackAllocator.cpp).
+//
+// Worlds are grouped in tiles of 32 (one warp).  Every per-world array of `cap` elements is stored
+// as  elem[(tile * cap + item) * 32 + lane]  with lane = world % 32, so a warp whose lanes are 32
+// consecutive worlds reads item i of a field as one contiguous 128 B (4 B elements) or 512 B
+// (16 B elements) segment: fully coalesced and vectorised, and a whole tile of a field is one
+// contiguous block (the unit a TMA bulk copy moves).
+//
+// Persistent per-world state follows SURVEY.md Appendix E; temporaries of the island solver
+// (b2Island / b2ContactSolver stack allocations) live in the same arena and are reused every step.
+#pragma once
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#else
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+#endif
+
+namespace b2g {
+
+constexpr int kTile = 32;  // worlds per tile = lanes per warp
+
+// body flag bits (bodyFlags); low 2 bits hold b2BodyType (Box2D/Dynamics/b2Body.h:41-49, 408-417)
+enum : int {
+    kBodyTypeMask = 3,
+    kBodyIsland = 1 << 2,
+    kBodyAwake = 1 << 3,
+    kBodyAutoSleep = 1 << 4,
+    kBodyBullet = 1 << 5,
+    kBodyFixedRotation = 1 << 6,
+    kBodyActive = 1 << 7,
+};
+// contact flag bits (Box2D/Dynamics/Contacts/b2Contact.h:155-174)
+enum : int { kContactIsland = 1, kContactTouching = 2, kContactEnabled = 4, kContactFilter = 8, kContactDead = 16 };
+// per-world status bits surfaced by b2gpu_batch_read_status
+enum : int {
+    kStatusContactOverflow = 1,
+    kStatusEventOverflow = 2,
+};
+// event types in the readback buffer (b2ContactListener, Box2D/Dynamics/b2WorldCallbacks.h:74-120)
+enum : int { kEventBegin = 0, kEventEnd = 1, kEventPreSolve = 2, kEventPostSolve = 3 };
+
+// Words per shape in the shape table (see b2g_host.cpp for the writer):
+//   polygon: [count, radius, centroid.xy, vertex0.xy .. , normal0.xy ..]          4 + 4*count words
+//   circle : [radius, p.xy]                                                        3 words
+//   edge   : [radius, v0.xy, v1.xy, v2.xy, v3.xy, has0 | has3 << 1]               10 words
+//   chain  : [radius, firstVertex, count, prev.xy, next.xy, hasPrev | hasNext<<1]  8 words (+ vertices in chainVerts)
+
+struct Arena {
+    int numWorlds, numTiles;
+    // capacities per world
+    int NB, NF, NP, NC, NS, NV, NE;
+
+    // ---- world scalars [tile][lane] ----
+    float2* gravity;
+    int* worldFlags;     // B2G_WORLD_* (include/b2g_scene.h)
+    float* invDt0;       // b2World::m_inv_dt0
+    int* bodyCount;
+    int* proxyCount;
+    int* contactCount;
+    int* status;         // kStatus*
+    int* eventCount;
+    int* islandCount;    // last step (diagnostics)
+    int* stepCount;
+
+    // ---- bodies [tile][NB][lane] ----
+    float4* bodyXf;      // m_xf: p.x p.y q.s q.c
+    float4* bodySweep;   // m_sweep.c.xy, m_sweep.a, m_sleepTime
+    float4* bodySweep0;  // m_sweep.c0.xy, m_sweep.a0, (unused)
+    float4* bodyVel;     // m_linearVelocity.xy, m_angularVelocity, (unused)
+    float4* bodyForce;   // m_force.xy, m_torque, (unused)
+    float4* bodyMass;    // m_invMass, m_invI, localCenter.xy
+    float4* bodyDamp;    // m_linearDamping, m_angularDamping, m_gravityScale, (unused)
+    int* bodyFlags;      // type | kBody*
+    int* bodyIsland;     // island id of this step (-1 = none)
+
+    // ---- fixtures [tile][NF][lane] ----
+    int* fixtureInfo;    // body | shapeType << 16 | isSensor << 18
+    int* fixtureShape;   // word offset into shapeWords
+    float2* fixtureMat;  // friction, restitution
+    int2* fixtureFilter; // categoryBits | maskBits << 16, groupIndex
+
+    // ---- proxies [tile][NP][lane] (creation order == ascending tree id) ----
+    float4* proxyFat;    // fat AABB lo.xy hi.xy (b2TreeNode::aabb)
+    int* proxyInfo;      // fixture | child << 16
+    int* proxyMoved;     // 1 = in the move buffer
+
+    // ---- shapes ----
+    float* shapeWords;   // [tile][NS][lane]
+    float2* chainVerts;  // [tile][NV][lane]
+
+    // ---- contacts [tile][NC][lane], array order = creation order, list order = reverse ----
+    int4* contactA;      // proxyA | proxyB << 16, bodyA | bodyB << 16, flags,
+                         // manifold type | pointCount << 8 | shapeTypeA << 16 | shapeTypeB << 18
+    int4* contactK;      // key0, key1, friction bits, restitution bits
+    int2* contactS;      // shape-table offsets of fixture A / fixture B (cached at creation)
+    float4* contactP0;   // points[0]: localPoint.xy, normalImpulse, tangentImpulse
+    float4* contactP1;   // points[1]
+    float4* contactN;    // localNormal.xy, localPoint.xy
+
+    // ---- per-step temporaries ----
+    int* bodyAdjStart;   // [tile][NB+1][lane] CSR of contact edges per body (newest first)
+    int* bodyAdj;        // [tile][2*NC][lane] contact index per edge
+    int* dfsStack;       // [tile][NB][lane]
+    int* movedList;      // [tile][NP][lane] ascending indices of the proxies in the move buffer
+    int* islandBodies;   // [tile][NB+NC][lane] bodies of all islands, concatenated (statics repeat)
+    int* islandBodyEnd;  // [tile][NB][lane]   end offset into islandBodies per island
+    int* islandContacts; // [tile][NC][lane]   contact indices in solver order, concatenated
+    int* islandContactEnd; // [tile][NB][lane]
+    // b2ContactVelocityConstraint, 9 x 16 B per island contact: [tile][NC*9][lane]
+    float4* vc;
+
+    // ---- events [tile][NE][lane] ----
+    int4* eventA;        // type, fixtureA | childA << 16, fixtureB | childB << 16, count
+    float4* eventB;      // normalImpulses[2], tangentImpulses[2]
+    int eventMask;       // bit per kEvent* type recorded
+};
+
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+size_t TileIndex(int tile, int cap, int item, int lane) {
+    return ((size_t)tile * (size_t)cap + (size_t)item) * kTile + (size_t)lane;
+}
+
+}  // namespace b2g

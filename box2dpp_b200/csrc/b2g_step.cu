@@ -1,0 +1,468 @@
+// b2g_step.cu — device layer of libb2gpu.so: arena allocation, field transfer, kernel launches and the
+// b2gpu_batch_* C ABI declared in include/b2gpu.h.  Build: nvcc -gencode arch=compute_100a,code=sm_100a
+// --fmad=false -prec-div=true -prec-sqrt=true -ftz=false (see __graft_entry__.py).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b2gpu.h"
+#include "b2g_kernels.cuh"
+
+using namespace b2g;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) return fail(B2GPU_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct Field {
+    void** dev;      // address of the arena pointer
+    int capacity;    // items per world
+    int components;  // 32-bit words per item
+};
+
+// world-major host layout <-> tile-interleaved arena; one thread per (world, item, component)
+__global__ void k_interleave(uint32_t* __restrict__ arena, const uint32_t* __restrict__ flat, int cap, int comps,
+                             int firstWorld, int worldCount, int toArena) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)worldCount * cap * comps;
+    if (idx >= total) return;
+    int c = (int)(idx % comps);
+    size_t r = idx / comps;
+    int item = (int)(r % cap);
+    int wl = (int)(r / cap);
+    int w = firstWorld + wl;
+    size_t a = (((size_t)(w >> 5) * cap + item) * kTile + (w & 31)) * comps + c;
+    if (toArena) arena[a] = flat[idx];
+    else const_cast<uint32_t*>(flat)[idx] = arena[a];
+}
+
+// b2Body::ApplyForceToCenter / ApplyTorque for every body (Box2D/Dynamics/b2Body.h:738-790):
+// wake on a non-zero force, then accumulate if awake.
+__global__ void k_apply_forces(Arena A, const float* __restrict__ forces) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // lane-fastest: (tile, body, lane)
+    size_t total = (size_t)A.numTiles * A.NB * kTile;
+    if (idx >= total) return;
+    int lane = (int)(idx & 31);
+    size_t r = idx >> 5;
+    int body = (int)(r % A.NB);
+    int tile = (int)(r / A.NB);
+    int w = tile * kTile + lane;
+    if (w >= A.numWorlds || body >= A.bodyCount[(size_t)tile * kTile + lane]) return;
+    const float* f = forces + ((size_t)w * A.NB + body) * 3;
+    float fx = f[0], fy = f[1], tq = f[2];
+    if (fx == 0.0f && fy == 0.0f && tq == 0.0f) return;
+    int flags = A.bodyFlags[idx];
+    if ((flags & kBodyTypeMask) != B2G_DYNAMIC_BODY) return;
+    if ((flags & kBodyAwake) == 0) {
+        A.bodyFlags[idx] = flags | kBodyAwake;
+        A.bodySweep[idx].w = 0.0f;
+    }
+    float4 cur = A.bodyForce[idx];
+    A.bodyForce[idx] = make_float4(cur.x + fx, cur.y + fy, cur.z + tq, 0.0f);
+}
+
+// b2Body::GetTransform for every body, world-major output
+__global__ void k_read_transforms(Arena A, float4* __restrict__ out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)A.numTiles * A.NB * kTile;
+    if (idx >= total) return;
+    int lane = (int)(idx & 31);
+    size_t r = idx >> 5;
+    int body = (int)(r % A.NB);
+    int tile = (int)(r / A.NB);
+    int w = tile * kTile + lane;
+    if (w >= A.numWorlds) return;
+    out[(size_t)w * A.NB + body] = A.bodyXf[idx];
+}
+
+}  // namespace
+
+struct b2gpu_batch {
+    b2gpu_batch_desc desc;
+    Arena A;
+    cudaStream_t stream = nullptr;
+    std::vector<Field> fields;
+    std::vector<void*> allocations;
+    bool needInitialPairs = true;  // b2World::e_newFixture
+    int blockSize = 32;
+    int64_t launches = 0;
+    size_t arenaBytes = 0;
+    // graph of one step, keyed by its parameters
+    cudaGraphExec_t graphExec = nullptr;
+    float graphDt = 0.0f;
+    int graphVel = 0, graphPos = 0;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    float lastStepMs = 0.0f;
+    // per-step I/O staging
+    float* ioDev = nullptr;
+    size_t ioBytes = 0;
+};
+
+namespace {
+
+template <class T>
+int arenaAlloc(b2gpu_batch* b, T** ptr, size_t itemsPerWorld, size_t elemBytes) {
+    size_t bytes = (size_t)b->A.numTiles * kTile * itemsPerWorld * elemBytes;
+    if (bytes == 0) bytes = 16;
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    CUDA_TRY(cudaMemsetAsync(p, 0, bytes, b->stream));
+    b->allocations.push_back(p);
+    b->arenaBytes += bytes;
+    *ptr = (T*)p;
+    return B2GPU_OK;
+}
+
+#define ALLOC(ptr, items, T)                                                       \
+    do {                                                                           \
+        int rc__ = arenaAlloc(b, &b->A.ptr, (size_t)(items), sizeof(T));           \
+        if (rc__ != B2GPU_OK) return rc__;                                         \
+    } while (0)
+
+int allocateArena(b2gpu_batch* b) {
+    Arena& A = b->A;
+    const b2gpu_batch_desc& d = b->desc;
+    A.numWorlds = d.numWorlds;
+    A.numTiles = (d.numWorlds + kTile - 1) / kTile;
+    A.NB = d.maxBodies; A.NF = d.maxFixtures; A.NP = d.maxProxies; A.NC = d.maxContacts;
+    A.NS = d.maxShapeWords; A.NV = d.maxChainVerts > 0 ? d.maxChainVerts : 1; A.NE = d.maxEvents > 0 ? d.maxEvents : 1;
+    A.eventMask = d.eventMask;
+    ALLOC(gravity, 1, float2); ALLOC(worldFlags, 1, int); ALLOC(invDt0, 1, float);
+    ALLOC(bodyCount, 1, int); ALLOC(proxyCount, 1, int); ALLOC(contactCount, 1, int);
+    ALLOC(status, 1, int); ALLOC(eventCount, 1, int); ALLOC(islandCount, 1, int); ALLOC(stepCount, 1, int);
+    ALLOC(bodyXf, A.NB, float4); ALLOC(bodySweep, A.NB, float4); ALLOC(bodySweep0, A.NB, float4);
+    ALLOC(bodyVel, A.NB, float4); ALLOC(bodyForce, A.NB, float4); ALLOC(bodyMass, A.NB, float4);
+    ALLOC(bodyDamp, A.NB, float4); ALLOC(bodyFlags, A.NB, int); ALLOC(bodyIsland, A.NB, int);
+    ALLOC(fixtureInfo, A.NF, int); ALLOC(fixtureShape, A.NF, int); ALLOC(fixtureMat, A.NF, float2);
+    ALLOC(fixtureFilter, A.NF, int2);
+    ALLOC(proxyFat, A.NP, float4); ALLOC(proxyInfo, A.NP, int); ALLOC(proxyMoved, A.NP, int);
+    ALLOC(shapeWords, A.NS, float); ALLOC(chainVerts, A.NV, float2);
+    ALLOC(contactA, A.NC, int4); ALLOC(contactK, A.NC, int4); ALLOC(contactS, A.NC, int2);
+    ALLOC(contactP0, A.NC, float4); ALLOC(contactP1, A.NC, float4); ALLOC(contactN, A.NC, float4);
+    ALLOC(bodyAdjStart, A.NB + 1, int); ALLOC(bodyAdj, 2 * A.NC, int); ALLOC(dfsStack, A.NB, int);
+    ALLOC(movedList, A.NP, int);
+    ALLOC(islandBodies, A.NB + A.NC, int); ALLOC(islandBodyEnd, A.NB, int);
+    ALLOC(islandContacts, A.NC, int); ALLOC(islandContactEnd, A.NB, int);
+    ALLOC(vc, (size_t)A.NC * kVcStride, float4);
+    ALLOC(eventA, A.NE, int4); ALLOC(eventB, A.NE, float4);
+
+    b->fields.assign(B2GPU_F_COUNT, Field{nullptr, 0, 0});
+    auto F = [&](int id, void** p, int cap, int comps) { b->fields[id] = Field{p, cap, comps}; };
+    F(B2GPU_F_GRAVITY, (void**)&A.gravity, 1, 2);
+    F(B2GPU_F_WORLD_FLAGS, (void**)&A.worldFlags, 1, 1);
+    F(B2GPU_F_INV_DT0, (void**)&A.invDt0, 1, 1);
+    F(B2GPU_F_BODY_COUNT, (void**)&A.bodyCount, 1, 1);
+    F(B2GPU_F_PROXY_COUNT, (void**)&A.proxyCount, 1, 1);
+    F(B2GPU_F_CONTACT_COUNT, (void**)&A.contactCount, 1, 1);
+    F(B2GPU_F_STATUS, (void**)&A.status, 1, 1);
+    F(B2GPU_F_EVENT_COUNT, (void**)&A.eventCount, 1, 1);
+    F(B2GPU_F_ISLAND_COUNT, (void**)&A.islandCount, 1, 1);
+    F(B2GPU_F_STEP_COUNT, (void**)&A.stepCount, 1, 1);
+    F(B2GPU_F_BODY_XF, (void**)&A.bodyXf, A.NB, 4);
+    F(B2GPU_F_BODY_SWEEP, (void**)&A.bodySweep, A.NB, 4);
+    F(B2GPU_F_BODY_SWEEP0, (void**)&A.bodySweep0, A.NB, 4);
+    F(B2GPU_F_BODY_VEL, (void**)&A.bodyVel, A.NB, 4);
+    F(B2GPU_F_BODY_FORCE, (void**)&A.bodyForce, A.NB, 4);
+    F(B2GPU_F_BODY_MASS, (void**)&A.bodyMass, A.NB, 4);
+    F(B2GPU_F_BODY_DAMP, (void**)&A.bodyDamp, A.NB, 4);
+    F(B2GPU_F_BODY_FLAGS, (void**)&A.bodyFlags, A.NB, 1);
+    F(B2GPU_F_FIXTURE_INFO, (void**)&A.fixtureInfo, A.NF, 1);
+    F(B2GPU_F_FIXTURE_SHAPE, (void**)&A.fixtureShape, A.NF, 1);
+    F(B2GPU_F_FIXTURE_MAT, (void**)&A.fixtureMat, A.NF, 2);
+    F(B2GPU_F_FIXTURE_FILTER, (void**)&A.fixtureFilter, A.NF, 2);
+    F(B2GPU_F_PROXY_FAT, (void**)&A.proxyFat, A.NP, 4);
+    F(B2GPU_F_PROXY_INFO, (void**)&A.proxyInfo, A.NP, 1);
+    F(B2GPU_F_PROXY_MOVED, (void**)&A.proxyMoved, A.NP, 1);
+    F(B2GPU_F_SHAPE_WORDS, (void**)&A.shapeWords, A.NS, 1);
+    F(B2GPU_F_CHAIN_VERTS, (void**)&A.chainVerts, A.NV, 2);
+    F(B2GPU_F_CONTACT_A, (void**)&A.contactA, A.NC, 4);
+    F(B2GPU_F_CONTACT_K, (void**)&A.contactK, A.NC, 4);
+    F(B2GPU_F_CONTACT_S, (void**)&A.contactS, A.NC, 2);
+    F(B2GPU_F_CONTACT_P0, (void**)&A.contactP0, A.NC, 4);
+    F(B2GPU_F_CONTACT_P1, (void**)&A.contactP1, A.NC, 4);
+    F(B2GPU_F_CONTACT_N, (void**)&A.contactN, A.NC, 4);
+    F(B2GPU_F_EVENT_A, (void**)&A.eventA, A.NE, 4);
+    F(B2GPU_F_EVENT_B, (void**)&A.eventB, A.NE, 4);
+    F(B2GPU_F_ISLAND_CONTACTS, (void**)&A.islandContacts, A.NC, 1);
+    F(B2GPU_F_ISLAND_CONTACT_END, (void**)&A.islandContactEnd, A.NB, 1);
+    return B2GPU_OK;
+}
+
+int transferField(b2gpu_batch* b, int field, void* host, int firstWorld, int worldCount, bool toArena) {
+    if (!b || field < 0 || field >= B2GPU_F_COUNT || !host) return fail(B2GPU_ERR_INVALID, "bad field transfer arguments");
+    if (firstWorld < 0 || worldCount < 0 || firstWorld + worldCount > b->desc.numWorlds)
+        return fail(B2GPU_ERR_INVALID, "world range [%d, %d) outside the batch", firstWorld, firstWorld + worldCount);
+    if (worldCount == 0) return B2GPU_OK;
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    const Field& f = b->fields[field];
+    size_t words = (size_t)worldCount * f.capacity * f.components;
+    size_t bytes = words * 4;
+    uint32_t* staging = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&staging, bytes));
+    int threads = 256;
+    unsigned blocks = (unsigned)((words + threads - 1) / threads);
+    cudaError_t e = cudaSuccess;
+    if (toArena) {
+        e = cudaMemcpyAsync(staging, host, bytes, cudaMemcpyHostToDevice, b->stream);
+        if (e == cudaSuccess) {
+            k_interleave<<<blocks, threads, 0, b->stream>>>((uint32_t*)*f.dev, staging, f.capacity, f.components, firstWorld,
+                                                            worldCount, 1);
+            e = cudaGetLastError();
+        }
+    } else {
+        k_interleave<<<blocks, threads, 0, b->stream>>>((uint32_t*)*f.dev, staging, f.capacity, f.components, firstWorld,
+                                                        worldCount, 0);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host, staging, bytes, cudaMemcpyDeviceToHost, b->stream);
+    }
+    b->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    cudaFree(staging);
+    if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "field transfer failed: %s", cudaGetErrorString(e));
+    return B2GPU_OK;
+}
+
+// One b2World::Step for the whole batch (Box2D/Dynamics/b2World.cpp:888-954), TOI excluded.
+int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks) {
+    const int threads = b->blockSize;
+    const unsigned blocks = (unsigned)(((size_t)b->A.numTiles * kTile + threads - 1) / threads);
+    if (b->needInitialPairs) {  // if (m_flags & e_newFixture) FindNewContacts()
+        k_sync_pairs<false><<<blocks, threads, 0, b->stream>>>(b->A, dt, 0);
+        b->needInitialPairs = false;
+        b->launches++;
+    }
+    if (marks) cudaEventRecord(marks[0], b->stream);
+    k_collide<<<blocks, threads, 0, b->stream>>>(b->A);
+    b->launches++;
+    if (marks) cudaEventRecord(marks[1], b->stream);
+    if (dt > 0.0f) {
+        k_islands<<<blocks, threads, 0, b->stream>>>(b->A);
+        if (marks) cudaEventRecord(marks[2], b->stream);
+        k_solve<<<blocks, threads, 0, b->stream>>>(b->A, dt, velIters, posIters);
+        if (marks) cudaEventRecord(marks[3], b->stream);
+        k_sync_pairs<true><<<blocks, threads, 0, b->stream>>>(b->A, dt, 1);
+        if (marks) cudaEventRecord(marks[4], b->stream);
+        b->launches += 3;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return B2GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2gpu_last_error(void) { return g_error.c_str(); }
+
+// lets the host layer (b2g_host.cpp) report through the same thread-local message
+int b2gpu_host_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
+int b2gpu_batch_create(const b2gpu_batch_desc* desc, b2gpu_batch** out) {
+    if (!desc || !out) return fail(B2GPU_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B2GPU_ERR_NO_DEVICE, "no CUDA device available (%s); box2dpp_b200 has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (desc->device < 0 || desc->device >= count) return fail(B2GPU_ERR_INVALID, "device %d out of range", desc->device);
+    if (desc->numWorlds <= 0 || desc->maxBodies <= 0 || desc->maxFixtures <= 0 || desc->maxProxies <= 0 ||
+        desc->maxContacts <= 0 || desc->maxShapeWords <= 0)
+        return fail(B2GPU_ERR_INVALID, "capacities must be positive");
+    if (desc->maxBodies > 65535 || desc->maxFixtures > 65535 || desc->maxProxies > 65535)
+        return fail(B2GPU_ERR_CAPACITY, "bodies, fixtures and proxies per world are limited to 65535");
+    if (desc->blockSize != 0 && (desc->blockSize % 32 != 0 || desc->blockSize > 128))
+        return fail(B2GPU_ERR_INVALID, "blockSize must be 32, 64, 96 or 128");
+    CUDA_TRY(cudaSetDevice(desc->device));
+    b2gpu_batch* b = new b2gpu_batch;
+    b->desc = *desc;
+    b->blockSize = desc->blockSize ? desc->blockSize : 32;
+    memset(&b->A, 0, sizeof(b->A));
+    e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete b; return fail(B2GPU_ERR_CUDA, "stream create failed: %s", cudaGetErrorString(e)); }
+    int rc = allocateArena(b);
+    if (rc == B2GPU_OK) {
+        e = cudaEventCreate(&b->evStart);
+        if (e == cudaSuccess) e = cudaEventCreate(&b->evStop);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+        if (e != cudaSuccess) rc = fail(B2GPU_ERR_CUDA, "batch setup failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != B2GPU_OK) { b2gpu_batch_destroy(b); return rc; }
+    *out = b;
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_destroy(b2gpu_batch* b) {
+    if (!b) return B2GPU_OK;
+    cudaSetDevice(b->desc.device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void* p : b->allocations) cudaFree(p);
+    if (b->ioDev) cudaFree(b->ioDev);
+    if (b->graphExec) cudaGraphExecDestroy(b->graphExec);
+    if (b->evStart) cudaEventDestroy(b->evStart);
+    if (b->evStop) cudaEventDestroy(b->evStop);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_upload_field(b2gpu_batch* b, int32_t field, const void* host, int32_t firstWorld, int32_t worldCount) {
+    int rc = transferField(b, field, const_cast<void*>(host), firstWorld, worldCount, true);
+    // a freshly uploaded move buffer == b2World::e_newFixture: the next Step starts with FindNewContacts
+    if (rc == B2GPU_OK && field == B2GPU_F_PROXY_MOVED) b->needInitialPairs = true;
+    return rc;
+}
+int b2gpu_batch_download_field(b2gpu_batch* b, int32_t field, void* host, int32_t firstWorld, int32_t worldCount) {
+    return transferField(b, field, host, firstWorld, worldCount, false);
+}
+int b2gpu_batch_field_shape(b2gpu_batch* b, int32_t field, int32_t* capacity, int32_t* components) {
+    if (!b || field < 0 || field >= B2GPU_F_COUNT) return fail(B2GPU_ERR_INVALID, "bad field id");
+    if (capacity) *capacity = b->fields[field].capacity;
+    if (components) *components = b->fields[field].components;
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_step(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIters) {
+    if (!b) return fail(B2GPU_ERR_INVALID, "null batch");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    return enqueueStep(b, dt, velIters, posIters, nullptr);
+}
+
+int b2gpu_batch_step_n(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIters, int32_t steps) {
+    if (!b || steps < 0) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    if (steps == 0) return B2GPU_OK;
+    int done = 0;
+    CUDA_TRY(cudaEventRecord(b->evStart, b->stream));
+    if (b->needInitialPairs) {  // the first step also runs FindNewContacts: keep it out of the graph
+        int rc = enqueueStep(b, dt, velIters, posIters, nullptr);
+        if (rc != B2GPU_OK) return rc;
+        done = 1;
+    }
+    if (done < steps) {
+        if (!b->graphExec || b->graphDt != dt || b->graphVel != velIters || b->graphPos != posIters) {
+            if (b->graphExec) { cudaGraphExecDestroy(b->graphExec); b->graphExec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+            int64_t before = b->launches;
+            int rc = enqueueStep(b, dt, velIters, posIters, nullptr);
+            b->launches = before;
+            cudaError_t e = cudaStreamEndCapture(b->stream, &graph);
+            if (rc != B2GPU_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&b->graphExec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+            b->graphDt = dt; b->graphVel = velIters; b->graphPos = posIters;
+        }
+        const int perStep = dt > 0.0f ? 4 : 1;
+        for (; done < steps; ++done) {
+            CUDA_TRY(cudaGraphLaunch(b->graphExec, b->stream));
+            b->launches += perStep;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(b->evStop, b->stream));
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_sync(b2gpu_batch* b) {
+    if (!b) return fail(B2GPU_ERR_INVALID, "null batch");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_last_step_ms(b2gpu_batch* b, float* ms) {
+    if (!b || !ms) return fail(B2GPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    CUDA_TRY(cudaEventSynchronize(b->evStop));
+    CUDA_TRY(cudaEventElapsedTime(ms, b->evStart, b->evStop));
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_profile_steps(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIters, int32_t steps, float* ms) {
+    if (!b || !ms || steps <= 0) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    cudaEvent_t marks[5];
+    for (auto& m : marks) CUDA_TRY(cudaEventCreate(&m));
+    for (int i = 0; i < 4; ++i) ms[i] = 0.0f;
+    for (int s = 0; s < steps; ++s) {
+        int rc = enqueueStep(b, dt, velIters, posIters, marks);
+        if (rc != B2GPU_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        if (dt > 0.0f) {
+            for (int i = 0; i < 4; ++i) {
+                float t = 0.0f;
+                CUDA_TRY(cudaEventElapsedTime(&t, marks[i], marks[i + 1]));
+                ms[i] += t;
+            }
+        }
+    }
+    for (auto& m : marks) cudaEventDestroy(m);
+    return B2GPU_OK;
+}
+
+int64_t b2gpu_batch_launch_count(b2gpu_batch* b) { return b ? b->launches : 0; }
+
+static int ensureIo(b2gpu_batch* b) {
+    size_t need = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
+    if (b->ioBytes < need) {
+        if (b->ioDev) cudaFree(b->ioDev);
+        b->ioDev = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&b->ioDev, need));
+        b->ioBytes = need;
+    }
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_apply_forces(b2gpu_batch* b, const float* forces) {
+    if (!b || !forces) return fail(B2GPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    int rc = ensureIo(b);
+    if (rc != B2GPU_OK) return rc;
+    size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 3 * sizeof(float);
+    CUDA_TRY(cudaMemcpyAsync(b->ioDev, forces, bytes, cudaMemcpyHostToDevice, b->stream));
+    size_t total = (size_t)b->A.numTiles * b->A.NB * kTile;
+    k_apply_forces<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, b->ioDev);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_read_transforms(b2gpu_batch* b, float* out) {
+    if (!b || !out) return fail(B2GPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    int rc = ensureIo(b);
+    if (rc != B2GPU_OK) return rc;
+    size_t total = (size_t)b->A.numTiles * b->A.NB * kTile;
+    k_read_transforms<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, (float4*)b->ioDev);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
+    CUDA_TRY(cudaMemcpyAsync(out, b->ioDev, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+/*
+ * b2gpu.h — the drop-in boundary: a C ABI over the CUDA runtime for stepping a batch of
+ * independent Box2D worlds on one B200.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * The reference (ilektron/box2dpp) has no FFI layer: its boundary is the C++ class b2World.  Each
+ * entry point below names the reference interface it replaces; the C++ host class b2WorldBatch
+ * (box2dpp_b200/include/Box2D/Gpu/b2WorldBatch.h) keeps the reference's spelling on top of this ABI,
+ * and INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Two layers live in libb2gpu.so:
+ *   b2gpu_batch_*   device layer: arenas, kernels, field upload/download, per-step I/O.
+ *   b2gpu_scene_*   host layer: turns b2g_scene descriptions (the CreateBody/CreateFixture calls
+ *                   of the reference, include/b2g_scene.h) into arena fields (mass data, hulls, fat
+ *                   AABBs, proxy ids) exactly like b2Body/b2Fixture/b2PolygonShape do on the CPU.
+ *
+ * Error convention: every call returns B2GPU_OK (0) or a negative B2GPU_ERR_*; the message of the last
+ * failure on the calling thread is b2gpu_last_error().  The caller owns every host buffer; device
+ * memory is owned by the batch handle.  A handle is not thread-safe; distinct handles are.
+ * There is NO CPU fallback: without a usable CUDA device b2gpu_batch_create fails with
+ * B2GPU_ERR_NO_DEVICE.
+ */
+#ifndef B2GPU_H
+#define B2GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "b2g_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    B2GPU_OK = 0,
+    B2GPU_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product does not run on the CPU */
+    B2GPU_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    B2GPU_ERR_INVALID = -3,     /* bad argument */
+    B2GPU_ERR_UNSUPPORTED = -4, /* scene uses a feature outside the device path (sensors, TOI, joints) */
+    B2GPU_ERR_CAPACITY = -5     /* a per-world capacity in the descriptor is too small */
+};
+
+/* Event types in the readback buffer == b2ContactListener callbacks
+ * (Box2D/Dynamics/b2WorldCallbacks.h:74-120; call sites b2Contact.cpp:242-255, b2ContactManager.cpp:49-52,
+ * b2Island.cpp:517-540). */
+enum { B2GPU_EVENT_BEGIN = 0, B2GPU_EVENT_END = 1, B2GPU_EVENT_PRESOLVE = 2, B2GPU_EVENT_POSTSOLVE = 3 };
+
+/* Per-world status bits (b2gpu_batch_download_field(B2GPU_F_STATUS)). */
+enum { B2GPU_STATUS_CONTACT_OVERFLOW = 1, B2GPU_STATUS_EVENT_OVERFLOW = 2 };
+
+typedef struct b2gpu_batch b2gpu_batch;
+
+/* Replaces the allocators a b2World embeds (b2BlockAllocator / b2StackAllocator members,
+ * Box2D/Dynamics/b2World.h:254-256): fixed per-world capacities for the world-interleaved arenas. */
+typedef struct b2gpu_batch_desc {
+    int32_t device;        /* CUDA device ordinal */
+    int32_t numWorlds;
+    int32_t maxBodies;     /* per world */
+    int32_t maxFixtures;
+    int32_t maxProxies;
+    int32_t maxContacts;   /* contact list capacity; overflow sets B2GPU_STATUS_CONTACT_OVERFLOW */
+    int32_t maxShapeWords;
+    int32_t maxChainVerts;
+    int32_t maxEvents;     /* per world per step */
+    int32_t eventMask;     /* bit (1 << B2GPU_EVENT_*) per recorded event type; 0 = no listener */
+    int32_t blockSize;     /* threads per CTA, multiple of 32; 0 = default */
+    int32_t reserved;
+} b2gpu_batch_desc;
+
+/* Arena fields reachable through upload/download.  Host layout is world-major:
+ * host[(world * capacity + item) * components + c].  Component type is float unless noted. */
+enum {
+    B2GPU_F_GRAVITY = 0,        /* [W][1][2]                 b2World::m_gravity */
+    B2GPU_F_WORLD_FLAGS,        /* [W][1][1] int32           B2G_WORLD_* */
+    B2GPU_F_INV_DT0,            /* [W][1][1]                 b2World::m_inv_dt0 */
+    B2GPU_F_BODY_COUNT,         /* [W][1][1] int32 */
+    B2GPU_F_PROXY_COUNT,        /* [W][1][1] int32 */
+    B2GPU_F_CONTACT_COUNT,      /* [W][1][1] int32 */
+    B2GPU_F_STATUS,             /* [W][1][1] int32           B2GPU_STATUS_* */
+    B2GPU_F_EVENT_COUNT,        /* [W][1][1] int32 */
+    B2GPU_F_ISLAND_COUNT,       /* [W][1][1] int32 */
+    B2GPU_F_STEP_COUNT,         /* [W][1][1] int32 */
+    B2GPU_F_BODY_XF,            /* [W][NB][4]  m_xf: p.x p.y q.s q.c */
+    B2GPU_F_BODY_SWEEP,         /* [W][NB][4]  m_sweep.c.xy, m_sweep.a, m_sleepTime */
+    B2GPU_F_BODY_SWEEP0,        /* [W][NB][4]  m_sweep.c0.xy, m_sweep.a0, 0 */
+    B2GPU_F_BODY_VEL,           /* [W][NB][4]  m_linearVelocity.xy, m_angularVelocity, 0 */
+    B2GPU_F_BODY_FORCE,         /* [W][NB][4]  m_force.xy, m_torque, 0 */
+    B2GPU_F_BODY_MASS,          /* [W][NB][4]  m_invMass, m_invI, m_sweep.localCenter.xy */
+    B2GPU_F_BODY_DAMP,          /* [W][NB][4]  m_linearDamping, m_angularDamping, m_gravityScale, 0 */
+    B2GPU_F_BODY_FLAGS,         /* [W][NB][1] int32: type | island 4 | awake 8 | autoSleep 16 | bullet 32 | fixedRotation 64 | active 128 */
+    B2GPU_F_FIXTURE_INFO,       /* [W][NF][1] int32: body | shapeType << 16 | isSensor << 18 */
+    B2GPU_F_FIXTURE_SHAPE,      /* [W][NF][1] int32: word offset into the shape table */
+    B2GPU_F_FIXTURE_MAT,        /* [W][NF][2]  friction, restitution */
+    B2GPU_F_FIXTURE_FILTER,     /* [W][NF][2] int32: categoryBits | maskBits << 16, groupIndex */
+    B2GPU_F_PROXY_FAT,          /* [W][NP][4]  fat AABB lo.xy hi.xy */
+    B2GPU_F_PROXY_INFO,         /* [W][NP][1] int32: fixture | child << 16 */
+    B2GPU_F_PROXY_MOVED,        /* [W][NP][1] int32: 1 = in b2BroadPhase::m_moveBuffer */
+    B2GPU_F_SHAPE_WORDS,        /* [W][NS][1]  shape table (layout: box2dpp_b200/csrc/b2g_layout.h) */
+    B2GPU_F_CHAIN_VERTS,        /* [W][NV][2] */
+    B2GPU_F_CONTACT_A,          /* [W][NC][4] int32: proxyA|proxyB<<16, bodyA|bodyB<<16, flags, type|pointCount<<8|shapeTypes<<16 */
+    B2GPU_F_CONTACT_K,          /* [W][NC][4] int32: id.key of point 0, of point 1, friction bits, restitution bits */
+    B2GPU_F_CONTACT_S,          /* [W][NC][2] int32 */
+    B2GPU_F_CONTACT_P0,         /* [W][NC][4]  points[0]: localPoint.xy, normalImpulse, tangentImpulse */
+    B2GPU_F_CONTACT_P1,         /* [W][NC][4]  points[1] */
+    B2GPU_F_CONTACT_N,          /* [W][NC][4]  localNormal.xy, localPoint.xy */
+    B2GPU_F_EVENT_A,            /* [W][NE][4] int32: type, fixtureA|childA<<16, fixtureB|childB<<16, count */
+    B2GPU_F_EVENT_B,            /* [W][NE][4]  normalImpulses[2], tangentImpulses[2] */
+    B2GPU_F_ISLAND_CONTACTS,    /* [W][NC][1] int32: contact array index in solver order (last step) */
+    B2GPU_F_ISLAND_CONTACT_END, /* [W][NB][1] int32 */
+    B2GPU_F_COUNT
+};
+
+/* ---- device layer ------------------------------------------------------------------------------ */
+
+/* Replaces b2World::b2World(gravity) for a whole batch (Box2D/Dynamics/b2World.cpp:39-55): allocates the
+ * arenas on desc->device.  All counts start at zero. */
+int b2gpu_batch_create(const b2gpu_batch_desc* desc, b2gpu_batch** out);
+
+/* Replaces b2World::~b2World (b2World.cpp:57-76). */
+int b2gpu_batch_destroy(b2gpu_batch* batch);
+
+/* Copy a field for worlds [firstWorld, firstWorld + worldCount) between a world-major host buffer and the
+ * interleaved arena.  Replaces direct member access / getters of b2Body, b2Fixture, b2Contact
+ * (Box2D/Dynamics/b2Body.h:163-197, Contacts/b2Contact.h:92-139) and doubles as snapshot / restore. */
+int b2gpu_batch_upload_field(b2gpu_batch* batch, int32_t field, const void* host, int32_t firstWorld, int32_t worldCount);
+int b2gpu_batch_download_field(b2gpu_batch* batch, int32_t field, void* host, int32_t firstWorld, int32_t worldCount);
+/* Capacity (items per world) and components per item of a field. */
+int b2gpu_batch_field_shape(b2gpu_batch* batch, int32_t field, int32_t* capacity, int32_t* components);
+
+/* Replaces b2World::Step(dt, velocityIterations, positionIterations) (b2World.cpp:888-954) for every world
+ * of the batch.  Asynchronous on the batch's stream; b2gpu_batch_sync waits for it. */
+int b2gpu_batch_step(b2gpu_batch* batch, float dt, int32_t velocityIterations, int32_t positionIterations);
+/* Same, `steps` times, replayed from a captured CUDA graph. */
+int b2gpu_batch_step_n(b2gpu_batch* batch, float dt, int32_t velocityIterations, int32_t positionIterations, int32_t steps);
+int b2gpu_batch_sync(b2gpu_batch* batch);
+
+/* Per-step I/O for a caller that drives the batch (host buffers, pinned or not):
+ * apply_forces replaces b2Body::ApplyForceToCenter / ApplyTorque (Box2D/Dynamics/b2Body.h:738-790) for every
+ * body: forces[(world * maxBodies + body) * 3] = fx, fy, torque; non-zero entries wake the body.
+ * read_transforms replaces b2Body::GetPosition / GetAngle / GetTransform (b2Body.h:500-533):
+ * out[(world * maxBodies + body) * 4] = p.x, p.y, q.s, q.c. */
+int b2gpu_batch_apply_forces(b2gpu_batch* batch, const float* forces);
+int b2gpu_batch_read_transforms(b2gpu_batch* batch, float* out);
+
+/* CUDA-event time of the last b2gpu_batch_step_n in milliseconds, and per-kernel times of a profiled step. */
+int b2gpu_batch_last_step_ms(b2gpu_batch* batch, float* ms);
+/* Runs `steps` steps with CUDA events around each kernel; ms[4] = collide, islands, solve, sync_pairs totals. */
+int b2gpu_batch_profile_steps(b2gpu_batch* batch, float dt, int32_t velocityIterations, int32_t positionIterations,
+                              int32_t steps, float* ms);
+/* Number of kernel launches issued by this batch so far. */
+int64_t b2gpu_batch_launch_count(b2gpu_batch* batch);
+
+const char* b2gpu_last_error(void);
+
+/* ---- host layer -------------------------------------------------------------------------------- */
+
+/* Capacities a batch needs for these scenes (max over scenes; contacts/events are estimates the caller
+ * may raise).  Fills every max* field of desc. */
+int b2gpu_scene_capacities(const b2g_scene* scenes, int32_t sceneCount, b2gpu_batch_desc* desc);
+
+/* Replaces the b2World::CreateBody / b2Body::CreateFixture call sequence (b2World.cpp:98-122, b2Body.cpp:168-214)
+ * for worlds [firstWorld, firstWorld + sceneCount): world firstWorld + i is built from scenes[i].
+ * sceneCount == 1 with replicate > 1 builds `replicate` identical worlds. */
+int b2gpu_batch_build_worlds(b2gpu_batch* batch, const b2g_scene* scenes, int32_t sceneCount, int32_t firstWorld,
+                             int32_t replicate);
+
+/* Host-side shape math, exported for tests: b2PolygonShape::Set / SetAsBox / ComputeMass
+ * (Box2D/Collision/Shapes/b2PolygonShape.cpp:32-245, 354-437).  out: 8 vertices, 8 normals, centroid, then
+ * mass, center.xy, I (38 floats); returns the vertex count. */
+int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
