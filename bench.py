@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — batched b2World::Step throughput on B200 (BASELINE.json metric: world-steps/s).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU Step, all host cores
+
+Workload (config.workload): BASELINE.json configs[2] — 16,384 independent 20-row box-pyramid worlds per B200
+(weak scaling: every rank owns 16,384 worlds, sharded by world index, no collective on the step path),
+jittered per world so control flow diverges inside a warp, dt = 1/60, 8 velocity / 3 position iterations,
+sleeping off and continuous physics off on BOTH arms, contact events off on both arms.
+Worlds are pre-rolled 90 steps (untimed) so the timed steps run on the settled pyramid (~590 contacts,
+~400 touching per world), which is the expensive regime.
+
+One JSON line on stdout (rank 0).  `value` = device-timed world-steps/s with state resident in HBM;
+`e2e` = same metric through the C ABI with host buffers (forces H2D + transforms D2H every step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = 1.0 / 60.0
+ROWS = 20
+BODIES_DYNAMIC = ROWS * (ROWS + 1) // 2
+PREROLL = 90
+# algorithmic bytes per item per step
+BYTES_PER_DYNAMIC_BODY = 144
+BYTES_PER_PROXY = 84
+BYTES_PER_CONTACT = 188
+
+
+def flags_throughput():
+    from box2dpp_b200 import scene as S
+    return S.WORLD_DEFAULT & ~S.WORLD_CONTINUOUS & ~S.WORLD_ALLOW_SLEEP
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.window = index, [], False, None
+
+    def run(self):
+        while not self.stop_flag:
+            t = time.perf_counter()
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.samples.append((t, f))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        inside = [s for s in self.samples if self.window and self.window[0] <= s[0] <= self.window[1]]
+        if not inside and self.window:  # region shorter than one sample: take the closest one
+            mid = 0.5 * (self.window[0] + self.window[1])
+            inside = [min(self.samples, key=lambda s: abs(s[0] - mid))]
+        use = inside or self.samples
+        sm = sorted(float(s[1][0]) for s in use)
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for _, f in use:
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(use[0][1][1]), "reasons": sorted(reasons),
+                "samples": len(use), "power_w_max": max(float(s[1][2]) for s in use)}
+
+
+def cpu_reference_run(steps, warmup, threads=None, worlds_per_thread=16):
+    """The reference's own b2World::Step (vanilla Box2D compiled from /root/reference into oracle/_ref),
+    one world per thread slot on every host core.  Falls back to nothing: if oracle/_ref is absent the
+    C port is NOT a fair stand-in for speed, so we say so."""
+    from box2dpp_b200 import scene as S
+    from oracle import worlds  # TEST INFRASTRUCTURE: used only as the CPU baseline / reference arm
+    threads = threads or os.cpu_count()
+    n = threads * worlds_per_thread
+    sb = S.pyramid_batch(n, ROWS, flags=flags_throughput(), first_seed=0)
+    scenes = [sb.scene(i) for i in range(n)]
+    if not worlds.available("ref"):
+        return None
+    sec, _ = worlds.bench_run(scenes, worlds_per_thread, threads, steps, warmup, DT, 8, 3)
+    return {"value": n * steps / sec, "unit": "world-steps/s", "cores": threads, "kind": "reference",
+            "sample": f"{threads} threads x {worlds_per_thread} jittered pyramid-{ROWS} worlds, {warmup} warm-up + "
+                      f"{steps} timed steps, 8/3 iterations, sleeping off, TOI off, vanilla Box2D 2.3.2 -O2",
+            "seconds": sec, "worlds": n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--worlds-per-gpu", type=int, default=16384)
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--identical", action="store_true", help="identical worlds instead of jittered ones")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3)
+
+    config = {"workload": f"{args.worlds_per_gpu} {'identical' if args.identical else 'jittered'} pyramid-{ROWS} worlds "
+                          f"per GPU (BASELINE configs[2]), dt=1/60, 8 vel / 3 pos iterations",
+              "worlds_per_gpu": args.worlds_per_gpu, "dynamic_bodies_per_world": BODIES_DYNAMIC,
+              "sleeping": False, "continuous_physics": False, "warm_starting": True, "events": "off",
+              "preroll_steps": PREROLL, "sharding": f"world-index blocks x{args.gpus}, no collective",
+              "l2": "working set (~0.25 MB/world x worlds) far exceeds the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(args.steps, PREROLL + warmup)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libb2ref.so not built on this box"}))
+            return
+        line = {"impl": "reference", "metric": "world_steps_per_s", "value": r["value"], "unit": "world-steps/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "body_steps_per_s": r["value"] * BODIES_DYNAMIC,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    from box2dpp_b200 import scene as S
+    from box2dpp_b200.batch import F_CONTACT_COUNT, F_ISLAND_CONTACT_END, F_ISLAND_COUNT, WorldBatch
+
+    dist = None
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W = args.worlds_per_gpu
+    sb = S.pyramid_batch(W, ROWS, flags=flags_throughput(), first_seed=rank * W, jittered=not args.identical)
+    batch = WorldBatch(sb, device=local_rank, block_size=args.block)
+    batch.step_n(DT, 8, 3, PREROLL)
+    batch.sync()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    batch.step_n(DT, 8, 3, warmup)
+    batch.sync()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, barrier + sync on both sides ----
+    barrier()
+    launches0 = batch.launch_count()
+    t0 = time.perf_counter()
+    batch.step_n(DT, 8, 3, args.steps)
+    batch.sync()
+    t1 = time.perf_counter()
+    ms = batch.last_step_ms()
+    launches = batch.launch_count() - launches0
+    barrier()
+    sampler.window = (t0, t1)
+    ms = max_over_ranks(ms)
+    total_worlds = W * world_size
+    value = total_worlds * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers: forces H2D, step, transforms D2H, every step ----
+    import ctypes
+    e2e_steps = args.e2e_steps or max(10, min(args.steps, 100))
+    try:
+        import torch
+        forces_t = torch.zeros((W, batch.max_bodies, 3), dtype=torch.float32).pin_memory()
+        out_t = torch.empty((W, batch.max_bodies, 4), dtype=torch.float32).pin_memory()
+        forces, out = forces_t.numpy(), out_t.numpy()
+    except Exception:
+        forces = np.zeros((W, batch.max_bodies, 3), np.float32)
+        out = np.empty((W, batch.max_bodies, 4), np.float32)
+    for _ in range(3):
+        batch.apply_forces(forces); batch.step(DT, 8, 3); batch.read_transforms(out)
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.apply_forces(forces)
+        batch.step(DT, 8, 3)
+        batch.read_transforms(out)  # synchronises: the caller holds this step's transforms
+    t3 = time.perf_counter()
+    e2e_s = max_over_ranks(t3 - t2)
+    e2e = {"value": total_worlds * e2e_steps / e2e_s, "unit": "world-steps/s",
+           "h2d_bytes_per_step": int(forces.nbytes) * world_size, "d2h_bytes_per_step": int(out.nbytes) * world_size,
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- per-kernel times and the roofline of the dominant kernel (live CUDA events, same stream) ----
+    prof_steps = 10
+    kms = batch.profile_steps(DT, 8, 3, prof_steps)
+    contacts = batch.field(F_CONTACT_COUNT)[:, 0, 0].astype(np.float64)
+    nisl = batch.field(F_ISLAND_COUNT)[:, 0, 0]
+    iend = batch.field(F_ISLAND_CONTACT_END)[:, :, 0]
+    touching = np.array([iend[w, nisl[w] - 1] if nisl[w] > 0 else 0 for w in range(W)], dtype=np.float64)
+    alg_step = BODIES_DYNAMIC * BYTES_PER_DYNAMIC_BODY + (BODIES_DYNAMIC + 1) * BYTES_PER_PROXY + contacts.mean() * BYTES_PER_CONTACT
+    # the solver kernel owns all dynamic-body traffic and the manifolds of touching contacts
+    alg_solve = BODIES_DYNAMIC * BYTES_PER_DYNAMIC_BODY + touching.mean() * BYTES_PER_CONTACT
+    solve_ms = kms["solve"] / prof_steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_solve * W / (solve_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("k_solve_dram_bytes_per_launch")
+    except Exception:
+        pass
+    step_ms_sum = sum(kms.values()) / prof_steps
+    roofline = {"kernel": "k_solve", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": alg_solve * W, "kernel_ms": solve_ms,
+                "kernel_share_of_step": solve_ms / step_ms_sum,
+                "kernels_ms": {k: v / prof_steps for k, v in kms.items()},
+                "step_algorithmic_bytes_per_world": alg_step,
+                "step_achieved_gbs": alg_step * value / world_size / 1e9,
+                "step_frac": alg_step * value / world_size / 1e9 / peak,
+                "mean_contacts": float(contacts.mean()), "mean_touching_contacts": float(touching.mean())}
+
+    status_bad = int((batch.status() != 0).sum())
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_reference_run(200, PREROLL + 10)
+            if cpu:
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as exc:  # the baseline is a report, never a dependency of the GPU number
+            cpu = {"error": str(exc)}
+    batch.close()
+    if rank == 0:
+        line = {"metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": world_size,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "body_steps_per_s": value * BODIES_DYNAMIC, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
+                "worlds_with_overflow": status_bad}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-from .scene import CScene, FixtureDef, Scene, scene_array
+from .scene import CScene, FixtureDef, Scene, SceneBatch, scene_array
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2gpu.so")
@@ -103,18 +103,22 @@ class WorldBatch:
     def __init__(self, scenes, replicate=1, device=0, max_contacts=0, max_events=0, event_mask=0, block_size=0):
         if isinstance(scenes, Scene):
             scenes = [scenes]
-        self.scenes = list(scenes)
-        self.num_worlds = len(self.scenes) * replicate
+        if isinstance(scenes, SceneBatch):
+            self.scenes = scenes
+            arr, n_scenes = scenes.c_array, scenes.count
+        else:
+            self.scenes = list(scenes)
+            arr, n_scenes = scene_array(self.scenes), len(self.scenes)
+        self.num_worlds = n_scenes * replicate
         L = lib()
-        arr = scene_array(self.scenes)
         d = BatchDesc()
         d.device, d.numWorlds = device, self.num_worlds
         d.maxContacts, d.maxEvents, d.eventMask, d.blockSize = max_contacts, max_events, event_mask, block_size
-        _check(L.b2gpu_scene_capacities(arr, len(self.scenes), C.byref(d)))
+        _check(L.b2gpu_scene_capacities(arr, n_scenes, C.byref(d)))
         self.desc = d
         self.h = C.c_void_p()
         _check(L.b2gpu_batch_create(C.byref(d), C.byref(self.h)))
-        _check(L.b2gpu_batch_build_worlds(self.h, arr, len(self.scenes), 0, replicate))
+        _check(L.b2gpu_batch_build_worlds(self.h, arr, n_scenes, 0, replicate))
         self.max_bodies = d.maxBodies
         self._pinned = {}
 

@@ -307,3 +307,57 @@ def mixed(seed: int, flags=WORLD_DEFAULT, bodies=40) -> Scene:
                 poly.append((float(F32(r * np.cos(ang))), float(F32(r * np.sin(ang)))))
             s.create_polygon(b, poly, density=1.0)
     return s
+
+
+class SceneBatch:
+    """Many worlds that share fixtures/vertices and differ only in their body definitions.
+
+    Built with numpy so that 10^5 jittered worlds do not cost 10^5 x Python object construction.
+    ``c_array`` is a contiguous array of b2g_scene whose ``bodies`` pointers point into one big buffer.
+    """
+
+    def __init__(self, base: Scene, bodies: np.ndarray):
+        self.base = base
+        self.count = bodies.shape[0]
+        self._bodies = np.ascontiguousarray(bodies)
+        cs = base.c_scene()
+        arr = (CScene * self.count)()
+        stride = self._bodies.strides[0]
+        addr = self._bodies.ctypes.data
+        for i in range(self.count):
+            C.memmove(C.byref(arr, i * C.sizeof(CScene)), C.byref(cs), C.sizeof(CScene))
+            arr[i].bodies = C.cast(addr + i * stride, C.POINTER(BodyDef))
+        self.c_array = arr
+
+    def scene(self, i) -> Scene:
+        """Materialise world i as a standalone Scene (for the oracles)."""
+        s = Scene(self.base.gravity, self.base.flags)
+        s.fixtures = self.base.fixtures
+        s.vertices = self.base.vertices
+        raw = self._bodies[i].tobytes()
+        n = len(self.base.bodies)
+        s.bodies = list((BodyDef * n).from_buffer_copy(raw))
+        return s
+
+
+BODY_DTYPE = np.dtype([("type", "<i4"), ("flags", "<i4"), ("position", "<f4", 2), ("angle", "<f4"),
+                       ("linearVelocity", "<f4", 2), ("angularVelocity", "<f4"), ("linearDamping", "<f4"),
+                       ("angularDamping", "<f4"), ("gravityScale", "<f4")])
+assert BODY_DTYPE.itemsize == C.sizeof(BodyDef)
+
+
+def pyramid_batch(count, rows=20, flags=WORLD_DEFAULT, first_seed=0, jitter=0.02, jittered=True) -> SceneBatch:
+    """`count` pyramid worlds; world i equals ``pyramid(rows, flags, jitter_seed=first_seed + i)`` bit for bit."""
+    base = pyramid(rows, flags)
+    nb = len(base.bodies)
+    one = np.frombuffer(b"".join(bytes(b) for b in base.bodies), dtype=BODY_DTYPE)
+    bodies = np.tile(one, (count, 1))
+    if jittered:
+        seeds = (np.arange(first_seed, first_seed + count, dtype=np.uint64) * 2654435761 + 12345) & 0xFFFFFFFF
+        state = seeds.copy()
+        for j in range(1, nb):  # body 0 is the ground; boxes in creation order
+            state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+            u = (state >> 8).astype(np.float64) / float(1 << 24)
+            delta = (-jitter + (2 * jitter) * u).astype(np.float32)
+            bodies["position"][:, j, 0] = bodies["position"][:, j, 0] + delta
+    return SceneBatch(base, bodies)
