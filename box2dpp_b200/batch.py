@@ -37,8 +37,11 @@ EXPORTED_SYMBOLS = [
     "b2gpu_batch_field_shape", "b2gpu_batch_step", "b2gpu_batch_step_n", "b2gpu_batch_sync",
     "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_last_step_ms",
     "b2gpu_batch_profile_steps", "b2gpu_batch_launch_count", "b2gpu_last_error", "b2gpu_scene_capacities",
-    "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build",
+    "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build", "b2gpu_host_sincosf", "b2gpu_sincosf",
+    "b2gpu_collide_pairs",
 ]
+
+COLLIDE_POLYGONS, COLLIDE_CIRCLES, COLLIDE_POLYGON_CIRCLE, COLLIDE_EDGE_CIRCLE, COLLIDE_EDGE_POLYGON = range(5)
 
 
 class BatchDesc(C.Structure):
@@ -81,6 +84,9 @@ def lib():
         L.b2gpu_scene_capacities.argtypes = [C.POINTER(CScene), i32, C.POINTER(BatchDesc)]
         L.b2gpu_batch_build_worlds.argtypes = [vp, C.POINTER(CScene), i32, i32, i32]
         L.b2gpu_host_polygon_build.argtypes = [C.POINTER(FixtureDef), vp, vp]
+        L.b2gpu_host_sincosf.argtypes = [vp, vp, vp, C.c_int64]
+        L.b2gpu_sincosf.argtypes = [i32, vp, vp, vp, C.c_int64]
+        L.b2gpu_collide_pairs.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -95,6 +101,17 @@ def host_polygon_build(fd: FixtureDef, verts):
     out = np.zeros(38, np.float32)
     n = lib().b2gpu_host_polygon_build(C.byref(fd), v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return n, out
+
+
+def collide_pairs(kind, shape_a, xf_a, shape_b, xf_b, device=0):
+    """b2gpu_collide_pairs: the device narrow phase on n independent shape pairs (flat formats of include/b2gpu.h)."""
+    a, xa, b, xb = (np.ascontiguousarray(t, np.float32) for t in (shape_a, xf_a, shape_b, xf_b))
+    n = xa.shape[0]
+    ints = np.zeros((n, 4), np.int32)
+    fl = np.zeros((n, 8), np.float32)
+    p = lambda t: t.ctypes.data_as(C.c_void_p)  # noqa: E731
+    _check(lib().b2gpu_collide_pairs(device, kind, n, p(a), p(xa), p(b), p(xb), p(ints), p(fl)))
+    return ints, fl
 
 
 class WorldBatch:

@@ -593,4 +593,10 @@ int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, f
     return sh.count;
 }
 
+int b2gpu_host_sincosf(const float* x, float* s, float* c, int64_t n) {
+    if (!x || !s || !c || n < 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    for (int64_t i = 0; i < n; ++i) SinCos(x[i], &s[i], &c[i]);
+    return B2GPU_OK;
+}
+
 }  // extern "C"

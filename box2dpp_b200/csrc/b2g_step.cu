@@ -95,6 +95,64 @@ __global__ void k_read_transforms(Arena A, float4* __restrict__ out) {
     out[(size_t)w * A.NB + body] = A.bodyXf[idx];
 }
 
+// ---- stateless entry points: the kernels' building blocks on flat inputs (unit-level parity) ----
+struct FlatPoly {  // 35 floats: count, 8 vertices, 8 normals, centroid (oracle/ref_harness.cpp fill_poly)
+    const float* w;
+    __device__ __forceinline__ int count() const { return (int)w[0]; }
+    __device__ __forceinline__ float radius() const { return kPolygonRadius; }
+    __device__ __forceinline__ Vec2 centroid() const { return V2(w[33], w[34]); }
+    __device__ __forceinline__ Vec2 vert(int i) const { return V2(w[1 + 2 * i], w[2 + 2 * i]); }
+    __device__ __forceinline__ Vec2 normal(int i) const { return V2(w[17 + 2 * i], w[18 + 2 * i]); }
+};
+
+__global__ void k_collide_pairs(int kind, int n, const float* __restrict__ shapeA, const float* __restrict__ xfA,
+                                const float* __restrict__ shapeB, const float* __restrict__ xfB, int* __restrict__ ints,
+                                float* __restrict__ floats) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Xf xa, xb;
+    xa.p = V2(xfA[4 * i], xfA[4 * i + 1]); xa.q.s = xfA[4 * i + 2]; xa.q.c = xfA[4 * i + 3];
+    xb.p = V2(xfB[4 * i], xfB[4 * i + 1]); xb.q.s = xfB[4 * i + 2]; xb.q.c = xfB[4 * i + 3];
+    Manifold m;
+    m.pointCount = 0; m.type = 0; m.key0 = m.key1 = 0;
+    m.lp0 = m.lp1 = m.localNormal = m.localPoint = V2(0.0f, 0.0f);
+    auto circle = [](const float* c) { CircleData d; d.p = V2(c[0], c[1]); d.radius = c[2]; return d; };
+    auto edge = [](const float* e) {
+        EdgeData d;
+        d.v0 = V2(e[0], e[1]); d.v1 = V2(e[2], e[3]); d.v2 = V2(e[4], e[5]); d.v3 = V2(e[6], e[7]);
+        d.has0 = e[8] != 0.0f; d.has3 = e[9] != 0.0f; d.radius = kPolygonRadius;
+        return d;
+    };
+    switch (kind) {
+        case B2GPU_COLLIDE_POLYGONS:
+            CollidePolygons(&m, FlatPoly{shapeA + 35 * (size_t)i}, xa, FlatPoly{shapeB + 35 * (size_t)i}, xb); break;
+        case B2GPU_COLLIDE_CIRCLES:
+            CollideCircles(&m, circle(shapeA + 3 * (size_t)i), xa, circle(shapeB + 3 * (size_t)i), xb); break;
+        case B2GPU_COLLIDE_POLYGON_CIRCLE:
+            CollidePolygonAndCircle(&m, FlatPoly{shapeA + 35 * (size_t)i}, xa, circle(shapeB + 3 * (size_t)i), xb); break;
+        case B2GPU_COLLIDE_EDGE_CIRCLE:
+            CollideEdgeAndCircle(&m, edge(shapeA + 10 * (size_t)i), xa, circle(shapeB + 3 * (size_t)i), xb); break;
+        default:
+            CollideEdgeAndPolygon(&m, edge(shapeA + 10 * (size_t)i), xa, FlatPoly{shapeB + 35 * (size_t)i}, xb); break;
+    }
+    int* I = ints + 4 * (size_t)i;
+    float* F = floats + 8 * (size_t)i;
+    I[0] = m.pointCount; I[1] = m.type;
+    I[2] = m.pointCount > 0 ? (int)m.key0 : 0;
+    I[3] = m.pointCount > 1 ? (int)m.key1 : 0;
+    for (int k = 0; k < 8; ++k) F[k] = 0.0f;
+    if (m.pointCount > 0) {
+        F[0] = m.localNormal.x; F[1] = m.localNormal.y; F[2] = m.localPoint.x; F[3] = m.localPoint.y;
+        F[4] = m.lp0.x; F[5] = m.lp0.y;
+        if (m.pointCount > 1) { F[6] = m.lp1.x; F[7] = m.lp1.y; }
+    }
+}
+
+__global__ void k_sincosf(const float* __restrict__ x, float* __restrict__ s, float* __restrict__ c, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) SinCos(x[i], &s[i], &c[i]);
+}
+
 }  // namespace
 
 struct b2gpu_batch {
@@ -462,6 +520,66 @@ int b2gpu_batch_read_transforms(b2gpu_batch* b, float* out) {
     size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
     CUDA_TRY(cudaMemcpyAsync(out, b->ioDev, bytes, cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+// ---- stateless device entry points ---------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        return e == cudaSuccess ? B2GPU_OK : fail(B2GPU_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+};
+int requireDevice(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B2GPU_ERR_NO_DEVICE, "no CUDA device available (%s); box2dpp_b200 has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(B2GPU_ERR_INVALID, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    return B2GPU_OK;
+}
+}  // namespace
+
+int b2gpu_sincosf(int32_t device, const float* x, float* s, float* c, int64_t n) {
+    if (!x || !s || !c || n < 0) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    int rc = requireDevice(device);
+    if (rc != B2GPU_OK || n == 0) return rc;
+    DevBuf dx, ds, dc;
+    if ((rc = dx.alloc(n * 4)) || (rc = ds.alloc(n * 4)) || (rc = dc.alloc(n * 4))) return rc;
+    CUDA_TRY(cudaMemcpy(dx.p, x, n * 4, cudaMemcpyHostToDevice));
+    k_sincosf<<<(unsigned)((n + 255) / 256), 256>>>((const float*)dx.p, (float*)ds.p, (float*)dc.p, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(s, ds.p, n * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(c, dc.p, n * 4, cudaMemcpyDeviceToHost));
+    return B2GPU_OK;
+}
+
+int b2gpu_collide_pairs(int32_t device, int32_t kind, int32_t n, const float* shapeA, const float* xfA, const float* shapeB,
+                        const float* xfB, int32_t* ints, float* floats) {
+    if (!shapeA || !xfA || !shapeB || !xfB || !ints || !floats || n < 0 || kind < 0 || kind > B2GPU_COLLIDE_EDGE_POLYGON)
+        return fail(B2GPU_ERR_INVALID, "bad arguments");
+    int rc = requireDevice(device);
+    if (rc != B2GPU_OK || n == 0) return rc;
+    const size_t wa = (kind == B2GPU_COLLIDE_CIRCLES) ? 3 : (kind >= B2GPU_COLLIDE_EDGE_CIRCLE ? 10 : 35);
+    const size_t wb = (kind == B2GPU_COLLIDE_POLYGONS || kind == B2GPU_COLLIDE_EDGE_POLYGON) ? 35 : 3;
+    DevBuf da, db, dxa, dxb, di, df;
+    if ((rc = da.alloc(n * wa * 4)) || (rc = db.alloc(n * wb * 4)) || (rc = dxa.alloc(n * 16)) || (rc = dxb.alloc(n * 16)) ||
+        (rc = di.alloc(n * 16)) || (rc = df.alloc(n * 32)))
+        return rc;
+    CUDA_TRY(cudaMemcpy(da.p, shapeA, n * wa * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db.p, shapeB, n * wb * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dxa.p, xfA, (size_t)n * 16, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dxb.p, xfB, (size_t)n * 16, cudaMemcpyHostToDevice));
+    k_collide_pairs<<<(n + 127) / 128, 128>>>(kind, n, (const float*)da.p, (const float*)dxa.p, (const float*)db.p,
+                                              (const float*)dxb.p, (int*)di.p, (float*)df.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(ints, di.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(floats, df.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
     return B2GPU_OK;
 }
 

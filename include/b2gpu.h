@@ -169,6 +169,28 @@ int b2gpu_batch_build_worlds(b2gpu_batch* batch, const b2g_scene* scenes, int32_
  * mass, center.xy, I (38 floats); returns the vertex count. */
 int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, float* out);
 
+/* b2Rot::Set(angle) (Box2D/Common/b2Math.h:302-311) as the host layer evaluates it: the library's own
+ * sinf / cosf, bit-identical to the libm the reference links (tests/test_sincos.py).  Host code, no device. */
+int b2gpu_host_sincosf(const float* x, float* s, float* c, int64_t n);
+
+/* ---- stateless device entry points (unit-level parity of the kernels' building blocks) -------------- */
+
+/* The same b2Rot::Set evaluated by a CUDA kernel on `device` (host buffers in and out). */
+int b2gpu_sincosf(int32_t device, const float* x, float* s, float* c, int64_t n);
+
+/* Replaces direct calls of the narrow-phase functions (Box2D/Collision/b2Collision.h:237-300;
+ * b2CollidePolygons b2CollidePolygon.cpp:119-242, b2CollideCircles / b2CollidePolygonAndCircle
+ * b2CollideCircle.cpp:25-153, b2CollideEdgeAndCircle / b2CollideEdgeAndPolygon b2CollideEdge.cpp) for n
+ * independent shape pairs, one CUDA thread per pair.  Flat host formats:
+ *   polygon 35 floats: count, 8 vertices, 8 normals, centroid      circle 3 floats: p.xy, radius
+ *   edge 10 floats: v0 v1 v2 v3, hasVertex0, hasVertex3            transform 4 floats: p.xy, q.s, q.c
+ * out ints[4n]: pointCount, manifold type, id.key of point 0 / 1; floats[8n]: localNormal, localPoint,
+ * points[0].localPoint, points[1].localPoint (zero when pointCount == 0). */
+enum { B2GPU_COLLIDE_POLYGONS = 0, B2GPU_COLLIDE_CIRCLES = 1, B2GPU_COLLIDE_POLYGON_CIRCLE = 2,
+       B2GPU_COLLIDE_EDGE_CIRCLE = 3, B2GPU_COLLIDE_EDGE_POLYGON = 4 };
+int b2gpu_collide_pairs(int32_t device, int32_t kind, int32_t n, const float* shapeA, const float* xfA,
+                        const float* shapeB, const float* xfB, int32_t* ints, float* floats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,12 +5,19 @@ Bar (BASELINE.json north_star): proxy-pair sets and manifold point counts bit-ex
 FMA contraction, these tests assert the stronger property: EVERY float of every body, manifold, fat AABB
 and listener event is bit-identical to the unmodified reference, every step.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 
+import golden_cases as G
+from box2dpp_b200 import batch as B
 from box2dpp_b200 import scene as S
 from box2dpp_b200.batch import EVENT_ALL, WorldBatch
 from parity_util import NOCCD, compare_world
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 pytestmark = pytest.mark.gpu
 
@@ -81,3 +88,89 @@ def test_replicated_worlds_identical(oracles):
         ref.step(1.0 / 60.0, 8, 3)
     compare_world(ref, batch.bodies(69), batch.contacts(69), what="replica 69")
     batch.close()
+
+
+# ---- against the frozen reference answers (tests/golden/, no oracle library needed) ---------------
+@pytest.mark.parametrize("name,kind", [("polygons", B.COLLIDE_POLYGONS), ("circles", B.COLLIDE_CIRCLES),
+                                       ("polygon_circle", B.COLLIDE_POLYGON_CIRCLE),
+                                       ("edge_circle", B.COLLIDE_EDGE_CIRCLE), ("edge_polygon", B.COLLIDE_EDGE_POLYGON)])
+def test_device_narrow_phase_matches_golden(name, kind):
+    """The reference's narrow-phase known-answer tests (Regression/tests/helloworld.cpp:268-418) and the seeded
+    random pairs, evaluated by the device functions the collide kernel calls: manifold ids, point counts and
+    every float bit-exact."""
+    g = np.load(os.path.join(GOLD, "narrowphase.npz"))
+    cases = G.NARROW_CASES[name][1]()
+    a, xa, b, xb = (np.stack([c[i] for c in cases]) for i in range(4))
+    ints, fl = B.collide_pairs(kind, a, xa, b, xb)
+    gi, gf = g[name + "_ints"], g[name + "_floats"]
+    assert (ints == gi).all(), f"{name}: ids / point counts differ at {np.argwhere(ints != gi)[:4].tolist()}"
+    assert (fl.view(np.uint32) == gf.view(np.uint32)).all(), f"{name}: manifold floats differ"
+
+
+def test_device_narrow_phase_large_random(oracles):
+    """200k random convex-polygon pairs, device vs the C restatement (bit-exact)."""
+    rs = np.random.RandomState(5)
+    n = 200000
+    base = [G.random_convex(rs) for _ in range(256)]
+    ia, ib = rs.randint(0, 256, n), rs.randint(0, 256, n)
+    a, b = np.stack(base)[ia], np.stack(base)[ib]
+    ang = rs.uniform(-3.2, 3.2, (n, 2)).astype(np.float32)
+    xa = np.stack([rs.uniform(-.5, .5, n), rs.uniform(-.5, .5, n), np.sin(ang[:, 0]), np.cos(ang[:, 0])], 1).astype(np.float32)
+    xb = np.stack([rs.uniform(-2, 2, n), rs.uniform(-2, 2, n), np.sin(ang[:, 1]), np.cos(ang[:, 1])], 1).astype(np.float32)
+    ints, fl = B.collide_pairs(B.COLLIDE_POLYGONS, a, xa, b, xb)
+    assert (ints[:, 0] > 0).mean() > 0.1
+    for i in rs.randint(0, n, 4000):
+        ri, rf = oracles.collide_polygons(a[i], xa[i], b[i], xb[i], kind="port")
+        assert (ri == ints[i]).all() and (rf.view(np.uint32) == fl[i].view(np.uint32)).all(), f"pair {i}"
+
+
+@pytest.mark.parametrize("name", G.NOCCD_CASES)
+def test_worlds_match_golden_hashes(name):
+    """Every parity scene against the per-step hashes frozen from the reference (body state bits, contact-list
+    order with point counts, contact / touching / manifold-point totals)."""
+    g = json.load(open(os.path.join(GOLD, "worlds.json")))[name]
+    make, steps, vi, pi = G.WORLD_CASES[name]
+    sc = make()
+    fb = G.fixture_bodies(sc)
+    batch = WorldBatch([sc])
+    stride = 1 if steps <= 250 else 6
+    for step in range(steps):
+        batch.step(1.0 / 60.0, vi, pi)
+        if step % stride == 0 or step == steps - 1:
+            ints, _ = batch.contacts(0)
+            touching = (ints[:, 4] & 1) != 0
+            assert [len(ints), int(touching.sum()), int(ints[touching, 5].sum())] == g["contacts_touching_points"][step], \
+                f"{name} step {step}: contact / touching / point counts"
+            assert "%016x" % G.contact_order_hash(ints, fb) == g["contact_order_hash"][step], f"{name} step {step}: order"
+            assert "%016x" % G.state_hash(batch.bodies(0)) == g["state_hash"][step], f"{name} step {step}: state"
+    assert (batch.status() == 0).all()
+    batch.close()
+
+
+def test_full_size_batch_properties(oracles):
+    """BASELINE configs[2] at full size: 16,384 pyramid-20 worlds on one B200.  Size-independent properties:
+    (a) identical worlds stay bit-identical to each other and to the oracle's single world;
+    (b) jittered worlds: 16 spot-checked worlds equal the oracle bit-for-bit; no arena overflow anywhere;
+    (c) determinism: two batches stepped separately agree bit-for-bit."""
+    flags = NOCCD & ~S.WORLD_ALLOW_SLEEP
+    steps = 40
+    W = 16384
+    sb = S.pyramid_batch(W, 20, flags=flags, first_seed=0, jittered=True)
+    batch = WorldBatch(sb)
+    batch.step_n(1.0 / 60.0, 8, 3, steps)
+    batch.sync()
+    assert (batch.status() == 0).all()
+    xf = batch.read_transforms().copy()
+    Ref = _ref_cls(oracles)
+    for w in [0, 1, 31, 32, 33, 1000, 4095, 4096, 8191, 8192, 12345, 16000, 16352, 16382, 16383, 777]:
+        ref = Ref(sb.scene(w))
+        for _ in range(steps):
+            ref.step(1.0 / 60.0, 8, 3)
+        compare_world(ref, batch.bodies(w), batch.contacts(w), batch.proxies(w), what=f"jittered world {w}")
+    batch.close()
+    batch2 = WorldBatch(sb)
+    for _ in range(steps):
+        batch2.step(1.0 / 60.0, 8, 3)
+    xf2 = batch2.read_transforms()
+    assert (xf.view(np.uint32) == xf2.view(np.uint32)).all(), "graph replay and single steps disagree"
+    batch2.close()

@@ -1,0 +1,136 @@
+"""CPU tests of the oracle (TEST INFRASTRUCTURE): the C restatement oracle/b2o_*.c against
+
+  * the golden fixtures frozen from the reference's vanilla Box2D (tests/golden/, tools/make_golden.py),
+  * SURVEY.md Appendix D's independently produced checkpoints, and
+  * the live reference library oracle/_ref/libb2ref.so when it is present (build container).
+
+Bar: bit-exact everywhere (integer ids, point counts, and every float32).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as G
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold_worlds():
+    return json.load(open(os.path.join(GOLD, "worlds.json")))
+
+
+@pytest.fixture(scope="module")
+def gold_narrow():
+    return np.load(os.path.join(GOLD, "narrowphase.npz"))
+
+
+def _kinds(oracles):
+    return ["port"] + (["ref"] if oracles.available("ref") else [])
+
+
+@pytest.mark.parametrize("name", list(G.NARROW_CASES))
+def test_narrow_phase_matches_golden(oracles, gold_narrow, name):
+    fn, gen = G.NARROW_CASES[name]
+    cases = gen()
+    gi, gf = gold_narrow[name + "_ints"], gold_narrow[name + "_floats"]
+    assert len(cases) == len(gi)
+    assert (gi[:, 0] > 0).sum() > len(cases) // 10, "fixture must contain touching cases"
+    for kind in _kinds(oracles):
+        for i, (a, xa, b, xb) in enumerate(cases):
+            ints, fl = getattr(oracles, fn)(a, xa, b, xb, kind=kind)
+            assert (ints == gi[i]).all(), f"{kind} {name}[{i}]: ids/pointCount {ints} vs golden {gi[i]}"
+            assert (fl.view(np.uint32) == gf[i].view(np.uint32)).all(), f"{kind} {name}[{i}]: manifold floats differ"
+
+
+def test_reference_known_answer_tests(gold_narrow):
+    """The reference's own narrow-phase KATs (Regression/tests/helloworld.cpp:268-293, 393-418) pin
+    pointCount; these are cases 0/1 of the circles fixture and case 0 of the polygons fixture."""
+    assert gold_narrow["circles_ints"][0, 0] == 1 and gold_narrow["circles_ints"][1, 0] == 1
+    # two unit boxes rotated by 1 rad with centres 2 apart overlap at their corners: a 2-point face manifold
+    assert gold_narrow["polygons_ints"][0, 0] == 2
+    # the separated pair of Testb2FindMaxSeparation (:295-325) yields no manifold
+    assert gold_narrow["polygons_ints"][2, 0] == 0
+
+
+def test_polygon_build_matches_golden(oracles):
+    g = np.load(os.path.join(GOLD, "polygons.npz"))
+    for kind in _kinds(oracles):
+        for i, (fd, verts) in enumerate(G.polygon_cases()):
+            n, out = oracles.polygon_build(fd, verts, kind=kind)
+            assert n == g["counts"][i], f"{kind} polygon {i}: vertex count {n} vs {g['counts'][i]}"
+            assert (out.view(np.uint32) == g["outs"][i].view(np.uint32)).all(), f"{kind} polygon {i}: hull/mass differ"
+
+
+def _run_world(World, name):
+    make, steps, vi, pi = G.WORLD_CASES[name]
+    sc = make()
+    w = World(sc)
+    fb = G.fixture_bodies(sc)
+    for step in range(steps):
+        w.step(1.0 / 60.0, vi, pi)
+        ints, _ = w.contacts()
+        touching = (ints[:, 4] & 1) != 0
+        yield step, w.bodies(), ints, fb, [len(ints), int(touching.sum()), int(ints[touching, 5].sum())]
+
+
+@pytest.mark.parametrize("name", G.NOCCD_CASES)
+def test_port_worlds_match_golden(oracles, gold_worlds, name):
+    """The C restatement reproduces the reference's per-step body-state and contact-order hashes."""
+    g = gold_worlds[name]
+    stride = 1 if g["steps"] <= 250 else 4  # the pure-Python FNV is the slow part
+    for step, bodies, ints, fb, counts in _run_world(oracles.PortWorld, name):
+        assert counts == g["contacts_touching_points"][step], f"{name} step {step}: contact/touching/point counts"
+        if step % stride == 0 or step == g["steps"] - 1:
+            assert "%016x" % G.contact_order_hash(ints, fb) == g["contact_order_hash"][step], f"{name} step {step}: contact order"
+            assert "%016x" % G.state_hash(bodies) == g["state_hash"][step], f"{name} step {step}: body state"
+
+
+@pytest.mark.parametrize("name", list(G.APPENDIX_D))
+def test_golden_reproduces_survey_appendix_d(gold_worlds, name):
+    """The frozen fixtures agree with the checkpoints SURVEY.md Appendix D obtained from vanilla with an
+    independent probe: the golden file and the survey pin each other."""
+    g = gold_worlds[name]
+    for step, (contacts, touching, points, sh, ch) in G.APPENDIX_D[name].items():
+        if contacts is not None:
+            assert g["contacts_touching_points"][step] == [contacts, touching, points], f"{name} step {step}"
+        assert g["state_hash"][step] == sh, f"{name} step {step}: state hash"
+        if ch is not None:
+            assert g["contact_order_hash"][step] == ch, f"{name} step {step}: contact-order hash"
+
+
+def test_hello_world_reference_defaults(gold_worlds):
+    """BASELINE config 1 with the reference's default flags (continuous physics on): Appendix D values."""
+    rows = gold_worlds["hello_world_default_flags_xya_bits"]
+    assert len(rows) == 60
+    for step, ybits in G.APPENDIX_D_HELLO_Y.items():
+        assert rows[step][1] == ybits, f"HelloWorld step {step}: y bits {rows[step][1]:08x} vs {ybits:08x}"
+
+
+def test_live_reference_matches_golden(oracles, gold_worlds):
+    """When the reference library is present (build container), it still produces the frozen answers."""
+    if not oracles.available("ref"):
+        pytest.skip("oracle/_ref/libb2ref.so not present on this box")
+    for name in ("hello_world_default", "pyramid7_jitter3", "mixed_seed5"):
+        g = gold_worlds[name]
+        for step, bodies, ints, fb, counts in _run_world(oracles.RefWorld, name):
+            assert "%016x" % G.state_hash(bodies) == g["state_hash"][step], f"{name} step {step}"
+            assert "%016x" % G.contact_order_hash(ints, fb) == g["contact_order_hash"][step], f"{name} step {step}"
+
+
+def test_port_equals_reference_every_float(oracles):
+    """Port vs live reference, all dumps bit-for-bit (bodies, manifolds with impulses, fat AABBs, events)."""
+    if not oracles.available("ref"):
+        pytest.skip("oracle/_ref/libb2ref.so not present on this box")
+    from box2dpp_b200 import scene as S
+    from parity_util import compare_world
+    scenes = [S.pyramid(6, flags=G.NOCCD, jitter_seed=9), S.mixed(2, flags=G.NOCCD), S.hello_world(G.NOCCD)]
+    for si, sc in enumerate(scenes):
+        r, p = oracles.RefWorld(sc, record_events=True), oracles.PortWorld(sc, record_events=True)
+        for step in range(150):
+            r.step(1.0 / 60.0, 8, 3)
+            p.step(1.0 / 60.0, 8, 3)
+            if step % 3 == 0:
+                compare_world(r, p.bodies(), p.contacts(), p.proxies()[0], p.events(), what=f"scene {si} step {step}")
