@@ -115,6 +115,7 @@ def main():
     ap.add_argument("--identical", action="store_true", help="identical worlds instead of jittered ones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--generic-solver", action="store_true", help="force the fallback solver kernel")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -170,7 +171,7 @@ def main():
 
     W = args.worlds_per_gpu
     sb = S.pyramid_batch(W, ROWS, flags=flags_throughput(), first_seed=rank * W, jittered=not args.identical)
-    batch = WorldBatch(sb, device=local_rank, block_size=args.block)
+    batch = WorldBatch(sb, device=local_rank, block_size=args.block, generic_solver=args.generic_solver)
     batch.step_n(DT, 8, 3, PREROLL)
     batch.sync()
 
@@ -223,34 +224,49 @@ def main():
 
     # ---- per-kernel times and the roofline of the dominant kernel (live CUDA events, same stream) ----
     prof_steps = 10
-    kms = batch.profile_steps(DT, 8, 3, prof_steps)
+    kms = {k: v / prof_steps for k, v in batch.profile_kernels(DT, 8, 3, prof_steps).items()}
     contacts = batch.field(F_CONTACT_COUNT)[:, 0, 0].astype(np.float64)
     nisl = batch.field(F_ISLAND_COUNT)[:, 0, 0]
     iend = batch.field(F_ISLAND_CONTACT_END)[:, :, 0]
     touching = np.array([iend[w, nisl[w] - 1] if nisl[w] > 0 else 0 for w in range(W)], dtype=np.float64)
-    alg_step = BODIES_DYNAMIC * BYTES_PER_DYNAMIC_BODY + (BODIES_DYNAMIC + 1) * BYTES_PER_PROXY + contacts.mean() * BYTES_PER_CONTACT
-    # the solver kernel owns all dynamic-body traffic and the manifolds of touching contacts
-    alg_solve = BODIES_DYNAMIC * BYTES_PER_DYNAMIC_BODY + touching.mean() * BYTES_PER_CONTACT
-    solve_ms = kms["solve"] / prof_steps
+    nbody, nproxy = BODIES_DYNAMIC, BODIES_DYNAMIC + 1
+    alg_step = nbody * BYTES_PER_DYNAMIC_BODY + nproxy * BYTES_PER_PROXY + contacts.mean() * BYTES_PER_CONTACT
+    # Algorithmic bytes per world for each kernel taken alone: persistent fields it must read once
+    # plus persistent fields it must write once; solver temporaries (constraint records) count zero.
+    tc, nc = touching.mean(), contacts.mean()
+    alg_kernel = {
+        "k_collide": nc * (128 + 24 + 4) + nproxy * 84 + nbody * 16,           # manifolds r/w, ids/flags, fat AABB + shape, xf
+        "k_islands": nc * (4 + 8 + 32) + nbody * 8,                              # flags, body pair, list links; body flags r/w
+        "k_solve_prepare": nbody * (24 + 12 + 28 + 24 + 12) + tc * (64 + 24),    # c,a,v,w, c0/a0, mass data, force; manifold + ids
+        "k_solve_velocity": nbody * 24 + tc * 32,                                # b2Velocity in/out; impulses in/out
+        "k_solve_integrate": nbody * (12 + 12 + 12) + tc * 32,                   # v in, v out, c/a out; impulses -> manifold
+        "k_solve_position": nbody * 24 + tc * 40,                                # b2Position in/out; local manifold geometry
+        "k_solve_finalize": nbody * (12 + 16 + 16),                              # c/a, xf, flags + sleep time
+        "k_sync_pairs": nproxy * (16 + 68) + nbody * (16 + 12),                  # fat AABB + shape; xf, c0/a0
+        "k_solve": nbody * BYTES_PER_DYNAMIC_BODY + tc * BYTES_PER_CONTACT,
+    }
+    top = max(kms, key=kms.get)
+    top_ms = kms[top]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_solve * W / (solve_ms * 1e-3) / 1e9
+    achieved = alg_kernel[top] * W / (top_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("k_solve_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top + "_dram_bytes_per_launch")
     except Exception:
         pass
-    step_ms_sum = sum(kms.values()) / prof_steps
-    roofline = {"kernel": "k_solve", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    step_ms_sum = sum(kms.values())
+    roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": alg_solve * W, "kernel_ms": solve_ms,
-                "kernel_share_of_step": solve_ms / step_ms_sum,
-                "kernels_ms": {k: v / prof_steps for k, v in kms.items()},
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": alg_kernel[top] * W, "kernel_ms": top_ms,
+                "kernel_share_of_step": top_ms / step_ms_sum,
+                "kernels_ms": kms,
+                "kernels_frac": {k: alg_kernel[k] * W / (v * 1e-3) / 1e9 / peak for k, v in kms.items() if v > 0},
                 "step_algorithmic_bytes_per_world": alg_step,
                 "step_achieved_gbs": alg_step * value / world_size / 1e9,
                 "step_frac": alg_step * value / world_size / 1e9 / peak,

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "b2gpu_batch_create", "b2gpu_batch_destroy", "b2gpu_batch_upload_field", "b2gpu_batch_download_field",
     "b2gpu_batch_field_shape", "b2gpu_batch_step", "b2gpu_batch_step_n", "b2gpu_batch_sync",
     "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_last_step_ms",
-    "b2gpu_batch_profile_steps", "b2gpu_batch_launch_count", "b2gpu_last_error", "b2gpu_scene_capacities",
+    "b2gpu_batch_profile_steps", "b2gpu_batch_profile_kernels", "b2gpu_batch_kernel_name", "b2gpu_batch_launch_count", "b2gpu_last_error", "b2gpu_scene_capacities",
     "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build", "b2gpu_host_sincosf", "b2gpu_sincosf",
     "b2gpu_collide_pairs",
 ]
@@ -78,6 +78,9 @@ def lib():
         L.b2gpu_batch_read_transforms.argtypes = [vp, vp]
         L.b2gpu_batch_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_steps.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
+        L.b2gpu_batch_profile_kernels.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
+        L.b2gpu_batch_kernel_name.argtypes = [vp, i32]
+        L.b2gpu_batch_kernel_name.restype = C.c_char_p
         L.b2gpu_batch_launch_count.argtypes = [vp]
         L.b2gpu_batch_launch_count.restype = C.c_int64
         L.b2gpu_last_error.restype = C.c_char_p
@@ -117,7 +120,8 @@ def collide_pairs(kind, shape_a, xf_a, shape_b, xf_b, device=0):
 class WorldBatch:
     """A batch of independent worlds on one GPU."""
 
-    def __init__(self, scenes, replicate=1, device=0, max_contacts=0, max_events=0, event_mask=0, block_size=0):
+    def __init__(self, scenes, replicate=1, device=0, max_contacts=0, max_events=0, event_mask=0, block_size=0,
+                 generic_solver=False):
         if isinstance(scenes, Scene):
             scenes = [scenes]
         if isinstance(scenes, SceneBatch):
@@ -131,6 +135,7 @@ class WorldBatch:
         d = BatchDesc()
         d.device, d.numWorlds = device, self.num_worlds
         d.maxContacts, d.maxEvents, d.eventMask, d.blockSize = max_contacts, max_events, event_mask, block_size
+        d.reserved = 1 if generic_solver else 0
         _check(L.b2gpu_scene_capacities(arr, n_scenes, C.byref(d)))
         self.desc = d
         self.h = C.c_void_p()
@@ -169,6 +174,13 @@ class WorldBatch:
         ms = (C.c_float * 4)()
         _check(lib().b2gpu_batch_profile_steps(self.h, dt, vel_iters, pos_iters, steps, ms))
         return dict(zip(("collide", "islands", "solve", "sync_pairs"), [float(x) for x in ms]))
+
+    def profile_kernels(self, dt, vel_iters, pos_iters, steps):
+        """{kernel name: total ms over `steps` steps}, in launch order (CUDA events around every kernel)."""
+        ms = (C.c_float * 16)()
+        n = C.c_int32(0)
+        _check(lib().b2gpu_batch_profile_kernels(self.h, dt, vel_iters, pos_iters, steps, ms, 16, C.byref(n)))
+        return {lib().b2gpu_batch_kernel_name(self.h, i).decode(): float(ms[i]) for i in range(n.value)}
 
     def launch_count(self) -> int:
         return int(lib().b2gpu_batch_launch_count(self.h))

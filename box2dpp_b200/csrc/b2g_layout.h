@@ -113,8 +113,16 @@ struct Arena {
     int* islandBodyEnd;  // [tile][NB][lane]   end offset into islandBodies per island
     int* islandContacts; // [tile][NC][lane]   contact indices in solver order, concatenated
     int* islandContactEnd; // [tile][NB][lane]
-    // b2ContactVelocityConstraint, 9 x 16 B per island contact: [tile][NC*9][lane]
+    // b2ContactVelocityConstraint, 9 x 16 B per island contact: [tile][NC*9][lane] (generic solver path only)
     float4* vc;
+    // tile solver path (b2g_solve.cuh): per island contact i, records of all 32 worlds of a tile are contiguous
+    float4* velRec;      // [tile][NC][7][lane]  velocity constraint record
+    float4* posRec;      // [tile][NC][5][lane]  position constraint record
+    float4* impRec;      // [tile][NC][lane]     accumulated impulses: normal0, tangent0, normal1, tangent1
+    float* solveVel;     // [tile][NB][3][lane]  b2Velocity table (v.x, v.y, w): TMA source / sink of the velocity kernel
+    float* solvePos;     // [tile][NB][3][lane]  b2Position table (c.x, c.y, a)
+    int* solveCount;     // [tile][lane]         island contacts of this step (all islands)
+    int* islandSolved;   // [tile][ceil(NB/32)][lane]  bit per island: position solver converged
 
     // ---- events [tile][NE][lane] ----
     int4* eventA;        // type, fixtureA | childA << 16, fixtureB | childB << 16, count

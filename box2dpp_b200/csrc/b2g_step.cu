@@ -11,6 +11,7 @@
 
 #include "../../include/b2gpu.h"
 #include "b2g_kernels.cuh"
+#include "b2g_solve.cuh"
 
 using namespace b2g;
 
@@ -163,6 +164,8 @@ struct b2gpu_batch {
     std::vector<void*> allocations;
     bool needInitialPairs = true;  // b2World::e_newFixture
     int blockSize = 32;
+    bool tileSolver = false;       // b2g_solve.cuh path: the tile's body table fits in shared memory
+    size_t solveSmem = 0;
     int64_t launches = 0;
     size_t arenaBytes = 0;
     // graph of one step, keyed by its parameters
@@ -221,7 +224,14 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(movedList, A.NP, int);
     ALLOC(islandBodies, A.NB + A.NC, int); ALLOC(islandBodyEnd, A.NB, int);
     ALLOC(islandContacts, A.NC, int); ALLOC(islandContactEnd, A.NB, int);
-    ALLOC(vc, (size_t)A.NC * kVcStride, float4);
+    if (b->tileSolver) {
+        ALLOC(velRec, (size_t)A.NC * kVelRec, float4); ALLOC(posRec, (size_t)A.NC * kPosRec, float4);
+        ALLOC(impRec, A.NC, float4);
+        ALLOC(solveVel, (size_t)A.NB * 3, float); ALLOC(solvePos, (size_t)A.NB * 3, float);
+        ALLOC(solveCount, 1, int); ALLOC(islandSolved, (A.NB + 31) / 32, int);
+    } else {
+        ALLOC(vc, (size_t)A.NC * kVcStride, float4);
+    }
     ALLOC(eventA, A.NE, int4); ALLOC(eventB, A.NE, float4);
 
     b->fields.assign(B2GPU_F_COUNT, Field{nullptr, 0, 0});
@@ -300,27 +310,55 @@ int transferField(b2gpu_batch* b, int field, void* host, int firstWorld, int wor
     return B2GPU_OK;
 }
 
+// Kernel names in launch order of one step (b2gpu_batch_profile_kernels reports times in this order).
+const char* const kTileKernels[] = {"k_collide", "k_islands", "k_solve_prepare", "k_solve_velocity", "k_solve_integrate",
+                                    "k_solve_position", "k_solve_finalize", "k_sync_pairs"};
+const char* const kGenericKernels[] = {"k_collide", "k_islands", "k_solve", "k_sync_pairs"};
+constexpr int kMaxStepKernels = 8;
+
+int stepKernelCount(const b2gpu_batch* b) { return b->tileSolver ? 8 : 4; }
+
 // One b2World::Step for the whole batch (Box2D/Dynamics/b2World.cpp:888-954), TOI excluded.
+// marks (optional): stepKernelCount + 1 events, one before each kernel and one after the last.
 int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks) {
     const int threads = b->blockSize;
+    const unsigned tiles = (unsigned)b->A.numTiles;
     const unsigned blocks = (unsigned)(((size_t)b->A.numTiles * kTile + threads - 1) / threads);
+    cudaStream_t st = b->stream;
     if (b->needInitialPairs) {  // if (m_flags & e_newFixture) FindNewContacts()
-        k_sync_pairs<false><<<blocks, threads, 0, b->stream>>>(b->A, dt, 0);
+        k_sync_pairs<false><<<blocks, threads, 0, st>>>(b->A, dt, 0);
         b->needInitialPairs = false;
         b->launches++;
     }
-    if (marks) cudaEventRecord(marks[0], b->stream);
-    k_collide<<<blocks, threads, 0, b->stream>>>(b->A);
+    int m = 0;
+    auto mark = [&]() { if (marks) cudaEventRecord(marks[m++], st); };
+    mark();
+    k_collide<<<blocks, threads, 0, st>>>(b->A);
     b->launches++;
-    if (marks) cudaEventRecord(marks[1], b->stream);
+    mark();
     if (dt > 0.0f) {
-        k_islands<<<blocks, threads, 0, b->stream>>>(b->A);
-        if (marks) cudaEventRecord(marks[2], b->stream);
-        k_solve<<<blocks, threads, 0, b->stream>>>(b->A, dt, velIters, posIters);
-        if (marks) cudaEventRecord(marks[3], b->stream);
-        k_sync_pairs<true><<<blocks, threads, 0, b->stream>>>(b->A, dt, 1);
-        if (marks) cudaEventRecord(marks[4], b->stream);
-        b->launches += 3;
+        k_islands<<<blocks, threads, 0, st>>>(b->A);
+        mark();
+        if (b->tileSolver) {
+            k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
+            mark();
+            k_solve_velocity<<<tiles, 64, b->solveSmem, st>>>(b->A, velIters);
+            mark();
+            k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
+            mark();
+            k_solve_position<<<tiles, 32, b->solveSmem, st>>>(b->A, posIters);
+            mark();
+            k_solve_finalize<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
+            mark();
+            b->launches += 5;
+        } else {
+            k_solve<<<blocks, threads, 0, st>>>(b->A, dt, velIters, posIters);
+            mark();
+            b->launches++;
+        }
+        k_sync_pairs<true><<<blocks, threads, 0, st>>>(b->A, dt, 1);
+        mark();
+        b->launches += 2;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -357,6 +395,16 @@ int b2gpu_batch_create(const b2gpu_batch_desc* desc, b2gpu_batch** out) {
     b->desc = *desc;
     b->blockSize = desc->blockSize ? desc->blockSize : 32;
     memset(&b->A, 0, sizeof(b->A));
+    {   // Solver path: the tile path keeps the b2Velocity / b2Position table of 32 worlds in shared memory.
+        int maxSmem = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
+        b->solveSmem = SolveSmemBytes(desc->maxBodies);
+        b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0;
+        if (b->tileSolver) {
+            CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
+            CUDA_TRY(cudaFuncSetAttribute(k_solve_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
+        }
+    }
     e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete b; return fail(B2GPU_ERR_CUDA, "stream create failed: %s", cudaGetErrorString(e)); }
     int rc = allocateArena(b);
@@ -434,7 +482,7 @@ int b2gpu_batch_step_n(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIt
             if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
             b->graphDt = dt; b->graphVel = velIters; b->graphPos = posIters;
         }
-        const int perStep = dt > 0.0f ? 4 : 1;
+        const int perStep = dt > 0.0f ? stepKernelCount(b) : 1;
         for (; done < steps; ++done) {
             CUDA_TRY(cudaGraphLaunch(b->graphExec, b->stream));
             b->launches += perStep;
@@ -459,25 +507,46 @@ int b2gpu_batch_last_step_ms(b2gpu_batch* b, float* ms) {
     return B2GPU_OK;
 }
 
-int b2gpu_batch_profile_steps(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIters, int32_t steps, float* ms) {
-    if (!b || !ms || steps <= 0) return fail(B2GPU_ERR_INVALID, "bad arguments");
+int b2gpu_batch_profile_kernels(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIters, int32_t steps, float* ms,
+                                int32_t capacity, int32_t* count) {
+    if (!b || !ms || steps <= 0 || dt <= 0.0f) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    const int nk = stepKernelCount(b);
+    if (capacity < nk) return fail(B2GPU_ERR_INVALID, "ms[] needs room for %d kernels", nk);
     CUDA_TRY(cudaSetDevice(b->desc.device));
-    cudaEvent_t marks[5];
-    for (auto& m : marks) CUDA_TRY(cudaEventCreate(&m));
-    for (int i = 0; i < 4; ++i) ms[i] = 0.0f;
-    for (int s = 0; s < steps; ++s) {
-        int rc = enqueueStep(b, dt, velIters, posIters, marks);
-        if (rc != B2GPU_OK) return rc;
-        CUDA_TRY(cudaStreamSynchronize(b->stream));
-        if (dt > 0.0f) {
-            for (int i = 0; i < 4; ++i) {
-                float t = 0.0f;
-                CUDA_TRY(cudaEventElapsedTime(&t, marks[i], marks[i + 1]));
-                ms[i] += t;
-            }
+    cudaEvent_t marks[kMaxStepKernels + 1];
+    for (int i = 0; i <= nk; ++i) CUDA_TRY(cudaEventCreate(&marks[i]));
+    for (int i = 0; i < nk; ++i) ms[i] = 0.0f;
+    int rc = B2GPU_OK;
+    for (int s = 0; s < steps && rc == B2GPU_OK; ++s) {
+        rc = enqueueStep(b, dt, velIters, posIters, marks);
+        if (rc != B2GPU_OK) break;
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) { rc = fail(B2GPU_ERR_CUDA, "step failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        for (int i = 0; i < nk; ++i) {
+            float t = 0.0f;
+            cudaEventElapsedTime(&t, marks[i], marks[i + 1]);
+            ms[i] += t;
         }
     }
-    for (auto& m : marks) cudaEventDestroy(m);
+    for (int i = 0; i <= nk; ++i) cudaEventDestroy(marks[i]);
+    if (count) *count = nk;
+    return rc;
+}
+
+const char* b2gpu_batch_kernel_name(b2gpu_batch* b, int32_t index) {
+    if (!b || index < 0 || index >= stepKernelCount(b)) return "";
+    return b->tileSolver ? kTileKernels[index] : kGenericKernels[index];
+}
+
+int b2gpu_batch_profile_steps(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIters, int32_t steps, float* ms) {
+    float k[kMaxStepKernels];
+    int32_t nk = 0;
+    int rc = b2gpu_batch_profile_kernels(b, dt, velIters, posIters, steps, k, kMaxStepKernels, &nk);
+    if (rc != B2GPU_OK) return rc;
+    ms[0] = k[0];
+    ms[1] = k[1];
+    ms[2] = 0.0f;
+    for (int i = 2; i < nk - 1; ++i) ms[2] += k[i];
+    ms[3] = k[nk - 1];
     return B2GPU_OK;
 }
 

@@ -64,7 +64,7 @@ typedef struct b2gpu_batch_desc {
     int32_t maxEvents;     /* per world per step */
     int32_t eventMask;     /* bit (1 << B2GPU_EVENT_*) per recorded event type; 0 = no listener */
     int32_t blockSize;     /* threads per CTA, multiple of 32; 0 = default */
-    int32_t reserved;
+    int32_t reserved;      /* bit 0: force the generic solver kernel (body state in global memory) */
 } b2gpu_batch_desc;
 
 /* Arena fields reachable through upload/download.  Host layout is world-major:
@@ -147,6 +147,11 @@ int b2gpu_batch_last_step_ms(b2gpu_batch* batch, float* ms);
 /* Runs `steps` steps with CUDA events around each kernel; ms[4] = collide, islands, solve, sync_pairs totals. */
 int b2gpu_batch_profile_steps(b2gpu_batch* batch, float dt, int32_t velocityIterations, int32_t positionIterations,
                               int32_t steps, float* ms);
+/* Same per kernel: ms[i] = total time of the i-th kernel of a step over `steps` steps, *count = kernels per step
+ * (<= capacity); b2gpu_batch_kernel_name(batch, i) names them. */
+int b2gpu_batch_profile_kernels(b2gpu_batch* batch, float dt, int32_t velocityIterations, int32_t positionIterations,
+                                int32_t steps, float* ms, int32_t capacity, int32_t* count);
+const char* b2gpu_batch_kernel_name(b2gpu_batch* batch, int32_t index);
 /* Number of kernel launches issued by this batch so far. */
 int64_t b2gpu_batch_launch_count(b2gpu_batch* batch);
 

@@ -26,10 +26,10 @@ def _ref_cls(oracles):
     return oracles.RefWorld if oracles.available("ref") else oracles.PortWorld
 
 
-def run_parity(oracles, scenes, steps, vi, pi, check_every=1, events=True, dt=1.0 / 60.0):
+def run_parity(oracles, scenes, steps, vi, pi, check_every=1, events=True, dt=1.0 / 60.0, generic_solver=False):
     Ref = _ref_cls(oracles)
     refs = [Ref(s, record_events=events) for s in scenes]
-    batch = WorldBatch(scenes, event_mask=EVENT_ALL if events else 0)
+    batch = WorldBatch(scenes, event_mask=EVENT_ALL if events else 0, generic_solver=generic_solver)
     for step in range(steps):
         for r in refs:
             r.step(dt, vi, pi)
@@ -70,6 +70,13 @@ def test_mixed_shapes(oracles):
     # BASELINE config 4: circles, convex polygons, chain terrain; many islands, sleeping per island
     scenes = [S.mixed(seed, flags=NOCCD) for seed in range(8)]
     run_parity(oracles, scenes, 400, 8, 3, check_every=9)
+
+
+def test_generic_solver_path(oracles):
+    """The fallback solver kernel (body state in global memory, used when a tile's body table exceeds shared
+    memory) stays bit-exact too."""
+    scenes = [S.pyramid(6 + (w % 3), flags=NOCCD, jitter_seed=w) for w in range(6)] + [S.mixed(1, flags=NOCCD)]
+    run_parity(oracles, scenes, 120, 8, 3, check_every=6, generic_solver=True)
 
 
 def test_edge_ground_pyramid(oracles):
