@@ -164,14 +164,16 @@ __device__ __forceinline__ bool FatOverlap(float4 a, float4 b) {  // b2TestOverl
 }
 
 // b2Body::SetAwake(true) — Box2D/Dynamics/b2Body.h:634-643
-__device__ __forceinline__ void WakeBody(const Col<int>& bodyFlags, const Col<float4>& bodySweep, int b) {
+__device__ __forceinline__ bool WakeBody(const Col<int>& bodyFlags, const Col<float4>& bodySweep, int b) {
     int f = bodyFlags[b];
     if ((f & kBodyAwake) == 0) {
         bodyFlags[b] = f | kBodyAwake;
         float4 s = bodySweep[b];
         s.w = 0.0f;  // m_sleepTime
         bodySweep[b] = s;
+        return true;
     }
+    return false;
 }
 
 struct EventSink {
@@ -225,100 +227,177 @@ __device__ __forceinline__ void EvaluateContact(const Arena& A, int tile, int la
     }
 }
 
-__global__ void __launch_bounds__(128) k_collide(Arena A) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    int tile = w >> 5, lane = w & 31;
-    if (tile >= A.numTiles) return;
-    size_t ws = (size_t)tile * kTile + lane;
-    A.eventCount[ws] = 0;
-    int n = A.contactCount[ws];
+// Result bits of CollideOne; one byte per contact carries them from phase 1 to phase 2 of k_collide
+// (point counts are 0..2: two bits each)
+enum : int { kResEvaluated = 1, kResDead = 2, kResWasTouching = 4, kResTouching = 8, kResCountShift = 4, kResOldCountShift = 6 };
+
+// One iteration of the loop in b2ContactManager::Collide for contact k, WITHOUT its side effects on other
+// objects (waking bodies, listener events): fat-AABB test -> mark for destruction, else b2Contact::Update's
+// manifold evaluation and impulse matching.  Returns kRes* | pointCount << 4 | old pointCount << 6.
+__device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, int k) {
     Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    const int4 a0 = cA[k];
+    int4 a = a0;
+    const int proxyA = a.x & 0xffff, proxyB = (a.x >> 16) & 0xffff;
+    const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+    int flags = a.z;
+    const int pointCountOld = (a.w >> 8) & 0xff;
+    const bool wasTouching = (flags & kContactTouching) != 0;
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    if (!FatOverlap(proxyFat[proxyA], proxyFat[proxyB])) {
+        a.z = flags | kContactDead;
+        cA[k] = a;
+        return kResDead | (wasTouching ? kResWasTouching : 0) | (pointCountOld << kResOldCountShift);
+    }
+    // b2Contact::Update
     Col<int4> cK = col(A.contactK, tile, A.NC, lane);
-    Col<int2> cS = col(A.contactS, tile, A.NC, lane);
     Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane);
     Col<float4> cP1 = col(A.contactP1, tile, A.NC, lane);
-    Col<float4> cN = col(A.contactN, tile, A.NC, lane);
-    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
-    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
     Col<float4> bodyXf = col(A.bodyXf, tile, A.NB, lane);
-    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    int4 kk = cK[k];
+    const float4 p0 = cP0[k], p1 = cP1[k];
+    const uint32_t oldKey0 = (uint32_t)kk.x, oldKey1 = (uint32_t)kk.y;
+    const float oldN0 = p0.z, oldT0 = p0.w, oldN1 = p1.z, oldT1 = p1.w;
+    flags |= kContactEnabled;
+    Manifold m;
+    m.pointCount = 0;
+    m.type = a.w & 0xff;
+    const int2 so = col(A.contactS, tile, A.NC, lane)[k];
+    EvaluateContact(A, tile, lane, &m, (a.w >> 16) & 0xf, so.x, so.y, proxyA, LoadXf(bodyXf, bodyA), LoadXf(bodyXf, bodyB));
+    const bool touching = m.pointCount > 0;
+    if (m.pointCount > 0) {
+        float nI = 0.0f, tI = 0.0f;
+        if (pointCountOld > 0 && oldKey0 == m.key0) { nI = oldN0; tI = oldT0; }
+        else if (pointCountOld > 1 && oldKey1 == m.key0) { nI = oldN1; tI = oldT1; }
+        const float4 np0 = make_float4(m.lp0.x, m.lp0.y, nI, tI);
+        if (__float_as_int(np0.x) != __float_as_int(p0.x) || __float_as_int(np0.y) != __float_as_int(p0.y) ||
+            __float_as_int(np0.z) != __float_as_int(p0.z) || __float_as_int(np0.w) != __float_as_int(p0.w))
+            cP0[k] = np0;
+        if (m.pointCount > 1) {
+            nI = 0.0f; tI = 0.0f;
+            if (pointCountOld > 0 && oldKey0 == m.key1) { nI = oldN0; tI = oldT0; }
+            else if (pointCountOld > 1 && oldKey1 == m.key1) { nI = oldN1; tI = oldT1; }
+            cP1[k] = make_float4(m.lp1.x, m.lp1.y, nI, tI);
+        }
+        col(A.contactN, tile, A.NC, lane)[k] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
+        if (kk.x != (int)m.key0 || kk.y != (int)m.key1) {
+            kk.x = (int)m.key0;
+            kk.y = (int)m.key1;
+            cK[k] = kk;
+        }
+    }
+    if (touching) flags |= kContactTouching; else flags &= ~kContactTouching;
+    a.z = flags;
+    a.w = (a.w & 0xffff0000) | (m.type & 0xff) | (m.pointCount << 8);
+    if (a.z != a0.z || a.w != a0.w) cA[k] = a;
+    return kResEvaluated | (wasTouching ? kResWasTouching : 0) | (touching ? kResTouching : 0) |
+           (m.pointCount << kResCountShift) | (pointCountOld << kResOldCountShift);
+}
+
+constexpr int kCollideWarps = 8;
+
+// CTA = one tile of 32 worlds (lane = world), kCollideWarps warps.
+// Phase 1 (all warps, contacts strided over warps): every contact that is active under the body flags the step
+//   started with is evaluated independently (CollideOne).
+// Phase 2 (warp 0, only lanes that need it): the reference's list-order side effects — SetAwake on touching
+//   changes and destruction, contacts that only became active because an earlier contact woke a body, listener
+//   events in list order, and the stable erase of destroyed contacts.
+__global__ void __launch_bounds__(kCollideWarps * 32, 2) k_collide(Arena A) {
+    __shared__ int sSummary[kTile];
+    extern __shared__ unsigned char sRes[];  // [NC][lane] result byte of phase 1
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t ws = (size_t)tile * kTile + lane;
+    if (warp == 0) {
+        sSummary[lane] = 0;
+        A.eventCount[ws] = 0;
+    }
+    const int n = A.contactCount[ws];
+    const int nMax = __reduce_max_sync(0xffffffffu, n);
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    unsigned char* tmp = sRes + lane;  // contact k at tmp[k * 32]
+    __syncthreads();
+
+    int summary = 0;  // 1: the list-order pass is needed, 2: island topology changed
+    for (int k = warp; k < nMax; k += kCollideWarps) {
+        if (k >= n) continue;
+        const int bodies = cA[k].y;
+        const int bfA = bodyFlags[bodies & 0xffff], bfB = bodyFlags[(bodies >> 16) & 0xffff];
+        const bool activeA = (bfA & kBodyAwake) && (bfA & kBodyTypeMask) != B2G_STATIC_BODY;
+        const bool activeB = (bfB & kBodyAwake) && (bfB & kBodyTypeMask) != B2G_STATIC_BODY;
+        int res = 0;
+        if (activeA || activeB) {
+            res = CollideOne(A, tile, lane, k);
+            const bool changed = ((res & kResWasTouching) != 0) != ((res & kResTouching) != 0);
+            if ((res & kResDead) || changed) summary |= 3;
+            if (A.eventMask) summary |= 1;
+        }
+        tmp[k * kTile] = (unsigned char)res;
+    }
+    if (summary) atomicOr(&sSummary[lane], summary);
+    __syncthreads();
+    if (warp != 0) return;
+    summary = sSummary[lane];
+    if (summary & 2) A.topoDirty[ws] = 1;
+    if ((summary & 1) == 0) return;
+
+    // ---- list-order pass (head of the world contact list = newest = highest index) ----
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
     Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
     EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws],
                  A.NE, A.eventMask};
     bool anyDead = false;
+    bool anyWake = false;  // a sleeping body has been woken in this pass
     for (int k = n - 1; k >= 0; --k) {
-        int4 a = cA[k];
-        int proxyA = a.x & 0xffff, proxyB = (a.x >> 16) & 0xffff;
-        int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
-        int flags = a.z;
-        int pointCountOld = (a.w >> 8) & 0xff;
-        int bfA = bodyFlags[bodyA], bfB = bodyFlags[bodyB];
-        bool activeA = (bfA & kBodyAwake) && (bfA & kBodyTypeMask) != B2G_STATIC_BODY;
-        bool activeB = (bfB & kBodyAwake) && (bfB & kBodyTypeMask) != B2G_STATIC_BODY;
-        if (!activeA && !activeB) continue;
-        if (!FatOverlap(proxyFat[proxyA], proxyFat[proxyB])) {
+        int res = tmp[k * kTile];
+        // nothing to do in list order: evaluated, alive, touching unchanged, no listener
+        if ((res & kResEvaluated) && ((res & kResWasTouching) != 0) == ((res & kResTouching) != 0) && !A.eventMask) continue;
+        if (res == 0 && !anyWake) continue;  // inactive at the start of the step and nobody has been woken since
+        const int4 a = cA[k];
+        const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+        if (res == 0) {  // skipped in phase 1: did an earlier contact of the list wake one of its bodies?
+            const int bfA = bodyFlags[bodyA], bfB = bodyFlags[bodyB];
+            const bool activeA = (bfA & kBodyAwake) && (bfA & kBodyTypeMask) != B2G_STATIC_BODY;
+            const bool activeB = (bfB & kBodyAwake) && (bfB & kBodyTypeMask) != B2G_STATIC_BODY;
+            if (!activeA && !activeB) continue;
+            res = CollideOne(A, tile, lane, k);
+            A.topoDirty[ws] = 1;
+        }
+        const int pointCount = (res >> kResCountShift) & 3, pointCountOld = (res >> kResOldCountShift) & 3;
+        const bool wasTouching = (res & kResWasTouching) != 0, touching = (res & kResTouching) != 0;
+        const int proxyA = a.x & 0xffff, proxyB = (a.x >> 16) & 0xffff;
+        if (res & kResDead) {
             // b2ContactManager::Destroy + b2Contact::Destroy
-            if (flags & kContactTouching) {
+            if (wasTouching) {
                 int pa = proxyInfo[proxyA], pb = proxyInfo[proxyB];
                 ev.push(kEventEnd, pa & 0xffff, (pa >> 16) & 0xffff, pb & 0xffff, (pb >> 16) & 0xffff, pointCountOld,
                         make_float4(0, 0, 0, 0));
             }
             if (pointCountOld > 0) {
-                WakeBody(bodyFlags, bodySweep, bodyA);
-                WakeBody(bodyFlags, bodySweep, bodyB);
+                anyWake |= WakeBody(bodyFlags, bodySweep, bodyA);
+                anyWake |= WakeBody(bodyFlags, bodySweep, bodyB);
             }
-            a.z = flags | kContactDead;
-            cA[k] = a;
             anyDead = true;
             continue;
         }
-        // b2Contact::Update
-        int4 kk = cK[k];
-        float4 p0 = cP0[k], p1 = cP1[k];
-        uint32_t oldKey0 = (uint32_t)kk.x, oldKey1 = (uint32_t)kk.y;
-        float oldN0 = p0.z, oldT0 = p0.w, oldN1 = p1.z, oldT1 = p1.w;
-        flags |= kContactEnabled;
-        bool wasTouching = (flags & kContactTouching) != 0;
-        Manifold m;
-        m.pointCount = 0;
-        m.type = a.w & 0xff;
-        int2 so = cS[k];
-        EvaluateContact(A, tile, lane, &m, (a.w >> 16) & 0xf, so.x, so.y, proxyA, LoadXf(bodyXf, bodyA),
-                        LoadXf(bodyXf, bodyB));
-        bool touching = m.pointCount > 0;
-        if (m.pointCount > 0) {
-            float nI = 0.0f, tI = 0.0f;
-            if (pointCountOld > 0 && oldKey0 == m.key0) { nI = oldN0; tI = oldT0; }
-            else if (pointCountOld > 1 && oldKey1 == m.key0) { nI = oldN1; tI = oldT1; }
-            cP0[k] = make_float4(m.lp0.x, m.lp0.y, nI, tI);
-            if (m.pointCount > 1) {
-                nI = 0.0f; tI = 0.0f;
-                if (pointCountOld > 0 && oldKey0 == m.key1) { nI = oldN0; tI = oldT0; }
-                else if (pointCountOld > 1 && oldKey1 == m.key1) { nI = oldN1; tI = oldT1; }
-                cP1[k] = make_float4(m.lp1.x, m.lp1.y, nI, tI);
-            }
-            cN[k] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
-            kk.x = (int)m.key0;
-            kk.y = (int)m.key1;
-            cK[k] = kk;
-        }
         if (touching != wasTouching) {
-            WakeBody(bodyFlags, bodySweep, bodyA);
-            WakeBody(bodyFlags, bodySweep, bodyB);
+            anyWake |= WakeBody(bodyFlags, bodySweep, bodyA);
+            anyWake |= WakeBody(bodyFlags, bodySweep, bodyB);
         }
-        if (touching) flags |= kContactTouching; else flags &= ~kContactTouching;
-        a.z = flags;
-        a.w = (a.w & 0xffff0000) | (m.type & 0xff) | (m.pointCount << 8);
-        cA[k] = a;
         if (A.eventMask) {
             int pa = proxyInfo[proxyA], pb = proxyInfo[proxyB];
             int fA = pa & 0xffff, chA = (pa >> 16) & 0xffff, fB = pb & 0xffff, chB = (pb >> 16) & 0xffff;
-            if (!wasTouching && touching) ev.push(kEventBegin, fA, chA, fB, chB, m.pointCount, make_float4(0, 0, 0, 0));
-            if (wasTouching && !touching) ev.push(kEventEnd, fA, chA, fB, chB, m.pointCount, make_float4(0, 0, 0, 0));
-            if (touching) ev.push(kEventPreSolve, fA, chA, fB, chB, m.pointCount, make_float4(0, 0, 0, 0));
+            if (!wasTouching && touching) ev.push(kEventBegin, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
+            if (wasTouching && !touching) ev.push(kEventEnd, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
+            if (touching) ev.push(kEventPreSolve, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
         }
     }
     if (anyDead) {  // stable erase keeps every list in the reference's order
+        Col<int4> cK = col(A.contactK, tile, A.NC, lane);
+        Col<int2> cS = col(A.contactS, tile, A.NC, lane);
+        Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane);
+        Col<float4> cP1 = col(A.contactP1, tile, A.NC, lane);
+        Col<float4> cN = col(A.contactN, tile, A.NC, lane);
         int wpos = 0;
         for (int k = 0; k < n; ++k) {
             int4 a = cA[k];
@@ -338,101 +417,155 @@ __global__ void __launch_bounds__(128) k_collide(Arena A) {
 }
 
 // =================================================================================================
-// k_islands
+// k_islands — b2World::Solve's island construction (Dynamics/b2World.cpp:381-537)
 // =================================================================================================
-__global__ void __launch_bounds__(128) k_islands(Arena A) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    int tile = w >> 5, lane = w & 31;
-    if (tile >= A.numTiles) return;
-    size_t ws = (size_t)tile * kTile + lane;
-    int nb = A.bodyCount[ws];
-    int nc = A.contactCount[ws];
-    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
-    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
-    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
-    Col<int> adjStart = col(A.bodyAdjStart, tile, A.NB + 1, lane);
-    Col<int> adj = col(A.bodyAdj, tile, 2 * A.NC, lane);
-    Col<int> stack = col(A.dfsStack, tile, A.NB, lane);
-    Col<int> iBodies = col(A.islandBodies, tile, A.NB + A.NC, lane);
-    Col<int> iBodyEnd = col(A.islandBodyEnd, tile, A.NB, lane);
-    Col<int> iContacts = col(A.islandContacts, tile, A.NC, lane);
-    Col<int> iContactEnd = col(A.islandContactEnd, tile, A.NB, lane);
+// The DFS of one world is a serial pointer chase, so its latency — not its throughput — sets the kernel's
+// duration.  A CTA takes a group of L consecutive worlds (L = 4..32, chosen by the host so that the group's
+// contact graph fits in shared memory), loads the graph with all its threads, then one thread per world builds
+// the per-body contact lists (head insertion, like b2ContactManager::AddPair does: newest contact first) and
+// runs the DFS out of shared memory; island arrays go straight to global memory.
+//
+// Islands are a function of the contact graph, the touching / enabled flags and the awake / active flags.
+// Every kernel that changes one of those raises topoDirty; a world whose flag is clear keeps last step's
+// islands (body order, contact order, island flags), which are exactly what b2World::Solve would rebuild.
+constexpr int kIslandThreads = 128;
+enum : int { kIbType = 3, kIbAwake = 4, kIbActive = 8, kIbIsland = 16, kIbWoken = 32 };  // smem body flag byte
+enum : int { kIcEligible = 1, kIcIsland = 2 };                                              // smem contact flag byte
 
-    // clear island flags; count contact edges per body
-    for (int b = 0; b < nb; ++b) {
-        bodyFlags[b] &= ~kBodyIsland;
-        adjStart[b] = 0;
-    }
-    for (int k = 0; k < nc; ++k) {
-        int4 a = cA[k];
-        if (a.z & kContactIsland) {
-            a.z &= ~kContactIsland;
-            cA[k] = a;
+__host__ __device__ inline size_t IslandSmemPerWorld(int NB, int NC) {
+    // next[2*NC] u16, pair[NC] 2 x u16, contact flag u8, head[NB] u16, stack[NB] u16, body flag u8
+    return (size_t)NC * 9 + (size_t)NB * 5;
+}
+
+__global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
+    extern __shared__ __align__(16) unsigned char ismem[];
+    __shared__ int sDirty[kTile];
+    const int g = blockIdx.x;            // group of L worlds
+    const int w0 = g * L;                // first world of the group
+    const int t = threadIdx.x;
+    const int NB = A.NB, NC = A.NC;
+    // shared arrays, element (index, l) at [index * L + l]
+    uint16_t* sNext = reinterpret_cast<uint16_t*>(ismem);              // [2 * NC][L]
+    uint16_t* sPair = sNext + (size_t)2 * NC * L;                      // [2 * NC][L]: bodyA at 2k, bodyB at 2k + 1
+    uint16_t* sHead = sPair + (size_t)2 * NC * L;                      // [NB][L]
+    uint16_t* sStack = sHead + (size_t)NB * L;                         // [NB][L]
+    unsigned char* sCF = reinterpret_cast<unsigned char*>(sStack + (size_t)NB * L);  // [NC][L]
+    unsigned char* sBF = sCF + (size_t)NC * L;                         // [NB][L]
+
+    if (t < L) {
+        const int w = w0 + t;
+        int d = 0;
+        if (w < A.numWorlds) {
+            d = A.topoDirty[w];
+            if (d) A.topoDirty[w] = 0;
         }
-        adjStart[a.y & 0xffff] += 1;
-        adjStart[(a.y >> 16) & 0xffff] += 1;
+        sDirty[t] = d;
     }
-    int run = 0;
-    for (int b = 0; b < nb; ++b) {
-        int c = adjStart[b];
-        adjStart[b] = run;
-        run += c;
-    }
-    // fill newest-first (= the order of b2Body::m_contactList); afterwards adjStart[b] is the END of b
-    for (int k = nc - 1; k >= 0; --k) {
-        int4 a = cA[k];
-        int bA = a.y & 0xffff, bB = (a.y >> 16) & 0xffff;
-        int pA = adjStart[bA];
-        adj[pA] = k;
-        adjStart[bA] = pA + 1;
-        int pB = adjStart[bB];
-        adj[pB] = k;
-        adjStart[bB] = pB + 1;
-    }
+    const int anyDirty = __syncthreads_or(t < L ? sDirty[t] : 0);
+    if (!anyDirty) return;
 
-    int islands = 0, nBodies = 0, nContacts = 0;
-    for (int seed = nb - 1; seed >= 0; --seed) {  // m_bodyList is head-inserted: newest first
-        int sf = bodyFlags[seed];
-        if (sf & kBodyIsland) continue;
-        if ((sf & kBodyAwake) == 0 || (sf & kBodyActive) == 0) continue;
-        if ((sf & kBodyTypeMask) == B2G_STATIC_BODY) continue;
-        int stackCount = 0;
-        stack[stackCount++] = seed;
-        bodyFlags[seed] = sf | kBodyIsland;
-        while (stackCount > 0) {
-            int b = stack[--stackCount];
-            iBodies[nBodies++] = b;
-            WakeBody(bodyFlags, bodySweep, b);
-            if ((bodyFlags[b] & kBodyTypeMask) == B2G_STATIC_BODY) continue;
-            int e0 = b == 0 ? 0 : adjStart[b - 1], e1 = adjStart[b];
-            for (int e = e0; e < e1; ++e) {
-                int k = adj[e];
-                int4 a = cA[k];
-                if (a.z & kContactIsland) continue;
-                if ((a.z & kContactEnabled) == 0 || (a.z & kContactTouching) == 0) continue;
-                iContacts[nContacts++] = k;
-                a.z |= kContactIsland;
-                cA[k] = a;
-                int bA = a.y & 0xffff, bB = (a.y >> 16) & 0xffff;
-                int other = bA == b ? bB : bA;
-                int of = bodyFlags[other];
-                if (of & kBodyIsland) continue;
-                stack[stackCount++] = other;
-                bodyFlags[other] = of | kBodyIsland;
+    // ---- load the contact graph and the body flags of the dirty worlds ----
+    const int l = t % L;                 // world within the group
+    const int w = w0 + l;
+    const int tile = w >> 5, lane = w & 31;
+    const size_t ws = (size_t)tile * kTile + lane;
+    const bool mine = w < A.numWorlds && sDirty[l] != 0;
+    const int nb = mine ? A.bodyCount[ws] : 0;
+    const int nc = mine ? A.contactCount[ws] : 0;
+    Col<int4> cA = col(A.contactA, tile, NC, lane);
+    Col<int> bodyFlags = col(A.bodyFlags, tile, NB, lane);
+    const int stride = kIslandThreads / L;
+    for (int k = t / L; k < nc; k += stride) {
+        const int4 a = cA[k];
+        sPair[(size_t)(2 * k) * L + l] = (uint16_t)(a.y & 0xffff);
+        sPair[(size_t)(2 * k + 1) * L + l] = (uint16_t)((a.y >> 16) & 0xffff);
+        sCF[(size_t)k * L + l] = ((a.z & kContactEnabled) && (a.z & kContactTouching)) ? kIcEligible : 0;
+    }
+    for (int b = t / L; b < nb; b += stride) {
+        const int f = bodyFlags[b];
+        sBF[(size_t)b * L + l] = (unsigned char)((f & kBodyTypeMask) | ((f & kBodyAwake) ? kIbAwake : 0) | ((f & kBodyActive) ? kIbActive : 0));
+        sHead[(size_t)b * L + l] = 0xffff;
+    }
+    __syncthreads();
+
+    // ---- one thread per world: contact lists, then the DFS ----
+    if (t < L && mine) {
+        // b2Body::m_contactList: head insertion in creation order -> newest (highest index) first
+        for (int k = 0; k < nc; ++k) {
+            const int bA = sPair[(size_t)(2 * k) * L + l], bB = sPair[(size_t)(2 * k + 1) * L + l];
+            sNext[(size_t)(2 * k) * L + l] = sHead[(size_t)bA * L + l];
+            sHead[(size_t)bA * L + l] = (uint16_t)k;
+            sNext[(size_t)(2 * k + 1) * L + l] = sHead[(size_t)bB * L + l];
+            sHead[(size_t)bB * L + l] = (uint16_t)k;
+        }
+        Col<int> iBodies = col(A.islandBodies, tile, NB + NC, lane);
+        Col<int> iBodyEnd = col(A.islandBodyEnd, tile, NB, lane);
+        Col<int> iContacts = col(A.islandContacts, tile, NC, lane);
+        Col<int> iContactEnd = col(A.islandContactEnd, tile, NB, lane);
+        int islands = 0, nBodies = 0, nContacts = 0;
+        for (int seed = nb - 1; seed >= 0; --seed) {  // m_bodyList is head-inserted: newest first
+            const int sf = sBF[(size_t)seed * L + l];
+            if (sf & kIbIsland) continue;
+            if ((sf & kIbAwake) == 0 || (sf & kIbActive) == 0) continue;
+            if ((sf & kIbType) == B2G_STATIC_BODY) continue;
+            int stackCount = 0;
+            sStack[(size_t)(stackCount++) * L + l] = (uint16_t)seed;
+            sBF[(size_t)seed * L + l] = (unsigned char)(sf | kIbIsland);
+            const int islandBody0 = nBodies;
+            while (stackCount > 0) {
+                const int b = sStack[(size_t)(--stackCount) * L + l];
+                iBodies[nBodies++] = b;
+                int bf = sBF[(size_t)b * L + l];
+                if ((bf & kIbAwake) == 0) {  // b2Body::SetAwake(true)
+                    bf |= kIbAwake | kIbWoken;
+                    sBF[(size_t)b * L + l] = (unsigned char)bf;
+                }
+                if ((bf & kIbType) == B2G_STATIC_BODY) continue;
+                for (int k = sHead[(size_t)b * L + l]; k != 0xffff;) {
+                    const int bA = sPair[(size_t)(2 * k) * L + l], bB = sPair[(size_t)(2 * k + 1) * L + l];
+                    const int side = bA == b ? 0 : 1;
+                    const int kn = sNext[(size_t)(2 * k + side) * L + l];
+                    const int cf = sCF[(size_t)k * L + l];
+                    if (cf == kIcEligible) {  // touching, enabled, not yet in an island
+                        iContacts[nContacts++] = k;
+                        sCF[(size_t)k * L + l] = kIcEligible | kIcIsland;
+                        const int other = side == 0 ? bB : bA;
+                        const int of = sBF[(size_t)other * L + l];
+                        if ((of & kIbIsland) == 0) {
+                            sStack[(size_t)(stackCount++) * L + l] = (uint16_t)other;
+                            sBF[(size_t)other * L + l] = (unsigned char)(of | kIbIsland);
+                        }
+                    }
+                    k = kn;
+                }
             }
+            // statics may join the next island
+            for (int i = islandBody0; i < nBodies; ++i) {
+                const int b = iBodies[i];
+                const int f = sBF[(size_t)b * L + l];
+                if ((f & kIbType) == B2G_STATIC_BODY) sBF[(size_t)b * L + l] = (unsigned char)(f & ~kIbIsland);
+            }
+            iBodyEnd[islands] = nBodies;
+            iContactEnd[islands] = nContacts;
+            ++islands;
         }
-        // statics may join the next island
-        int b0 = islands == 0 ? 0 : iBodyEnd[islands - 1];
-        for (int i = b0; i < nBodies; ++i) {
-            int b = iBodies[i];
-            int f = bodyFlags[b];
-            if ((f & kBodyTypeMask) == B2G_STATIC_BODY) bodyFlags[b] = f & ~kBodyIsland;
-        }
-        iBodyEnd[islands] = nBodies;
-        iContactEnd[islands] = nContacts;
-        ++islands;
+        A.islandCount[ws] = islands;
     }
-    A.islandCount[ws] = islands;
+    __syncthreads();
+
+    // ---- write the island / awake flags back ----
+    Col<float4> bodySweep = col(A.bodySweep, tile, NB, lane);
+    for (int b = t / L; b < nb; b += stride) {
+        const int sf = sBF[(size_t)b * L + l];
+        const int f = bodyFlags[b];
+        int nf = (f & ~kBodyIsland) | ((sf & kIbIsland) ? kBodyIsland : 0) | ((sf & kIbAwake) ? kBodyAwake : 0);
+        if (nf != f) bodyFlags[b] = nf;
+        if (sf & kIbWoken) {
+            float4 s = bodySweep[b];
+            s.w = 0.0f;  // m_sleepTime
+            bodySweep[b] = s;
+        }
+    }
 }
 
 // =================================================================================================
@@ -967,6 +1100,7 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
                 bodySweep[b] = sw;
             }
             if (minSleepTime >= kTimeToSleep && positionSolved) {
+                A.topoDirty[ws] = 1;
                 for (int i = b0; i < b1; ++i) {  // b2Body::SetAwake(false), b2Body.h:644-652
                     int b = iBodies[i];
                     bodyFlags[b] &= ~kBodyAwake;
@@ -1010,31 +1144,36 @@ struct PairCtx {
     size_t ws;
     Col<int4> cA, cK;
     Col<int2> cS;
-    Col<int> proxyInfo, fixtureInfo, fixtureShape, bodyFlags, adjStart, adj;
+    Col<int> proxyInfo, fixtureInfo, fixtureShape, bodyFlags;
     Col<float2> fixtureMat;
     Col<int2> fixtureFilter;
     Col<float4> bodySweep;
     int nc;          // running contact count
     int ncAtStart;   // contacts that existed before this UpdatePairs
-    bool useCsr;
 };
 
-// b2ContactManager::AddPair for proxies a < b (ascending tree id)
-__device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB) {
+__device__ __forceinline__ PairCtx MakePairCtx(const Arena& A, int tile, int lane) {
+    const size_t ws = (size_t)tile * kTile + lane;
+    PairCtx c{A, tile, lane, ws,
+              col(A.contactA, tile, A.NC, lane), col(A.contactK, tile, A.NC, lane), col(A.contactS, tile, A.NC, lane),
+              col(A.proxyInfo, tile, A.NP, lane), col(A.fixtureInfo, tile, A.NF, lane), col(A.fixtureShape, tile, A.NF, lane),
+              col(A.bodyFlags, tile, A.NB, lane), col(A.fixtureMat, tile, A.NF, lane), col(A.fixtureFilter, tile, A.NF, lane),
+              col(A.bodySweep, tile, A.NB, lane), 0, 0};
+    c.nc = A.contactCount[ws];
+    c.ncAtStart = c.nc;
+    return c;
+}
+
+// b2ContactManager::AddPair for proxies a < b (ascending tree id).  `knownNew`: the caller has already
+// established that no contact between the two proxies exists (the walk of bodyB's edge list in the reference).
+__device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB, bool knownNew) {
     int pa = c.proxyInfo[proxyA], pb = c.proxyInfo[proxyB];
     int fixtureA = pa & 0xffff, fixtureB = pb & 0xffff;
     int fiA = c.fixtureInfo[fixtureA], fiB = c.fixtureInfo[fixtureB];
     int bodyA = fiA & 0xffff, bodyB = fiB & 0xffff;
     if (bodyA == bodyB) return;
-    // does a contact already exist? (walk of bodyB's edge list in the reference)
-    const int key1 = proxyA | (proxyB << 16), key2 = proxyB | (proxyA << 16);
-    if (c.useCsr) {
-        int e0 = bodyB == 0 ? 0 : c.adjStart[bodyB - 1], e1 = c.adjStart[bodyB];
-        for (int e = e0; e < e1; ++e) {
-            int x = c.cA[c.adj[e]].x;
-            if (x == key1 || x == key2) return;
-        }
-    } else {
+    if (!knownNew) {
+        const int key1 = proxyA | (proxyB << 16), key2 = proxyB | (proxyA << 16);
         for (int k = 0; k < c.ncAtStart; ++k) {
             int x = c.cA[k].x;
             if (x == key1 || x == key2) return;
@@ -1062,6 +1201,7 @@ __device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB) {
     float friction = Sqrt(matA.x * matB.x);                      // b2MixFriction
     float restitution = matA.y > matB.y ? matA.y : matB.y;       // b2MixRestitution
     int k = c.nc++;
+    c.A.topoDirty[c.ws] = 1;
     c.cA[k] = make_int4(proxyA | (proxyB << 16), bodyA | (bodyB << 16), kContactEnabled, (tA | (tB << 2)) << 16);
     c.cK[k] = make_int4(0, 0, __float_as_int(friction), __float_as_int(restitution));
     c.cS[k] = make_int2(c.fixtureShape[fixtureA], c.fixtureShape[fixtureB]);
@@ -1069,13 +1209,78 @@ __device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB) {
     WakeBody(c.bodyFlags, c.bodySweep, bodyB);
 }
 
-template <bool kSync>
-__global__ void __launch_bounds__(128) k_sync_pairs(Arena A, float dt, int useCsr) {
+// b2BroadPhase::UpdatePairs for one world by one thread: the move buffer is read from the proxyMoved flags and
+// the pairs are produced directly in (proxyIdA, proxyIdB) order.  Used for the initial FindNewContacts of a
+// freshly built world and as the overflow path of k_sync_pairs.
+__device__ __noinline__ void UpdatePairsOrdered(const Arena* Ap, int tile, int lane) {
+    const Arena& A = *Ap;
+    const size_t ws = (size_t)tile * kTile + lane;
+    const int np = A.proxyCount[ws];
+    Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    Col<int> movedList = col(A.movedList, tile, A.NP, lane);
+    int nMoved = 0;
+    for (int p = 0; p < np; ++p) {
+        if (proxyMoved[p]) {
+            movedList[nMoved++] = p;
+            proxyMoved[p] = 0;
+        }
+    }
+    if (nMoved == 0) return;
+    PairCtx c = MakePairCtx(A, tile, lane);
+    int mi = 0;  // first moved proxy with index > a
+    for (int a = 0; a < np; ++a) {
+        while (mi < nMoved && movedList[mi] <= a) ++mi;
+        bool aMoved = mi > 0 && movedList[mi - 1] == a;
+        float4 fatA = proxyFat[a];
+        if (aMoved) {
+            for (int b = a + 1; b < np; ++b)
+                if (FatOverlap(proxyFat[b], fatA)) AddPair(c, a, b, false);
+        } else {
+            for (int m = mi; m < nMoved; ++m) {
+                int b = movedList[m];
+                if (FatOverlap(fatA, proxyFat[b])) AddPair(c, a, b, false);
+            }
+        }
+    }
+    A.contactCount[ws] = c.nc;
+}
+
+// b2World::Step's leading `if (m_flags & e_newFixture) FindNewContacts()` for freshly built worlds.
+__global__ void __launch_bounds__(128) k_find_new_contacts(Arena A) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     int tile = w >> 5, lane = w & 31;
     if (tile >= A.numTiles) return;
-    size_t ws = (size_t)tile * kTile + lane;
-    const int np = A.proxyCount[ws];
+    UpdatePairsOrdered(&A, tile, lane);
+}
+
+// k_sync_pairs: CTA = one tile (lane = world), kPairWarps warps.
+//   A  all warps, proxies strided: b2Body::SynchronizeFixtures -> b2Fixture::Synchronize -> b2DynamicTree::MoveProxy
+//      (swept AABB, containment test against the fat AABB, re-fattening); moved proxies go to a per-world list.
+//   B  all warps: every moved proxy is tested against every proxy of its world (the tree query of UpdatePairs);
+//      hits become candidate pairs (min, max).
+//   C  warp 0: sort + dedupe the candidates (std::sort + the duplicate skip of UpdatePairs).
+//   D  all warps: one pass over the contact array marks candidates that already have a contact.
+//   E  warp 0: b2ContactManager::AddPair for the remaining candidates in sorted order.
+// Worlds whose move buffer or candidate list overflows the shared-memory lists take UpdatePairsOrdered instead.
+constexpr int kPairWarps = 8;
+constexpr int kMaxMoved = 64;     // per world, else overflow path
+constexpr int kMaxCand = 256;     // per world, else overflow path
+
+__global__ void __launch_bounds__(kPairWarps * 32) k_sync_pairs(Arena A, float dt) {
+    __shared__ uint16_t sMoved[kMaxMoved][kTile];
+    __shared__ uint32_t sCand[kMaxCand][kTile];
+    __shared__ unsigned char sExists[kMaxCand][kTile];
+    __shared__ int sNMoved[kTile], sNCand[kTile];
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t ws = (size_t)tile * kTile + lane;
+    const bool live = tile * kTile + lane < A.numWorlds;
+    const int np = live ? A.proxyCount[ws] : 0;
+    if (warp == 0) {
+        sNMoved[lane] = 0;
+        sNCand[lane] = 0;
+    }
+    __syncthreads();
     Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
     Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
     Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
@@ -1086,80 +1291,130 @@ __global__ void __launch_bounds__(128) k_sync_pairs(Arena A, float dt, int useCs
     Col<float4> bodySweep0 = col(A.bodySweep0, tile, A.NB, lane);
     Col<float4> bodyMass = col(A.bodyMass, tile, A.NB, lane);
     Col<float2> chainVerts = col(A.chainVerts, tile, A.NV, lane);
-    Col<int> movedList = col(A.movedList, tile, A.NP, lane);
 
-    if (kSync) {
-        for (int p = 0; p < np; ++p) {
-            int pi = proxyInfo[p];
-            int fixture = pi & 0xffff, child = (pi >> 16) & 0xffff;
-            int fi = fixtureInfo[fixture];
-            int body = fi & 0xffff;
-            int bf = bodyFlags[body];
-            if ((bf & kBodyIsland) == 0) continue;          // not in an island: did not move
-            if ((bf & kBodyTypeMask) == B2G_STATIC_BODY) continue;
-            int shapeType = (fi >> 16) & 3;
-            const float* sw = A.shapeWords + ((size_t)tile * A.NS + fixtureShape[fixture]) * kTile + lane;
-            float4 s0 = bodySweep0[body];
-            float4 ms = bodyMass[body];
-            Xf xf1;
-            xf1.q = MakeRot(s0.z);
-            xf1.p = V2(s0.x, s0.y) - Mul(xf1.q, V2(ms.z, ms.w));
-            Xf xf2 = LoadXf(bodyXf, body);
-            Vec2 lo1, hi1, lo2, hi2;
-            ShapeAABB(sw, shapeType, chainVerts, child, xf1, &lo1, &hi1);
-            ShapeAABB(sw, shapeType, chainVerts, child, xf2, &lo2, &hi2);
-            Vec2 lo = Min(lo1, lo2), hi = Max(hi1, hi2);
-            Vec2 displacement = xf2.p - xf1.p;
-            float4 fat = proxyFat[p];
-            // b2AABB::Contains
-            bool contains = fat.x <= lo.x && fat.y <= lo.y && hi.x <= fat.z && hi.y <= fat.w;
-            if (contains) continue;
-            Vec2 r = V2(kAabbExtension, kAabbExtension);
-            lo = lo - r;
-            hi = hi + r;
-            Vec2 d = kAabbMultiplier * displacement;
-            if (d.x < 0.0f) lo.x += d.x; else hi.x += d.x;
-            if (d.y < 0.0f) lo.y += d.y; else hi.y += d.y;
-            proxyFat[p] = make_float4(lo.x, lo.y, hi.x, hi.y);
-            proxyMoved[p] = 1;
-        }
+    // ---- A: synchronize fixtures ----
+    const int npMax = __reduce_max_sync(0xffffffffu, np);
+    for (int p = warp; p < npMax; p += kPairWarps) {
+        if (p >= np) continue;
+        int pi = proxyInfo[p];
+        int fixture = pi & 0xffff, child = (pi >> 16) & 0xffff;
+        int fi = fixtureInfo[fixture];
+        int body = fi & 0xffff;
+        int bf = bodyFlags[body];
+        if ((bf & kBodyIsland) == 0) continue;          // not in an island: did not move
+        if ((bf & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+        int shapeType = (fi >> 16) & 3;
+        const float* sw = A.shapeWords + ((size_t)tile * A.NS + fixtureShape[fixture]) * kTile + lane;
+        float4 s0 = bodySweep0[body];
+        float4 ms = bodyMass[body];
+        Xf xf1;
+        xf1.q = MakeRot(s0.z);
+        xf1.p = V2(s0.x, s0.y) - Mul(xf1.q, V2(ms.z, ms.w));
+        Xf xf2 = LoadXf(bodyXf, body);
+        Vec2 lo1, hi1, lo2, hi2;
+        ShapeAABB(sw, shapeType, chainVerts, child, xf1, &lo1, &hi1);
+        ShapeAABB(sw, shapeType, chainVerts, child, xf2, &lo2, &hi2);
+        Vec2 lo = Min(lo1, lo2), hi = Max(hi1, hi2);
+        Vec2 displacement = xf2.p - xf1.p;
+        float4 fat = proxyFat[p];
+        // b2AABB::Contains
+        bool contains = fat.x <= lo.x && fat.y <= lo.y && hi.x <= fat.z && hi.y <= fat.w;
+        if (contains) continue;
+        Vec2 r = V2(kAabbExtension, kAabbExtension);
+        lo = lo - r;
+        hi = hi + r;
+        Vec2 d = kAabbMultiplier * displacement;
+        if (d.x < 0.0f) lo.x += d.x; else hi.x += d.x;
+        if (d.y < 0.0f) lo.y += d.y; else hi.y += d.y;
+        proxyFat[p] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        proxyMoved[p] = 1;  // b2BroadPhase::BufferMove
+        int slot = atomicAdd(&sNMoved[lane], 1);
+        if (slot < kMaxMoved) sMoved[slot][lane] = (uint16_t)p;
     }
+    __syncthreads();  // also orders the fat-AABB writes before the reads below
+    const int nMoved = sNMoved[lane];
+    if (__syncthreads_or(nMoved) == 0) {
+        if (warp == 0 && live) {
+            if (dt > 0.0f) A.invDt0[ws] = Div(1.0f, dt);
+            A.stepCount[ws] += 1;
+        }
+        return;
+    }
+    const bool overflowMoved = nMoved > kMaxMoved;
 
-    // ---- b2BroadPhase::UpdatePairs: pairs are produced directly in (proxyIdA, proxyIdB) order ----
-    int nMoved = 0;
-    for (int p = 0; p < np; ++p) {
-        if (proxyMoved[p]) {
-            movedList[nMoved++] = p;
-            proxyMoved[p] = 0;
-        }
-    }
-    if (nMoved > 0) {
-        PairCtx c{A, tile, lane, ws,
-                  col(A.contactA, tile, A.NC, lane), col(A.contactK, tile, A.NC, lane), col(A.contactS, tile, A.NC, lane),
-                  proxyInfo, fixtureInfo, fixtureShape, bodyFlags,
-                  col(A.bodyAdjStart, tile, A.NB + 1, lane), col(A.bodyAdj, tile, 2 * A.NC, lane),
-                  col(A.fixtureMat, tile, A.NF, lane), col(A.fixtureFilter, tile, A.NF, lane),
-                  col(A.bodySweep, tile, A.NB, lane), 0, 0, useCsr != 0};
-        c.nc = A.contactCount[ws];
-        c.ncAtStart = c.nc;
-        int mi = 0;  // first moved proxy with index > a
-        for (int a = 0; a < np; ++a) {
-            while (mi < nMoved && movedList[mi] <= a) ++mi;
-            bool aMoved = mi > 0 && movedList[mi - 1] == a;
-            float4 fatA = proxyFat[a];
-            if (aMoved) {
-                for (int b = a + 1; b < np; ++b)
-                    if (FatOverlap(proxyFat[b], fatA)) AddPair(c, a, b);
-            } else {
-                for (int m = mi; m < nMoved; ++m) {
-                    int b = movedList[m];
-                    if (FatOverlap(fatA, proxyFat[b])) AddPair(c, a, b);
-                }
+    // ---- B: candidate pairs ----
+    if (nMoved > 0 && !overflowMoved) {
+        for (int j = 0; j < nMoved; ++j) {
+            const int m = sMoved[j][lane];
+            const float4 fatM = proxyFat[m];
+            for (int q = warp; q < np; q += kPairWarps) {
+                if (q == m) continue;
+                if (!FatOverlap(fatM, proxyFat[q])) continue;
+                int slot = atomicAdd(&sNCand[lane], 1);
+                if (slot < kMaxCand) sCand[slot][lane] = q < m ? ((uint32_t)q << 16 | (uint32_t)m) : ((uint32_t)m << 16 | (uint32_t)q);
             }
         }
-        A.contactCount[ws] = c.nc;
     }
-    if (kSync) {
+    __syncthreads();
+    int nCand = sNCand[lane];
+    const bool overflow = overflowMoved || nCand > kMaxCand;
+
+    // ---- C: sort + dedupe (insertion sort; the lists are short) ----
+    if (warp == 0 && !overflow && nCand > 0) {
+        for (int i = 1; i < nCand; ++i) {
+            uint32_t v = sCand[i][lane];
+            int j = i - 1;
+            while (j >= 0 && sCand[j][lane] > v) {
+                sCand[j + 1][lane] = sCand[j][lane];
+                --j;
+            }
+            sCand[j + 1][lane] = v;
+        }
+        int u = 0;
+        for (int i = 0; i < nCand; ++i) {
+            uint32_t v = sCand[i][lane];
+            if (u > 0 && sCand[u - 1][lane] == v) continue;
+            sCand[u][lane] = v;
+            sExists[u][lane] = 0;
+            ++u;
+        }
+        nCand = u;
+        sNCand[lane] = u;
+    }
+    __syncthreads();
+    nCand = sNCand[lane];
+
+    // ---- D: which candidates already have a contact ----
+    const int nc = live ? A.contactCount[ws] : 0;
+    if (!overflow && nCand > 0) {
+        Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+        for (int k = warp; k < nc; k += kPairWarps) {
+            const uint32_t x = (uint32_t)cA[k].x;  // proxyA | proxyB << 16, either order
+            const uint32_t y = (x >> 16) | (x << 16);
+            for (int c = 0; c < nCand; ++c) {
+                const uint32_t v = sCand[c][lane];
+                if (v == x || v == y) sExists[c][lane] = 1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- E: AddPair in sorted order ----
+    if (warp == 0 && live) {
+        if (overflow) {
+            UpdatePairsOrdered(&A, tile, lane);
+        } else if (nMoved > 0) {
+            for (int j = 0; j < nMoved; ++j) proxyMoved[sMoved[j][lane]] = 0;  // the move buffer is consumed
+            if (nCand > 0) {
+                PairCtx c = MakePairCtx(A, tile, lane);
+                for (int i = 0; i < nCand; ++i) {
+                    if (sExists[i][lane]) continue;
+                    const uint32_t v = sCand[i][lane];
+                    AddPair(c, (int)(v >> 16), (int)(v & 0xffff), true);
+                }
+                if (c.nc != c.ncAtStart) A.contactCount[ws] = c.nc;
+            }
+        }
         if (dt > 0.0f) A.invDt0[ws] = Div(1.0f, dt);
         A.stepCount[ws] += 1;
     }

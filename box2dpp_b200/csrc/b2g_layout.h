@@ -68,6 +68,7 @@ struct Arena {
     int* eventCount;
     int* islandCount;    // last step (diagnostics)
     int* stepCount;
+    int* topoDirty;      // != 0: contact graph / touching / awake flags changed since the islands were built
 
     // ---- bodies [tile][NB][lane] ----
     float4* bodyXf;      // m_xf: p.x p.y q.s q.c
@@ -105,9 +106,6 @@ struct Arena {
     float4* contactN;    // localNormal.xy, localPoint.xy
 
     // ---- per-step temporaries ----
-    int* bodyAdjStart;   // [tile][NB+1][lane] CSR of contact edges per body (newest first)
-    int* bodyAdj;        // [tile][2*NC][lane] contact index per edge
-    int* dfsStack;       // [tile][NB][lane]
     int* movedList;      // [tile][NP][lane] ascending indices of the proxies in the move buffer
     int* islandBodies;   // [tile][NB+NC][lane] bodies of all islands, concatenated (statics repeat)
     int* islandBodyEnd;  // [tile][NB][lane]   end offset into islandBodies per island

@@ -908,6 +908,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_solve_finalize(Arena A, flo
         }
         const bool positionSolved = (gDone[(size_t)(isl >> 5) * kTile] >> (isl & 31) & 1) != 0;
         if (minSleepTime >= kTimeToSleep && positionSolved) {
+            A.topoDirty[ws] = 1;
             for (int i = b0; i < b1; ++i) {  // b2Body::SetAwake(false), b2Body.h:644-652
                 int b = iBodies[i];
                 bodyFlags[b] &= ~kBodyAwake;

@@ -77,6 +77,7 @@ __global__ void k_apply_forces(Arena A, const float* __restrict__ forces) {
     if ((flags & kBodyAwake) == 0) {
         A.bodyFlags[idx] = flags | kBodyAwake;
         A.bodySweep[idx].w = 0.0f;
+        A.topoDirty[(size_t)tile * kTile + lane] = 1;
     }
     float4 cur = A.bodyForce[idx];
     A.bodyForce[idx] = make_float4(cur.x + fx, cur.y + fy, cur.z + tq, 0.0f);
@@ -166,6 +167,8 @@ struct b2gpu_batch {
     int blockSize = 32;
     bool tileSolver = false;       // b2g_solve.cuh path: the tile's body table fits in shared memory
     size_t solveSmem = 0;
+    int islandLanes = 32;          // worlds per CTA of k_islands
+    size_t islandSmem = 0;
     int64_t launches = 0;
     size_t arenaBytes = 0;
     // graph of one step, keyed by its parameters
@@ -211,6 +214,8 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(gravity, 1, float2); ALLOC(worldFlags, 1, int); ALLOC(invDt0, 1, float);
     ALLOC(bodyCount, 1, int); ALLOC(proxyCount, 1, int); ALLOC(contactCount, 1, int);
     ALLOC(status, 1, int); ALLOC(eventCount, 1, int); ALLOC(islandCount, 1, int); ALLOC(stepCount, 1, int);
+    ALLOC(topoDirty, 1, int);
+    CUDA_TRY(cudaMemsetAsync(A.topoDirty, 1, (size_t)A.numTiles * kTile * sizeof(int), b->stream));
     ALLOC(bodyXf, A.NB, float4); ALLOC(bodySweep, A.NB, float4); ALLOC(bodySweep0, A.NB, float4);
     ALLOC(bodyVel, A.NB, float4); ALLOC(bodyForce, A.NB, float4); ALLOC(bodyMass, A.NB, float4);
     ALLOC(bodyDamp, A.NB, float4); ALLOC(bodyFlags, A.NB, int); ALLOC(bodyIsland, A.NB, int);
@@ -220,7 +225,6 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(shapeWords, A.NS, float); ALLOC(chainVerts, A.NV, float2);
     ALLOC(contactA, A.NC, int4); ALLOC(contactK, A.NC, int4); ALLOC(contactS, A.NC, int2);
     ALLOC(contactP0, A.NC, float4); ALLOC(contactP1, A.NC, float4); ALLOC(contactN, A.NC, float4);
-    ALLOC(bodyAdjStart, A.NB + 1, int); ALLOC(bodyAdj, 2 * A.NC, int); ALLOC(dfsStack, A.NB, int);
     ALLOC(movedList, A.NP, int);
     ALLOC(islandBodies, A.NB + A.NC, int); ALLOC(islandBodyEnd, A.NB, int);
     ALLOC(islandContacts, A.NC, int); ALLOC(islandContactEnd, A.NB, int);
@@ -310,6 +314,35 @@ int transferField(b2gpu_batch* b, int field, void* host, int firstWorld, int wor
     return B2GPU_OK;
 }
 
+// Shared-memory configuration of the step kernels for this batch's per-world capacities.
+int configureKernels(b2gpu_batch* b) {
+    const b2gpu_batch_desc* desc = &b->desc;
+    int maxSmem = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
+    // Solver path: the tile path keeps the b2Velocity / b2Position table of 32 worlds in shared memory.
+    b->solveSmem = SolveSmemBytes(desc->maxBodies);
+    b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0;
+    if ((size_t)desc->maxContacts * kTile > (size_t)maxSmem - 1024)
+        return fail(B2GPU_ERR_CAPACITY, "maxContacts %d exceeds the collide kernel's shared-memory budget (%d)",
+                    desc->maxContacts, (maxSmem - 1024) / kTile);
+    CUDA_TRY(cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, desc->maxContacts * kTile));
+    if (b->tileSolver) {
+        CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_solve_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
+    }
+    // k_islands: as many worlds per CTA as keep two or more CTAs resident per SM (the DFS is latency bound)
+    const size_t perWorld = IslandSmemPerWorld(desc->maxBodies, desc->maxContacts);
+    int L = 32;
+    while (L > 1 && perWorld * L > (size_t)100 * 1024) L >>= 1;
+    if (perWorld * L > (size_t)maxSmem - 1024)
+        return fail(B2GPU_ERR_CAPACITY, "a world with %d bodies / %d contacts exceeds the island kernel's shared memory",
+                    desc->maxBodies, desc->maxContacts);
+    b->islandLanes = L;
+    b->islandSmem = perWorld * L;
+    CUDA_TRY(cudaFuncSetAttribute(k_islands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->islandSmem));
+    return B2GPU_OK;
+}
+
 // Kernel names in launch order of one step (b2gpu_batch_profile_kernels reports times in this order).
 const char* const kTileKernels[] = {"k_collide", "k_islands", "k_solve_prepare", "k_solve_velocity", "k_solve_integrate",
                                     "k_solve_position", "k_solve_finalize", "k_sync_pairs"};
@@ -326,18 +359,18 @@ int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_
     const unsigned blocks = (unsigned)(((size_t)b->A.numTiles * kTile + threads - 1) / threads);
     cudaStream_t st = b->stream;
     if (b->needInitialPairs) {  // if (m_flags & e_newFixture) FindNewContacts()
-        k_sync_pairs<false><<<blocks, threads, 0, st>>>(b->A, dt, 0);
+        k_find_new_contacts<<<blocks, threads, 0, st>>>(b->A);
         b->needInitialPairs = false;
         b->launches++;
     }
     int m = 0;
     auto mark = [&]() { if (marks) cudaEventRecord(marks[m++], st); };
     mark();
-    k_collide<<<blocks, threads, 0, st>>>(b->A);
+    k_collide<<<tiles, kCollideWarps * 32, (size_t)b->A.NC * kTile, st>>>(b->A);
     b->launches++;
     mark();
     if (dt > 0.0f) {
-        k_islands<<<blocks, threads, 0, st>>>(b->A);
+        k_islands<<<(unsigned)((b->A.numTiles * kTile + b->islandLanes - 1) / b->islandLanes), kIslandThreads, b->islandSmem, st>>>(b->A, b->islandLanes);
         mark();
         if (b->tileSolver) {
             k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
@@ -356,7 +389,7 @@ int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_
             mark();
             b->launches++;
         }
-        k_sync_pairs<true><<<blocks, threads, 0, st>>>(b->A, dt, 1);
+        k_sync_pairs<<<tiles, kPairWarps * 32, 0, st>>>(b->A, dt);
         mark();
         b->launches += 2;
     }
@@ -395,15 +428,9 @@ int b2gpu_batch_create(const b2gpu_batch_desc* desc, b2gpu_batch** out) {
     b->desc = *desc;
     b->blockSize = desc->blockSize ? desc->blockSize : 32;
     memset(&b->A, 0, sizeof(b->A));
-    {   // Solver path: the tile path keeps the b2Velocity / b2Position table of 32 worlds in shared memory.
-        int maxSmem = 0;
-        CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
-        b->solveSmem = SolveSmemBytes(desc->maxBodies);
-        b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0;
-        if (b->tileSolver) {
-            CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
-            CUDA_TRY(cudaFuncSetAttribute(k_solve_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
-        }
+    {
+        int rc = configureKernels(b);
+        if (rc != B2GPU_OK) { delete b; return rc; }
     }
     e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete b; return fail(B2GPU_ERR_CUDA, "stream create failed: %s", cudaGetErrorString(e)); }
@@ -437,6 +464,8 @@ int b2gpu_batch_upload_field(b2gpu_batch* b, int32_t field, const void* host, in
     int rc = transferField(b, field, const_cast<void*>(host), firstWorld, worldCount, true);
     // a freshly uploaded move buffer == b2World::e_newFixture: the next Step starts with FindNewContacts
     if (rc == B2GPU_OK && field == B2GPU_F_PROXY_MOVED) b->needInitialPairs = true;
+    // any host edit may change what the islands depend on: rebuild them on the next step
+    if (rc == B2GPU_OK) cudaMemsetAsync(b->A.topoDirty, 1, (size_t)b->A.numTiles * kTile * sizeof(int), b->stream);
     return rc;
 }
 int b2gpu_batch_download_field(b2gpu_batch* b, int32_t field, void* host, int32_t firstWorld, int32_t worldCount) {
