@@ -653,40 +653,19 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_solve_integrate(Arena A, fl
     }
 }
 
-// Single-warp TMA ring used by the position kernel: the consuming warp re-arms a stage itself.
-struct RecRing {
-    unsigned char* stages;  // kRecStages x kStageBytes
-    uint64_t* bars;         // kRecStages
-    const unsigned char* src;  // record 0 of this tile
-    uint32_t recBytes;         // bytes per record (all 32 lanes)
-    int perPass, total, issued;
-    __device__ __forceinline__ void issue(int lane) {  // lane 0 only issues; all lanes track `issued`
-        if (issued < total) {
-            if (lane == 0) {
-                int s = issued % kRecStages;
-                int i = issued % perPass;
-                MbarExpectTx(&bars[s], recBytes);
-                TmaLoad1D(stages + (size_t)s * kStageBytes, src + (size_t)i * recBytes, recBytes, &bars[s]);
-            }
-            ++issued;
-        }
-    }
-    __device__ __forceinline__ const float4* wait(int seq, int lane) {
-        int s = seq % kRecStages;
-        MbarWait(&bars[s], (uint32_t)(seq / kRecStages) & 1u);
-        return reinterpret_cast<const float4*>(stages + (size_t)s * kStageBytes) + lane;
-    }
-    __device__ __forceinline__ void drain(int seq) {  // consume every load still in flight after `seq` records
-        for (; seq < issued; ++seq) MbarWait(&bars[seq % kRecStages], (uint32_t)(seq / kRecStages) & 1u);
-    }
-};
+// =================================================================================================
+// k_solve_position: one tile per CTA, lane = world.  Up to posIters NGS passes (b2Island.cpp:308-328,
+// b2ContactSolver.cpp:614-744); each island stops as soon as one of its passes ends with
+// minSeparation >= -3 * b2_linearSlop.  Warp 0 (consumer) solves out of shared memory, lane 0 of warp 1
+// (producer) streams the position records of one pass through a TMA + mbarrier ring and then waits for the
+// consumer's verdict on whether another pass is needed.
+// =================================================================================================
+constexpr int kPosStageBytes = kPosRec * 16 * kTile;  // 2560
 
-// =================================================================================================
-// k_solve_position: one warp per tile.  Up to posIters NGS passes, each island stops when it converged.
-// =================================================================================================
-__global__ void __launch_bounds__(32) k_solve_position(Arena A, int posIters) {
+__global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tile = blockIdx.x, lane = threadIdx.x;
+    __shared__ int sContinue;
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const int n = A.solveCount[ws];
     const int islands = A.islandCount[ws];
@@ -696,42 +675,55 @@ __global__ void __launch_bounds__(32) k_solve_position(Arena A, int posIters) {
     Col<int> iContactEnd = col(A.islandContactEnd, tile, A.NB, lane);
     if (nMax == 0 || posIters <= 0) {
         // islands without contacts converge in the first pass (minSeparation == 0); no pass, no convergence
-        for (int wd = 0; wd < doneWords; ++wd) gDone[(size_t)wd * kTile] = posIters > 0 ? -1 : 0;
+        if (warp == 0)
+            for (int wd = 0; wd < doneWords; ++wd) gDone[(size_t)wd * kTile] = posIters > 0 ? -1 : 0;
         return;
     }
 
     const uint32_t bodyBytes = (uint32_t)A.NB * 3 * kTile * 4;
     float* sPos = reinterpret_cast<float*>(smem) + lane;
-    unsigned char* p = smem + ((bodyBytes + 127) & ~127u);
-    RecRing ring;
-    ring.stages = p;
-    p += kRecStages * kStageBytes;
-    p += kImpStages * 16 * kTile;
-    uint32_t* sDone = reinterpret_cast<uint32_t*>(p) + lane;  // word wd at sDone[wd * 32]
-    p += (size_t)doneWords * kTile * 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p);
-    ring.bars = bars;
-    uint64_t* bodyBar = bars + kRecStages;
+    unsigned char* stages = smem + ((bodyBytes + 127) & ~127u);
+    uint32_t* sDone = reinterpret_cast<uint32_t*>(stages + kRecStages * kPosStageBytes) + lane;  // word wd at sDone[wd * 32]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + kRecStages * kPosStageBytes + (size_t)doneWords * kTile * 4);
+    uint64_t* empty = full + kRecStages;
+    uint64_t* bodyBar = empty + kRecStages;
+    uint64_t* passBar = bodyBar + 1;
     float* gPos = A.solvePos + (size_t)tile * A.NB * 3 * kTile;
+    const int depth = nMax < kRecStages ? nMax : kRecStages;
 
-    if (lane == 0) {
-        for (int s = 0; s < kRecStages; ++s) MbarInit(&bars[s], 1);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kRecStages; ++s) {
+            MbarInit(&full[s], 1);    // the TMA issuer's expect_tx arrive
+            MbarInit(&empty[s], 32);  // every consumer lane
+        }
         MbarInit(bodyBar, 1);
+        MbarInit(passBar, 32);
         FenceBarrierInit();
     }
-    for (int wd = 0; wd < doneWords; ++wd) sDone[wd * kTile] = 0u;
-    __syncwarp();
-    ring.src = reinterpret_cast<const unsigned char*>(A.posRec + (size_t)tile * A.NC * kPosRec * kTile);
-    ring.recBytes = kPosRec * 16 * kTile;
-    ring.perPass = nMax;
-    ring.total = nMax * posIters;
-    ring.issued = 0;
-    if (lane == 0) {
+    __syncthreads();
+
+    if (warp == 1) {
+        // ================= producer (one lane) =================
+        if (lane != 0) return;
         MbarExpectTx(bodyBar, bodyBytes);
         TmaLoad1D(smem, gPos, bodyBytes, bodyBar);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(A.posRec + (size_t)tile * A.NC * kPosRec * kTile);
+        int s = 0, use = 0;
+        for (int pass = 0; pass < posIters; ++pass) {
+            for (int i = 0; i < nMax; ++i) {
+                if (use > 0) while (!MbarTryWait(&empty[s], (uint32_t)(use - 1) & 1u)) {}
+                MbarExpectTx(&full[s], kPosStageBytes);
+                TmaLoad1D(stages + (size_t)s * kPosStageBytes, src + (size_t)i * kPosStageBytes, kPosStageBytes, &full[s]);
+                if (++s == depth) { s = 0; ++use; }
+            }
+            while (!MbarTryWait(passBar, (uint32_t)pass & 1u)) {}
+            if (*(volatile int*)&sContinue == 0) break;
+        }
+        return;
     }
-    for (int s = 0; s < kRecStages; ++s) ring.issue(lane);
 
+    // ================= consumer =================
+    for (int wd = 0; wd < doneWords; ++wd) sDone[wd * kTile] = 0u;
     // islands that own at least one contact and have not converged yet
     int pending = 0;
     {
@@ -743,16 +735,17 @@ __global__ void __launch_bounds__(32) k_solve_position(Arena A, int posIters) {
             prev = e;
         }
     }
-    MbarWait(bodyBar, 0);
+    while (!MbarTryWait(bodyBar, 0)) {}
 
-    int seq = 0;
+    int s = 0, use = 0;
     for (int pass = 0; pass < posIters; ++pass) {
         int isl = 0;
         int islEnd = islands > 0 ? iContactEnd[0] : 0;
         float minSeparation = 0.0f;
         bool islDone = islands > 0 ? ((sDone[0] & 1u) != 0) : true;
-        for (int i = 0; i < nMax; ++i, ++seq) {
-            const float4* rec = ring.wait(seq, lane);
+        for (int i = 0; i < nMax; ++i) {
+            const float4* rec = reinterpret_cast<const float4*>(stages + (size_t)s * kPosStageBytes) + lane;
+            while (!MbarTryWait(&full[s], (uint32_t)use & 1u)) {}
             if (i < n) {
                 while (i >= islEnd) {  // entering the next island: close the previous one
                     if (!islDone && minSeparation >= -3.0f * kLinearSlop) {
@@ -827,16 +820,19 @@ __global__ void __launch_bounds__(32) k_solve_position(Arena A, int posIters) {
                     pB[0] = cBp.x; pB[kTile] = cBp.y; pB[2 * kTile] = aB;
                 }
             }
-            __syncwarp();
-            ring.issue(lane);
+            MbarArrive(&empty[s]);
+            if (++s == depth) { s = 0; ++use; }
         }
         if (n > 0 && !islDone && minSeparation >= -3.0f * kLinearSlop) {  // close the last island of this pass
             sDone[(isl >> 5) * kTile] |= 1u << (isl & 31);
             --pending;
         }
-        if (__all_sync(0xffffffffu, pending == 0)) break;
+        const bool more = pass + 1 < posIters && !__all_sync(0xffffffffu, pending == 0);
+        if (lane == 0) *(volatile int*)&sContinue = more ? 1 : 0;
+        __syncwarp();
+        MbarArrive(passBar);
+        if (!more) break;
     }
-    ring.drain(seq);
     for (int wd = 0; wd < doneWords; ++wd) gDone[(size_t)wd * kTile] = (int)sDone[wd * kTile];
     FenceProxyAsync();
     __syncwarp();

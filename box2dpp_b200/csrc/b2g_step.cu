@@ -379,7 +379,7 @@ int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_
             mark();
             k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
             mark();
-            k_solve_position<<<tiles, 32, b->solveSmem, st>>>(b->A, posIters);
+            k_solve_position<<<tiles, 64, b->solveSmem, st>>>(b->A, posIters);
             mark();
             k_solve_finalize<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
             mark();
