@@ -28,7 +28,8 @@ namespace b2g {
 
 constexpr int kVelRec = 7;      // float4 per velocity record
 constexpr int kPosRec = 5;      // float4 per position record
-constexpr int kRecStages = 6;   // TMA ring depth (records in flight per tile)
+constexpr int kRecStages = 6;   // TMA ring depth of the position kernel (records in flight per tile)
+constexpr int kVelStages = 7;   // TMA ring depth of the velocity kernel
 constexpr int kImpStages = 8;   // cp.async ring depth for accumulated impulses
 constexpr int kStageBytes = kVelRec * 16 * kTile;  // 3584
 constexpr int kPrepWarps = 8;
@@ -83,7 +84,9 @@ __device__ __forceinline__ int PackBodies(int bodyA, int bodyB, int pointCount) 
 __host__ __device__ inline size_t SolveSmemBytes(int NB) {
     size_t body = ((size_t)NB * 3 * kTile * 4 + 127) & ~(size_t)127;
     size_t done = (size_t)((NB + 31) / 32) * kTile * 4;
-    return body + (size_t)kRecStages * (kStageBytes + 16 * kTile) + (size_t)kImpStages * 16 * kTile + done + 256 /* barriers */;
+    size_t vel = (size_t)kVelStages * (kVelRec + 1) * 16 * kTile + 256;                // ring + barriers
+    size_t pos = (size_t)kRecStages * kPosRec * 16 * kTile + done + 256;
+    return body + (vel > pos ? vel : pos);
 }
 
 // =================================================================================================
@@ -312,9 +315,11 @@ constexpr int kVelStageBytes = (kVelRec + 1) * 16 * kTile;  // record + impulses
 
 __device__ __forceinline__ uint32_t MbarTryWait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+    // suspend-time hint: the producer / watcher warps sleep in hardware until the phase completes instead of
+    // spinning next to the consumer warp
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok)
-                 : "r"(SmemAddr(bar)), "r"(parity)
+                 : "r"(SmemAddr(bar)), "r"(parity), "r"(20000u)
                  : "memory");
     return ok;
 }
@@ -329,26 +334,77 @@ __device__ __forceinline__ void CpAsync16Cg(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(SmemAddr(dst)), "l"(src) : "memory");
 }
 
+
+// ---- shared-memory accessors on 32-bit shared-window addresses (no generic->shared conversion in the loops) ----
+__device__ __forceinline__ float4 LdsF4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float LdsF(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void StsF(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void StsF4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ uint32_t MbarTryWaitA(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok;
+}
+__device__ __forceinline__ void MbarArriveA(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Opaque identity: stops the compiler from rematerialising a loop invariant inside the loop.
+__device__ __forceinline__ uint32_t Keep(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ int Keep(int v) { asm volatile("" : "+r"(v)); return v; }
+template <class P>
+__device__ __forceinline__ P* Keep(P* v) { asm volatile("" : "+l"(v)); return v; }
+__device__ __forceinline__ uint32_t LdsAcquire(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void StsRelease(uint32_t a, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void CpAsync16CgA(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void CpAsyncArriveNoIncA(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// The tile's b2Velocity / b2Position table in shared memory: component c of body b of this lane's world.
+struct BodyTable {
+    uint32_t base;  // shared address of (body 0, component 0, this lane)
+    __device__ __forceinline__ uint32_t at(int b) const { return base + (uint32_t)b * (3 * kTile * 4); }
+};
+
 struct VelRecord {
     float4 q0, q1, q2, q3, q4, q5, q6, imp;
 };
-__device__ __forceinline__ VelRecord LoadVelRecord(const float4* st) {
+__device__ __forceinline__ VelRecord LoadVelRecord(uint32_t st) {  // st: shared address of this lane's float4 0
     VelRecord r;
-    r.q0 = st[0 * kTile]; r.q1 = st[1 * kTile]; r.q2 = st[2 * kTile]; r.q3 = st[3 * kTile];
-    r.q4 = st[4 * kTile]; r.q5 = st[5 * kTile]; r.q6 = st[6 * kTile]; r.imp = st[7 * kTile];
+    r.q0 = LdsF4(st + 0 * 512); r.q1 = LdsF4(st + 1 * 512); r.q2 = LdsF4(st + 2 * 512); r.q3 = LdsF4(st + 3 * 512);
+    r.q4 = LdsF4(st + 4 * 512); r.q5 = LdsF4(st + 5 * 512); r.q6 = LdsF4(st + 6 * 512); r.imp = LdsF4(st + 7 * 512);
     return r;
 }
 
 // WarmStart of one contact (b2ContactSolver.cpp:240-278)
-__device__ __forceinline__ void WarmStartContact(const VelRecord& r, float* sVel) {
+__device__ __forceinline__ void WarmStartContact(const VelRecord& r, BodyTable T) {
     const int packed = __float_as_int(r.q0.w);
     const int bodyA = packed & 0x7fff, bodyB = (packed >> 15) & 0x7fff;
     const int pointCount = (packed >> 30) & 3;
     const float mA = r.q1.x, iA = r.q1.y, mB = r.q1.z, iB = r.q1.w;
-    float* pA = sVel + (size_t)bodyA * 3 * kTile;
-    float* pB = sVel + (size_t)bodyB * 3 * kTile;
-    Vec2 vA = V2(pA[0], pA[kTile]), vB = V2(pB[0], pB[kTile]);
-    float wA = pA[2 * kTile], wB = pB[2 * kTile];
+    const uint32_t pA = T.at(bodyA), pB = T.at(bodyB);
+    Vec2 vA = V2(LdsF(pA), LdsF(pA + 128)), vB = V2(LdsF(pB), LdsF(pB + 128));
+    float wA = LdsF(pA + 256), wB = LdsF(pB + 256);
     const Vec2 normal = V2(r.q0.x, r.q0.y);
     const Vec2 tangent = Cross(normal, 1.0f);
     {
@@ -365,22 +421,21 @@ __device__ __forceinline__ void WarmStartContact(const VelRecord& r, float* sVel
         wB += iB * Cross(V2(r.q4.z, r.q4.w), P);
         vB = vB + mB * P;
     }
-    pA[0] = vA.x; pA[kTile] = vA.y; pA[2 * kTile] = wA;
-    pB[0] = vB.x; pB[kTile] = vB.y; pB[2 * kTile] = wB;
+    StsF(pA, vA.x); StsF(pA + 128, vA.y); StsF(pA + 256, wA);
+    StsF(pB, vB.x); StsF(pB + 128, vB.y); StsF(pB + 256, wB);
 }
 
 // SolveVelocityConstraints for one contact (b2ContactSolver.cpp:280-597); returns the updated impulses
-__device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, float* sVel) {
+__device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, BodyTable T) {
     const float4 q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3;
     float4 imp = r.imp;
     const int packed = __float_as_int(q0.w);
     const int bodyA = packed & 0x7fff, bodyB = (packed >> 15) & 0x7fff;
     const int pointCount = (packed >> 30) & 3;
     const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
-    float* pA = sVel + (size_t)bodyA * 3 * kTile;
-    float* pB = sVel + (size_t)bodyB * 3 * kTile;
-    Vec2 vA = V2(pA[0], pA[kTile]), vB = V2(pB[0], pB[kTile]);
-    float wA = pA[2 * kTile], wB = pB[2 * kTile];
+    const uint32_t pA = T.at(bodyA), pB = T.at(bodyB);
+    Vec2 vA = V2(LdsF(pA), LdsF(pA + 128)), vB = V2(LdsF(pB), LdsF(pB + 128));
+    float wA = LdsF(pA + 256), wB = LdsF(pB + 256);
     const Vec2 normal = V2(q0.x, q0.y);
     const Vec2 tangent = Cross(normal, 1.0f);
     const Vec2 rA0 = V2(q2.x, q2.y), rB0 = V2(q2.z, q2.w);
@@ -467,13 +522,14 @@ __device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, float
             imp.z = x.y;
         }
     }
-    pA[0] = vA.x; pA[kTile] = vA.y; pA[2 * kTile] = wA;
-    pB[0] = vB.x; pB[kTile] = vB.y; pB[2 * kTile] = wB;
+    StsF(pA, vA.x); StsF(pA + 128, vA.y); StsF(pA + 256, wA);
+    StsF(pB, vB.x); StsF(pB + 128, vB.y); StsF(pB + 256, wB);
     return imp;
 }
 
-__global__ void __launch_bounds__(64) k_solve_velocity(Arena A, int velIters) {
+__global__ void __launch_bounds__(96) k_solve_velocity(Arena A, int velIters) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint32_t sReady;  // records whose data has landed in the ring (published by the watcher warp)
     const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const int n = A.solveCount[ws];
@@ -482,29 +538,46 @@ __global__ void __launch_bounds__(64) k_solve_velocity(Arena A, int velIters) {
     const bool warm = (A.worldFlags[ws] & B2G_WORLD_WARM_STARTING) != 0;
     const int anyWarm = __any_sync(0xffffffffu, warm) ? 1 : 0;
     const int total = nMax * (velIters + anyWarm);
-    // ring depth: a record of the next pass may only be fetched after this pass' impulses of the same contact
-    // have been written back, i.e. at most nMax - 1 records ahead
-    const int depth = nMax - 1 < 1 ? 1 : (nMax - 1 < kRecStages ? nMax - 1 : kRecStages);
+    // Ring depth.  The accumulated impulses of a contact travel with its record: the consumer leaves the updated
+    // values in the ring stage, and the producer lane that fetched them (cp.async) writes them back to global
+    // memory when the stage is recycled and fetches them again for the next pass — store and re-fetch of one
+    // contact are issued by the same thread, in that order, as long as the ring holds fewer than nMax records.
+    const int depth = nMax - 1 < 1 ? 1 : (nMax - 1 < kVelStages ? nMax - 1 : kVelStages);
 
     const uint32_t bodyBytes = (uint32_t)A.NB * 3 * kTile * 4;
-    float* sVel = reinterpret_cast<float*>(smem) + lane;  // element (b, c) at sVel[(b * 3 + c) * 32]
     unsigned char* stages = smem + ((bodyBytes + 127) & ~127u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(stages + kRecStages * kVelStageBytes);
-    uint64_t* empty = full + kRecStages;
-    uint64_t* bodyBar = empty + kRecStages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + kVelStages * kVelStageBytes);
+    uint64_t* empty = full + kVelStages;
+    uint64_t* bodyBar = empty + kVelStages;
     float* gVel = A.solveVel + (size_t)tile * A.NB * 3 * kTile;
     float4* gImp = A.impRec + (size_t)tile * A.NC * kTile + lane;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kRecStages; ++s) {
+        for (int s = 0; s < kVelStages; ++s) {
             MbarInit(&full[s], 33);   // expect_tx arrive of the TMA issuer + 32 cp.async completions
             MbarInit(&empty[s], 32);  // every consumer lane
         }
         MbarInit(bodyBar, 1);
+        sReady = 0;
         FenceBarrierInit();
     }
     __syncthreads();
 
+    if (warp == 2) {
+        // ================= watcher: waits for every record in order and publishes the count =================
+        // (mbarrier.try_wait returns a predicate that must be consumed at once, ~50-90 cycles; the consumer
+        // polls this word with an ordinary load instead, whose latency it overlaps with the solve)
+        if (lane != 0) return;
+        const uint32_t ready = SmemAddr(&sReady);
+        int s = 0;
+        uint32_t phase = 0;
+        for (int r = 0; r < total; ++r) {
+            while (!MbarTryWait(&full[s], phase)) {}
+            StsRelease(ready, (uint32_t)r + 1u);
+            if (++s == depth) { s = 0; phase ^= 1u; }
+        }
+        return;
+    }
     if (warp == 1) {
         // ================= producer =================
         if (lane == 0) {
@@ -512,13 +585,14 @@ __global__ void __launch_bounds__(64) k_solve_velocity(Arena A, int velIters) {
             TmaLoad1D(smem, gVel, bodyBytes, bodyBar);
         }
         const unsigned char* src = reinterpret_cast<const unsigned char*>(A.velRec + (size_t)tile * A.NC * kVelRec * kTile);
-        const bool fence = nMax - 1 <= depth;  // tiny worlds: write-back and re-fetch of a record are back to back
-        int i = 0, s = 0, use = 0;             // record index within the pass, stage, how often the ring wrapped
-        int wi = 0, wpass = 0;                 // record that previously occupied stage s (write-back cursor)
+        const bool fence = nMax - 1 <= depth;  // tiny worlds: write-back and re-fetch of a contact are back to back
+        int i = 0, s = 0;
+        int wi = 0, wpass = 0;  // record that previously occupied stage s (write-back cursor)
+        uint32_t phase = 1;     // parity of the consumer's release that frees stage s for its next use
         for (int seq = 0; seq < total + depth; ++seq) {
             float4* st = reinterpret_cast<float4*>(stages + (size_t)s * kVelStageBytes) + lane;
             if (seq >= depth) {  // stage s holds record seq - depth: wait for the consumer, write its impulses back
-                while (!MbarTryWait(&empty[s], (uint32_t)(use - 1) & 1u)) {}
+                while (!MbarTryWait(&empty[s], phase)) {}
                 if (wi < n && !(anyWarm && wpass == 0)) gImp[(size_t)wi * kTile] = st[7 * kTile];
                 if (fence) __threadfence();
                 if (++wi == nMax) { wi = 0; ++wpass; }
@@ -532,29 +606,78 @@ __global__ void __launch_bounds__(64) k_solve_velocity(Arena A, int velIters) {
                 CpAsyncArriveNoInc(&full[s]);
                 if (++i == nMax) i = 0;
             }
-            if (++s == depth) { s = 0; ++use; }
+            if (++s == depth) { s = 0; phase ^= 1u; }
         }
         return;
     }
 
     // ================= consumer =================
     while (!MbarTryWait(bodyBar, 0)) {}
-    int i = 0, s = 0, use = 0;
-    const int warmRecords = anyWarm ? nMax : 0;
-    for (int seq = 0; seq < total; ++seq) {
-        float4* st = reinterpret_cast<float4*>(stages + (size_t)s * kVelStageBytes) + lane;
-        while (!MbarTryWait(&full[s], (uint32_t)use & 1u)) {}
-        if (i < n) {
-            const VelRecord r = LoadVelRecord(st);
-            if (seq < warmRecords) {
-                if (warm) WarmStartContact(r, sVel);
-            } else {
-                st[7 * kTile] = SolveVelocityContact(r, sVel);
+    // Loop invariants are pinned in registers (Keep): left alone, the compiler re-derives them from %tid / %ctaid /
+    // the shared-window base inside the loop, which costs more than the solve's own address arithmetic.
+    const BodyTable T{Keep(SmemAddr(smem) + (uint32_t)lane * 4)};
+    const uint32_t stage0 = Keep(SmemAddr(stages) + (uint32_t)lane * 16);
+    const uint32_t empty0 = Keep(SmemAddr(empty));
+    const uint32_t ready = Keep(SmemAddr(&sReady));
+    const uint32_t stageEnd = Keep(stage0 + (uint32_t)depth * kVelStageBytes);
+    const int warmRecords = Keep(anyWarm ? nMax : 0);
+    const int nK = Keep(n), nMaxK = Keep(nMax), totalK = Keep(total);
+    if (depth >= 3) {
+        // Two records of look-ahead in registers: the record solved in an iteration was loaded one iteration
+        // earlier, so neither the ring's barrier nor the LDS latency sits on the solver's dependency chain.
+        uint32_t ldStage = stage0, stStage = stage0, stEmpty = empty0;
+        int i = 0, seq = 0;
+        auto load = [&](VelRecord& r) {
+            r = LoadVelRecord(ldStage);
+            ldStage += kVelStageBytes;
+            if (ldStage == stageEnd) ldStage = stage0;
+        };
+        // one solver step on the record held in `r`, then refill `r` with the record two ahead
+        auto step = [&](VelRecord& r) {
+            uint32_t landed = LdsAcquire(ready);  // polled now, needed after the solve
+            if (i < nK) {
+                if (seq < warmRecords) {
+                    if (warm) WarmStartContact(r, T);
+                } else {
+                    StsF4(stStage + 7 * 512, SolveVelocityContact(r, T));
+                }
             }
+            MbarArriveA(stEmpty);  // hands the stage (and the updated impulses in it) back to the producer
+            stStage += kVelStageBytes;
+            stEmpty += 8;
+            if (stStage == stageEnd) { stStage = stage0; stEmpty = empty0; }
+            if (seq + 2 < totalK) {
+                while (landed < (uint32_t)seq + 3u) landed = LdsAcquire(ready);
+                load(r);
+            }
+            if (++i == nMaxK) i = 0;
+            ++seq;
+        };
+        VelRecord r0, r1;
+        while (LdsAcquire(ready) < 2u) {}
+        load(r0);
+        load(r1);
+        while (seq < totalK) {
+            step(r0);
+            if (seq < totalK) step(r1);
         }
-        MbarArrive(&empty[s]);
-        if (++i == nMax) i = 0;
-        if (++s == depth) { s = 0; ++use; }
+    } else {
+        int i = 0, cs = 0;
+        for (int seq = 0; seq < total; ++seq) {
+            const uint32_t st = stage0 + cs * kVelStageBytes;
+            while (LdsAcquire(ready) < (uint32_t)seq + 1u) {}
+            if (i < n) {
+                const VelRecord r = LoadVelRecord(st);
+                if (seq < warmRecords) {
+                    if (warm) WarmStartContact(r, T);
+                } else {
+                    StsF4(st + 7 * 512, SolveVelocityContact(r, T));
+                }
+            }
+            MbarArriveA(empty0 + cs * 8);
+            if (++i == nMax) i = 0;
+            if (++cs == depth) cs = 0;
+        }
     }
     // velocities back to the solver table in global memory
     FenceProxyAsync();

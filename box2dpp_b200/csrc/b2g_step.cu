@@ -375,7 +375,7 @@ int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_
         if (b->tileSolver) {
             k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
             mark();
-            k_solve_velocity<<<tiles, 64, b->solveSmem, st>>>(b->A, velIters);
+            k_solve_velocity<<<tiles, 96, b->solveSmem, st>>>(b->A, velIters);
             mark();
             k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
             mark();
