@@ -1,0 +1,614 @@
+// b2WorldBatch.h — the reference's scene-construction and stepping API over the B200 batch engine.
+//
+// box2dpp's boundary is its C++ public API (there is no FFI layer in the reference).  This header keeps that
+// API's spelling — namespace box2d, b2Vec<float, 2>, b2BodyDef / b2FixtureDef / the four shape classes,
+// b2World::CreateBody, b2Body::CreateFixture, b2World::Step — and adds the batch axis: a b2WorldBatch owns N
+// independent b2World objects that are built through the same calls and stepped together on one GPU by
+// b2gpu_batch_step (include/b2gpu.h), the replacement of b2World::Step (Box2D/Dynamics/b2World.cpp:888-954).
+// A b2World constructed on its own is a batch of one, so HelloWorld/HelloWorld.cpp:36-101 compiles against this
+// header unchanged apart from the include line and one call: world.SetContinuousPhysics(false) — the TOI
+// sub-stepper (b2World::SolveTOI) is not on the device path yet and the engine refuses to pretend otherwise.
+//
+// Reference interfaces mirrored (paths under /root/reference/Box2D):
+//   b2Vec<T, N>, b2VecX / b2VecY              Common/b2Vec.h:17-72
+//   b2BodyType, b2BodyDef, b2Body getters     Dynamics/b2Body.h:41-125, 163-197, 500-533, 738-790
+//   b2Filter, b2FixtureDef, b2Fixture         Dynamics/b2Fixture.h:35-95
+//   b2Shape and the four shapes               Collision/Shapes/b2Shape.h:44-128, b2CircleShape.h, b2EdgeShape.h:35,
+//                                             b2PolygonShape.h:48-60, b2ChainShape.h:48-61
+//   b2World                                   Dynamics/b2World.h:48-232
+//   b2ContactListener, b2ContactImpulse       Dynamics/b2WorldCallbacks.h:74-136
+//
+// Differences a caller must know:
+//   * Worlds are frozen at the first Step: CreateBody / CreateFixture afterwards return nullptr, exactly like a
+//     locked reference world does (b2World.cpp:100-104).  DestroyBody, joints, queries are out of scope.
+//   * Shapes record HOW they were built (SetAsBox / Set / CreateChain ...); hulls, normals, mass data and fat
+//     AABBs are computed by the host layer of libb2gpu.so with the reference's arithmetic when the batch is built.
+//   * Listener callbacks are delivered after Step from the device's readback buffer, in the reference's order,
+//     as b2ContactEvent records; they cannot mutate the contact mid-step (PreSolve is read-only).
+//   * Errors: misuse that the reference asserts on throws std::runtime_error carrying b2gpu_last_error().
+#ifndef B2_WORLD_BATCH_H
+#define B2_WORLD_BATCH_H
+
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b2gpu.h"
+
+namespace box2d {
+
+// ---- b2Vec (Common/b2Vec.h) ------------------------------------------------------------------------
+template <class T, std::size_t N>
+struct b2Vec {
+    std::array<T, N> v;
+    T& operator[](std::size_t i) { return v[i]; }
+    const T& operator[](std::size_t i) const { return v[i]; }
+};
+constexpr std::size_t b2VecX = 0, b2VecY = 1;
+using b2Vec2f = b2Vec<float, 2>;
+
+enum class b2BodyType { STATIC_BODY = 0, KINEMATIC_BODY, DYNAMIC_BODY };
+
+struct b2BodyDef {
+    b2BodyType type = b2BodyType::STATIC_BODY;
+    b2Vec<float, 2> position{{0.0f, 0.0f}};
+    float angle = 0.0f;
+    b2Vec<float, 2> linearVelocity{{0.0f, 0.0f}};
+    float angularVelocity = 0.0f;
+    float linearDamping = 0.0f;
+    float angularDamping = 0.0f;
+    bool allowSleep = true;
+    bool awake = true;
+    bool fixedRotation = false;
+    bool bullet = false;
+    bool active = true;
+    void* userData = nullptr;
+    float gravityScale = 1.0f;
+};
+
+struct b2Filter {
+    uint16_t categoryBits = 0x0001;
+    uint16_t maskBits = 0xFFFF;
+    int16_t groupIndex = 0;
+};
+
+// ---- shapes ----------------------------------------------------------------------------------------
+class b2Shape {
+public:
+    enum Type { e_circle = 0, e_edge = 1, e_polygon = 2, e_chain = 3, e_typeCount = 4 };
+    virtual ~b2Shape() {}
+    Type GetType() const { return m_type; }
+    float GetRadius() const { return m_radius; }
+    void SetRadius(float radius) { m_radius = radius; }
+
+protected:
+    friend class b2Body;
+    explicit b2Shape(Type t, float r) : m_type(t), m_radius(r) {}
+    // appends this shape's construction record to a fixture def + vertex pool (include/b2g_scene.h)
+    virtual void Describe(b2g_fixture_def& fd, std::vector<float>& vertices) const = 0;
+    Type m_type;
+    float m_radius;
+};
+
+class b2CircleShape : public b2Shape {
+public:
+    b2CircleShape() : b2Shape(e_circle, 0.0f) {}
+    b2Vec<float, 2> m_p{{0.0f, 0.0f}};
+
+protected:
+    void Describe(b2g_fixture_def& fd, std::vector<float>&) const override {
+        fd.shapeType = B2G_SHAPE_CIRCLE;
+        fd.radius = m_radius;
+        fd.p[0] = m_p[0];
+        fd.p[1] = m_p[1];
+    }
+};
+
+class b2EdgeShape : public b2Shape {
+public:
+    b2EdgeShape() : b2Shape(e_edge, 0.01f) {}
+    void Set(b2Vec<float, 2> v1, b2Vec<float, 2> v2) {
+        m_vertex1 = v1;
+        m_vertex2 = v2;
+        m_hasVertex0 = m_hasVertex3 = false;
+    }
+    b2Vec<float, 2> m_vertex0{{0, 0}}, m_vertex1{{0, 0}}, m_vertex2{{0, 0}}, m_vertex3{{0, 0}};
+    bool m_hasVertex0 = false, m_hasVertex3 = false;
+
+protected:
+    void Describe(b2g_fixture_def& fd, std::vector<float>& vertices) const override {
+        fd.shapeType = B2G_SHAPE_EDGE;
+        fd.firstVertex = (int32_t)(vertices.size() / 2);
+        fd.vertexCount = 2;
+        vertices.insert(vertices.end(), {m_vertex1[0], m_vertex1[1], m_vertex2[0], m_vertex2[1]});
+        fd.hasVertex0 = m_hasVertex0;
+        fd.hasVertex3 = m_hasVertex3;
+        fd.vertex0[0] = m_vertex0[0]; fd.vertex0[1] = m_vertex0[1];
+        fd.vertex3[0] = m_vertex3[0]; fd.vertex3[1] = m_vertex3[1];
+    }
+};
+
+class b2PolygonShape : public b2Shape {
+public:
+    b2PolygonShape() : b2Shape(e_polygon, 0.01f) {}
+    void SetAsBox(float hx, float hy) {
+        m_kind = B2G_POLY_BOX;
+        m_hx = hx;
+        m_hy = hy;
+    }
+    void SetAsBox(float hx, float hy, const b2Vec<float, 2>& center, float angle) {
+        m_kind = B2G_POLY_BOX_OFFSET;
+        m_hx = hx;
+        m_hy = hy;
+        m_center = center;
+        m_angle = angle;
+    }
+    void Set(const b2Vec<float, 2>* points, int32_t count) {
+        if (count < 3 || count > 8) throw std::runtime_error("b2PolygonShape::Set: 3 <= count <= b2_maxPolygonVertices");
+        m_kind = B2G_POLY_SET;
+        m_points.assign(points, points + count);
+    }
+
+protected:
+    void Describe(b2g_fixture_def& fd, std::vector<float>& vertices) const override {
+        fd.shapeType = B2G_SHAPE_POLYGON;
+        fd.shapeKind = m_kind;
+        fd.p[0] = m_hx; fd.p[1] = m_hy;
+        fd.center[0] = m_center[0]; fd.center[1] = m_center[1];
+        fd.angle = m_angle;
+        if (m_kind == B2G_POLY_SET) {
+            fd.firstVertex = (int32_t)(vertices.size() / 2);
+            fd.vertexCount = (int32_t)m_points.size();
+            for (const auto& p : m_points) { vertices.push_back(p[0]); vertices.push_back(p[1]); }
+        }
+    }
+    int m_kind = B2G_POLY_BOX;
+    float m_hx = 0.0f, m_hy = 0.0f, m_angle = 0.0f;
+    b2Vec<float, 2> m_center{{0, 0}};
+    std::vector<b2Vec<float, 2>> m_points;
+};
+
+class b2ChainShape : public b2Shape {
+public:
+    b2ChainShape() : b2Shape(e_chain, 0.01f) {}
+    void CreateLoop(const b2Vec<float, 2>* vertices, int32_t count) { m_loop = true; m_points.assign(vertices, vertices + count); }
+    void CreateChain(const b2Vec<float, 2>* vertices, int32_t count) { m_loop = false; m_points.assign(vertices, vertices + count); }
+    void SetPrevVertex(const b2Vec<float, 2>& v) { m_prev = v; m_hasPrev = true; }
+    void SetNextVertex(const b2Vec<float, 2>& v) { m_next = v; m_hasNext = true; }
+
+protected:
+    void Describe(b2g_fixture_def& fd, std::vector<float>& vertices) const override {
+        fd.shapeType = B2G_SHAPE_CHAIN;
+        fd.shapeKind = m_loop ? B2G_CHAIN_LOOP : B2G_CHAIN_OPEN;
+        fd.firstVertex = (int32_t)(vertices.size() / 2);
+        fd.vertexCount = (int32_t)m_points.size();
+        for (const auto& p : m_points) { vertices.push_back(p[0]); vertices.push_back(p[1]); }
+        fd.hasVertex0 = m_hasPrev; fd.hasVertex3 = m_hasNext;
+        fd.vertex0[0] = m_prev[0]; fd.vertex0[1] = m_prev[1];
+        fd.vertex3[0] = m_next[0]; fd.vertex3[1] = m_next[1];
+    }
+    bool m_loop = false, m_hasPrev = false, m_hasNext = false;
+    b2Vec<float, 2> m_prev{{0, 0}}, m_next{{0, 0}};
+    std::vector<b2Vec<float, 2>> m_points;
+};
+
+struct b2FixtureDef {
+    const b2Shape* shape = nullptr;
+    void* userData = nullptr;
+    float friction = 0.2f;
+    float restitution = 0.0f;
+    float density = 0.0f;
+    bool isSensor = false;
+    b2Filter filter;
+};
+
+class b2Body;
+class b2World;
+class b2WorldBatch;
+
+class b2Fixture {
+public:
+    b2Body* GetBody() const { return m_body; }
+    void* GetUserData() const { return m_userData; }
+    b2Shape::Type GetType() const { return m_type; }
+    int32_t GetIndex() const { return m_index; }  // creation order within the world
+
+private:
+    friend class b2Body;
+    b2Body* m_body = nullptr;
+    void* m_userData = nullptr;
+    b2Shape::Type m_type = b2Shape::e_circle;
+    int32_t m_index = 0;
+};
+
+// ---- listener: b2ContactListener over the readback buffer -------------------------------------------
+struct b2ContactImpulse {  // Dynamics/b2WorldCallbacks.h:74-79
+    float normalImpulses[2];
+    float tangentImpulses[2];
+    int32_t count;
+};
+struct b2ContactEvent {  // what a b2Contact* tells a listener, by value
+    b2World* world;
+    b2Fixture* fixtureA;
+    b2Fixture* fixtureB;
+    int32_t childIndexA, childIndexB;
+    int32_t pointCount;
+};
+class b2ContactListener {
+public:
+    virtual ~b2ContactListener() {}
+    virtual void BeginContact(const b2ContactEvent&) {}
+    virtual void EndContact(const b2ContactEvent&) {}
+    virtual void PreSolve(const b2ContactEvent&) {}
+    virtual void PostSolve(const b2ContactEvent&, const b2ContactImpulse&) {}
+};
+
+class b2Body {
+public:
+    b2Fixture* CreateFixture(const b2FixtureDef* def);
+    b2Fixture* CreateFixture(const b2Shape* shape, float density) {
+        b2FixtureDef def;
+        def.shape = shape;
+        def.density = density;
+        return CreateFixture(&def);
+    }
+    const b2Vec<float, 2>& GetPosition() const;
+    float GetAngle() const;
+    const b2Vec<float, 2>& GetWorldCenter() const;
+    const b2Vec<float, 2>& GetLinearVelocity() const;
+    float GetAngularVelocity() const;
+    bool IsAwake() const;
+    b2BodyType GetType() const { return m_type; }
+    void* GetUserData() const { return m_userData; }
+    b2World* GetWorld() const { return m_world; }
+    int32_t GetIndex() const { return m_index; }  // creation order within the world
+    // b2Body::ApplyForceToCenter / ApplyTorque (b2Body.h:738-790): accumulated on the host, uploaded at the next Step
+    void ApplyForceToCenter(const b2Vec<float, 2>& force, bool wake);
+    void ApplyTorque(float torque, bool wake);
+
+private:
+    friend class b2World;
+    friend class b2WorldBatch;
+    b2World* m_world = nullptr;
+    int32_t m_index = 0;
+    b2BodyType m_type = b2BodyType::STATIC_BODY;
+    void* m_userData = nullptr;
+    mutable b2Vec<float, 2> m_tmp[3];
+};
+
+class b2World {
+public:
+    // A world on its own is a batch of one (HelloWorld/HelloWorld.cpp:39).
+    explicit b2World(const b2Vec<float, 2>& gravity);
+    ~b2World();
+    b2World(const b2World&) = delete;
+    b2World& operator=(const b2World&) = delete;
+
+    b2Body* CreateBody(const b2BodyDef* def);
+    void Step(float timeStep, int32_t velocityIterations, int32_t positionIterations);
+    void SetContactListener(b2ContactListener* listener);
+    void SetAllowSleeping(bool flag) { SetFlag(B2G_WORLD_ALLOW_SLEEP, flag); }
+    bool GetAllowSleeping() const { return (m_flags & B2G_WORLD_ALLOW_SLEEP) != 0; }
+    void SetWarmStarting(bool flag) { SetFlag(B2G_WORLD_WARM_STARTING, flag); }
+    bool GetWarmStarting() const { return (m_flags & B2G_WORLD_WARM_STARTING) != 0; }
+    void SetContinuousPhysics(bool flag) { SetFlag(B2G_WORLD_CONTINUOUS, flag); }
+    bool GetContinuousPhysics() const { return (m_flags & B2G_WORLD_CONTINUOUS) != 0; }
+    void SetAutoClearForces(bool flag) { SetFlag(B2G_WORLD_CLEAR_FORCES, flag); }
+    bool GetAutoClearForces() const { return (m_flags & B2G_WORLD_CLEAR_FORCES) != 0; }
+    b2Vec<float, 2> GetGravity() const { return m_gravity; }
+    int32_t GetBodyCount() const;
+    int32_t GetProxyCount() const;
+    int32_t GetContactCount() const;
+    bool IsLocked() const;
+    int32_t GetIndex() const { return m_index; }  // world index within its batch
+
+private:
+    friend class b2Body;
+    friend class b2WorldBatch;
+    b2World(b2WorldBatch* batch, int32_t index, const b2Vec<float, 2>& gravity) : m_batch(batch), m_index(index), m_gravity(gravity) {}
+    void SetFlag(int bit, bool on);
+    b2WorldBatch* m_batch = nullptr;
+    std::unique_ptr<b2WorldBatch> m_owned;  // standalone world: its private batch of one
+    int32_t m_index = 0;
+    b2Vec<float, 2> m_gravity{{0.0f, -10.0f}};
+    int32_t m_flags = B2G_WORLD_DEFAULT_FLAGS;
+    std::vector<std::unique_ptr<b2Body>> m_bodies;
+    std::vector<std::unique_ptr<b2Fixture>> m_fixtures;
+    std::vector<b2g_body_def> m_bodyDefs;
+    std::vector<b2g_fixture_def> m_fixtureDefs;
+    std::vector<float> m_vertices;
+    std::vector<int32_t> m_firstProxy;  // per fixture: index of its first proxy (creation order)
+    int32_t m_proxyCount = 0;
+};
+
+// N independent worlds stepped together on one GPU.
+class b2WorldBatch {
+public:
+    b2WorldBatch(const b2Vec<float, 2>& gravity, int32_t worldCount, int32_t device = 0) : m_device(device) {
+        if (worldCount <= 0) throw std::runtime_error("b2WorldBatch: worldCount must be positive");
+        for (int32_t i = 0; i < worldCount; ++i) m_worlds.emplace_back(new b2World(this, i, gravity));
+    }
+    ~b2WorldBatch() {
+        if (m_handle) b2gpu_batch_destroy(m_handle);
+    }
+    b2WorldBatch(const b2WorldBatch&) = delete;
+    b2WorldBatch& operator=(const b2WorldBatch&) = delete;
+
+    int32_t GetWorldCount() const { return (int32_t)m_worlds.size(); }
+    b2World& World(int32_t i) { return *m_worlds[i]; }
+    b2World& operator[](int32_t i) { return *m_worlds[i]; }
+
+    // Per-world capacity overrides for the device arenas (0 = derived from the scenes); call before the first Step.
+    void SetCapacities(int32_t maxContacts, int32_t maxEvents) { m_maxContacts = maxContacts; m_maxEvents = maxEvents; }
+    void SetContactListener(b2ContactListener* listener) {
+        if (m_handle && listener && !m_eventMask) throw std::runtime_error("SetContactListener must precede the first Step");
+        m_listener = listener;
+    }
+
+    // b2World::Step for every world of the batch.
+    void Step(float timeStep, int32_t velocityIterations, int32_t positionIterations) {
+        Build();
+        if (m_forcesDirty) {
+            Check(b2gpu_batch_apply_forces(m_handle, m_forces.data()));
+            std::fill(m_forces.begin(), m_forces.end(), 0.0f);
+            m_forcesDirty = false;
+        }
+        Check(b2gpu_batch_step(m_handle, timeStep, velocityIterations, positionIterations));
+        m_stateValid = false;
+        if (m_listener) DispatchEvents();
+    }
+    // `steps` steps replayed from a CUDA graph (no listener dispatch in between).
+    void StepN(float timeStep, int32_t velocityIterations, int32_t positionIterations, int32_t steps) {
+        Build();
+        Check(b2gpu_batch_step_n(m_handle, timeStep, velocityIterations, positionIterations, steps));
+        m_stateValid = false;
+    }
+    void Synchronize() { if (m_handle) Check(b2gpu_batch_sync(m_handle)); }
+    bool IsBuilt() const { return m_handle != nullptr; }
+    b2gpu_batch* GetHandle() const { return m_handle; }
+    // OR of B2GPU_STATUS_* over all worlds (arena overflow is reported, never silent)
+    int32_t GetStatus() {
+        Build();
+        std::vector<int32_t> st(m_worlds.size());
+        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_STATUS, st.data(), 0, (int32_t)st.size()));
+        int32_t acc = 0;
+        for (int32_t v : st) acc |= v;
+        return acc;
+    }
+
+private:
+    friend class b2World;
+    friend class b2Body;
+    static void Check(int rc) {
+        if (rc != B2GPU_OK) throw std::runtime_error(std::string("b2gpu: ") + b2gpu_last_error());
+    }
+    void Build() {
+        if (m_handle) return;
+        std::vector<b2g_scene> scenes(m_worlds.size());
+        for (size_t i = 0; i < m_worlds.size(); ++i) {
+            b2World& w = *m_worlds[i];
+            b2g_scene& s = scenes[i];
+            s.gravity[0] = w.m_gravity[0];
+            s.gravity[1] = w.m_gravity[1];
+            s.worldFlags = w.m_flags;
+            s.bodyCount = (int32_t)w.m_bodyDefs.size();
+            s.fixtureCount = (int32_t)w.m_fixtureDefs.size();
+            s.vertexCount = (int32_t)(w.m_vertices.size() / 2);
+            s.bodies = w.m_bodyDefs.data();
+            s.fixtures = w.m_fixtureDefs.data();
+            s.vertices = w.m_vertices.data();
+        }
+        b2gpu_batch_desc desc;
+        std::memset(&desc, 0, sizeof(desc));
+        desc.device = m_device;
+        desc.numWorlds = (int32_t)m_worlds.size();
+        desc.maxContacts = m_maxContacts;
+        desc.maxEvents = m_maxEvents;
+        m_eventMask = m_listener ? 15 : 0;
+        desc.eventMask = m_eventMask;
+        Check(b2gpu_scene_capacities(scenes.data(), desc.numWorlds, &desc));
+        Check(b2gpu_batch_create(&desc, &m_handle));
+        int rc = b2gpu_batch_build_worlds(m_handle, scenes.data(), desc.numWorlds, 0, 1);
+        if (rc != B2GPU_OK) {
+            std::string msg = b2gpu_last_error();
+            b2gpu_batch_destroy(m_handle);
+            m_handle = nullptr;
+            throw std::runtime_error("b2gpu: " + msg);
+        }
+        m_maxBodies = desc.maxBodies;
+        m_maxEventsBuilt = desc.maxEvents;
+        m_forces.assign((size_t)desc.numWorlds * m_maxBodies * 3, 0.0f);
+    }
+    void Refresh() {  // lazy readback of body state after a Step
+        Build();
+        if (m_stateValid) return;
+        const size_t n = m_worlds.size() * (size_t)m_maxBodies;
+        m_xf.resize(n * 4); m_sweep.resize(n * 4); m_vel.resize(n * 4); m_bodyFlags.resize(n);
+        const int32_t W = (int32_t)m_worlds.size();
+        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_BODY_XF, m_xf.data(), 0, W));
+        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_BODY_SWEEP, m_sweep.data(), 0, W));
+        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_BODY_VEL, m_vel.data(), 0, W));
+        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_BODY_FLAGS, m_bodyFlags.data(), 0, W));
+        m_stateValid = true;
+    }
+    size_t Slot(const b2Body* b) const { return (size_t)b->m_world->m_index * m_maxBodies + b->m_index; }
+    void DispatchEvents() {
+        const int32_t W = (int32_t)m_worlds.size();
+        std::vector<int32_t> counts(W), a((size_t)W * m_maxEventsBuilt * 4);
+        std::vector<float> b((size_t)W * m_maxEventsBuilt * 4);
+        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_EVENT_COUNT, counts.data(), 0, W));
+        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_EVENT_A, a.data(), 0, W));
+        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_EVENT_B, b.data(), 0, W));
+        for (int32_t w = 0; w < W; ++w) {
+            b2World& world = *m_worlds[w];
+            const int32_t n = counts[w] < m_maxEventsBuilt ? counts[w] : m_maxEventsBuilt;
+            for (int32_t e = 0; e < n; ++e) {
+                const int32_t* ia = &a[((size_t)w * m_maxEventsBuilt + e) * 4];
+                const float* fb = &b[((size_t)w * m_maxEventsBuilt + e) * 4];
+                b2ContactEvent ev{&world, world.m_fixtures[ia[1] & 0xffff].get(), world.m_fixtures[ia[2] & 0xffff].get(),
+                                  (ia[1] >> 16) & 0xffff, (ia[2] >> 16) & 0xffff, ia[3]};
+                switch (ia[0]) {
+                    case B2GPU_EVENT_BEGIN: m_listener->BeginContact(ev); break;
+                    case B2GPU_EVENT_END: m_listener->EndContact(ev); break;
+                    case B2GPU_EVENT_PRESOLVE: m_listener->PreSolve(ev); break;
+                    default: {
+                        b2ContactImpulse imp{{fb[0], fb[1]}, {fb[2], fb[3]}, ia[3]};
+                        m_listener->PostSolve(ev, imp);
+                    }
+                }
+            }
+        }
+    }
+
+    int32_t m_device = 0;
+    std::vector<std::unique_ptr<b2World>> m_worlds;
+    b2gpu_batch* m_handle = nullptr;
+    b2ContactListener* m_listener = nullptr;
+    int32_t m_eventMask = 0, m_maxContacts = 0, m_maxEvents = 0, m_maxBodies = 0, m_maxEventsBuilt = 0;
+    bool m_stateValid = false, m_forcesDirty = false;
+    std::vector<float> m_xf, m_sweep, m_vel, m_forces;
+    std::vector<int32_t> m_bodyFlags;
+};
+
+// ---- inline members ---------------------------------------------------------------------------------
+inline b2World::b2World(const b2Vec<float, 2>& gravity) : m_gravity(gravity) {
+    m_owned.reset(new b2WorldBatch(gravity, 1));
+    m_batch = m_owned.get();
+}
+inline b2World::~b2World() {}
+
+// A standalone b2World forwards to world 0 of its private batch, which holds the recorded scene.
+#define B2_SELF (m_owned ? m_owned->World(0) : *this)
+
+inline void b2World::SetFlag(int bit, bool on) {
+    b2World& w = B2_SELF;
+    if (w.m_batch->IsBuilt()) throw std::runtime_error("world flags are frozen at the first Step");
+    w.m_flags = on ? (w.m_flags | bit) : (w.m_flags & ~bit);
+    if (&w != this) m_flags = w.m_flags;
+}
+inline bool b2World::IsLocked() const { return m_batch->IsBuilt(); }
+inline int32_t b2World::GetBodyCount() const { return (int32_t)(m_owned ? m_owned->World(0) : *this).m_bodies.size(); }
+inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
+    b2World& w = B2_SELF;
+    if (w.m_batch->IsBuilt()) return nullptr;  // like a locked world (b2World.cpp:100-104)
+    b2g_body_def d;
+    std::memset(&d, 0, sizeof(d));
+    d.type = (int32_t)def->type;
+    d.flags = (def->allowSleep ? B2G_BD_ALLOW_SLEEP : 0) | (def->awake ? B2G_BD_AWAKE : 0) |
+              (def->fixedRotation ? B2G_BD_FIXED_ROTATION : 0) | (def->bullet ? B2G_BD_BULLET : 0) |
+              (def->active ? B2G_BD_ACTIVE : 0);
+    d.position[0] = def->position[0]; d.position[1] = def->position[1];
+    d.angle = def->angle;
+    d.linearVelocity[0] = def->linearVelocity[0]; d.linearVelocity[1] = def->linearVelocity[1];
+    d.angularVelocity = def->angularVelocity;
+    d.linearDamping = def->linearDamping;
+    d.angularDamping = def->angularDamping;
+    d.gravityScale = def->gravityScale;
+    w.m_bodyDefs.push_back(d);
+    std::unique_ptr<b2Body> b(new b2Body);
+    b->m_world = &w;
+    b->m_index = (int32_t)w.m_bodies.size();
+    b->m_type = def->type;
+    b->m_userData = def->userData;
+    w.m_bodies.push_back(std::move(b));
+    return w.m_bodies.back().get();
+}
+inline void b2World::Step(float dt, int32_t vi, int32_t pi) { m_batch->Step(dt, vi, pi); }
+inline void b2World::SetContactListener(b2ContactListener* l) { m_batch->SetContactListener(l); }
+inline int32_t b2World::GetProxyCount() const { return (m_owned ? m_owned->World(0) : *this).m_proxyCount; }
+inline int32_t b2World::GetContactCount() const {
+    b2WorldBatch* batch = m_batch;
+    const b2World& w = m_owned ? m_owned->World(0) : *this;
+    batch->Build();
+    int32_t n = 0;
+    b2WorldBatch::Check(b2gpu_batch_download_field(batch->m_handle, B2GPU_F_CONTACT_COUNT, &n, w.m_index, 1));
+    return n;
+}
+#undef B2_SELF
+
+inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
+    b2World& w = *m_world;
+    if (w.m_batch->IsBuilt() || !def->shape) return nullptr;
+    b2g_fixture_def fd;
+    std::memset(&fd, 0, sizeof(fd));
+    fd.body = m_index;
+    fd.isSensor = def->isSensor;
+    fd.friction = def->friction;
+    fd.restitution = def->restitution;
+    fd.density = def->density;
+    fd.categoryBits = def->filter.categoryBits;
+    fd.maskBits = def->filter.maskBits;
+    fd.groupIndex = def->filter.groupIndex;
+    def->shape->Describe(fd, w.m_vertices);
+    w.m_fixtureDefs.push_back(fd);
+    std::unique_ptr<b2Fixture> f(new b2Fixture);
+    f->m_body = this;
+    f->m_userData = def->userData;
+    f->m_type = def->shape->GetType();
+    f->m_index = (int32_t)w.m_fixtures.size();
+    w.m_firstProxy.push_back(w.m_proxyCount);
+    // proxies: one per shape child (b2Fixture::CreateProxies, b2Fixture.cpp:124-139)
+    int children = 1;
+    if (fd.shapeType == B2G_SHAPE_CHAIN) children = fd.shapeKind == B2G_CHAIN_LOOP ? fd.vertexCount : fd.vertexCount - 1;
+    w.m_proxyCount += children;
+    w.m_fixtures.push_back(std::move(f));
+    return w.m_fixtures.back().get();
+}
+inline const b2Vec<float, 2>& b2Body::GetPosition() const {
+    b2WorldBatch* B = m_world->m_batch;
+    B->Refresh();
+    const float* x = &B->m_xf[B->Slot(this) * 4];
+    m_tmp[0] = {{x[0], x[1]}};
+    return m_tmp[0];
+}
+inline float b2Body::GetAngle() const {
+    b2WorldBatch* B = m_world->m_batch;
+    B->Refresh();
+    return B->m_sweep[B->Slot(this) * 4 + 2];
+}
+inline const b2Vec<float, 2>& b2Body::GetWorldCenter() const {
+    b2WorldBatch* B = m_world->m_batch;
+    B->Refresh();
+    const float* s = &B->m_sweep[B->Slot(this) * 4];
+    m_tmp[1] = {{s[0], s[1]}};
+    return m_tmp[1];
+}
+inline const b2Vec<float, 2>& b2Body::GetLinearVelocity() const {
+    b2WorldBatch* B = m_world->m_batch;
+    B->Refresh();
+    const float* v = &B->m_vel[B->Slot(this) * 4];
+    m_tmp[2] = {{v[0], v[1]}};
+    return m_tmp[2];
+}
+inline float b2Body::GetAngularVelocity() const {
+    b2WorldBatch* B = m_world->m_batch;
+    B->Refresh();
+    return B->m_vel[B->Slot(this) * 4 + 2];
+}
+inline bool b2Body::IsAwake() const {
+    b2WorldBatch* B = m_world->m_batch;
+    B->Refresh();
+    return (B->m_bodyFlags[B->Slot(this)] & 8) != 0;
+}
+inline void b2Body::ApplyForceToCenter(const b2Vec<float, 2>& force, bool) {
+    b2WorldBatch* B = m_world->m_batch;
+    B->Build();
+    float* f = &B->m_forces[B->Slot(this) * 3];
+    f[0] += force[0];
+    f[1] += force[1];
+    B->m_forcesDirty = true;
+}
+inline void b2Body::ApplyTorque(float torque, bool) {
+    b2WorldBatch* B = m_world->m_batch;
+    B->Build();
+    B->m_forces[B->Slot(this) * 3 + 2] += torque;
+    B->m_forcesDirty = true;
+}
+
+}  // namespace box2d
+
+#endif

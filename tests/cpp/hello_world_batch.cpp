@@ -1,0 +1,123 @@
+// HelloWorld/HelloWorld.cpp:30-107 of the reference, compiled against the B200 batch engine's mirror of the
+// reference API (box2dpp_b200/include/Box2D/Gpu/b2WorldBatch.h).  Differences from the reference file: the
+// include line, SetContinuousPhysics(false) (TOI is not on the device path), and the output format — bit
+// patterns instead of %4.2f so that the Python test can compare with the golden answers bit-for-bit.
+//
+// Modes:  hello           the reference's main(): one b2World, 60 steps
+//         batch N ROWS    N pyramid worlds built through CreateBody / CreateFixture in a b2WorldBatch, with a
+//                         contact listener; prints per-world event counts and the top box's state
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include <Box2D/Gpu/b2WorldBatch.h>
+
+using namespace box2d;
+
+static unsigned bits(float f) {
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+
+static int hello() {
+    b2Vec<float, 2> gravity{{0.0f, -10.0f}};
+    b2World world(gravity);
+    world.SetContinuousPhysics(false);
+
+    b2BodyDef groundBodyDef;
+    groundBodyDef.position = {{0.0f, -10.0f}};
+    b2Body* groundBody = world.CreateBody(&groundBodyDef);
+    b2PolygonShape groundBox;
+    groundBox.SetAsBox(50.0f, 10.0f);
+    groundBody->CreateFixture(&groundBox, 0.0f);
+
+    b2BodyDef bodyDef;
+    bodyDef.type = b2BodyType::DYNAMIC_BODY;
+    bodyDef.position = {{0.0f, 4.0f}};
+    b2Body* body = world.CreateBody(&bodyDef);
+    b2PolygonShape dynamicBox;
+    dynamicBox.SetAsBox(1.0f, 1.0f);
+    b2FixtureDef fixtureDef;
+    fixtureDef.shape = &dynamicBox;
+    fixtureDef.density = 1.0f;
+    fixtureDef.friction = 0.3f;
+    body->CreateFixture(&fixtureDef);
+
+    float timeStep = 1.0f / 60.0f;
+    int32_t velocityIterations = 6;
+    int32_t positionIterations = 2;
+    for (int32_t i = 0; i < 60; ++i) {
+        world.Step(timeStep, velocityIterations, positionIterations);
+        b2Vec<float, 2> position = body->GetPosition();
+        float angle = body->GetAngle();
+        b2Vec<float, 2> v = body->GetLinearVelocity();
+        std::printf("%08x %08x %08x %08x %08x %08x\n", bits(position[b2VecX]), bits(position[b2VecY]), bits(angle),
+                    bits(v[b2VecX]), bits(v[b2VecY]), bits(body->GetAngularVelocity()));
+    }
+    if (world.CreateBody(&bodyDef) != nullptr) return 2;  // a stepped world is frozen, like a locked b2World
+    return world.GetBodyCount() == 2 && world.GetProxyCount() == 2 ? 0 : 3;
+}
+
+struct Counter : public b2ContactListener {
+    int begin[64] = {0}, end[64] = {0}, pre[64] = {0}, post[64] = {0};
+    void BeginContact(const b2ContactEvent& e) override { begin[e.world->GetIndex()]++; }
+    void EndContact(const b2ContactEvent& e) override { end[e.world->GetIndex()]++; }
+    void PreSolve(const b2ContactEvent& e) override { pre[e.world->GetIndex()]++; }
+    void PostSolve(const b2ContactEvent& e, const b2ContactImpulse&) override { post[e.world->GetIndex()]++; }
+};
+
+// The Testbed "Pyramid" (ground variant A), world w gets w extra rows
+static int batch(int n, int rows, int steps) {
+    b2WorldBatch worlds(b2Vec<float, 2>{{0.0f, -10.0f}}, n);
+    Counter counter;
+    worlds.SetContactListener(&counter);
+    std::vector<b2Body*> top(n);
+    for (int w = 0; w < n; ++w) {
+        b2World& world = worlds[w];
+        world.SetContinuousPhysics(false);
+        b2BodyDef gd;
+        b2Body* ground = world.CreateBody(&gd);
+        b2PolygonShape gs;
+        gs.SetAsBox(50.0f, 10.0f, b2Vec<float, 2>{{0.0f, -10.0f}}, 0.0f);
+        ground->CreateFixture(&gs, 0.0f);
+        b2PolygonShape box;
+        box.SetAsBox(0.5f, 0.5f);
+        const int count = rows + w;
+        b2Vec<float, 2> x{{-7.0f, 0.75f}};
+        for (int i = 0; i < count; ++i) {
+            b2Vec<float, 2> y = x;
+            for (int j = i; j < count; ++j) {
+                b2BodyDef bd;
+                bd.type = b2BodyType::DYNAMIC_BODY;
+                bd.position = y;
+                b2Body* body = world.CreateBody(&bd);
+                body->CreateFixture(&box, 5.0f);
+                top[w] = body;
+                y[0] += 1.125f;
+            }
+            x[0] += 0.5625f;
+            x[1] += 1.25f;
+        }
+    }
+    for (int s = 0; s < steps; ++s) worlds.Step(1.0f / 60.0f, 8, 3);
+    if (worlds.GetStatus() != 0) return 4;
+    for (int w = 0; w < n; ++w) {
+        b2Vec<float, 2> p = top[w]->GetPosition();
+        std::printf("%d %d %d %d %d %d %d %08x %08x %08x %d\n", w, worlds[w].GetBodyCount(), worlds[w].GetContactCount(),
+                    counter.begin[w], counter.end[w], counter.pre[w], counter.post[w], bits(p[0]), bits(p[1]),
+                    bits(top[w]->GetAngle()), top[w]->IsAwake() ? 1 : 0);
+    }
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    try {
+        if (argc >= 2 && std::strcmp(argv[1], "batch") == 0)
+            return batch(argc > 2 ? std::atoi(argv[2]) : 3, argc > 3 ? std::atoi(argv[3]) : 4, argc > 4 ? std::atoi(argv[4]) : 120);
+        return hello();
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+}
