@@ -169,8 +169,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    W = args.worlds_per_gpu
-    sb = S.pyramid_batch(W, ROWS, flags=flags_throughput(), first_seed=rank * W, jittered=not args.identical)
+    from box2dpp_b200.shard import shard_range
+    # weak scaling: the job has worlds_per_gpu x N worlds; rank r owns a contiguous world-index block
+    first_world, W = shard_range(args.worlds_per_gpu * world_size, world_size, rank)
+    sb = S.pyramid_batch(W, ROWS, flags=flags_throughput(), first_seed=first_world, jittered=not args.identical)
     batch = WorldBatch(sb, device=local_rank, block_size=args.block, generic_solver=args.generic_solver)
     batch.step_n(DT, 8, 3, PREROLL)
     batch.sync()
