@@ -121,7 +121,7 @@ class WorldBatch:
     """A batch of independent worlds on one GPU."""
 
     def __init__(self, scenes, replicate=1, device=0, max_contacts=0, max_events=0, event_mask=0, block_size=0,
-                 generic_solver=False):
+                 generic_solver=False, always_rebuild_islands=False):
         if isinstance(scenes, Scene):
             scenes = [scenes]
         if isinstance(scenes, SceneBatch):
@@ -135,7 +135,7 @@ class WorldBatch:
         d = BatchDesc()
         d.device, d.numWorlds = device, self.num_worlds
         d.maxContacts, d.maxEvents, d.eventMask, d.blockSize = max_contacts, max_events, event_mask, block_size
-        d.reserved = 1 if generic_solver else 0
+        d.reserved = (1 if generic_solver else 0) | (2 if always_rebuild_islands else 0)
         _check(L.b2gpu_scene_capacities(arr, n_scenes, C.byref(d)))
         self.desc = d
         self.h = C.c_void_p()

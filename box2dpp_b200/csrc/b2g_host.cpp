@@ -332,10 +332,6 @@ void put(std::vector<uint32_t>& dst, size_t wordIndex, T v) {
 
 int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int, int>>& shapes /*cap, comps per field*/,
             FlatWorld& out, std::string& err) {
-    if (s.worldFlags & B2G_WORLD_CONTINUOUS) {
-        err = "continuous physics (TOI) is not on the device path: build the world with SetContinuousPhysics(false)";
-        return B2GPU_ERR_UNSUPPORTED;
-    }
     int nb, nf, np, ns, nv;
     CountScene(s, &nb, &nf, &np, &ns, &nv);
     if (nb > cap.NB || nf > cap.NF || np > cap.NP || nv > cap.NV || ns > cap.NS) {

@@ -234,22 +234,16 @@ enum : int { kResEvaluated = 1, kResDead = 2, kResWasTouching = 4, kResTouching 
 // One iteration of the loop in b2ContactManager::Collide for contact k, WITHOUT its side effects on other
 // objects (waking bodies, listener events): fat-AABB test -> mark for destruction, else b2Contact::Update's
 // manifold evaluation and impulse matching.  Returns kRes* | pointCount << 4 | old pointCount << 6.
-__device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, int k) {
+// b2Contact::Update (b2Contact.cpp:170-256) for contact k whose a-record is a0, without the side effects on other
+// objects (SetAwake, listener events), which the callers apply in list order.
+__device__ __forceinline__ int UpdateOne(const Arena& A, int tile, int lane, int k, const int4 a0) {
     Col<int4> cA = col(A.contactA, tile, A.NC, lane);
-    const int4 a0 = cA[k];
     int4 a = a0;
-    const int proxyA = a.x & 0xffff, proxyB = (a.x >> 16) & 0xffff;
+    const int proxyA = a.x & 0xffff;
     const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
     int flags = a.z;
     const int pointCountOld = (a.w >> 8) & 0xff;
     const bool wasTouching = (flags & kContactTouching) != 0;
-    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
-    if (!FatOverlap(proxyFat[proxyA], proxyFat[proxyB])) {
-        a.z = flags | kContactDead;
-        cA[k] = a;
-        return kResDead | (wasTouching ? kResWasTouching : 0) | (pointCountOld << kResOldCountShift);
-    }
-    // b2Contact::Update
     Col<int4> cK = col(A.contactK, tile, A.NC, lane);
     Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane);
     Col<float4> cP1 = col(A.contactP1, tile, A.NC, lane);
@@ -292,6 +286,21 @@ __device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, in
     if (a.z != a0.z || a.w != a0.w) cA[k] = a;
     return kResEvaluated | (wasTouching ? kResWasTouching : 0) | (touching ? kResTouching : 0) |
            (m.pointCount << kResCountShift) | (pointCountOld << kResOldCountShift);
+}
+
+__device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, int k) {
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    const int4 a0 = cA[k];
+    const int proxyA = a0.x & 0xffff, proxyB = (a0.x >> 16) & 0xffff;
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    if (!FatOverlap(proxyFat[proxyA], proxyFat[proxyB])) {
+        int4 a = a0;
+        a.z = a0.z | kContactDead;
+        cA[k] = a;
+        const int pointCountOld = (a0.w >> 8) & 0xff;
+        return kResDead | ((a0.z & kContactTouching) ? kResWasTouching : 0) | (pointCountOld << kResOldCountShift);
+    }
+    return UpdateOne(A, tile, lane, k, a0);
 }
 
 constexpr int kCollideWarps = 8;
@@ -456,7 +465,7 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
         const int w = w0 + t;
         int d = 0;
         if (w < A.numWorlds) {
-            d = A.topoDirty[w];
+            d = A.topoDirty[w] | A.alwaysRebuildIslands;
             if (d) A.topoDirty[w] = 0;
         }
         sDirty[t] = d;
@@ -503,6 +512,7 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
         Col<int> iContacts = col(A.islandContacts, tile, NC, lane);
         Col<int> iContactEnd = col(A.islandContactEnd, tile, NB, lane);
         int islands = 0, nBodies = 0, nContacts = 0;
+        bool wokeAny = false;
         for (int seed = nb - 1; seed >= 0; --seed) {  // m_bodyList is head-inserted: newest first
             const int sf = sBF[(size_t)seed * L + l];
             if (sf & kIbIsland) continue;
@@ -519,6 +529,7 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
                 if ((bf & kIbAwake) == 0) {  // b2Body::SetAwake(true)
                     bf |= kIbAwake | kIbWoken;
                     sBF[(size_t)b * L + l] = (unsigned char)bf;
+                    wokeAny = true;
                 }
                 if ((bf & kIbType) == B2G_STATIC_BODY) continue;
                 for (int k = sHead[(size_t)b * L + l]; k != 0xffff;) {
@@ -550,6 +561,9 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
             ++islands;
         }
         A.islandCount[ws] = islands;
+        // A body woken by this DFS is a seed candidate from the next step on (seeds must be awake, b2World.cpp:415):
+        // the same graph then yields a different seed and DFS order, so the islands have to be rebuilt once more.
+        if (wokeAny) A.topoDirty[w] = 1;
     }
     __syncthreads();
 
@@ -568,10 +582,398 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
     }
 }
 
+constexpr int kVcStride = 9;  // float4 per b2ContactVelocityConstraint
+
+// ---- the reference's b2ContactSolver on one constraint at a time, body state in the body arrays ----
+// Shared by the generic solver kernel (k_solve) and the TOI sub-step solver (b2g_toi.cuh).
+// `vc`: per-world scratch of kVcStride float4 per constraint; i = constraint slot, k = contact array index.
+
+// b2ContactSolver ctor + InitializeVelocityConstraints for one contact (b2ContactSolver.cpp:33-238)
+__device__ __forceinline__ void InitVelocityConstraint(const Arena& A, int tile, int lane, const Col<float4>& vc, int i, int k,
+                                                       bool warmStarting, float dtRatio) {
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    Col<int4> cK = col(A.contactK, tile, A.NC, lane);
+    Col<int2> cS = col(A.contactS, tile, A.NC, lane);
+    Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane);
+    Col<float4> cP1 = col(A.contactP1, tile, A.NC, lane);
+    Col<float4> cN = col(A.contactN, tile, A.NC, lane);
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
+    Col<float4> bodyVel = col(A.bodyVel, tile, A.NB, lane);
+    Col<float4> bodyMass = col(A.bodyMass, tile, A.NB, lane);
+    const int4 a = cA[k];
+    const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+    const int mtype = a.w & 0xff;
+    const int pointCount = (a.w >> 8) & 0xff;
+    const int shapeTypes = (a.w >> 16) & 0xf;
+    const int4 kk = cK[k];
+    const int2 so = cS[k];
+    const float friction = __int_as_float(kk.z), restitution = __int_as_float(kk.w);
+    const float radiusA = ShapeRadius(A.shapeWords + ((size_t)tile * A.NS + so.x) * kTile + lane, shapeTypes & 3);
+    const float radiusB = ShapeRadius(A.shapeWords + ((size_t)tile * A.NS + so.y) * kTile + lane, (shapeTypes >> 2) & 3);
+    const float4 msA = bodyMass[bodyA], msB = bodyMass[bodyB];
+    const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
+    const float4 swA = bodySweep[bodyA], swB = bodySweep[bodyB];
+    const float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
+    const Vec2 cAp = V2(swA.x, swA.y), cBp = V2(swB.x, swB.y);
+    const Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
+    const float wA = veA.z, wB = veB.z;
+    Xf xfA, xfB;
+    xfA.q = MakeRot(swA.z);
+    xfB.q = MakeRot(swB.z);
+    xfA.p = cAp - Mul(xfA.q, V2(msA.z, msA.w));
+    xfB.p = cBp - Mul(xfB.q, V2(msB.z, msB.w));
+    const float4 p0 = cP0[k];
+    float4 p1 = make_float4(0, 0, 0, 0);
+    if (pointCount > 1) p1 = cP1[k];
+    const float4 nn = cN[k];
+    // b2WorldManifold::Initialize (b2Collision.cpp:24-87)
+    Vec2 normal, wp0, wp1 = V2(0, 0);
+    if (mtype == kManifoldCircles) {
+        normal = V2(1.0f, 0.0f);
+        Vec2 pointA = Mul(xfA, V2(nn.z, nn.w));
+        Vec2 pointB = Mul(xfB, V2(p0.x, p0.y));
+        if (DistanceSquared(pointA, pointB) > kEpsilon * kEpsilon) {
+            normal = pointB - pointA;
+            Normalize(normal);
+        }
+        Vec2 ca = pointA + radiusA * normal;
+        Vec2 cb = pointB - radiusB * normal;
+        wp0 = 0.5f * (ca + cb);
+    } else if (mtype == kManifoldFaceA) {
+        normal = Mul(xfA.q, V2(nn.x, nn.y));
+        Vec2 planePoint = Mul(xfA, V2(nn.z, nn.w));
+        {
+            Vec2 clipPoint = Mul(xfB, V2(p0.x, p0.y));
+            Vec2 ca = clipPoint + (radiusA - Dot(clipPoint - planePoint, normal)) * normal;
+            Vec2 cb = clipPoint - radiusB * normal;
+            wp0 = 0.5f * (ca + cb);
+        }
+        if (pointCount > 1) {
+            Vec2 clipPoint = Mul(xfB, V2(p1.x, p1.y));
+            Vec2 ca = clipPoint + (radiusA - Dot(clipPoint - planePoint, normal)) * normal;
+            Vec2 cb = clipPoint - radiusB * normal;
+            wp1 = 0.5f * (ca + cb);
+        }
+    } else {
+        normal = Mul(xfB.q, V2(nn.x, nn.y));
+        Vec2 planePoint = Mul(xfB, V2(nn.z, nn.w));
+        {
+            Vec2 clipPoint = Mul(xfA, V2(p0.x, p0.y));
+            Vec2 cb = clipPoint + (radiusB - Dot(clipPoint - planePoint, normal)) * normal;
+            Vec2 ca = clipPoint - radiusA * normal;
+            wp0 = 0.5f * (ca + cb);
+        }
+        if (pointCount > 1) {
+            Vec2 clipPoint = Mul(xfA, V2(p1.x, p1.y));
+            Vec2 cb = clipPoint + (radiusB - Dot(clipPoint - planePoint, normal)) * normal;
+            Vec2 ca = clipPoint - radiusA * normal;
+            wp1 = 0.5f * (ca + cb);
+        }
+        normal = -normal;
+    }
+    const Vec2 tangent = Cross(normal, 1.0f);
+    int vcPointCount = pointCount;
+    float4 q2, q3, q4 = make_float4(0, 0, 0, 0), q5 = make_float4(0, 0, 0, 0);
+    float4 q6 = make_float4(0, 0, 0, 0), q7 = make_float4(0, 0, 0, 0);
+    Vec2 rA0, rB0, rA1 = V2(0, 0), rB1 = V2(0, 0);
+    {
+        rA0 = wp0 - cAp;
+        rB0 = wp0 - cBp;
+        float rnA = Cross(rA0, normal), rnB = Cross(rB0, normal);
+        float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        float normalMass = kNormal > 0.0f ? Div(1.0f, kNormal) : 0.0f;
+        float rtA = Cross(rA0, tangent), rtB = Cross(rB0, tangent);
+        float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+        float tangentMass = kTangent > 0.0f ? Div(1.0f, kTangent) : 0.0f;
+        float velocityBias = 0.0f;
+        float vRel = Dot(normal, vB + Cross(wB, rB0) - vA - Cross(wA, rA0));
+        if (vRel < -kVelocityThreshold) velocityBias = -restitution * vRel;
+        q2 = make_float4(rA0.x, rA0.y, rB0.x, rB0.y);
+        q3 = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
+    }
+    if (pointCount > 1) {
+        rA1 = wp1 - cAp;
+        rB1 = wp1 - cBp;
+        float rnA = Cross(rA1, normal), rnB = Cross(rB1, normal);
+        float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        float normalMass = kNormal > 0.0f ? Div(1.0f, kNormal) : 0.0f;
+        float rtA = Cross(rA1, tangent), rtB = Cross(rB1, tangent);
+        float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+        float tangentMass = kTangent > 0.0f ? Div(1.0f, kTangent) : 0.0f;
+        float velocityBias = 0.0f;
+        float vRel = Dot(normal, vB + Cross(wB, rB1) - vA - Cross(wA, rA1));
+        if (vRel < -kVelocityThreshold) velocityBias = -restitution * vRel;
+        q4 = make_float4(rA1.x, rA1.y, rB1.x, rB1.y);
+        q5 = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
+        // block solver preparation
+        float rn1A = Cross(rA0, normal), rn1B = Cross(rB0, normal);
+        float rn2A = Cross(rA1, normal), rn2B = Cross(rB1, normal);
+        float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+        float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+        float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+        const float k_maxConditionNumber = 1000.0f;
+        if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
+            // b2Mat22::GetInverse with ex = (k11, k12), ey = (k12, k22)
+            float ma = k11, mb = k12, mc = k12, md = k22;
+            float det = ma * md - mb * mc;
+            if (det != 0.0f) det = Div(1.0f, det);
+            q6 = make_float4(k11, k12, k22, det * md);        // K, normalMass.ex.x
+            q7 = make_float4(-det * mc, -det * mb, det * ma, 0.0f);  // nm.ex.y, nm.ey.x, nm.ey.y
+        } else {
+            vcPointCount = 1;
+        }
+    }
+    float4 imp = make_float4(0, 0, 0, 0);
+    if (warmStarting) imp = make_float4(dtRatio * p0.z, dtRatio * p0.w, dtRatio * p1.z, dtRatio * p1.w);
+    q3.w = __int_as_float(vcPointCount | (pointCount << 8));
+    q5.w = radiusA;
+    q7.w = radiusB;
+    const size_t o = (size_t)i * kVcStride;
+    vc[o + 0] = make_float4(normal.x, normal.y, friction, __int_as_float(a.y));
+    vc[o + 1] = make_float4(mA, iA, mB, iB);
+    vc[o + 2] = q2;
+    vc[o + 3] = q3;
+    vc[o + 4] = q4;
+    vc[o + 5] = q5;
+    vc[o + 6] = q6;
+    vc[o + 7] = q7;
+    vc[o + 8] = imp;
+}
+
+// WarmStart of one constraint (b2ContactSolver.cpp:240-278)
+__device__ __forceinline__ void WarmStartConstraint(const Col<float4>& vc, const Col<float4>& bodyVel, int i) {
+    const size_t o = (size_t)i * kVcStride;
+    const float4 q0 = vc[o + 0], q1 = vc[o + 1], q2 = vc[o + 2], q3 = vc[o + 3], imp = vc[o + 8];
+    const int bodies = __float_as_int(q0.w);
+    const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
+    const int pointCount = __float_as_int(q3.w) & 0xff;
+    const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
+    float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
+    Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
+    float wA = veA.z, wB = veB.z;
+    const Vec2 normal = V2(q0.x, q0.y);
+    const Vec2 tangent = Cross(normal, 1.0f);
+    {
+        Vec2 P = imp.x * normal + imp.y * tangent;
+        wA -= iA * Cross(V2(q2.x, q2.y), P);
+        vA = vA - mA * P;
+        wB += iB * Cross(V2(q2.z, q2.w), P);
+        vB = vB + mB * P;
+    }
+    if (pointCount > 1) {
+        const float4 q4 = vc[o + 4];
+        Vec2 P = imp.z * normal + imp.w * tangent;
+        wA -= iA * Cross(V2(q4.x, q4.y), P);
+        vA = vA - mA * P;
+        wB += iB * Cross(V2(q4.z, q4.w), P);
+        vB = vB + mB * P;
+    }
+    bodyVel[bodyA] = make_float4(vA.x, vA.y, wA, 0.0f);
+    bodyVel[bodyB] = make_float4(vB.x, vB.y, wB, 0.0f);
+}
+
+// SolveVelocityConstraints for one constraint (b2ContactSolver.cpp:280-597)
+__device__ __forceinline__ void SolveVelocityConstraint(const Col<float4>& vc, const Col<float4>& bodyVel, int i) {
+    const size_t o = (size_t)i * kVcStride;
+    const float4 q0 = vc[o + 0], q1 = vc[o + 1], q2 = vc[o + 2], q3 = vc[o + 3];
+    float4 imp = vc[o + 8];
+    const int bodies = __float_as_int(q0.w);
+    const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
+    const int pointCount = __float_as_int(q3.w) & 0xff;
+    const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
+    float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
+    Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
+    float wA = veA.z, wB = veB.z;
+    const Vec2 normal = V2(q0.x, q0.y);
+    const Vec2 tangent = Cross(normal, 1.0f);
+    const float friction = q0.z;
+    const Vec2 rA0 = V2(q2.x, q2.y), rB0 = V2(q2.z, q2.w);
+    // tangent constraints first (tangentSpeed is 0: b2Contact::SetTangentSpeed is not exposed)
+    {
+        Vec2 dv = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
+        float vt = Dot(dv, tangent) - 0.0f;
+        float lambda = q3.y * (-vt);
+        float maxFriction = friction * imp.x;
+        float newImpulse = Clamp(imp.y + lambda, -maxFriction, maxFriction);
+        lambda = newImpulse - imp.y;
+        imp.y = newImpulse;
+        Vec2 P = lambda * tangent;
+        vA = vA - mA * P;
+        wA -= iA * Cross(rA0, P);
+        vB = vB + mB * P;
+        wB += iB * Cross(rB0, P);
+    }
+    if (pointCount == 1) {
+        Vec2 dv = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
+        float vn = Dot(dv, normal);
+        float lambda = -q3.x * (vn - q3.z);
+        float newImpulse = Max(imp.x + lambda, 0.0f);
+        lambda = newImpulse - imp.x;
+        imp.x = newImpulse;
+        Vec2 P = lambda * normal;
+        vA = vA - mA * P;
+        wA -= iA * Cross(rA0, P);
+        vB = vB + mB * P;
+        wB += iB * Cross(rB0, P);
+    } else {
+        const float4 q4 = vc[o + 4], q5 = vc[o + 5], q6 = vc[o + 6], q7 = vc[o + 7];
+        const Vec2 rA1 = V2(q4.x, q4.y), rB1 = V2(q4.z, q4.w);
+        {
+            Vec2 dv = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
+            float vt = Dot(dv, tangent) - 0.0f;
+            float lambda = q5.y * (-vt);
+            float maxFriction = friction * imp.z;
+            float newImpulse = Clamp(imp.w + lambda, -maxFriction, maxFriction);
+            lambda = newImpulse - imp.w;
+            imp.w = newImpulse;
+            Vec2 P = lambda * tangent;
+            vA = vA - mA * P;
+            wA -= iA * Cross(rA1, P);
+            vB = vB + mB * P;
+            wB += iB * Cross(rB1, P);
+        }
+        // block solver
+        Vec2 a = V2(imp.x, imp.z);
+        Vec2 dv1 = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
+        Vec2 dv2 = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
+        float vn1 = Dot(dv1, normal);
+        float vn2 = Dot(dv2, normal);
+        Vec2 b;
+        b.x = vn1 - q3.z;
+        b.y = vn2 - q5.z;
+        const float k11 = q6.x, k12 = q6.y, k22 = q6.z;
+        // b -= b2Mul(K, a), K.ex = (k11, k12), K.ey = (k12, k22)
+        b.x -= k11 * a.x + k12 * a.y;
+        b.y -= k12 * a.x + k22 * a.y;
+        Vec2 x;
+        bool solved = false;
+        // case 1: x = -b2Mul(normalMass, b)
+        x.x = -(q6.w * b.x + q7.y * b.y);
+        x.y = -(q7.x * b.x + q7.z * b.y);
+        if (x.x >= 0.0f && x.y >= 0.0f) solved = true;
+        if (!solved) {  // case 2
+            x.x = -q3.x * b.x;
+            x.y = 0.0f;
+            vn2 = k12 * x.x + b.y;
+            if (x.x >= 0.0f && vn2 >= 0.0f) solved = true;
+        }
+        if (!solved) {  // case 3
+            x.x = 0.0f;
+            x.y = -q5.x * b.y;
+            vn1 = k12 * x.y + b.x;
+            if (x.y >= 0.0f && vn1 >= 0.0f) solved = true;
+        }
+        if (!solved) {  // case 4
+            x.x = 0.0f;
+            x.y = 0.0f;
+            if (b.x >= 0.0f && b.y >= 0.0f) solved = true;
+        }
+        if (solved) {
+            Vec2 d = x - a;
+            Vec2 P1 = d.x * normal;
+            Vec2 P2 = d.y * normal;
+            vA = vA - mA * (P1 + P2);
+            wA -= iA * (Cross(rA0, P1) + Cross(rA1, P2));
+            vB = vB + mB * (P1 + P2);
+            wB += iB * (Cross(rB0, P1) + Cross(rB1, P2));
+            imp.x = x.x;
+            imp.z = x.y;
+        }
+    }
+    vc[o + 8] = imp;
+    bodyVel[bodyA] = make_float4(vA.x, vA.y, wA, 0.0f);
+    bodyVel[bodyB] = make_float4(vB.x, vB.y, wB, 0.0f);
+}
+
+// SolvePositionConstraints / SolveTOIPositionConstraints for one constraint (b2ContactSolver.cpp:614-744, 747-836);
+// folds the constraint's separations into *minSeparationIO.
+__device__ __forceinline__ void SolvePositionConstraint(const Arena& A, int tile, int lane, const Col<float4>& vc, int i, int k,
+                                                        float baumgarte, bool toi, int toiBodyA, int toiBodyB,
+                                                        float* minSeparationIO) {
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane);
+    Col<float4> cP1 = col(A.contactP1, tile, A.NC, lane);
+    Col<float4> cN = col(A.contactN, tile, A.NC, lane);
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
+    Col<float4> bodyMass = col(A.bodyMass, tile, A.NB, lane);
+    float minSeparation = *minSeparationIO;
+    const size_t o = (size_t)i * kVcStride;
+    const float4 q0 = vc[o + 0], q1 = vc[o + 1];
+    const float radiusA = vc[o + 5].w, radiusB = vc[o + 7].w;
+    const int counts = __float_as_int(vc[o + 3].w);
+    const int pointCount = (counts >> 8) & 0xff;  // pc->pointCount is the manifold's
+    const int bodies = __float_as_int(q0.w);
+    const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
+    float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
+    if (toi) {  // SolveTOIPositionConstraints: only the two TOI bodies move (b2ContactSolver.cpp:747-836)
+        if (bodyA != toiBodyA && bodyA != toiBodyB) { mA = 0.0f; iA = 0.0f; }
+        if (bodyB != toiBodyA && bodyB != toiBodyB) { mB = 0.0f; iB = 0.0f; }
+    }
+    const int mtype = cA[k].w & 0xff;
+    const float4 nn = cN[k];
+    const float4 p0 = cP0[k];
+    const float4 msA = bodyMass[bodyA], msB = bodyMass[bodyB];
+    const Vec2 localCenterA = V2(msA.z, msA.w), localCenterB = V2(msB.z, msB.w);
+    float4 swA = bodySweep[bodyA], swB = bodySweep[bodyB];
+    Vec2 cAp = V2(swA.x, swA.y), cBp = V2(swB.x, swB.y);
+    float aA = swA.z, aB = swB.z;
+    const Vec2 localNormal = V2(nn.x, nn.y), localPoint = V2(nn.z, nn.w);
+    for (int j = 0; j < pointCount; ++j) {
+        Vec2 lp = V2(p0.x, p0.y);
+        if (j == 1) {
+            float4 p1 = cP1[k];
+            lp = V2(p1.x, p1.y);
+        }
+        Xf xfA, xfB;
+        xfA.q = MakeRot(aA);
+        xfB.q = MakeRot(aB);
+        xfA.p = cAp - Mul(xfA.q, localCenterA);
+        xfB.p = cBp - Mul(xfB.q, localCenterB);
+        Vec2 normal, point;
+        float separation;
+        if (mtype == kManifoldCircles) {
+            Vec2 pointA = Mul(xfA, localPoint);
+            Vec2 pointB = Mul(xfB, lp);
+            normal = pointB - pointA;
+            Normalize(normal);
+            point = 0.5f * (pointA + pointB);
+            separation = Dot(pointB - pointA, normal) - radiusA - radiusB;
+        } else if (mtype == kManifoldFaceA) {
+            normal = Mul(xfA.q, localNormal);
+            Vec2 planePoint = Mul(xfA, localPoint);
+            Vec2 clipPoint = Mul(xfB, lp);
+            separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+            point = clipPoint;
+        } else {
+            normal = Mul(xfB.q, localNormal);
+            Vec2 planePoint = Mul(xfB, localPoint);
+            Vec2 clipPoint = Mul(xfA, lp);
+            separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+            point = clipPoint;
+            normal = -normal;
+        }
+        Vec2 rA = point - cAp;
+        Vec2 rB = point - cBp;
+        minSeparation = Min(minSeparation, separation);
+        float C = Clamp(baumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+        float rnA = Cross(rA, normal);
+        float rnB = Cross(rB, normal);
+        float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        float impulse = K > 0.0f ? Div(-C, K) : 0.0f;
+        Vec2 P = impulse * normal;
+        cAp = cAp - mA * P;
+        aA -= iA * Cross(rA, P);
+        cBp = cBp + mB * P;
+        aB += iB * Cross(rB, P);
+    }
+    bodySweep[bodyA] = make_float4(cAp.x, cAp.y, aA, swA.w);
+    bodySweep[bodyB] = make_float4(cBp.x, cBp.y, aB, swB.w);
+    *minSeparationIO = minSeparation;
+}
+
 // =================================================================================================
 // k_solve
 // =================================================================================================
-constexpr int kVcStride = 9;  // float4 per b2ContactVelocityConstraint
 
 __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, int posIters) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -639,296 +1041,15 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
         }
 
         // ---- b2ContactSolver ctor + InitializeVelocityConstraints (b2ContactSolver.cpp:33-238) ----
-        for (int i = c0; i < c1; ++i) {
-            const int k = iContacts[i];
-            const int4 a = cA[k];
-            const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
-            const int mtype = a.w & 0xff;
-            const int pointCount = (a.w >> 8) & 0xff;
-            const int shapeTypes = (a.w >> 16) & 0xf;
-            const int4 kk = cK[k];
-            const int2 so = cS[k];
-            const float friction = __int_as_float(kk.z), restitution = __int_as_float(kk.w);
-            const float radiusA = ShapeRadius(A.shapeWords + ((size_t)tile * A.NS + so.x) * kTile + lane, shapeTypes & 3);
-            const float radiusB = ShapeRadius(A.shapeWords + ((size_t)tile * A.NS + so.y) * kTile + lane, (shapeTypes >> 2) & 3);
-            const float4 msA = bodyMass[bodyA], msB = bodyMass[bodyB];
-            const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
-            const float4 swA = bodySweep[bodyA], swB = bodySweep[bodyB];
-            const float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
-            const Vec2 cAp = V2(swA.x, swA.y), cBp = V2(swB.x, swB.y);
-            const Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
-            const float wA = veA.z, wB = veB.z;
-            Xf xfA, xfB;
-            xfA.q = MakeRot(swA.z);
-            xfB.q = MakeRot(swB.z);
-            xfA.p = cAp - Mul(xfA.q, V2(msA.z, msA.w));
-            xfB.p = cBp - Mul(xfB.q, V2(msB.z, msB.w));
-            const float4 p0 = cP0[k];
-            float4 p1 = make_float4(0, 0, 0, 0);
-            if (pointCount > 1) p1 = cP1[k];
-            const float4 nn = cN[k];
-            // b2WorldManifold::Initialize (b2Collision.cpp:24-87)
-            Vec2 normal, wp0, wp1 = V2(0, 0);
-            if (mtype == kManifoldCircles) {
-                normal = V2(1.0f, 0.0f);
-                Vec2 pointA = Mul(xfA, V2(nn.z, nn.w));
-                Vec2 pointB = Mul(xfB, V2(p0.x, p0.y));
-                if (DistanceSquared(pointA, pointB) > kEpsilon * kEpsilon) {
-                    normal = pointB - pointA;
-                    Normalize(normal);
-                }
-                Vec2 ca = pointA + radiusA * normal;
-                Vec2 cb = pointB - radiusB * normal;
-                wp0 = 0.5f * (ca + cb);
-            } else if (mtype == kManifoldFaceA) {
-                normal = Mul(xfA.q, V2(nn.x, nn.y));
-                Vec2 planePoint = Mul(xfA, V2(nn.z, nn.w));
-                {
-                    Vec2 clipPoint = Mul(xfB, V2(p0.x, p0.y));
-                    Vec2 ca = clipPoint + (radiusA - Dot(clipPoint - planePoint, normal)) * normal;
-                    Vec2 cb = clipPoint - radiusB * normal;
-                    wp0 = 0.5f * (ca + cb);
-                }
-                if (pointCount > 1) {
-                    Vec2 clipPoint = Mul(xfB, V2(p1.x, p1.y));
-                    Vec2 ca = clipPoint + (radiusA - Dot(clipPoint - planePoint, normal)) * normal;
-                    Vec2 cb = clipPoint - radiusB * normal;
-                    wp1 = 0.5f * (ca + cb);
-                }
-            } else {
-                normal = Mul(xfB.q, V2(nn.x, nn.y));
-                Vec2 planePoint = Mul(xfB, V2(nn.z, nn.w));
-                {
-                    Vec2 clipPoint = Mul(xfA, V2(p0.x, p0.y));
-                    Vec2 cb = clipPoint + (radiusB - Dot(clipPoint - planePoint, normal)) * normal;
-                    Vec2 ca = clipPoint - radiusA * normal;
-                    wp0 = 0.5f * (ca + cb);
-                }
-                if (pointCount > 1) {
-                    Vec2 clipPoint = Mul(xfA, V2(p1.x, p1.y));
-                    Vec2 cb = clipPoint + (radiusB - Dot(clipPoint - planePoint, normal)) * normal;
-                    Vec2 ca = clipPoint - radiusA * normal;
-                    wp1 = 0.5f * (ca + cb);
-                }
-                normal = -normal;
-            }
-            const Vec2 tangent = Cross(normal, 1.0f);
-            int vcPointCount = pointCount;
-            float4 q2, q3, q4 = make_float4(0, 0, 0, 0), q5 = make_float4(0, 0, 0, 0);
-            float4 q6 = make_float4(0, 0, 0, 0), q7 = make_float4(0, 0, 0, 0);
-            Vec2 rA0, rB0, rA1 = V2(0, 0), rB1 = V2(0, 0);
-            {
-                rA0 = wp0 - cAp;
-                rB0 = wp0 - cBp;
-                float rnA = Cross(rA0, normal), rnB = Cross(rB0, normal);
-                float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-                float normalMass = kNormal > 0.0f ? Div(1.0f, kNormal) : 0.0f;
-                float rtA = Cross(rA0, tangent), rtB = Cross(rB0, tangent);
-                float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
-                float tangentMass = kTangent > 0.0f ? Div(1.0f, kTangent) : 0.0f;
-                float velocityBias = 0.0f;
-                float vRel = Dot(normal, vB + Cross(wB, rB0) - vA - Cross(wA, rA0));
-                if (vRel < -kVelocityThreshold) velocityBias = -restitution * vRel;
-                q2 = make_float4(rA0.x, rA0.y, rB0.x, rB0.y);
-                q3 = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
-            }
-            if (pointCount > 1) {
-                rA1 = wp1 - cAp;
-                rB1 = wp1 - cBp;
-                float rnA = Cross(rA1, normal), rnB = Cross(rB1, normal);
-                float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-                float normalMass = kNormal > 0.0f ? Div(1.0f, kNormal) : 0.0f;
-                float rtA = Cross(rA1, tangent), rtB = Cross(rB1, tangent);
-                float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
-                float tangentMass = kTangent > 0.0f ? Div(1.0f, kTangent) : 0.0f;
-                float velocityBias = 0.0f;
-                float vRel = Dot(normal, vB + Cross(wB, rB1) - vA - Cross(wA, rA1));
-                if (vRel < -kVelocityThreshold) velocityBias = -restitution * vRel;
-                q4 = make_float4(rA1.x, rA1.y, rB1.x, rB1.y);
-                q5 = make_float4(normalMass, tangentMass, velocityBias, 0.0f);
-                // block solver preparation
-                float rn1A = Cross(rA0, normal), rn1B = Cross(rB0, normal);
-                float rn2A = Cross(rA1, normal), rn2B = Cross(rB1, normal);
-                float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
-                float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
-                float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
-                const float k_maxConditionNumber = 1000.0f;
-                if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
-                    // b2Mat22::GetInverse with ex = (k11, k12), ey = (k12, k22)
-                    float ma = k11, mb = k12, mc = k12, md = k22;
-                    float det = ma * md - mb * mc;
-                    if (det != 0.0f) det = Div(1.0f, det);
-                    q6 = make_float4(k11, k12, k22, det * md);        // K, normalMass.ex.x
-                    q7 = make_float4(-det * mc, -det * mb, det * ma, 0.0f);  // nm.ex.y, nm.ey.x, nm.ey.y
-                } else {
-                    vcPointCount = 1;
-                }
-            }
-            float4 imp = make_float4(0, 0, 0, 0);
-            if (warmStarting) imp = make_float4(dtRatio * p0.z, dtRatio * p0.w, dtRatio * p1.z, dtRatio * p1.w);
-            q3.w = __int_as_float(vcPointCount | (pointCount << 8));
-            q5.w = radiusA;
-            q7.w = radiusB;
-            const size_t o = (size_t)i * kVcStride;
-            vc[o + 0] = make_float4(normal.x, normal.y, friction, __int_as_float(a.y));
-            vc[o + 1] = make_float4(mA, iA, mB, iB);
-            vc[o + 2] = q2;
-            vc[o + 3] = q3;
-            vc[o + 4] = q4;
-            vc[o + 5] = q5;
-            vc[o + 6] = q6;
-            vc[o + 7] = q7;
-            vc[o + 8] = imp;
-        }
+        for (int i = c0; i < c1; ++i) InitVelocityConstraint(A, tile, lane, vc, i, iContacts[i], warmStarting, dtRatio);
 
         // ---- WarmStart (b2ContactSolver.cpp:240-278) ----
-        if (warmStarting) {
-            for (int i = c0; i < c1; ++i) {
-                const size_t o = (size_t)i * kVcStride;
-                const float4 q0 = vc[o + 0], q1 = vc[o + 1], q2 = vc[o + 2], q3 = vc[o + 3], imp = vc[o + 8];
-                const int bodies = __float_as_int(q0.w);
-                const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
-                const int pointCount = __float_as_int(q3.w) & 0xff;
-                const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
-                float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
-                Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
-                float wA = veA.z, wB = veB.z;
-                const Vec2 normal = V2(q0.x, q0.y);
-                const Vec2 tangent = Cross(normal, 1.0f);
-                {
-                    Vec2 P = imp.x * normal + imp.y * tangent;
-                    wA -= iA * Cross(V2(q2.x, q2.y), P);
-                    vA = vA - mA * P;
-                    wB += iB * Cross(V2(q2.z, q2.w), P);
-                    vB = vB + mB * P;
-                }
-                if (pointCount > 1) {
-                    const float4 q4 = vc[o + 4];
-                    Vec2 P = imp.z * normal + imp.w * tangent;
-                    wA -= iA * Cross(V2(q4.x, q4.y), P);
-                    vA = vA - mA * P;
-                    wB += iB * Cross(V2(q4.z, q4.w), P);
-                    vB = vB + mB * P;
-                }
-                bodyVel[bodyA] = make_float4(vA.x, vA.y, wA, 0.0f);
-                bodyVel[bodyB] = make_float4(vB.x, vB.y, wB, 0.0f);
-            }
-        }
+        if (warmStarting)
+            for (int i = c0; i < c1; ++i) WarmStartConstraint(vc, bodyVel, i);
 
         // ---- SolveVelocityConstraints (b2ContactSolver.cpp:280-597) ----
-        for (int it = 0; it < velIters; ++it) {
-            for (int i = c0; i < c1; ++i) {
-                const size_t o = (size_t)i * kVcStride;
-                const float4 q0 = vc[o + 0], q1 = vc[o + 1], q2 = vc[o + 2], q3 = vc[o + 3];
-                float4 imp = vc[o + 8];
-                const int bodies = __float_as_int(q0.w);
-                const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
-                const int pointCount = __float_as_int(q3.w) & 0xff;
-                const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
-                float4 veA = bodyVel[bodyA], veB = bodyVel[bodyB];
-                Vec2 vA = V2(veA.x, veA.y), vB = V2(veB.x, veB.y);
-                float wA = veA.z, wB = veB.z;
-                const Vec2 normal = V2(q0.x, q0.y);
-                const Vec2 tangent = Cross(normal, 1.0f);
-                const float friction = q0.z;
-                const Vec2 rA0 = V2(q2.x, q2.y), rB0 = V2(q2.z, q2.w);
-                // tangent constraints first (tangentSpeed is 0: b2Contact::SetTangentSpeed is not exposed)
-                {
-                    Vec2 dv = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
-                    float vt = Dot(dv, tangent) - 0.0f;
-                    float lambda = q3.y * (-vt);
-                    float maxFriction = friction * imp.x;
-                    float newImpulse = Clamp(imp.y + lambda, -maxFriction, maxFriction);
-                    lambda = newImpulse - imp.y;
-                    imp.y = newImpulse;
-                    Vec2 P = lambda * tangent;
-                    vA = vA - mA * P;
-                    wA -= iA * Cross(rA0, P);
-                    vB = vB + mB * P;
-                    wB += iB * Cross(rB0, P);
-                }
-                if (pointCount == 1) {
-                    Vec2 dv = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
-                    float vn = Dot(dv, normal);
-                    float lambda = -q3.x * (vn - q3.z);
-                    float newImpulse = Max(imp.x + lambda, 0.0f);
-                    lambda = newImpulse - imp.x;
-                    imp.x = newImpulse;
-                    Vec2 P = lambda * normal;
-                    vA = vA - mA * P;
-                    wA -= iA * Cross(rA0, P);
-                    vB = vB + mB * P;
-                    wB += iB * Cross(rB0, P);
-                } else {
-                    const float4 q4 = vc[o + 4], q5 = vc[o + 5], q6 = vc[o + 6], q7 = vc[o + 7];
-                    const Vec2 rA1 = V2(q4.x, q4.y), rB1 = V2(q4.z, q4.w);
-                    {
-                        Vec2 dv = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
-                        float vt = Dot(dv, tangent) - 0.0f;
-                        float lambda = q5.y * (-vt);
-                        float maxFriction = friction * imp.z;
-                        float newImpulse = Clamp(imp.w + lambda, -maxFriction, maxFriction);
-                        lambda = newImpulse - imp.w;
-                        imp.w = newImpulse;
-                        Vec2 P = lambda * tangent;
-                        vA = vA - mA * P;
-                        wA -= iA * Cross(rA1, P);
-                        vB = vB + mB * P;
-                        wB += iB * Cross(rB1, P);
-                    }
-                    // block solver
-                    Vec2 a = V2(imp.x, imp.z);
-                    Vec2 dv1 = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
-                    Vec2 dv2 = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
-                    float vn1 = Dot(dv1, normal);
-                    float vn2 = Dot(dv2, normal);
-                    Vec2 b;
-                    b.x = vn1 - q3.z;
-                    b.y = vn2 - q5.z;
-                    const float k11 = q6.x, k12 = q6.y, k22 = q6.z;
-                    // b -= b2Mul(K, a), K.ex = (k11, k12), K.ey = (k12, k22)
-                    b.x -= k11 * a.x + k12 * a.y;
-                    b.y -= k12 * a.x + k22 * a.y;
-                    Vec2 x;
-                    bool solved = false;
-                    // case 1: x = -b2Mul(normalMass, b)
-                    x.x = -(q6.w * b.x + q7.y * b.y);
-                    x.y = -(q7.x * b.x + q7.z * b.y);
-                    if (x.x >= 0.0f && x.y >= 0.0f) solved = true;
-                    if (!solved) {  // case 2
-                        x.x = -q3.x * b.x;
-                        x.y = 0.0f;
-                        vn2 = k12 * x.x + b.y;
-                        if (x.x >= 0.0f && vn2 >= 0.0f) solved = true;
-                    }
-                    if (!solved) {  // case 3
-                        x.x = 0.0f;
-                        x.y = -q5.x * b.y;
-                        vn1 = k12 * x.y + b.x;
-                        if (x.y >= 0.0f && vn1 >= 0.0f) solved = true;
-                    }
-                    if (!solved) {  // case 4
-                        x.x = 0.0f;
-                        x.y = 0.0f;
-                        if (b.x >= 0.0f && b.y >= 0.0f) solved = true;
-                    }
-                    if (solved) {
-                        Vec2 d = x - a;
-                        Vec2 P1 = d.x * normal;
-                        Vec2 P2 = d.y * normal;
-                        vA = vA - mA * (P1 + P2);
-                        wA -= iA * (Cross(rA0, P1) + Cross(rA1, P2));
-                        vB = vB + mB * (P1 + P2);
-                        wB += iB * (Cross(rB0, P1) + Cross(rB1, P2));
-                        imp.x = x.x;
-                        imp.z = x.y;
-                    }
-                }
-                vc[o + 8] = imp;
-                bodyVel[bodyA] = make_float4(vA.x, vA.y, wA, 0.0f);
-                bodyVel[bodyB] = make_float4(vB.x, vB.y, wB, 0.0f);
-            }
-        }
+        for (int it = 0; it < velIters; ++it)
+            for (int i = c0; i < c1; ++i) SolveVelocityConstraint(vc, bodyVel, i);
 
         // ---- StoreImpulses (b2ContactSolver.cpp:599-612) + Report/PostSolve (b2Island.cpp:517-540) ----
         for (int i = c0; i < c1; ++i) {
@@ -978,76 +1099,8 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
         bool positionSolved = false;
         for (int it = 0; it < posIters; ++it) {
             float minSeparation = 0.0f;
-            for (int i = c0; i < c1; ++i) {
-                const size_t o = (size_t)i * kVcStride;
-                const int k = iContacts[i];
-                const float4 q0 = vc[o + 0], q1 = vc[o + 1];
-                const float radiusA = vc[o + 5].w, radiusB = vc[o + 7].w;
-                const int counts = __float_as_int(vc[o + 3].w);
-                const int pointCount = (counts >> 8) & 0xff;  // pc->pointCount is the manifold's
-                const int bodies = __float_as_int(q0.w);
-                const int bodyA = bodies & 0xffff, bodyB = (bodies >> 16) & 0xffff;
-                const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
-                const int mtype = cA[k].w & 0xff;
-                const float4 nn = cN[k];
-                const float4 p0 = cP0[k];
-                const float4 msA = bodyMass[bodyA], msB = bodyMass[bodyB];
-                const Vec2 localCenterA = V2(msA.z, msA.w), localCenterB = V2(msB.z, msB.w);
-                float4 swA = bodySweep[bodyA], swB = bodySweep[bodyB];
-                Vec2 cAp = V2(swA.x, swA.y), cBp = V2(swB.x, swB.y);
-                float aA = swA.z, aB = swB.z;
-                const Vec2 localNormal = V2(nn.x, nn.y), localPoint = V2(nn.z, nn.w);
-                for (int j = 0; j < pointCount; ++j) {
-                    Vec2 lp = V2(p0.x, p0.y);
-                    if (j == 1) {
-                        float4 p1 = cP1[k];
-                        lp = V2(p1.x, p1.y);
-                    }
-                    Xf xfA, xfB;
-                    xfA.q = MakeRot(aA);
-                    xfB.q = MakeRot(aB);
-                    xfA.p = cAp - Mul(xfA.q, localCenterA);
-                    xfB.p = cBp - Mul(xfB.q, localCenterB);
-                    Vec2 normal, point;
-                    float separation;
-                    if (mtype == kManifoldCircles) {
-                        Vec2 pointA = Mul(xfA, localPoint);
-                        Vec2 pointB = Mul(xfB, lp);
-                        normal = pointB - pointA;
-                        Normalize(normal);
-                        point = 0.5f * (pointA + pointB);
-                        separation = Dot(pointB - pointA, normal) - radiusA - radiusB;
-                    } else if (mtype == kManifoldFaceA) {
-                        normal = Mul(xfA.q, localNormal);
-                        Vec2 planePoint = Mul(xfA, localPoint);
-                        Vec2 clipPoint = Mul(xfB, lp);
-                        separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
-                        point = clipPoint;
-                    } else {
-                        normal = Mul(xfB.q, localNormal);
-                        Vec2 planePoint = Mul(xfB, localPoint);
-                        Vec2 clipPoint = Mul(xfA, lp);
-                        separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
-                        point = clipPoint;
-                        normal = -normal;
-                    }
-                    Vec2 rA = point - cAp;
-                    Vec2 rB = point - cBp;
-                    minSeparation = Min(minSeparation, separation);
-                    float C = Clamp(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
-                    float rnA = Cross(rA, normal);
-                    float rnB = Cross(rB, normal);
-                    float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-                    float impulse = K > 0.0f ? Div(-C, K) : 0.0f;
-                    Vec2 P = impulse * normal;
-                    cAp = cAp - mA * P;
-                    aA -= iA * Cross(rA, P);
-                    cBp = cBp + mB * P;
-                    aB += iB * Cross(rB, P);
-                }
-                bodySweep[bodyA] = make_float4(cAp.x, cAp.y, aA, swA.w);
-                bodySweep[bodyB] = make_float4(cBp.x, cBp.y, aB, swB.w);
-            }
+            for (int i = c0; i < c1; ++i)
+                SolvePositionConstraint(A, tile, lane, vc, i, iContacts[i], kBaumgarte, false, -1, -1, &minSeparation);
             if (minSeparation >= -3.0f * kLinearSlop) {
                 positionSolved = true;
                 break;
@@ -1087,7 +1140,12 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
             for (int i = b0; i < b1; ++i) {
                 int b = iBodies[i];
                 int f = bodyFlags[b];
-                if ((f & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+                if ((f & kBodyTypeMask) == B2G_STATIC_BODY) {
+                    // islands are built and solved alternately: this island's DFS re-woke a static body that an
+                    // earlier island of the same step had put to sleep (b2World.cpp:441)
+                    if ((f & kBodyAwake) == 0) bodyFlags[b] = f | kBodyAwake;
+                    continue;
+                }
                 float4 vel = bodyVel[b];
                 float4 sw = bodySweep[b];
                 if ((f & kBodyAutoSleep) == 0 || vel.z * vel.z > angTolSqr || Dot(V2(vel.x, vel.y), V2(vel.x, vel.y)) > linTolSqr) {
@@ -1209,6 +1267,42 @@ __device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB, bool
     WakeBody(c.bodyFlags, c.bodySweep, bodyB);
 }
 
+// b2Fixture::Synchronize for one proxy (Dynamics/b2Fixture.cpp:154-177) + b2DynamicTree::MoveProxy's fat-AABB rule
+// (Collision/b2DynamicTree.cpp:137-181) + b2BroadPhase::BufferMove.  Returns true when the proxy was re-fattened.
+__device__ __forceinline__ bool SynchronizeProxy(const Arena& A, int tile, int lane, int p, int fixture, int child, int fi, int body) {
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    Col<float4> bodyXf = col(A.bodyXf, tile, A.NB, lane);
+    Col<float4> bodySweep0 = col(A.bodySweep0, tile, A.NB, lane);
+    Col<float4> bodyMass = col(A.bodyMass, tile, A.NB, lane);
+    Col<float2> chainVerts = col(A.chainVerts, tile, A.NV, lane);
+    int shapeType = (fi >> 16) & 3;
+    const float* sw = A.shapeWords + ((size_t)tile * A.NS + col(A.fixtureShape, tile, A.NF, lane)[fixture]) * kTile + lane;
+    float4 s0 = bodySweep0[body];
+    float4 ms = bodyMass[body];
+    Xf xf1;
+    xf1.q = MakeRot(s0.z);
+    xf1.p = V2(s0.x, s0.y) - Mul(xf1.q, V2(ms.z, ms.w));
+    Xf xf2 = LoadXf(bodyXf, body);
+    Vec2 lo1, hi1, lo2, hi2;
+    ShapeAABB(sw, shapeType, chainVerts, child, xf1, &lo1, &hi1);
+    ShapeAABB(sw, shapeType, chainVerts, child, xf2, &lo2, &hi2);
+    Vec2 lo = Min(lo1, lo2), hi = Max(hi1, hi2);
+    Vec2 displacement = xf2.p - xf1.p;
+    float4 fat = proxyFat[p];
+    // b2AABB::Contains
+    bool contains = fat.x <= lo.x && fat.y <= lo.y && hi.x <= fat.z && hi.y <= fat.w;
+    if (contains) return false;
+    Vec2 r = V2(kAabbExtension, kAabbExtension);
+    lo = lo - r;
+    hi = hi + r;
+    Vec2 d = kAabbMultiplier * displacement;
+    if (d.x < 0.0f) lo.x += d.x; else hi.x += d.x;
+    if (d.y < 0.0f) lo.y += d.y; else hi.y += d.y;
+    proxyFat[p] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    col(A.proxyMoved, tile, A.NP, lane)[p] = 1;  // b2BroadPhase::BufferMove
+    return true;
+}
+
 // b2BroadPhase::UpdatePairs for one world by one thread: the move buffer is read from the proxyMoved flags and
 // the pairs are produced directly in (proxyIdA, proxyIdB) order.  Used for the initial FindNewContacts of a
 // freshly built world and as the overflow path of k_sync_pairs.
@@ -1303,31 +1397,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_sync_pairs(Arena A, float d
         int bf = bodyFlags[body];
         if ((bf & kBodyIsland) == 0) continue;          // not in an island: did not move
         if ((bf & kBodyTypeMask) == B2G_STATIC_BODY) continue;
-        int shapeType = (fi >> 16) & 3;
-        const float* sw = A.shapeWords + ((size_t)tile * A.NS + fixtureShape[fixture]) * kTile + lane;
-        float4 s0 = bodySweep0[body];
-        float4 ms = bodyMass[body];
-        Xf xf1;
-        xf1.q = MakeRot(s0.z);
-        xf1.p = V2(s0.x, s0.y) - Mul(xf1.q, V2(ms.z, ms.w));
-        Xf xf2 = LoadXf(bodyXf, body);
-        Vec2 lo1, hi1, lo2, hi2;
-        ShapeAABB(sw, shapeType, chainVerts, child, xf1, &lo1, &hi1);
-        ShapeAABB(sw, shapeType, chainVerts, child, xf2, &lo2, &hi2);
-        Vec2 lo = Min(lo1, lo2), hi = Max(hi1, hi2);
-        Vec2 displacement = xf2.p - xf1.p;
-        float4 fat = proxyFat[p];
-        // b2AABB::Contains
-        bool contains = fat.x <= lo.x && fat.y <= lo.y && hi.x <= fat.z && hi.y <= fat.w;
-        if (contains) continue;
-        Vec2 r = V2(kAabbExtension, kAabbExtension);
-        lo = lo - r;
-        hi = hi + r;
-        Vec2 d = kAabbMultiplier * displacement;
-        if (d.x < 0.0f) lo.x += d.x; else hi.x += d.x;
-        if (d.y < 0.0f) lo.y += d.y; else hi.y += d.y;
-        proxyFat[p] = make_float4(lo.x, lo.y, hi.x, hi.y);
-        proxyMoved[p] = 1;  // b2BroadPhase::BufferMove
+        if (!SynchronizeProxy(A, tile, lane, p, fixture, child, fi, body)) continue;
         int slot = atomicAdd(&sNMoved[lane], 1);
         if (slot < kMaxMoved) sMoved[slot][lane] = (uint16_t)p;
     }

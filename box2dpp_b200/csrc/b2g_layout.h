@@ -35,9 +35,16 @@ enum : int {
     kBodyBullet = 1 << 5,
     kBodyFixedRotation = 1 << 6,
     kBodyActive = 1 << 7,
+    kBodyToiIsland = 1 << 8,  // e_islandFlag as b2World::SolveTOI uses it (kBodyIsland keeps the discrete islands)
+    kBodyToiMoved = 1 << 9,   // displaced by the current TOI sub-step (temporary)
 };
 // contact flag bits (Box2D/Dynamics/Contacts/b2Contact.h:155-174)
-enum : int { kContactIsland = 1, kContactTouching = 2, kContactEnabled = 4, kContactFilter = 8, kContactDead = 16 };
+enum : int {
+    kContactIsland = 1, kContactTouching = 2, kContactEnabled = 4, kContactFilter = 8, kContactDead = 16,
+    kContactToi = 32,         // e_toiFlag: contactToi[k] holds a valid cached time of impact
+    kContactToiIsland = 64,   // e_islandFlag inside b2World::SolveTOI
+    kContactToiCountShift = 8, kContactToiCountMask = 0xf << 8,  // m_toiCount (0 .. b2_maxSubSteps + 1)
+};
 // per-world status bits surfaced by b2gpu_batch_read_status
 enum : int {
     kStatusContactOverflow = 1,
@@ -73,7 +80,7 @@ struct Arena {
     // ---- bodies [tile][NB][lane] ----
     float4* bodyXf;      // m_xf: p.x p.y q.s q.c
     float4* bodySweep;   // m_sweep.c.xy, m_sweep.a, m_sleepTime
-    float4* bodySweep0;  // m_sweep.c0.xy, m_sweep.a0, (unused)
+    float4* bodySweep0;  // m_sweep.c0.xy, m_sweep.a0, m_sweep.alpha0
     float4* bodyVel;     // m_linearVelocity.xy, m_angularVelocity, (unused)
     float4* bodyForce;   // m_force.xy, m_torque, (unused)
     float4* bodyMass;    // m_invMass, m_invI, localCenter.xy
@@ -122,10 +129,17 @@ struct Arena {
     int* solveCount;     // [tile][lane]         island contacts of this step (all islands)
     int* islandSolved;   // [tile][ceil(NB/32)][lane]  bit per island: position solver converged
 
+    // ---- continuous collision (b2World::SolveTOI) ----
+    float* contactToi;   // [tile][NC][lane]      b2Contact::m_toi (valid while kContactToi is set)
+    int* toiBodies;      // [tile][64][lane]      bodies of the current TOI mini-island (2 * b2_maxTOIContacts)
+    int* toiContacts;    // [tile][32][lane]      its contacts (b2_maxTOIContacts)
+    float4* toiVc;       // [tile][32 * 9][lane]  its velocity constraints
+
     // ---- events [tile][NE][lane] ----
     int4* eventA;        // type, fixtureA | childA << 16, fixtureB | childB << 16, count
     float4* eventB;      // normalImpulses[2], tangentImpulses[2]
     int eventMask;       // bit per kEvent* type recorded
+    int alwaysRebuildIslands;  // validation switch: k_islands ignores topoDirty (desc.reserved bit 1)
 };
 
 #ifdef __CUDACC__

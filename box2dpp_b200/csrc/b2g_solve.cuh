@@ -1013,7 +1013,12 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_solve_finalize(Arena A, flo
         for (int i = b0; i < b1; ++i) {
             int b = iBodies[i];
             int f = bodyFlags[b];
-            if ((f & kBodyTypeMask) == B2G_STATIC_BODY) continue;
+            if ((f & kBodyTypeMask) == B2G_STATIC_BODY) {
+                // b2World::Solve builds and solves islands alternately: this island's DFS re-woke a static body
+                // that an earlier island of the same step had put to sleep (b2World.cpp:441)
+                if ((f & kBodyAwake) == 0) bodyFlags[b] = f | kBodyAwake;
+                continue;
+            }
             float4 vel = bodyVel[b];
             float4 sw = bodySweep[b];
             if ((f & kBodyAutoSleep) == 0 || vel.z * vel.z > angTolSqr || Dot(V2(vel.x, vel.y), V2(vel.x, vel.y)) > linTolSqr) {

@@ -12,6 +12,7 @@
 #include "../../include/b2gpu.h"
 #include "b2g_kernels.cuh"
 #include "b2g_solve.cuh"
+#include "b2g_toi.cuh"
 
 using namespace b2g;
 
@@ -164,6 +165,7 @@ struct b2gpu_batch {
     std::vector<Field> fields;
     std::vector<void*> allocations;
     bool needInitialPairs = true;  // b2World::e_newFixture
+    bool anyContinuous = false;    // some world has B2G_WORLD_CONTINUOUS: the step ends with k_toi
     int blockSize = 32;
     bool tileSolver = false;       // b2g_solve.cuh path: the tile's body table fits in shared memory
     size_t solveSmem = 0;
@@ -211,6 +213,7 @@ int allocateArena(b2gpu_batch* b) {
     A.NB = d.maxBodies; A.NF = d.maxFixtures; A.NP = d.maxProxies; A.NC = d.maxContacts;
     A.NS = d.maxShapeWords; A.NV = d.maxChainVerts > 0 ? d.maxChainVerts : 1; A.NE = d.maxEvents > 0 ? d.maxEvents : 1;
     A.eventMask = d.eventMask;
+    A.alwaysRebuildIslands = (d.reserved >> 1) & 1;
     ALLOC(gravity, 1, float2); ALLOC(worldFlags, 1, int); ALLOC(invDt0, 1, float);
     ALLOC(bodyCount, 1, int); ALLOC(proxyCount, 1, int); ALLOC(contactCount, 1, int);
     ALLOC(status, 1, int); ALLOC(eventCount, 1, int); ALLOC(islandCount, 1, int); ALLOC(stepCount, 1, int);
@@ -236,6 +239,8 @@ int allocateArena(b2gpu_batch* b) {
     } else {
         ALLOC(vc, (size_t)A.NC * kVcStride, float4);
     }
+    ALLOC(contactToi, A.NC, float); ALLOC(toiBodies, kToiBodyCap, int); ALLOC(toiContacts, kMaxToiContacts, int);
+    ALLOC(toiVc, (size_t)kMaxToiContacts * kVcStride, float4);
     ALLOC(eventA, A.NE, int4); ALLOC(eventB, A.NE, float4);
 
     b->fields.assign(B2GPU_F_COUNT, Field{nullptr, 0, 0});
@@ -345,13 +350,14 @@ int configureKernels(b2gpu_batch* b) {
 
 // Kernel names in launch order of one step (b2gpu_batch_profile_kernels reports times in this order).
 const char* const kTileKernels[] = {"k_collide", "k_islands", "k_solve_prepare", "k_solve_velocity", "k_solve_integrate",
-                                    "k_solve_position", "k_solve_finalize", "k_sync_pairs"};
-const char* const kGenericKernels[] = {"k_collide", "k_islands", "k_solve", "k_sync_pairs"};
-constexpr int kMaxStepKernels = 8;
+                                    "k_solve_position", "k_solve_finalize", "k_sync_pairs", "k_toi"};
+const char* const kGenericKernels[] = {"k_collide", "k_islands", "k_solve", "k_sync_pairs", "k_toi"};
+constexpr int kMaxStepKernels = 9;
 
-int stepKernelCount(const b2gpu_batch* b) { return b->tileSolver ? 8 : 4; }
+// k_toi only runs when some world has continuous physics on (b2World::Step: `if (m_continuousPhysics && dt > 0)`)
+int stepKernelCount(const b2gpu_batch* b) { return (b->tileSolver ? 8 : 4) + (b->anyContinuous ? 1 : 0); }
 
-// One b2World::Step for the whole batch (Box2D/Dynamics/b2World.cpp:888-954), TOI excluded.
+// One b2World::Step for the whole batch (Box2D/Dynamics/b2World.cpp:888-954).
 // marks (optional): stepKernelCount + 1 events, one before each kernel and one after the last.
 int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks) {
     const int threads = b->blockSize;
@@ -392,6 +398,11 @@ int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_
         k_sync_pairs<<<tiles, kPairWarps * 32, 0, st>>>(b->A, dt);
         mark();
         b->launches += 2;
+        if (b->anyContinuous) {  // if (m_continuousPhysics && step.dt > 0) SolveTOI(step)
+            k_toi<<<tiles, kToiWarps * 32, 0, st>>>(b->A, dt, velIters);
+            mark();
+            b->launches++;
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -464,6 +475,15 @@ int b2gpu_batch_upload_field(b2gpu_batch* b, int32_t field, const void* host, in
     int rc = transferField(b, field, const_cast<void*>(host), firstWorld, worldCount, true);
     // a freshly uploaded move buffer == b2World::e_newFixture: the next Step starts with FindNewContacts
     if (rc == B2GPU_OK && field == B2GPU_F_PROXY_MOVED) b->needInitialPairs = true;
+    if (rc == B2GPU_OK && field == B2GPU_F_WORLD_FLAGS && !b->anyContinuous) {
+        const int32_t* flags = static_cast<const int32_t*>(host);
+        for (int32_t i = 0; i < worldCount; ++i)
+            if (flags[i] & B2G_WORLD_CONTINUOUS) { b->anyContinuous = true; break; }
+        if (b->anyContinuous && b->graphExec) {  // the captured step has no k_toi: capture again
+            cudaGraphExecDestroy(b->graphExec);
+            b->graphExec = nullptr;
+        }
+    }
     // any host edit may change what the islands depend on: rebuild them on the next step
     if (rc == B2GPU_OK) cudaMemsetAsync(b->A.topoDirty, 1, (size_t)b->A.numTiles * kTile * sizeof(int), b->stream);
     return rc;

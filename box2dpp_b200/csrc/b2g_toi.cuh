@@ -1,0 +1,889 @@
+// b2g_toi.cuh — continuous collision of the Step path for sm_100a: b2World::SolveTOI and everything under it.
+//
+// Reference (fork paths under /root/reference/Box2D, vanilla twin under Regression/box2d-ref/Box2DRef; the two
+// are bit-identical on this path):
+//   b2World::SolveTOI                       Dynamics/b2World.cpp:568-886
+//   b2Island::SolveTOI                      Dynamics/b2Island.cpp:385-515
+//   b2ContactSolver::SolveTOIPositionConstraints  Dynamics/Contacts/b2ContactSolver.cpp:747-836
+//   b2TimeOfImpact, b2SeparationFunction    Collision/b2TimeOfImpact.cpp:39-497
+//   b2Distance, b2Simplex, b2DistanceProxy  Collision/b2Distance.cpp:28-604, b2Distance.h:103-141
+//   b2Sweep::GetTransform/Advance/Normalize Common/b2Math.h:657-683, b2Body::Advance Dynamics/b2Body.h:841-849
+//
+// Shape of the kernel (k_toi, CTA = one tile of 32 worlds, lane = world):
+//   phase 1  all warps, contacts strided over warps: the first pass of SolveTOI's outer loop.  Every sweep starts
+//            at alpha0 = 0, so the times of impact of the candidate contacts (awake, at least one bullet or
+//            non-dynamic body) are independent: b2TimeOfImpact per (world, contact) in parallel, the minimum
+//            per world through a shared-memory atomicMin.
+//   phase 2  warp 0, only lanes whose minimum is a real event (alpha < 1 - 10 eps): the reference's loop verbatim,
+//            one world per lane — advance the two bodies, update the contact, build the mini-island in the
+//            body's contact-list order, b2Island::SolveTOI, synchronise the displaced fixtures, FindNewContacts,
+//            recompute the invalidated times of impact in list order (their sweeps now start at different
+//            alpha0, which makes that part order dependent), repeat.
+// Resting scenes take phase 1 only (a handful of GJK calls per world); events are rare and short.
+#pragma once
+
+#include "b2g_kernels.cuh"
+
+namespace b2g {
+
+constexpr float kToiBaumgarte = 0.75f;
+constexpr int kMaxSubSteps = 8;
+constexpr int kMaxToiContacts = 32;
+constexpr int kToiBodyCap = 2 * kMaxToiContacts;
+constexpr int kToiWarps = 8;
+
+// ---- b2DistanceProxy (b2Distance.cpp:33-88) ------------------------------------------------------
+struct DistanceProxy {
+    const float* w;  // polygons: address of vertex 0 in the shape table of this lane (vertex i at w[2i*32], w[(2i+1)*32])
+    Vec2 v0, v1;     // circles, edges, chain children: the one or two vertices themselves
+    int count;
+    float radius;
+    bool table;
+    __device__ __forceinline__ Vec2 vertex(int i) const {
+        if (table) return V2(w[(size_t)(2 * i) * kTile], w[(size_t)(2 * i + 1) * kTile]);
+        return i == 0 ? v0 : v1;
+    }
+    // b2DistanceProxy::GetSupport (b2Distance.h:109-124)
+    __device__ __forceinline__ int support(Vec2 d) const {
+        int bestIndex = 0;
+        float bestValue = Dot(vertex(0), d);
+        for (int i = 1; i < count; ++i) {
+            float value = Dot(vertex(i), d);
+            if (value > bestValue) {
+                bestIndex = i;
+                bestValue = value;
+            }
+        }
+        return bestIndex;
+    }
+};
+
+__device__ __forceinline__ DistanceProxy MakeDistanceProxy(const Arena& A, int tile, int lane, int shapeOff, int shapeType, int child) {
+    const float* w = A.shapeWords + ((size_t)tile * A.NS + shapeOff) * kTile + lane;
+    DistanceProxy p;
+    p.w = w;
+    p.v0 = p.v1 = V2(0.0f, 0.0f);
+    p.table = false;
+    if (shapeType == B2G_SHAPE_POLYGON) {
+        p.count = __float_as_int(w[0]);
+        p.radius = w[1 * kTile];
+        p.w = w + 4 * kTile;
+        p.table = true;
+    } else if (shapeType == B2G_SHAPE_CIRCLE) {
+        p.count = 1;
+        p.radius = w[0];
+        p.v0 = V2(w[1 * kTile], w[2 * kTile]);
+    } else if (shapeType == B2G_SHAPE_EDGE) {
+        p.count = 2;
+        p.radius = w[0];
+        p.v0 = V2(w[3 * kTile], w[4 * kTile]);
+        p.v1 = V2(w[5 * kTile], w[6 * kTile]);
+    } else {  // chain child: vertices index and index + 1 (wrapping to 0)
+        Col<float2> verts = col(A.chainVerts, tile, A.NV, lane);
+        const int first = __float_as_int(w[1 * kTile]);
+        const int n = __float_as_int(w[2 * kTile]);
+        p.count = 2;
+        p.radius = w[0];
+        float2 a = verts[first + child];
+        float2 b = child + 1 < n ? verts[first + child + 1] : verts[first];
+        p.v0 = V2(a.x, a.y);
+        p.v1 = V2(b.x, b.y);
+    }
+    return p;
+}
+
+// ---- b2Sweep (b2Math.h:380-396, 657-683) --------------------------------------------------------
+struct Sweep {
+    Vec2 localCenter, c0, c;
+    float a0, a, alpha0;
+};
+__device__ __forceinline__ Xf SweepTransform(const Sweep& s, float beta) {
+    Xf xf;
+    xf.p = (1.0f - beta) * s.c0 + beta * s.c;
+    float angle = (1.0f - beta) * s.a0 + beta * s.a;
+    xf.q = MakeRot(angle);
+    xf.p = xf.p - Mul(xf.q, s.localCenter);
+    return xf;
+}
+__device__ __forceinline__ void SweepAdvance(Sweep& s, float alpha) {
+    float beta = Div(alpha - s.alpha0, 1.0f - s.alpha0);
+    s.c0 = s.c0 + beta * (s.c - s.c0);
+    s.a0 += beta * (s.a - s.a0);
+    s.alpha0 = alpha;
+}
+__device__ __forceinline__ void SweepNormalize(Sweep& s) {
+    float twoPi = 2.0f * kPi;
+    float d = twoPi * floorf(Div(s.a0, twoPi));
+    s.a0 -= d;
+    s.a -= d;
+}
+
+// ---- b2Distance (GJK) ----------------------------------------------------------------------------
+struct SimplexCache {
+    float metric;
+    int count;
+    int indexA[3], indexB[3];
+};
+struct SimplexVertex {
+    Vec2 wA, wB, w;
+    float a;
+    int indexA, indexB;
+};
+struct Simplex {
+    SimplexVertex v[3];
+    int count;
+
+    __device__ float metric() const {
+        if (count == 2) return Length(v[0].w - v[1].w);
+        if (count == 3) return Cross(v[1].w - v[0].w, v[2].w - v[0].w);
+        return 0.0f;
+    }
+    __device__ void readCache(const SimplexCache* cache, const DistanceProxy& proxyA, Xf xfA, const DistanceProxy& proxyB, Xf xfB) {
+        count = cache->count;
+        for (int i = 0; i < count; ++i) {
+            SimplexVertex* sv = v + i;
+            sv->indexA = cache->indexA[i];
+            sv->indexB = cache->indexB[i];
+            sv->wA = Mul(xfA, proxyA.vertex(sv->indexA));
+            sv->wB = Mul(xfB, proxyB.vertex(sv->indexB));
+            sv->w = sv->wB - sv->wA;
+            sv->a = 0.0f;
+        }
+        if (count > 1) {
+            float metric1 = cache->metric;
+            float metric2 = metric();
+            if (metric2 < 0.5f * metric1 || 2.0f * metric1 < metric2 || metric2 < kEpsilon) count = 0;
+        }
+        if (count == 0) {
+            SimplexVertex* sv = v;
+            sv->indexA = 0;
+            sv->indexB = 0;
+            sv->wA = Mul(xfA, proxyA.vertex(0));
+            sv->wB = Mul(xfB, proxyB.vertex(0));
+            sv->w = sv->wB - sv->wA;
+            sv->a = 1.0f;
+            count = 1;
+        }
+    }
+    __device__ void writeCache(SimplexCache* cache) const {
+        cache->metric = metric();
+        cache->count = count;
+        for (int i = 0; i < count; ++i) {
+            cache->indexA[i] = v[i].indexA;
+            cache->indexB[i] = v[i].indexB;
+        }
+    }
+    __device__ Vec2 searchDirection() const {
+        if (count == 1) return -v[0].w;
+        Vec2 e12 = v[1].w - v[0].w;
+        float sgn = Cross(e12, -v[0].w);
+        if (sgn > 0.0f) return Cross(1.0f, e12);  // origin is left of e12
+        return Cross(e12, 1.0f);
+    }
+    __device__ void witnessPoints(Vec2* pA, Vec2* pB) const {
+        if (count == 1) {
+            *pA = v[0].wA;
+            *pB = v[0].wB;
+        } else if (count == 2) {
+            *pA = v[0].a * v[0].wA + v[1].a * v[1].wA;
+            *pB = v[0].a * v[0].wB + v[1].a * v[1].wB;
+        } else {
+            *pA = v[0].a * v[0].wA + v[1].a * v[1].wA + v[2].a * v[2].wA;
+            *pB = *pA;
+        }
+    }
+    // b2Simplex::Solve2 (b2Distance.cpp:250-281)
+    __device__ void solve2() {
+        Vec2 w1 = v[0].w, w2 = v[1].w;
+        Vec2 e12 = w2 - w1;
+        float d12_2 = -Dot(w1, e12);
+        if (d12_2 <= 0.0f) {
+            v[0].a = 1.0f;
+            count = 1;
+            return;
+        }
+        float d12_1 = Dot(w2, e12);
+        if (d12_1 <= 0.0f) {
+            v[1].a = 1.0f;
+            count = 1;
+            v[0] = v[1];
+            return;
+        }
+        float inv_d12 = Div(1.0f, d12_1 + d12_2);
+        v[0].a = d12_1 * inv_d12;
+        v[1].a = d12_2 * inv_d12;
+        count = 2;
+    }
+    // b2Simplex::Solve3 (b2Distance.cpp:288-398)
+    __device__ void solve3() {
+        Vec2 w1 = v[0].w, w2 = v[1].w, w3 = v[2].w;
+        Vec2 e12 = w2 - w1;
+        float w1e12 = Dot(w1, e12), w2e12 = Dot(w2, e12);
+        float d12_1 = w2e12, d12_2 = -w1e12;
+        Vec2 e13 = w3 - w1;
+        float w1e13 = Dot(w1, e13), w3e13 = Dot(w3, e13);
+        float d13_1 = w3e13, d13_2 = -w1e13;
+        Vec2 e23 = w3 - w2;
+        float w2e23 = Dot(w2, e23), w3e23 = Dot(w3, e23);
+        float d23_1 = w3e23, d23_2 = -w2e23;
+        float n123 = Cross(e12, e13);
+        float d123_1 = n123 * Cross(w2, w3);
+        float d123_2 = n123 * Cross(w3, w1);
+        float d123_3 = n123 * Cross(w1, w2);
+        if (d12_2 <= 0.0f && d13_2 <= 0.0f) {
+            v[0].a = 1.0f;
+            count = 1;
+            return;
+        }
+        if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) {
+            float inv_d12 = Div(1.0f, d12_1 + d12_2);
+            v[0].a = d12_1 * inv_d12;
+            v[1].a = d12_2 * inv_d12;
+            count = 2;
+            return;
+        }
+        if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) {
+            float inv_d13 = Div(1.0f, d13_1 + d13_2);
+            v[0].a = d13_1 * inv_d13;
+            v[2].a = d13_2 * inv_d13;
+            count = 2;
+            v[1] = v[2];
+            return;
+        }
+        if (d12_1 <= 0.0f && d23_2 <= 0.0f) {
+            v[1].a = 1.0f;
+            count = 1;
+            v[0] = v[1];
+            return;
+        }
+        if (d13_1 <= 0.0f && d23_1 <= 0.0f) {
+            v[2].a = 1.0f;
+            count = 1;
+            v[0] = v[2];
+            return;
+        }
+        if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) {
+            float inv_d23 = Div(1.0f, d23_1 + d23_2);
+            v[1].a = d23_1 * inv_d23;
+            v[2].a = d23_2 * inv_d23;
+            count = 2;
+            v[0] = v[2];
+            return;
+        }
+        float inv_d123 = Div(1.0f, d123_1 + d123_2 + d123_3);
+        v[0].a = d123_1 * inv_d123;
+        v[1].a = d123_2 * inv_d123;
+        v[2].a = d123_3 * inv_d123;
+        count = 3;
+    }
+};
+
+// b2Distance with useRadii = false (b2Distance.cpp:446-572); returns the distance, updates the cache.
+__device__ __noinline__ float GjkDistance(SimplexCache* cache, const DistanceProxy* pA, Xf xfA, const DistanceProxy* pB, Xf xfB) {
+    const DistanceProxy& proxyA = *pA;
+    const DistanceProxy& proxyB = *pB;
+    Simplex simplex;
+    simplex.readCache(cache, proxyA, xfA, proxyB, xfB);
+    const int k_maxIters = 20;
+    int saveA[3], saveB[3];
+    int saveCount = 0;
+    int iter = 0;
+    while (iter < k_maxIters) {
+        saveCount = simplex.count;
+        for (int i = 0; i < saveCount; ++i) {
+            saveA[i] = simplex.v[i].indexA;
+            saveB[i] = simplex.v[i].indexB;
+        }
+        if (simplex.count == 2) simplex.solve2();
+        else if (simplex.count == 3) simplex.solve3();
+        if (simplex.count == 3) break;
+        Vec2 d = simplex.searchDirection();
+        if (LengthSquared(d) < kEpsilon * kEpsilon) break;
+        SimplexVertex* vertex = simplex.v + simplex.count;
+        vertex->indexA = proxyA.support(MulT(xfA.q, -d));
+        vertex->wA = Mul(xfA, proxyA.vertex(vertex->indexA));
+        vertex->indexB = proxyB.support(MulT(xfB.q, d));
+        vertex->wB = Mul(xfB, proxyB.vertex(vertex->indexB));
+        vertex->w = vertex->wB - vertex->wA;
+        ++iter;
+        bool duplicate = false;
+        for (int i = 0; i < saveCount; ++i) {
+            if (vertex->indexA == saveA[i] && vertex->indexB == saveB[i]) {
+                duplicate = true;
+                break;
+            }
+        }
+        if (duplicate) break;
+        ++simplex.count;
+    }
+    Vec2 pointA, pointB;
+    simplex.witnessPoints(&pointA, &pointB);
+    float distance = Length(pointA - pointB);
+    simplex.writeCache(cache);
+    return distance;
+}
+
+// ---- b2SeparationFunction (b2TimeOfImpact.cpp:39-260) ------------------------------------------------
+enum { kSepPoints = 0, kSepFaceA = 1, kSepFaceB = 2 };
+struct SeparationFunction {
+    const DistanceProxy* proxyA;
+    const DistanceProxy* proxyB;
+    Sweep sweepA, sweepB;
+    int type;
+    Vec2 localPoint, axis;
+
+    __device__ void initialize(const SimplexCache* cache, const DistanceProxy* pA, const Sweep& sA, const DistanceProxy* pB,
+                               const Sweep& sB, float t1) {
+        proxyA = pA;
+        proxyB = pB;
+        const int count = cache->count;
+        sweepA = sA;
+        sweepB = sB;
+        localPoint = V2(0.0f, 0.0f);
+        Xf xfA = SweepTransform(sweepA, t1), xfB = SweepTransform(sweepB, t1);
+        if (count == 1) {
+            type = kSepPoints;
+            Vec2 pointA = Mul(xfA, proxyA->vertex(cache->indexA[0]));
+            Vec2 pointB = Mul(xfB, proxyB->vertex(cache->indexB[0]));
+            axis = pointB - pointA;
+            Normalize(axis);
+        } else if (cache->indexA[0] == cache->indexA[1]) {
+            type = kSepFaceB;  // two points on B and one on A
+            Vec2 localPointB1 = proxyB->vertex(cache->indexB[0]);
+            Vec2 localPointB2 = proxyB->vertex(cache->indexB[1]);
+            axis = Cross(localPointB2 - localPointB1, 1.0f);
+            Normalize(axis);
+            Vec2 normal = Mul(xfB.q, axis);
+            localPoint = 0.5f * (localPointB1 + localPointB2);
+            Vec2 pointB = Mul(xfB, localPoint);
+            Vec2 pointA = Mul(xfA, proxyA->vertex(cache->indexA[0]));
+            float s = Dot(pointA - pointB, normal);
+            if (s < 0.0f) axis = -axis;
+        } else {
+            type = kSepFaceA;  // two points on A and one or two points on B
+            Vec2 localPointA1 = proxyA->vertex(cache->indexA[0]);
+            Vec2 localPointA2 = proxyA->vertex(cache->indexA[1]);
+            axis = Cross(localPointA2 - localPointA1, 1.0f);
+            Normalize(axis);
+            Vec2 normal = Mul(xfA.q, axis);
+            localPoint = 0.5f * (localPointA1 + localPointA2);
+            Vec2 pointA = Mul(xfA, localPoint);
+            Vec2 pointB = Mul(xfB, proxyB->vertex(cache->indexB[0]));
+            float s = Dot(pointB - pointA, normal);
+            if (s < 0.0f) axis = -axis;
+        }
+    }
+    __device__ float findMinSeparation(int* indexA, int* indexB, float t) const {
+        Xf xfA = SweepTransform(sweepA, t), xfB = SweepTransform(sweepB, t);
+        if (type == kSepPoints) {
+            Vec2 axisA = MulT(xfA.q, axis);
+            Vec2 axisB = MulT(xfB.q, -axis);
+            *indexA = proxyA->support(axisA);
+            *indexB = proxyB->support(axisB);
+            Vec2 pointA = Mul(xfA, proxyA->vertex(*indexA));
+            Vec2 pointB = Mul(xfB, proxyB->vertex(*indexB));
+            return Dot(pointB - pointA, axis);
+        }
+        if (type == kSepFaceA) {
+            Vec2 normal = Mul(xfA.q, axis);
+            Vec2 pointA = Mul(xfA, localPoint);
+            Vec2 axisB = MulT(xfB.q, -normal);
+            *indexA = -1;
+            *indexB = proxyB->support(axisB);
+            Vec2 pointB = Mul(xfB, proxyB->vertex(*indexB));
+            return Dot(pointB - pointA, normal);
+        }
+        Vec2 normal = Mul(xfB.q, axis);
+        Vec2 pointB = Mul(xfB, localPoint);
+        Vec2 axisA = MulT(xfA.q, -normal);
+        *indexB = -1;
+        *indexA = proxyA->support(axisA);
+        Vec2 pointA = Mul(xfA, proxyA->vertex(*indexA));
+        return Dot(pointA - pointB, normal);
+    }
+    __device__ float evaluate(int indexA, int indexB, float t) const {
+        Xf xfA = SweepTransform(sweepA, t), xfB = SweepTransform(sweepB, t);
+        if (type == kSepPoints) {
+            Vec2 pointA = Mul(xfA, proxyA->vertex(indexA));
+            Vec2 pointB = Mul(xfB, proxyB->vertex(indexB));
+            return Dot(pointB - pointA, axis);
+        }
+        if (type == kSepFaceA) {
+            Vec2 normal = Mul(xfA.q, axis);
+            Vec2 pointA = Mul(xfA, localPoint);
+            Vec2 pointB = Mul(xfB, proxyB->vertex(indexB));
+            return Dot(pointB - pointA, normal);
+        }
+        Vec2 normal = Mul(xfB.q, axis);
+        Vec2 pointB = Mul(xfB, localPoint);
+        Vec2 pointA = Mul(xfA, proxyA->vertex(indexA));
+        return Dot(pointA - pointB, normal);
+    }
+};
+
+enum { kToiUnknown = 0, kToiFailed = 1, kToiOverlapped = 2, kToiTouching = 3, kToiSeparated = 4 };
+
+// b2TimeOfImpact (b2TimeOfImpact.cpp:264-497).  Returns the state, *tOut = output.t.
+__device__ __noinline__ int TimeOfImpact(const DistanceProxy* proxyA, const DistanceProxy* proxyB, const Sweep* sweepAIn,
+                                         const Sweep* sweepBIn, float tMax, float* tOut) {
+    int state = kToiUnknown;
+    float tResult = tMax;
+    Sweep sweepA = *sweepAIn, sweepB = *sweepBIn;
+    SweepNormalize(sweepA);
+    SweepNormalize(sweepB);
+    const float totalRadius = proxyA->radius + proxyB->radius;
+    const float target = Max(kLinearSlop, totalRadius - 3.0f * kLinearSlop);
+    const float tolerance = 0.25f * kLinearSlop;
+    float t1 = 0.0f;
+    const int k_maxIterations = 20;
+    int iter = 0;
+    SimplexCache cache;
+    cache.count = 0;
+    cache.metric = 0.0f;
+    for (;;) {
+        Xf xfA = SweepTransform(sweepA, t1), xfB = SweepTransform(sweepB, t1);
+        float distance = GjkDistance(&cache, proxyA, xfA, proxyB, xfB);
+        if (distance <= 0.0f) {  // overlapped: give up on continuous collision
+            state = kToiOverlapped;
+            tResult = 0.0f;
+            break;
+        }
+        if (distance < target + tolerance) {
+            state = kToiTouching;
+            tResult = t1;
+            break;
+        }
+        SeparationFunction fcn;
+        fcn.initialize(&cache, proxyA, sweepA, proxyB, sweepB, t1);
+        bool done = false;
+        float t2 = tMax;
+        int pushBackIter = 0;
+        for (;;) {
+            int indexA, indexB;
+            float s2 = fcn.findMinSeparation(&indexA, &indexB, t2);
+            if (s2 > target + tolerance) {
+                state = kToiSeparated;
+                tResult = tMax;
+                done = true;
+                break;
+            }
+            if (s2 > target - tolerance) {
+                t1 = t2;
+                break;
+            }
+            float s1 = fcn.evaluate(indexA, indexB, t1);
+            if (s1 < target - tolerance) {
+                state = kToiFailed;
+                tResult = t1;
+                done = true;
+                break;
+            }
+            if (s1 <= target + tolerance) {
+                state = kToiTouching;
+                tResult = t1;
+                done = true;
+                break;
+            }
+            int rootIterCount = 0;
+            float a1 = t1, a2 = t2;
+            for (;;) {
+                float t;
+                if (rootIterCount & 1) t = a1 + Div((target - s1) * (a2 - a1), s2 - s1);  // secant
+                else t = 0.5f * (a1 + a2);                                                 // bisection
+                ++rootIterCount;
+                float s = fcn.evaluate(indexA, indexB, t);
+                if (Abs(s - target) < tolerance) {
+                    t2 = t;
+                    break;
+                }
+                if (s > target) {
+                    a1 = t;
+                    s1 = s;
+                } else {
+                    a2 = t;
+                    s2 = s;
+                }
+                if (rootIterCount == 50) break;
+            }
+            ++pushBackIter;
+            if (pushBackIter == kMaxPolygonVertices) break;
+        }
+        ++iter;
+        if (done) break;
+        if (iter == k_maxIterations) {
+            state = kToiFailed;
+            tResult = t1;
+            break;
+        }
+    }
+    *tOut = tResult;
+    return state;
+}
+
+// ---- body helpers ----------------------------------------------------------------------------------
+struct ToiCols {
+    Col<int4> cA;
+    Col<int2> cS;
+    Col<float> cToi;
+    Col<int> bodyFlags, proxyInfo;
+    Col<float4> bodyXf, bodySweep, bodySweep0, bodyVel, bodyMass;
+};
+__device__ __forceinline__ ToiCols MakeToiCols(const Arena& A, int tile, int lane) {
+    ToiCols c{col(A.contactA, tile, A.NC, lane), col(A.contactS, tile, A.NC, lane), col(A.contactToi, tile, A.NC, lane),
+              col(A.bodyFlags, tile, A.NB, lane), col(A.proxyInfo, tile, A.NP, lane),
+              col(A.bodyXf, tile, A.NB, lane), col(A.bodySweep, tile, A.NB, lane), col(A.bodySweep0, tile, A.NB, lane),
+              col(A.bodyVel, tile, A.NB, lane), col(A.bodyMass, tile, A.NB, lane)};
+    return c;
+}
+__device__ __forceinline__ Sweep LoadSweep(const ToiCols& c, int b) {
+    const float4 s0 = c.bodySweep0[b], s1 = c.bodySweep[b], ms = c.bodyMass[b];
+    Sweep s;
+    s.localCenter = V2(ms.z, ms.w);
+    s.c0 = V2(s0.x, s0.y);
+    s.a0 = s0.z;
+    s.alpha0 = s0.w;
+    s.c = V2(s1.x, s1.y);
+    s.a = s1.z;
+    return s;
+}
+// b2Body::SynchronizeTransform (b2Body.h:835-839)
+__device__ __forceinline__ void SynchronizeTransform(const ToiCols& c, int b) {
+    const float4 sw = c.bodySweep[b], ms = c.bodyMass[b];
+    Rot q = MakeRot(sw.z);
+    Vec2 p = V2(sw.x, sw.y) - Mul(q, V2(ms.z, ms.w));
+    c.bodyXf[b] = make_float4(p.x, p.y, q.s, q.c);
+}
+// b2Body::Advance (b2Body.h:841-849)
+__device__ __forceinline__ void BodyAdvance(const ToiCols& c, int b, float alpha) {
+    Sweep s = LoadSweep(c, b);
+    SweepAdvance(s, alpha);
+    s.c = s.c0;
+    s.a = s.a0;
+    c.bodySweep0[b] = make_float4(s.c0.x, s.c0.y, s.a0, s.alpha0);
+    float4 sw = c.bodySweep[b];
+    sw.x = s.c.x; sw.y = s.c.y; sw.z = s.a;
+    c.bodySweep[b] = sw;
+    Rot q = MakeRot(s.a);
+    Vec2 p = s.c - Mul(q, s.localCenter);
+    c.bodyXf[b] = make_float4(p.x, p.y, q.s, q.c);
+}
+
+// Is contact (flags, bodies) a TOI candidate, per b2World::SolveTOI's filter (b2World.cpp:634-659)?
+__device__ __forceinline__ bool ToiCandidate(int bfA, int bfB) {
+    const int typeA = bfA & kBodyTypeMask, typeB = bfB & kBodyTypeMask;
+    const bool activeA = (bfA & kBodyAwake) && typeA != B2G_STATIC_BODY;
+    const bool activeB = (bfB & kBodyAwake) && typeB != B2G_STATIC_BODY;
+    if (!activeA && !activeB) return false;
+    const bool collideA = (bfA & kBodyBullet) || typeA != B2G_DYNAMIC_BODY;
+    const bool collideB = (bfB & kBodyBullet) || typeB != B2G_DYNAMIC_BODY;
+    return collideA || collideB;
+}
+
+// Time of impact of contact k given both sweeps (already on the same alpha0): b2World.cpp:680-709
+__device__ __forceinline__ float ContactToi(const Arena& A, int tile, int lane, const ToiCols& c, int k, const int4 a,
+                                            const Sweep& sA, const Sweep& sB, float alpha0) {
+    const int2 so = c.cS[k];
+    const int shapeTypes = (a.w >> 16) & 0xf;
+    const int childA = (c.proxyInfo[a.x & 0xffff] >> 16) & 0xffff, childB = (c.proxyInfo[(a.x >> 16) & 0xffff] >> 16) & 0xffff;
+    const DistanceProxy pA = MakeDistanceProxy(A, tile, lane, so.x, shapeTypes & 3, childA);
+    const DistanceProxy pB = MakeDistanceProxy(A, tile, lane, so.y, (shapeTypes >> 2) & 3, childB);
+    float beta;
+    const int state = TimeOfImpact(&pA, &pB, &sA, &sB, 1.0f, &beta);
+    return state == kToiTouching ? Min(alpha0 + (1.0f - alpha0) * beta, 1.0f) : 1.0f;
+}
+
+// b2Contact::Update with its side effects, as called inside SolveTOI (b2Contact.cpp:170-256)
+__device__ __forceinline__ void ToiUpdateContact(const Arena& A, int tile, int lane, const ToiCols& c, const EventSink& ev, int k) {
+    const int4 a = c.cA[k];
+    const int res = UpdateOne(A, tile, lane, k, a);
+    const bool wasTouching = (res & kResWasTouching) != 0, touching = (res & kResTouching) != 0;
+    const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+    if (touching != wasTouching) {
+        WakeBody(c.bodyFlags, c.bodySweep, bodyA);
+        WakeBody(c.bodyFlags, c.bodySweep, bodyB);
+    }
+    if (A.eventMask) {
+        const int pointCount = (res >> kResCountShift) & 3;
+        const int pa = c.proxyInfo[a.x & 0xffff], pb = c.proxyInfo[(a.x >> 16) & 0xffff];
+        const int fA = pa & 0xffff, chA = (pa >> 16) & 0xffff, fB = pb & 0xffff, chB = (pb >> 16) & 0xffff;
+        if (!wasTouching && touching) ev.push(kEventBegin, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
+        if (wasTouching && !touching) ev.push(kEventEnd, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
+        if (touching) ev.push(kEventPreSolve, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
+    }
+}
+
+// The reference's SolveTOI loop for one world, entered after phase 1 has cached every first-pass time of impact.
+__device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, float dt, int velIters) {
+    const Arena& A = *Ap;
+    const size_t ws = (size_t)tile * kTile + lane;
+    const ToiCols c = MakeToiCols(A, tile, lane);
+    Col<int> toiBodies = col(A.toiBodies, tile, kToiBodyCap, lane);
+    Col<int> toiContacts = col(A.toiContacts, tile, kMaxToiContacts, lane);
+    Col<float4> vc = col(A.toiVc, tile, kMaxToiContacts * kVcStride, lane);
+    Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+    EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws],
+                 A.NE, A.eventMask};
+
+    for (;;) {
+        // ---- find the first TOI (b2World.cpp:598-722): world contact list order = descending array index ----
+        const int n = A.contactCount[ws];
+        int minContact = -1;
+        float minAlpha = 1.0f;
+        for (int k = n - 1; k >= 0; --k) {
+            int4 a = c.cA[k];
+            if ((a.z & kContactEnabled) == 0) continue;
+            if (((a.z & kContactToiCountMask) >> kContactToiCountShift) > kMaxSubSteps) continue;
+            float alpha = 1.0f;
+            if (a.z & kContactToi) {
+                alpha = c.cToi[k];
+            } else {
+                const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+                if (!ToiCandidate(c.bodyFlags[bodyA], c.bodyFlags[bodyB])) continue;
+                // put the sweeps onto the same time interval
+                Sweep sA = LoadSweep(c, bodyA), sB = LoadSweep(c, bodyB);
+                float alpha0 = sA.alpha0;
+                if (sA.alpha0 < sB.alpha0) {
+                    alpha0 = sB.alpha0;
+                    SweepAdvance(sA, alpha0);
+                    c.bodySweep0[bodyA] = make_float4(sA.c0.x, sA.c0.y, sA.a0, sA.alpha0);
+                } else if (sB.alpha0 < sA.alpha0) {
+                    alpha0 = sA.alpha0;
+                    SweepAdvance(sB, alpha0);
+                    c.bodySweep0[bodyB] = make_float4(sB.c0.x, sB.c0.y, sB.a0, sB.alpha0);
+                }
+                alpha = ContactToi(A, tile, lane, c, k, a, sA, sB, alpha0);
+                c.cToi[k] = alpha;
+                a.z |= kContactToi;
+                c.cA[k] = a;
+            }
+            if (alpha < minAlpha) {
+                minContact = k;
+                minAlpha = alpha;
+            }
+        }
+        if (minContact < 0 || 1.0f - 10.0f * kEpsilon < minAlpha) break;  // no more TOI events
+
+        A.topoDirty[ws] = 1;  // bodies move / wake, touching flags and the contact set may change
+        // ---- advance the bodies to the TOI (b2World.cpp:730-760) ----
+        int4 mc = c.cA[minContact];
+        const int bA = mc.y & 0xffff, bB = (mc.y >> 16) & 0xffff;
+        const float4 backupSwA = c.bodySweep[bA], backupSw0A = c.bodySweep0[bA];
+        const float4 backupSwB = c.bodySweep[bB], backupSw0B = c.bodySweep0[bB];
+        BodyAdvance(c, bA, minAlpha);
+        BodyAdvance(c, bB, minAlpha);
+        ToiUpdateContact(A, tile, lane, c, ev, minContact);
+        mc = c.cA[minContact];
+        mc.z &= ~kContactToi;
+        mc.z += 1 << kContactToiCountShift;
+        if ((mc.z & kContactEnabled) == 0 || (mc.z & kContactTouching) == 0) {  // not solid: restore the sweeps
+            mc.z &= ~kContactEnabled;
+            c.cA[minContact] = mc;
+            float4 sw = backupSwA;
+            sw.w = c.bodySweep[bA].w;  // m_sleepTime is not part of b2Sweep
+            c.bodySweep[bA] = sw;
+            c.bodySweep0[bA] = backupSw0A;
+            sw = backupSwB;
+            sw.w = c.bodySweep[bB].w;
+            c.bodySweep[bB] = sw;
+            c.bodySweep0[bB] = backupSw0B;
+            SynchronizeTransform(c, bA);
+            SynchronizeTransform(c, bB);
+            continue;
+        }
+        WakeBody(c.bodyFlags, c.bodySweep, bA);
+        WakeBody(c.bodyFlags, c.bodySweep, bB);
+
+        // ---- build the island (b2World.cpp:765-857) ----
+        int nB = 0, nC = 0;
+        toiBodies[nB++] = bA;
+        toiBodies[nB++] = bB;
+        toiContacts[nC++] = minContact;
+        c.bodyFlags[bA] |= kBodyToiIsland;
+        c.bodyFlags[bB] |= kBodyToiIsland;
+        mc.z |= kContactToiIsland;
+        c.cA[minContact] = mc;
+        for (int i = 0; i < 2; ++i) {
+            const int body = i == 0 ? bA : bB;
+            if ((c.bodyFlags[body] & kBodyTypeMask) != B2G_DYNAMIC_BODY) continue;
+            // the body's contact edge list is head-inserted: newest contact (highest array index) first
+            for (int k = n - 1; k >= 0; --k) {
+                int4 a = c.cA[k];
+                const int kA = a.y & 0xffff, kB = (a.y >> 16) & 0xffff;
+                if (kA != body && kB != body) continue;
+                if (nB == kToiBodyCap) break;
+                if (nC == kMaxToiContacts) break;
+                if (a.z & kContactToiIsland) continue;
+                const int other = kA == body ? kB : kA;
+                const int of = c.bodyFlags[other];
+                // only static, kinematic or bullet bodies
+                if ((of & kBodyTypeMask) == B2G_DYNAMIC_BODY && (c.bodyFlags[body] & kBodyBullet) == 0 && (of & kBodyBullet) == 0)
+                    continue;
+                // tentatively advance the body to the TOI
+                const float4 backupSw = c.bodySweep[other], backupSw0 = c.bodySweep0[other];
+                if ((of & kBodyToiIsland) == 0) BodyAdvance(c, other, minAlpha);
+                ToiUpdateContact(A, tile, lane, c, ev, k);
+                a = c.cA[k];
+                if ((a.z & kContactEnabled) == 0 || (a.z & kContactTouching) == 0) {
+                    float4 sw = backupSw;
+                    sw.w = c.bodySweep[other].w;  // m_sleepTime is not part of b2Sweep
+                    c.bodySweep[other] = sw;
+                    c.bodySweep0[other] = backupSw0;
+                    SynchronizeTransform(c, other);
+                    continue;
+                }
+                a.z |= kContactToiIsland;
+                c.cA[k] = a;
+                toiContacts[nC++] = k;
+                const int of2 = c.bodyFlags[other];
+                if (of2 & kBodyToiIsland) continue;
+                c.bodyFlags[other] = of2 | kBodyToiIsland;
+                if ((of2 & kBodyTypeMask) != B2G_STATIC_BODY) WakeBody(c.bodyFlags, c.bodySweep, other);
+                toiBodies[nB++] = other;
+            }
+        }
+
+        // ---- b2Island::SolveTOI (b2Island.cpp:385-515): positions / velocities live in the body arrays ----
+        const float h = (1.0f - minAlpha) * dt;
+        for (int i = 0; i < nC; ++i) InitVelocityConstraint(A, tile, lane, vc, i, toiContacts[i], false, 1.0f);  // solver ctor
+        for (int it = 0; it < 20; ++it) {
+            float minSeparation = 0.0f;
+            for (int i = 0; i < nC; ++i)
+                SolvePositionConstraint(A, tile, lane, vc, i, toiContacts[i], kToiBaumgarte, true, bA, bB, &minSeparation);
+            if (minSeparation >= -1.5f * kLinearSlop) break;
+        }
+        {  // leap of faith to the new safe state
+            float4 s = c.bodySweep[bA], s0 = c.bodySweep0[bA];
+            c.bodySweep0[bA] = make_float4(s.x, s.y, s.z, s0.w);
+            s = c.bodySweep[bB]; s0 = c.bodySweep0[bB];
+            c.bodySweep0[bB] = make_float4(s.x, s.y, s.z, s0.w);
+        }
+        for (int i = 0; i < nC; ++i) InitVelocityConstraint(A, tile, lane, vc, i, toiContacts[i], false, 1.0f);
+        for (int it = 0; it < velIters; ++it)
+            for (int i = 0; i < nC; ++i) SolveVelocityConstraint(vc, c.bodyVel, i);
+        for (int i = 0; i < nB; ++i) {  // integrate positions, sync bodies
+            const int b = toiBodies[i];
+            float4 sw = c.bodySweep[b];
+            const float4 vel = c.bodyVel[b];
+            Vec2 cc = V2(sw.x, sw.y);
+            float a = sw.z;
+            Vec2 v = V2(vel.x, vel.y);
+            float wv = vel.z;
+            Vec2 translation = h * v;
+            if (Dot(translation, translation) > kMaxTranslationSquared) {
+                float ratio = Div(kMaxTranslation, Length(translation));
+                v = ratio * v;
+            }
+            float rotation = h * wv;
+            if (rotation * rotation > kMaxRotationSquared) {
+                float ratio = Div(kMaxRotation, Abs(rotation));
+                wv *= ratio;
+            }
+            cc = cc + h * v;
+            a += h * wv;
+            c.bodySweep[b] = make_float4(cc.x, cc.y, a, sw.w);
+            c.bodyVel[b] = make_float4(v.x, v.y, wv, 0.0f);
+            SynchronizeTransform(c, b);
+        }
+        if (A.eventMask >> kEventPostSolve & 1) {  // b2Island::Report
+            for (int i = 0; i < nC; ++i) {
+                const size_t o = (size_t)i * kVcStride;
+                const float4 imp = vc[o + 8];
+                const int vcPointCount = __float_as_int(vc[o + 3].w) & 0xff;
+                const int4 a = c.cA[toiContacts[i]];
+                const int pa = c.proxyInfo[a.x & 0xffff], pb = c.proxyInfo[(a.x >> 16) & 0xffff];
+                ev.push(kEventPostSolve, pa & 0xffff, (pa >> 16) & 0xffff, pb & 0xffff, (pb >> 16) & 0xffff, vcPointCount,
+                        make_float4(imp.x, vcPointCount > 1 ? imp.z : 0.0f, imp.y, vcPointCount > 1 ? imp.w : 0.0f));
+            }
+        }
+
+        // ---- reset island flags, synchronise broad-phase proxies, invalidate TOIs (b2World.cpp:868-886) ----
+        for (int i = 0; i < nB; ++i) {
+            const int b = toiBodies[i];
+            int f = c.bodyFlags[b] & ~kBodyToiIsland;
+            if ((f & kBodyTypeMask) == B2G_DYNAMIC_BODY) f |= kBodyToiMoved;
+            c.bodyFlags[b] = f;
+        }
+        const int np = A.proxyCount[ws];
+        for (int p = 0; p < np; ++p) {
+            const int pi = c.proxyInfo[p];
+            const int fixture = pi & 0xffff, child = (pi >> 16) & 0xffff;
+            const int fi = fixtureInfo[fixture];
+            const int body = fi & 0xffff;
+            if (c.bodyFlags[body] & kBodyToiMoved) SynchronizeProxy(A, tile, lane, p, fixture, child, fi, body);
+        }
+        for (int k = 0; k < n; ++k) {
+            int4 a = c.cA[k];
+            if ((a.z & (kContactToi | kContactToiIsland)) == 0) continue;
+            if ((c.bodyFlags[a.y & 0xffff] | c.bodyFlags[(a.y >> 16) & 0xffff]) & kBodyToiMoved) {
+                a.z &= ~(kContactToi | kContactToiIsland);
+                c.cA[k] = a;
+            }
+        }
+        for (int i = 0; i < nB; ++i) c.bodyFlags[toiBodies[i]] &= ~kBodyToiMoved;
+        UpdatePairsOrdered(Ap, tile, lane);  // m_contactManager.FindNewContacts()
+    }
+}
+
+// =================================================================================================
+// k_toi — b2World::SolveTOI for every world with continuous physics
+// =================================================================================================
+__global__ void __launch_bounds__(kToiWarps * 32) k_toi(Arena A, float dt, int velIters) {
+    __shared__ unsigned int sMinAlpha[kTile];
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t ws = (size_t)tile * kTile + lane;
+    const bool live = tile * kTile + lane < A.numWorlds && (A.worldFlags[ws] & B2G_WORLD_CONTINUOUS) != 0;
+    if (!__syncthreads_or(live)) return;
+    if (warp == 0) sMinAlpha[lane] = __float_as_uint(1.0f);
+    __syncthreads();
+    const ToiCols c = MakeToiCols(A, tile, lane);
+    const int n = live ? A.contactCount[ws] : 0;
+    const int nb = live ? A.bodyCount[ws] : 0;
+
+    // ---- b2World.cpp:582-596: clear island flags, alpha0 = 0, invalidate every TOI.  alpha0 is only read by
+    // phase 2 (after the barrier); phase 1 knows it is 0. ----
+    const int nbMax = __reduce_max_sync(0xffffffffu, nb);
+    for (int b = warp; b < nbMax; b += kToiWarps) {
+        if (b >= nb) continue;
+        float4 s0 = c.bodySweep0[b];
+        if (s0.w != 0.0f) {
+            s0.w = 0.0f;
+            c.bodySweep0[b] = s0;
+        }
+        const int f = c.bodyFlags[b];
+        if (f & (kBodyToiIsland | kBodyToiMoved)) c.bodyFlags[b] = f & ~(kBodyToiIsland | kBodyToiMoved);
+    }
+
+    __syncthreads();
+
+    // ---- phase 1: first pass over the contact list, every candidate's time of impact in parallel ----
+    const int nMax = __reduce_max_sync(0xffffffffu, n);
+    float myMin = 1.0f;
+    for (int k = warp; k < nMax; k += kToiWarps) {
+        if (k >= n) continue;
+        int4 a = c.cA[k];
+        const int z0 = a.z;
+        a.z &= ~(kContactToi | kContactToiIsland | kContactToiCountMask);
+        if (a.z & kContactEnabled) {
+            const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+            if (ToiCandidate(c.bodyFlags[bodyA], c.bodyFlags[bodyB])) {
+                Sweep sA = LoadSweep(c, bodyA), sB = LoadSweep(c, bodyB);
+                sA.alpha0 = 0.0f;
+                sB.alpha0 = 0.0f;
+                const float alpha = ContactToi(A, tile, lane, c, k, a, sA, sB, 0.0f);
+                c.cToi[k] = alpha;
+                a.z |= kContactToi;
+                myMin = Min(myMin, alpha);
+            }
+        }
+        if (a.z != z0) c.cA[k] = a;
+    }
+    if (myMin < 1.0f) atomicMin(&sMinAlpha[lane], __float_as_uint(myMin));  // alpha >= 0: uint order == float order
+    __syncthreads();
+    if (warp != 0 || !live) return;
+
+    // ---- phase 2: worlds with a TOI event run the reference's loop ----
+    if (1.0f - 10.0f * kEpsilon < __uint_as_float(sMinAlpha[lane])) return;
+    SolveToiWorld(&A, tile, lane, dt, velIters);
+}
+
+}  // namespace b2g

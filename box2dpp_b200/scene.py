@@ -309,6 +309,36 @@ def mixed(seed: int, flags=WORLD_DEFAULT, bodies=40) -> Scene:
     return s
 
 
+def bullets(seed: int, flags=WORLD_DEFAULT, shots=6) -> Scene:
+    """Continuous-collision scene: bullet bodies fired at a thin static wall and at a stack of
+    boxes, plus a kinematic paddle.  Exercises every branch of b2World::SolveTOI — bullet-vs-dynamic times of
+    impact, sweeps at different alpha0, mini-islands with kinematic / static / bullet neighbours.
+    All randomness from LCG(seed)."""
+    rng = LCG(seed)
+    s = Scene((0.0, -10.0), flags)
+    g = s.create_body(STATIC_BODY, (0.0, 0.0))
+    s.create_box(g, 40.0, 1.0, center=(0.0, -1.0), angle=0.0)
+    s.create_box(g, 0.05, 4.0, center=(12.0, 4.0), angle=0.0)          # thin wall
+    s.create_edge(g, (-20.0, 0.0), (-20.0, 12.0))                      # edge wall on the left
+    for k in range(6):                                                 # stack
+        b = s.create_body(DYNAMIC_BODY, (4.0 + rng.uniform(-0.05, 0.05), 0.5 + 1.0 * k))
+        s.create_box(b, 0.5, 0.5, density=2.0, friction=0.4)
+    paddle = s.create_body(KINEMATIC_BODY, (-6.0, 3.0), linear_velocity=(2.5, 0.0), angular_velocity=1.0)
+    s.create_box(paddle, 1.5, 0.2)
+    for k in range(shots):
+        y = 0.6 + rng.uniform(0.0, 5.0)
+        speed = 60.0 + rng.uniform(0.0, 120.0)
+        left = k % 3 == 2
+        b = s.create_body(DYNAMIC_BODY, (-15.0 + 2.0 * k if not left else 9.0, y),
+                          linear_velocity=(-speed if left else speed, rng.uniform(-5.0, 5.0)),
+                          angular_velocity=rng.uniform(-20.0, 20.0), flags=BD_DEFAULT | BD_BULLET)
+        if k % 2 == 0:
+            s.create_circle(b, rng.uniform(0.1, 0.25), density=8.0, restitution=0.3)
+        else:
+            s.create_box(b, rng.uniform(0.1, 0.3), rng.uniform(0.05, 0.2), density=8.0, friction=0.3)
+    return s
+
+
 class SceneBatch:
     """Many worlds that share fixtures/vertices and differ only in their body definitions.
 

@@ -64,7 +64,8 @@ typedef struct b2gpu_batch_desc {
     int32_t maxEvents;     /* per world per step */
     int32_t eventMask;     /* bit (1 << B2GPU_EVENT_*) per recorded event type; 0 = no listener */
     int32_t blockSize;     /* threads per CTA, multiple of 32; 0 = default */
-    int32_t reserved;      /* bit 0: force the generic solver kernel (body state in global memory) */
+    int32_t reserved;      /* bit 0: force the generic solver kernel (body state in global memory);
+                              bit 1: rebuild the islands every step (validation of the topology-dirty tracking) */
 } b2gpu_batch_desc;
 
 /* Arena fields reachable through upload/download.  Host layout is world-major:

@@ -173,8 +173,12 @@ WORLD_CASES = {
     "pyramid7_jitter3": (lambda: S.pyramid(7, flags=NOCCD, jitter_seed=3), 200, 8, 3),
     "mixed_seed0": (lambda: S.mixed(0, flags=NOCCD), 400, 8, 3),
     "mixed_seed5": (lambda: S.mixed(5, flags=NOCCD), 400, 8, 3),
+    # continuous physics on (b2World::SolveTOI): the reference's default flags
+    "mixed_seed2_default": (lambda: S.mixed(2), 300, 8, 3),
+    "bullets_seed1_default": (lambda: S.bullets(1), 240, 8, 3),
+    "bullets_seed3_default_nosleep": (lambda: S.bullets(3, flags=S.WORLD_DEFAULT & ~S.WORLD_ALLOW_SLEEP), 240, 6, 2),
 }
-# scenes the C restatement / the device path can run (continuous physics off)
+# scenes the C restatement can run (continuous physics off); the device path runs every case
 NOCCD_CASES = [k for k in WORLD_CASES if "default" not in k and "_ccd_" not in k]
 
 # SURVEY.md Appendix D checkpoints (vanilla, produced by the survey's independent probe):

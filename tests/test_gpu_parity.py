@@ -72,6 +72,12 @@ def test_mixed_shapes(oracles):
     run_parity(oracles, scenes, 400, 8, 3, check_every=9)
 
 
+def test_mixed_shapes_every_step(oracles):
+    # per-step check: catches state that is only wrong for a step (e.g. a static body's awake flag when islands
+    # sharing it fall asleep at different times: b2World::Solve builds and solves islands alternately)
+    run_parity(oracles, [S.mixed(seed, flags=NOCCD) for seed in (1, 6)], 400, 8, 3)
+
+
 def test_generic_solver_path(oracles):
     """The fallback solver kernel (body state in global memory, used when a tile's body table exceeds shared
     memory) stays bit-exact too."""
@@ -81,6 +87,45 @@ def test_generic_solver_path(oracles):
 
 def test_edge_ground_pyramid(oracles):
     run_parity(oracles, [S.pyramid(8, flags=NOCCD, ground="edge")], 250, 8, 3, check_every=5)
+
+
+# ---- continuous physics ON: b2World::SolveTOI on the device -------------------------
+def _need_ref(oracles):
+    if not oracles.available("ref"):
+        pytest.skip("continuous physics parity needs oracle/_ref (the C restatement stops at SolveTOI); "
+                    "the golden-hash tests below cover it without the library")
+
+
+def test_hello_world_default_flags(oracles):
+    # BASELINE config 1 exactly as HelloWorld/HelloWorld.cpp runs it (TOI event at the landing)
+    _need_ref(oracles)
+    run_parity(oracles, [S.hello_world()], 60, 6, 2)
+
+
+def test_pyramid_20_default_flags(oracles):
+    # BASELINE config 2 with the reference's defaults: 386 TOI events in the first 210 steps, asleep from 212
+    _need_ref(oracles)
+    run_parity(oracles, [S.pyramid(20)], 260, 8, 3, check_every=3)
+
+
+def test_toi_batch_divergent(oracles):
+    # different worlds in one tile: lanes with and without TOI events, different sub-step counts
+    _need_ref(oracles)
+    scenes = [S.pyramid(5 + (w % 4), jitter_seed=w) for w in range(20)] + [S.mixed(s) for s in range(6)] + \
+             [S.bullets(s) for s in range(8)] + [S.hello_world()]
+    run_parity(oracles, scenes, 200, 8, 3, check_every=8)
+
+
+def test_toi_bullets_every_step(oracles):
+    _need_ref(oracles)
+    run_parity(oracles, [S.bullets(s, shots=9) for s in range(5)], 150, 6, 2)
+
+
+def test_toi_generic_solver_and_mixed_flags(oracles):
+    # worlds with and without continuous physics in the same batch, on the fallback solver path
+    _need_ref(oracles)
+    scenes = [S.bullets(2), S.bullets(2, flags=NOCCD), S.pyramid(6), S.pyramid(6, flags=NOCCD), S.mixed(3)]
+    run_parity(oracles, scenes, 150, 8, 3, check_every=5, generic_solver=True)
 
 
 def test_replicated_worlds_identical(oracles):
@@ -131,7 +176,7 @@ def test_device_narrow_phase_large_random(oracles):
         assert (ri == ints[i]).all() and (rf.view(np.uint32) == fl[i].view(np.uint32)).all(), f"pair {i}"
 
 
-@pytest.mark.parametrize("name", G.NOCCD_CASES)
+@pytest.mark.parametrize("name", list(G.WORLD_CASES))
 def test_worlds_match_golden_hashes(name):
     """Every parity scene against the per-step hashes frozen from the reference (body state bits, contact-list
     order with point counts, contact / touching / manifold-point totals)."""
