@@ -85,7 +85,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(use), "power_w_max": max(float(s[1][2]) for s in use)}
 
 
-def cpu_reference_run(steps, warmup, threads=None, worlds_per_thread=16):
+def build_scenes(workload, count, first_seed, flags, jittered=True):
+    """`count` worlds of the named workload, world i seeded with first_seed + i.  Returns (batch-or-list, scene(i))."""
+    from box2dpp_b200 import scene as S
+    if workload == "pyramid":
+        sb = S.pyramid_batch(count, ROWS, flags=flags, first_seed=first_seed, jittered=jittered)
+        return sb, sb.scene
+    scenes = [S.mixed(first_seed + i, flags=flags) for i in range(count)]
+    return scenes, scenes.__getitem__
+
+
+def cpu_reference_run(steps, warmup, threads=None, worlds_per_thread=16, workload="pyramid", flags=None):
     """The reference's own b2World::Step (vanilla Box2D compiled from /root/reference into oracle/_ref),
     one world per thread slot on every host core.  Falls back to nothing: if oracle/_ref is absent the
     C port is NOT a fair stand-in for speed, so we say so."""
@@ -93,14 +103,17 @@ def cpu_reference_run(steps, warmup, threads=None, worlds_per_thread=16):
     from oracle import worlds  # TEST INFRASTRUCTURE: used only as the CPU baseline / reference arm
     threads = threads or os.cpu_count()
     n = threads * worlds_per_thread
-    sb = S.pyramid_batch(n, ROWS, flags=flags_throughput(), first_seed=0)
-    scenes = [sb.scene(i) for i in range(n)]
+    flags = flags_throughput() if flags is None else flags
+    _, get = build_scenes(workload, n, 0, flags)
+    scenes = [get(i) for i in range(n)]
     if not worlds.available("ref"):
         return None
     sec, _ = worlds.bench_run(scenes, worlds_per_thread, threads, steps, warmup, DT, 8, 3)
+    what = f"jittered pyramid-{ROWS}" if workload == "pyramid" else "mixed-shape (chain terrain, circles, polygons)"
     return {"value": n * steps / sec, "unit": "world-steps/s", "cores": threads, "kind": "reference",
-            "sample": f"{threads} threads x {worlds_per_thread} jittered pyramid-{ROWS} worlds, {warmup} warm-up + "
-                      f"{steps} timed steps, 8/3 iterations, sleeping off, TOI off, vanilla Box2D 2.3.2 -O2",
+            "sample": f"{threads} threads x {worlds_per_thread} {what} worlds, {warmup} warm-up + "
+                      f"{steps} timed steps, 8/3 iterations, sleeping {'on' if flags & S.WORLD_ALLOW_SLEEP else 'off'}, "
+                      f"TOI {'on' if flags & S.WORLD_CONTINUOUS else 'off'}, vanilla Box2D 2.3.2 -O2",
             "seconds": sec, "worlds": n}
 
 
@@ -116,6 +129,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--generic-solver", action="store_true", help="force the fallback solver kernel")
+    ap.add_argument("--workload", default="pyramid", choices=["pyramid", "mixed"],
+                    help="pyramid = BASELINE configs[2] (the headline); mixed = configs[3] per-GPU share")
+    ap.add_argument("--toi", action="store_true", help="continuous physics on (the reference's default) on both arms")
+    ap.add_argument("--sleep", action="store_true", help="sleeping allowed (the reference's default) on both arms")
+    ap.add_argument("--preroll", type=int, default=-1)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -123,31 +141,44 @@ def main():
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(args.warmup, 3)
 
-    config = {"workload": f"{args.worlds_per_gpu} {'identical' if args.identical else 'jittered'} pyramid-{ROWS} worlds "
-                          f"per GPU (BASELINE configs[2]), dt=1/60, 8 vel / 3 pos iterations",
-              "worlds_per_gpu": args.worlds_per_gpu, "dynamic_bodies_per_world": BODIES_DYNAMIC,
-              "sleeping": False, "continuous_physics": False, "warm_starting": True, "events": "off",
-              "preroll_steps": PREROLL, "sharding": f"world-index blocks x{args.gpus}, no collective",
+    from box2dpp_b200 import scene as S
+    flags = flags_throughput()
+    if args.toi:
+        flags |= S.WORLD_CONTINUOUS
+    if args.sleep:
+        flags |= S.WORLD_ALLOW_SLEEP
+    preroll = args.preroll if args.preroll >= 0 else (PREROLL if args.workload == "pyramid" else 120)
+    if args.workload == "pyramid":
+        nbody, nproxy = BODIES_DYNAMIC, BODIES_DYNAMIC + 1
+        what = (f"{args.worlds_per_gpu} {'identical' if args.identical else 'jittered'} pyramid-{ROWS} worlds "
+                f"per GPU (BASELINE configs[2])")
+    else:
+        nbody, nproxy = 40, 72
+        what = (f"{args.worlds_per_gpu} mixed-shape worlds per GPU (BASELINE configs[3]'s per-GPU share: 32-edge chain "
+                f"terrain, 20 circles + 20 random convex polygons, seed = world index)")
+    config = {"workload": what + ", dt=1/60, 8 vel / 3 pos iterations",
+              "worlds_per_gpu": args.worlds_per_gpu, "dynamic_bodies_per_world": nbody,
+              "sleeping": bool(args.sleep), "continuous_physics": bool(args.toi), "warm_starting": True, "events": "off",
+              "preroll_steps": preroll, "sharding": f"world-index blocks x{args.gpus}, no collective",
               "l2": "working set (~0.25 MB/world x worlds) far exceeds the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(args.steps, PREROLL + warmup)
+        r = cpu_reference_run(args.steps, preroll + warmup, workload=args.workload, flags=flags)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libb2ref.so not built on this box"}))
             return
         line = {"impl": "reference", "metric": "world_steps_per_s", "value": r["value"], "unit": "world-steps/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config, "body_steps_per_s": r["value"] * BODIES_DYNAMIC,
+                "config": config, "body_steps_per_s": r["value"] * nbody,
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
 
-    from box2dpp_b200 import scene as S
     from box2dpp_b200.batch import F_CONTACT_COUNT, F_ISLAND_CONTACT_END, F_ISLAND_COUNT, WorldBatch
 
     dist = None
@@ -172,9 +203,9 @@ def main():
     from box2dpp_b200.shard import shard_range
     # weak scaling: the job has worlds_per_gpu x N worlds; rank r owns a contiguous world-index block
     first_world, W = shard_range(args.worlds_per_gpu * world_size, world_size, rank)
-    sb = S.pyramid_batch(W, ROWS, flags=flags_throughput(), first_seed=first_world, jittered=not args.identical)
+    sb, _ = build_scenes(args.workload, W, first_world, flags, jittered=not args.identical)
     batch = WorldBatch(sb, device=local_rank, block_size=args.block, generic_solver=args.generic_solver)
-    batch.step_n(DT, 8, 3, PREROLL)
+    batch.step_n(DT, 8, 3, preroll)
     batch.sync()
 
     sampler = ClockSampler(local_rank)
@@ -234,7 +265,6 @@ def main():
     nisl = batch.field(F_ISLAND_COUNT)[:, 0, 0]
     iend = batch.field(F_ISLAND_CONTACT_END)[:, :, 0]
     touching = np.array([iend[w, nisl[w] - 1] if nisl[w] > 0 else 0 for w in range(W)], dtype=np.float64)
-    nbody, nproxy = BODIES_DYNAMIC, BODIES_DYNAMIC + 1
     alg_step = nbody * BYTES_PER_DYNAMIC_BODY + nproxy * BYTES_PER_PROXY + contacts.mean() * BYTES_PER_CONTACT
     # Algorithmic bytes per world for each kernel taken alone: persistent fields it must read once
     # plus persistent fields it must write once; solver temporaries (constraint records) count zero.
@@ -249,6 +279,8 @@ def main():
         "k_solve_finalize": nbody * (12 + 16 + 16),                              # c/a, xf, flags + sleep time
         "k_sync_pairs": nproxy * (16 + 68) + nbody * (16 + 12),                  # fat AABB + shape; xf, c0/a0
         "k_solve": nbody * BYTES_PER_DYNAMIC_BODY + tc * BYTES_PER_CONTACT,
+        "k_toi": nc * (4 + 4 + 4) + nbody * (16 + 16 + 4) + nproxy * 84,          # flags r/w + cached toi; sweep, sweep0.alpha0, flags; shapes
+        "k_toi_events": nc * (4 + 4) + nbody * 4,                                # flags + cached toi of the list walk; body flags
     }
     top = max(kms, key=kms.get)
     top_ms = kms[top]
@@ -281,7 +313,7 @@ def main():
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_reference_run(200, PREROLL + 10)
+            cpu = cpu_reference_run(200, preroll + 10, workload=args.workload, flags=flags)
             if cpu:
                 cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as exc:  # the baseline is a report, never a dependency of the GPU number
@@ -291,7 +323,7 @@ def main():
         line = {"metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": world_size,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "body_steps_per_s": value * BODIES_DYNAMIC, "e2e": e2e, "gpu_launches": int(launches),
+                "body_steps_per_s": value * nbody, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
                 "worlds_with_overflow": status_bad}
         print(json.dumps(line))

@@ -15,7 +15,8 @@ import numpy as np
 from .scene import CScene, FixtureDef, Scene, SceneBatch, scene_array
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2gpu.so")
+# B2GPU_LIB selects another build of the same library (diagnostic variants: tools/build_variant.sh)
+LIB_PATH = os.environ.get("B2GPU_LIB") or os.path.join(_HERE, "libb2gpu.so")
 
 # field ids — keep in sync with include/b2gpu.h
 (F_GRAVITY, F_WORLD_FLAGS, F_INV_DT0, F_BODY_COUNT, F_PROXY_COUNT, F_CONTACT_COUNT, F_STATUS, F_EVENT_COUNT,
@@ -57,6 +58,13 @@ class B2GpuError(RuntimeError):
 _lib = None
 
 
+# b2gpu_body_command (include/b2gpu.h)
+BODY_COMMAND_DTYPE = np.dtype([("world", "<i4"), ("body", "<i4"), ("op", "<i4"), ("wake", "<i4"),
+                               ("v", "<f4", 2), ("p", "<f4", 2)])
+(CMD_APPLY_FORCE, CMD_APPLY_FORCE_TO_CENTER, CMD_APPLY_TORQUE, CMD_APPLY_LINEAR_IMPULSE, CMD_APPLY_ANGULAR_IMPULSE,
+ CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE) = range(9)
+
+
 def lib():
     """Load libb2gpu.so.  Raises (never falls back) when the CUDA extension has not been built."""
     global _lib
@@ -76,6 +84,8 @@ def lib():
         L.b2gpu_batch_sync.argtypes = [vp]
         L.b2gpu_batch_apply_forces.argtypes = [vp, vp]
         L.b2gpu_batch_read_transforms.argtypes = [vp, vp]
+        L.b2gpu_batch_body_commands.argtypes = [vp, vp, C.c_int64]
+        L.b2gpu_batch_read_body_state.argtypes = [vp, vp]
         L.b2gpu_batch_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_steps.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_kernels.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
@@ -208,6 +218,18 @@ class WorldBatch:
         f = np.ascontiguousarray(forces, np.float32)
         assert f.size == self.num_worlds * self.max_bodies * 3
         _check(lib().b2gpu_batch_apply_forces(self.h, f.ctypes.data_as(C.c_void_p)))
+
+    def body_commands(self, commands: np.ndarray):
+        """b2gpu_batch_body_commands: `commands` is a BODY_COMMAND_DTYPE array (any world order)."""
+        cmds = np.ascontiguousarray(commands, BODY_COMMAND_DTYPE)
+        _check(lib().b2gpu_batch_body_commands(self.h, cmds.ctypes.data_as(C.c_void_p), cmds.shape[0]))
+
+    def read_body_state(self, out: np.ndarray | None = None) -> np.ndarray:
+        """[W, maxBodies, 8] float32: p.x p.y angle awake | v.x v.y omega sleepTime."""
+        if out is None:
+            out = np.empty((self.num_worlds, self.max_bodies, 8), np.float32)
+        _check(lib().b2gpu_batch_read_body_state(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def read_transforms(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:

@@ -1340,6 +1340,29 @@ __device__ __noinline__ void UpdatePairsOrdered(const Arena* Ap, int tile, int l
     A.contactCount[ws] = c.nc;
 }
 
+// Body -> proxies index (the reference reaches a body's proxies through m_fixtureList / m_proxies): counting sort
+// of the proxies by body, one thread per world.  Runs when fixtures were created (with the initial FindNewContacts).
+__global__ void __launch_bounds__(128) k_index_proxies(Arena A) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int tile = w >> 5, lane = w & 31;
+    if (tile >= A.numTiles || w >= A.numWorlds) return;
+    const size_t ws = (size_t)tile * kTile + lane;
+    const int nb = A.bodyCount[ws], np = A.proxyCount[ws];
+    Col<int> start = col(A.bodyProxyStart, tile, A.NB + 1, lane);
+    Col<int> list = col(A.bodyProxyList, tile, A.NP, lane);
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+    for (int b = 0; b <= nb; ++b) start[b] = 0;
+    for (int p = 0; p < np; ++p) start[(fixtureInfo[proxyInfo[p] & 0xffff] & 0xffff) + 1] += 1;
+    for (int b = 0; b < nb; ++b) start[b + 1] += start[b];  // start[b] = first slot of body b
+    for (int p = 0; p < np; ++p) {
+        const int b = fixtureInfo[proxyInfo[p] & 0xffff] & 0xffff;
+        list[start[b]++] = p;  // start[b] ends up as the first slot of body b + 1
+    }
+    for (int b = nb; b > 0; --b) start[b] = start[b - 1];
+    start[0] = 0;
+}
+
 // b2World::Step's leading `if (m_flags & e_newFixture) FindNewContacts()` for freshly built worlds.
 __global__ void __launch_bounds__(128) k_find_new_contacts(Arena A) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1395,9 +1418,11 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_sync_pairs(Arena A, float d
         int fi = fixtureInfo[fixture];
         int body = fi & 0xffff;
         int bf = bodyFlags[body];
-        if ((bf & kBodyIsland) == 0) continue;          // not in an island: did not move
-        if ((bf & kBodyTypeMask) == B2G_STATIC_BODY) continue;
-        if (!SynchronizeProxy(A, tile, lane, p, fixture, child, fi, body)) continue;
+        // a proxy may already sit in the move buffer: b2Body::SetTransform between two steps (k_body_commands)
+        bool moved = proxyMoved[p] != 0;
+        if ((bf & kBodyIsland) != 0 && (bf & kBodyTypeMask) != B2G_STATIC_BODY)  // else: not in an island, did not move
+            moved |= SynchronizeProxy(A, tile, lane, p, fixture, child, fi, body);
+        if (!moved) continue;
         int slot = atomicAdd(&sNMoved[lane], 1);
         if (slot < kMaxMoved) sMoved[slot][lane] = (uint16_t)p;
     }

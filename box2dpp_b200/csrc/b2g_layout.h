@@ -130,6 +130,11 @@ struct Arena {
     int* islandSolved;   // [tile][ceil(NB/32)][lane]  bit per island: position solver converged
 
     // ---- continuous collision (b2World::SolveTOI) ----
+    float* toiMinAlpha;  // [tile][lane]          smallest time of impact of the first pass (k_toi -> k_toi_events)
+    int* toiCand;        // [tile][NC][lane]      contacts that can ever be TOI candidates (static criterion), ascending
+    int* toiCandCount;   // [tile][lane]
+    int* bodyProxyStart; // [tile][NB+1][lane]    proxies of body b: bodyProxyList[bodyProxyStart[b] .. bodyProxyStart[b+1])
+    int* bodyProxyList;  // [tile][NP][lane]      (b2Body::m_fixtureList -> b2Fixture::m_proxies, any order)
     float* contactToi;   // [tile][NC][lane]      b2Contact::m_toi (valid while kContactToi is set)
     int* toiBodies;      // [tile][64][lane]      bodies of the current TOI mini-island (2 * b2_maxTOIContacts)
     int* toiContacts;    // [tile][32][lane]      its contacts (b2_maxTOIContacts)

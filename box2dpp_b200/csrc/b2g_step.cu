@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/b2gpu.h"
 #include "b2g_kernels.cuh"
@@ -98,6 +99,167 @@ __global__ void k_read_transforms(Arena A, float4* __restrict__ out) {
     out[(size_t)w * A.NB + body] = A.bodyXf[idx];
 }
 
+// b2Body state for every body, world-major output: p.x p.y angle awake | v.x v.y omega sleepTime
+__global__ void k_read_body_state(Arena A, float4* __restrict__ out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)A.numTiles * A.NB * kTile;
+    if (idx >= total) return;
+    int lane = (int)(idx & 31);
+    size_t r = idx >> 5;
+    int body = (int)(r % A.NB);
+    int tile = (int)(r / A.NB);
+    int w = tile * kTile + lane;
+    if (w >= A.numWorlds) return;
+    const float4 xf = A.bodyXf[idx], sw = A.bodySweep[idx], v = A.bodyVel[idx];
+    const int f = A.bodyFlags[idx];
+    float4* o = out + ((size_t)w * A.NB + body) * 2;
+    o[0] = make_float4(xf.x, xf.y, sw.z, (f & kBodyAwake) ? 1.0f : 0.0f);
+    o[1] = make_float4(v.x, v.y, v.z, sw.w);
+}
+
+// Between-step body edits (include/b2gpu.h B2GPU_CMD_*).  The command array is grouped by world; the thread that
+// owns the first command of a world applies that world's commands in order, exactly as the reference's user
+// would have made the calls (Box2D/Dynamics/b2Body.h:738-833, 408-467, 634-653; b2Body.cpp:418-440).
+__global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ cmds, long long count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int w = cmds[i].world;
+    if (i > 0 && cmds[i - 1].world == w) return;  // not the first command of its world
+    const int tile = w >> 5, lane = w & 31;
+    const size_t ws = (size_t)tile * kTile + lane;
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
+    Col<float4> bodySweep0 = col(A.bodySweep0, tile, A.NB, lane);
+    Col<float4> bodyVel = col(A.bodyVel, tile, A.NB, lane);
+    Col<float4> bodyForce = col(A.bodyForce, tile, A.NB, lane);
+    Col<float4> bodyMass = col(A.bodyMass, tile, A.NB, lane);
+    Col<float4> bodyXf = col(A.bodyXf, tile, A.NB, lane);
+    const int nb = A.bodyCount[ws];
+    for (; i < count && cmds[i].world == w; ++i) {
+        const b2gpu_body_command c = cmds[i];
+        if (c.body < 0 || c.body >= nb || c.op < 0 || c.op >= B2GPU_CMD_COUNT) {
+            A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
+            continue;
+        }
+        const int b = c.body;
+        int f = bodyFlags[b];
+        const int type = f & kBodyTypeMask;
+        auto wake = [&]() {  // SetAwake(true)
+            if (WakeBody(bodyFlags, bodySweep, b)) A.topoDirty[ws] = 1;
+            f |= kBodyAwake;
+        };
+        switch (c.op) {
+            case B2GPU_CMD_APPLY_FORCE:
+            case B2GPU_CMD_APPLY_FORCE_TO_CENTER:
+            case B2GPU_CMD_APPLY_TORQUE: {
+                if (type != B2G_DYNAMIC_BODY) break;
+                if (c.wake && (f & kBodyAwake) == 0) wake();
+                if ((f & kBodyAwake) == 0) break;
+                float4 cur = bodyForce[b];
+                if (c.op == B2GPU_CMD_APPLY_TORQUE) {
+                    cur.z += c.v[0];
+                } else {
+                    cur.x += c.v[0];
+                    cur.y += c.v[1];
+                    if (c.op == B2GPU_CMD_APPLY_FORCE) {
+                        const float4 sw = bodySweep[b];
+                        cur.z += Cross(V2(c.p[0], c.p[1]) - V2(sw.x, sw.y), V2(c.v[0], c.v[1]));
+                    }
+                }
+                bodyForce[b] = cur;
+            } break;
+            case B2GPU_CMD_APPLY_LINEAR_IMPULSE:
+            case B2GPU_CMD_APPLY_ANGULAR_IMPULSE: {
+                if (type != B2G_DYNAMIC_BODY) break;
+                if (c.wake && (f & kBodyAwake) == 0) wake();
+                if ((f & kBodyAwake) == 0) break;
+                const float4 m = bodyMass[b];
+                float4 v = bodyVel[b];
+                if (c.op == B2GPU_CMD_APPLY_LINEAR_IMPULSE) {
+                    const float4 sw = bodySweep[b];
+                    const Vec2 imp = V2(c.v[0], c.v[1]);
+                    const Vec2 lv = V2(v.x, v.y) + m.x * imp;
+                    v.x = lv.x;
+                    v.y = lv.y;
+                    v.z += m.y * Cross(V2(c.p[0], c.p[1]) - V2(sw.x, sw.y), imp);
+                } else {
+                    v.z += m.y * c.v[0];
+                }
+                bodyVel[b] = v;
+            } break;
+            case B2GPU_CMD_SET_LINEAR_VELOCITY: {
+                if (type == B2G_STATIC_BODY) break;
+                if (Dot(V2(c.v[0], c.v[1]), V2(c.v[0], c.v[1])) > 0.0f) wake();
+                float4 v = bodyVel[b];
+                v.x = c.v[0];
+                v.y = c.v[1];
+                bodyVel[b] = v;
+            } break;
+            case B2GPU_CMD_SET_ANGULAR_VELOCITY: {
+                if (type == B2G_STATIC_BODY) break;
+                if (c.v[0] * c.v[0] > 0.0f) wake();
+                float4 v = bodyVel[b];
+                v.z = c.v[0];
+                bodyVel[b] = v;
+            } break;
+            case B2GPU_CMD_SET_AWAKE: {
+                if (c.wake) {
+                    wake();
+                } else {
+                    if (f & kBodyAwake) A.topoDirty[ws] = 1;
+                    bodyFlags[b] = f & ~kBodyAwake;
+                    float4 sw = bodySweep[b];
+                    sw.w = 0.0f;
+                    bodySweep[b] = sw;
+                    bodyVel[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    bodyForce[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+            } break;
+            case B2GPU_CMD_SET_TRANSFORM: {
+                Xf xf;
+                xf.q = MakeRot(c.p[0]);
+                xf.p = V2(c.v[0], c.v[1]);
+                bodyXf[b] = make_float4(xf.p.x, xf.p.y, xf.q.s, xf.q.c);
+                const float4 m = bodyMass[b];
+                const Vec2 cen = Mul(xf, V2(m.z, m.w));
+                float4 sw = bodySweep[b];
+                sw.x = cen.x; sw.y = cen.y; sw.z = c.p[0];
+                bodySweep[b] = sw;
+                float4 s0 = bodySweep0[b];
+                s0.x = cen.x; s0.y = cen.y; s0.z = c.p[0];
+                bodySweep0[b] = s0;
+                // f->Synchronize(broadPhase, m_xf, m_xf) for every fixture of the body (b2Fixture.cpp:154-177)
+                Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+                Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+                Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+                Col<float2> chainVerts = col(A.chainVerts, tile, A.NV, lane);
+                const int np = A.proxyCount[ws];
+                for (int p = 0; p < np; ++p) {
+                    const int pi = proxyInfo[p];
+                    const int fixture = pi & 0xffff, child = pi >> 16;
+                    const int fi = fixtureInfo[fixture];
+                    if ((fi & 0xffff) != b) continue;
+                    const float* sw_ = A.shapeWords + ((size_t)tile * A.NS + col(A.fixtureShape, tile, A.NF, lane)[fixture]) * kTile + lane;
+                    Vec2 lo1, hi1;
+                    ShapeAABB(sw_, (fi >> 16) & 3, chainVerts, child, xf, &lo1, &hi1);
+                    Vec2 lo = Min(lo1, lo1), hi = Max(hi1, hi1);
+                    const Vec2 displacement = xf.p - xf.p;
+                    const float4 fat = proxyFat[p];
+                    if (fat.x <= lo.x && fat.y <= lo.y && hi.x <= fat.z && hi.y <= fat.w) continue;
+                    const Vec2 r = V2(kAabbExtension, kAabbExtension);
+                    lo = lo - r;
+                    hi = hi + r;
+                    const Vec2 d = kAabbMultiplier * displacement;
+                    if (d.x < 0.0f) lo.x += d.x; else hi.x += d.x;
+                    if (d.y < 0.0f) lo.y += d.y; else hi.y += d.y;
+                    proxyFat[p] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    col(A.proxyMoved, tile, A.NP, lane)[p] = 1;
+                }
+            } break;
+        }
+    }
+}
+
 // ---- stateless entry points: the kernels' building blocks on flat inputs (unit-level parity) ----
 struct FlatPoly {  // 35 floats: count, 8 vertices, 8 normals, centroid (oracle/ref_harness.cpp fill_poly)
     const float* w;
@@ -182,6 +344,8 @@ struct b2gpu_batch {
     // per-step I/O staging
     float* ioDev = nullptr;
     size_t ioBytes = 0;
+    b2gpu_body_command* cmdDev = nullptr;
+    size_t cmdBytes = 0;
 };
 
 namespace {
@@ -239,7 +403,9 @@ int allocateArena(b2gpu_batch* b) {
     } else {
         ALLOC(vc, (size_t)A.NC * kVcStride, float4);
     }
-    ALLOC(contactToi, A.NC, float); ALLOC(toiBodies, kToiBodyCap, int); ALLOC(toiContacts, kMaxToiContacts, int);
+    ALLOC(toiMinAlpha, 1, float); ALLOC(contactToi, A.NC, float);
+    ALLOC(toiCand, A.NC, int); ALLOC(toiCandCount, 1, int);
+    ALLOC(bodyProxyStart, A.NB + 1, int); ALLOC(bodyProxyList, A.NP, int); ALLOC(toiBodies, kToiBodyCap, int); ALLOC(toiContacts, kMaxToiContacts, int);
     ALLOC(toiVc, (size_t)kMaxToiContacts * kVcStride, float4);
     ALLOC(eventA, A.NE, int4); ALLOC(eventB, A.NE, float4);
 
@@ -331,6 +497,7 @@ int configureKernels(b2gpu_batch* b) {
         return fail(B2GPU_ERR_CAPACITY, "maxContacts %d exceeds the collide kernel's shared-memory budget (%d)",
                     desc->maxContacts, (maxSmem - 1024) / kTile);
     CUDA_TRY(cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, desc->maxContacts * kTile));
+    CUDA_TRY(cudaFuncSetAttribute(k_toi, cudaFuncAttributeMaxDynamicSharedMemorySize, desc->maxContacts * kTile));
     if (b->tileSolver) {
         CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
         CUDA_TRY(cudaFuncSetAttribute(k_solve_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
@@ -350,12 +517,12 @@ int configureKernels(b2gpu_batch* b) {
 
 // Kernel names in launch order of one step (b2gpu_batch_profile_kernels reports times in this order).
 const char* const kTileKernels[] = {"k_collide", "k_islands", "k_solve_prepare", "k_solve_velocity", "k_solve_integrate",
-                                    "k_solve_position", "k_solve_finalize", "k_sync_pairs", "k_toi"};
-const char* const kGenericKernels[] = {"k_collide", "k_islands", "k_solve", "k_sync_pairs", "k_toi"};
-constexpr int kMaxStepKernels = 9;
+                                    "k_solve_position", "k_solve_finalize", "k_sync_pairs", "k_toi", "k_toi_events"};
+const char* const kGenericKernels[] = {"k_collide", "k_islands", "k_solve", "k_sync_pairs", "k_toi", "k_toi_events"};
+constexpr int kMaxStepKernels = 10;
 
 // k_toi only runs when some world has continuous physics on (b2World::Step: `if (m_continuousPhysics && dt > 0)`)
-int stepKernelCount(const b2gpu_batch* b) { return (b->tileSolver ? 8 : 4) + (b->anyContinuous ? 1 : 0); }
+int stepKernelCount(const b2gpu_batch* b) { return (b->tileSolver ? 8 : 4) + (b->anyContinuous ? 2 : 0); }
 
 // One b2World::Step for the whole batch (Box2D/Dynamics/b2World.cpp:888-954).
 // marks (optional): stepKernelCount + 1 events, one before each kernel and one after the last.
@@ -366,8 +533,9 @@ int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_
     cudaStream_t st = b->stream;
     if (b->needInitialPairs) {  // if (m_flags & e_newFixture) FindNewContacts()
         k_find_new_contacts<<<blocks, threads, 0, st>>>(b->A);
+        k_index_proxies<<<(unsigned)((b->A.numTiles * kTile + 127) / 128), 128, 0, st>>>(b->A);
         b->needInitialPairs = false;
-        b->launches++;
+        b->launches += 2;
     }
     int m = 0;
     auto mark = [&]() { if (marks) cudaEventRecord(marks[m++], st); };
@@ -399,9 +567,11 @@ int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_
         mark();
         b->launches += 2;
         if (b->anyContinuous) {  // if (m_continuousPhysics && step.dt > 0) SolveTOI(step)
-            k_toi<<<tiles, kToiWarps * 32, 0, st>>>(b->A, dt, velIters);
+            k_toi<<<tiles, kToiWarps * 32, (size_t)b->A.NC * kTile, st>>>(b->A, dt, velIters);
             mark();
-            b->launches++;
+            k_toi_events<<<tiles, 32, 0, st>>>(b->A, dt, velIters);
+            mark();
+            b->launches += 2;
         }
     }
     cudaError_t e = cudaGetLastError();
@@ -463,6 +633,7 @@ int b2gpu_batch_destroy(b2gpu_batch* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (void* p : b->allocations) cudaFree(p);
     if (b->ioDev) cudaFree(b->ioDev);
+    if (b->cmdDev) cudaFree(b->cmdDev);
     if (b->graphExec) cudaGraphExecDestroy(b->graphExec);
     if (b->evStart) cudaEventDestroy(b->evStart);
     if (b->evStop) cudaEventDestroy(b->evStop);
@@ -599,10 +770,18 @@ int b2gpu_batch_profile_steps(b2gpu_batch* b, float dt, int32_t velIters, int32_
     return B2GPU_OK;
 }
 
+#ifdef B2G_TOI_PROFILE
+int b2gpu_debug_toi_profile(unsigned long long* out16, int reset) {
+    cudaMemcpyFromSymbol(out16, g_toiProf, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_toiProf, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 int64_t b2gpu_batch_launch_count(b2gpu_batch* b) { return b ? b->launches : 0; }
 
-static int ensureIo(b2gpu_batch* b) {
-    size_t need = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
+static int ensureIo(b2gpu_batch* b, size_t need = 0) {
+    if (need == 0) need = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
     if (b->ioBytes < need) {
         if (b->ioDev) cudaFree(b->ioDev);
         b->ioDev = nullptr;
@@ -637,6 +816,56 @@ int b2gpu_batch_read_transforms(b2gpu_batch* b, float* out) {
     CUDA_TRY(cudaGetLastError());
     size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
     CUDA_TRY(cudaMemcpyAsync(out, b->ioDev, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_read_body_state(b2gpu_batch* b, float* out) {
+    if (!b || !out) return fail(B2GPU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    const size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 8 * sizeof(float);
+    int rc = ensureIo(b, bytes);
+    if (rc != B2GPU_OK) return rc;
+    size_t total = (size_t)b->A.numTiles * b->A.NB * kTile;
+    k_read_body_state<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, (float4*)b->ioDev);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, b->ioDev, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_body_commands(b2gpu_batch* b, const b2gpu_body_command* commands, int64_t count) {
+    if (!b || count < 0 || (count > 0 && !commands)) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    if (count == 0) return B2GPU_OK;
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    // group by world, keeping the caller's order inside a world (already grouped input is passed through)
+    bool sorted = true;
+    for (int64_t i = 0; i < count; ++i) {
+        if (commands[i].world < 0 || commands[i].world >= b->desc.numWorlds)
+            return fail(B2GPU_ERR_INVALID, "command %lld names world %d outside the batch", (long long)i, commands[i].world);
+        if (i > 0 && commands[i].world < commands[i - 1].world) sorted = false;
+    }
+    std::vector<b2gpu_body_command> grouped;
+    if (!sorted) {
+        grouped.assign(commands, commands + count);
+        std::stable_sort(grouped.begin(), grouped.end(),
+                         [](const b2gpu_body_command& x, const b2gpu_body_command& y) { return x.world < y.world; });
+        commands = grouped.data();
+    }
+    const size_t bytes = (size_t)count * sizeof(b2gpu_body_command);
+    if (b->cmdBytes < bytes) {
+        if (b->cmdDev) cudaFree(b->cmdDev);
+        b->cmdDev = nullptr;
+        b->cmdBytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&b->cmdDev, bytes * 2));
+        b->cmdBytes = bytes * 2;
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->cmdDev, commands, bytes, cudaMemcpyHostToDevice, b->stream));
+    k_body_commands<<<(unsigned)((count + 127) / 128), 128, 0, b->stream>>>(b->A, b->cmdDev, (long long)count);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    // the host array (or its grouped copy) may die when we return
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     return B2GPU_OK;
 }

@@ -14,7 +14,7 @@
 //            at alpha0 = 0, so the times of impact of the candidate contacts (awake, at least one bullet or
 //            non-dynamic body) are independent: b2TimeOfImpact per (world, contact) in parallel, the minimum
 //            per world through a shared-memory atomicMin.
-//   phase 2  warp 0, only lanes whose minimum is a real event (alpha < 1 - 10 eps): the reference's loop verbatim,
+//   phase 2  (k_toi_events, one warp per tile) only lanes whose minimum is a real event (alpha < 1 - 10 eps): the reference's loop verbatim,
 //            one world per lane — advance the two bodies, update the contact, build the mini-island in the
 //            body's contact-list order, b2Island::SolveTOI, synchronise the displaced fixtures, FindNewContacts,
 //            recompute the invalidated times of impact in list order (their sweeps now start at different
@@ -579,6 +579,14 @@ __device__ __forceinline__ bool ToiCandidate(int bfA, int bfB) {
     return collideA || collideB;
 }
 
+// The part of that filter that cannot change during a step (body types and bullet flags): a contact that fails it
+// can never become a candidate, can never join a TOI mini-island (b2World.cpp:806-811 admits only static, kinematic
+// or bullet neighbours) and never carries e_toiFlag.  Contacts that pass it form the per-world candidate list.
+__device__ __forceinline__ bool ToiStaticCandidate(int bfA, int bfB) {
+    return (bfA & kBodyBullet) || (bfA & kBodyTypeMask) != B2G_DYNAMIC_BODY || (bfB & kBodyBullet) ||
+           (bfB & kBodyTypeMask) != B2G_DYNAMIC_BODY;
+}
+
 // Time of impact of contact k given both sweeps (already on the same alpha0): b2World.cpp:680-709
 __device__ __forceinline__ float ContactToi(const Arena& A, int tile, int lane, const ToiCols& c, int k, const int4 a,
                                             const Sweep& sA, const Sweep& sB, float alpha0) {
@@ -613,7 +621,134 @@ __device__ __forceinline__ void ToiUpdateContact(const Arena& A, int tile, int l
 }
 
 // The reference's SolveTOI loop for one world, entered after phase 1 has cached every first-pass time of impact.
-__device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, float dt, int velIters) {
+#ifdef B2G_TOI_PROFILE
+// Diagnostic build only (tools/toi_profile.py): SM-clock cycles per section of the event loop, summed over the
+// first active lane of every warp.
+__device__ unsigned long long g_toiProf[16];
+#define TOI_T0() long long t0__ = clock64()
+#define TOI_T(slot)                                                                                  \
+    do {                                                                                             \
+        long long t1__ = clock64();                                                                  \
+        if ((__activemask() & ((1u << lane) - 1)) == 0) {                                            \
+            atomicAdd(&g_toiProf[slot], (unsigned long long)(t1__ - t0__));                          \
+            atomicAdd(&g_toiProf[8 + slot], 1ull);                                                   \
+        }                                                                                            \
+        t0__ = clock64();                                                                            \
+    } while (0)
+#define TOI_TA() long long ta__ = clock64()
+#define TOI_TB(slot)                                                                                 \
+    do {                                                                                             \
+        long long tb__ = clock64();                                                                  \
+        if ((__activemask() & ((1u << lane) - 1)) == 0) {                                            \
+            atomicAdd(&g_toiProf[slot], (unsigned long long)(tb__ - ta__));                          \
+            atomicAdd(&g_toiProf[8 + slot], 1ull);                                                   \
+        }                                                                                            \
+    } while (0)
+#else
+#define TOI_T0()
+#define TOI_T(slot)
+#define TOI_TA()
+#define TOI_TB(slot)
+#endif
+
+constexpr int kToiScan = 8;      // list entries fetched ahead per walk step
+constexpr int kToiMaxMoved = 32;  // per world and sub-step, else the ordered fallback
+constexpr int kToiMaxCand = 96;
+
+// Per-lane scratch lists of one tile in shared memory (column `lane` belongs to this lane's world).
+struct ToiLists {
+    uint16_t moved[kToiMaxMoved][kTile];
+    uint32_t cand[kToiMaxCand][kTile];
+    unsigned char exists[kToiMaxCand][kTile];
+};
+
+// b2BroadPhase::UpdatePairs + b2ContactManager::AddPair for one world by one lane, after a TOI sub-step
+// (b2World.cpp:883-885).  Same result as UpdatePairsOrdered; organised like k_sync_pairs so that an existing
+// contact is found by ONE walk over the contact array for all candidate pairs instead of one walk per pair:
+// moved proxies -> overlap candidates (min, max) -> sort + dedupe -> mark the pairs that already have a contact
+// -> AddPair for the rest in (proxyIdA, proxyIdB) order.
+__device__ __noinline__ void UpdatePairsLane(const Arena* Ap, int tile, int lane, ToiLists* L) {
+    const Arena& A = *Ap;
+    const size_t ws = (size_t)tile * kTile + lane;
+    const int np = A.proxyCount[ws];
+    Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    int nMoved = 0;
+    for (int p0 = 0; p0 < np; p0 += kToiScan) {
+        int mv[kToiScan];
+#pragma unroll
+        for (int j = 0; j < kToiScan; ++j) mv[j] = p0 + j < np ? proxyMoved[p0 + j] : 0;
+#pragma unroll
+        for (int j = 0; j < kToiScan; ++j)
+            if (mv[j]) {
+                if (nMoved < kToiMaxMoved) L->moved[nMoved][lane] = (uint16_t)(p0 + j);
+                ++nMoved;
+            }
+    }
+    if (nMoved == 0) return;
+    if (nMoved > kToiMaxMoved) { UpdatePairsOrdered(Ap, tile, lane); return; }
+    int nCand = 0;
+    for (int m = 0; m < nMoved; ++m) {
+        const int pm = L->moved[m][lane];
+        const float4 fatM = proxyFat[pm];
+        for (int q0 = 0; q0 < np; q0 += kToiScan) {
+            float4 fq[kToiScan];
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j)
+                if (q0 + j < np) fq[j] = proxyFat[q0 + j];
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j) {
+                const int q = q0 + j;
+                if (q >= np) break;
+                if (q == pm || !FatOverlap(fatM, fq[j])) continue;
+                if (nCand < kToiMaxCand) L->cand[nCand][lane] = q < pm ? ((uint32_t)q << 16 | (uint32_t)pm) : ((uint32_t)pm << 16 | (uint32_t)q);
+                ++nCand;
+            }
+        }
+    }
+    if (nCand > kToiMaxCand) { UpdatePairsOrdered(Ap, tile, lane); return; }  // the move flags are still set
+    for (int m = 0; m < nMoved; ++m) proxyMoved[L->moved[m][lane]] = 0;  // the move buffer is consumed
+    if (nCand == 0) return;
+    for (int i = 1; i < nCand; ++i) {  // std::sort by (proxyIdA, proxyIdB); the lists are short
+        const uint32_t v = L->cand[i][lane];
+        int j = i - 1;
+        while (j >= 0 && L->cand[j][lane] > v) {
+            L->cand[j + 1][lane] = L->cand[j][lane];
+            --j;
+        }
+        L->cand[j + 1][lane] = v;
+    }
+    int u = 0;
+    for (int i = 0; i < nCand; ++i) {  // the duplicate skip of UpdatePairs
+        const uint32_t v = L->cand[i][lane];
+        if (u > 0 && L->cand[u - 1][lane] == v) continue;
+        L->cand[u][lane] = v;
+        L->exists[u][lane] = 0;
+        ++u;
+    }
+    nCand = u;
+    PairCtx c = MakePairCtx(A, tile, lane);
+    for (int k0 = 0; k0 < c.nc; k0 += kToiScan) {  // which candidates already have a contact
+        uint32_t xs[kToiScan];
+#pragma unroll
+        for (int j = 0; j < kToiScan; ++j) xs[j] = k0 + j < c.nc ? (uint32_t)c.cA[k0 + j].x : 0xffffffffu;
+        for (int i = 0; i < nCand; ++i) {
+            const uint32_t v = L->cand[i][lane], vs = (v >> 16) | (v << 16);
+            bool hit = false;
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j) hit |= xs[j] == v || xs[j] == vs;
+            if (hit) L->exists[i][lane] = 1;
+        }
+    }
+    for (int i = 0; i < nCand; ++i) {
+        if (L->exists[i][lane]) continue;
+        const uint32_t v = L->cand[i][lane];
+        AddPair(c, (int)(v >> 16), (int)(v & 0xffff), true);
+    }
+    if (c.nc != c.ncAtStart) A.contactCount[ws] = c.nc;
+}
+
+__device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, float dt, int velIters, ToiLists* lists) {
     const Arena& A = *Ap;
     const size_t ws = (size_t)tile * kTile + lane;
     const ToiCols c = MakeToiCols(A, tile, lane);
@@ -623,44 +758,74 @@ __device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, 
     Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
     EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws],
                  A.NE, A.eventMask};
+    // contact indices that pass ToiStaticCandidate, ascending (k_toi); the world's contact list is that array
+    // walked backwards, so every list walk below visits the candidates from the end of this list to its start
+    Col<int> candList = col(A.toiCand, tile, A.NC, lane);
+    int nCandList = A.toiCandCount[ws];
+    Col<int> bodyProxyStart = col(A.bodyProxyStart, tile, A.NB + 1, lane);
+    Col<int> bodyProxyList = col(A.bodyProxyList, tile, A.NP, lane);
 
     for (;;) {
+        TOI_T0();
         // ---- find the first TOI (b2World.cpp:598-722): world contact list order = descending array index ----
         const int n = A.contactCount[ws];
         int minContact = -1;
         float minAlpha = 1.0f;
-        for (int k = n - 1; k >= 0; --k) {
-            int4 a = c.cA[k];
-            if ((a.z & kContactEnabled) == 0) continue;
-            if (((a.z & kContactToiCountMask) >> kContactToiCountShift) > kMaxSubSteps) continue;
-            float alpha = 1.0f;
-            if (a.z & kContactToi) {
-                alpha = c.cToi[k];
-            } else {
-                const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
-                if (!ToiCandidate(c.bodyFlags[bodyA], c.bodyFlags[bodyB])) continue;
-                // put the sweeps onto the same time interval
-                Sweep sA = LoadSweep(c, bodyA), sB = LoadSweep(c, bodyB);
-                float alpha0 = sA.alpha0;
-                if (sA.alpha0 < sB.alpha0) {
-                    alpha0 = sB.alpha0;
-                    SweepAdvance(sA, alpha0);
-                    c.bodySweep0[bodyA] = make_float4(sA.c0.x, sA.c0.y, sA.a0, sA.alpha0);
-                } else if (sB.alpha0 < sA.alpha0) {
-                    alpha0 = sA.alpha0;
-                    SweepAdvance(sB, alpha0);
-                    c.bodySweep0[bodyB] = make_float4(sB.c0.x, sB.c0.y, sB.a0, sB.alpha0);
+        // The list walks of this loop are chains of dependent global loads when written naively (load, branch,
+        // next); each walk fetches kToiScan contacts ahead into registers so that one memory latency covers
+        // kToiScan list entries.  No entry other than the one being processed is written inside a walk.
+        for (int i0 = nCandList - 1; i0 >= 0; i0 -= kToiScan) {
+            int kk[kToiScan];
+            int4 aa[kToiScan];
+            float tt[kToiScan];
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j) kk[j] = i0 - j >= 0 ? candList[i0 - j] : 0;
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j) {
+                if (i0 - j >= 0) {
+                    aa[j] = c.cA[kk[j]];
+                    tt[j] = c.cToi[kk[j]];
                 }
-                alpha = ContactToi(A, tile, lane, c, k, a, sA, sB, alpha0);
-                c.cToi[k] = alpha;
-                a.z |= kContactToi;
-                c.cA[k] = a;
             }
-            if (alpha < minAlpha) {
-                minContact = k;
-                minAlpha = alpha;
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j) {
+                if (i0 - j < 0) break;
+                const int k = kk[j];
+                int4 a = aa[j];
+                if ((a.z & kContactEnabled) == 0) continue;
+                if (((a.z & kContactToiCountMask) >> kContactToiCountShift) > kMaxSubSteps) continue;
+                float alpha = 1.0f;
+                if (a.z & kContactToi) {
+                    alpha = tt[j];
+                } else {
+                    const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+                    if (!ToiCandidate(c.bodyFlags[bodyA], c.bodyFlags[bodyB])) continue;
+                    // put the sweeps onto the same time interval
+                    Sweep sA = LoadSweep(c, bodyA), sB = LoadSweep(c, bodyB);
+                    float alpha0 = sA.alpha0;
+                    if (sA.alpha0 < sB.alpha0) {
+                        alpha0 = sB.alpha0;
+                        SweepAdvance(sA, alpha0);
+                        c.bodySweep0[bodyA] = make_float4(sA.c0.x, sA.c0.y, sA.a0, sA.alpha0);
+                    } else if (sB.alpha0 < sA.alpha0) {
+                        alpha0 = sA.alpha0;
+                        SweepAdvance(sB, alpha0);
+                        c.bodySweep0[bodyB] = make_float4(sB.c0.x, sB.c0.y, sB.a0, sB.alpha0);
+                    }
+                    TOI_TA();
+                    alpha = ContactToi(A, tile, lane, c, k, a, sA, sB, alpha0);
+                    TOI_TB(6);
+                    c.cToi[k] = alpha;
+                    a.z |= kContactToi;
+                    c.cA[k] = a;
+                }
+                if (alpha < minAlpha) {
+                    minContact = k;
+                    minAlpha = alpha;
+                }
             }
         }
+        TOI_T(0);
         if (minContact < 0 || 1.0f - 10.0f * kEpsilon < minAlpha) break;  // no more TOI events
 
         A.topoDirty[ws] = 1;  // bodies move / wake, touching flags and the contact set may change
@@ -692,6 +857,7 @@ __device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, 
         }
         WakeBody(c.bodyFlags, c.bodySweep, bA);
         WakeBody(c.bodyFlags, c.bodySweep, bB);
+        TOI_T(1);
 
         // ---- build the island (b2World.cpp:765-857) ----
         int nB = 0, nC = 0;
@@ -706,42 +872,55 @@ __device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, 
             const int body = i == 0 ? bA : bB;
             if ((c.bodyFlags[body] & kBodyTypeMask) != B2G_DYNAMIC_BODY) continue;
             // the body's contact edge list is head-inserted: newest contact (highest array index) first
-            for (int k = n - 1; k >= 0; --k) {
-                int4 a = c.cA[k];
-                const int kA = a.y & 0xffff, kB = (a.y >> 16) & 0xffff;
-                if (kA != body && kB != body) continue;
-                if (nB == kToiBodyCap) break;
-                if (nC == kMaxToiContacts) break;
-                if (a.z & kContactToiIsland) continue;
-                const int other = kA == body ? kB : kA;
-                const int of = c.bodyFlags[other];
-                // only static, kinematic or bullet bodies
-                if ((of & kBodyTypeMask) == B2G_DYNAMIC_BODY && (c.bodyFlags[body] & kBodyBullet) == 0 && (of & kBodyBullet) == 0)
-                    continue;
-                // tentatively advance the body to the TOI
-                const float4 backupSw = c.bodySweep[other], backupSw0 = c.bodySweep0[other];
-                if ((of & kBodyToiIsland) == 0) BodyAdvance(c, other, minAlpha);
-                ToiUpdateContact(A, tile, lane, c, ev, k);
-                a = c.cA[k];
-                if ((a.z & kContactEnabled) == 0 || (a.z & kContactTouching) == 0) {
-                    float4 sw = backupSw;
-                    sw.w = c.bodySweep[other].w;  // m_sleepTime is not part of b2Sweep
-                    c.bodySweep[other] = sw;
-                    c.bodySweep0[other] = backupSw0;
-                    SynchronizeTransform(c, other);
-                    continue;
+            bool full = false;
+            for (int i0 = nCandList - 1; i0 >= 0 && !full; i0 -= kToiScan) {
+                int kk[kToiScan];
+                int4 aa[kToiScan];
+#pragma unroll
+                for (int j = 0; j < kToiScan; ++j) kk[j] = i0 - j >= 0 ? candList[i0 - j] : 0;
+#pragma unroll
+                for (int j = 0; j < kToiScan; ++j)
+                    if (i0 - j >= 0) aa[j] = c.cA[kk[j]];
+#pragma unroll
+                for (int j = 0; j < kToiScan; ++j) {
+                    if (i0 - j < 0) break;
+                    const int k = kk[j];
+                    int4 a = aa[j];
+                    const int kA = a.y & 0xffff, kB = (a.y >> 16) & 0xffff;
+                    if (kA != body && kB != body) continue;
+                    if (nB == kToiBodyCap || nC == kMaxToiContacts) { full = true; break; }
+                    if (a.z & kContactToiIsland) continue;
+                    const int other = kA == body ? kB : kA;
+                    const int of = c.bodyFlags[other];
+                    // only static, kinematic or bullet bodies
+                    if ((of & kBodyTypeMask) == B2G_DYNAMIC_BODY && (c.bodyFlags[body] & kBodyBullet) == 0 && (of & kBodyBullet) == 0)
+                        continue;
+                    // tentatively advance the body to the TOI
+                    const float4 backupSw = c.bodySweep[other], backupSw0 = c.bodySweep0[other];
+                    if ((of & kBodyToiIsland) == 0) BodyAdvance(c, other, minAlpha);
+                    ToiUpdateContact(A, tile, lane, c, ev, k);
+                    a = c.cA[k];
+                    if ((a.z & kContactEnabled) == 0 || (a.z & kContactTouching) == 0) {
+                        float4 sw = backupSw;
+                        sw.w = c.bodySweep[other].w;  // m_sleepTime is not part of b2Sweep
+                        c.bodySweep[other] = sw;
+                        c.bodySweep0[other] = backupSw0;
+                        SynchronizeTransform(c, other);
+                        continue;
+                    }
+                    a.z |= kContactToiIsland;
+                    c.cA[k] = a;
+                    toiContacts[nC++] = k;
+                    const int of2 = c.bodyFlags[other];
+                    if (of2 & kBodyToiIsland) continue;
+                    c.bodyFlags[other] = of2 | kBodyToiIsland;
+                    if ((of2 & kBodyTypeMask) != B2G_STATIC_BODY) WakeBody(c.bodyFlags, c.bodySweep, other);
+                    toiBodies[nB++] = other;
                 }
-                a.z |= kContactToiIsland;
-                c.cA[k] = a;
-                toiContacts[nC++] = k;
-                const int of2 = c.bodyFlags[other];
-                if (of2 & kBodyToiIsland) continue;
-                c.bodyFlags[other] = of2 | kBodyToiIsland;
-                if ((of2 & kBodyTypeMask) != B2G_STATIC_BODY) WakeBody(c.bodyFlags, c.bodySweep, other);
-                toiBodies[nB++] = other;
             }
         }
 
+        TOI_T(2);
         // ---- b2Island::SolveTOI (b2Island.cpp:385-515): positions / velocities live in the body arrays ----
         const float h = (1.0f - minAlpha) * dt;
         for (int i = 0; i < nC; ++i) InitVelocityConstraint(A, tile, lane, vc, i, toiContacts[i], false, 1.0f);  // solver ctor
@@ -796,6 +975,7 @@ __device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, 
             }
         }
 
+        TOI_T(3);
         // ---- reset island flags, synchronise broad-phase proxies, invalidate TOIs (b2World.cpp:868-886) ----
         for (int i = 0; i < nB; ++i) {
             const int b = toiBodies[i];
@@ -803,24 +983,47 @@ __device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, 
             if ((f & kBodyTypeMask) == B2G_DYNAMIC_BODY) f |= kBodyToiMoved;
             c.bodyFlags[b] = f;
         }
-        const int np = A.proxyCount[ws];
-        for (int p = 0; p < np; ++p) {
-            const int pi = c.proxyInfo[p];
-            const int fixture = pi & 0xffff, child = (pi >> 16) & 0xffff;
-            const int fi = fixtureInfo[fixture];
-            const int body = fi & 0xffff;
-            if (c.bodyFlags[body] & kBodyToiMoved) SynchronizeProxy(A, tile, lane, p, fixture, child, fi, body);
-        }
-        for (int k = 0; k < n; ++k) {
-            int4 a = c.cA[k];
-            if ((a.z & (kContactToi | kContactToiIsland)) == 0) continue;
-            if ((c.bodyFlags[a.y & 0xffff] | c.bodyFlags[(a.y >> 16) & 0xffff]) & kBodyToiMoved) {
-                a.z &= ~(kContactToi | kContactToiIsland);
-                c.cA[k] = a;
+        for (int i = 0; i < nB; ++i) {  // b2Body::SynchronizeFixtures of the displaced bodies
+            const int b = toiBodies[i];
+            if ((c.bodyFlags[b] & kBodyToiMoved) == 0) continue;
+            const int pEnd = bodyProxyStart[b + 1];
+            for (int j = bodyProxyStart[b]; j < pEnd; ++j) {
+                const int p = bodyProxyList[j];
+                const int pi = c.proxyInfo[p];
+                const int fi = fixtureInfo[pi & 0xffff];
+                SynchronizeProxy(A, tile, lane, p, pi & 0xffff, (pi >> 16) & 0xffff, fi, b);
             }
         }
+        TOI_TA();
+        for (int i0 = 0; i0 < nCandList; i0 += kToiScan) {  // only candidates carry e_toiFlag / the TOI island flag
+            int kk[kToiScan];
+            int4 aa[kToiScan];
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j) kk[j] = i0 + j < nCandList ? candList[i0 + j] : 0;
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j)
+                if (i0 + j < nCandList) aa[j] = c.cA[kk[j]];
+#pragma unroll
+            for (int j = 0; j < kToiScan; ++j) {
+                if (i0 + j >= nCandList) break;
+                const int k = kk[j];
+                int4 a = aa[j];
+                if ((a.z & (kContactToi | kContactToiIsland)) == 0) continue;
+                if ((c.bodyFlags[a.y & 0xffff] | c.bodyFlags[(a.y >> 16) & 0xffff]) & kBodyToiMoved) {
+                    a.z &= ~(kContactToi | kContactToiIsland);
+                    c.cA[k] = a;
+                }
+            }
+        }
+        TOI_TB(7);
         for (int i = 0; i < nB; ++i) c.bodyFlags[toiBodies[i]] &= ~kBodyToiMoved;
-        UpdatePairsOrdered(Ap, tile, lane);  // m_contactManager.FindNewContacts()
+        TOI_T(4);
+        UpdatePairsLane(Ap, tile, lane, lists);  // m_contactManager.FindNewContacts()
+        for (int k = n, nNew = A.contactCount[ws]; k < nNew; ++k) {  // new contacts sit at the head of the list
+            const int4 a = c.cA[k];
+            if (ToiStaticCandidate(c.bodyFlags[a.y & 0xffff], c.bodyFlags[(a.y >> 16) & 0xffff])) candList[nCandList++] = k;
+        }
+        TOI_T(5);
     }
 }
 
@@ -828,6 +1031,7 @@ __device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, 
 // k_toi — b2World::SolveTOI for every world with continuous physics
 // =================================================================================================
 __global__ void __launch_bounds__(kToiWarps * 32) k_toi(Arena A, float dt, int velIters) {
+    extern __shared__ unsigned char sIsCand[];  // [NC][kTile]: contact passes ToiStaticCandidate
     __shared__ unsigned int sMinAlpha[kTile];
     const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
@@ -863,9 +1067,11 @@ __global__ void __launch_bounds__(kToiWarps * 32) k_toi(Arena A, float dt, int v
         int4 a = c.cA[k];
         const int z0 = a.z;
         a.z &= ~(kContactToi | kContactToiIsland | kContactToiCountMask);
+        const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
+        const int bfA = c.bodyFlags[bodyA], bfB = c.bodyFlags[bodyB];
+        sIsCand[k * kTile + lane] = ToiStaticCandidate(bfA, bfB) ? 1 : 0;
         if (a.z & kContactEnabled) {
-            const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
-            if (ToiCandidate(c.bodyFlags[bodyA], c.bodyFlags[bodyB])) {
+            if (ToiCandidate(bfA, bfB)) {
                 Sweep sA = LoadSweep(c, bodyA), sB = LoadSweep(c, bodyB);
                 sA.alpha0 = 0.0f;
                 sB.alpha0 = 0.0f;
@@ -879,11 +1085,29 @@ __global__ void __launch_bounds__(kToiWarps * 32) k_toi(Arena A, float dt, int v
     }
     if (myMin < 1.0f) atomicMin(&sMinAlpha[lane], __float_as_uint(myMin));  // alpha >= 0: uint order == float order
     __syncthreads();
-    if (warp != 0 || !live) return;
+    if (warp == 0) {
+        const float minAlpha = live ? __uint_as_float(sMinAlpha[lane]) : 1.0f;
+        A.toiMinAlpha[ws] = minAlpha;
+        if (!(1.0f - 10.0f * kEpsilon < minAlpha)) {  // k_toi_events will run this world: give it the candidate list
+            Col<int> candList = col(A.toiCand, tile, A.NC, lane);
+            int m = 0;
+            for (int k = 0; k < n; ++k)
+                if (sIsCand[k * kTile + lane]) candList[m++] = k;
+            A.toiCandCount[ws] = m;
+        }
+    }
+}
 
-    // ---- phase 2: worlds with a TOI event run the reference's loop ----
-    if (1.0f - 10.0f * kEpsilon < __uint_as_float(sMinAlpha[lane])) return;
-    SolveToiWorld(&A, tile, lane, dt, velIters);
+// k_toi_events — phase 2: worlds with a TOI event run the reference's loop, one world per lane.  A CTA is one
+// warp (one tile) so that many tiles are resident per SM: the loop is a chain of dependent global loads and the
+// only way to hide them is other tiles' warps.
+__global__ void __launch_bounds__(32) k_toi_events(Arena A, float dt, int velIters) {
+    __shared__ ToiLists lists;
+    const int tile = blockIdx.x, lane = threadIdx.x;
+    const size_t ws = (size_t)tile * kTile + lane;
+    if (tile * kTile + lane >= A.numWorlds) return;
+    if (1.0f - 10.0f * kEpsilon < A.toiMinAlpha[ws]) return;
+    SolveToiWorld(&A, tile, lane, dt, velIters, &lists);
 }
 
 }  // namespace b2g

@@ -46,7 +46,30 @@ enum {
 enum { B2GPU_EVENT_BEGIN = 0, B2GPU_EVENT_END = 1, B2GPU_EVENT_PRESOLVE = 2, B2GPU_EVENT_POSTSOLVE = 3 };
 
 /* Per-world status bits (b2gpu_batch_download_field(B2GPU_F_STATUS)). */
-enum { B2GPU_STATUS_CONTACT_OVERFLOW = 1, B2GPU_STATUS_EVENT_OVERFLOW = 2 };
+enum { B2GPU_STATUS_CONTACT_OVERFLOW = 1, B2GPU_STATUS_EVENT_OVERFLOW = 2, B2GPU_STATUS_BAD_COMMAND = 4 };
+
+/* Between-step body edits: one record per call the reference's user would make on a b2Body
+ * between two Steps.  Box2D/Dynamics/b2Body.h:738-833 (Apply*), :408-467 (SetLinearVelocity, SetAngularVelocity,
+ * SetAwake), Box2D/Dynamics/b2Body.cpp:418-440 (SetTransform). */
+enum {
+    B2GPU_CMD_APPLY_FORCE = 0,           /* v = force, p = world point        b2Body::ApplyForce(force, point, wake) */
+    B2GPU_CMD_APPLY_FORCE_TO_CENTER = 1, /* v = force                         b2Body::ApplyForceToCenter(force, wake) */
+    B2GPU_CMD_APPLY_TORQUE = 2,          /* v[0] = torque                     b2Body::ApplyTorque(torque, wake) */
+    B2GPU_CMD_APPLY_LINEAR_IMPULSE = 3,  /* v = impulse, p = world point      b2Body::ApplyLinearImpulse(impulse, point, wake) */
+    B2GPU_CMD_APPLY_ANGULAR_IMPULSE = 4, /* v[0] = impulse                    b2Body::ApplyAngularImpulse(impulse, wake) */
+    B2GPU_CMD_SET_LINEAR_VELOCITY = 5,   /* v = velocity                      b2Body::SetLinearVelocity(v) */
+    B2GPU_CMD_SET_ANGULAR_VELOCITY = 6,  /* v[0] = omega                      b2Body::SetAngularVelocity(omega) */
+    B2GPU_CMD_SET_TRANSFORM = 7,         /* v = position, p[0] = angle        b2Body::SetTransform(position, angle) */
+    B2GPU_CMD_SET_AWAKE = 8,             /* wake = flag                       b2Body::SetAwake(flag) */
+    B2GPU_CMD_COUNT
+};
+typedef struct b2gpu_body_command {
+    int32_t world, body; /* world index in the batch, body index = creation order within the world */
+    int32_t op;          /* B2GPU_CMD_* */
+    int32_t wake;        /* the call's `wake` argument (SET_AWAKE: the flag) */
+    float v[2];
+    float p[2];
+} b2gpu_body_command;
 
 typedef struct b2gpu_batch b2gpu_batch;
 
@@ -142,6 +165,18 @@ int b2gpu_batch_sync(b2gpu_batch* batch);
  * out[(world * maxBodies + body) * 4] = p.x, p.y, q.s, q.c. */
 int b2gpu_batch_apply_forces(b2gpu_batch* batch, const float* forces);
 int b2gpu_batch_read_transforms(b2gpu_batch* batch, float* out);
+
+/* Applies `count` body commands between two steps.  Commands of one world are applied in array order (the order
+ * the reference's user would have made the calls in); different worlds are independent and run in parallel.
+ * The array may be in any world order (it is grouped by world on the host, stably).  A command naming a body
+ * that does not exist sets B2GPU_STATUS_BAD_COMMAND on its world and is skipped.  Asynchronous on the batch's
+ * stream (the command array is consumed before the call returns). */
+int b2gpu_batch_body_commands(b2gpu_batch* batch, const b2gpu_body_command* commands, int64_t count);
+
+/* Observation readback for every body in one call: out[(world * maxBodies + body) * 8] = position.xy (GetPosition),
+ * angle (GetAngle), awake (1.0 / 0.0, IsAwake), linearVelocity.xy, angularVelocity, sleep time.  Replaces the per-body getters of
+ * Box2D/Dynamics/b2Body.h:500-560 for an RL / game-server caller.  Synchronises. */
+int b2gpu_batch_read_body_state(b2gpu_batch* batch, float* out);
 
 /* CUDA-event time of the last b2gpu_batch_step_n in milliseconds, and per-kernel times of a profiled step. */
 int b2gpu_batch_last_step_ms(b2gpu_batch* batch, float* ms);

@@ -1075,6 +1075,76 @@ void b2o_world_step(void* h, float dt, int velIters, int posIters) {
     }
 }
 
+/* Between-step body edits (ops = B2GPU_CMD_* of include/b2gpu.h) — Box2D/Dynamics/b2Body.h:738-833 (Apply*),
+ * :408-467 (SetLinearVelocity / SetAngularVelocity), :634-653 (SetAwake), b2Body.cpp:418-440 (SetTransform). */
+void b2o_world_body_command(void* h, int body, int op, int wake, float vx, float vy, float px, float py) {
+    world_t* w = (world_t*)h;
+    if (body < 0 || body >= w->nb) return;
+    body_t* b = &w->bodies[body];
+    v2 v = V2(vx, vy), p = V2(px, py);
+    switch (op) {
+        case 0: case 1: case 2:
+            if (b->type != B2G_DYNAMIC_BODY) return;
+            if (wake && (b->flags & BF_AWAKE) == 0) set_awake(b, 1);
+            if ((b->flags & BF_AWAKE) == 0) return;
+            if (op == 2) { b->torque += vx; return; }
+            b->force = v2_add(b->force, v);
+            if (op == 0) b->torque += v2_cross(v2_sub(p, b->c), v);
+            return;
+        case 3: case 4:
+            if (b->type != B2G_DYNAMIC_BODY) return;
+            if (wake && (b->flags & BF_AWAKE) == 0) set_awake(b, 1);
+            if ((b->flags & BF_AWAKE) == 0) return;
+            if (op == 4) { b->w += b->invI * vx; return; }
+            b->v = v2_add(b->v, v2_scale(b->invMass, v));
+            b->w += b->invI * v2_cross(v2_sub(p, b->c), v);
+            return;
+        case 5:
+            if (b->type == B2G_STATIC_BODY) return;
+            if (v2_dot(v, v) > 0.0f) set_awake(b, 1);
+            b->v = v;
+            return;
+        case 6:
+            if (b->type == B2G_STATIC_BODY) return;
+            if (vx * vx > 0.0f) set_awake(b, 1);
+            b->w = vx;
+            return;
+        case 8:
+            set_awake(b, wake);
+            return;
+        case 7: {
+            b->xf.q = rot_set(px);
+            b->xf.p = v;
+            b->c = xf_mul(b->xf, b->localCenter);
+            b->a = px;
+            b->c0 = b->c;
+            b->a0 = px;
+            for (int fi = w->nf - 1; fi >= 0; --fi) {
+                fixture_t* f = &w->fixtures[fi];
+                if (f->body != body) continue;
+                for (int k = 0; k < f->proxyCount; ++k) {
+                    proxy_t* pr = &w->proxies[f->firstProxy + k];
+                    aabb a1, box;
+                    b2o_shape_aabb(&f->shape, b->xf, pr->child, &a1);
+                    box.lo = v2_min(a1.lo, a1.lo);
+                    box.hi = v2_max(a1.hi, a1.hi);
+                    v2 displacement = v2_sub(b->xf.p, b->xf.p);
+                    if (aabb_contains(pr->fat, box)) continue;
+                    v2 r = V2(B2O_AABB_EXTENSION, B2O_AABB_EXTENSION);
+                    box.lo = v2_sub(box.lo, r);
+                    box.hi = v2_add(box.hi, r);
+                    v2 d = v2_scale(B2O_AABB_MULTIPLIER, displacement);
+                    if (d.x < 0.0f) box.lo.x += d.x; else box.hi.x += d.x;
+                    if (d.y < 0.0f) box.lo.y += d.y; else box.hi.y += d.y;
+                    pr->fat = box;
+                    buffer_move(w, f->firstProxy + k);
+                }
+            }
+            return;
+        }
+    }
+}
+
 /* ---- dumps: same formats as oracle/ref_harness.cpp ------------------------------------------ */
 void b2o_world_record_events(void* h, int on) { ((world_t*)h)->recordEvents = on; }
 int b2o_world_body_count(void* h) { return ((world_t*)h)->nb; }

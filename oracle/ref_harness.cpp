@@ -194,6 +194,24 @@ void ref_world_step(void* h, float dt, int velIters, int posIters) {
     rw->world->Step(dt, velIters, posIters);
 }
 
+// Between-step body edits, ops = B2GPU_CMD_* of include/b2gpu.h: the call a user of the reference makes on a b2Body.
+void ref_world_body_command(void* h, int body, int op, int wake, float vx, float vy, float px, float py) {
+    RefWorld* rw = (RefWorld*)h;
+    if (body < 0 || body >= (int)rw->bodies.size()) return;
+    b2Body* b = rw->bodies[body];
+    switch (op) {
+        case 0: b->ApplyForce(b2Vec2(vx, vy), b2Vec2(px, py), wake != 0); break;
+        case 1: b->ApplyForceToCenter(b2Vec2(vx, vy), wake != 0); break;
+        case 2: b->ApplyTorque(vx, wake != 0); break;
+        case 3: b->ApplyLinearImpulse(b2Vec2(vx, vy), b2Vec2(px, py), wake != 0); break;
+        case 4: b->ApplyAngularImpulse(vx, wake != 0); break;
+        case 5: b->SetLinearVelocity(b2Vec2(vx, vy)); break;
+        case 6: b->SetAngularVelocity(vx); break;
+        case 7: b->SetTransform(b2Vec2(vx, vy), px); break;
+        case 8: b->SetAwake(wake != 0); break;
+    }
+}
+
 int ref_world_body_count(void* h) { return (int)((RefWorld*)h)->bodies.size(); }
 int ref_world_contact_count(void* h) { return ((RefWorld*)h)->world->GetContactCount(); }
 int ref_world_proxy_count(void* h) { return ((RefWorld*)h)->world->GetProxyCount(); }

@@ -59,6 +59,8 @@ def lib(kind="ref"):
         L.ref_world_get_proxies.restype = C.c_int
         L.ref_world_get_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_world_get_events.restype = C.c_int
+        L.ref_world_body_command.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.ref_world_body_command.restype = None
         L.ref_polygon_build.argtypes = [C.POINTER(FixtureDef), C.c_void_p, C.c_void_p]
         L.ref_polygon_build.restype = C.c_int
         for f in ("ref_collide_polygons", "ref_collide_circles", "ref_collide_polygon_circle",
@@ -96,6 +98,10 @@ class RefWorld:
 
     def step(self, dt, vel_iters, pos_iters):
         self.L.ref_world_step(self.h, dt, vel_iters, pos_iters)
+
+    def command(self, body, op, wake=1, v=(0.0, 0.0), p=(0.0, 0.0)):
+        """One between-step b2Body call (op = B2GPU_CMD_* of include/b2gpu.h)."""
+        self.L.ref_world_body_command(self.h, body, op, wake, v[0], v[1], p[0], p[1])
 
     def bodies(self) -> np.ndarray:
         """[nb,16] float32: xf.p(2) q.s q.c | c(2) a | v(2) w | awake mass I localCenter(2) pad."""
