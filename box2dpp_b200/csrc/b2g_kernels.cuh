@@ -155,6 +155,8 @@ __device__ __forceinline__ void ShapeAABB(const float* w, int shapeType, const C
     }
 }
 
+#include "b2g_distance.cuh"
+
 __device__ __forceinline__ bool FatOverlap(float4 a, float4 b) {  // b2TestOverlap(AABB, AABB), b2Collision.h:278-291
     float d1x = b.x - a.z, d1y = b.y - a.w;
     float d2x = a.x - b.z, d2y = a.y - b.w;

@@ -43,6 +43,7 @@ enum : int {
     kContactIsland = 1, kContactTouching = 2, kContactEnabled = 4, kContactFilter = 8, kContactDead = 16,
     kContactToi = 32,         // e_toiFlag: contactToi[k] holds a valid cached time of impact
     kContactToiIsland = 64,   // e_islandFlag inside b2World::SolveTOI
+    kContactSensor = 128,     // fixtureA->IsSensor() || fixtureB->IsSensor(), fixed when the contact is created
     kContactToiCountShift = 8, kContactToiCountMask = 0xf << 8,  // m_toiCount (0 .. b2_maxSubSteps + 1)
 };
 // per-world status bits surfaced by b2gpu_batch_read_status
