@@ -379,7 +379,6 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
     auto& CV = out.f[B2GPU_F_CHAIN_VERTS];
     for (int i = 0; i < nf; ++i) {
         const b2g_fixture_def& d = s.fixtures[i];
-        if (d.isSensor) { err = "sensor fixtures are not on the device path"; return B2GPU_ERR_UNSUPPORTED; }
         if (d.body < 0 || d.body >= nb) { err = "fixture references a body that does not exist"; return B2GPU_ERR_INVALID; }
         HostShape& sh = fshapes[i];
         int childCount = BuildShape(sh, d, s.vertices);
@@ -401,7 +400,7 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
             shapeWordsUsed += (int)words.size();
             shapeDedup[words] = offset;
         }
-        put(out.f[B2GPU_F_FIXTURE_INFO], i, d.body | (sh.type << 16));
+        put(out.f[B2GPU_F_FIXTURE_INFO], i, d.body | (sh.type << 16) | ((d.isSensor ? 1 : 0) << 18));
         put(out.f[B2GPU_F_FIXTURE_SHAPE], i, offset);
         put(out.f[B2GPU_F_FIXTURE_MAT], (size_t)i * 2, d.friction);
         put(out.f[B2GPU_F_FIXTURE_MAT], (size_t)i * 2 + 1, d.restitution);

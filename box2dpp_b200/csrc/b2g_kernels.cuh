@@ -259,8 +259,17 @@ __device__ __forceinline__ int UpdateOne(const Arena& A, int tile, int lane, int
     m.pointCount = 0;
     m.type = a.w & 0xff;
     const int2 so = col(A.contactS, tile, A.NC, lane)[k];
-    EvaluateContact(A, tile, lane, &m, (a.w >> 16) & 0xf, so.x, so.y, proxyA, LoadXf(bodyXf, bodyA), LoadXf(bodyXf, bodyB));
-    const bool touching = m.pointCount > 0;
+    bool touching;
+    if (flags & kContactSensor) {
+        // sensors don't generate manifolds: touching = b2TestOverlap(shapeA, indexA, shapeB, indexB, xfA, xfB)
+        Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+        const int childA = (proxyInfo[proxyA] >> 16) & 0xffff, childB = (proxyInfo[(a.x >> 16) & 0xffff] >> 16) & 0xffff;
+        touching = TestOverlapShapes(&A, tile, lane, so.x, (a.w >> 16) & 3, childA, LoadXf(bodyXf, bodyA), so.y, (a.w >> 18) & 3,
+                                     childB, LoadXf(bodyXf, bodyB));
+    } else {
+        EvaluateContact(A, tile, lane, &m, (a.w >> 16) & 0xf, so.x, so.y, proxyA, LoadXf(bodyXf, bodyA), LoadXf(bodyXf, bodyB));
+        touching = m.pointCount > 0;
+    }
     if (m.pointCount > 0) {
         float nI = 0.0f, tI = 0.0f;
         if (pointCountOld > 0 && oldKey0 == m.key0) { nI = oldN0; tI = oldT0; }
@@ -391,7 +400,8 @@ __global__ void __launch_bounds__(kCollideWarps * 32, 2) k_collide(Arena A) {
             anyDead = true;
             continue;
         }
-        if (touching != wasTouching) {
+        const bool sensor = (a.z & kContactSensor) != 0;
+        if (touching != wasTouching && !sensor) {  // the wake-up sits in Update's non-sensor branch (b2Contact.cpp:225-229)
             anyWake |= WakeBody(bodyFlags, bodySweep, bodyA);
             anyWake |= WakeBody(bodyFlags, bodySweep, bodyB);
         }
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(kCollideWarps * 32, 2) k_collide(Arena A) {
             int fA = pa & 0xffff, chA = (pa >> 16) & 0xffff, fB = pb & 0xffff, chB = (pb >> 16) & 0xffff;
             if (!wasTouching && touching) ev.push(kEventBegin, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
             if (wasTouching && !touching) ev.push(kEventEnd, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
-            if (touching) ev.push(kEventPreSolve, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
+            if (touching && !sensor) ev.push(kEventPreSolve, fA, chA, fB, chB, pointCount, make_float4(0, 0, 0, 0));
         }
     }
     if (anyDead) {  // stable erase keeps every list in the reference's order
@@ -490,7 +500,7 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
         const int4 a = cA[k];
         sPair[(size_t)(2 * k) * L + l] = (uint16_t)(a.y & 0xffff);
         sPair[(size_t)(2 * k + 1) * L + l] = (uint16_t)((a.y >> 16) & 0xffff);
-        sCF[(size_t)k * L + l] = ((a.z & kContactEnabled) && (a.z & kContactTouching)) ? kIcEligible : 0;
+        sCF[(size_t)k * L + l] = ((a.z & kContactEnabled) && (a.z & kContactTouching) && !(a.z & kContactSensor)) ? kIcEligible : 0;
     }
     for (int b = t / L; b < nb; b += stride) {
         const int f = bodyFlags[b];
@@ -1262,11 +1272,15 @@ __device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB, bool
     float restitution = matA.y > matB.y ? matA.y : matB.y;       // b2MixRestitution
     int k = c.nc++;
     c.A.topoDirty[c.ws] = 1;
-    c.cA[k] = make_int4(proxyA | (proxyB << 16), bodyA | (bodyB << 16), kContactEnabled, (tA | (tB << 2)) << 16);
+    const bool sensor = ((fiA | fiB) >> 18 & 1) != 0;
+    c.cA[k] = make_int4(proxyA | (proxyB << 16), bodyA | (bodyB << 16), kContactEnabled | (sensor ? kContactSensor : 0),
+                        (tA | (tB << 2)) << 16);
     c.cK[k] = make_int4(0, 0, __float_as_int(friction), __float_as_int(restitution));
     c.cS[k] = make_int2(c.fixtureShape[fixtureA], c.fixtureShape[fixtureB]);
-    WakeBody(c.bodyFlags, c.bodySweep, bodyA);
-    WakeBody(c.bodyFlags, c.bodySweep, bodyB);
+    if (!sensor) {  // wake up the bodies (b2ContactManager.cpp:291-295)
+        WakeBody(c.bodyFlags, c.bodySweep, bodyA);
+        WakeBody(c.bodyFlags, c.bodySweep, bodyB);
+    }
 }
 
 // b2Fixture::Synchronize for one proxy (Dynamics/b2Fixture.cpp:154-177) + b2DynamicTree::MoveProxy's fat-AABB rule

@@ -758,7 +758,8 @@ __device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, 
         UpdatePairsLane(Ap, tile, lane, lists);  // m_contactManager.FindNewContacts()
         for (int k = n, nNew = A.contactCount[ws]; k < nNew; ++k) {  // new contacts sit at the head of the list
             const int4 a = c.cA[k];
-            if (ToiStaticCandidate(c.bodyFlags[a.y & 0xffff], c.bodyFlags[(a.y >> 16) & 0xffff])) candList[nCandList++] = k;
+            if ((a.z & kContactSensor) == 0 && ToiStaticCandidate(c.bodyFlags[a.y & 0xffff], c.bodyFlags[(a.y >> 16) & 0xffff]))
+                candList[nCandList++] = k;
         }
         TOI_T(5);
     }
@@ -806,8 +807,9 @@ __global__ void __launch_bounds__(kToiWarps * 32) k_toi(Arena A, float dt, int v
         a.z &= ~(kContactToi | kContactToiIsland | kContactToiCountMask);
         const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
         const int bfA = c.bodyFlags[bodyA], bfB = c.bodyFlags[bodyB];
-        sIsCand[k * kTile + lane] = ToiStaticCandidate(bfA, bfB) ? 1 : 0;
-        if (a.z & kContactEnabled) {
+        const bool sensor = (a.z & kContactSensor) != 0;  // b2World.cpp:632-636: sensors never take part
+        sIsCand[k * kTile + lane] = (!sensor && ToiStaticCandidate(bfA, bfB)) ? 1 : 0;
+        if ((a.z & kContactEnabled) && !sensor) {
             if (ToiCandidate(bfA, bfB)) {
                 Sweep sA = LoadSweep(c, bodyA), sB = LoadSweep(c, bodyB);
                 sA.alpha0 = 0.0f;

@@ -339,6 +339,33 @@ def bullets(seed: int, flags=WORLD_DEFAULT, shots=6) -> Scene:
     return s
 
 
+def sensors(seed: int, flags=WORLD_DEFAULT, bodies=14) -> Scene:
+    """Sensor scene (SURVEY.md §8 a5, the sensor branch of b2Contact::Update): static sensor zones (box, circle,
+    and one on an edge-ground body) that dynamic circles / boxes fall through, and dynamic bodies that carry a
+    sensor halo next to their solid fixture, so sensor-vs-solid and sensor-vs-sensor pairs both occur.
+    All randomness from LCG(seed)."""
+    rng = LCG(seed)
+    s = Scene((0.0, -10.0), flags)
+    g = s.create_body(STATIC_BODY, (0.0, 0.0))
+    s.create_edge(g, (-20.0, 0.0), (20.0, 0.0))
+    s.create_box(g, 5.0, 1.0, center=(-4.0, 4.0), angle=0.2, sensor=True)       # tilted sensor slab
+    s.create_circle(g, 2.5, p=(6.0, 3.0), sensor=True)                          # sensor disc
+    s.create_edge(g, (-12.0, 1.5), (12.0, 1.5), sensor=True)                    # sensor trip wire
+    z = s.create_body(KINEMATIC_BODY, (0.0, 7.0), linear_velocity=(1.0, 0.0), angular_velocity=0.5)
+    s.create_box(z, 3.0, 0.5, sensor=True)                                      # moving sensor
+    for k in range(bodies):
+        px = float(F32(-9.0 + 1.5 * k) + F32(rng.uniform(0.0, 0.5)))
+        py = float(F32(6.0 + 1.2 * (k % 4)) + F32(rng.uniform(0.0, 1.0)))
+        b = s.create_body(DYNAMIC_BODY, (px, py), angle=rng.uniform(-1.0, 1.0))
+        if k % 3 == 0:
+            s.create_circle(b, rng.uniform(0.25, 0.6), density=1.0, restitution=0.2)
+        else:
+            s.create_box(b, rng.uniform(0.25, 0.6), rng.uniform(0.25, 0.6), density=1.0, friction=0.3)
+        if k % 2 == 0:
+            s.create_circle(b, rng.uniform(0.9, 1.6), sensor=True)              # halo around the solid fixture
+    return s
+
+
 class SceneBatch:
     """Many worlds that share fixtures/vertices and differ only in their body definitions.
 

@@ -177,6 +177,9 @@ WORLD_CASES = {
     "mixed_seed2_default": (lambda: S.mixed(2), 300, 8, 3),
     "bullets_seed1_default": (lambda: S.bullets(1), 240, 8, 3),
     "bullets_seed3_default_nosleep": (lambda: S.bullets(3, flags=S.WORLD_DEFAULT & ~S.WORLD_ALLOW_SLEEP), 240, 6, 2),
+    # sensor fixtures (b2Contact::Update's b2TestOverlap branch); live-reference only, like continuous physics
+    "sensors_seed1_default": (lambda: S.sensors(1), 300, 8, 3),
+    "sensors_seed2_default_noccd": (lambda: S.sensors(2, flags=NOCCD), 300, 6, 2),
 }
 # scenes the C restatement can run (continuous physics off); the device path runs every case
 NOCCD_CASES = [k for k in WORLD_CASES if "default" not in k and "_ccd_" not in k]

@@ -128,6 +128,19 @@ def test_toi_generic_solver_and_mixed_flags(oracles):
     run_parity(oracles, scenes, 150, 8, 3, check_every=5, generic_solver=True)
 
 
+def test_sensors_every_step(oracles):
+    # sensor fixtures (b2Contact::Update's b2TestOverlap branch): Begin/End without PreSolve/PostSolve, no wake-ups,
+    # never in an island or a TOI; with and without continuous physics, sleeping allowed, mixed with solid worlds
+    _need_ref(oracles)
+    scenes = [S.sensors(s, flags=(S.WORLD_DEFAULT if s % 2 else NOCCD)) for s in range(6)] + [S.bullets(4), S.mixed(1)]
+    run_parity(oracles, scenes, 320, 8, 3)
+
+
+def test_sensors_generic_solver(oracles):
+    _need_ref(oracles)
+    run_parity(oracles, [S.sensors(7), S.sensors(8, flags=NOCCD)], 200, 6, 2, check_every=4, generic_solver=True)
+
+
 def test_replicated_worlds_identical(oracles):
     sc = S.pyramid(10, flags=NOCCD)
     batch = WorldBatch(sc, replicate=70)
