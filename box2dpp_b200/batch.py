@@ -65,6 +65,12 @@ BODY_COMMAND_DTYPE = np.dtype([("world", "<i4"), ("body", "<i4"), ("op", "<i4"),
  CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE) = range(9)
 
 
+AABB_QUERY_DTYPE = np.dtype([("world", "<i4"), ("lower", "<f4", 2), ("upper", "<f4", 2)])       # b2gpu_aabb_query
+RAY_DTYPE = np.dtype([("world", "<i4"), ("p1", "<f4", 2), ("p2", "<f4", 2), ("maxFraction", "<f4")])  # b2gpu_ray
+RAY_HIT_DTYPE = np.dtype([("fixture", "<i4"), ("child", "<i4"), ("fraction", "<f4"), ("point", "<f4", 2),
+                          ("normal", "<f4", 2)])                                                      # b2gpu_ray_hit
+
+
 def lib():
     """Load libb2gpu.so.  Raises (never falls back) when the CUDA extension has not been built."""
     global _lib
@@ -86,6 +92,8 @@ def lib():
         L.b2gpu_batch_read_transforms.argtypes = [vp, vp]
         L.b2gpu_batch_body_commands.argtypes = [vp, vp, C.c_int64]
         L.b2gpu_batch_read_body_state.argtypes = [vp, vp]
+        L.b2gpu_batch_query_aabb.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
+        L.b2gpu_batch_raycast_closest.argtypes = [vp, vp, C.c_int64, vp]
         L.b2gpu_batch_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_steps.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_kernels.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
@@ -229,6 +237,22 @@ class WorldBatch:
         if out is None:
             out = np.empty((self.num_worlds, self.max_bodies, 8), np.float32)
         _check(lib().b2gpu_batch_read_body_state(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def query_aabb(self, queries: np.ndarray, max_hits=64):
+        """b2gpu_batch_query_aabb -> (counts [n], hits [n, max_hits] fixture | child << 16, ascending proxy id)."""
+        q = np.ascontiguousarray(queries, AABB_QUERY_DTYPE)
+        counts = np.zeros(q.shape[0], np.int32)
+        hits = np.zeros((q.shape[0], max_hits), np.int32)
+        p = lambda t: t.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _check(lib().b2gpu_batch_query_aabb(self.h, p(q), q.shape[0], max_hits, p(counts), p(hits)))
+        return counts, hits
+
+    def raycast_closest(self, rays: np.ndarray) -> np.ndarray:
+        """b2gpu_batch_raycast_closest -> RAY_HIT_DTYPE array (fixture = -1: no hit)."""
+        r = np.ascontiguousarray(rays, RAY_DTYPE)
+        out = np.zeros(r.shape[0], RAY_HIT_DTYPE)
+        _check(lib().b2gpu_batch_raycast_closest(self.h, r.ctypes.data_as(C.c_void_p), r.shape[0], out.ctypes.data_as(C.c_void_p)))
         return out
 
     def read_transforms(self, out: np.ndarray | None = None) -> np.ndarray:

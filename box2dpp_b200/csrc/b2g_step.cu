@@ -14,6 +14,7 @@
 #include "b2g_kernels.cuh"
 #include "b2g_solve.cuh"
 #include "b2g_toi.cuh"
+#include "b2g_query.cuh"
 
 using namespace b2g;
 
@@ -891,6 +892,53 @@ int requireDevice(int device) {
     return B2GPU_OK;
 }
 }  // namespace
+
+int b2gpu_batch_query_aabb(b2gpu_batch* b, const b2gpu_aabb_query* queries, int64_t count, int32_t maxHits, int32_t* counts,
+                           int32_t* hits) {
+    if (!b || count < 0 || maxHits < 0 || (count > 0 && (!queries || !counts || (maxHits > 0 && !hits))))
+        return fail(B2GPU_ERR_INVALID, "bad arguments");
+    if (count == 0) return B2GPU_OK;
+    for (int64_t i = 0; i < count; ++i)
+        if (queries[i].world < 0 || queries[i].world >= b->desc.numWorlds)
+            return fail(B2GPU_ERR_INVALID, "query %lld names world %d outside the batch", (long long)i, queries[i].world);
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    DevBuf dq, dc, dh;
+    int rc;
+    if ((rc = dq.alloc((size_t)count * sizeof(b2gpu_aabb_query))) != B2GPU_OK) return rc;
+    if ((rc = dc.alloc((size_t)count * sizeof(int32_t))) != B2GPU_OK) return rc;
+    if ((rc = dh.alloc((size_t)count * maxHits * sizeof(int32_t))) != B2GPU_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dq.p, queries, (size_t)count * sizeof(b2gpu_aabb_query), cudaMemcpyHostToDevice, b->stream));
+    k_query_aabb<<<(unsigned)((count + 127) / 128), 128, 0, b->stream>>>(b->A, (const b2gpu_aabb_query*)dq.p, (long long)count, maxHits,
+                                                                         (int*)dc.p, (int*)dh.p);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(counts, dc.p, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    if (maxHits > 0)
+        CUDA_TRY(cudaMemcpyAsync(hits, dh.p, (size_t)count * maxHits * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_raycast_closest(b2gpu_batch* b, const b2gpu_ray* rays, int64_t count, b2gpu_ray_hit* hits) {
+    if (!b || count < 0 || (count > 0 && (!rays || !hits))) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    if (count == 0) return B2GPU_OK;
+    for (int64_t i = 0; i < count; ++i)
+        if (rays[i].world < 0 || rays[i].world >= b->desc.numWorlds)
+            return fail(B2GPU_ERR_INVALID, "ray %lld names world %d outside the batch", (long long)i, rays[i].world);
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    DevBuf dr, dh;
+    int rc;
+    if ((rc = dr.alloc((size_t)count * sizeof(b2gpu_ray))) != B2GPU_OK) return rc;
+    if ((rc = dh.alloc((size_t)count * sizeof(b2gpu_ray_hit))) != B2GPU_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dr.p, rays, (size_t)count * sizeof(b2gpu_ray), cudaMemcpyHostToDevice, b->stream));
+    k_raycast_closest<<<(unsigned)((count + 127) / 128), 128, 0, b->stream>>>(b->A, (const b2gpu_ray*)dr.p, (long long)count,
+                                                                              (b2gpu_ray_hit*)dh.p);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(hits, dh.p, (size_t)count * sizeof(b2gpu_ray_hit), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
 
 int b2gpu_sincosf(int32_t device, const float* x, float* s, float* c, int64_t n) {
     if (!x || !s || !c || n < 0) return fail(B2GPU_ERR_INVALID, "bad arguments");

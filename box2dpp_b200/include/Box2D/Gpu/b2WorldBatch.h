@@ -266,9 +266,19 @@ public:
     void* GetUserData() const { return m_userData; }
     b2World* GetWorld() const { return m_world; }
     int32_t GetIndex() const { return m_index; }  // creation order within the world
-    // b2Body::ApplyForceToCenter / ApplyTorque (b2Body.h:738-790): accumulated on the host, uploaded at the next Step
+    // Between-step edits (Dynamics/b2Body.h:738-833, 408-467, 634-653; b2Body.cpp:418-440).  Each call is queued as a
+    // b2gpu_body_command in call order and applied on the device before the next Step / getter, with the
+    // reference's semantics (type checks, wake rules, force only accumulates on awake bodies, SetTransform
+    // re-synchronises the body's proxies).
+    void ApplyForce(const b2Vec<float, 2>& force, const b2Vec<float, 2>& point, bool wake);
     void ApplyForceToCenter(const b2Vec<float, 2>& force, bool wake);
     void ApplyTorque(float torque, bool wake);
+    void ApplyLinearImpulse(const b2Vec<float, 2>& impulse, const b2Vec<float, 2>& point, bool wake);
+    void ApplyAngularImpulse(float impulse, bool wake);
+    void SetLinearVelocity(const b2Vec<float, 2>& v);
+    void SetAngularVelocity(float omega);
+    void SetTransform(const b2Vec<float, 2>& position, float angle);
+    void SetAwake(bool flag);
 
 private:
     friend class b2World;
@@ -352,11 +362,7 @@ public:
     // b2World::Step for every world of the batch.
     void Step(float timeStep, int32_t velocityIterations, int32_t positionIterations) {
         Build();
-        if (m_forcesDirty) {
-            Check(b2gpu_batch_apply_forces(m_handle, m_forces.data()));
-            std::fill(m_forces.begin(), m_forces.end(), 0.0f);
-            m_forcesDirty = false;
-        }
+        Flush();
         Check(b2gpu_batch_step(m_handle, timeStep, velocityIterations, positionIterations));
         m_stateValid = false;
         if (m_listener) DispatchEvents();
@@ -364,6 +370,7 @@ public:
     // `steps` steps replayed from a CUDA graph (no listener dispatch in between).
     void StepN(float timeStep, int32_t velocityIterations, int32_t positionIterations, int32_t steps) {
         Build();
+        Flush();
         Check(b2gpu_batch_step_n(m_handle, timeStep, velocityIterations, positionIterations, steps));
         m_stateValid = false;
     }
@@ -421,10 +428,17 @@ private:
         }
         m_maxBodies = desc.maxBodies;
         m_maxEventsBuilt = desc.maxEvents;
-        m_forces.assign((size_t)desc.numWorlds * m_maxBodies * 3, 0.0f);
+    }
+    void Queue(const b2Body* b, int32_t op, bool wake, float vx, float vy, float px, float py);
+    void Flush() {  // queued body edits -> device, in call order per world
+        if (m_commands.empty()) return;
+        Check(b2gpu_batch_body_commands(m_handle, m_commands.data(), (int64_t)m_commands.size()));
+        m_commands.clear();
+        m_stateValid = false;
     }
     void Refresh() {  // lazy readback of body state after a Step
         Build();
+        Flush();
         if (m_stateValid) return;
         const size_t n = m_worlds.size() * (size_t)m_maxBodies;
         m_xf.resize(n * 4); m_sweep.resize(n * 4); m_vel.resize(n * 4); m_bodyFlags.resize(n);
@@ -469,8 +483,9 @@ private:
     b2gpu_batch* m_handle = nullptr;
     b2ContactListener* m_listener = nullptr;
     int32_t m_eventMask = 0, m_maxContacts = 0, m_maxEvents = 0, m_maxBodies = 0, m_maxEventsBuilt = 0;
-    bool m_stateValid = false, m_forcesDirty = false;
-    std::vector<float> m_xf, m_sweep, m_vel, m_forces;
+    bool m_stateValid = false;
+    std::vector<float> m_xf, m_sweep, m_vel;
+    std::vector<b2gpu_body_command> m_commands;
     std::vector<int32_t> m_bodyFlags;
 };
 
@@ -594,19 +609,42 @@ inline bool b2Body::IsAwake() const {
     B->Refresh();
     return (B->m_bodyFlags[B->Slot(this)] & 8) != 0;
 }
-inline void b2Body::ApplyForceToCenter(const b2Vec<float, 2>& force, bool) {
-    b2WorldBatch* B = m_world->m_batch;
-    B->Build();
-    float* f = &B->m_forces[B->Slot(this) * 3];
-    f[0] += force[0];
-    f[1] += force[1];
-    B->m_forcesDirty = true;
+inline void b2WorldBatch::Queue(const b2Body* b, int32_t op, bool wake, float vx, float vy, float px, float py) {
+    Build();
+    b2gpu_body_command c;
+    c.world = b->m_world->m_index;
+    c.body = b->m_index;
+    c.op = op;
+    c.wake = wake ? 1 : 0;
+    c.v[0] = vx; c.v[1] = vy; c.p[0] = px; c.p[1] = py;
+    m_commands.push_back(c);
 }
-inline void b2Body::ApplyTorque(float torque, bool) {
-    b2WorldBatch* B = m_world->m_batch;
-    B->Build();
-    B->m_forces[B->Slot(this) * 3 + 2] += torque;
-    B->m_forcesDirty = true;
+inline void b2Body::ApplyForce(const b2Vec<float, 2>& force, const b2Vec<float, 2>& point, bool wake) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_APPLY_FORCE, wake, force[0], force[1], point[0], point[1]);
+}
+inline void b2Body::ApplyForceToCenter(const b2Vec<float, 2>& force, bool wake) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_APPLY_FORCE_TO_CENTER, wake, force[0], force[1], 0.0f, 0.0f);
+}
+inline void b2Body::ApplyTorque(float torque, bool wake) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_APPLY_TORQUE, wake, torque, 0.0f, 0.0f, 0.0f);
+}
+inline void b2Body::ApplyLinearImpulse(const b2Vec<float, 2>& impulse, const b2Vec<float, 2>& point, bool wake) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_APPLY_LINEAR_IMPULSE, wake, impulse[0], impulse[1], point[0], point[1]);
+}
+inline void b2Body::ApplyAngularImpulse(float impulse, bool wake) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_APPLY_ANGULAR_IMPULSE, wake, impulse, 0.0f, 0.0f, 0.0f);
+}
+inline void b2Body::SetLinearVelocity(const b2Vec<float, 2>& v) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_SET_LINEAR_VELOCITY, true, v[0], v[1], 0.0f, 0.0f);
+}
+inline void b2Body::SetAngularVelocity(float omega) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_SET_ANGULAR_VELOCITY, true, omega, 0.0f, 0.0f, 0.0f);
+}
+inline void b2Body::SetTransform(const b2Vec<float, 2>& position, float angle) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_SET_TRANSFORM, true, position[0], position[1], angle, 0.0f);
+}
+inline void b2Body::SetAwake(bool flag) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_SET_AWAKE, flag, 0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 }  // namespace box2d

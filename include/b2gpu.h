@@ -178,6 +178,34 @@ int b2gpu_batch_body_commands(b2gpu_batch* batch, const b2gpu_body_command* comm
  * Box2D/Dynamics/b2Body.h:500-560 for an RL / game-server caller.  Synchronises. */
 int b2gpu_batch_read_body_state(b2gpu_batch* batch, float* out);
 
+/* ---- batched read-only queries --------------------------------------------------------
+ * b2World::QueryAABB / b2World::RayCast (Box2D/Dynamics/b2World.cpp:965-1020; b2DynamicTree::Query / RayCast,
+ * Box2D/Collision/b2DynamicTree.h:218-303) for many (world, query) pairs in one call.  Host buffers in and out;
+ * both calls synchronise.  Order queries world-fastest for coalesced arena reads. */
+typedef struct b2gpu_aabb_query {
+    int32_t world;
+    float lower[2], upper[2];
+} b2gpu_aabb_query;
+/* counts[q] = number of proxies whose fat AABB overlaps query q (what b2QueryCallback::ReportFixture would be called
+ * for, once per proxy); hits[q * maxHits + i] = fixture | child << 16 for the first maxHits of them in ascending
+ * proxy id (the reference reports the same set in tree-traversal order). */
+int b2gpu_batch_query_aabb(b2gpu_batch* batch, const b2gpu_aabb_query* queries, int64_t count, int32_t maxHits,
+                           int32_t* counts, int32_t* hits);
+
+typedef struct b2gpu_ray {
+    int32_t world;
+    float p1[2], p2[2];
+    float maxFraction; /* b2RayCastInput::maxFraction; b2World::RayCast uses 1 */
+} b2gpu_ray;
+typedef struct b2gpu_ray_hit {
+    int32_t fixture, child; /* fixture = -1: no hit */
+    float fraction;
+    float point[2], normal[2];
+} b2gpu_ray_hit;
+/* b2World::RayCast with the closest-hit callback (ReportFixture returns `fraction`): nearest fixture along each ray,
+ * with the reference's point / normal / fraction bit for bit (exact ties in the fraction go to the lower proxy id). */
+int b2gpu_batch_raycast_closest(b2gpu_batch* batch, const b2gpu_ray* rays, int64_t count, b2gpu_ray_hit* hits);
+
 /* CUDA-event time of the last b2gpu_batch_step_n in milliseconds, and per-kernel times of a profiled step. */
 int b2gpu_batch_last_step_ms(b2gpu_batch* batch, float* ms);
 /* Runs `steps` steps with CUDA events around each kernel; ms[4] = collide, islands, solve, sync_pairs totals. */

@@ -212,6 +212,68 @@ void ref_world_body_command(void* h, int body, int op, int wake, float vx, float
     }
 }
 
+// b2World::QueryAABB: (fixture index, child) of every reported proxy, in the reference's (tree) order.
+namespace {
+struct QueryCollector : public b2QueryCallback {
+    std::vector<int32_t> out;
+    bool ReportFixture(b2Fixture*) override { return true; }
+};
+}  // namespace
+int ref_world_query_aabb(void* h, const float* lower, const float* upper, int32_t* out, int cap) {
+    // b2QueryCallback only hands over the fixture; the child index lives in the proxy, so go through the broad
+    // phase like b2World::QueryAABB's wrapper does (Dynamics/b2World.cpp:965-985).
+    RefWorld* rw = (RefWorld*)h;
+    struct Wrapper {
+        const b2BroadPhase* bp;
+        std::vector<int32_t>* out;
+        bool QueryCallback(int32 proxyId) {
+            b2FixtureProxy* proxy = (b2FixtureProxy*)bp->GetUserData(proxyId);
+            out->push_back((int32_t)(intptr_t)proxy->fixture->GetUserData() | (proxy->childIndex << 16));
+            return true;
+        }
+    };
+    std::vector<int32_t> hits;
+    Wrapper wrap{&rw->world->GetContactManager().m_broadPhase, &hits};
+    b2AABB aabb;
+    aabb.lowerBound.Set(lower[0], lower[1]);
+    aabb.upperBound.Set(upper[0], upper[1]);
+    wrap.bp->Query(&wrap, aabb);
+    for (int i = 0; i < (int)hits.size() && i < cap; ++i) out[i] = hits[i];
+    return (int)hits.size();
+}
+
+// b2World::RayCast with the closest-hit callback.  out: fixture, child | fraction, point.xy, normal.xy
+namespace {
+struct ClosestHit : public b2RayCastCallback {
+    b2Fixture* fixture = nullptr;
+    b2Vec2 point, normal;
+    float32 fraction = 0.0f;
+    float32 ReportFixture(b2Fixture* f, const b2Vec2& p, const b2Vec2& n, float32 fr) override {
+        fixture = f; point = p; normal = n; fraction = fr;
+        return fr;
+    }
+};
+}  // namespace
+int ref_world_raycast_closest(void* h, const float* p1, const float* p2, int32_t* outI, float* outF) {
+    RefWorld* rw = (RefWorld*)h;
+    ClosestHit cb;
+    rw->world->RayCast(&cb, b2Vec2(p1[0], p1[1]), b2Vec2(p2[0], p2[1]));
+    if (!cb.fixture) { outI[0] = -1; outI[1] = 0; return 0; }
+    outI[0] = (int32_t)(intptr_t)cb.fixture->GetUserData();
+    // the child index is not reported to the callback: recover it by re-casting the fixture's children
+    outI[1] = 0;
+    b2RayCastInput in; in.p1.Set(p1[0], p1[1]); in.p2.Set(p2[0], p2[1]); in.maxFraction = 1.0f;
+    for (int32 c = 0; c < cb.fixture->GetShape()->GetChildCount(); ++c) {
+        b2RayCastOutput o;
+        if (cb.fixture->RayCast(&o, in, c) && o.fraction == cb.fraction && o.normal.x == cb.normal.x && o.normal.y == cb.normal.y) {
+            outI[1] = c;
+            break;
+        }
+    }
+    outF[0] = cb.fraction; outF[1] = cb.point.x; outF[2] = cb.point.y; outF[3] = cb.normal.x; outF[4] = cb.normal.y;
+    return 1;
+}
+
 int ref_world_body_count(void* h) { return (int)((RefWorld*)h)->bodies.size(); }
 int ref_world_contact_count(void* h) { return ((RefWorld*)h)->world->GetContactCount(); }
 int ref_world_proxy_count(void* h) { return ((RefWorld*)h)->world->GetProxyCount(); }

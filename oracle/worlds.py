@@ -67,6 +67,10 @@ def lib(kind="ref"):
                   "ref_collide_edge_circle", "ref_collide_edge_polygon"):
             getattr(L, f).argtypes = [C.c_void_p] * 6
         if kind == "ref":
+            L.ref_world_query_aabb.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            L.ref_world_query_aabb.restype = C.c_int
+            L.ref_world_raycast_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.ref_world_raycast_closest.restype = C.c_int
             L.ref_sincosf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
             L.ref_bench_run.restype = C.c_double
             L.ref_bench_run.argtypes = [C.POINTER(CScene), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
@@ -102,6 +106,21 @@ class RefWorld:
     def command(self, body, op, wake=1, v=(0.0, 0.0), p=(0.0, 0.0)):
         """One between-step b2Body call (op = B2GPU_CMD_* of include/b2gpu.h)."""
         self.L.ref_world_body_command(self.h, body, op, wake, v[0], v[1], p[0], p[1])
+
+    def query_aabb(self, lower, upper):
+        """b2World::QueryAABB: fixture | child << 16 per reported proxy, in the reference's order (live reference only)."""
+        lo, hi = np.asarray(lower, np.float32), np.asarray(upper, np.float32)
+        out = np.zeros(4096, np.int32)
+        n = self.L.ref_world_query_aabb(self.h, _p(lo), _p(hi), _p(out), out.shape[0])
+        return out[:n].copy()
+
+    def raycast_closest(self, p1, p2):
+        """b2World::RayCast with the closest-hit callback: (fixture, child, fraction, point[2], normal[2]) or None."""
+        a, b = np.asarray(p1, np.float32), np.asarray(p2, np.float32)
+        oi, of = np.zeros(2, np.int32), np.zeros(5, np.float32)
+        if not self.L.ref_world_raycast_closest(self.h, _p(a), _p(b), _p(oi), _p(of)):
+            return None
+        return int(oi[0]), int(oi[1]), of[0], of[1:3].copy(), of[3:5].copy()
 
     def bodies(self) -> np.ndarray:
         """[nb,16] float32: xf.p(2) q.s q.c | c(2) a | v(2) w | awake mass I localCenter(2) pad."""

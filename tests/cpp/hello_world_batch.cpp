@@ -111,10 +111,74 @@ static int batch(int n, int rows, int steps) {
     return 0;
 }
 
+// Between-step edits through the b2Body API: a small pyramid per world, poked every few steps the way a game /
+// RL loop would (impulses, velocity resets, a teleport, putting a body to sleep).  tests/test_cpp_api.py replays the
+// same calls on the oracle.
+static int edits(int n, int steps) {
+    b2WorldBatch worlds(b2Vec<float, 2>{{0.0f, -10.0f}}, n);
+    std::vector<std::vector<b2Body*>> bodies(n);
+    for (int w = 0; w < n; ++w) {
+        b2World& world = worlds[w];
+        world.SetContinuousPhysics(false);
+        b2BodyDef gd;
+        b2Body* ground = world.CreateBody(&gd);
+        b2PolygonShape gs;
+        gs.SetAsBox(50.0f, 10.0f, b2Vec<float, 2>{{0.0f, -10.0f}}, 0.0f);
+        ground->CreateFixture(&gs, 0.0f);
+        bodies[w].push_back(ground);
+        b2PolygonShape box;
+        box.SetAsBox(0.5f, 0.5f);
+        const int count = 4;
+        b2Vec<float, 2> x{{-7.0f, 0.75f}};
+        for (int i = 0; i < count; ++i) {
+            b2Vec<float, 2> y = x;
+            for (int j = i; j < count; ++j) {
+                b2BodyDef bd;
+                bd.type = b2BodyType::DYNAMIC_BODY;
+                bd.position = y;
+                b2Body* body = world.CreateBody(&bd);
+                body->CreateFixture(&box, 5.0f);
+                bodies[w].push_back(body);
+                y[0] += 1.125f;
+            }
+            x[0] += 0.5625f;
+            x[1] += 1.25f;
+        }
+    }
+    for (int s = 0; s < steps; ++s) {
+        for (int w = 0; w < n; ++w) {
+            std::vector<b2Body*>& b = bodies[w];
+            const int nb = (int)b.size();
+            b2Body* target = b[1 + (s + w) % (nb - 1)];
+            switch ((s + 2 * w) % 7) {
+                case 0: target->ApplyLinearImpulse(b2Vec<float, 2>{{3.0f + w, 12.0f}}, target->GetWorldCenter(), true); break;
+                case 1: target->ApplyForce(b2Vec<float, 2>{{-150.0f, 400.0f}}, b2Vec<float, 2>{{0.25f * s, 2.0f}}, (s & 1) != 0); break;
+                case 2: target->SetAngularVelocity(0.5f * w - 1.0f); break;
+                case 3: if (s % 21 == 3) target->SetTransform(b2Vec<float, 2>{{-2.0f + w, 6.0f}}, 0.3f); break;
+                case 4: target->ApplyTorque(25.0f, true); target->ApplyForceToCenter(b2Vec<float, 2>{{40.0f, 0.0f}}, true); break;
+                case 5: if (s % 35 == 5) target->SetAwake(false); else target->ApplyAngularImpulse(-1.5f, true); break;
+                case 6: target->SetLinearVelocity(b2Vec<float, 2>{{0.0f, s % 14 == 6 ? 4.0f : 0.0f}}); break;
+            }
+        }
+        worlds.Step(1.0f / 60.0f, 8, 3);
+    }
+    if (worlds.GetStatus() != 0) return 4;
+    for (int w = 0; w < n; ++w)
+        for (size_t i = 0; i < bodies[w].size(); ++i) {
+            b2Body* b = bodies[w][i];
+            b2Vec<float, 2> p = b->GetPosition(), v = b->GetLinearVelocity();
+            std::printf("%d %zu %08x %08x %08x %08x %08x %08x %d\n", w, i, bits(p[0]), bits(p[1]), bits(b->GetAngle()), bits(v[0]),
+                        bits(v[1]), bits(b->GetAngularVelocity()), b->IsAwake() ? 1 : 0);
+        }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     try {
         if (argc >= 2 && std::strcmp(argv[1], "batch") == 0)
             return batch(argc > 2 ? std::atoi(argv[2]) : 3, argc > 3 ? std::atoi(argv[3]) : 4, argc > 4 ? std::atoi(argv[4]) : 120);
+        if (argc >= 2 && std::strcmp(argv[1], "edits") == 0)
+            return edits(argc > 2 ? std::atoi(argv[2]) : 3, argc > 3 ? std::atoi(argv[3]) : 150);
         return hello();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());

@@ -85,3 +85,51 @@ def test_world_batch_cpp_with_listener(exe, oracles):
         want = [int(np.float32(v).view(np.uint32)) for v in (top[0], top[1], top[6])]
         assert got == want, f"world {w}: top box state"
         assert int(f[10]) == int(top[10] != 0)
+
+
+@pytest.mark.gpu
+def test_body_edits_through_cpp_api(exe, oracles):
+    """b2Body::ApplyLinearImpulse / ApplyForce / SetTransform / SetAwake ... called between steps through the C++
+    mirror (queued as b2gpu_body_command): final state of every body equals the oracle's, bit for bit."""
+    from box2dpp_b200 import batch as B
+    n, steps = 3, 150
+    r = subprocess.run([exe, "edits", str(n), str(steps)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = {}
+    for line in r.stdout.strip().splitlines():
+        f = line.split()
+        got[(int(f[0]), int(f[1]))] = [int(x, 16) for x in f[2:8]] + [int(f[8])]
+    Ref = oracles.RefWorld if oracles.available("ref") else oracles.PortWorld
+    f32 = lambda x: float(np.float32(x))  # noqa: E731
+    for w in range(n):
+        ref = Ref(S.pyramid(4, flags=G.NOCCD))
+        nb = ref.bodies().shape[0]
+        for s in range(steps):
+            t = 1 + (s + w) % (nb - 1)
+            k = (s + 2 * w) % 7
+            if k == 0:
+                c = ref.bodies()[t]
+                ref.command(t, B.CMD_APPLY_LINEAR_IMPULSE, 1, (3.0 + w, 12.0), (float(c[4]), float(c[5])))
+            elif k == 1:
+                ref.command(t, B.CMD_APPLY_FORCE, s & 1, (-150.0, 400.0), (f32(0.25 * s), 2.0))
+            elif k == 2:
+                ref.command(t, B.CMD_SET_ANGULAR_VELOCITY, 1, (f32(0.5 * w - 1.0), 0.0))
+            elif k == 3:
+                if s % 21 == 3:
+                    ref.command(t, B.CMD_SET_TRANSFORM, 1, (-2.0 + w, 6.0), (f32(0.3), 0.0))
+            elif k == 4:
+                ref.command(t, B.CMD_APPLY_TORQUE, 1, (25.0, 0.0))
+                ref.command(t, B.CMD_APPLY_FORCE_TO_CENTER, 1, (40.0, 0.0))
+            elif k == 5:
+                if s % 35 == 5:
+                    ref.command(t, B.CMD_SET_AWAKE, 0)
+                else:
+                    ref.command(t, B.CMD_APPLY_ANGULAR_IMPULSE, 1, (-1.5, 0.0))
+            else:
+                ref.command(t, B.CMD_SET_LINEAR_VELOCITY, 1, (0.0, 4.0 if s % 14 == 6 else 0.0))
+            ref.step(1.0 / 60.0, 8, 3)
+        rb = ref.bodies()
+        for i in range(nb):
+            want = [int(np.float32(v).view(np.uint32)) for v in (rb[i, 0], rb[i, 1], rb[i, 6], rb[i, 7], rb[i, 8], rb[i, 9])]
+            assert got[(w, i)][:6] == want, f"world {w} body {i}"
+            assert got[(w, i)][6] == int(rb[i, 10] != 0)
