@@ -23,12 +23,13 @@ LIB_PATH = os.environ.get("B2GPU_LIB") or os.path.join(_HERE, "libb2gpu.so")
  F_ISLAND_COUNT, F_STEP_COUNT, F_BODY_XF, F_BODY_SWEEP, F_BODY_SWEEP0, F_BODY_VEL, F_BODY_FORCE, F_BODY_MASS,
  F_BODY_DAMP, F_BODY_FLAGS, F_FIXTURE_INFO, F_FIXTURE_SHAPE, F_FIXTURE_MAT, F_FIXTURE_FILTER, F_PROXY_FAT,
  F_PROXY_INFO, F_PROXY_MOVED, F_SHAPE_WORDS, F_CHAIN_VERTS, F_CONTACT_A, F_CONTACT_K, F_CONTACT_S, F_CONTACT_P0,
- F_CONTACT_P1, F_CONTACT_N, F_EVENT_A, F_EVENT_B, F_ISLAND_CONTACTS, F_ISLAND_CONTACT_END, F_COUNT) = range(38)
+ F_CONTACT_P1, F_CONTACT_N, F_EVENT_A, F_EVENT_B, F_ISLAND_CONTACTS, F_ISLAND_CONTACT_END, F_JOINT_COUNT, F_JOINT_I,
+ F_JOINT_F0, F_JOINT_F1, F_JOINT_F2, F_JOINT_IMPULSE, F_COUNT) = range(44)
 
 INT_FIELDS = {F_WORLD_FLAGS, F_BODY_COUNT, F_PROXY_COUNT, F_CONTACT_COUNT, F_STATUS, F_EVENT_COUNT, F_ISLAND_COUNT,
               F_STEP_COUNT, F_BODY_FLAGS, F_FIXTURE_INFO, F_FIXTURE_SHAPE, F_FIXTURE_FILTER, F_PROXY_INFO,
               F_PROXY_MOVED, F_CONTACT_A, F_CONTACT_K, F_CONTACT_S, F_EVENT_A, F_ISLAND_CONTACTS,
-              F_ISLAND_CONTACT_END}
+              F_ISLAND_CONTACT_END, F_JOINT_COUNT, F_JOINT_I}
 
 EVENT_BEGIN, EVENT_END, EVENT_PRESOLVE, EVENT_POSTSOLVE = 0, 1, 2, 3
 EVENT_ALL = 15
@@ -48,7 +49,7 @@ COLLIDE_POLYGONS, COLLIDE_CIRCLES, COLLIDE_POLYGON_CIRCLE, COLLIDE_EDGE_CIRCLE, 
 class BatchDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "device", "numWorlds", "maxBodies", "maxFixtures", "maxProxies", "maxContacts", "maxShapeWords",
-        "maxChainVerts", "maxEvents", "eventMask", "blockSize", "reserved")]
+        "maxChainVerts", "maxEvents", "eventMask", "blockSize", "reserved", "maxJoints")]
 
 
 class B2GpuError(RuntimeError):

@@ -485,6 +485,44 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
     put(out.f[B2GPU_F_INV_DT0], 0, 0.0f);
     put(out.f[B2GPU_F_BODY_COUNT], 0, nb);
     put(out.f[B2GPU_F_PROXY_COUNT], 0, proxyCount);
+
+    // ---- b2World::CreateJoint calls (b2World.cpp:211-270); the joint constructors copy the def
+    // (b2RevoluteJoint.cpp:47-64, b2PrismaticJoint.cpp:100-125, b2DistanceJoint.cpp:51-62) ----
+    const int nj = s.jointCount > 0 ? s.jointCount : 0;
+    if (nj > shapes[B2GPU_F_JOINT_I].first || (nj > 0 && !s.joints)) {
+        err = "scene exceeds the batch's joint capacity";
+        return B2GPU_ERR_CAPACITY;
+    }
+    for (int j = 0; j < nj; ++j) {
+        const b2g_joint_def& d = s.joints[j];
+        if (d.type != B2G_JOINT_REVOLUTE && d.type != B2G_JOINT_PRISMATIC && d.type != B2G_JOINT_DISTANCE) {
+            err = "joint type outside the device path (revolute, prismatic and distance joints are built)";
+            return B2GPU_ERR_UNSUPPORTED;
+        }
+        if (d.bodyA < 0 || d.bodyA >= nb || d.bodyB < 0 || d.bodyB >= nb || d.bodyA == d.bodyB) {
+            err = "joint references a body that does not exist (or connects a body to itself)";
+            return B2GPU_ERR_INVALID;
+        }
+        const size_t o = (size_t)j * 4;
+        auto& JI = out.f[B2GPU_F_JOINT_I];
+        put(JI, o, d.type | ((d.collideConnected ? 1 : 0) << 8) | ((d.enableLimit ? 1 : 0) << 9) | ((d.enableMotor ? 1 : 0) << 10));
+        put(JI, o + 1, d.bodyA | (d.bodyB << 16));
+        put(JI, o + 2, 0);  // m_limitState = e_inactiveLimit
+        put(JI, o + 3, 0);
+        auto& F0 = out.f[B2GPU_F_JOINT_F0];
+        put(F0, o, d.localAnchorA[0]); put(F0, o + 1, d.localAnchorA[1]); put(F0, o + 2, d.localAnchorB[0]); put(F0, o + 3, d.localAnchorB[1]);
+        auto& F1 = out.f[B2GPU_F_JOINT_F1];
+        if (d.type == B2G_JOINT_DISTANCE) {
+            put(F1, o, d.length); put(F1, o + 1, d.frequencyHz); put(F1, o + 2, d.dampingRatio); put(F1, o + 3, 0.0f);
+        } else {
+            put(F1, o, d.referenceAngle); put(F1, o + 1, d.lower); put(F1, o + 2, d.upper); put(F1, o + 3, d.maxMotor);
+        }
+        Vec2 axis = V2(d.localAxisA[0], d.localAxisA[1]);
+        if (d.type == B2G_JOINT_PRISMATIC) Normalize(axis);  // m_localXAxisA.Normalize()
+        auto& F2 = out.f[B2GPU_F_JOINT_F2];
+        put(F2, o, d.motorSpeed); put(F2, o + 1, axis.x); put(F2, o + 2, axis.y); put(F2, o + 3, 0.0f);
+    }
+    put(out.f[B2GPU_F_JOINT_COUNT], 0, nj);
     return B2GPU_OK;
 }
 
@@ -495,6 +533,7 @@ const int kBuildFields[] = {
     B2GPU_F_BODY_XF, B2GPU_F_BODY_SWEEP, B2GPU_F_BODY_SWEEP0, B2GPU_F_BODY_VEL, B2GPU_F_BODY_FORCE, B2GPU_F_BODY_MASS,
     B2GPU_F_BODY_DAMP, B2GPU_F_BODY_FLAGS, B2GPU_F_FIXTURE_INFO, B2GPU_F_FIXTURE_SHAPE, B2GPU_F_FIXTURE_MAT,
     B2GPU_F_FIXTURE_FILTER, B2GPU_F_PROXY_FAT, B2GPU_F_PROXY_INFO, B2GPU_F_SHAPE_WORDS, B2GPU_F_CHAIN_VERTS,
+    B2GPU_F_JOINT_COUNT, B2GPU_F_JOINT_I, B2GPU_F_JOINT_F0, B2GPU_F_JOINT_F1, B2GPU_F_JOINT_F2, B2GPU_F_JOINT_IMPULSE,
     B2GPU_F_PROXY_MOVED,
 };
 
@@ -515,6 +554,9 @@ int b2gpu_scene_capacities(const b2g_scene* scenes, int32_t sceneCount, b2gpu_ba
     desc->maxProxies = NP;
     desc->maxShapeWords = NS;
     desc->maxChainVerts = NV;
+    int NJ = 0;
+    for (int i = 0; i < sceneCount; ++i) NJ = scenes[i].jointCount > NJ ? scenes[i].jointCount : NJ;
+    desc->maxJoints = NJ;
     if (desc->maxContacts <= 0) desc->maxContacts = 4 * NP + 32;   // pyramid-20 peaks at 604 for 211 proxies
     if (desc->maxEvents <= 0) desc->maxEvents = desc->eventMask ? 3 * desc->maxContacts : 1;
     return B2GPU_OK;

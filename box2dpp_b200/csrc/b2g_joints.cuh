@@ -1,0 +1,530 @@
+// b2g_joints.cuh — joints in the island solver: revolute, prismatic and distance joints.
+//
+// Reference (vanilla twin Regression/box2d-ref/Box2DRef/Dynamics/Joints; the fork's files are
+// Box2D/Dynamics/Joints/b2RevoluteJoint.cpp, b2PrismaticJoint.cpp, b2DistanceJoint.cpp, same line structure):
+//   InitVelocityConstraints / SolveVelocityConstraints / SolvePositionConstraints of each joint class,
+//   b2Mat33::Solve33 / Solve22 (Common/b2Math.cpp:22-52), b2Mat22::Solve (Common/b2Math.h:242-254).
+// Hooks in the island solver: b2Island.cpp:252-255 (init after the contact warm start), :263-266 (before the contacts in
+// every velocity iteration), :316-320 (after the contacts in every position iteration).
+//
+// One world per thread, like the rest of the generic solver kernel (k_solve): positions and velocities are the body
+// arrays (b2Position = bodySweep.c/a, b2Velocity = bodyVel), joint temporaries live in a per-world scratch column.
+// Textually included inside namespace b2g (from b2g_kernels.cuh).
+#pragma once
+
+constexpr int kJointTmp = 5;  // float4 of solver temporaries per joint
+enum : int { kLimitInactive = 0, kLimitAtLower = 1, kLimitAtUpper = 2, kLimitEqual = 3 };  // b2LimitState
+enum : int { kJointCollide = 1 << 8, kJointEnableLimit = 1 << 9, kJointEnableMotor = 1 << 10 };
+
+struct Vec3 { float x, y, z; };
+__device__ __forceinline__ Vec3 V3(float x, float y, float z) { Vec3 v; v.x = x; v.y = y; v.z = z; return v; }
+__device__ __forceinline__ float Dot3(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ Vec3 Cross3(Vec3 a, Vec3 b) {
+    return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+struct Mat33 { Vec3 ex, ey, ez; };
+// b2Mat33::Solve33 — Common/b2Math.cpp:22-35
+__device__ __forceinline__ Vec3 Solve33(const Mat33& M, Vec3 b) {
+    float det = Dot3(M.ex, Cross3(M.ey, M.ez));
+    if (det != 0.0f) det = Div(1.0f, det);
+    Vec3 x;
+    x.x = det * Dot3(b, Cross3(M.ey, M.ez));
+    x.y = det * Dot3(M.ex, Cross3(b, M.ez));
+    x.z = det * Dot3(M.ex, Cross3(M.ey, b));
+    return x;
+}
+// b2Mat33::Solve22 / b2Mat22::Solve — Common/b2Math.cpp:39-52, b2Math.h:242-254 (a11 = ex.x, a12 = ey.x, a21 = ex.y, a22 = ey.y)
+__device__ __forceinline__ Vec2 Solve22(float a11, float a12, float a21, float a22, Vec2 b) {
+    float det = a11 * a22 - a12 * a21;
+    if (det != 0.0f) det = Div(1.0f, det);
+    Vec2 x;
+    x.x = det * (a22 * b.x - a12 * b.y);
+    x.y = det * (a11 * b.y - a21 * b.x);
+    return x;
+}
+
+struct JointCols {
+    Col<int4> jI;
+    Col<float4> jF0, jF1, jF2, jImp, jTmp;
+    Col<float4> bodySweep, bodyVel, bodyMass;
+};
+__device__ __forceinline__ JointCols MakeJointCols(const Arena& A, int tile, int lane) {
+    JointCols c{col(A.jointI, tile, A.NJ, lane), col(A.jointF0, tile, A.NJ, lane), col(A.jointF1, tile, A.NJ, lane),
+                col(A.jointF2, tile, A.NJ, lane), col(A.jointImp, tile, A.NJ, lane), col(A.jointTmp, tile, A.NJ * kJointTmp, lane),
+                col(A.bodySweep, tile, A.NB, lane), col(A.bodyVel, tile, A.NB, lane), col(A.bodyMass, tile, A.NB, lane)};
+    return c;
+}
+
+// ---- InitVelocityConstraints ---------------------------------------------------------------------------------
+__device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float h, float dtRatio, bool warmStarting) {
+    const JointCols& c = *cp;
+    int4 ji = c.jI[j];
+    const int type = ji.x & 0xff;
+    const int bA = ji.y & 0xffff, bB = (ji.y >> 16) & 0xffff;
+    const float4 f0 = c.jF0[j], f1 = c.jF1[j], f2 = c.jF2[j];
+    const float4 msA = c.bodyMass[bA], msB = c.bodyMass[bB];
+    const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
+    const float4 swA = c.bodySweep[bA], swB = c.bodySweep[bB];
+    const Vec2 cA = V2(swA.x, swA.y), cB = V2(swB.x, swB.y);
+    const float aA = swA.z, aB = swB.z;
+    float4 velA = c.bodyVel[bA], velB = c.bodyVel[bB];
+    Vec2 vA = V2(velA.x, velA.y), vB = V2(velB.x, velB.y);
+    float wA = velA.z, wB = velB.z;
+    const Rot qA = MakeRot(aA), qB = MakeRot(aB);
+    const Vec2 rA = Mul(qA, V2(f0.x, f0.y) - V2(msA.z, msA.w));
+    const Vec2 rB = Mul(qB, V2(f0.z, f0.w) - V2(msB.z, msB.w));
+    float4 imp = c.jImp[j];
+    const size_t t = (size_t)j * kJointTmp;
+
+    if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:66-176
+        const bool fixedRotation = (iA + iB == 0.0f);
+        Mat33 M;
+        M.ex.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+        M.ey.x = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+        M.ez.x = -rA.y * iA - rB.y * iB;
+        M.ex.y = M.ey.x;
+        M.ey.y = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+        M.ez.y = rA.x * iA + rB.x * iB;
+        M.ex.z = M.ez.x;
+        M.ey.z = M.ez.y;
+        M.ez.z = iA + iB;
+        float motorMass = iA + iB;
+        if (motorMass > 0.0f) motorMass = Div(1.0f, motorMass);
+        if ((ji.x & kJointEnableMotor) == 0 || fixedRotation) imp.w = 0.0f;
+        int limitState = ji.z;
+        if ((ji.x & kJointEnableLimit) && !fixedRotation) {
+            const float jointAngle = aB - aA - f1.x;
+            if (Abs(f1.z - f1.y) < 2.0f * kAngularSlop) {
+                limitState = kLimitEqual;
+            } else if (jointAngle <= f1.y) {
+                if (limitState != kLimitAtLower) imp.z = 0.0f;
+                limitState = kLimitAtLower;
+            } else if (jointAngle >= f1.z) {
+                if (limitState != kLimitAtUpper) imp.z = 0.0f;
+                limitState = kLimitAtUpper;
+            } else {
+                limitState = kLimitInactive;
+                imp.z = 0.0f;
+            }
+        } else {
+            limitState = kLimitInactive;
+        }
+        if (limitState != ji.z) {
+            ji.z = limitState;
+            c.jI[j] = ji;
+        }
+        if (warmStarting) {
+            imp.x *= dtRatio; imp.y *= dtRatio; imp.z *= dtRatio;
+            imp.w *= dtRatio;
+            const Vec2 P = V2(imp.x, imp.y);
+            vA = vA - mA * P;
+            wA -= iA * (Cross(rA, P) + imp.w + imp.z);
+            vB = vB + mB * P;
+            wB += iB * (Cross(rB, P) + imp.w + imp.z);
+        } else {
+            imp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
+        c.jTmp[t + 1] = make_float4(M.ex.x, M.ex.y, M.ex.z, motorMass);
+        c.jTmp[t + 2] = make_float4(M.ey.x, M.ey.y, M.ey.z, 0.0f);
+        c.jTmp[t + 3] = make_float4(M.ez.x, M.ez.y, M.ez.z, 0.0f);
+    } else if (type == B2G_JOINT_DISTANCE) {  // b2DistanceJoint.cpp:64-152
+        Vec2 u = cB + rB - cA - rA;
+        const float length = Length(u);
+        if (length > kLinearSlop) u = Div(1.0f, length) * u;
+        else u = V2(0.0f, 0.0f);
+        const float crAu = Cross(rA, u), crBu = Cross(rB, u);
+        float invMass = mA + iA * crAu * crAu + mB + iB * crBu * crBu;
+        float mass = invMass != 0.0f ? Div(1.0f, invMass) : 0.0f;
+        float gamma = 0.0f, bias = 0.0f;
+        if (f1.y > 0.0f) {
+            const float C = length - f1.x;
+            const float omega = 2.0f * kPi * f1.y;
+            const float d = 2.0f * mass * f1.z * omega;
+            const float k = mass * omega * omega;
+            gamma = h * (d + h * k);
+            gamma = gamma != 0.0f ? Div(1.0f, gamma) : 0.0f;
+            bias = C * h * k * gamma;
+            invMass += gamma;
+            mass = invMass != 0.0f ? Div(1.0f, invMass) : 0.0f;
+        }
+        if (warmStarting) {
+            imp.x *= dtRatio;
+            const Vec2 P = imp.x * u;
+            vA = vA - mA * P;
+            wA -= iA * Cross(rA, P);
+            vB = vB + mB * P;
+            wB += iB * Cross(rB, P);
+        } else {
+            imp.x = 0.0f;
+        }
+        c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
+        c.jTmp[t + 1] = make_float4(u.x, u.y, mass, gamma);
+        c.jTmp[t + 2] = make_float4(bias, 0.0f, 0.0f, 0.0f);
+    } else {  // prismatic — b2PrismaticJoint.cpp:127-264
+        const Vec2 d = (cB - cA) + rB - rA;
+        const Vec2 localX = V2(f2.y, f2.z), localY = Cross(1.0f, localX);
+        const Vec2 axis = Mul(qA, localX);
+        const float a1 = Cross(d + rA, axis), a2 = Cross(rB, axis);
+        float motorMass = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+        if (motorMass > 0.0f) motorMass = Div(1.0f, motorMass);
+        const Vec2 perp = Mul(qA, localY);
+        const float s1 = Cross(d + rA, perp), s2 = Cross(rB, perp);
+        const float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+        const float k12 = iA * s1 + iB * s2;
+        const float k13 = iA * s1 * a1 + iB * s2 * a2;
+        float k22 = iA + iB;
+        if (k22 == 0.0f) k22 = 1.0f;
+        const float k23 = iA * a1 + iB * a2;
+        const float k33 = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+        int limitState = ji.z;
+        if (ji.x & kJointEnableLimit) {
+            const float jointTranslation = Dot(axis, d);
+            if (Abs(f1.z - f1.y) < 2.0f * kLinearSlop) {
+                limitState = kLimitEqual;
+            } else if (jointTranslation <= f1.y) {
+                if (limitState != kLimitAtLower) {
+                    limitState = kLimitAtLower;
+                    imp.z = 0.0f;
+                }
+            } else if (jointTranslation >= f1.z) {
+                if (limitState != kLimitAtUpper) {
+                    limitState = kLimitAtUpper;
+                    imp.z = 0.0f;
+                }
+            } else {
+                limitState = kLimitInactive;
+                imp.z = 0.0f;
+            }
+        } else {
+            limitState = kLimitInactive;
+            imp.z = 0.0f;
+        }
+        if (limitState != ji.z) {
+            ji.z = limitState;
+            c.jI[j] = ji;
+        }
+        if ((ji.x & kJointEnableMotor) == 0) imp.w = 0.0f;
+        if (warmStarting) {
+            imp.x *= dtRatio; imp.y *= dtRatio; imp.z *= dtRatio;
+            imp.w *= dtRatio;
+            const Vec2 P = imp.x * perp + (imp.w + imp.z) * axis;
+            const float LA = imp.x * s1 + imp.y + (imp.w + imp.z) * a1;
+            const float LB = imp.x * s2 + imp.y + (imp.w + imp.z) * a2;
+            vA = vA - mA * P;
+            wA -= iA * LA;
+            vB = vB + mB * P;
+            wB += iB * LB;
+        } else {
+            imp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        c.jTmp[t + 0] = make_float4(axis.x, axis.y, perp.x, perp.y);
+        c.jTmp[t + 1] = make_float4(a1, a2, s1, s2);
+        c.jTmp[t + 2] = make_float4(k11, k12, k13, motorMass);
+        c.jTmp[t + 3] = make_float4(k12, k22, k23, 0.0f);
+        c.jTmp[t + 4] = make_float4(k13, k23, k33, 0.0f);
+    }
+    c.jImp[j] = imp;
+    c.bodyVel[bA] = make_float4(vA.x, vA.y, wA, 0.0f);
+    c.bodyVel[bB] = make_float4(vB.x, vB.y, wB, 0.0f);
+}
+
+// ---- SolveVelocityConstraints ----------------------------------------------------------------------------------
+__device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, float h) {
+    const JointCols& c = *cp;
+    const int4 ji = c.jI[j];
+    const int type = ji.x & 0xff;
+    const int bA = ji.y & 0xffff, bB = (ji.y >> 16) & 0xffff;
+    const float4 msA = c.bodyMass[bA], msB = c.bodyMass[bB];
+    const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
+    float4 velA = c.bodyVel[bA], velB = c.bodyVel[bB];
+    Vec2 vA = V2(velA.x, velA.y), vB = V2(velB.x, velB.y);
+    float wA = velA.z, wB = velB.z;
+    float4 imp = c.jImp[j];
+    const size_t t = (size_t)j * kJointTmp;
+    const int limitState = ji.z;
+
+    if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:178-277
+        const float4 f1 = c.jF1[j], f2 = c.jF2[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2], t3 = c.jTmp[t + 3];
+        const Vec2 rA = V2(t0.x, t0.y), rB = V2(t0.z, t0.w);
+        Mat33 M;
+        M.ex = V3(t1.x, t1.y, t1.z); M.ey = V3(t2.x, t2.y, t2.z); M.ez = V3(t3.x, t3.y, t3.z);
+        const float motorMass = t1.w;
+        const bool fixedRotation = (iA + iB == 0.0f);
+        if ((ji.x & kJointEnableMotor) && limitState != kLimitEqual && !fixedRotation) {
+            const float Cdot = wB - wA - f2.x;
+            float impulse = -motorMass * Cdot;
+            const float oldImpulse = imp.w;
+            const float maxImpulse = h * f1.w;
+            imp.w = Clamp(imp.w + impulse, -maxImpulse, maxImpulse);
+            impulse = imp.w - oldImpulse;
+            wA -= iA * impulse;
+            wB += iB * impulse;
+        }
+        if ((ji.x & kJointEnableLimit) && limitState != kLimitInactive && !fixedRotation) {
+            const Vec2 Cdot1 = vB + Cross(wB, rB) - vA - Cross(wA, rA);
+            const float Cdot2 = wB - wA;
+            const Vec3 s = Solve33(M, V3(Cdot1.x, Cdot1.y, Cdot2));
+            Vec3 impulse = V3(-s.x, -s.y, -s.z);
+            if (limitState == kLimitEqual) {
+                imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z;
+            } else if (limitState == kLimitAtLower) {
+                const float newImpulse = imp.z + impulse.z;
+                if (newImpulse < 0.0f) {
+                    const Vec2 rhs = -Cdot1 + imp.z * V2(M.ez.x, M.ez.y);
+                    const Vec2 reduced = Solve22(M.ex.x, M.ey.x, M.ex.y, M.ey.y, rhs);
+                    impulse.x = reduced.x;
+                    impulse.y = reduced.y;
+                    impulse.z = -imp.z;
+                    imp.x += reduced.x;
+                    imp.y += reduced.y;
+                    imp.z = 0.0f;
+                } else {
+                    imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z;
+                }
+            } else if (limitState == kLimitAtUpper) {
+                const float newImpulse = imp.z + impulse.z;
+                if (newImpulse > 0.0f) {
+                    const Vec2 rhs = -Cdot1 + imp.z * V2(M.ez.x, M.ez.y);
+                    const Vec2 reduced = Solve22(M.ex.x, M.ey.x, M.ex.y, M.ey.y, rhs);
+                    impulse.x = reduced.x;
+                    impulse.y = reduced.y;
+                    impulse.z = -imp.z;
+                    imp.x += reduced.x;
+                    imp.y += reduced.y;
+                    imp.z = 0.0f;
+                } else {
+                    imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z;
+                }
+            }
+            const Vec2 P = V2(impulse.x, impulse.y);
+            vA = vA - mA * P;
+            wA -= iA * (Cross(rA, P) + impulse.z);
+            vB = vB + mB * P;
+            wB += iB * (Cross(rB, P) + impulse.z);
+        } else {
+            const Vec2 Cdot = vB + Cross(wB, rB) - vA - Cross(wA, rA);
+            const Vec2 impulse = Solve22(M.ex.x, M.ey.x, M.ex.y, M.ey.y, -Cdot);
+            imp.x += impulse.x;
+            imp.y += impulse.y;
+            vA = vA - mA * impulse;
+            wA -= iA * Cross(rA, impulse);
+            vB = vB + mB * impulse;
+            wB += iB * Cross(rB, impulse);
+        }
+    } else if (type == B2G_JOINT_DISTANCE) {  // b2DistanceJoint.cpp:154-181
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2];
+        const Vec2 rA = V2(t0.x, t0.y), rB = V2(t0.z, t0.w), u = V2(t1.x, t1.y);
+        const Vec2 vpA = vA + Cross(wA, rA);
+        const Vec2 vpB = vB + Cross(wB, rB);
+        const float Cdot = Dot(u, vpB - vpA);
+        const float impulse = -t1.z * (Cdot + t2.x + t1.w * imp.x);
+        imp.x += impulse;
+        const Vec2 P = impulse * u;
+        vA = vA - mA * P;
+        wA -= iA * Cross(rA, P);
+        vB = vB + mB * P;
+        wB += iB * Cross(rB, P);
+    } else {  // prismatic — b2PrismaticJoint.cpp:266-372
+        const float4 f1 = c.jF1[j], f2 = c.jF2[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2], t3 = c.jTmp[t + 3], t4 = c.jTmp[t + 4];
+        const Vec2 axis = V2(t0.x, t0.y), perp = V2(t0.z, t0.w);
+        const float a1 = t1.x, a2 = t1.y, s1 = t1.z, s2 = t1.w;
+        Mat33 K;
+        K.ex = V3(t2.x, t2.y, t2.z); K.ey = V3(t3.x, t3.y, t3.z); K.ez = V3(t4.x, t4.y, t4.z);
+        const float motorMass = t2.w;
+        if ((ji.x & kJointEnableMotor) && limitState != kLimitEqual) {
+            const float Cdot = Dot(axis, vB - vA) + a2 * wB - a1 * wA;
+            float impulse = motorMass * (f2.x - Cdot);
+            const float oldImpulse = imp.w;
+            const float maxImpulse = h * f1.w;
+            imp.w = Clamp(imp.w + impulse, -maxImpulse, maxImpulse);
+            impulse = imp.w - oldImpulse;
+            const Vec2 P = impulse * axis;
+            const float LA = impulse * a1;
+            const float LB = impulse * a2;
+            vA = vA - mA * P;
+            wA -= iA * LA;
+            vB = vB + mB * P;
+            wB += iB * LB;
+        }
+        Vec2 Cdot1;
+        Cdot1.x = Dot(perp, vB - vA) + s2 * wB - s1 * wA;
+        Cdot1.y = wB - wA;
+        if ((ji.x & kJointEnableLimit) && limitState != kLimitInactive) {
+            const float Cdot2 = Dot(axis, vB - vA) + a2 * wB - a1 * wA;
+            const Vec3 f1v = V3(imp.x, imp.y, imp.z);
+            Vec3 df = Solve33(K, V3(-Cdot1.x, -Cdot1.y, -Cdot2));
+            imp.x += df.x; imp.y += df.y; imp.z += df.z;
+            if (limitState == kLimitAtLower) imp.z = Max(imp.z, 0.0f);
+            else if (limitState == kLimitAtUpper) imp.z = Min(imp.z, 0.0f);
+            const Vec2 b = -Cdot1 - (imp.z - f1v.z) * V2(K.ez.x, K.ez.y);
+            const Vec2 f2r = Solve22(K.ex.x, K.ey.x, K.ex.y, K.ey.y, b) + V2(f1v.x, f1v.y);
+            imp.x = f2r.x;
+            imp.y = f2r.y;
+            df = V3(imp.x - f1v.x, imp.y - f1v.y, imp.z - f1v.z);
+            const Vec2 P = df.x * perp + df.z * axis;
+            const float LA = df.x * s1 + df.y + df.z * a1;
+            const float LB = df.x * s2 + df.y + df.z * a2;
+            vA = vA - mA * P;
+            wA -= iA * LA;
+            vB = vB + mB * P;
+            wB += iB * LB;
+        } else {
+            const Vec2 df = Solve22(K.ex.x, K.ey.x, K.ex.y, K.ey.y, -Cdot1);
+            imp.x += df.x;
+            imp.y += df.y;
+            const Vec2 P = df.x * perp;
+            const float LA = df.x * s1 + df.y;
+            const float LB = df.x * s2 + df.y;
+            vA = vA - mA * P;
+            wA -= iA * LA;
+            vB = vB + mB * P;
+            wB += iB * LB;
+        }
+    }
+    c.jImp[j] = imp;
+    c.bodyVel[bA] = make_float4(vA.x, vA.y, wA, 0.0f);
+    c.bodyVel[bB] = make_float4(vB.x, vB.y, wB, 0.0f);
+}
+
+// ---- SolvePositionConstraints; returns the joint's "okay" -------------------------------------------------------------
+__device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
+    const JointCols& c = *cp;
+    const int4 ji = c.jI[j];
+    const int type = ji.x & 0xff;
+    const int bA = ji.y & 0xffff, bB = (ji.y >> 16) & 0xffff;
+    const float4 f0 = c.jF0[j], f1 = c.jF1[j];
+    const float4 msA = c.bodyMass[bA], msB = c.bodyMass[bB];
+    const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
+    float4 swA = c.bodySweep[bA], swB = c.bodySweep[bB];
+    Vec2 cA = V2(swA.x, swA.y), cB = V2(swB.x, swB.y);
+    float aA = swA.z, aB = swB.z;
+    const Vec2 lA = V2(f0.x, f0.y) - V2(msA.z, msA.w), lB = V2(f0.z, f0.w) - V2(msB.z, msB.w);
+    const int limitState = ji.z;
+    bool okay;
+
+    if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:279-371
+        float angularError = 0.0f, positionError = 0.0f;
+        const bool fixedRotation = (iA + iB == 0.0f);
+        if ((ji.x & kJointEnableLimit) && limitState != kLimitInactive && !fixedRotation) {
+            const float motorMass = c.jTmp[(size_t)j * kJointTmp + 1].w;
+            const float angle = aB - aA - f1.x;
+            float limitImpulse = 0.0f;
+            if (limitState == kLimitEqual) {
+                const float C = Clamp(angle - f1.y, -kMaxAngularCorrection, kMaxAngularCorrection);
+                limitImpulse = -motorMass * C;
+                angularError = Abs(C);
+            } else if (limitState == kLimitAtLower) {
+                float C = angle - f1.y;
+                angularError = -C;
+                C = Clamp(C + kAngularSlop, -kMaxAngularCorrection, 0.0f);
+                limitImpulse = -motorMass * C;
+            } else if (limitState == kLimitAtUpper) {
+                float C = angle - f1.z;
+                angularError = C;
+                C = Clamp(C - kAngularSlop, 0.0f, kMaxAngularCorrection);
+                limitImpulse = -motorMass * C;
+            }
+            aA -= iA * limitImpulse;
+            aB += iB * limitImpulse;
+        }
+        {
+            const Rot qA = MakeRot(aA), qB = MakeRot(aB);
+            const Vec2 rA = Mul(qA, lA), rB = Mul(qB, lB);
+            const Vec2 C = cB + rB - cA - rA;
+            positionError = Length(C);
+            const float k11 = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+            const float k12 = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+            const float k22 = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+            const Vec2 s = Solve22(k11, k12, k12, k22, C);
+            const Vec2 impulse = -s;
+            cA = cA - mA * impulse;
+            aA -= iA * Cross(rA, impulse);
+            cB = cB + mB * impulse;
+            aB += iB * Cross(rB, impulse);
+        }
+        okay = positionError <= kLinearSlop && angularError <= kAngularSlop;
+    } else if (type == B2G_JOINT_DISTANCE) {  // b2DistanceJoint.cpp:183-220
+        if (f1.y > 0.0f) return true;  // soft constraint: no position correction
+        const float mass = c.jTmp[(size_t)j * kJointTmp + 1].z;
+        const Rot qA = MakeRot(aA), qB = MakeRot(aB);
+        const Vec2 rA = Mul(qA, lA), rB = Mul(qB, lB);
+        Vec2 u = cB + rB - cA - rA;
+        const float length = Normalize(u);
+        float C = length - f1.x;
+        C = Clamp(C, -kMaxLinearCorrection, kMaxLinearCorrection);
+        const float impulse = -mass * C;
+        const Vec2 P = impulse * u;
+        cA = cA - mA * P;
+        aA -= iA * Cross(rA, P);
+        cB = cB + mB * P;
+        aB += iB * Cross(rB, P);
+        okay = Abs(C) < kLinearSlop;
+    } else {  // prismatic — b2PrismaticJoint.cpp:374-491
+        const float4 f2 = c.jF2[j];
+        const Rot qA = MakeRot(aA), qB = MakeRot(aB);
+        const Vec2 rA = Mul(qA, lA), rB = Mul(qB, lB);
+        const Vec2 d = cB + rB - cA - rA;
+        const Vec2 localX = V2(f2.y, f2.z), localY = Cross(1.0f, localX);
+        const Vec2 axis = Mul(qA, localX);
+        const float a1 = Cross(d + rA, axis), a2 = Cross(rB, axis);
+        const Vec2 perp = Mul(qA, localY);
+        const float s1 = Cross(d + rA, perp), s2 = Cross(rB, perp);
+        Vec3 impulse;
+        Vec2 C1;
+        C1.x = Dot(perp, d);
+        C1.y = aB - aA - f1.x;
+        float linearError = Abs(C1.x);
+        const float angularError = Abs(C1.y);
+        bool active = false;
+        float C2 = 0.0f;
+        if (ji.x & kJointEnableLimit) {
+            const float translation = Dot(axis, d);
+            if (Abs(f1.z - f1.y) < 2.0f * kLinearSlop) {
+                C2 = Clamp(translation, -kMaxLinearCorrection, kMaxLinearCorrection);
+                linearError = Max(linearError, Abs(translation));
+                active = true;
+            } else if (translation <= f1.y) {
+                C2 = Clamp(translation - f1.y + kLinearSlop, -kMaxLinearCorrection, 0.0f);
+                linearError = Max(linearError, f1.y - translation);
+                active = true;
+            } else if (translation >= f1.z) {
+                C2 = Clamp(translation - f1.z - kLinearSlop, 0.0f, kMaxLinearCorrection);
+                linearError = Max(linearError, translation - f1.z);
+                active = true;
+            }
+        }
+        if (active) {
+            const float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+            const float k12 = iA * s1 + iB * s2;
+            const float k13 = iA * s1 * a1 + iB * s2 * a2;
+            float k22 = iA + iB;
+            if (k22 == 0.0f) k22 = 1.0f;
+            const float k23 = iA * a1 + iB * a2;
+            const float k33 = mA + mB + iA * a1 * a1 + iB * a2 * a2;
+            Mat33 K;
+            K.ex = V3(k11, k12, k13); K.ey = V3(k12, k22, k23); K.ez = V3(k13, k23, k33);
+            impulse = Solve33(K, V3(-C1.x, -C1.y, -C2));
+        } else {
+            const float k11 = mA + mB + iA * s1 * s1 + iB * s2 * s2;
+            const float k12 = iA * s1 + iB * s2;
+            float k22 = iA + iB;
+            if (k22 == 0.0f) k22 = 1.0f;
+            const Vec2 impulse1 = Solve22(k11, k12, k12, k22, -C1);
+            impulse = V3(impulse1.x, impulse1.y, 0.0f);
+        }
+        const Vec2 P = impulse.x * perp + impulse.z * axis;
+        const float LA = impulse.x * s1 + impulse.y + impulse.z * a1;
+        const float LB = impulse.x * s2 + impulse.y + impulse.z * a2;
+        cA = cA - mA * P;
+        aA -= iA * LA;
+        cB = cB + mB * P;
+        aB += iB * LB;
+        okay = linearError <= kLinearSlop && angularError <= kAngularSlop;
+    }
+    c.bodySweep[bA] = make_float4(cA.x, cA.y, aA, swA.w);
+    c.bodySweep[bB] = make_float4(cB.x, cB.y, aB, swB.w);
+    return okay;
+}

@@ -453,9 +453,10 @@ constexpr int kIslandThreads = 128;
 enum : int { kIbType = 3, kIbAwake = 4, kIbActive = 8, kIbIsland = 16, kIbWoken = 32 };  // smem body flag byte
 enum : int { kIcEligible = 1, kIcIsland = 2 };                                              // smem contact flag byte
 
-__host__ __device__ inline size_t IslandSmemPerWorld(int NB, int NC) {
-    // next[2*NC] u16, pair[NC] 2 x u16, contact flag u8, head[NB] u16, stack[NB] u16, body flag u8
-    return (size_t)NC * 9 + (size_t)NB * 5;
+__host__ __device__ inline size_t IslandSmemPerWorld(int NB, int NC, int NJ) {
+    // next[2*NC] u16, pair[NC] 2 x u16, contact flag u8, head[NB] u16, stack[NB] u16, body flag u8;
+    // with joints: the same three arrays per joint (NJ * 9, rounded up to keep the u16 arrays aligned) and a joint head per body
+    return (size_t)NC * 9 + (size_t)NB * 5 + (NJ > 0 ? (size_t)((NJ + 1) & ~1) * 9 + (size_t)NB * 2 : 0);
 }
 
 __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
@@ -470,8 +471,16 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
     uint16_t* sPair = sNext + (size_t)2 * NC * L;                      // [2 * NC][L]: bodyA at 2k, bodyB at 2k + 1
     uint16_t* sHead = sPair + (size_t)2 * NC * L;                      // [NB][L]
     uint16_t* sStack = sHead + (size_t)NB * L;                         // [NB][L]
-    unsigned char* sCF = reinterpret_cast<unsigned char*>(sStack + (size_t)NB * L);  // [NC][L]
+    // joints (only when the batch has any): b2Body::m_jointList as head-inserted edge lists, like the contacts
+    const int NJ = A.NJ, NJe = (A.NJ + 1) & ~1;
+    const bool joints = A.hasJoints != 0;
+    uint16_t* sJNext = sStack + (size_t)NB * L;                        // [2 * NJe][L]
+    uint16_t* sJPair = sJNext + (joints ? (size_t)2 * NJe * L : 0);    // [2 * NJe][L]
+    uint16_t* sJHead = sJPair + (joints ? (size_t)2 * NJe * L : 0);    // [NB][L]
+    unsigned char* sCF = reinterpret_cast<unsigned char*>(sJHead + (joints ? (size_t)NB * L : 0));  // [NC][L]
     unsigned char* sBF = sCF + (size_t)NC * L;                         // [NB][L]
+    unsigned char* sJF = sBF + (size_t)NB * L;                         // [NJe][L]: joint already in an island
+    (void)NJ;
 
     if (t < L) {
         const int w = w0 + t;
@@ -506,6 +515,17 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
         const int f = bodyFlags[b];
         sBF[(size_t)b * L + l] = (unsigned char)((f & kBodyTypeMask) | ((f & kBodyAwake) ? kIbAwake : 0) | ((f & kBodyActive) ? kIbActive : 0));
         sHead[(size_t)b * L + l] = 0xffff;
+        if (joints) sJHead[(size_t)b * L + l] = 0xffff;
+    }
+    const int nj = (mine && joints) ? A.jointCount[ws] : 0;
+    if (joints) {
+        Col<int4> jI = col(A.jointI, tile, A.NJ, lane);
+        for (int j = t / L; j < nj; j += stride) {
+            const int bodies = jI[j].y;
+            sJPair[(size_t)(2 * j) * L + l] = (uint16_t)(bodies & 0xffff);
+            sJPair[(size_t)(2 * j + 1) * L + l] = (uint16_t)((bodies >> 16) & 0xffff);
+            sJF[(size_t)j * L + l] = 0;
+        }
     }
     __syncthreads();
 
@@ -519,11 +539,21 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
             sNext[(size_t)(2 * k + 1) * L + l] = sHead[(size_t)bB * L + l];
             sHead[(size_t)bB * L + l] = (uint16_t)k;
         }
+        // b2Body::m_jointList: CreateJoint links edge A into bodyA's list, then edge B into bodyB's (b2World.cpp:232-246)
+        for (int j = 0; j < nj; ++j) {
+            const int bA = sJPair[(size_t)(2 * j) * L + l], bB = sJPair[(size_t)(2 * j + 1) * L + l];
+            sJNext[(size_t)(2 * j) * L + l] = sJHead[(size_t)bA * L + l];
+            sJHead[(size_t)bA * L + l] = (uint16_t)j;
+            sJNext[(size_t)(2 * j + 1) * L + l] = sJHead[(size_t)bB * L + l];
+            sJHead[(size_t)bB * L + l] = (uint16_t)j;
+        }
         Col<int> iBodies = col(A.islandBodies, tile, NB + NC, lane);
         Col<int> iBodyEnd = col(A.islandBodyEnd, tile, NB, lane);
         Col<int> iContacts = col(A.islandContacts, tile, NC, lane);
         Col<int> iContactEnd = col(A.islandContactEnd, tile, NB, lane);
-        int islands = 0, nBodies = 0, nContacts = 0;
+        Col<int> iJoints = col(A.islandJoints, tile, A.NJ, lane);
+        Col<int> iJointEnd = col(A.islandJointEnd, tile, NB, lane);
+        int islands = 0, nBodies = 0, nContacts = 0, nJoints = 0;
         bool wokeAny = false;
         for (int seed = nb - 1; seed >= 0; --seed) {  // m_bodyList is head-inserted: newest first
             const int sf = sBF[(size_t)seed * L + l];
@@ -561,6 +591,25 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
                     }
                     k = kn;
                 }
+                // search all joints connected to this body (b2World.cpp:497-525)
+                for (int j = joints ? sJHead[(size_t)b * L + l] : 0xffff; j != 0xffff;) {
+                    const int bA = sJPair[(size_t)(2 * j) * L + l], bB = sJPair[(size_t)(2 * j + 1) * L + l];
+                    const int side = bA == b ? 0 : 1;
+                    const int jn = sJNext[(size_t)(2 * j + side) * L + l];
+                    if (sJF[(size_t)j * L + l] == 0) {
+                        const int other = side == 0 ? bB : bA;
+                        const int of = sBF[(size_t)other * L + l];
+                        if (of & kIbActive) {  // don't simulate joints connected to inactive bodies
+                            iJoints[nJoints++] = j;
+                            sJF[(size_t)j * L + l] = 1;
+                            if ((of & kIbIsland) == 0) {
+                                sStack[(size_t)(stackCount++) * L + l] = (uint16_t)other;
+                                sBF[(size_t)other * L + l] = (unsigned char)(of | kIbIsland);
+                            }
+                        }
+                    }
+                    j = jn;
+                }
             }
             // statics may join the next island
             for (int i = islandBody0; i < nBodies; ++i) {
@@ -570,6 +619,7 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
             }
             iBodyEnd[islands] = nBodies;
             iContactEnd[islands] = nContacts;
+            if (joints) iJointEnd[islands] = nJoints;
             ++islands;
         }
         A.islandCount[ws] = islands;
@@ -987,6 +1037,8 @@ __device__ __forceinline__ void SolvePositionConstraint(const Arena& A, int tile
 // k_solve
 // =================================================================================================
 
+#include "b2g_joints.cuh"
+
 __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, int posIters) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     int tile = w >> 5, lane = w & 31;
@@ -1024,9 +1076,14 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
     EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws],
                  A.NE, A.eventMask};
 
-    int b0 = 0, c0 = 0;
+    const bool joints = A.hasJoints != 0 && A.jointCount[ws] > 0;
+    const JointCols jc = MakeJointCols(A, tile, lane);
+    Col<int> iJoints = col(A.islandJoints, tile, A.NJ, lane);
+    Col<int> iJointEnd = col(A.islandJointEnd, tile, A.NB, lane);
+    int b0 = 0, c0 = 0, j0 = 0;
     for (int isl = 0; isl < islands; ++isl) {
         const int b1 = iBodyEnd[isl], c1 = iContactEnd[isl];
+        const int j1 = joints ? iJointEnd[isl] : 0;
 
         // ---- integrate velocities (b2Island.cpp:190-225); positions/velocities stay in the body arrays ----
         for (int i = b0; i < b1; ++i) {
@@ -1059,9 +1116,14 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
         if (warmStarting)
             for (int i = c0; i < c1; ++i) WarmStartConstraint(vc, bodyVel, i);
 
-        // ---- SolveVelocityConstraints (b2ContactSolver.cpp:280-597) ----
-        for (int it = 0; it < velIters; ++it)
+        // ---- joints: InitVelocityConstraints, after the contacts' warm start (b2Island.cpp:252-255) ----
+        for (int i = j0; i < j1; ++i) JointInitVelocity(&jc, iJoints[i], h, dtRatio, warmStarting);
+
+        // ---- SolveVelocityConstraints: joints, then contacts (b2Island.cpp:260-269, b2ContactSolver.cpp:280-597) ----
+        for (int it = 0; it < velIters; ++it) {
+            for (int i = j0; i < j1; ++i) JointSolveVelocity(&jc, iJoints[i], h);
             for (int i = c0; i < c1; ++i) SolveVelocityConstraint(vc, bodyVel, i);
+        }
 
         // ---- StoreImpulses (b2ContactSolver.cpp:599-612) + Report/PostSolve (b2Island.cpp:517-540) ----
         for (int i = c0; i < c1; ++i) {
@@ -1113,7 +1175,13 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
             float minSeparation = 0.0f;
             for (int i = c0; i < c1; ++i)
                 SolvePositionConstraint(A, tile, lane, vc, i, iContacts[i], kBaumgarte, false, -1, -1, &minSeparation);
-            if (minSeparation >= -3.0f * kLinearSlop) {
+            const bool contactsOkay = minSeparation >= -3.0f * kLinearSlop;
+            bool jointsOkay = true;
+            for (int i = j0; i < j1; ++i) {
+                const bool jointOkay = JointSolvePosition(&jc, iJoints[i]);
+                jointsOkay = jointsOkay && jointOkay;
+            }
+            if (contactsOkay && jointsOkay) {
                 positionSolved = true;
                 break;
             }
@@ -1184,6 +1252,7 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
         }
         b0 = b1;
         c0 = c1;
+        j0 = j1;
     }
 }
 
@@ -1250,8 +1319,18 @@ __device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB, bool
         }
     }
     int bfA = c.bodyFlags[bodyA], bfB = c.bodyFlags[bodyB];
-    // b2Body::ShouldCollide (no joints): at least one dynamic body
+    // b2Body::ShouldCollide (b2Body.cpp:395-416): at least one dynamic body, and no joint between the two bodies that
+    // has collideConnected == false
     if ((bfA & kBodyTypeMask) != B2G_DYNAMIC_BODY && (bfB & kBodyTypeMask) != B2G_DYNAMIC_BODY) return;
+    if (c.A.hasJoints) {
+        Col<int4> jI = col(c.A.jointI, c.tile, c.A.NJ, c.lane);
+        const int nj = c.A.jointCount[c.ws];
+        const int ab = bodyA | (bodyB << 16), ba = bodyB | (bodyA << 16);
+        for (int j = 0; j < nj; ++j) {
+            const int4 ji = jI[j];
+            if ((ji.y == ab || ji.y == ba) && (ji.x & (1 << 8)) == 0) return;
+        }
+    }
     if (!FilterShouldCollide(c.fixtureFilter[fixtureA], c.fixtureFilter[fixtureB])) return;
     int tA = (fiA >> 16) & 3, tB = (fiB >> 16) & 3;
     int reg = ContactRegister(tA, tB);

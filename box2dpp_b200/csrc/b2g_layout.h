@@ -63,7 +63,7 @@ enum : int { kEventBegin = 0, kEventEnd = 1, kEventPreSolve = 2, kEventPostSolve
 struct Arena {
     int numWorlds, numTiles;
     // capacities per world
-    int NB, NF, NP, NC, NS, NV, NE;
+    int NB, NF, NP, NC, NS, NV, NE, NJ;
 
     // ---- world scalars [tile][lane] ----
     float2* gravity;
@@ -113,6 +113,17 @@ struct Arena {
     float4* contactP1;   // points[1]
     float4* contactN;    // localNormal.xy, localPoint.xy
 
+    // ---- joints [tile][NJ][lane], creation order (b2World::m_jointList is that array walked backwards) ----
+    int* jointCount;     // [tile][lane]
+    int4* jointI;        // type | collideConnected << 8 | enableLimit << 9 | enableMotor << 10, bodyA | bodyB << 16, m_limitState, 0
+    float4* jointF0;     // localAnchorA.xy, localAnchorB.xy
+    float4* jointF1;     // referenceAngle, lower, upper, maxMotorTorque|Force   (distance: length, frequencyHz, dampingRatio)
+    float4* jointF2;     // motorSpeed, localXAxisA.xy
+    float4* jointImp;    // m_impulse.xyz, m_motorImpulse
+    float4* jointTmp;    // [tile][NJ * 5][lane] solver temporaries of the step (b2g_joints.cuh)
+    int* islandJoints;   // [tile][NJ][lane] joint indices in solver order, concatenated over islands
+    int* islandJointEnd; // [tile][NB][lane]
+
     // ---- per-step temporaries ----
     int* movedList;      // [tile][NP][lane] ascending indices of the proxies in the move buffer
     int* islandBodies;   // [tile][NB+NC][lane] bodies of all islands, concatenated (statics repeat)
@@ -145,6 +156,7 @@ struct Arena {
     int4* eventA;        // type, fixtureA | childA << 16, fixtureB | childB << 16, count
     float4* eventB;      // normalImpulses[2], tangentImpulses[2]
     int eventMask;       // bit per kEvent* type recorded
+    int hasJoints;       // desc.maxJoints > 0: the joint arrays are live (generic solver path)
     int alwaysRebuildIslands;  // validation switch: k_islands ignores topoDirty (desc.reserved bit 1)
 };
 

@@ -31,6 +31,7 @@ constexpr float kAabbExtension = 0.1f;
 constexpr float kAabbMultiplier = 2.0f;
 constexpr float kVelocityThreshold = 1.0f;
 constexpr float kMaxLinearCorrection = 0.2f;
+constexpr float kMaxAngularCorrection = 8.0f / 180.0f * kPi;
 constexpr float kMaxTranslation = 2.0f;
 constexpr float kMaxTranslationSquared = kMaxTranslation * kMaxTranslation;
 constexpr float kMaxRotation = 0.5f * kPi;

@@ -377,6 +377,8 @@ int allocateArena(b2gpu_batch* b) {
     A.numTiles = (d.numWorlds + kTile - 1) / kTile;
     A.NB = d.maxBodies; A.NF = d.maxFixtures; A.NP = d.maxProxies; A.NC = d.maxContacts;
     A.NS = d.maxShapeWords; A.NV = d.maxChainVerts > 0 ? d.maxChainVerts : 1; A.NE = d.maxEvents > 0 ? d.maxEvents : 1;
+    A.NJ = d.maxJoints > 0 ? d.maxJoints : 1;
+    A.hasJoints = d.maxJoints > 0 ? 1 : 0;
     A.eventMask = d.eventMask;
     A.alwaysRebuildIslands = (d.reserved >> 1) & 1;
     ALLOC(gravity, 1, float2); ALLOC(worldFlags, 1, int); ALLOC(invDt0, 1, float);
@@ -409,6 +411,9 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(bodyProxyStart, A.NB + 1, int); ALLOC(bodyProxyList, A.NP, int); ALLOC(toiBodies, kToiBodyCap, int); ALLOC(toiContacts, kMaxToiContacts, int);
     ALLOC(toiVc, (size_t)kMaxToiContacts * kVcStride, float4);
     ALLOC(eventA, A.NE, int4); ALLOC(eventB, A.NE, float4);
+    ALLOC(jointCount, 1, int); ALLOC(jointI, A.NJ, int4); ALLOC(jointF0, A.NJ, float4); ALLOC(jointF1, A.NJ, float4);
+    ALLOC(jointF2, A.NJ, float4); ALLOC(jointImp, A.NJ, float4); ALLOC(jointTmp, (size_t)A.NJ * kJointTmp, float4);
+    ALLOC(islandJoints, A.NJ, int); ALLOC(islandJointEnd, A.NB, int);
 
     b->fields.assign(B2GPU_F_COUNT, Field{nullptr, 0, 0});
     auto F = [&](int id, void** p, int cap, int comps) { b->fields[id] = Field{p, cap, comps}; };
@@ -449,6 +454,12 @@ int allocateArena(b2gpu_batch* b) {
     F(B2GPU_F_EVENT_B, (void**)&A.eventB, A.NE, 4);
     F(B2GPU_F_ISLAND_CONTACTS, (void**)&A.islandContacts, A.NC, 1);
     F(B2GPU_F_ISLAND_CONTACT_END, (void**)&A.islandContactEnd, A.NB, 1);
+    F(B2GPU_F_JOINT_COUNT, (void**)&A.jointCount, 1, 1);
+    F(B2GPU_F_JOINT_I, (void**)&A.jointI, A.NJ, 4);
+    F(B2GPU_F_JOINT_F0, (void**)&A.jointF0, A.NJ, 4);
+    F(B2GPU_F_JOINT_F1, (void**)&A.jointF1, A.NJ, 4);
+    F(B2GPU_F_JOINT_F2, (void**)&A.jointF2, A.NJ, 4);
+    F(B2GPU_F_JOINT_IMPULSE, (void**)&A.jointImp, A.NJ, 4);
     return B2GPU_OK;
 }
 
@@ -493,7 +504,8 @@ int configureKernels(b2gpu_batch* b) {
     CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
     // Solver path: the tile path keeps the b2Velocity / b2Position table of 32 worlds in shared memory.
     b->solveSmem = SolveSmemBytes(desc->maxBodies);
-    b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0;
+    // joints are solved by the generic kernel only (b2g_joints.cuh)
+    b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0 && desc->maxJoints <= 0;
     if ((size_t)desc->maxContacts * kTile > (size_t)maxSmem - 1024)
         return fail(B2GPU_ERR_CAPACITY, "maxContacts %d exceeds the collide kernel's shared-memory budget (%d)",
                     desc->maxContacts, (maxSmem - 1024) / kTile);
@@ -504,7 +516,7 @@ int configureKernels(b2gpu_batch* b) {
         CUDA_TRY(cudaFuncSetAttribute(k_solve_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
     }
     // k_islands: as many worlds per CTA as keep two or more CTAs resident per SM (the DFS is latency bound)
-    const size_t perWorld = IslandSmemPerWorld(desc->maxBodies, desc->maxContacts);
+    const size_t perWorld = IslandSmemPerWorld(desc->maxBodies, desc->maxContacts, desc->maxJoints > 0 ? desc->maxJoints : 0);
     int L = 32;
     while (L > 1 && perWorld * L > (size_t)100 * 1024) L >>= 1;
     if (perWorld * L > (size_t)maxSmem - 1024)

@@ -63,6 +63,31 @@ class FixtureDef(C.Structure):
     ]
 
 
+JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE = 1, 2, 3
+
+
+class JointDef(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("bodyA", C.c_int32),
+        ("bodyB", C.c_int32),
+        ("collideConnected", C.c_int32),
+        ("localAnchorA", C.c_float * 2),
+        ("localAnchorB", C.c_float * 2),
+        ("localAxisA", C.c_float * 2),
+        ("referenceAngle", C.c_float),
+        ("enableLimit", C.c_int32),
+        ("enableMotor", C.c_int32),
+        ("lower", C.c_float),
+        ("upper", C.c_float),
+        ("maxMotor", C.c_float),
+        ("motorSpeed", C.c_float),
+        ("length", C.c_float),
+        ("frequencyHz", C.c_float),
+        ("dampingRatio", C.c_float),
+    ]
+
+
 class CScene(C.Structure):
     _fields_ = [
         ("gravity", C.c_float * 2),
@@ -73,6 +98,9 @@ class CScene(C.Structure):
         ("bodies", C.POINTER(BodyDef)),
         ("fixtures", C.POINTER(FixtureDef)),
         ("vertices", C.POINTER(C.c_float)),
+        ("joints", C.POINTER(JointDef)),
+        ("jointCount", C.c_int32),
+        ("pad0", C.c_int32),
     ]
 
 
@@ -85,7 +113,61 @@ class Scene:
         self.bodies: list[BodyDef] = []
         self.fixtures: list[FixtureDef] = []
         self.vertices: list[float] = []
+        self.joints: list[JointDef] = []
         self._c = None
+
+    # ---- b2World::CreateJoint (Box2D/Dynamics/b2World.cpp:211-270) ----
+    def _local(self, body, point):
+        """b2Body::GetLocalPoint of a freshly created body (b2MulT(xf, p)) in float32."""
+        bd = self.bodies[body]
+        s, c = F32(np.sin(F32(bd.angle))), F32(np.cos(F32(bd.angle)))
+        px, py = F32(F32(point[0]) - F32(bd.position[0])), F32(F32(point[1]) - F32(bd.position[1]))
+        return float(F32(c * px) + F32(s * py)), float(F32(-s * px) + F32(c * py))
+
+    def _joint(self, type, body_a, body_b, collide_connected):
+        jd = JointDef()
+        jd.type, jd.bodyA, jd.bodyB, jd.collideConnected = type, body_a, body_b, int(collide_connected)
+        self.joints.append(jd)
+        self._c = None
+        return jd
+
+    def create_revolute_joint(self, body_a, body_b, anchor, lower=0.0, upper=0.0, enable_limit=False,
+                              max_motor_torque=0.0, motor_speed=0.0, enable_motor=False, collide_connected=False) -> int:
+        """b2RevoluteJointDef::Initialize(bodyA, bodyB, anchor) + the def's members (b2RevoluteJoint.cpp:38-45)."""
+        jd = self._joint(JOINT_REVOLUTE, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor)
+        jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor)
+        jd.referenceAngle = float(F32(self.bodies[body_b].angle) - F32(self.bodies[body_a].angle))
+        jd.lower, jd.upper, jd.enableLimit = lower, upper, int(enable_limit)
+        jd.maxMotor, jd.motorSpeed, jd.enableMotor = max_motor_torque, motor_speed, int(enable_motor)
+        return len(self.joints) - 1
+
+    def create_prismatic_joint(self, body_a, body_b, anchor, axis, lower=0.0, upper=0.0, enable_limit=False,
+                               max_motor_force=0.0, motor_speed=0.0, enable_motor=False, collide_connected=False) -> int:
+        """b2PrismaticJointDef::Initialize(bodyA, bodyB, anchor, axis) (b2PrismaticJoint.cpp:90-98)."""
+        jd = self._joint(JOINT_PRISMATIC, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor)
+        jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor)
+        bd = self.bodies[body_a]  # GetLocalVector(axis) = b2MulT(q, axis)
+        s, c = F32(np.sin(F32(bd.angle))), F32(np.cos(F32(bd.angle)))
+        ax, ay = F32(axis[0]), F32(axis[1])
+        jd.localAxisA[0], jd.localAxisA[1] = float(F32(c * ax) + F32(s * ay)), float(F32(-s * ax) + F32(c * ay))
+        jd.referenceAngle = float(F32(self.bodies[body_b].angle) - F32(self.bodies[body_a].angle))
+        jd.lower, jd.upper, jd.enableLimit = lower, upper, int(enable_limit)
+        jd.maxMotor, jd.motorSpeed, jd.enableMotor = max_motor_force, motor_speed, int(enable_motor)
+        return len(self.joints) - 1
+
+    def create_distance_joint(self, body_a, body_b, anchor_a, anchor_b, frequency_hz=0.0, damping_ratio=0.0,
+                              length=None, collide_connected=False) -> int:
+        """b2DistanceJointDef::Initialize(bodyA, bodyB, anchorA, anchorB) (b2DistanceJoint.cpp:40-49)."""
+        jd = self._joint(JOINT_DISTANCE, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor_a)
+        jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor_b)
+        if length is None:
+            dx, dy = F32(F32(anchor_b[0]) - F32(anchor_a[0])), F32(F32(anchor_b[1]) - F32(anchor_a[1]))
+            length = float(np.sqrt(F32(dx * dx) + F32(dy * dy), dtype=F32))
+        jd.length, jd.frequencyHz, jd.dampingRatio = length, frequency_hz, damping_ratio
+        return len(self.joints) - 1
 
     # ---- b2World::CreateBody ----
     def create_body(self, type=STATIC_BODY, position=(0.0, 0.0), angle=0.0, linear_velocity=(0.0, 0.0),
@@ -205,7 +287,11 @@ class Scene:
             cs.bodies = C.cast(bodies, C.POINTER(BodyDef))
             cs.fixtures = C.cast(fixtures, C.POINTER(FixtureDef))
             cs.vertices = C.cast(verts, C.POINTER(C.c_float))
-            self._c = (cs, bodies, fixtures, verts)  # keep the arrays alive
+            nj = len(self.joints)
+            joints = (JointDef * max(nj, 1))(*self.joints)
+            cs.joints = C.cast(joints, C.POINTER(JointDef))
+            cs.jointCount = nj
+            self._c = (cs, bodies, fixtures, verts, joints)  # keep the arrays alive
         return self._c[0]
 
 
@@ -366,6 +452,72 @@ def sensors(seed: int, flags=WORLD_DEFAULT, bodies=14) -> Scene:
     return s
 
 
+def jointed(seed: int, flags=WORLD_DEFAULT) -> Scene:
+    """Joint scene: every mechanism the device path solves, in one world so that islands mix joints
+    and contacts —
+      * a plank bridge (revolute joints, no limits) between two posts with boxes dropped on it (Testbed "Bridge"),
+      * a cart on a rail (prismatic joint with limits and a motor) carrying a pole (revolute joint): cart-pole,
+      * a two-legged walker (revolute joints with limits and motors, collideConnected off) standing on the ground,
+      * pendulums on rigid and soft distance joints, one pair of bodies tied by a distance joint with collideConnected.
+    All randomness from LCG(seed)."""
+    rng = LCG(seed)
+    s = Scene((0.0, -10.0), flags)
+    g = s.create_body(STATIC_BODY, (0.0, 0.0))
+    s.create_edge(g, (-40.0, 0.0), (40.0, 0.0))
+    # ---- bridge ----
+    n = 10
+    prev = g
+    x0, y0 = -18.0, 6.0
+    for i in range(n):
+        b = s.create_body(DYNAMIC_BODY, (x0 + 0.5 + 1.0 * i, y0))
+        s.create_box(b, 0.5, 0.125, density=20.0, friction=0.2)
+        s.create_revolute_joint(prev, b, (x0 + 1.0 * i, y0))
+        prev = b
+    s.create_revolute_joint(prev, g, (x0 + 1.0 * n, y0))
+    for k in range(3):
+        b = s.create_body(DYNAMIC_BODY, (x0 + 3.0 + 2.0 * k + rng.uniform(-0.2, 0.2), 8.0 + 1.5 * k), angle=rng.uniform(-0.5, 0.5))
+        if k % 2:
+            s.create_circle(b, 0.4, density=1.0)
+        else:
+            s.create_box(b, 0.4, 0.4, density=1.0)
+    # ---- cart-pole ----
+    cart = s.create_body(DYNAMIC_BODY, (0.0, 3.0))
+    s.create_box(cart, 0.6, 0.25, density=2.0)
+    s.create_prismatic_joint(g, cart, (0.0, 3.0), (1.0, 0.0), lower=-3.0, upper=3.0, enable_limit=True,
+                             max_motor_force=60.0, motor_speed=rng.uniform(1.0, 4.0) * (1 if seed % 2 else -1), enable_motor=True)
+    pole = s.create_body(DYNAMIC_BODY, (0.0, 4.0), angle=rng.uniform(-0.3, 0.3))
+    s.create_box(pole, 0.08, 1.0, density=1.0)
+    s.create_revolute_joint(cart, pole, (0.0, 3.0))
+    # ---- walker: torso + two legs of two segments ----
+    tx, ty = 10.0 + rng.uniform(-0.5, 0.5), 2.6
+    torso = s.create_body(DYNAMIC_BODY, (tx, ty))
+    s.create_box(torso, 0.7, 0.3, density=3.0)
+    for side in (-1, 1):
+        hipx = tx + 0.4 * side
+        thigh = s.create_body(DYNAMIC_BODY, (hipx, ty - 0.7))
+        s.create_box(thigh, 0.12, 0.5, density=1.0, friction=0.8)
+        s.create_revolute_joint(torso, thigh, (hipx, ty - 0.25), lower=-0.6, upper=0.8, enable_limit=True,
+                                max_motor_torque=40.0, motor_speed=1.5 * side, enable_motor=True)
+        shin = s.create_body(DYNAMIC_BODY, (hipx, ty - 1.65))
+        s.create_box(shin, 0.1, 0.5, density=1.0, friction=0.8)
+        s.create_revolute_joint(thigh, shin, (hipx, ty - 1.2), lower=-1.2, upper=0.05, enable_limit=True,
+                                max_motor_torque=20.0, motor_speed=-1.0 * side, enable_motor=(side > 0))
+    # ---- pendulums on distance joints ----
+    for k in range(4):
+        ax = 18.0 + 2.5 * k
+        bx = ax + 2.0 + rng.uniform(0.0, 0.5)
+        bob = s.create_body(DYNAMIC_BODY, (bx, 9.0))
+        s.create_circle(bob, 0.35, density=2.0)
+        s.create_distance_joint(g, bob, (ax, 10.0), (float(F32(bx)), 9.0),
+                                frequency_hz=(0.0 if k % 2 == 0 else 2.0 + k), damping_ratio=(0.0 if k % 2 == 0 else 0.3))
+    a = s.create_body(DYNAMIC_BODY, (30.0, 1.0))
+    s.create_box(a, 0.5, 0.5, density=1.0)
+    b = s.create_body(DYNAMIC_BODY, (31.5, 1.0), linear_velocity=(-3.0, 0.0))
+    s.create_box(b, 0.5, 0.5, density=1.0)
+    s.create_distance_joint(a, b, (30.0, 1.0), (31.5, 1.0), collide_connected=True)
+    return s
+
+
 class SceneBatch:
     """Many worlds that share fixtures/vertices and differ only in their body definitions.
 
@@ -391,6 +543,7 @@ class SceneBatch:
         s = Scene(self.base.gravity, self.base.flags)
         s.fixtures = self.base.fixtures
         s.vertices = self.base.vertices
+        s.joints = self.base.joints
         raw = self._bodies[i].tobytes()
         n = len(self.base.bodies)
         s.bodies = list((BodyDef * n).from_buffer_copy(raw))

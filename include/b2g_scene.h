@@ -96,6 +96,27 @@ typedef struct b2g_fixture_def {
     float vertex0[2], vertex3[2];
 } b2g_fixture_def;
 
+/* Joint types: the values of b2JointType (Box2D/Dynamics/Joints/b2Joint.h:31-45). */
+enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3 };
+
+/* The arguments of b2World::CreateJoint: the members of b2RevoluteJointDef (b2RevoluteJoint.h:35-86),
+ * b2PrismaticJointDef (b2PrismaticJoint.h:33-87) and b2DistanceJointDef (b2DistanceJoint.h:32-67), already in the
+ * bodies' local frames (what the defs' Initialize() helpers compute). */
+typedef struct b2g_joint_def {
+    int32_t type;             /* B2G_JOINT_* */
+    int32_t bodyA, bodyB;     /* indices into bodies[] */
+    int32_t collideConnected; /* b2JointDef::collideConnected, default false */
+    float localAnchorA[2], localAnchorB[2];
+    float localAxisA[2];      /* prismatic (normalised by the joint's constructor) */
+    float referenceAngle;     /* revolute, prismatic */
+    int32_t enableLimit, enableMotor;
+    float lower, upper;       /* revolute: lowerAngle / upperAngle; prismatic: lowerTranslation / upperTranslation */
+    float maxMotor;           /* revolute: maxMotorTorque; prismatic: maxMotorForce */
+    float motorSpeed;
+    float length;             /* distance */
+    float frequencyHz, dampingRatio; /* distance */
+} b2g_joint_def;
+
 typedef struct b2g_scene {
     float gravity[2];
     int32_t worldFlags;      /* B2G_WORLD_* */
@@ -105,6 +126,9 @@ typedef struct b2g_scene {
     const b2g_body_def* bodies;       /* creation order */
     const b2g_fixture_def* fixtures;  /* creation order (global, across bodies) */
     const float* vertices;            /* xy pairs */
+    const b2g_joint_def* joints;      /* b2World::CreateJoint calls in call order (may be NULL when jointCount == 0) */
+    int32_t jointCount;
+    int32_t pad0;
 } b2g_scene;
 
 #ifdef __cplusplus

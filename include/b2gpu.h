@@ -89,6 +89,7 @@ typedef struct b2gpu_batch_desc {
     int32_t blockSize;     /* threads per CTA, multiple of 32; 0 = default */
     int32_t reserved;      /* bit 0: force the generic solver kernel (body state in global memory);
                               bit 1: rebuild the islands every step (validation of the topology-dirty tracking) */
+    int32_t maxJoints;     /* per world; > 0 selects the generic solver kernel (joints are solved there) */
 } b2gpu_batch_desc;
 
 /* Arena fields reachable through upload/download.  Host layout is world-major:
@@ -131,6 +132,14 @@ enum {
     B2GPU_F_EVENT_B,            /* [W][NE][4]  normalImpulses[2], tangentImpulses[2] */
     B2GPU_F_ISLAND_CONTACTS,    /* [W][NC][1] int32: contact array index in solver order (last step) */
     B2GPU_F_ISLAND_CONTACT_END, /* [W][NB][1] int32 */
+    B2GPU_F_JOINT_COUNT,        /* [W][1][1] int32 */
+    B2GPU_F_JOINT_I,            /* [W][NJ][4] int32: type | collideConnected << 8 | enableLimit << 9 | enableMotor << 10,
+                                   bodyA | bodyB << 16, m_limitState, 0 */
+    B2GPU_F_JOINT_F0,           /* [W][NJ][4]  localAnchorA.xy, localAnchorB.xy */
+    B2GPU_F_JOINT_F1,           /* [W][NJ][4]  revolute / prismatic: referenceAngle, lower, upper, maxMotorTorque|Force;
+                                               distance: length, frequencyHz, dampingRatio, 0 */
+    B2GPU_F_JOINT_F2,           /* [W][NJ][4]  motorSpeed, localXAxisA.xy (normalised), 0 */
+    B2GPU_F_JOINT_IMPULSE,      /* [W][NJ][4]  m_impulse.xyz, m_motorImpulse (warm-starting state) */
     B2GPU_F_COUNT
 };
 

@@ -167,6 +167,7 @@ static void reset_mass_data(world_t* w, int bi) {
 }
 
 void* b2o_world_create(const b2g_scene* s) {
+    if (s->jointCount > 0) return NULL; /* joints are checked against the live reference only */
     world_t* w = (world_t*)calloc(1, sizeof(world_t));
     w->gravity = V2(s->gravity[0], s->gravity[1]);
     w->flags = s->worldFlags;

@@ -171,6 +171,39 @@ RefWorld* build_world(const b2g_scene* s) {
         }
         rw->fixtures.push_back(f);
     }
+    // b2World::CreateJoint in call order, from the same local-frame definitions the device path receives
+    for (int i = 0; i < s->jointCount; ++i) {
+        const b2g_joint_def& d = s->joints[i];
+        b2Body* bA = rw->bodies[d.bodyA];
+        b2Body* bB = rw->bodies[d.bodyB];
+        if (d.type == B2G_JOINT_REVOLUTE) {
+            b2RevoluteJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.referenceAngle = d.referenceAngle;
+            jd.enableLimit = d.enableLimit != 0; jd.lowerAngle = d.lower; jd.upperAngle = d.upper;
+            jd.enableMotor = d.enableMotor != 0; jd.maxMotorTorque = d.maxMotor; jd.motorSpeed = d.motorSpeed;
+            w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_PRISMATIC) {
+            b2PrismaticJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.localAxisA.Set(d.localAxisA[0], d.localAxisA[1]);
+            jd.referenceAngle = d.referenceAngle;
+            jd.enableLimit = d.enableLimit != 0; jd.lowerTranslation = d.lower; jd.upperTranslation = d.upper;
+            jd.enableMotor = d.enableMotor != 0; jd.maxMotorForce = d.maxMotor; jd.motorSpeed = d.motorSpeed;
+            w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_DISTANCE) {
+            b2DistanceJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.length = d.length; jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
+            w->CreateJoint(&jd);
+        }
+    }
     return rw;
 }
 

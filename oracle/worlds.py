@@ -92,6 +92,8 @@ class RefWorld:
         self.scene = scene
         self.L = lib(self.KIND)
         self.h = self.L.ref_world_create(C.byref(scene.c_scene()))
+        if not self.h:
+            raise RuntimeError(f"the {self.KIND} oracle cannot build this scene (joints need the live reference)")
         if record_events:
             self.L.ref_world_record_events(self.h, 1)
 

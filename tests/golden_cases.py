@@ -180,6 +180,9 @@ WORLD_CASES = {
     # sensor fixtures (b2Contact::Update's b2TestOverlap branch); live-reference only, like continuous physics
     "sensors_seed1_default": (lambda: S.sensors(1), 300, 8, 3),
     "sensors_seed2_default_noccd": (lambda: S.sensors(2, flags=NOCCD), 300, 6, 2),
+    # joints in the island solver (revolute, prismatic, distance); live-reference only
+    "jointed_seed1_default": (lambda: S.jointed(1), 400, 8, 3),
+    "jointed_seed2_default_noccd": (lambda: S.jointed(2, flags=NOCCD), 400, 6, 2),
 }
 # scenes the C restatement can run (continuous physics off); the device path runs every case
 NOCCD_CASES = [k for k in WORLD_CASES if "default" not in k and "_ccd_" not in k]

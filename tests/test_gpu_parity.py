@@ -141,6 +141,21 @@ def test_sensors_generic_solver(oracles):
     run_parity(oracles, [S.sensors(7), S.sensors(8, flags=NOCCD)], 200, 6, 2, check_every=4, generic_solver=True)
 
 
+def test_joints_every_step(oracles):
+    # revolute (limits, motors), prismatic (limits, motor) and distance (rigid, soft) joints in the island solver:
+    # joint edges in the island DFS, ShouldCollide's collideConnected rule, joint init / velocity / position passes
+    # interleaved with the contacts', warm starting of joint impulses; with and without continuous physics
+    _need_ref(oracles)
+    scenes = [S.jointed(s, flags=(S.WORLD_DEFAULT if s % 2 else NOCCD)) for s in range(6)] + [S.mixed(4), S.pyramid(5)]
+    run_parity(oracles, scenes, 420, 8, 3)
+
+
+def test_joints_no_warm_starting_and_62(oracles):
+    _need_ref(oracles)
+    scenes = [S.jointed(9, flags=S.WORLD_DEFAULT & ~S.WORLD_WARM_STARTING), S.jointed(10, flags=NOCCD & ~S.WORLD_ALLOW_SLEEP)]
+    run_parity(oracles, scenes, 300, 6, 2, check_every=3)
+
+
 def test_replicated_worlds_identical(oracles):
     sc = S.pyramid(10, flags=NOCCD)
     batch = WorldBatch(sc, replicate=70)
