@@ -30,6 +30,7 @@
 #define B2_WORLD_BATCH_H
 
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -210,6 +211,61 @@ class b2Body;
 class b2World;
 class b2WorldBatch;
 
+// ---- joints (Dynamics/Joints/b2Joint.h:31-101, b2RevoluteJoint.h:35-86, b2PrismaticJoint.h:33-87, b2DistanceJoint.h:32-67)
+enum class b2JointType {
+    UNKNOWN_JOINT, REVOLUTE_JOINT, PRISMATIC_JOINT, DISTANCE_JOINT, PULLEY_JOINT, MOUSE_JOINT, GEAR_JOINT, WHEEL_JOINT,
+    WELD_JOINT, FRICTION_JOINT, ROPE_JOINT, MOTOR_JOINT
+};
+struct b2JointDef {
+    b2JointType type = b2JointType::UNKNOWN_JOINT;
+    void* userData = nullptr;
+    b2Body* bodyA = nullptr;
+    b2Body* bodyB = nullptr;
+    bool collideConnected = false;
+};
+struct b2RevoluteJointDef : public b2JointDef {
+    b2RevoluteJointDef() { type = b2JointType::REVOLUTE_JOINT; }
+    void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec<float, 2>& anchor);
+    b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}};
+    float referenceAngle = 0.0f;
+    bool enableLimit = false;
+    float lowerAngle = 0.0f, upperAngle = 0.0f;
+    bool enableMotor = false;
+    float motorSpeed = 0.0f, maxMotorTorque = 0.0f;
+};
+struct b2PrismaticJointDef : public b2JointDef {
+    b2PrismaticJointDef() { type = b2JointType::PRISMATIC_JOINT; }
+    void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec<float, 2>& anchor, const b2Vec<float, 2>& axis);
+    b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}}, localAxisA{{1.0f, 0.0f}};
+    float referenceAngle = 0.0f;
+    bool enableLimit = false;
+    float lowerTranslation = 0.0f, upperTranslation = 0.0f;
+    bool enableMotor = false;
+    float maxMotorForce = 0.0f, motorSpeed = 0.0f;
+};
+struct b2DistanceJointDef : public b2JointDef {
+    b2DistanceJointDef() { type = b2JointType::DISTANCE_JOINT; }
+    void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec<float, 2>& anchorA, const b2Vec<float, 2>& anchorB);
+    b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}};
+    float length = 1.0f, frequencyHz = 0.0f, dampingRatio = 0.0f;
+};
+class b2Joint {
+public:
+    b2JointType GetType() const { return m_type; }
+    b2Body* GetBodyA() const { return m_bodyA; }
+    b2Body* GetBodyB() const { return m_bodyB; }
+    void* GetUserData() const { return m_userData; }
+    int32_t GetIndex() const { return m_index; }  // creation order within the world
+
+private:
+    friend class b2World;
+    b2JointType m_type = b2JointType::UNKNOWN_JOINT;
+    b2Body* m_bodyA = nullptr;
+    b2Body* m_bodyB = nullptr;
+    void* m_userData = nullptr;
+    int32_t m_index = 0;
+};
+
 class b2Fixture {
 public:
     b2Body* GetBody() const { return m_body; }
@@ -266,6 +322,10 @@ public:
     void* GetUserData() const { return m_userData; }
     b2World* GetWorld() const { return m_world; }
     int32_t GetIndex() const { return m_index; }  // creation order within the world
+    // b2Body::GetLocalPoint / GetLocalVector (b2Body.h:567-575) — before the first Step they are evaluated from the
+    // body definition, which is what the joint defs' Initialize() helpers need
+    b2Vec<float, 2> GetLocalPoint(const b2Vec<float, 2>& worldPoint) const;
+    b2Vec<float, 2> GetLocalVector(const b2Vec<float, 2>& worldVector) const;
     // Between-step edits (Dynamics/b2Body.h:738-833, 408-467, 634-653; b2Body.cpp:418-440).  Each call is queued as a
     // b2gpu_body_command in call order and applied on the device before the next Step / getter, with the
     // reference's semantics (type checks, wake rules, force only accumulates on awake bodies, SetTransform
@@ -299,6 +359,9 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
+    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic and distance joints; nullptr for the
+    // joint types outside the device path and once the world is locked (after the first Step)
+    b2Joint* CreateJoint(const b2JointDef* def);
     void Step(float timeStep, int32_t velocityIterations, int32_t positionIterations);
     void SetContactListener(b2ContactListener* listener);
     void SetAllowSleeping(bool flag) { SetFlag(B2G_WORLD_ALLOW_SLEEP, flag); }
@@ -331,6 +394,8 @@ private:
     std::vector<b2g_body_def> m_bodyDefs;
     std::vector<b2g_fixture_def> m_fixtureDefs;
     std::vector<float> m_vertices;
+    std::vector<b2g_joint_def> m_jointDefs;
+    std::vector<std::unique_ptr<b2Joint>> m_joints;
     std::vector<int32_t> m_firstProxy;  // per fixture: index of its first proxy (creation order)
     int32_t m_proxyCount = 0;
 };
@@ -408,6 +473,8 @@ private:
             s.bodies = w.m_bodyDefs.data();
             s.fixtures = w.m_fixtureDefs.data();
             s.vertices = w.m_vertices.data();
+            s.joints = w.m_jointDefs.data();
+            s.jointCount = (int32_t)w.m_jointDefs.size();
         }
         b2gpu_batch_desc desc;
         std::memset(&desc, 0, sizeof(desc));
@@ -532,6 +599,47 @@ inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
     w.m_bodies.push_back(std::move(b));
     return w.m_bodies.back().get();
 }
+inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
+    b2World& w = B2_SELF;
+    if (w.m_batch->IsBuilt() || !def->bodyA || !def->bodyB) return nullptr;
+    b2g_joint_def d;
+    std::memset(&d, 0, sizeof(d));
+    d.bodyA = def->bodyA->GetIndex();
+    d.bodyB = def->bodyB->GetIndex();
+    d.collideConnected = def->collideConnected ? 1 : 0;
+    auto set2 = [](float* dst, const b2Vec<float, 2>& v) { dst[0] = v[0]; dst[1] = v[1]; };
+    if (def->type == b2JointType::REVOLUTE_JOINT) {
+        const b2RevoluteJointDef* r = static_cast<const b2RevoluteJointDef*>(def);
+        d.type = B2G_JOINT_REVOLUTE;
+        set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB);
+        d.referenceAngle = r->referenceAngle;
+        d.enableLimit = r->enableLimit; d.lower = r->lowerAngle; d.upper = r->upperAngle;
+        d.enableMotor = r->enableMotor; d.maxMotor = r->maxMotorTorque; d.motorSpeed = r->motorSpeed;
+    } else if (def->type == b2JointType::PRISMATIC_JOINT) {
+        const b2PrismaticJointDef* r = static_cast<const b2PrismaticJointDef*>(def);
+        d.type = B2G_JOINT_PRISMATIC;
+        set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB); set2(d.localAxisA, r->localAxisA);
+        d.referenceAngle = r->referenceAngle;
+        d.enableLimit = r->enableLimit; d.lower = r->lowerTranslation; d.upper = r->upperTranslation;
+        d.enableMotor = r->enableMotor; d.maxMotor = r->maxMotorForce; d.motorSpeed = r->motorSpeed;
+    } else if (def->type == b2JointType::DISTANCE_JOINT) {
+        const b2DistanceJointDef* r = static_cast<const b2DistanceJointDef*>(def);
+        d.type = B2G_JOINT_DISTANCE;
+        set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB);
+        d.length = r->length; d.frequencyHz = r->frequencyHz; d.dampingRatio = r->dampingRatio;
+    } else {
+        return nullptr;
+    }
+    w.m_jointDefs.push_back(d);
+    std::unique_ptr<b2Joint> j(new b2Joint);
+    j->m_type = def->type;
+    j->m_bodyA = def->bodyA;
+    j->m_bodyB = def->bodyB;
+    j->m_userData = def->userData;
+    j->m_index = (int32_t)w.m_joints.size();
+    w.m_joints.push_back(std::move(j));
+    return w.m_joints.back().get();
+}
 inline void b2World::Step(float dt, int32_t vi, int32_t pi) { m_batch->Step(dt, vi, pi); }
 inline void b2World::SetContactListener(b2ContactListener* l) { m_batch->SetContactListener(l); }
 inline int32_t b2World::GetProxyCount() const { return (m_owned ? m_owned->World(0) : *this).m_proxyCount; }
@@ -582,6 +690,7 @@ inline const b2Vec<float, 2>& b2Body::GetPosition() const {
 }
 inline float b2Body::GetAngle() const {
     b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt()) return m_world->m_bodyDefs[m_index].angle;  // scene still open (joint defs' Initialize())
     B->Refresh();
     return B->m_sweep[B->Slot(this) * 4 + 2];
 }
@@ -609,6 +718,56 @@ inline bool b2Body::IsAwake() const {
     B->Refresh();
     return (B->m_bodyFlags[B->Slot(this)] & 8) != 0;
 }
+// Transform of a body: from its definition until the batch is built, from the device afterwards.
+inline b2Vec<float, 2> b2Body::GetLocalPoint(const b2Vec<float, 2>& p) const {
+    float px, py, qs, qc;
+    b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt()) {
+        const b2g_body_def& d = m_world->m_bodyDefs[m_index];
+        px = d.position[0]; py = d.position[1]; qs = std::sin(d.angle); qc = std::cos(d.angle);
+    } else {
+        B->Refresh();
+        const float* x = &B->m_xf[B->Slot(this) * 4];
+        px = x[0]; py = x[1]; qs = x[2]; qc = x[3];
+    }
+    const float dx = p[0] - px, dy = p[1] - py;  // b2MulT(xf, p)
+    return b2Vec<float, 2>{{qc * dx + qs * dy, -qs * dx + qc * dy}};
+}
+inline b2Vec<float, 2> b2Body::GetLocalVector(const b2Vec<float, 2>& v) const {
+    float qs, qc;
+    b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt()) {
+        const b2g_body_def& d = m_world->m_bodyDefs[m_index];
+        qs = std::sin(d.angle); qc = std::cos(d.angle);
+    } else {
+        B->Refresh();
+        const float* x = &B->m_xf[B->Slot(this) * 4];
+        qs = x[2]; qc = x[3];
+    }
+    return b2Vec<float, 2>{{qc * v[0] + qs * v[1], -qs * v[0] + qc * v[1]}};  // b2MulT(q, v)
+}
+// The defs' Initialize() helpers (b2RevoluteJoint.cpp:38-45, b2PrismaticJoint.cpp:90-98, b2DistanceJoint.cpp:40-49)
+inline void b2RevoluteJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& anchor) {
+    bodyA = bA; bodyB = bB;
+    localAnchorA = bodyA->GetLocalPoint(anchor);
+    localAnchorB = bodyB->GetLocalPoint(anchor);
+    referenceAngle = bodyB->GetAngle() - bodyA->GetAngle();
+}
+inline void b2PrismaticJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& anchor, const b2Vec<float, 2>& axis) {
+    bodyA = bA; bodyB = bB;
+    localAnchorA = bodyA->GetLocalPoint(anchor);
+    localAnchorB = bodyB->GetLocalPoint(anchor);
+    localAxisA = bodyA->GetLocalVector(axis);
+    referenceAngle = bodyB->GetAngle() - bodyA->GetAngle();
+}
+inline void b2DistanceJointDef::Initialize(b2Body* b1, b2Body* b2, const b2Vec<float, 2>& anchor1, const b2Vec<float, 2>& anchor2) {
+    bodyA = b1; bodyB = b2;
+    localAnchorA = bodyA->GetLocalPoint(anchor1);
+    localAnchorB = bodyB->GetLocalPoint(anchor2);
+    const float dx = anchor2[0] - anchor1[0], dy = anchor2[1] - anchor1[1];
+    length = std::sqrt(dx * dx + dy * dy);
+}
+
 inline void b2WorldBatch::Queue(const b2Body* b, int32_t op, bool wake, float vx, float vy, float px, float py) {
     Build();
     b2gpu_body_command c;

@@ -104,6 +104,14 @@ class CScene(C.Structure):
     ]
 
 
+def _sincos(angle):
+    """b2Rot::Set(angle) as the reference evaluates it (libm sinf / cosf): the library's own host-side restatement."""
+    from .batch import lib
+    x, s, c = (np.array([angle], F32), np.zeros(1, F32), np.zeros(1, F32))
+    lib().b2gpu_host_sincosf(x.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), 1)
+    return s[0], c[0]
+
+
 class Scene:
     """One world, as built by the user.  Mirrors b2World / b2Body construction calls."""
 
@@ -120,7 +128,7 @@ class Scene:
     def _local(self, body, point):
         """b2Body::GetLocalPoint of a freshly created body (b2MulT(xf, p)) in float32."""
         bd = self.bodies[body]
-        s, c = F32(np.sin(F32(bd.angle))), F32(np.cos(F32(bd.angle)))
+        s, c = _sincos(bd.angle)
         px, py = F32(F32(point[0]) - F32(bd.position[0])), F32(F32(point[1]) - F32(bd.position[1]))
         return float(F32(c * px) + F32(s * py)), float(F32(-s * px) + F32(c * py))
 
@@ -149,7 +157,7 @@ class Scene:
         jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor)
         jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor)
         bd = self.bodies[body_a]  # GetLocalVector(axis) = b2MulT(q, axis)
-        s, c = F32(np.sin(F32(bd.angle))), F32(np.cos(F32(bd.angle)))
+        s, c = _sincos(bd.angle)
         ax, ay = F32(axis[0]), F32(axis[1])
         jd.localAxisA[0], jd.localAxisA[1] = float(F32(c * ax) + F32(s * ay)), float(F32(-s * ax) + F32(c * ay))
         jd.referenceAngle = float(F32(self.bodies[body_b].angle) - F32(self.bodies[body_a].angle))

@@ -173,10 +173,60 @@ static int edits(int n, int steps) {
     return 0;
 }
 
+// Joints through the reference's API: a cart on a rail (b2PrismaticJointDef, limits + motor) carrying a pole
+// (b2RevoluteJointDef) and a bob on a b2DistanceJointDef, built with the defs' Initialize() helpers.
+static int joints(int steps) {
+    b2World world(b2Vec<float, 2>{{0.0f, -10.0f}});
+    b2BodyDef gd;
+    b2Body* ground = world.CreateBody(&gd);
+    b2EdgeShape ge;
+    ge.Set(b2Vec<float, 2>{{-40.0f, 0.0f}}, b2Vec<float, 2>{{40.0f, 0.0f}});
+    ground->CreateFixture(&ge, 0.0f);
+    b2BodyDef bd;
+    bd.type = b2BodyType::DYNAMIC_BODY;
+    bd.position = b2Vec<float, 2>{{0.0f, 3.0f}};
+    b2Body* cart = world.CreateBody(&bd);
+    b2PolygonShape cs;
+    cs.SetAsBox(0.6f, 0.25f);
+    cart->CreateFixture(&cs, 2.0f);
+    b2PrismaticJointDef pj;
+    pj.Initialize(ground, cart, b2Vec<float, 2>{{0.0f, 3.0f}}, b2Vec<float, 2>{{1.0f, 0.0f}});
+    pj.lowerTranslation = -3.0f; pj.upperTranslation = 3.0f; pj.enableLimit = true;
+    pj.maxMotorForce = 60.0f; pj.motorSpeed = 2.5f; pj.enableMotor = true;
+    if (!world.CreateJoint(&pj)) return 5;
+    bd.position = b2Vec<float, 2>{{0.0f, 4.0f}};
+    bd.angle = 0.2f;
+    b2Body* pole = world.CreateBody(&bd);
+    b2PolygonShape ps;
+    ps.SetAsBox(0.08f, 1.0f);
+    pole->CreateFixture(&ps, 1.0f);
+    b2RevoluteJointDef rj;
+    rj.Initialize(cart, pole, b2Vec<float, 2>{{0.0f, 3.0f}});
+    if (!world.CreateJoint(&rj)) return 5;
+    bd.position = b2Vec<float, 2>{{8.0f, 6.0f}};
+    bd.angle = 0.0f;
+    b2Body* bob = world.CreateBody(&bd);
+    b2CircleShape bs;
+    bs.SetRadius(0.35f);
+    bob->CreateFixture(&bs, 2.0f);
+    b2DistanceJointDef dj;
+    dj.Initialize(ground, bob, b2Vec<float, 2>{{6.0f, 8.0f}}, b2Vec<float, 2>{{8.0f, 6.0f}});
+    dj.frequencyHz = 3.0f; dj.dampingRatio = 0.2f;
+    if (!world.CreateJoint(&dj)) return 5;
+    for (int s = 0; s < steps; ++s) world.Step(1.0f / 60.0f, 8, 3);
+    b2Body* all[3] = {cart, pole, bob};
+    for (b2Body* b : all) {
+        b2Vec<float, 2> p = b->GetPosition();
+        std::printf("%08x %08x %08x\n", bits(p[0]), bits(p[1]), bits(b->GetAngle()));
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     try {
         if (argc >= 2 && std::strcmp(argv[1], "batch") == 0)
             return batch(argc > 2 ? std::atoi(argv[2]) : 3, argc > 3 ? std::atoi(argv[3]) : 4, argc > 4 ? std::atoi(argv[4]) : 120);
+        if (argc >= 2 && std::strcmp(argv[1], "joints") == 0) return joints(argc > 2 ? std::atoi(argv[2]) : 200);
         if (argc >= 2 && std::strcmp(argv[1], "edits") == 0)
             return edits(argc > 2 ? std::atoi(argv[2]) : 3, argc > 3 ? std::atoi(argv[3]) : 150);
         return hello();

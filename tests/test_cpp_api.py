@@ -133,3 +133,34 @@ def test_body_edits_through_cpp_api(exe, oracles):
             want = [int(np.float32(v).view(np.uint32)) for v in (rb[i, 0], rb[i, 1], rb[i, 6], rb[i, 7], rb[i, 8], rb[i, 9])]
             assert got[(w, i)][:6] == want, f"world {w} body {i}"
             assert got[(w, i)][6] == int(rb[i, 10] != 0)
+
+
+@pytest.mark.gpu
+def test_joints_through_cpp_api(exe, oracles):
+    """b2PrismaticJointDef / b2RevoluteJointDef / b2DistanceJointDef with Initialize() and b2World::CreateJoint through
+    the C++ mirror (reference defaults: continuous physics on): state after 200 steps equals the reference's."""
+    if not oracles.available("ref"):
+        pytest.skip("joints are checked against the live reference")
+    r = subprocess.run([exe, "joints", "200"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [[int(x, 16) for x in line.split()] for line in r.stdout.strip().splitlines()]
+    s = S.Scene()
+    g = s.create_body(S.STATIC_BODY)
+    s.create_edge(g, (-40.0, 0.0), (40.0, 0.0))
+    cart = s.create_body(S.DYNAMIC_BODY, (0.0, 3.0))
+    s.create_box(cart, 0.6, 0.25, density=2.0)
+    s.create_prismatic_joint(g, cart, (0.0, 3.0), (1.0, 0.0), lower=-3.0, upper=3.0, enable_limit=True,
+                             max_motor_force=60.0, motor_speed=2.5, enable_motor=True)
+    pole = s.create_body(S.DYNAMIC_BODY, (0.0, 4.0), angle=0.2)
+    s.create_box(pole, 0.08, 1.0, density=1.0)
+    s.create_revolute_joint(cart, pole, (0.0, 3.0))
+    bob = s.create_body(S.DYNAMIC_BODY, (8.0, 6.0))
+    s.create_circle(bob, 0.35, density=2.0)
+    s.create_distance_joint(g, bob, (6.0, 8.0), (8.0, 6.0), frequency_hz=3.0, damping_ratio=0.2)
+    ref = oracles.RefWorld(s)
+    for _ in range(200):
+        ref.step(1.0 / 60.0, 8, 3)
+    rb = ref.bodies()
+    for i, b in enumerate((cart, pole, bob)):
+        want = [int(np.float32(v).view(np.uint32)) for v in (rb[b, 0], rb[b, 1], rb[b, 6])]
+        assert got[i] == want, f"body {b}: {got[i]} vs {want}"
