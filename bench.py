@@ -91,7 +91,8 @@ def build_scenes(workload, count, first_seed, flags, jittered=True):
     if workload == "pyramid":
         sb = S.pyramid_batch(count, ROWS, flags=flags, first_seed=first_seed, jittered=jittered)
         return sb, sb.scene
-    scenes = [S.mixed(first_seed + i, flags=flags) for i in range(count)]
+    make = S.mixed if workload == "mixed" else S.jointed
+    scenes = [make(first_seed + i, flags=flags) for i in range(count)]
     return scenes, scenes.__getitem__
 
 
@@ -109,7 +110,8 @@ def cpu_reference_run(steps, warmup, threads=None, worlds_per_thread=16, workloa
     if not worlds.available("ref"):
         return None
     sec, _ = worlds.bench_run(scenes, worlds_per_thread, threads, steps, warmup, DT, 8, 3)
-    what = f"jittered pyramid-{ROWS}" if workload == "pyramid" else "mixed-shape (chain terrain, circles, polygons)"
+    what = {"pyramid": f"jittered pyramid-{ROWS}", "mixed": "mixed-shape (chain terrain, circles, polygons)",
+            "jointed": "jointed (bridge, cart-pole, walker, pendulums)"}[workload]
     return {"value": n * steps / sec, "unit": "world-steps/s", "cores": threads, "kind": "reference",
             "sample": f"{threads} threads x {worlds_per_thread} {what} worlds, {warmup} warm-up + "
                       f"{steps} timed steps, 8/3 iterations, sleeping {'on' if flags & S.WORLD_ALLOW_SLEEP else 'off'}, "
@@ -129,8 +131,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--generic-solver", action="store_true", help="force the fallback solver kernel")
-    ap.add_argument("--workload", default="pyramid", choices=["pyramid", "mixed"],
-                    help="pyramid = BASELINE configs[2] (the headline); mixed = configs[3] per-GPU share")
+    ap.add_argument("--workload", default="pyramid", choices=["pyramid", "mixed", "jointed"],
+                    help="pyramid = BASELINE configs[2] (the headline); mixed = configs[3] per-GPU share; "
+                         "jointed = bridge + cart-pole + walker + pendulums (joints: generic solver kernel)")
     ap.add_argument("--toi", action="store_true", help="continuous physics on (the reference's default) on both arms")
     ap.add_argument("--sleep", action="store_true", help="sleeping allowed (the reference's default) on both arms")
     ap.add_argument("--preroll", type=int, default=-1)
@@ -152,10 +155,14 @@ def main():
         nbody, nproxy = BODIES_DYNAMIC, BODIES_DYNAMIC + 1
         what = (f"{args.worlds_per_gpu} {'identical' if args.identical else 'jittered'} pyramid-{ROWS} worlds "
                 f"per GPU (BASELINE configs[2])")
-    else:
+    elif args.workload == "mixed":
         nbody, nproxy = 40, 72
         what = (f"{args.worlds_per_gpu} mixed-shape worlds per GPU (BASELINE configs[3]'s per-GPU share: 32-edge chain "
                 f"terrain, 20 circles + 20 random convex polygons, seed = world index)")
+    else:
+        nbody, nproxy = 26, 27
+        what = (f"{args.worlds_per_gpu} jointed worlds per GPU (plank bridge, cart-pole, two-legged walker, pendulums: "
+                f"22 revolute / prismatic / distance joints, seed = world index)")
     config = {"workload": what + ", dt=1/60, 8 vel / 3 pos iterations",
               "worlds_per_gpu": args.worlds_per_gpu, "dynamic_bodies_per_world": nbody,
               "sleeping": bool(args.sleep), "continuous_physics": bool(args.toi), "warm_starting": True, "events": "off",
@@ -291,9 +298,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_kernel[top] * W / (top_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+    # (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); only quoted for the configuration it was taken on
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top + "_dram_bytes_per_launch")
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
+        if t and t.get("worlds") == W and t.get("workload") == args.workload and not args.toi and not args.sleep:
+            traffic = t["dram_bytes_per_launch"]
     except Exception:
         pass
     step_ms_sum = sum(kms.values())
