@@ -1,4 +1,4 @@
-// b2g_joints.cuh — joints in the island solver: revolute, prismatic and distance joints.
+// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel and weld joints.
 //
 // Reference (vanilla twin Regression/box2d-ref/Box2DRef/Dynamics/Joints; the fork's files are
 // Box2D/Dynamics/Joints/b2RevoluteJoint.cpp, b2PrismaticJoint.cpp, b2DistanceJoint.cpp, same line structure):
@@ -41,6 +41,43 @@ __device__ __forceinline__ Vec2 Solve22(float a11, float a12, float a21, float a
     x.x = det * (a22 * b.x - a12 * b.y);
     x.y = det * (a11 * b.y - a21 * b.x);
     return x;
+}
+
+// b2Mat33::GetInverse22 / GetSymInverse33 — Common/b2Math.cpp:55-95; b2Mul(b2Mat33, b2Vec3), b2Mul22 — b2Math.h:531-540
+__device__ __forceinline__ Mat33 GetInverse22(const Mat33& K) {
+    const float a = K.ex.x, b = K.ey.x, c = K.ex.y, d = K.ey.y;
+    float det = a * d - b * c;
+    if (det != 0.0f) det = Div(1.0f, det);
+    Mat33 M;
+    M.ex = V3(det * d, -det * c, 0.0f);
+    M.ey = V3(-det * b, det * a, 0.0f);
+    M.ez = V3(0.0f, 0.0f, 0.0f);
+    return M;
+}
+__device__ __forceinline__ Mat33 GetSymInverse33(const Mat33& K) {
+    float det = Dot3(K.ex, Cross3(K.ey, K.ez));
+    if (det != 0.0f) det = Div(1.0f, det);
+    const float a11 = K.ex.x, a12 = K.ey.x, a13 = K.ez.x;
+    const float a22 = K.ey.y, a23 = K.ez.y;
+    const float a33 = K.ez.z;
+    Mat33 M;
+    M.ex.x = det * (a22 * a33 - a23 * a23);
+    M.ex.y = det * (a13 * a23 - a12 * a33);
+    M.ex.z = det * (a12 * a23 - a13 * a22);
+    M.ey.x = M.ex.y;
+    M.ey.y = det * (a11 * a33 - a13 * a13);
+    M.ey.z = det * (a13 * a12 - a11 * a23);
+    M.ez.x = M.ex.z;
+    M.ez.y = M.ey.z;
+    M.ez.z = det * (a11 * a22 - a12 * a12);
+    return M;
+}
+__device__ __forceinline__ Vec3 Mul33(const Mat33& A, Vec3 v) {
+    return V3(v.x * A.ex.x + v.y * A.ey.x + v.z * A.ez.x, v.x * A.ex.y + v.y * A.ey.y + v.z * A.ez.y,
+              v.x * A.ex.z + v.y * A.ey.z + v.z * A.ez.z);
+}
+__device__ __forceinline__ Vec2 Mul22(const Mat33& A, Vec2 v) {
+    return V2(A.ex.x * v.x + A.ey.x * v.y, A.ex.y * v.x + A.ey.y * v.y);
 }
 
 struct JointCols {
@@ -161,6 +198,109 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
         c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
         c.jTmp[t + 1] = make_float4(u.x, u.y, mass, gamma);
         c.jTmp[t + 2] = make_float4(bias, 0.0f, 0.0f, 0.0f);
+    } else if (type == B2G_JOINT_WHEEL) {  // b2WheelJoint.cpp:79-199
+        // jImp: m_impulse, m_springImpulse, -, m_motorImpulse.  f1: frequencyHz, dampingRatio, -, maxMotorTorque
+        const Vec2 d = cB + rB - cA - rA;
+        const Vec2 localX = V2(f2.y, f2.z), localY = Cross(1.0f, localX);
+        const Vec2 ay = Mul(qA, localY);
+        const float sAy = Cross(d + rA, ay), sBy = Cross(rB, ay);
+        float mass = mA + mB + iA * sAy * sAy + iB * sBy * sBy;
+        if (mass > 0.0f) mass = Div(1.0f, mass);
+        float springMass = 0.0f, bias = 0.0f, gamma = 0.0f;
+        // m_ax / m_sAx / m_sBx keep their constructor values (zero) while the spring is off
+        Vec2 ax = V2(0.0f, 0.0f);
+        float sAx = 0.0f, sBx = 0.0f;
+        if (f1.x > 0.0f) {
+            ax = Mul(qA, localX);
+            sAx = Cross(d + rA, ax);
+            sBx = Cross(rB, ax);
+            const float invMass = mA + mB + iA * sAx * sAx + iB * sBx * sBx;
+            if (invMass > 0.0f) {
+                springMass = Div(1.0f, invMass);
+                const float C = Dot(d, ax);
+                const float omega = 2.0f * kPi * f1.x;
+                const float dd = 2.0f * springMass * f1.y * omega;
+                const float k = springMass * omega * omega;
+                gamma = h * (dd + h * k);
+                if (gamma > 0.0f) gamma = Div(1.0f, gamma);
+                bias = C * h * k * gamma;
+                springMass = invMass + gamma;
+                if (springMass > 0.0f) springMass = Div(1.0f, springMass);
+            }
+        } else {
+            imp.y = 0.0f;
+        }
+        float motorMass = 0.0f;
+        if (ji.x & kJointEnableMotor) {
+            motorMass = iA + iB;
+            if (motorMass > 0.0f) motorMass = Div(1.0f, motorMass);
+        } else {
+            imp.w = 0.0f;
+        }
+        if (warmStarting) {
+            imp.x *= dtRatio;
+            imp.y *= dtRatio;
+            imp.w *= dtRatio;
+            const Vec2 P = imp.x * ay + imp.y * ax;
+            const float LA = imp.x * sAy + imp.y * sAx + imp.w;
+            const float LB = imp.x * sBy + imp.y * sBx + imp.w;
+            vA = vA - mA * P;
+            wA -= iA * LA;
+            vB = vB + mB * P;
+            wB += iB * LB;
+        } else {
+            imp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        c.jTmp[t + 0] = make_float4(ax.x, ax.y, ay.x, ay.y);
+        c.jTmp[t + 1] = make_float4(sAx, sBx, sAy, sBy);
+        c.jTmp[t + 2] = make_float4(mass, springMass, motorMass, gamma);
+        c.jTmp[t + 3] = make_float4(bias, 0.0f, 0.0f, 0.0f);
+    } else if (type == B2G_JOINT_WELD) {  // b2WeldJoint.cpp:66-154
+        // f1: referenceAngle, frequencyHz, dampingRatio
+        Mat33 K;
+        K.ex.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+        K.ey.x = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+        K.ez.x = -rA.y * iA - rB.y * iB;
+        K.ex.y = K.ey.x;
+        K.ey.y = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+        K.ez.y = rA.x * iA + rB.x * iB;
+        K.ex.z = K.ez.x;
+        K.ey.z = K.ez.y;
+        K.ez.z = iA + iB;
+        Mat33 M;
+        float gamma = 0.0f, bias = 0.0f;
+        if (f1.y > 0.0f) {
+            M = GetInverse22(K);
+            float invM = iA + iB;
+            const float m = invM > 0.0f ? Div(1.0f, invM) : 0.0f;
+            const float C = aB - aA - f1.x;
+            const float omega = 2.0f * kPi * f1.y;
+            const float dd = 2.0f * m * f1.z * omega;
+            const float k = m * omega * omega;
+            gamma = h * (dd + h * k);
+            gamma = gamma != 0.0f ? Div(1.0f, gamma) : 0.0f;
+            bias = C * h * k * gamma;
+            invM += gamma;
+            M.ez.z = invM != 0.0f ? Div(1.0f, invM) : 0.0f;
+        } else if (K.ez.z == 0.0f) {
+            M = GetInverse22(K);
+        } else {
+            M = GetSymInverse33(K);
+        }
+        if (warmStarting) {
+            imp.x *= dtRatio; imp.y *= dtRatio; imp.z *= dtRatio;
+            const Vec2 P = V2(imp.x, imp.y);
+            vA = vA - mA * P;
+            wA -= iA * (Cross(rA, P) + imp.z);
+            vB = vB + mB * P;
+            wB += iB * (Cross(rB, P) + imp.z);
+        } else {
+            imp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
+        c.jTmp[t + 1] = make_float4(M.ex.x, M.ex.y, M.ex.z, gamma);
+        c.jTmp[t + 2] = make_float4(M.ey.x, M.ey.y, M.ey.z, bias);
+        c.jTmp[t + 3] = make_float4(M.ez.x, M.ez.y, M.ez.z, 0.0f);
     } else {  // prismatic — b2PrismaticJoint.cpp:127-264
         const Vec2 d = (cB - cA) + rB - rA;
         const Vec2 localX = V2(f2.y, f2.z), localY = Cross(1.0f, localX);
@@ -326,6 +466,78 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
         wA -= iA * Cross(rA, P);
         vB = vB + mB * P;
         wB += iB * Cross(rB, P);
+    } else if (type == B2G_JOINT_WHEEL) {  // b2WheelJoint.cpp:201-261
+        const float4 f1 = c.jF1[j], f2 = c.jF2[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2], t3 = c.jTmp[t + 3];
+        const Vec2 ax = V2(t0.x, t0.y), ay = V2(t0.z, t0.w);
+        const float sAx = t1.x, sBx = t1.y, sAy = t1.z, sBy = t1.w;
+        {  // spring constraint
+            const float Cdot = Dot(ax, vB - vA) + sBx * wB - sAx * wA;
+            const float impulse = -t2.y * (Cdot + t3.x + t2.w * imp.y);
+            imp.y += impulse;
+            const Vec2 P = impulse * ax;
+            const float LA = impulse * sAx;
+            const float LB = impulse * sBx;
+            vA = vA - mA * P;
+            wA -= iA * LA;
+            vB = vB + mB * P;
+            wB += iB * LB;
+        }
+        {  // rotational motor constraint
+            const float Cdot = wB - wA - f2.x;
+            float impulse = -t2.z * Cdot;
+            const float oldImpulse = imp.w;
+            const float maxImpulse = h * f1.w;
+            imp.w = Clamp(imp.w + impulse, -maxImpulse, maxImpulse);
+            impulse = imp.w - oldImpulse;
+            wA -= iA * impulse;
+            wB += iB * impulse;
+        }
+        {  // point to line constraint
+            const float Cdot = Dot(ay, vB - vA) + sBy * wB - sAy * wA;
+            const float impulse = -t2.x * Cdot;
+            imp.x += impulse;
+            const Vec2 P = impulse * ay;
+            const float LA = impulse * sAy;
+            const float LB = impulse * sBy;
+            vA = vA - mA * P;
+            wA -= iA * LA;
+            vB = vB + mB * P;
+            wB += iB * LB;
+        }
+    } else if (type == B2G_JOINT_WELD) {  // b2WeldJoint.cpp:156-213
+        const float4 f1 = c.jF1[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2], t3 = c.jTmp[t + 3];
+        const Vec2 rA = V2(t0.x, t0.y), rB = V2(t0.z, t0.w);
+        Mat33 M;
+        M.ex = V3(t1.x, t1.y, t1.z); M.ey = V3(t2.x, t2.y, t2.z); M.ez = V3(t3.x, t3.y, t3.z);
+        if (f1.y > 0.0f) {
+            const float Cdot2 = wB - wA;
+            const float impulse2 = -M.ez.z * (Cdot2 + t2.w + t1.w * imp.z);
+            imp.z += impulse2;
+            wA -= iA * impulse2;
+            wB += iB * impulse2;
+            const Vec2 Cdot1 = vB + Cross(wB, rB) - vA - Cross(wA, rA);
+            const Vec2 impulse1 = -Mul22(M, Cdot1);
+            imp.x += impulse1.x;
+            imp.y += impulse1.y;
+            const Vec2 P = impulse1;
+            vA = vA - mA * P;
+            wA -= iA * Cross(rA, P);
+            vB = vB + mB * P;
+            wB += iB * Cross(rB, P);
+        } else {
+            const Vec2 Cdot1 = vB + Cross(wB, rB) - vA - Cross(wA, rA);
+            const float Cdot2 = wB - wA;
+            const Vec3 mm = Mul33(M, V3(Cdot1.x, Cdot1.y, Cdot2));
+            const Vec3 impulse = V3(-mm.x, -mm.y, -mm.z);
+            imp.x += impulse.x; imp.y += impulse.y; imp.z += impulse.z;
+            const Vec2 P = V2(impulse.x, impulse.y);
+            vA = vA - mA * P;
+            wA -= iA * (Cross(rA, P) + impulse.z);
+            vB = vB + mB * P;
+            wB += iB * (Cross(rB, P) + impulse.z);
+        }
     } else {  // prismatic — b2PrismaticJoint.cpp:266-372
         const float4 f1 = c.jF1[j], f2 = c.jF2[j];
         const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2], t3 = c.jTmp[t + 3], t4 = c.jTmp[t + 4];
@@ -462,6 +674,69 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
         cB = cB + mB * P;
         aB += iB * Cross(rB, P);
         okay = Abs(C) < kLinearSlop;
+    } else if (type == B2G_JOINT_WHEEL) {  // b2WheelJoint.cpp:263-312
+        const float4 f2 = c.jF2[j];
+        const float4 t1 = c.jTmp[(size_t)j * kJointTmp + 1];
+        const Rot qA = MakeRot(aA), qB = MakeRot(aB);
+        const Vec2 rA = Mul(qA, lA), rB = Mul(qB, lB);
+        const Vec2 d = (cB - cA) + rB - rA;
+        const Vec2 ay = Mul(qA, Cross(1.0f, V2(f2.y, f2.z)));
+        const float sAy = Cross(d + rA, ay), sBy = Cross(rB, ay);
+        const float C = Dot(d, ay);
+        // the reference evaluates k with the members m_sAy / m_sBy of InitVelocityConstraints, not the locals
+        const float k = mA + mB + iA * t1.z * t1.z + iB * t1.w * t1.w;
+        const float impulse = k != 0.0f ? Div(-C, k) : 0.0f;
+        const Vec2 P = impulse * ay;
+        const float LA = impulse * sAy;
+        const float LB = impulse * sBy;
+        cA = cA - mA * P;
+        aA -= iA * LA;
+        cB = cB + mB * P;
+        aB += iB * LB;
+        okay = Abs(C) <= kLinearSlop;
+    } else if (type == B2G_JOINT_WELD) {  // b2WeldJoint.cpp:215-289
+        const Rot qA = MakeRot(aA), qB = MakeRot(aB);
+        const Vec2 rA = Mul(qA, lA), rB = Mul(qB, lB);
+        float positionError, angularError;
+        Mat33 K;
+        K.ex.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+        K.ey.x = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+        K.ez.x = -rA.y * iA - rB.y * iB;
+        K.ex.y = K.ey.x;
+        K.ey.y = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+        K.ez.y = rA.x * iA + rB.x * iB;
+        K.ex.z = K.ez.x;
+        K.ey.z = K.ez.y;
+        K.ez.z = iA + iB;
+        if (f1.y > 0.0f) {
+            const Vec2 C1 = cB + rB - cA - rA;
+            positionError = Length(C1);
+            angularError = 0.0f;
+            const Vec2 P = -Solve22(K.ex.x, K.ey.x, K.ex.y, K.ey.y, C1);
+            cA = cA - mA * P;
+            aA -= iA * Cross(rA, P);
+            cB = cB + mB * P;
+            aB += iB * Cross(rB, P);
+        } else {
+            const Vec2 C1 = cB + rB - cA - rA;
+            const float C2 = aB - aA - f1.x;
+            positionError = Length(C1);
+            angularError = Abs(C2);
+            Vec3 impulse;
+            if (K.ez.z > 0.0f) {
+                const Vec3 s3 = Solve33(K, V3(C1.x, C1.y, C2));
+                impulse = V3(-s3.x, -s3.y, -s3.z);
+            } else {
+                const Vec2 impulse2 = -Solve22(K.ex.x, K.ey.x, K.ex.y, K.ey.y, C1);
+                impulse = V3(impulse2.x, impulse2.y, 0.0f);
+            }
+            const Vec2 P = V2(impulse.x, impulse.y);
+            cA = cA - mA * P;
+            aA -= iA * (Cross(rA, P) + impulse.z);
+            cB = cB + mB * P;
+            aB += iB * (Cross(rB, P) + impulse.z);
+        }
+        okay = positionError <= kLinearSlop && angularError <= kAngularSlop;
     } else {  // prismatic — b2PrismaticJoint.cpp:374-491
         const float4 f2 = c.jF2[j];
         const Rot qA = MakeRot(aA), qB = MakeRot(aB);

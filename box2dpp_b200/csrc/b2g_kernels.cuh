@@ -1305,7 +1305,8 @@ __device__ __forceinline__ PairCtx MakePairCtx(const Arena& A, int tile, int lan
 
 // b2ContactManager::AddPair for proxies a < b (ascending tree id).  `knownNew`: the caller has already
 // established that no contact between the two proxies exists (the walk of bodyB's edge list in the reference).
-__device__ __forceinline__ void AddPair(PairCtx& c, int proxyA, int proxyB, bool knownNew) {
+// (kept out of line: it runs for the few new pairs of a step and must not set the register budget of its callers)
+__device__ __noinline__ void AddPair(PairCtx& c, int proxyA, int proxyB, bool knownNew) {
     int pa = c.proxyInfo[proxyA], pb = c.proxyInfo[proxyB];
     int fixtureA = pa & 0xffff, fixtureB = pb & 0xffff;
     int fiA = c.fixtureInfo[fixtureA], fiB = c.fixtureInfo[fixtureB];
@@ -1479,7 +1480,7 @@ constexpr int kPairWarps = 8;
 constexpr int kMaxMoved = 64;     // per world, else overflow path
 constexpr int kMaxCand = 256;     // per world, else overflow path
 
-__global__ void __launch_bounds__(kPairWarps * 32) k_sync_pairs(Arena A, float dt) {
+__global__ void __launch_bounds__(kPairWarps * 32, 4) k_sync_pairs(Arena A, float dt) {
     __shared__ uint16_t sMoved[kMaxMoved][kTile];
     __shared__ uint32_t sCand[kMaxCand][kTile];
     __shared__ unsigned char sExists[kMaxCand][kTile];
@@ -1505,6 +1506,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_sync_pairs(Arena A, float d
     Col<float2> chainVerts = col(A.chainVerts, tile, A.NV, lane);
 
     // ---- A: synchronize fixtures ----
+    const bool pendingMoves = live && A.pendingMoves[ws] != 0;  // set by k_body_commands (SetTransform), cleared here
     const int npMax = __reduce_max_sync(0xffffffffu, np);
     for (int p = warp; p < npMax; p += kPairWarps) {
         if (p >= np) continue;
@@ -1514,7 +1516,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_sync_pairs(Arena A, float d
         int body = fi & 0xffff;
         int bf = bodyFlags[body];
         // a proxy may already sit in the move buffer: b2Body::SetTransform between two steps (k_body_commands)
-        bool moved = proxyMoved[p] != 0;
+        bool moved = pendingMoves && proxyMoved[p] != 0;
         if ((bf & kBodyIsland) != 0 && (bf & kBodyTypeMask) != B2G_STATIC_BODY)  // else: not in an island, did not move
             moved |= SynchronizeProxy(A, tile, lane, p, fixture, child, fi, body);
         if (!moved) continue;
@@ -1522,6 +1524,7 @@ __global__ void __launch_bounds__(kPairWarps * 32) k_sync_pairs(Arena A, float d
         if (slot < kMaxMoved) sMoved[slot][lane] = (uint16_t)p;
     }
     __syncthreads();  // also orders the fat-AABB writes before the reads below
+    if (warp == 0 && pendingMoves) A.pendingMoves[ws] = 0;
     const int nMoved = sNMoved[lane];
     if (__syncthreads_or(nMoved) == 0) {
         if (warp == 0 && live) {

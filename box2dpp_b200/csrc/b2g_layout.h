@@ -76,6 +76,7 @@ struct Arena {
     int* eventCount;
     int* islandCount;    // last step (diagnostics)
     int* stepCount;
+    int* pendingMoves;   // != 0: proxies were put into the move buffer between steps (b2Body::SetTransform)
     int* topoDirty;      // != 0: contact graph / touching / awake flags changed since the islands were built
 
     // ---- bodies [tile][NB][lane] ----

@@ -255,6 +255,7 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                     if (d.y < 0.0f) lo.y += d.y; else hi.y += d.y;
                     proxyFat[p] = make_float4(lo.x, lo.y, hi.x, hi.y);
                     col(A.proxyMoved, tile, A.NP, lane)[p] = 1;
+                    A.pendingMoves[ws] = 1;
                 }
             } break;
         }
@@ -384,7 +385,7 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(gravity, 1, float2); ALLOC(worldFlags, 1, int); ALLOC(invDt0, 1, float);
     ALLOC(bodyCount, 1, int); ALLOC(proxyCount, 1, int); ALLOC(contactCount, 1, int);
     ALLOC(status, 1, int); ALLOC(eventCount, 1, int); ALLOC(islandCount, 1, int); ALLOC(stepCount, 1, int);
-    ALLOC(topoDirty, 1, int);
+    ALLOC(topoDirty, 1, int); ALLOC(pendingMoves, 1, int);
     CUDA_TRY(cudaMemsetAsync(A.topoDirty, 1, (size_t)A.numTiles * kTile * sizeof(int), b->stream));
     ALLOC(bodyXf, A.NB, float4); ALLOC(bodySweep, A.NB, float4); ALLOC(bodySweep0, A.NB, float4);
     ALLOC(bodyVel, A.NB, float4); ALLOC(bodyForce, A.NB, float4); ALLOC(bodyMass, A.NB, float4);

@@ -63,7 +63,7 @@ class FixtureDef(C.Structure):
     ]
 
 
-JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE = 1, 2, 3
+JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WHEEL, JOINT_WELD = 1, 2, 3, 7, 8
 
 
 class JointDef(C.Structure):
@@ -163,6 +163,28 @@ class Scene:
         jd.referenceAngle = float(F32(self.bodies[body_b].angle) - F32(self.bodies[body_a].angle))
         jd.lower, jd.upper, jd.enableLimit = lower, upper, int(enable_limit)
         jd.maxMotor, jd.motorSpeed, jd.enableMotor = max_motor_force, motor_speed, int(enable_motor)
+        return len(self.joints) - 1
+
+    def create_wheel_joint(self, body_a, body_b, anchor, axis, frequency_hz=2.0, damping_ratio=0.7,
+                           max_motor_torque=0.0, motor_speed=0.0, enable_motor=False, collide_connected=False) -> int:
+        """b2WheelJointDef::Initialize(bodyA, bodyB, anchor, axis) (b2WheelJoint.cpp:39-46)."""
+        jd = self._joint(JOINT_WHEEL, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor)
+        jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor)
+        s, c = _sincos(self.bodies[body_a].angle)
+        ax, ay = F32(axis[0]), F32(axis[1])
+        jd.localAxisA[0], jd.localAxisA[1] = float(F32(c * ax) + F32(s * ay)), float(F32(-s * ax) + F32(c * ay))
+        jd.frequencyHz, jd.dampingRatio = frequency_hz, damping_ratio
+        jd.maxMotor, jd.motorSpeed, jd.enableMotor = max_motor_torque, motor_speed, int(enable_motor)
+        return len(self.joints) - 1
+
+    def create_weld_joint(self, body_a, body_b, anchor, frequency_hz=0.0, damping_ratio=0.0, collide_connected=False) -> int:
+        """b2WeldJointDef::Initialize(bodyA, bodyB, anchor) (b2WeldJoint.cpp:37-44)."""
+        jd = self._joint(JOINT_WELD, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor)
+        jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor)
+        jd.referenceAngle = float(F32(self.bodies[body_b].angle) - F32(self.bodies[body_a].angle))
+        jd.frequencyHz, jd.dampingRatio = frequency_hz, damping_ratio
         return len(self.joints) - 1
 
     def create_distance_joint(self, body_a, body_b, anchor_a, anchor_b, frequency_hz=0.0, damping_ratio=0.0,
@@ -523,6 +545,46 @@ def jointed(seed: int, flags=WORLD_DEFAULT) -> Scene:
     b = s.create_body(DYNAMIC_BODY, (31.5, 1.0), linear_velocity=(-3.0, 0.0))
     s.create_box(b, 0.5, 0.5, density=1.0)
     s.create_distance_joint(a, b, (30.0, 1.0), (31.5, 1.0), collide_connected=True)
+    return s
+
+
+def vehicles(seed: int, flags=WORLD_DEFAULT) -> Scene:
+    """Wheel and weld joints: a car (chassis + two wheels on b2WheelJoint springs, the rear one
+    motorised) driving over bumpy chain terrain towards a cantilever of planks held by weld joints (rigid and soft),
+    plus a welded compound that tumbles down.  All randomness from LCG(seed)."""
+    rng = LCG(seed)
+    s = Scene((0.0, -10.0), flags)
+    g = s.create_body(STATIC_BODY, (0.0, 0.0))
+    pts = [(-30.0, 0.0), (-10.0, 0.0)] + [(-10.0 + 2.0 * (i + 1), rng.uniform(0.0, 0.6)) for i in range(12)] + [(16.0, 0.0), (40.0, 0.0)]
+    s.create_chain(g, pts)
+    # ---- car (Testbed "Car" proportions) ----
+    cx = -20.0 + rng.uniform(-1.0, 1.0)
+    chassis = s.create_body(DYNAMIC_BODY, (cx, 1.0))
+    s.create_polygon(chassis, [(-1.5, -0.5), (1.5, -0.5), (1.5, 0.0), (0.0, 0.9), (-1.15, 0.9), (-1.5, 0.2)], density=1.0)
+    for i, (wx, motor) in enumerate(((-1.0, True), (1.0, False))):
+        wheel = s.create_body(DYNAMIC_BODY, (cx + wx, 0.35))
+        s.create_circle(wheel, 0.4, density=1.0, friction=0.9)
+        s.create_wheel_joint(chassis, wheel, (cx + wx, 0.35), (0.0, 1.0), frequency_hz=(4.0 if i == 0 else rng.uniform(3.0, 5.0)),
+                             damping_ratio=0.7, max_motor_torque=(20.0 if motor else 10.0), motor_speed=(-12.0 if motor else 0.0),
+                             enable_motor=motor)
+    # ---- cantilever: planks welded end to end, first to the ground ----
+    prev = g
+    for i in range(6):
+        b = s.create_body(DYNAMIC_BODY, (20.0 + 0.5 + 1.0 * i, 5.0))
+        s.create_box(b, 0.5, 0.125, density=20.0)
+        s.create_weld_joint(prev, b, (20.0 + 1.0 * i, 5.0), frequency_hz=(0.0 if i < 3 else 5.0), damping_ratio=(0.0 if i < 3 else 0.7))
+        prev = b
+    # ---- welded compound dropped onto the terrain ----
+    a = s.create_body(DYNAMIC_BODY, (2.0, 6.0), angle=rng.uniform(-0.8, 0.8), angular_velocity=rng.uniform(-3.0, 3.0))
+    s.create_box(a, 0.6, 0.2, density=2.0)
+    b = s.create_body(DYNAMIC_BODY, (2.9, 6.0))
+    s.create_circle(b, 0.35, density=1.0)
+    s.create_weld_joint(a, b, (2.6, 6.0))
+    c2 = s.create_body(DYNAMIC_BODY, (2.0, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)
+    s.create_box(c2, 0.3, 0.3, density=1.0)
+    d2 = s.create_body(DYNAMIC_BODY, (2.6, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)
+    s.create_box(d2, 0.3, 0.3, density=1.0)
+    s.create_weld_joint(c2, d2, (2.3, 8.0))  # both bodies with fixed rotation: K.ez.z == 0 branch
     return s
 
 

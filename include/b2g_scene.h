@@ -97,24 +97,25 @@ typedef struct b2g_fixture_def {
 } b2g_fixture_def;
 
 /* Joint types: the values of b2JointType (Box2D/Dynamics/Joints/b2Joint.h:31-45). */
-enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3 };
+enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3, B2G_JOINT_WHEEL = 7, B2G_JOINT_WELD = 8 };
 
 /* The arguments of b2World::CreateJoint: the members of b2RevoluteJointDef (b2RevoluteJoint.h:35-86),
- * b2PrismaticJointDef (b2PrismaticJoint.h:33-87) and b2DistanceJointDef (b2DistanceJoint.h:32-67), already in the
+ * b2PrismaticJointDef (b2PrismaticJoint.h:33-87), b2DistanceJointDef (b2DistanceJoint.h:32-67), b2WheelJointDef
+ * (b2WheelJoint.h:33-73) and b2WeldJointDef (b2WeldJoint.h:30-62), already in the
  * bodies' local frames (what the defs' Initialize() helpers compute). */
 typedef struct b2g_joint_def {
     int32_t type;             /* B2G_JOINT_* */
     int32_t bodyA, bodyB;     /* indices into bodies[] */
     int32_t collideConnected; /* b2JointDef::collideConnected, default false */
     float localAnchorA[2], localAnchorB[2];
-    float localAxisA[2];      /* prismatic (normalised by the joint's constructor) */
-    float referenceAngle;     /* revolute, prismatic */
+    float localAxisA[2];      /* prismatic (normalised by the joint's constructor), wheel (used as given) */
+    float referenceAngle;     /* revolute, prismatic, weld */
     int32_t enableLimit, enableMotor;
     float lower, upper;       /* revolute: lowerAngle / upperAngle; prismatic: lowerTranslation / upperTranslation */
-    float maxMotor;           /* revolute: maxMotorTorque; prismatic: maxMotorForce */
+    float maxMotor;           /* revolute, wheel: maxMotorTorque; prismatic: maxMotorForce */
     float motorSpeed;
     float length;             /* distance */
-    float frequencyHz, dampingRatio; /* distance */
+    float frequencyHz, dampingRatio; /* distance, wheel, weld */
 } b2g_joint_def;
 
 typedef struct b2g_scene {

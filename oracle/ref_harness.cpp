@@ -195,6 +195,23 @@ RefWorld* build_world(const b2g_scene* s) {
             jd.enableLimit = d.enableLimit != 0; jd.lowerTranslation = d.lower; jd.upperTranslation = d.upper;
             jd.enableMotor = d.enableMotor != 0; jd.maxMotorForce = d.maxMotor; jd.motorSpeed = d.motorSpeed;
             w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_WHEEL) {
+            b2WheelJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.localAxisA.Set(d.localAxisA[0], d.localAxisA[1]);
+            jd.enableMotor = d.enableMotor != 0; jd.maxMotorTorque = d.maxMotor; jd.motorSpeed = d.motorSpeed;
+            jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
+            w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_WELD) {
+            b2WeldJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.referenceAngle = d.referenceAngle;
+            jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
+            w->CreateJoint(&jd);
         } else if (d.type == B2G_JOINT_DISTANCE) {
             b2DistanceJointDef jd;
             jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;

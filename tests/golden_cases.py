@@ -183,6 +183,8 @@ WORLD_CASES = {
     # joints in the island solver (revolute, prismatic, distance); live-reference only
     "jointed_seed1_default": (lambda: S.jointed(1), 400, 8, 3),
     "jointed_seed2_default_noccd": (lambda: S.jointed(2, flags=NOCCD), 400, 6, 2),
+    "vehicles_seed1_default": (lambda: S.vehicles(1), 400, 8, 3),
+    "vehicles_seed2_default_noccd": (lambda: S.vehicles(2, flags=NOCCD), 400, 6, 2),
 }
 # scenes the C restatement can run (continuous physics off); the device path runs every case
 NOCCD_CASES = [k for k in WORLD_CASES if "default" not in k and "_ccd_" not in k]

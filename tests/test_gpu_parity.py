@@ -150,6 +150,15 @@ def test_joints_every_step(oracles):
     run_parity(oracles, scenes, 420, 8, 3)
 
 
+def test_wheel_and_weld_joints_every_step(oracles):
+    # b2WheelJoint (spring, motor, point-to-line) and b2WeldJoint (rigid 3x3, soft angular spring, the both-bodies-
+    # fixed-rotation branch) on chain terrain, with and without continuous physics and warm starting
+    _need_ref(oracles)
+    scenes = [S.vehicles(s, flags=(S.WORLD_DEFAULT if s % 2 else NOCCD)) for s in range(5)] + \
+             [S.vehicles(7, flags=S.WORLD_DEFAULT & ~S.WORLD_WARM_STARTING), S.jointed(3)]
+    run_parity(oracles, scenes, 420, 8, 3)
+
+
 def test_joints_no_warm_starting_and_62(oracles):
     _need_ref(oracles)
     scenes = [S.jointed(9, flags=S.WORLD_DEFAULT & ~S.WORLD_WARM_STARTING), S.jointed(10, flags=NOCCD & ~S.WORLD_ALLOW_SLEEP)]
