@@ -211,7 +211,8 @@ class b2Body;
 class b2World;
 class b2WorldBatch;
 
-// ---- joints (Dynamics/Joints/b2Joint.h:31-101, b2RevoluteJoint.h:35-86, b2PrismaticJoint.h:33-87, b2DistanceJoint.h:32-67)
+// ---- joints (Dynamics/Joints/b2Joint.h:31-101, b2RevoluteJoint.h:35-86, b2PrismaticJoint.h:33-87, b2DistanceJoint.h:32-67,
+// b2WheelJoint.h:33-73, b2WeldJoint.h:30-62)
 enum class b2JointType {
     UNKNOWN_JOINT, REVOLUTE_JOINT, PRISMATIC_JOINT, DISTANCE_JOINT, PULLEY_JOINT, MOUSE_JOINT, GEAR_JOINT, WHEEL_JOINT,
     WELD_JOINT, FRICTION_JOINT, ROPE_JOINT, MOTOR_JOINT
@@ -248,6 +249,20 @@ struct b2DistanceJointDef : public b2JointDef {
     void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec<float, 2>& anchorA, const b2Vec<float, 2>& anchorB);
     b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}};
     float length = 1.0f, frequencyHz = 0.0f, dampingRatio = 0.0f;
+};
+struct b2WheelJointDef : public b2JointDef {
+    b2WheelJointDef() { type = b2JointType::WHEEL_JOINT; }
+    void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec<float, 2>& anchor, const b2Vec<float, 2>& axis);
+    b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}}, localAxisA{{1.0f, 0.0f}};
+    bool enableMotor = false;
+    float maxMotorTorque = 0.0f, motorSpeed = 0.0f;
+    float frequencyHz = 2.0f, dampingRatio = 0.7f;
+};
+struct b2WeldJointDef : public b2JointDef {
+    b2WeldJointDef() { type = b2JointType::WELD_JOINT; }
+    void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec<float, 2>& anchor);
+    b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}};
+    float referenceAngle = 0.0f, frequencyHz = 0.0f, dampingRatio = 0.0f;
 };
 class b2Joint {
 public:
@@ -359,7 +374,7 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
-    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic and distance joints; nullptr for the
+    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel and weld joints; nullptr for the
     // joint types outside the device path and once the world is locked (after the first Step)
     b2Joint* CreateJoint(const b2JointDef* def);
     void Step(float timeStep, int32_t velocityIterations, int32_t positionIterations);
@@ -627,6 +642,18 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
         d.type = B2G_JOINT_DISTANCE;
         set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB);
         d.length = r->length; d.frequencyHz = r->frequencyHz; d.dampingRatio = r->dampingRatio;
+    } else if (def->type == b2JointType::WHEEL_JOINT) {
+        const b2WheelJointDef* r = static_cast<const b2WheelJointDef*>(def);
+        d.type = B2G_JOINT_WHEEL;
+        set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB); set2(d.localAxisA, r->localAxisA);
+        d.enableMotor = r->enableMotor; d.maxMotor = r->maxMotorTorque; d.motorSpeed = r->motorSpeed;
+        d.frequencyHz = r->frequencyHz; d.dampingRatio = r->dampingRatio;
+    } else if (def->type == b2JointType::WELD_JOINT) {
+        const b2WeldJointDef* r = static_cast<const b2WeldJointDef*>(def);
+        d.type = B2G_JOINT_WELD;
+        set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB);
+        d.referenceAngle = r->referenceAngle;
+        d.frequencyHz = r->frequencyHz; d.dampingRatio = r->dampingRatio;
     } else {
         return nullptr;
     }
@@ -758,6 +785,18 @@ inline void b2PrismaticJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<
     localAnchorA = bodyA->GetLocalPoint(anchor);
     localAnchorB = bodyB->GetLocalPoint(anchor);
     localAxisA = bodyA->GetLocalVector(axis);
+    referenceAngle = bodyB->GetAngle() - bodyA->GetAngle();
+}
+inline void b2WheelJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& anchor, const b2Vec<float, 2>& axis) {
+    bodyA = bA; bodyB = bB;
+    localAnchorA = bodyA->GetLocalPoint(anchor);
+    localAnchorB = bodyB->GetLocalPoint(anchor);
+    localAxisA = bodyA->GetLocalVector(axis);
+}
+inline void b2WeldJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& anchor) {
+    bodyA = bA; bodyB = bB;
+    localAnchorA = bodyA->GetLocalPoint(anchor);
+    localAnchorB = bodyB->GetLocalPoint(anchor);
     referenceAngle = bodyB->GetAngle() - bodyA->GetAngle();
 }
 inline void b2DistanceJointDef::Initialize(b2Body* b1, b2Body* b2, const b2Vec<float, 2>& anchor1, const b2Vec<float, 2>& anchor2) {
