@@ -92,7 +92,10 @@ __host__ __device__ inline size_t SolveSmemBytes(int NB) {
 // =================================================================================================
 // k_solve_prepare: CTA = one tile, kPrepWarps warps; warp w takes items w, w + kPrepWarps, ...
 // =================================================================================================
-__global__ void __launch_bounds__(kPrepWarps * 32) k_solve_prepare(Arena A, float h) {
+#ifndef B2G_PREP_MIN_BLOCKS
+#define B2G_PREP_MIN_BLOCKS 4  // 64 registers: measured best of 1..6 (0.58 -> 0.55 ms)
+#endif
+__global__ void __launch_bounds__(kPrepWarps * 32, B2G_PREP_MIN_BLOCKS) k_solve_prepare(Arena A, float h) {
     const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const bool live = tile * kTile + lane < A.numWorlds;
