@@ -327,8 +327,10 @@ constexpr int kCollideWarps = 8;
 #endif
 __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_collide(Arena A) {
     __shared__ int sSummary[kTile];
-    extern __shared__ unsigned char sRes[];  // [NC][lane] result byte of phase 1
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // [NC][lane] result byte of phase 1.  In global memory (L2-resident between the phases), not shared memory, so that
+    // the kernel's CTAs fit beside the resident CTAs of another world group's sequential kernels (b2g_step.cu: groups)
+    unsigned char* sRes = A.collideRes + (size_t)(A.tile0 + blockIdx.x) * A.NC * kTile;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     if (warp == 0) {
         sSummary[lane] = 0;
@@ -465,7 +467,7 @@ __host__ __device__ inline size_t IslandSmemPerWorld(int NB, int NC, int NJ) {
 __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
     extern __shared__ __align__(16) unsigned char ismem[];
     __shared__ int sDirty[kTile];
-    const int g = blockIdx.x;            // group of L worlds
+    const int g = A.tile0 * (kTile / L) + blockIdx.x;  // group of L worlds (L divides 32)
     const int w0 = g * L;                // first world of the group
     const int t = threadIdx.x;
     const int NB = A.NB, NC = A.NC;
@@ -1043,7 +1045,7 @@ __device__ __forceinline__ void SolvePositionConstraint(const Arena& A, int tile
 #include "b2g_joints.cuh"
 
 __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, int posIters) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    int w = A.tile0 * kTile + blockIdx.x * blockDim.x + threadIdx.x;
     int tile = w >> 5, lane = w & 31;
     if (tile >= A.numTiles) return;
     size_t ws = (size_t)tile * kTile + lane;
@@ -1488,7 +1490,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 4) k_sync_pairs(Arena A, floa
     __shared__ uint32_t sCand[kMaxCand][kTile];
     __shared__ unsigned char sExists[kMaxCand][kTile];
     __shared__ int sNMoved[kTile], sNCand[kTile];
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const bool live = tile * kTile + lane < A.numWorlds;
     const int np = live ? A.proxyCount[ws] : 0;

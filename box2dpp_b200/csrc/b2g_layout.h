@@ -126,6 +126,7 @@ struct Arena {
     int* islandJointEnd; // [tile][NB][lane]
 
     // ---- per-step temporaries ----
+    unsigned char* collideRes;  // [tile][NC][lane] k_collide: result byte of the evaluation pass
     int* movedList;      // [tile][NP][lane] ascending indices of the proxies in the move buffer
     int* islandBodies;   // [tile][NB+NC][lane] bodies of all islands, concatenated (statics repeat)
     int* islandBodyEnd;  // [tile][NB][lane]   end offset into islandBodies per island
@@ -157,6 +158,7 @@ struct Arena {
     int4* eventA;        // type, fixtureA | childA << 16, fixtureB | childB << 16, count
     float4* eventB;      // normalImpulses[2], tangentImpulses[2]
     int eventMask;       // bit per kEvent* type recorded
+    int tile0;           // first tile of this launch (world groups run the step chain on separate streams)
     int hasJoints;       // desc.maxJoints > 0: the joint arrays are live (generic solver path)
     int alwaysRebuildIslands;  // validation switch: k_islands ignores topoDirty (desc.reserved bit 1)
 };

@@ -96,7 +96,7 @@ __host__ __device__ inline size_t SolveSmemBytes(int NB) {
 #define B2G_PREP_MIN_BLOCKS 4  // 64 registers: measured best of 1..6 (0.58 -> 0.55 ms)
 #endif
 __global__ void __launch_bounds__(kPrepWarps * 32, B2G_PREP_MIN_BLOCKS) k_solve_prepare(Arena A, float h) {
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const bool live = tile * kTile + lane < A.numWorlds;
     const int nb = live ? A.bodyCount[ws] : 0;
@@ -533,7 +533,7 @@ __device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, BodyT
 __global__ void __launch_bounds__(96) k_solve_velocity(Arena A, int velIters) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t sReady;  // records whose data has landed in the ring (published by the watcher warp)
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const int n = A.solveCount[ws];
     const int nMax = __reduce_max_sync(0xffffffffu, n);
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(96) k_solve_velocity(Arena A, int velIters) {
 // k_solve_integrate: StoreImpulses, PostSolve events, integrate positions -> position table
 // =================================================================================================
 __global__ void __launch_bounds__(kPrepWarps * 32) k_solve_integrate(Arena A, float h) {
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const bool live = tile * kTile + lane < A.numWorlds;
     const int nb = live ? A.bodyCount[ws] : 0;
@@ -791,7 +791,7 @@ constexpr int kPosStageBytes = kPosRec * 16 * kTile;  // 2560
 __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int sContinue;
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const int n = A.solveCount[ws];
     const int islands = A.islandCount[ws];
@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
 // k_solve_finalize: write-back + SynchronizeTransform, sleep
 // =================================================================================================
 __global__ void __launch_bounds__(kPrepWarps * 32) k_solve_finalize(Arena A, float h) {
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const bool live = tile * kTile + lane < A.numWorlds;
     const int nb = live ? A.bodyCount[ws] : 0;

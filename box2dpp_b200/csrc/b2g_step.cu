@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -322,10 +323,21 @@ __global__ void k_sincosf(const float* __restrict__ x, float* __restrict__ s, fl
 
 }  // namespace
 
+constexpr int kGraphChunk = 8;
+
 struct b2gpu_batch {
     b2gpu_batch_desc desc;
     Arena A;
     cudaStream_t stream = nullptr;
+    // World groups: the step's kernel chain is enqueued once per group of tiles, group 0 on `stream`, the others on
+    // their own streams (forked from and joined back into `stream` with events, inside or outside graph capture).
+    // Groups are independent worlds, so one group's sequential kernels (64 worlds per SM, 2 of 4 schedulers) overlap
+    // another group's parallel kernels on the same SMs.
+    static constexpr int kMaxGroups = 8;
+    int groups = 1;
+    cudaStream_t groupStream[kMaxGroups] = {nullptr};
+    cudaEvent_t evFork = nullptr, evJoin[kMaxGroups] = {nullptr}, evSeq[kMaxGroups] = {nullptr};
+    bool pipelineGroups = false;  // B2GPU_PIPELINE=1 orders the groups' sequential parts (measured slower than free-running)
     std::vector<Field> fields;
     std::vector<void*> allocations;
     bool needInitialPairs = true;  // b2World::e_newFixture
@@ -338,7 +350,8 @@ struct b2gpu_batch {
     int64_t launches = 0;
     size_t arenaBytes = 0;
     // graph of one step, keyed by its parameters
-    cudaGraphExec_t graphExec = nullptr;
+    cudaGraphExec_t graphExec = nullptr;       // one step
+    cudaGraphExec_t graphExecChunk = nullptr;  // kGraphChunk steps (several groups only)
     float graphDt = 0.0f;
     int graphVel = 0, graphPos = 0;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
@@ -396,6 +409,7 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(shapeWords, A.NS, float); ALLOC(chainVerts, A.NV, float2);
     ALLOC(contactA, A.NC, int4); ALLOC(contactK, A.NC, int4); ALLOC(contactS, A.NC, int2);
     ALLOC(contactP0, A.NC, float4); ALLOC(contactP1, A.NC, float4); ALLOC(contactN, A.NC, float4);
+    ALLOC(collideRes, A.NC, unsigned char);
     ALLOC(movedList, A.NP, int);
     ALLOC(islandBodies, A.NB + A.NC, int); ALLOC(islandBodyEnd, A.NB, int);
     ALLOC(islandContacts, A.NC, int); ALLOC(islandContactEnd, A.NB, int);
@@ -507,11 +521,6 @@ int configureKernels(b2gpu_batch* b) {
     b->solveSmem = SolveSmemBytes(desc->maxBodies);
     // joints are solved by the generic kernel only (b2g_joints.cuh)
     b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0 && desc->maxJoints <= 0;
-    if ((size_t)desc->maxContacts * kTile > (size_t)maxSmem - 1024)
-        return fail(B2GPU_ERR_CAPACITY, "maxContacts %d exceeds the collide kernel's shared-memory budget (%d)",
-                    desc->maxContacts, (maxSmem - 1024) / kTile);
-    CUDA_TRY(cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, desc->maxContacts * kTile));
-    CUDA_TRY(cudaFuncSetAttribute(k_toi, cudaFuncAttributeMaxDynamicSharedMemorySize, desc->maxContacts * kTile));
     if (b->tileSolver) {
         CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
         CUDA_TRY(cudaFuncSetAttribute(k_solve_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
@@ -538,59 +547,118 @@ constexpr int kMaxStepKernels = 10;
 // k_toi only runs when some world has continuous physics on (b2World::Step: `if (m_continuousPhysics && dt > 0)`)
 int stepKernelCount(const b2gpu_batch* b) { return (b->tileSolver ? 8 : 4) + (b->anyContinuous ? 2 : 0); }
 
-// One b2World::Step for the whole batch (Box2D/Dynamics/b2World.cpp:888-954).
-// marks (optional): stepKernelCount + 1 events, one before each kernel and one after the last.
-int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks) {
+// The kernel chain of one step for tiles [tile0, tile0 + tileCount) on stream st, in three parts:
+//   part 0  k_collide, k_islands, k_solve_prepare            parallel kernels, little shared memory
+//   part 1  k_solve_velocity, k_solve_integrate, k_solve_position   the sequential kernels: they own the SMs' shared memory
+//   part 2  k_solve_finalize, k_sync_pairs, k_toi, k_toi_events
+// (the generic solver path has k_solve as part 1).  `m` is the running index into marks.
+void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters, cudaEvent_t* marks, int* m, cudaStream_t st,
+                 int tile0, int tileCount) {
+    Arena A = b->A;
+    A.tile0 = tile0;
     const int threads = b->blockSize;
-    const unsigned tiles = (unsigned)b->A.numTiles;
-    const unsigned blocks = (unsigned)(((size_t)b->A.numTiles * kTile + threads - 1) / threads);
+    const unsigned tiles = (unsigned)tileCount;
+    const unsigned blocks = (unsigned)(((size_t)tileCount * kTile + threads - 1) / threads);
+    auto mark = [&]() { if (marks) cudaEventRecord(marks[(*m)++], st); };
+    if (part == 0) {
+        mark();
+        k_collide<<<tiles, kCollideWarps * 32, 0, st>>>(A);
+        mark();
+        if (dt > 0.0f) {
+            k_islands<<<(unsigned)((tileCount * kTile + b->islandLanes - 1) / b->islandLanes), kIslandThreads, b->islandSmem, st>>>(A, b->islandLanes);
+            mark();
+            if (b->tileSolver) {
+                k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
+                mark();
+            }
+        }
+    } else if (dt <= 0.0f) {
+        return;
+    } else if (part == 1) {
+        if (b->tileSolver) {
+            k_solve_velocity<<<tiles, 96, b->solveSmem, st>>>(A, velIters);
+            mark();
+            k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
+            mark();
+            k_solve_position<<<tiles, 64, b->solveSmem, st>>>(A, posIters);
+            mark();
+        } else {
+            k_solve<<<blocks, threads, 0, st>>>(A, dt, velIters, posIters);
+            mark();
+        }
+    } else {
+        if (b->tileSolver) {
+            k_solve_finalize<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
+            mark();
+        }
+        k_sync_pairs<<<tiles, kPairWarps * 32, 0, st>>>(A, dt);
+        mark();
+        if (b->anyContinuous) {  // if (m_continuousPhysics && step.dt > 0) SolveTOI(step)
+            k_toi<<<tiles, kToiWarps * 32, 0, st>>>(A, dt, velIters);
+            mark();
+            k_toi_events<<<tiles, 32, 0, st>>>(A, dt, velIters);
+            mark();
+        }
+    }
+}
+
+// `count` b2World::Step calls for the whole batch (Box2D/Dynamics/b2World.cpp:888-954).
+// marks (optional): per chain stepKernelCount + 1 events, one before the first kernel and one after each.
+//
+// World groups (b->groups > 1): every group of tiles has its own stream and runs the same chain.  The sequential
+// kernels of a tile solver step hold nearly all shared memory of the SMs they run on (2 x 111 KB) but issue from two
+// warps per SM, while the parallel kernels need registers and issue slots but no shared memory: the groups are
+// software-pipelined so that one group's part 1 runs while the other groups are in parts 0 / 2 — group g's part 1 of
+// a step waits for group g-1's part 1 of the same step (group 0: for the last group's part 1 of the previous step).
+int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks, int count, bool traceGroups = false) {
     cudaStream_t st = b->stream;
     if (b->needInitialPairs) {  // if (m_flags & e_newFixture) FindNewContacts()
+        const int threads = b->blockSize;
+        const unsigned blocks = (unsigned)(((size_t)b->A.numTiles * kTile + threads - 1) / threads);
         k_find_new_contacts<<<blocks, threads, 0, st>>>(b->A);
         k_index_proxies<<<(unsigned)((b->A.numTiles * kTile + 127) / 128), 128, 0, st>>>(b->A);
         b->needInitialPairs = false;
         b->launches += 2;
     }
-    int m = 0;
-    auto mark = [&]() { if (marks) cudaEventRecord(marks[m++], st); };
-    mark();
-    k_collide<<<tiles, kCollideWarps * 32, (size_t)b->A.NC * kTile, st>>>(b->A);
-    b->launches++;
-    mark();
-    if (dt > 0.0f) {
-        k_islands<<<(unsigned)((b->A.numTiles * kTile + b->islandLanes - 1) / b->islandLanes), kIslandThreads, b->islandSmem, st>>>(b->A, b->islandLanes);
-        mark();
-        if (b->tileSolver) {
-            k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
-            mark();
-            k_solve_velocity<<<tiles, 96, b->solveSmem, st>>>(b->A, velIters);
-            mark();
-            k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
-            mark();
-            k_solve_position<<<tiles, 64, b->solveSmem, st>>>(b->A, posIters);
-            mark();
-            k_solve_finalize<<<tiles, kPrepWarps * 32, 0, st>>>(b->A, dt);
-            mark();
-            b->launches += 5;
-        } else {
-            k_solve<<<blocks, threads, 0, st>>>(b->A, dt, velIters, posIters);
-            mark();
-            b->launches++;
-        }
-        k_sync_pairs<<<tiles, kPairWarps * 32, 0, st>>>(b->A, dt);
-        mark();
-        b->launches += 2;
-        if (b->anyContinuous) {  // if (m_continuousPhysics && step.dt > 0) SolveTOI(step)
-            k_toi<<<tiles, kToiWarps * 32, (size_t)b->A.NC * kTile, st>>>(b->A, dt, velIters);
-            mark();
-            k_toi_events<<<tiles, 32, 0, st>>>(b->A, dt, velIters);
-            mark();
-            b->launches += 2;
+    const int perStep = dt > 0.0f ? stepKernelCount(b) : 1;
+    const int nkTrace = stepKernelCount(b) + 1;  // traceGroups: marks is [group][step][nk + 1]
+    int G = ((marks && !traceGroups) || b->groups < 1) ? 1 : b->groups;
+    if (G > b->A.numTiles) G = b->A.numTiles > 0 ? b->A.numTiles : 1;
+    const int per = (b->A.numTiles + G - 1) / G;
+    if (G > 1) {  // fork: every group stream waits for what is already queued on the batch's stream
+        cudaEventRecord(b->evFork, st);
+        for (int g = 1; g < G; ++g) cudaStreamWaitEvent(b->groupStream[g], b->evFork, 0);
+    }
+    const bool pipeline = G > 1 && b->tileSolver && dt > 0.0f && b->pipelineGroups;
+    for (int i = 0; i < count; ++i) {
+        for (int g = 0; g < G; ++g) {
+            const int t0 = g * per;
+            const int n = b->A.numTiles - t0 < per ? b->A.numTiles - t0 : per;
+            if (n <= 0) break;
+            cudaStream_t gs = g == 0 ? st : b->groupStream[g];
+            cudaEvent_t* mk = marks ? marks + (traceGroups ? ((size_t)g * count + i) * nkTrace : 0) : nullptr;
+            int m = 0;
+            enqueuePart(b, 0, dt, velIters, posIters, mk, &m, gs, t0, n);
+            if (pipeline) {
+                const int prev = g == 0 ? G - 1 : g - 1;
+                if (g > 0 || i > 0) cudaStreamWaitEvent(gs, b->evSeq[prev], 0);
+            }
+            enqueuePart(b, 1, dt, velIters, posIters, mk, &m, gs, t0, n);
+            if (pipeline) cudaEventRecord(b->evSeq[g], gs);
+            enqueuePart(b, 2, dt, velIters, posIters, mk, &m, gs, t0, n);
         }
     }
+    for (int g = 1; g < G; ++g) {  // join
+        cudaEventRecord(b->evJoin[g], b->groupStream[g]);
+        cudaStreamWaitEvent(st, b->evJoin[g], 0);
+    }
+    b->launches += (int64_t)perStep * G * count;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return B2GPU_OK;
+}
+int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks) {
+    return enqueueSteps(b, dt, velIters, posIters, marks, 1);
 }
 
 }  // namespace
@@ -601,6 +669,17 @@ const char* b2gpu_last_error(void) { return g_error.c_str(); }
 
 // lets the host layer (b2g_host.cpp) report through the same thread-local message
 int b2gpu_host_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
+// How many world groups step concurrently (measured with tools/groups_sweep2.sh, pyramid-20, ms per step for 1 / 2 / 4
+// groups): 8,192 worlds 3.46 / 3.47 / 3.56; 16,384 worlds 5.75 / 5.31 / 5.32; 32,768 worlds 10.79 / 9.55 / 9.14.
+// Groups pay off once the sequential kernels need more than one wave of resident tiles (2 per SM).
+static int defaultGroups(const b2gpu_batch* b) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->desc.device);
+    const int wave = 2 * sms;
+    if (!b->tileSolver || b->A.numTiles <= wave) return 1;
+    return b->A.numTiles >= 3 * wave ? 4 : 2;
+}
 
 int b2gpu_batch_create(const b2gpu_batch_desc* desc, b2gpu_batch** out) {
     if (!desc || !out) return fail(B2GPU_ERR_INVALID, "null argument");
@@ -633,6 +712,19 @@ int b2gpu_batch_create(const b2gpu_batch_desc* desc, b2gpu_batch** out) {
     if (rc == B2GPU_OK) {
         e = cudaEventCreate(&b->evStart);
         if (e == cudaSuccess) e = cudaEventCreate(&b->evStop);
+        // World groups (see b2gpu_batch::groups): B2GPU_GROUPS overrides the default for experiments.
+        b->groups = defaultGroups(b);
+        if (const char* env = getenv("B2GPU_GROUPS")) {
+            const int g = atoi(env);
+            if (g >= 1 && g <= b2gpu_batch::kMaxGroups) b->groups = g;
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->evFork, cudaEventDisableTiming);
+        if (const char* env = getenv("B2GPU_PIPELINE")) b->pipelineGroups = atoi(env) != 0;
+        for (int g = 0; g < b->groups && e == cudaSuccess; ++g) {
+            if (g > 0) e = cudaStreamCreateWithFlags(&b->groupStream[g], cudaStreamNonBlocking);
+            if (e == cudaSuccess && g > 0) e = cudaEventCreateWithFlags(&b->evJoin[g], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->evSeq[g], cudaEventDisableTiming);
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
         if (e != cudaSuccess) rc = fail(B2GPU_ERR_CUDA, "batch setup failed: %s", cudaGetErrorString(e));
     }
@@ -649,6 +741,14 @@ int b2gpu_batch_destroy(b2gpu_batch* b) {
     if (b->ioDev) cudaFree(b->ioDev);
     if (b->cmdDev) cudaFree(b->cmdDev);
     if (b->graphExec) cudaGraphExecDestroy(b->graphExec);
+    if (b->graphExecChunk) cudaGraphExecDestroy(b->graphExecChunk);
+    for (int g = 1; g < b2gpu_batch::kMaxGroups; ++g) {
+        if (b->groupStream[g]) { cudaStreamSynchronize(b->groupStream[g]); cudaStreamDestroy(b->groupStream[g]); }
+        if (b->evJoin[g]) cudaEventDestroy(b->evJoin[g]);
+    }
+    for (int g = 0; g < b2gpu_batch::kMaxGroups; ++g)
+        if (b->evSeq[g]) cudaEventDestroy(b->evSeq[g]);
+    if (b->evFork) cudaEventDestroy(b->evFork);
     if (b->evStart) cudaEventDestroy(b->evStart);
     if (b->evStop) cudaEventDestroy(b->evStop);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -664,9 +764,9 @@ int b2gpu_batch_upload_field(b2gpu_batch* b, int32_t field, const void* host, in
         const int32_t* flags = static_cast<const int32_t*>(host);
         for (int32_t i = 0; i < worldCount; ++i)
             if (flags[i] & B2G_WORLD_CONTINUOUS) { b->anyContinuous = true; break; }
-        if (b->anyContinuous && b->graphExec) {  // the captured step has no k_toi: capture again
-            cudaGraphExecDestroy(b->graphExec);
-            b->graphExec = nullptr;
+        if (b->anyContinuous) {  // the captured steps have no k_toi: capture again
+            if (b->graphExec) { cudaGraphExecDestroy(b->graphExec); b->graphExec = nullptr; }
+            if (b->graphExecChunk) { cudaGraphExecDestroy(b->graphExecChunk); b->graphExecChunk = nullptr; }
         }
     }
     // any host edit may change what the islands depend on: rebuild them on the next step
@@ -689,6 +789,22 @@ int b2gpu_batch_step(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIter
     return enqueueStep(b, dt, velIters, posIters, nullptr);
 }
 
+// Captures `count` steps into a graph (all group streams join the capture through the fork / join events).
+static int captureSteps(b2gpu_batch* b, float dt, int velIters, int posIters, int count, cudaGraphExec_t* out) {
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+    int64_t before = b->launches;
+    int rc = enqueueSteps(b, dt, velIters, posIters, nullptr, count);
+    b->launches = before;
+    cudaError_t e = cudaStreamEndCapture(b->stream, &graph);
+    if (rc != B2GPU_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    return B2GPU_OK;
+}
+
 int b2gpu_batch_step_n(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIters, int32_t steps) {
     if (!b || steps < 0) return fail(B2GPU_ERR_INVALID, "bad arguments");
     CUDA_TRY(cudaSetDevice(b->desc.device));
@@ -701,25 +817,33 @@ int b2gpu_batch_step_n(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIt
         done = 1;
     }
     if (done < steps) {
-        if (!b->graphExec || b->graphDt != dt || b->graphVel != velIters || b->graphPos != posIters) {
+        if (b->graphDt != dt || b->graphVel != velIters || b->graphPos != posIters) {
             if (b->graphExec) { cudaGraphExecDestroy(b->graphExec); b->graphExec = nullptr; }
-            cudaGraph_t graph = nullptr;
-            CUDA_TRY(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
-            int64_t before = b->launches;
-            int rc = enqueueStep(b, dt, velIters, posIters, nullptr);
-            b->launches = before;
-            cudaError_t e = cudaStreamEndCapture(b->stream, &graph);
-            if (rc != B2GPU_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&b->graphExec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+            if (b->graphExecChunk) { cudaGraphExecDestroy(b->graphExecChunk); b->graphExecChunk = nullptr; }
             b->graphDt = dt; b->graphVel = velIters; b->graphPos = posIters;
         }
-        const int perStep = dt > 0.0f ? stepKernelCount(b) : 1;
-        for (; done < steps; ++done) {
-            CUDA_TRY(cudaGraphLaunch(b->graphExec, b->stream));
-            b->launches += perStep;
+        const int perStep = (dt > 0.0f ? stepKernelCount(b) : 1) * (b->groups > 1 ? b->groups : 1);
+        // several groups: graphs of kGraphChunk steps, so that the groups only re-synchronise at chunk boundaries
+        const int chunk = b->groups > 1 ? kGraphChunk : 1;
+        if (chunk > 1 && steps - done >= chunk) {
+            if (!b->graphExecChunk) {
+                int rc = captureSteps(b, dt, velIters, posIters, chunk, &b->graphExecChunk);
+                if (rc != B2GPU_OK) return rc;
+            }
+            for (; steps - done >= chunk; done += chunk) {
+                CUDA_TRY(cudaGraphLaunch(b->graphExecChunk, b->stream));
+                b->launches += (int64_t)perStep * chunk;
+            }
+        }
+        if (done < steps) {
+            if (!b->graphExec) {
+                int rc = captureSteps(b, dt, velIters, posIters, 1, &b->graphExec);
+                if (rc != B2GPU_OK) return rc;
+            }
+            for (; done < steps; ++done) {
+                CUDA_TRY(cudaGraphLaunch(b->graphExec, b->stream));
+                b->launches += perStep;
+            }
         }
     }
     CUDA_TRY(cudaEventRecord(b->evStop, b->stream));
@@ -763,6 +887,30 @@ int b2gpu_batch_profile_kernels(b2gpu_batch* b, float dt, int32_t velIters, int3
     }
     for (int i = 0; i <= nk; ++i) cudaEventDestroy(marks[i]);
     if (count) *count = nk;
+    return rc;
+}
+
+// Diagnostic: `steps` steps with the batch's world groups, a CUDA event after every kernel of every group.
+// ms[(group * steps + step) * (kernels + 1) + k] = completion time of kernel k - 1 of that step on that group's
+// stream (k = 0: when the chain started), in ms since the first chain started.
+int b2gpu_batch_trace_groups(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIters, int32_t steps, float* ms,
+                             int32_t capacity, int32_t* groupsOut, int32_t* kernelsOut) {
+    if (!b || !ms || steps <= 0 || dt <= 0.0f) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    const int nk = stepKernelCount(b), G = b->groups < b->A.numTiles ? b->groups : 1;
+    const size_t n = (size_t)G * steps * (nk + 1);
+    if ((size_t)capacity < n) return fail(B2GPU_ERR_INVALID, "ms[] needs room for %zu values", n);
+    std::vector<cudaEvent_t> ev(n);
+    for (size_t i = 0; i < n; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
+    int rc = enqueueSteps(b, dt, velIters, posIters, ev.data(), steps, true);
+    if (rc == B2GPU_OK && cudaStreamSynchronize(b->stream) != cudaSuccess) rc = fail(B2GPU_ERR_CUDA, "trace failed");
+    for (size_t i = 0; i < n && rc == B2GPU_OK; ++i) {
+        ms[i] = 0.0f;
+        cudaEventElapsedTime(&ms[i], ev[0], ev[i]);
+    }
+    for (size_t i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+    if (groupsOut) *groupsOut = G;
+    if (kernelsOut) *kernelsOut = nk;
     return rc;
 }
 

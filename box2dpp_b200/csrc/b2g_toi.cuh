@@ -769,9 +769,10 @@ __device__ __noinline__ void SolveToiWorld(const Arena* Ap, int tile, int lane, 
 // k_toi — b2World::SolveTOI for every world with continuous physics
 // =================================================================================================
 __global__ void __launch_bounds__(kToiWarps * 32) k_toi(Arena A, float dt, int velIters) {
-    extern __shared__ unsigned char sIsCand[];  // [NC][kTile]: contact passes ToiStaticCandidate
+    // [NC][kTile]: contact passes ToiStaticCandidate (k_collide's result-byte scratch, free again at this point of the chain)
+    unsigned char* sIsCand = A.collideRes + (size_t)(A.tile0 + blockIdx.x) * A.NC * kTile;
     __shared__ unsigned int sMinAlpha[kTile];
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const bool live = tile * kTile + lane < A.numWorlds && (A.worldFlags[ws] & B2G_WORLD_CONTINUOUS) != 0;
     if (!__syncthreads_or(live)) return;
@@ -842,7 +843,7 @@ __global__ void __launch_bounds__(kToiWarps * 32) k_toi(Arena A, float dt, int v
 // only way to hide them is other tiles' warps.
 __global__ void __launch_bounds__(32) k_toi_events(Arena A, float dt, int velIters) {
     __shared__ ToiLists lists;
-    const int tile = blockIdx.x, lane = threadIdx.x;
+    const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x;
     const size_t ws = (size_t)tile * kTile + lane;
     if (tile * kTile + lane >= A.numWorlds) return;
     if (1.0f - 10.0f * kEpsilon < A.toiMinAlpha[ws]) return;

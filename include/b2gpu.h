@@ -228,6 +228,11 @@ int b2gpu_batch_profile_steps(b2gpu_batch* batch, float dt, int32_t velocityIter
 int b2gpu_batch_profile_kernels(b2gpu_batch* batch, float dt, int32_t velocityIterations, int32_t positionIterations,
                                 int32_t steps, float* ms, int32_t capacity, int32_t* count);
 const char* b2gpu_batch_kernel_name(b2gpu_batch* batch, int32_t index);
+/* Diagnostic timeline of the world groups (the step chain runs once per group of tiles, on separate streams):
+ * ms[(group * steps + step) * (kernels + 1) + k] = completion time of kernel k - 1 of that step on that group's stream
+ * (k = 0: start of the chain), in ms since the first chain started. */
+int b2gpu_batch_trace_groups(b2gpu_batch* batch, float dt, int32_t velocityIterations, int32_t positionIterations,
+                             int32_t steps, float* ms, int32_t capacity, int32_t* groups, int32_t* kernels);
 /* Number of kernel launches issued by this batch so far. */
 int64_t b2gpu_batch_launch_count(b2gpu_batch* batch);
 
