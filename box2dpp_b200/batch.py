@@ -140,7 +140,7 @@ class WorldBatch:
     """A batch of independent worlds on one GPU."""
 
     def __init__(self, scenes, replicate=1, device=0, max_contacts=0, max_events=0, event_mask=0, block_size=0,
-                 generic_solver=False, always_rebuild_islands=False):
+                 generic_solver=False, always_rebuild_islands=False, binned_collide=None):
         if isinstance(scenes, Scene):
             scenes = [scenes]
         if isinstance(scenes, SceneBatch):
@@ -156,6 +156,8 @@ class WorldBatch:
         d.maxContacts, d.maxEvents, d.eventMask, d.blockSize = max_contacts, max_events, event_mask, block_size
         d.reserved = (1 if generic_solver else 0) | (2 if always_rebuild_islands else 0)
         _check(L.b2gpu_scene_capacities(arr, n_scenes, C.byref(d)))
+        if binned_collide is not None:  # default: decided by b2gpu_scene_capacities (worlds that mix shape types)
+            d.reserved = (d.reserved | 4) if binned_collide else (d.reserved & ~4)
         self.desc = d
         self.h = C.c_void_p()
         _check(L.b2gpu_batch_create(C.byref(d), C.byref(self.h)))

@@ -562,6 +562,17 @@ int b2gpu_scene_capacities(const b2g_scene* scenes, int32_t sceneCount, b2gpu_ba
     int NJ = 0;
     for (int i = 0; i < sceneCount; ++i) NJ = scenes[i].jointCount > NJ ? scenes[i].jointCount : NJ;
     desc->maxJoints = NJ;
+    // worlds that mix shape types (or have sensors) take the type-binned narrow phase of k_collide
+    bool mixed = false;
+    for (int i = 0; i < sceneCount && !mixed; ++i) {
+        int types = 0;
+        for (int f = 0; f < scenes[i].fixtureCount; ++f) {
+            types |= 1 << (scenes[i].fixtures[f].shapeType & 3);
+            if (scenes[i].fixtures[f].isSensor) mixed = true;
+        }
+        if (types & (types - 1)) mixed = true;
+    }
+    if (mixed) desc->reserved |= 4;
     if (desc->maxContacts <= 0) desc->maxContacts = 4 * NP + 32;   // pyramid-20 peaks at 604 for 211 proxies
     if (desc->maxEvents <= 0) desc->maxEvents = desc->eventMask ? 3 * desc->maxContacts : 1;
     return B2GPU_OK;

@@ -285,9 +285,11 @@ __device__ __forceinline__ int UpdateOne(const Arena& A, int tile, int lane, int
             cP1[k] = make_float4(m.lp1.x, m.lp1.y, nI, tI);
         }
         col(A.contactN, tile, A.NC, lane)[k] = make_float4(m.localNormal.x, m.localNormal.y, m.localPoint.x, m.localPoint.y);
-        if (kk.x != (int)m.key0 || kk.y != (int)m.key1) {
+        // points[1].id keeps its old value while the manifold has one point (the reference evaluates in place)
+        const int newKey1 = m.pointCount > 1 ? (int)m.key1 : kk.y;
+        if (kk.x != (int)m.key0 || kk.y != newKey1) {
             kk.x = (int)m.key0;
-            kk.y = (int)m.key1;
+            kk.y = newKey1;
             cK[k] = kk;
         }
     }
@@ -315,6 +317,16 @@ __device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, in
 }
 
 constexpr int kCollideWarps = 8;
+constexpr int kCollideClasses = 6;
+// Which manifold function b2Contact::Update runs for this contact (EvaluateContact's dispatch; 5 = sensor overlap test)
+__device__ __forceinline__ int CollideClass(const int4 a) {
+    if (a.z & kContactSensor) return 5;
+    const int tA = (a.w >> 16) & 3, tB = (a.w >> 18) & 3;
+    if (tA == B2G_SHAPE_POLYGON && tB == B2G_SHAPE_POLYGON) return 0;
+    if (tA == B2G_SHAPE_CIRCLE && tB == B2G_SHAPE_CIRCLE) return 1;
+    if (tA == B2G_SHAPE_POLYGON && tB == B2G_SHAPE_CIRCLE) return 2;
+    return tB == B2G_SHAPE_CIRCLE ? 3 : 4;
+}
 
 // CTA = one tile of 32 worlds (lane = world), kCollideWarps warps.
 // Phase 1 (all warps, contacts strided over warps): every contact that is active under the body flags the step
@@ -344,6 +356,65 @@ __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_
     __syncthreads();
 
     int summary = 0;  // 1: the list-order pass is needed, 2: island topology changed
+    if (A.collideItems != nullptr) {
+        // ---- type-binned evaluation (batches whose worlds mix shape types) ----
+        // With lane = world, contact k of 32 different worlds is 32 different shape pairs and the warp runs up to
+        // five manifold functions one after the other.  Here the tile's active contacts are first classified and
+        // counting-sorted by manifold function, then evaluated 32 items of ONE function per warp; an item is
+        // (contact k, lane): the evaluation only touches that world's columns, so its result is the same.
+        __shared__ int sCount[kCollideClasses], sOffset[kCollideClasses + 1], sFill[kCollideClasses], sTotal;
+        uint32_t* list1 = A.collideItems + (size_t)tile * 2 * A.NC * kTile;
+        uint32_t* list2 = list1 + (size_t)A.NC * kTile;
+        if (threadIdx.x < kCollideClasses) { sCount[threadIdx.x] = 0; sFill[threadIdx.x] = 0; }
+        if (threadIdx.x == 0) sTotal = 0;
+        __syncthreads();
+        Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+        for (int k = warp; k < nMax; k += kCollideWarps) {
+            if (k >= n) continue;
+            const int4 a0 = cA[k];
+            const int bfA = bodyFlags[a0.y & 0xffff], bfB = bodyFlags[(a0.y >> 16) & 0xffff];
+            const bool activeA = (bfA & kBodyAwake) && (bfA & kBodyTypeMask) != B2G_STATIC_BODY;
+            const bool activeB = (bfB & kBodyAwake) && (bfB & kBodyTypeMask) != B2G_STATIC_BODY;
+            int res = 0;
+            if (activeA || activeB) {
+                if (!FatOverlap(proxyFat[a0.x & 0xffff], proxyFat[(a0.x >> 16) & 0xffff])) {
+                    res = CollideOne(A, tile, lane, k);  // the destroy branch
+                    summary |= 3;
+                } else {
+                    const int cls = CollideClass(a0);
+                    list1[atomicAdd(&sTotal, 1)] = (uint32_t)k | ((uint32_t)lane << 16) | ((uint32_t)cls << 24);
+                    atomicAdd(&sCount[cls], 1);
+                }
+                if (A.eventMask) summary |= 1;
+            }
+            tmp[k * kTile] = (unsigned char)res;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {  // class regions padded to whole warps
+            int o = 0;
+            for (int c = 0; c < kCollideClasses; ++c) { sOffset[c] = o; o += (sCount[c] + 31) & ~31; }
+            sOffset[kCollideClasses] = o;
+        }
+        __syncthreads();
+        const int total = sTotal, padded = sOffset[kCollideClasses];
+        for (int i = threadIdx.x; i < padded; i += kCollideWarps * 32) list2[i] = 0xffffffffu;
+        __syncthreads();
+        for (int i = threadIdx.x; i < total; i += kCollideWarps * 32) {
+            const uint32_t item = list1[i];
+            const int c = (int)(item >> 24);
+            list2[sOffset[c] + atomicAdd(&sFill[c], 1)] = item;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < padded; i += kCollideWarps * 32) {
+            const uint32_t item = list2[i];
+            if (item == 0xffffffffu) continue;
+            const int k = (int)(item & 0xffff), ln = (int)((item >> 16) & 31);
+            const int res = UpdateOne(A, tile, ln, k, col(A.contactA, tile, A.NC, ln)[k]);
+            const bool changed = ((res & kResWasTouching) != 0) != ((res & kResTouching) != 0);
+            if (changed) atomicOr(&sSummary[ln], 3);
+            sRes[k * kTile + ln] = (unsigned char)res;
+        }
+    } else
     for (int k = warp; k < nMax; k += kCollideWarps) {
         if (k >= n) continue;
         const int bodies = cA[k].y;

@@ -127,6 +127,7 @@ struct Arena {
 
     // ---- per-step temporaries ----
     unsigned char* collideRes;  // [tile][NC][lane] k_collide: result byte of the evaluation pass
+    uint32_t* collideItems;     // [tile][2][NC * 32] k_collide's type-binned work lists; nullptr = worlds of one shape type
     int* movedList;      // [tile][NP][lane] ascending indices of the proxies in the move buffer
     int* islandBodies;   // [tile][NB+NC][lane] bodies of all islands, concatenated (statics repeat)
     int* islandBodyEnd;  // [tile][NB][lane]   end offset into islandBodies per island

@@ -410,6 +410,7 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(contactA, A.NC, int4); ALLOC(contactK, A.NC, int4); ALLOC(contactS, A.NC, int2);
     ALLOC(contactP0, A.NC, float4); ALLOC(contactP1, A.NC, float4); ALLOC(contactN, A.NC, float4);
     ALLOC(collideRes, A.NC, unsigned char);
+    if ((d.reserved & 4) && A.NC <= 65535) ALLOC(collideItems, (size_t)2 * A.NC, uint32_t);  // mixed shape types: type-binned narrow phase
     ALLOC(movedList, A.NP, int);
     ALLOC(islandBodies, A.NB + A.NC, int); ALLOC(islandBodyEnd, A.NB, int);
     ALLOC(islandContacts, A.NC, int); ALLOC(islandContactEnd, A.NB, int);

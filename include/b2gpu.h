@@ -88,7 +88,9 @@ typedef struct b2gpu_batch_desc {
     int32_t eventMask;     /* bit (1 << B2GPU_EVENT_*) per recorded event type; 0 = no listener */
     int32_t blockSize;     /* threads per CTA, multiple of 32; 0 = default */
     int32_t reserved;      /* bit 0: force the generic solver kernel (body state in global memory);
-                              bit 1: rebuild the islands every step (validation of the topology-dirty tracking) */
+                              bit 1: rebuild the islands every step (validation of the topology-dirty tracking);
+                              bit 2: type-binned narrow phase (set by b2gpu_scene_capacities when a scene mixes shape
+                                     types or has sensors; results do not depend on it) */
     int32_t maxJoints;     /* per world; > 0 selects the generic solver kernel (joints are solved there) */
 } b2gpu_batch_desc;
 

@@ -165,6 +165,24 @@ def test_joints_no_warm_starting_and_62(oracles):
     run_parity(oracles, scenes, 300, 6, 2, check_every=3)
 
 
+def test_binned_and_lane_mapped_narrow_phase_agree():
+    # k_collide's type-binned evaluation (worlds that mix shape types) against the lane-per-world evaluation
+    scenes = [S.mixed(s) for s in range(20)] + [S.sensors(s) for s in range(8)] + [S.vehicles(s) for s in range(6)] + \
+             [S.pyramid(6, jitter_seed=s) for s in range(6)]
+    a = WorldBatch(scenes, event_mask=EVENT_ALL, binned_collide=True)
+    b = WorldBatch(scenes, event_mask=EVENT_ALL, binned_collide=False)
+    for step in range(200):
+        a.step(1.0 / 60.0, 8, 3)
+        b.step(1.0 / 60.0, 8, 3)
+        if step % 10 == 9:
+            for fid in (B.F_BODY_XF, B.F_BODY_VEL, B.F_CONTACT_A, B.F_CONTACT_K, B.F_CONTACT_P0, B.F_CONTACT_P1, B.F_CONTACT_N,
+                        B.F_PROXY_FAT, B.F_EVENT_COUNT):
+                assert (a.field(fid).view(np.uint32) == b.field(fid).view(np.uint32)).all(), f"field {fid} step {step}"
+    assert (a.status() == 0).all() and (b.status() == 0).all()
+    a.close()
+    b.close()
+
+
 def test_replicated_worlds_identical(oracles):
     sc = S.pyramid(10, flags=NOCCD)
     batch = WorldBatch(sc, replicate=70)
