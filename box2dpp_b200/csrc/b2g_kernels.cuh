@@ -535,11 +535,12 @@ __host__ __device__ inline size_t IslandSmemPerWorld(int NB, int NC, int NJ) {
     return (size_t)NC * 9 + (size_t)NB * 5 + (NJ > 0 ? (size_t)((NJ + 1) & ~1) * 9 + (size_t)NB * 2 : 0);
 }
 
-__global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
+// The grid is persistent (a few CTAs per SM, each walking groups of L worlds): in the steady state almost every
+// group's islands are still valid, and a CTA that only reads L dirty flags must not cost a launch slot with
+// tens of KB of shared memory.
+__global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L, int numGroups) {
     extern __shared__ __align__(16) unsigned char ismem[];
     __shared__ int sDirty[kTile];
-    const int g = A.tile0 * (kTile / L) + blockIdx.x;  // group of L worlds (L divides 32)
-    const int w0 = g * L;                // first world of the group
     const int t = threadIdx.x;
     const int NB = A.NB, NC = A.NC;
     // shared arrays, element (index, l) at [index * L + l]
@@ -558,6 +559,9 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
     unsigned char* sJF = sBF + (size_t)NB * L;                         // [NJe][L]: joint already in an island
     (void)NJ;
 
+    for (int gi = blockIdx.x; gi < numGroups; gi += gridDim.x) {
+    const int g = A.tile0 * (kTile / L) + gi;  // group of L worlds (L divides 32)
+    const int w0 = g * L;                      // first world of the group
     if (t < L) {
         const int w = w0 + t;
         int d = 0;
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
         sDirty[t] = d;
     }
     const int anyDirty = __syncthreads_or(t < L ? sDirty[t] : 0);
-    if (!anyDirty) return;
+    if (!anyDirty) continue;
 
     // ---- load the contact graph and the body flags of the dirty worlds ----
     const int l = t % L;                 // world within the group
@@ -717,6 +721,8 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L) {
             s.w = 0.0f;  // m_sleepTime
             bodySweep[b] = s;
         }
+    }
+    __syncthreads();  // the shared arrays are reused by the next group
     }
 }
 

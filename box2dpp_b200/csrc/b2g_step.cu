@@ -347,6 +347,7 @@ struct b2gpu_batch {
     size_t solveSmem = 0;
     int islandLanes = 32;          // worlds per CTA of k_islands
     size_t islandSmem = 0;
+    int islandGrid = 148;          // CTAs of k_islands' persistent grid
     int64_t launches = 0;
     size_t arenaBytes = 0;
     // graph of one step, keyed by its parameters
@@ -535,6 +536,14 @@ int configureKernels(b2gpu_batch* b) {
                     desc->maxBodies, desc->maxContacts);
     b->islandLanes = L;
     b->islandSmem = perWorld * L;
+    {  // persistent grid: as many CTAs as are resident at once
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, desc->device);
+        int perSm = (int)((size_t)(maxSmem + 1024) / (b->islandSmem + 1024));
+        if (perSm < 1) perSm = 1;
+        if (perSm > 8) perSm = 8;
+        b->islandGrid = sms * perSm;
+    }
     CUDA_TRY(cudaFuncSetAttribute(k_islands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->islandSmem));
     return B2GPU_OK;
 }
@@ -566,7 +575,9 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
         k_collide<<<tiles, kCollideWarps * 32, 0, st>>>(A);
         mark();
         if (dt > 0.0f) {
-            k_islands<<<(unsigned)((tileCount * kTile + b->islandLanes - 1) / b->islandLanes), kIslandThreads, b->islandSmem, st>>>(A, b->islandLanes);
+            const int islandGroups = (tileCount * kTile + b->islandLanes - 1) / b->islandLanes;
+            k_islands<<<(unsigned)(islandGroups < b->islandGrid ? islandGroups : b->islandGrid), kIslandThreads, b->islandSmem, st>>>(
+                A, b->islandLanes, islandGroups);
             mark();
             if (b->tileSolver) {
                 k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);

@@ -38,6 +38,18 @@ def test_scene_header_matches_ctypes_mirror():
     assert d.maxBodies >= 7 and d.maxFixtures >= 7 and d.maxProxies >= 7 and d.maxContacts > 0 and d.maxShapeWords > 0
 
 
+def test_joint_defs_reach_the_host_layer():
+    """b2g_joint_def / the joint fields of b2g_scene as ctypes sees them == as the C side reads them."""
+    sc = S.jointed(1)
+    d = B.BatchDesc()
+    assert B.lib().b2gpu_scene_capacities(C.byref(sc.c_scene()), 1, C.byref(d)) == 0
+    assert d.maxJoints == len(sc.joints) == 22 and d.maxBodies == len(sc.bodies)
+    assert d.reserved & 4  # circles + boxes + an edge: the type-binned narrow phase is selected
+    d2 = B.BatchDesc()
+    assert B.lib().b2gpu_scene_capacities(C.byref(S.pyramid(3).c_scene()), 1, C.byref(d2)) == 0
+    assert d2.maxJoints == 0 and (d2.reserved & 4) == 0
+
+
 def _has_gpu():
     try:
         import torch
