@@ -72,6 +72,10 @@ RAY_HIT_DTYPE = np.dtype([("fixture", "<i4"), ("child", "<i4"), ("fraction", "<f
                           ("normal", "<f4", 2)])                                                      # b2gpu_ray_hit
 
 
+EVENT_DTYPE = np.dtype([("type", "<i4"), ("fixtureA", "<i4"), ("childA", "<i4"), ("fixtureB", "<i4"), ("childB", "<i4"),
+                        ("count", "<i4"), ("normalImpulses", "<f4", 2), ("tangentImpulses", "<f4", 2)])  # b2gpu_event
+
+
 def lib():
     """Load libb2gpu.so.  Raises (never falls back) when the CUDA extension has not been built."""
     global _lib
@@ -95,6 +99,7 @@ def lib():
         L.b2gpu_batch_read_body_state.argtypes = [vp, vp]
         L.b2gpu_batch_query_aabb.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
         L.b2gpu_batch_raycast_closest.argtypes = [vp, vp, C.c_int64, vp]
+        L.b2gpu_batch_read_events.argtypes = [vp, vp, vp, C.c_int64]
         L.b2gpu_batch_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_steps.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_kernels.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
@@ -324,6 +329,16 @@ class WorldBatch:
         ints[:, 3], ints[:, 4] = A[:, 2] & 0xFFFF, (A[:, 2] >> 16) & 0xFFFF
         ints[:, 5] = A[:, 3]
         return ints, B.copy()
+
+    def read_events(self):
+        """b2gpu_batch_read_events -> (offsets [W + 1] int64, events EVENT_DTYPE[offsets[-1]]) of the last step."""
+        offsets = np.zeros(self.num_worlds + 1, np.int64)
+        _check(lib().b2gpu_batch_read_events(self.h, offsets.ctypes.data_as(C.c_void_p), None, 0))
+        events = np.zeros(int(offsets[-1]), EVENT_DTYPE)
+        if events.shape[0]:
+            _check(lib().b2gpu_batch_read_events(self.h, offsets.ctypes.data_as(C.c_void_p), events.ctypes.data_as(C.c_void_p),
+                                                 events.shape[0]))
+        return offsets, events
 
     def status(self):
         return self.field(F_STATUS)[:, 0, 0]

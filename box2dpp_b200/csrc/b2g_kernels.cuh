@@ -337,11 +337,16 @@ __device__ __forceinline__ int CollideClass(const int4 a) {
 #ifndef B2G_COLLIDE_MIN_BLOCKS
 #define B2G_COLLIDE_MIN_BLOCKS 4  // 64 registers, 4 CTAs per SM: measured best of 2..6 (0.97 -> 0.83 ms at 16,384 worlds)
 #endif
+template <bool kResShared>
 __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_collide(Arena A) {
     __shared__ int sSummary[kTile];
-    // [NC][lane] result byte of phase 1.  In global memory (L2-resident between the phases), not shared memory, so that
-    // the kernel's CTAs fit beside the resident CTAs of another world group's sequential kernels (b2g_step.cu: groups)
-    unsigned char* sRes = A.collideRes + (size_t)(A.tile0 + blockIdx.x) * A.NC * kTile;
+    // [NC][lane] result byte of phase 1: in shared memory when the batch steps as one group; in global memory
+    // (L2-resident between the phases) when world groups run concurrently, so that this kernel's CTAs fit beside the
+    // resident CTAs of another group's sequential kernels (b2g_step.cu: groups)
+    extern __shared__ unsigned char sResShared[];
+    unsigned char* sRes;
+    if (kResShared) sRes = sResShared;
+    else sRes = A.collideRes + (size_t)(A.tile0 + blockIdx.x) * A.NC * kTile;
     const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     if (warp == 0) {
@@ -356,6 +361,7 @@ __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_
     __syncthreads();
 
     int summary = 0;  // 1: the list-order pass is needed, 2: island topology changed
+#ifndef B2G_NO_BINNED
     if (A.collideItems != nullptr) {
         // ---- type-binned evaluation (batches whose worlds mix shape types) ----
         // With lane = world, contact k of 32 different worlds is 32 different shape pairs and the warp runs up to
@@ -415,6 +421,7 @@ __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_
             sRes[k * kTile + ln] = (unsigned char)res;
         }
     } else
+#endif
     for (int k = warp; k < nMax; k += kCollideWarps) {
         if (k >= n) continue;
         const int bodies = cA[k].y;

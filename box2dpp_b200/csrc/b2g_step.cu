@@ -39,6 +39,15 @@ int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(B2GPU_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        return e == cudaSuccess ? B2GPU_OK : fail(B2GPU_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+};
+
 struct Field {
     void** dev;      // address of the arena pointer
     int capacity;    // items per world
@@ -117,6 +126,30 @@ __global__ void k_read_body_state(Arena A, float4* __restrict__ out) {
     float4* o = out + ((size_t)w * A.NB + body) * 2;
     o[0] = make_float4(xf.x, xf.y, sw.z, (f & kBodyAwake) ? 1.0f : 0.0f);
     o[1] = make_float4(v.x, v.y, v.z, sw.w);
+}
+
+// Compaction of the per-world event arenas: world w's events go to out[offsets[w] ...] (b2gpu_batch_read_events).
+__global__ void k_gather_events(Arena A, const long long* __restrict__ offsets, b2gpu_event* __restrict__ out, long long capacity) {
+    const int w = blockIdx.x;  // one CTA per world, threads stride over its events
+    if (w >= A.numWorlds) return;
+    const int tile = w >> 5, lane = w & 31;
+    const long long o = offsets[w];
+    const int n = (int)(offsets[w + 1] - o);
+    Col<int4> ea = col(A.eventA, tile, A.NE, lane);
+    Col<float4> eb = col(A.eventB, tile, A.NE, lane);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (o + i >= capacity) break;
+        const int4 a = ea[i];
+        const float4 f = eb[i];
+        b2gpu_event e;
+        e.type = a.x;
+        e.fixtureA = a.y & 0xffff; e.childA = (a.y >> 16) & 0xffff;
+        e.fixtureB = a.z & 0xffff; e.childB = (a.z >> 16) & 0xffff;
+        e.count = a.w;
+        e.normalImpulses[0] = f.x; e.normalImpulses[1] = f.y;
+        e.tangentImpulses[0] = f.z; e.tangentImpulses[1] = f.w;
+        out[o + i] = e;
+    }
 }
 
 // Between-step body edits (include/b2gpu.h B2GPU_CMD_*).  The command array is grouped by world; the thread that
@@ -348,6 +381,7 @@ struct b2gpu_batch {
     int islandLanes = 32;          // worlds per CTA of k_islands
     size_t islandSmem = 0;
     int islandGrid = 148;          // CTAs of k_islands' persistent grid
+    bool collideSmemOk = false;    // k_collide's result bytes fit in shared memory
     int64_t launches = 0;
     size_t arenaBytes = 0;
     // graph of one step, keyed by its parameters
@@ -523,6 +557,9 @@ int configureKernels(b2gpu_batch* b) {
     b->solveSmem = SolveSmemBytes(desc->maxBodies);
     // joints are solved by the generic kernel only (b2g_joints.cuh)
     b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0 && desc->maxJoints <= 0;
+    b->collideSmemOk = (size_t)desc->maxContacts * kTile <= (size_t)maxSmem - 2048;
+    if (b->collideSmemOk)
+        CUDA_TRY(cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, desc->maxContacts * kTile));
     if (b->tileSolver) {
         CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
         CUDA_TRY(cudaFuncSetAttribute(k_solve_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
@@ -572,11 +609,16 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
     auto mark = [&]() { if (marks) cudaEventRecord(marks[(*m)++], st); };
     if (part == 0) {
         mark();
-        k_collide<<<tiles, kCollideWarps * 32, 0, st>>>(A);
+        // result bytes in shared memory when the batch steps as one group, in global memory when groups co-reside
+        if (b->groups <= 1 && b->collideSmemOk) k_collide<true><<<tiles, kCollideWarps * 32, (size_t)A.NC * kTile, st>>>(A);
+        else k_collide<false><<<tiles, kCollideWarps * 32, 0, st>>>(A);
         mark();
         if (dt > 0.0f) {
             const int islandGroups = (tileCount * kTile + b->islandLanes - 1) / b->islandLanes;
-            k_islands<<<(unsigned)(islandGroups < b->islandGrid ? islandGroups : b->islandGrid), kIslandThreads, b->islandSmem, st>>>(
+            // one CTA per group: a persistent grid (CTAs walking several groups) was measured 2x slower, the hardware
+            // scheduler overlaps one CTA's graph load with another's DFS better than a loop with barriers does
+            const unsigned islandCtas = (unsigned)islandGroups;
+            k_islands<<<islandCtas, kIslandThreads, b->islandSmem, st>>>(
                 A, b->islandLanes, islandGroups);
             mark();
             if (b->tileSolver) {
@@ -1009,6 +1051,32 @@ int b2gpu_batch_read_body_state(b2gpu_batch* b, float* out) {
     return B2GPU_OK;
 }
 
+int b2gpu_batch_read_events(b2gpu_batch* b, int64_t* offsets, b2gpu_event* events, int64_t capacity) {
+    if (!b || !offsets || capacity < 0) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    const int W = b->desc.numWorlds;
+    std::vector<int32_t> counts((size_t)W);
+    int rc = transferField(b, B2GPU_F_EVENT_COUNT, counts.data(), 0, W, false);
+    if (rc != B2GPU_OK) return rc;
+    offsets[0] = 0;
+    for (int w = 0; w < W; ++w) {
+        const int n = counts[w] < b->A.NE ? counts[w] : b->A.NE;  // an overflowed arena holds its first NE events
+        offsets[w + 1] = offsets[w] + (n > 0 ? n : 0);
+    }
+    const int64_t total = offsets[W] < capacity ? offsets[W] : capacity;
+    if (!events || total <= 0) return B2GPU_OK;
+    DevBuf dOff, dEv;
+    if ((rc = dOff.alloc((size_t)(W + 1) * sizeof(int64_t))) != B2GPU_OK) return rc;
+    if ((rc = dEv.alloc((size_t)total * sizeof(b2gpu_event))) != B2GPU_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dOff.p, offsets, (size_t)(W + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    k_gather_events<<<(unsigned)W, 128, 0, b->stream>>>(b->A, (const long long*)dOff.p, (b2gpu_event*)dEv.p, (long long)total);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(events, dEv.p, (size_t)total * sizeof(b2gpu_event), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
 int b2gpu_batch_body_commands(b2gpu_batch* b, const b2gpu_body_command* commands, int64_t count) {
     if (!b || count < 0 || (count > 0 && !commands)) return fail(B2GPU_ERR_INVALID, "bad arguments");
     if (count == 0) return B2GPU_OK;
@@ -1046,14 +1114,6 @@ int b2gpu_batch_body_commands(b2gpu_batch* b, const b2gpu_body_command* commands
 
 // ---- stateless device entry points ---------------------------------------------------------------
 namespace {
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
-        return e == cudaSuccess ? B2GPU_OK : fail(B2GPU_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
-    }
-};
 int requireDevice(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

@@ -532,27 +532,26 @@ private:
         m_stateValid = true;
     }
     size_t Slot(const b2Body* b) const { return (size_t)b->m_world->m_index * m_maxBodies + b->m_index; }
-    void DispatchEvents() {
+    void DispatchEvents() {  // compacted readback: only the events that happened cross the bus
         const int32_t W = (int32_t)m_worlds.size();
-        std::vector<int32_t> counts(W), a((size_t)W * m_maxEventsBuilt * 4);
-        std::vector<float> b((size_t)W * m_maxEventsBuilt * 4);
-        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_EVENT_COUNT, counts.data(), 0, W));
-        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_EVENT_A, a.data(), 0, W));
-        Check(b2gpu_batch_download_field(m_handle, B2GPU_F_EVENT_B, b.data(), 0, W));
+        m_eventOffsets.resize((size_t)W + 1);
+        Check(b2gpu_batch_read_events(m_handle, m_eventOffsets.data(), nullptr, 0));
+        m_events.resize((size_t)m_eventOffsets[W]);
+        if (m_events.empty()) return;
+        Check(b2gpu_batch_read_events(m_handle, m_eventOffsets.data(), m_events.data(), (int64_t)m_events.size()));
         for (int32_t w = 0; w < W; ++w) {
             b2World& world = *m_worlds[w];
-            const int32_t n = counts[w] < m_maxEventsBuilt ? counts[w] : m_maxEventsBuilt;
-            for (int32_t e = 0; e < n; ++e) {
-                const int32_t* ia = &a[((size_t)w * m_maxEventsBuilt + e) * 4];
-                const float* fb = &b[((size_t)w * m_maxEventsBuilt + e) * 4];
-                b2ContactEvent ev{&world, world.m_fixtures[ia[1] & 0xffff].get(), world.m_fixtures[ia[2] & 0xffff].get(),
-                                  (ia[1] >> 16) & 0xffff, (ia[2] >> 16) & 0xffff, ia[3]};
-                switch (ia[0]) {
+            for (int64_t i = m_eventOffsets[w]; i < m_eventOffsets[w + 1]; ++i) {
+                const b2gpu_event& e = m_events[(size_t)i];
+                b2ContactEvent ev{&world, world.m_fixtures[e.fixtureA].get(), world.m_fixtures[e.fixtureB].get(), e.childA, e.childB,
+                                  e.count};
+                switch (e.type) {
                     case B2GPU_EVENT_BEGIN: m_listener->BeginContact(ev); break;
                     case B2GPU_EVENT_END: m_listener->EndContact(ev); break;
                     case B2GPU_EVENT_PRESOLVE: m_listener->PreSolve(ev); break;
                     default: {
-                        b2ContactImpulse imp{{fb[0], fb[1]}, {fb[2], fb[3]}, ia[3]};
+                        b2ContactImpulse imp{{e.normalImpulses[0], e.normalImpulses[1]}, {e.tangentImpulses[0], e.tangentImpulses[1]},
+                                             e.count};
                         m_listener->PostSolve(ev, imp);
                     }
                 }
@@ -568,6 +567,8 @@ private:
     bool m_stateValid = false;
     std::vector<float> m_xf, m_sweep, m_vel;
     std::vector<b2gpu_body_command> m_commands;
+    std::vector<int64_t> m_eventOffsets;
+    std::vector<b2gpu_event> m_events;
     std::vector<int32_t> m_bodyFlags;
 };
 

@@ -192,6 +192,23 @@ int b2gpu_batch_body_commands(b2gpu_batch* batch, const b2gpu_body_command* comm
  * Box2D/Dynamics/b2Body.h:500-560 for an RL / game-server caller.  Synchronises. */
 int b2gpu_batch_read_body_state(b2gpu_batch* batch, float* out);
 
+/* Listener events of the last step, compacted: the b2ContactListener callbacks of every world in the reference's
+ * per-world order (Begin / End / PreSolve from b2Contact::Update and b2ContactManager::Destroy, PostSolve from
+ * b2Island::Report, then the TOI sub-steps' events), worlds back to back.
+ *   offsets[W + 1]  offsets[w] .. offsets[w + 1] = the events of world w in `events`
+ *   events[i]       one b2gpu_event
+ * Call with events == NULL (or capacity 0) to get the offsets only (offsets[W] = total).  Events beyond `capacity`
+ * are dropped from the copy (the offsets still describe the full list); a world whose per-step event arena overflowed
+ * has B2GPU_STATUS_EVENT_OVERFLOW set and holds its first maxEvents events.  Synchronises. */
+typedef struct b2gpu_event {
+    int32_t type;              /* B2GPU_EVENT_* */
+    int32_t fixtureA, childA;  /* b2Contact::GetFixtureA() (creation index) / GetChildIndexA() */
+    int32_t fixtureB, childB;
+    int32_t count;             /* Begin / End / PreSolve: manifold.pointCount; PostSolve: b2ContactImpulse::count */
+    float normalImpulses[2], tangentImpulses[2]; /* PostSolve only */
+} b2gpu_event;
+int b2gpu_batch_read_events(b2gpu_batch* batch, int64_t* offsets, b2gpu_event* events, int64_t capacity);
+
 /* ---- batched read-only queries --------------------------------------------------------
  * b2World::QueryAABB / b2World::RayCast (Box2D/Dynamics/b2World.cpp:965-1020; b2DynamicTree::Query / RayCast,
  * Box2D/Collision/b2DynamicTree.h:218-303) for many (world, query) pairs in one call.  Host buffers in and out;

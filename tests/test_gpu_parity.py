@@ -183,6 +183,29 @@ def test_binned_and_lane_mapped_narrow_phase_agree():
     b.close()
 
 
+def test_compacted_event_readback():
+    # b2gpu_batch_read_events == the per-world event arenas, world by world, in order
+    scenes = [S.pyramid(4 + w % 3, jitter_seed=w) for w in range(40)] + [S.sensors(1), S.hello_world()]
+    batch = WorldBatch(scenes, event_mask=EVENT_ALL)
+    seen = 0
+    for step in range(60):
+        batch.step(1.0 / 60.0, 8, 3)
+        if step % 7 == 0 or step == 59:
+            offsets, ev = batch.read_events()
+            assert offsets[0] == 0 and offsets[-1] == ev.shape[0]
+            for w in range(len(scenes)):
+                ints, fl = batch.events(w)
+                e = ev[offsets[w]:offsets[w + 1]]
+                assert e.shape[0] == ints.shape[0]
+                got = np.stack([e["type"], e["fixtureA"], e["childA"], e["fixtureB"], e["childB"], e["count"]], 1)
+                assert (got == ints).all()
+                want = np.concatenate([e["normalImpulses"], e["tangentImpulses"]], 1)
+                assert (want.view(np.uint32) == fl.view(np.uint32)).all()
+            seen += ev.shape[0]
+    assert seen > 1000
+    batch.close()
+
+
 def test_replicated_worlds_identical(oracles):
     sc = S.pyramid(10, flags=NOCCD)
     batch = WorldBatch(sc, replicate=70)
