@@ -100,6 +100,10 @@ def lib():
         L.b2gpu_batch_query_aabb.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
         L.b2gpu_batch_raycast_closest.argtypes = [vp, vp, C.c_int64, vp]
         L.b2gpu_batch_read_events.argtypes = [vp, vp, vp, C.c_int64]
+        L.b2gpu_batch_snapshot_size.argtypes = [vp]
+        L.b2gpu_batch_snapshot_size.restype = C.c_int64
+        L.b2gpu_batch_snapshot_save.argtypes = [vp, vp, C.c_int64]
+        L.b2gpu_batch_snapshot_load.argtypes = [vp, vp, C.c_int64]
         L.b2gpu_batch_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_steps.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_kernels.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
@@ -339,6 +343,16 @@ class WorldBatch:
             _check(lib().b2gpu_batch_read_events(self.h, offsets.ctypes.data_as(C.c_void_p), events.ctypes.data_as(C.c_void_p),
                                                  events.shape[0]))
         return offsets, events
+
+    def snapshot(self) -> np.ndarray:
+        """b2gpu_batch_snapshot_save: every persistent field of every world as one blob."""
+        blob = np.zeros(int(lib().b2gpu_batch_snapshot_size(self.h)), np.uint8)
+        _check(lib().b2gpu_batch_snapshot_save(self.h, blob.ctypes.data_as(C.c_void_p), blob.shape[0]))
+        return blob
+
+    def restore(self, blob: np.ndarray):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        _check(lib().b2gpu_batch_snapshot_load(self.h, blob.ctypes.data_as(C.c_void_p), blob.shape[0]))
 
     def status(self):
         return self.field(F_STATUS)[:, 0, 0]

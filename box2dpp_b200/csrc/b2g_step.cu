@@ -374,6 +374,7 @@ struct b2gpu_batch {
     std::vector<Field> fields;
     std::vector<void*> allocations;
     bool needInitialPairs = true;  // b2World::e_newFixture
+    bool needProxyIndex = true;    // the body -> proxies index has to be (re)built before the next step
     bool anyContinuous = false;    // some world has B2G_WORLD_CONTINUOUS: the step ends with k_toi
     int blockSize = 32;
     bool tileSolver = false;       // b2g_solve.cuh path: the tile's body table fits in shared memory
@@ -670,9 +671,13 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
         const int threads = b->blockSize;
         const unsigned blocks = (unsigned)(((size_t)b->A.numTiles * kTile + threads - 1) / threads);
         k_find_new_contacts<<<blocks, threads, 0, st>>>(b->A);
-        k_index_proxies<<<(unsigned)((b->A.numTiles * kTile + 127) / 128), 128, 0, st>>>(b->A);
         b->needInitialPairs = false;
-        b->launches += 2;
+        b->launches++;
+    }
+    if (b->needProxyIndex) {  // body -> proxies index (derived state: after the worlds were built or restored)
+        k_index_proxies<<<(unsigned)((b->A.numTiles * kTile + 127) / 128), 128, 0, st>>>(b->A);
+        b->needProxyIndex = false;
+        b->launches++;
     }
     const int perStep = dt > 0.0f ? stepKernelCount(b) : 1;
     const int nkTrace = stepKernelCount(b) + 1;  // traceGroups: marks is [group][step][nk + 1]
@@ -814,6 +819,7 @@ int b2gpu_batch_upload_field(b2gpu_batch* b, int32_t field, const void* host, in
     int rc = transferField(b, field, const_cast<void*>(host), firstWorld, worldCount, true);
     // a freshly uploaded move buffer == b2World::e_newFixture: the next Step starts with FindNewContacts
     if (rc == B2GPU_OK && field == B2GPU_F_PROXY_MOVED) b->needInitialPairs = true;
+    if (rc == B2GPU_OK && (field == B2GPU_F_PROXY_INFO || field == B2GPU_F_FIXTURE_INFO)) b->needProxyIndex = true;
     if (rc == B2GPU_OK && field == B2GPU_F_WORLD_FLAGS && !b->anyContinuous) {
         const int32_t* flags = static_cast<const int32_t*>(host);
         for (int32_t i = 0; i < worldCount; ++i)
@@ -865,7 +871,7 @@ int b2gpu_batch_step_n(b2gpu_batch* b, float dt, int32_t velIters, int32_t posIt
     if (steps == 0) return B2GPU_OK;
     int done = 0;
     CUDA_TRY(cudaEventRecord(b->evStart, b->stream));
-    if (b->needInitialPairs) {  // the first step also runs FindNewContacts: keep it out of the graph
+    if (b->needInitialPairs || b->needProxyIndex) {  // the first step also runs FindNewContacts: keep it out of the graph
         int rc = enqueueStep(b, dt, velIters, posIters, nullptr);
         if (rc != B2GPU_OK) return rc;
         done = 1;
@@ -1047,6 +1053,81 @@ int b2gpu_batch_read_body_state(b2gpu_batch* b, float* out) {
     b->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, b->ioDev, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+// ---- snapshot / restore ------------------------------------------------------------------------------------------
+namespace {
+// persistent state: everything except per-step temporaries (events, island arrays)
+const int kSnapshotFields[] = {
+    B2GPU_F_GRAVITY, B2GPU_F_WORLD_FLAGS, B2GPU_F_INV_DT0, B2GPU_F_BODY_COUNT, B2GPU_F_PROXY_COUNT, B2GPU_F_CONTACT_COUNT,
+    B2GPU_F_STATUS, B2GPU_F_STEP_COUNT, B2GPU_F_BODY_XF, B2GPU_F_BODY_SWEEP, B2GPU_F_BODY_SWEEP0, B2GPU_F_BODY_VEL,
+    B2GPU_F_BODY_FORCE, B2GPU_F_BODY_MASS, B2GPU_F_BODY_DAMP, B2GPU_F_BODY_FLAGS, B2GPU_F_FIXTURE_INFO, B2GPU_F_FIXTURE_SHAPE,
+    B2GPU_F_FIXTURE_MAT, B2GPU_F_FIXTURE_FILTER, B2GPU_F_PROXY_FAT, B2GPU_F_PROXY_INFO, B2GPU_F_PROXY_MOVED, B2GPU_F_SHAPE_WORDS,
+    B2GPU_F_CHAIN_VERTS, B2GPU_F_CONTACT_A, B2GPU_F_CONTACT_K, B2GPU_F_CONTACT_S, B2GPU_F_CONTACT_P0, B2GPU_F_CONTACT_P1,
+    B2GPU_F_CONTACT_N, B2GPU_F_JOINT_COUNT, B2GPU_F_JOINT_I, B2GPU_F_JOINT_F0, B2GPU_F_JOINT_F1, B2GPU_F_JOINT_F2,
+    B2GPU_F_JOINT_IMPULSE,
+};
+struct SnapshotHeader {
+    uint32_t magic, version;
+    int32_t numWorlds, NB, NF, NP, NC, NS, NV, NJ;
+    int32_t needInitialPairs, anyContinuous;
+};
+constexpr uint32_t kSnapshotMagic = 0x62326773u;  // "b2gs"
+size_t snapshotFieldBytes(const b2gpu_batch* b, int id) {
+    return (size_t)b->desc.numWorlds * b->fields[id].capacity * b->fields[id].components * 4;
+}
+}  // namespace
+
+int64_t b2gpu_batch_snapshot_size(b2gpu_batch* b) {
+    if (!b) return 0;
+    size_t n = sizeof(SnapshotHeader);
+    for (int id : kSnapshotFields) n += snapshotFieldBytes(b, id);
+    return (int64_t)n;
+}
+
+int b2gpu_batch_snapshot_save(b2gpu_batch* b, void* blob, int64_t size) {
+    if (!b || !blob || size < b2gpu_batch_snapshot_size(b)) return fail(B2GPU_ERR_INVALID, "snapshot buffer too small");
+    SnapshotHeader h = {kSnapshotMagic, 1, b->desc.numWorlds, b->A.NB, b->A.NF, b->A.NP, b->A.NC, b->A.NS, b->A.NV, b->A.NJ,
+                        b->needInitialPairs ? 1 : 0, b->anyContinuous ? 1 : 0};
+    unsigned char* p = static_cast<unsigned char*>(blob);
+    memcpy(p, &h, sizeof(h));
+    p += sizeof(h);
+    for (int id : kSnapshotFields) {
+        int rc = transferField(b, id, p, 0, b->desc.numWorlds, false);
+        if (rc != B2GPU_OK) return rc;
+        p += snapshotFieldBytes(b, id);
+    }
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_snapshot_load(b2gpu_batch* b, const void* blob, int64_t size) {
+    if (!b || !blob || size < b2gpu_batch_snapshot_size(b)) return fail(B2GPU_ERR_INVALID, "snapshot blob too small");
+    SnapshotHeader h;
+    const unsigned char* p = static_cast<const unsigned char*>(blob);
+    memcpy(&h, p, sizeof(h));
+    if (h.magic != kSnapshotMagic || h.version != 1) return fail(B2GPU_ERR_INVALID, "not a b2gpu snapshot");
+    if (h.numWorlds != b->desc.numWorlds || h.NB != b->A.NB || h.NF != b->A.NF || h.NP != b->A.NP || h.NC != b->A.NC ||
+        h.NS != b->A.NS || h.NV != b->A.NV || h.NJ != b->A.NJ)
+        return fail(B2GPU_ERR_INVALID, "snapshot was taken from a batch with other capacities");
+    p += sizeof(h);
+    for (int id : kSnapshotFields) {
+        int rc = transferField(b, id, const_cast<unsigned char*>(p), 0, b->desc.numWorlds, true);
+        if (rc != B2GPU_OK) return rc;
+        p += snapshotFieldBytes(b, id);
+    }
+    // the islands are rebuilt (they are a function of the restored state), buffered moves are looked at by the next
+    // step's pair search, and e_newFixture / the continuous-physics switch come back as they were
+    CUDA_TRY(cudaMemsetAsync(b->A.topoDirty, 1, (size_t)b->A.numTiles * kTile * sizeof(int), b->stream));
+    CUDA_TRY(cudaMemsetAsync(b->A.pendingMoves, 1, (size_t)b->A.numTiles * kTile * sizeof(int), b->stream));
+    b->needInitialPairs = h.needInitialPairs != 0;
+    if ((h.anyContinuous != 0) != b->anyContinuous) {
+        b->anyContinuous = h.anyContinuous != 0;
+        if (b->graphExec) { cudaGraphExecDestroy(b->graphExec); b->graphExec = nullptr; }
+        if (b->graphExecChunk) { cudaGraphExecDestroy(b->graphExecChunk); b->graphExecChunk = nullptr; }
+    }
+    b->needProxyIndex = true;
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     return B2GPU_OK;
 }

@@ -209,6 +209,16 @@ typedef struct b2gpu_event {
 } b2gpu_event;
 int b2gpu_batch_read_events(b2gpu_batch* batch, int64_t* offsets, b2gpu_event* events, int64_t capacity);
 
+/* ---- snapshot / restore (the arena snapshot is the checkpoint) ---------------------------------------
+ * Every persistent field of every world (bodies, fixtures, proxies with their fat AABBs and move flags, shapes, contacts
+ * with manifolds and accumulated impulses, joints with their impulses and limit states, world scalars) as one host blob;
+ * per-step temporaries (constraint records, islands, events) are not part of it.  A batch restored from a snapshot
+ * continues bit-identically to the batch the snapshot was taken from.  The blob is only valid for a batch created with
+ * the same b2gpu_batch_desc capacities and world count.  Both calls synchronise. */
+int64_t b2gpu_batch_snapshot_size(b2gpu_batch* batch);
+int b2gpu_batch_snapshot_save(b2gpu_batch* batch, void* blob, int64_t size);
+int b2gpu_batch_snapshot_load(b2gpu_batch* batch, const void* blob, int64_t size);
+
 /* ---- batched read-only queries --------------------------------------------------------
  * b2World::QueryAABB / b2World::RayCast (Box2D/Dynamics/b2World.cpp:965-1020; b2DynamicTree::Query / RayCast,
  * Box2D/Collision/b2DynamicTree.h:218-303) for many (world, query) pairs in one call.  Host buffers in and out;

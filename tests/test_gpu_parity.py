@@ -206,6 +206,60 @@ def test_compacted_event_readback():
     batch.close()
 
 
+def test_world_groups_do_not_change_results(monkeypatch):
+    # the step chain enqueued per group of tiles on separate streams (incl. the 8-step graph chunks of step_n) against
+    # a single group on one stream: every field identical
+    scenes = [S.pyramid(5 + w % 3, jitter_seed=w) for w in range(150)] + [S.mixed(w) for w in range(10)]  # 5 tiles
+    batches = []
+    for groups in ("1", "4"):
+        monkeypatch.setenv("B2GPU_GROUPS", groups)
+        batches.append(WorldBatch(scenes, event_mask=EVENT_ALL))
+    a, b = batches
+    for n in (1, 19, 8, 3):
+        a.step_n(1.0 / 60.0, 8, 3, n)
+        b.step_n(1.0 / 60.0, 8, 3, n)
+        a.step(1.0 / 60.0, 8, 3)
+        b.step(1.0 / 60.0, 8, 3)
+        for fid in (B.F_BODY_XF, B.F_BODY_SWEEP, B.F_BODY_VEL, B.F_BODY_FLAGS, B.F_CONTACT_COUNT, B.F_CONTACT_A, B.F_CONTACT_P0,
+                    B.F_PROXY_FAT, B.F_EVENT_COUNT, B.F_EVENT_A, B.F_STEP_COUNT):
+            assert (a.field(fid).view(np.uint32) == b.field(fid).view(np.uint32)).all(), f"field {fid} after {n}"
+    assert (a.status() == 0).all() and (b.status() == 0).all()
+    a.close()
+    b.close()
+
+
+def test_snapshot_restore_continues_bit_identically():
+    # b2gpu_batch_snapshot_save / load: restore into the same batch after it moved on, and into a fresh batch built from
+    # the same scenes; both continue exactly like the original (contacts, impulses, joints, sleep state, TOI on)
+    scenes = [S.pyramid(5, jitter_seed=1), S.mixed(2), S.jointed(1), S.vehicles(2), S.sensors(1), S.bullets(2)] * 6
+    a = WorldBatch(scenes, event_mask=EVENT_ALL)
+    a.step_n(1.0 / 60.0, 8, 3, 70)
+    cmds = np.zeros(2, B.BODY_COMMAND_DTYPE)
+    cmds[0] = (0, 3, B.CMD_SET_TRANSFORM, 1, (0.5, 6.0), (0.3, 0.0))  # a buffered move is part of the state
+    cmds[1] = (2, 12, B.CMD_APPLY_LINEAR_IMPULSE, 1, (2.0, 5.0), (0.0, 3.0))
+    a.body_commands(cmds)
+    blob = a.snapshot()
+    fresh = WorldBatch(scenes, event_mask=EVENT_ALL)
+    fresh.restore(blob)
+    fields = (B.F_BODY_XF, B.F_BODY_SWEEP, B.F_BODY_VEL, B.F_BODY_FLAGS, B.F_CONTACT_COUNT, B.F_CONTACT_A, B.F_CONTACT_K,
+              B.F_CONTACT_P0, B.F_CONTACT_P1, B.F_PROXY_FAT, B.F_JOINT_IMPULSE, B.F_JOINT_I, B.F_EVENT_COUNT, B.F_STEP_COUNT)
+    ref_states = []
+    for _ in range(4):
+        a.step_n(1.0 / 60.0, 8, 3, 15)
+        ref_states.append([a.field(f).copy() for f in fields])
+    a.restore(blob)  # rewind
+    for k in range(4):
+        a.step_n(1.0 / 60.0, 8, 3, 15)
+        fresh.step_n(1.0 / 60.0, 8, 3, 15)
+        for f, want in zip(fields, ref_states[k]):
+            assert (a.field(f).view(np.uint32) == want.view(np.uint32)).all(), f"rewound batch, field {f}, block {k}"
+            assert (fresh.field(f).view(np.uint32) == want.view(np.uint32)).all(), f"fresh batch, field {f}, block {k}"
+    with pytest.raises(B.B2GpuError):
+        WorldBatch(scenes[:6]).restore(blob)
+    a.close()
+    fresh.close()
+
+
 def test_replicated_worlds_identical(oracles):
     sc = S.pyramid(10, flags=NOCCD)
     batch = WorldBatch(sc, replicate=70)
