@@ -63,7 +63,7 @@ _lib = None
 BODY_COMMAND_DTYPE = np.dtype([("world", "<i4"), ("body", "<i4"), ("op", "<i4"), ("wake", "<i4"),
                                ("v", "<f4", 2), ("p", "<f4", 2)])
 (CMD_APPLY_FORCE, CMD_APPLY_FORCE_TO_CENTER, CMD_APPLY_TORQUE, CMD_APPLY_LINEAR_IMPULSE, CMD_APPLY_ANGULAR_IMPULSE,
- CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE) = range(9)
+ CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE, CMD_DESTROY_BODY) = range(10)
 
 
 AABB_QUERY_DTYPE = np.dtype([("world", "<i4"), ("lower", "<f4", 2), ("upper", "<f4", 2)])       # b2gpu_aabb_query
@@ -289,6 +289,9 @@ class WorldBatch:
         with np.errstate(divide="ignore"):
             out[:, 11] = np.where(ms[:, 0] > 0, np.float32(1.0) / ms[:, 0], 0.0)
         out[:, 13:15] = ms[:, 2:4]
+        dead = (fl & (1 << 10)) != 0  # destroyed bodies: a row of zeros with the marker in the last column (oracle format)
+        out[dead] = 0.0
+        out[dead, 15] = 1.0
         return out
 
     def contacts(self, world):
@@ -321,7 +324,9 @@ class WorldBatch:
 
     def proxies(self, world):
         n = int(self.field(F_PROXY_COUNT, world, 1)[0, 0, 0])
-        return self.field(F_PROXY_FAT, world, 1)[0, :n]
+        fat = self.field(F_PROXY_FAT, world, 1)[0, :n].copy()
+        fat[fat[:, 0] > fat[:, 2]] = 0.0  # proxies of destroyed bodies carry an empty box: zeros in the oracle format
+        return fat
 
     def events(self, world):
         n = int(self.field(F_EVENT_COUNT, world, 1)[0, 0, 0])

@@ -168,7 +168,7 @@ __device__ __forceinline__ bool FatOverlap(float4 a, float4 b) {  // b2TestOverl
 // b2Body::SetAwake(true) — Box2D/Dynamics/b2Body.h:634-643
 __device__ __forceinline__ bool WakeBody(const Col<int>& bodyFlags, const Col<float4>& bodySweep, int b) {
     int f = bodyFlags[b];
-    if ((f & kBodyAwake) == 0) {
+    if ((f & (kBodyAwake | kBodyDestroyed)) == 0) {
         bodyFlags[b] = f | kBodyAwake;
         float4 s = bodySweep[b];
         s.w = 0.0f;  // m_sleepTime

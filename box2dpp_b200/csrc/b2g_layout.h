@@ -37,6 +37,7 @@ enum : int {
     kBodyActive = 1 << 7,
     kBodyToiIsland = 1 << 8,  // e_islandFlag as b2World::SolveTOI uses it (kBodyIsland keeps the discrete islands)
     kBodyToiMoved = 1 << 9,   // displaced by the current TOI sub-step (temporary)
+    kBodyDestroyed = 1 << 10, // b2World::DestroyBody was called: the slot is a tombstone (never awake, never active)
 };
 // contact flag bits (Box2D/Dynamics/Contacts/b2Contact.h:155-174)
 enum : int {

@@ -86,7 +86,7 @@ __global__ void k_apply_forces(Arena A, const float* __restrict__ forces) {
     float fx = f[0], fy = f[1], tq = f[2];
     if (fx == 0.0f && fy == 0.0f && tq == 0.0f) return;
     int flags = A.bodyFlags[idx];
-    if ((flags & kBodyTypeMask) != B2G_DYNAMIC_BODY) return;
+    if ((flags & kBodyTypeMask) != B2G_DYNAMIC_BODY || (flags & kBodyDestroyed)) return;
     if ((flags & kBodyAwake) == 0) {
         A.bodyFlags[idx] = flags | kBodyAwake;
         A.bodySweep[idx].w = 0.0f;
@@ -178,6 +178,10 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
         }
         const int b = c.body;
         int f = bodyFlags[b];
+        if (f & kBodyDestroyed) {  // the reference would be handed a dangling b2Body*
+            A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
+            continue;
+        }
         const int type = f & kBodyTypeMask;
         auto wake = [&]() {  // SetAwake(true)
             if (WakeBody(bodyFlags, bodySweep, b)) A.topoDirty[ws] = 1;
@@ -236,6 +240,93 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                 float4 v = bodyVel[b];
                 v.z = c.v[0];
                 bodyVel[b] = v;
+            } break;
+            case B2GPU_CMD_DESTROY_BODY: {  // b2World::DestroyBody — Dynamics/b2World.cpp:124-203
+                A.topoDirty[ws] = 1;
+                // 1. the attached joints, in the body's joint-list order (newest first): b2World::DestroyJoint wakes
+                //    both bodies (b2World.cpp:302-304); then a stable erase keeps m_jointList's order
+                if (A.hasJoints) {
+                    Col<int4> jI = col(A.jointI, tile, A.NJ, lane);
+                    Col<float4> jF0 = col(A.jointF0, tile, A.NJ, lane), jF1 = col(A.jointF1, tile, A.NJ, lane);
+                    Col<float4> jF2 = col(A.jointF2, tile, A.NJ, lane), jImp = col(A.jointImp, tile, A.NJ, lane);
+                    const int nj = A.jointCount[ws];
+                    bool any = false;
+                    for (int j = nj - 1; j >= 0; --j) {
+                        const int4 ji = jI[j];
+                        const int jA = ji.y & 0xffff, jB = (ji.y >> 16) & 0xffff;
+                        if (jA != b && jB != b) continue;
+                        WakeBody(bodyFlags, bodySweep, jA);
+                        WakeBody(bodyFlags, bodySweep, jB);
+                        any = true;
+                    }
+                    if (any) {
+                        int wpos = 0;
+                        for (int j = 0; j < nj; ++j) {
+                            const int4 ji = jI[j];
+                            if ((ji.y & 0xffff) == b || ((ji.y >> 16) & 0xffff) == b) continue;
+                            if (wpos != j) { jI[wpos] = ji; jF0[wpos] = jF0[j]; jF1[wpos] = jF1[j]; jF2[wpos] = jF2[j]; jImp[wpos] = jImp[j]; }
+                            ++wpos;
+                        }
+                        A.jointCount[ws] = wpos;
+                    }
+                }
+                // 2. the attached contacts, in the body's contact-list order (newest first):
+                //    b2ContactManager::Destroy (EndContact if touching) + b2Contact::Destroy (wake if it had points)
+                {
+                    Col<int4> cA = col(A.contactA, tile, A.NC, lane), cK = col(A.contactK, tile, A.NC, lane);
+                    Col<int2> cS = col(A.contactS, tile, A.NC, lane);
+                    Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane), cP1 = col(A.contactP1, tile, A.NC, lane);
+                    Col<float4> cN = col(A.contactN, tile, A.NC, lane);
+                    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+                    EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws],
+                                 A.NE, A.eventMask};
+                    const int nc = A.contactCount[ws];
+                    bool any = false;
+                    for (int k = nc - 1; k >= 0; --k) {
+                        const int4 a = cA[k];
+                        const int kA = a.y & 0xffff, kB = (a.y >> 16) & 0xffff;
+                        if (kA != b && kB != b) continue;
+                        any = true;
+                        const int pointCount = (a.w >> 8) & 0xff;
+                        if (a.z & kContactTouching) {
+                            const int pa = proxyInfo[a.x & 0xffff], pb = proxyInfo[(a.x >> 16) & 0xffff];
+                            ev.push(kEventEnd, pa & 0xffff, (pa >> 16) & 0xffff, pb & 0xffff, (pb >> 16) & 0xffff, pointCount,
+                                    make_float4(0, 0, 0, 0));
+                        }
+                        if (pointCount > 0 && (a.z & kContactSensor) == 0) {
+                            WakeBody(bodyFlags, bodySweep, kA);
+                            WakeBody(bodyFlags, bodySweep, kB);
+                        }
+                    }
+                    if (any) {
+                        int wpos = 0;
+                        for (int k = 0; k < nc; ++k) {
+                            const int4 a = cA[k];
+                            if ((a.y & 0xffff) == b || ((a.y >> 16) & 0xffff) == b) continue;
+                            if (wpos != k) { cA[wpos] = a; cK[wpos] = cK[k]; cS[wpos] = cS[k]; cP0[wpos] = cP0[k]; cP1[wpos] = cP1[k]; cN[wpos] = cN[k]; }
+                            ++wpos;
+                        }
+                        A.contactCount[ws] = wpos;
+                    }
+                }
+                // 3. the fixtures' proxies leave the broad phase (b2Fixture::DestroyProxies): an empty fat AABB never
+                //    overlaps anything, and the proxy leaves the move buffer (b2BroadPhase::UnBufferMove)
+                {
+                    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+                    Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+                    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+                    Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
+                    const int np = A.proxyCount[ws];
+                    for (int p = 0; p < np; ++p) {
+                        if ((fixtureInfo[proxyInfo[p] & 0xffff] & 0xffff) != b) continue;
+                        proxyFat[p] = make_float4(kMaxFloat, kMaxFloat, -kMaxFloat, -kMaxFloat);
+                        proxyMoved[p] = 0;
+                    }
+                }
+                // 4. the body itself: a tombstone that is never a seed, never woken, never touched again
+                bodyFlags[b] = (bodyFlags[b] & kBodyTypeMask) | kBodyDestroyed;
+                bodyVel[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                bodyForce[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             } break;
             case B2GPU_CMD_SET_AWAKE: {
                 if (c.wake) {

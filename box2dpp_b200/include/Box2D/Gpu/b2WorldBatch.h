@@ -377,6 +377,10 @@ public:
     // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel and weld joints; nullptr for the
     // joint types outside the device path and once the world is locked (after the first Step)
     b2Joint* CreateJoint(const b2JointDef* def);
+    // b2World::DestroyBody (b2World.cpp:124-203): queued like the b2Body edits; the body's joints, contacts and proxies go
+    // with it on the device.  The b2Body object stays allocated (its index is reserved) but must not be used again.
+    // EndContact events of the destruction are in the readback buffer (b2gpu_batch_read_events) until the next Step.
+    void DestroyBody(b2Body* body);
     void Step(float timeStep, int32_t velocityIterations, int32_t positionIterations);
     void SetContactListener(b2ContactListener* listener);
     void SetAllowSleeping(bool flag) { SetFlag(B2G_WORLD_ALLOW_SLEEP, flag); }
@@ -667,6 +671,10 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
     j->m_index = (int32_t)w.m_joints.size();
     w.m_joints.push_back(std::move(j));
     return w.m_joints.back().get();
+}
+inline void b2World::DestroyBody(b2Body* body) {
+    if (!body || body->GetWorld() != &(B2_SELF)) return;
+    m_batch->Queue(body, B2GPU_CMD_DESTROY_BODY, false, 0.0f, 0.0f, 0.0f, 0.0f);
 }
 inline void b2World::Step(float dt, int32_t vi, int32_t pi) { m_batch->Step(dt, vi, pi); }
 inline void b2World::SetContactListener(b2ContactListener* l) { m_batch->SetContactListener(l); }

@@ -61,6 +61,9 @@ enum {
     B2GPU_CMD_SET_ANGULAR_VELOCITY = 6,  /* v[0] = omega                      b2Body::SetAngularVelocity(omega) */
     B2GPU_CMD_SET_TRANSFORM = 7,         /* v = position, p[0] = angle        b2Body::SetTransform(position, angle) */
     B2GPU_CMD_SET_AWAKE = 8,             /* wake = flag                       b2Body::SetAwake(flag) */
+    B2GPU_CMD_DESTROY_BODY = 9,          /*                                   b2World::DestroyBody(body), b2World.cpp:124-203:
+                                            its joints, contacts (EndContact events, wake-ups) and proxies go with it;
+                                            the body index stays reserved (later commands on it are BAD_COMMAND) */
     B2GPU_CMD_COUNT
 };
 typedef struct b2gpu_body_command {

@@ -71,7 +71,8 @@ struct Recorder : public b2ContactListener {
 struct RefWorld {
     b2World* world;
     std::vector<b2Body*> bodies;      // creation order
-    std::vector<b2Fixture*> fixtures; // creation order
+    std::vector<b2Fixture*> fixtures; // creation order (nullptr once the body was destroyed)
+    std::vector<int> childCounts;     // proxies per fixture, kept for the dumps after destruction
     Recorder recorder;
 };
 
@@ -170,6 +171,7 @@ RefWorld* build_world(const b2g_scene* s) {
             } break;
         }
         rw->fixtures.push_back(f);
+        rw->childCounts.push_back(f->GetShape()->GetChildCount());
     }
     // b2World::CreateJoint in call order, from the same local-frame definitions the device path receives
     for (int i = 0; i < s->jointCount; ++i) {
@@ -249,6 +251,14 @@ void ref_world_body_command(void* h, int body, int op, int wake, float vx, float
     RefWorld* rw = (RefWorld*)h;
     if (body < 0 || body >= (int)rw->bodies.size()) return;
     b2Body* b = rw->bodies[body];
+    if (!b) return;  // destroyed earlier
+    if (op == 9) {   // b2World::DestroyBody: the body's fixtures go with it; the indices stay reserved
+        for (size_t i = 0; i < rw->fixtures.size(); ++i)
+            if (rw->fixtures[i] && rw->fixtures[i]->GetBody() == b) rw->fixtures[i] = nullptr;
+        rw->world->DestroyBody(b);
+        rw->bodies[body] = nullptr;
+        return;
+    }
     switch (op) {
         case 0: b->ApplyForce(b2Vec2(vx, vy), b2Vec2(px, py), wake != 0); break;
         case 1: b->ApplyForceToCenter(b2Vec2(vx, vy), wake != 0); break;
@@ -335,6 +345,11 @@ void ref_world_get_bodies(void* h, float* out) {
     for (size_t i = 0; i < rw->bodies.size(); ++i) {
         b2Body* b = rw->bodies[i];
         float* o = out + 16 * i;
+        if (!b) {  // destroyed: a row of zeros with the marker in the last column
+            for (int k = 0; k < 15; ++k) o[k] = 0.0f;
+            o[15] = 1.0f;
+            continue;
+        }
         const b2Transform& xf = b->GetTransform();
         o[0] = xf.p.x; o[1] = xf.p.y; o[2] = xf.q.s; o[3] = xf.q.c;
         o[4] = b->GetWorldCenter().x; o[5] = b->GetWorldCenter().y; o[6] = b->GetAngle();
@@ -391,9 +406,15 @@ int ref_world_get_proxies(void* h, float* aabbs, int32_t* ids, int cap) {
     RefWorld* rw = (RefWorld*)h;
     int n = 0;
     const b2BroadPhase& bp = rw->world->GetContactManager().m_broadPhase;
-    for (b2Fixture* f : rw->fixtures) {
-        int cc = f->GetShape()->GetChildCount();
+    for (size_t fi = 0; fi < rw->fixtures.size(); ++fi) {
+        b2Fixture* f = rw->fixtures[fi];
+        int cc = f ? f->GetShape()->GetChildCount() : rw->childCounts[fi];
         for (int k = 0; k < cc; ++k) {
+            if (!f) {  // proxy of a destroyed body: zeros
+                if (n < cap) { aabbs[4 * n] = aabbs[4 * n + 1] = aabbs[4 * n + 2] = aabbs[4 * n + 3] = 0.0f; ids[n] = -1; }
+                ++n;
+                continue;
+            }
             // b2Fixture::m_proxies is private; the fat AABB is reachable through the proxy id,
             // and ids are recoverable from GetAABB's owner only via friend access.  We use the
             // public path: b2Fixture has no proxy-id getter in 2.3.2, so replicate the id rule

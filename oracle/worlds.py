@@ -140,11 +140,11 @@ class RefWorld:
         return ints[:n], fl[:n]
 
     def proxies(self):
-        n = self.L.ref_world_proxy_count(self.h)
-        aabbs = np.zeros((max(n, 1), 4), np.float32)
-        ids = np.zeros(max(n, 1), np.int32)
-        self.L.ref_world_get_proxies(self.h, _p(aabbs), _p(ids), n)
-        return aabbs[:n], ids[:n]
+        cap = self.L.ref_world_proxy_count(self.h) + 4096  # proxies of destroyed bodies keep their (zeroed) rows
+        aabbs = np.zeros((cap, 4), np.float32)
+        ids = np.zeros(cap, np.int32)
+        n = min(self.L.ref_world_get_proxies(self.h, _p(aabbs), _p(ids), cap), cap)
+        return aabbs[:n].copy(), ids[:n].copy()
 
     def events(self):
         cap = 1 << 16

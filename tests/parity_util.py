@@ -12,7 +12,7 @@ def same_bits(a, b):
     return a.shape == b.shape and bool((bits(a) == bits(b)).all())
 
 
-BODY_COLS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 13, 14]  # xf, sweep c/a, v, w, awake, localCenter
+BODY_COLS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 13, 14, 15]  # xf, sweep c/a, v, w, awake, localCenter, destroyed marker
 
 
 def compare_world(ref, gpu_bodies, gpu_contacts, gpu_proxies=None, gpu_events=None, what=""):

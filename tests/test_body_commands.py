@@ -112,3 +112,48 @@ def test_bad_command_sets_status():
         cmds[0]["world"] = 7
         batch.body_commands(cmds)
     batch.close()
+
+
+@pytest.mark.gpu
+def test_destroy_body_matches_reference(oracles):
+    """b2World::DestroyBody between steps (B2GPU_CMD_DESTROY_BODY): the body's joints, contacts (EndContact events, wake-ups
+    of the neighbours) and proxies go with it; everything that remains stays bit-identical to the reference."""
+    if not oracles.available("ref"):
+        pytest.skip("checked against the live reference")
+    scenes = [S.pyramid(6), S.pyramid(5, flags=NOCCD, jitter_seed=3), S.jointed(1), S.jointed(2, flags=NOCCD), S.vehicles(1),
+              S.mixed(3), S.sensors(2), S.bullets(1)] * 5  # 40 worlds
+    refs = [oracles.RefWorld(s, record_events=True) for s in scenes]
+    batch = B.WorldBatch(scenes, event_mask=B.EVENT_ALL)
+    rng = S.LCG(77)
+    alive = [list(range(s.body_count)) for s in scenes]
+    for step in range(260):
+        rows = []
+        if step % 9 == 4:
+            for w, r in enumerate(refs):
+                if len(alive[w]) <= 2 or rng.next_u() < 0.3:
+                    continue
+                # mostly dynamic bodies, now and then body 0 (the static ground / anchor of the joints)
+                pick = 0 if (rng.next_u() < 0.05 and 0 in alive[w]) else alive[w][1 + int(rng.next_u() * (len(alive[w]) - 1)) % (len(alive[w]) - 1)]
+                alive[w].remove(pick)
+                r.command(pick, B.CMD_DESTROY_BODY)
+                rows.append((w, pick, B.CMD_DESTROY_BODY, 0, (0, 0), (0, 0)))
+                if rng.next_u() < 0.5 and len(alive[w]) > 1:  # poke a survivor in the same batch of commands
+                    other = alive[w][-1]
+                    r.command(other, B.CMD_APPLY_LINEAR_IMPULSE, 1, (1.0, 3.0), (0.0, 2.0))
+                    rows.append((w, other, B.CMD_APPLY_LINEAR_IMPULSE, 1, (1.0, 3.0), (0.0, 2.0)))
+            batch.body_commands(np.array(rows, dtype=B.BODY_COMMAND_DTYPE))
+            for w, r in enumerate(refs):  # EndContact events of the destruction follow the last step's events
+                compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} after destroy at step {step}")
+        for r in refs:
+            r.step(1 / 60, 8, 3)
+        batch.step(1 / 60, 8, 3)
+        if step % 3 == 0 or step % 9 == 4:
+            for w, r in enumerate(refs):
+                compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} step {step}")
+    assert (batch.status() == 0).all()
+    # a command on a destroyed body is reported, not executed
+    w = next(i for i in range(len(scenes)) if len(alive[i]) < scenes[i].body_count)
+    dead = next(b for b in range(scenes[w].body_count) if b not in alive[w])
+    batch.body_commands(np.array([(w, dead, B.CMD_SET_AWAKE, 1, (0, 0), (0, 0))], dtype=B.BODY_COMMAND_DTYPE))
+    assert batch.status()[w] == 4
+    batch.close()
