@@ -24,12 +24,14 @@ LIB_PATH = os.environ.get("B2GPU_LIB") or os.path.join(_HERE, "libb2gpu.so")
  F_BODY_DAMP, F_BODY_FLAGS, F_FIXTURE_INFO, F_FIXTURE_SHAPE, F_FIXTURE_MAT, F_FIXTURE_FILTER, F_PROXY_FAT,
  F_PROXY_INFO, F_PROXY_MOVED, F_SHAPE_WORDS, F_CHAIN_VERTS, F_CONTACT_A, F_CONTACT_K, F_CONTACT_S, F_CONTACT_P0,
  F_CONTACT_P1, F_CONTACT_N, F_EVENT_A, F_EVENT_B, F_ISLAND_CONTACTS, F_ISLAND_CONTACT_END, F_JOINT_COUNT, F_JOINT_I,
- F_JOINT_F0, F_JOINT_F1, F_JOINT_F2, F_JOINT_IMPULSE, F_COUNT) = range(44)
+ F_JOINT_F0, F_JOINT_F1, F_JOINT_F2, F_JOINT_IMPULSE, F_FIXTURE_COUNT, F_SHAPE_WORD_COUNT, F_CHAIN_VERT_COUNT,
+ F_PROXY_FREE_COUNT, F_PROXY_FREE, F_NEW_FIXTURE, F_COUNT) = range(50)
 
 INT_FIELDS = {F_WORLD_FLAGS, F_BODY_COUNT, F_PROXY_COUNT, F_CONTACT_COUNT, F_STATUS, F_EVENT_COUNT, F_ISLAND_COUNT,
               F_STEP_COUNT, F_BODY_FLAGS, F_FIXTURE_INFO, F_FIXTURE_SHAPE, F_FIXTURE_FILTER, F_PROXY_INFO,
               F_PROXY_MOVED, F_CONTACT_A, F_CONTACT_K, F_CONTACT_S, F_EVENT_A, F_ISLAND_CONTACTS,
-              F_ISLAND_CONTACT_END, F_JOINT_COUNT, F_JOINT_I}
+              F_ISLAND_CONTACT_END, F_JOINT_COUNT, F_JOINT_I, F_FIXTURE_COUNT, F_SHAPE_WORD_COUNT, F_CHAIN_VERT_COUNT,
+              F_PROXY_FREE_COUNT, F_PROXY_FREE, F_NEW_FIXTURE}
 
 EVENT_BEGIN, EVENT_END, EVENT_PRESOLVE, EVENT_POSTSOLVE = 0, 1, 2, 3
 EVENT_ALL = 15
@@ -104,6 +106,7 @@ def lib():
         L.b2gpu_batch_snapshot_size.restype = C.c_int64
         L.b2gpu_batch_snapshot_save.argtypes = [vp, vp, C.c_int64]
         L.b2gpu_batch_snapshot_load.argtypes = [vp, vp, C.c_int64]
+        L.b2gpu_batch_create_bodies.argtypes = [vp, vp, i32, vp, vp, vp]
         L.b2gpu_batch_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_steps.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_kernels.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
@@ -149,7 +152,7 @@ class WorldBatch:
     """A batch of independent worlds on one GPU."""
 
     def __init__(self, scenes, replicate=1, device=0, max_contacts=0, max_events=0, event_mask=0, block_size=0,
-                 generic_solver=False, always_rebuild_islands=False, binned_collide=None):
+                 generic_solver=False, always_rebuild_islands=False, binned_collide=None, headroom=None):
         if isinstance(scenes, Scene):
             scenes = [scenes]
         if isinstance(scenes, SceneBatch):
@@ -165,6 +168,12 @@ class WorldBatch:
         d.maxContacts, d.maxEvents, d.eventMask, d.blockSize = max_contacts, max_events, event_mask, block_size
         d.reserved = (1 if generic_solver else 0) | (2 if always_rebuild_islands else 0)
         _check(L.b2gpu_scene_capacities(arr, n_scenes, C.byref(d)))
+        if headroom:  # room for bodies created after the first step: (bodies, fixtures, proxies, shape words, chain vertices)
+            d.maxBodies += headroom[0]; d.maxFixtures += headroom[1]; d.maxProxies += headroom[2]
+            d.maxShapeWords += headroom[3]; d.maxChainVerts += headroom[4]
+            d.maxContacts += 4 * headroom[2]
+            if d.eventMask:
+                d.maxEvents = max(d.maxEvents, 3 * d.maxContacts)
         if binned_collide is not None:  # default: decided by b2gpu_scene_capacities (worlds that mix shape types)
             d.reserved = (d.reserved | 4) if binned_collide else (d.reserved & ~4)
         self.desc = d
@@ -348,6 +357,31 @@ class WorldBatch:
             _check(lib().b2gpu_batch_read_events(self.h, offsets.ctypes.data_as(C.c_void_p), events.ctypes.data_as(C.c_void_p),
                                                  events.shape[0]))
         return offsets, events
+
+    def create_bodies(self, spawns):
+        """b2gpu_batch_create_bodies: spawns = [(world, BodyDef, [FixtureDef, ...], vertices xy list)], vertex indices of a
+        spawn's fixtures are relative to its own vertex list.  Returns the new body indices (-1: arenas full)."""
+        from .scene import BodyDef, FixtureDef
+
+        class Spawn(C.Structure):
+            _fields_ = [("world", C.c_int32), ("firstFixture", C.c_int32), ("fixtureCount", C.c_int32), ("body", BodyDef)]
+
+        n = len(spawns)
+        arr = (Spawn * max(n, 1))()
+        fds, verts = [], []
+        for i, (world, bd, fixtures, v) in enumerate(spawns):
+            arr[i].world, arr[i].firstFixture, arr[i].fixtureCount, arr[i].body = world, len(fds), len(fixtures), bd
+            base = len(verts) // 2
+            for f in fixtures:
+                g = FixtureDef.from_buffer_copy(bytes(f))
+                g.firstVertex += base
+                fds.append(g)
+            verts.extend(float(x) for x in v)
+        cf = (FixtureDef * max(len(fds), 1))(*fds)
+        cv = np.ascontiguousarray(verts if verts else [0.0, 0.0], np.float32)
+        out = np.zeros(max(n, 1), np.int32)
+        _check(lib().b2gpu_batch_create_bodies(self.h, arr, n, cf, cv.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out[:n]
 
     def snapshot(self) -> np.ndarray:
         """b2gpu_batch_snapshot_save: every persistent field of every world as one blob."""

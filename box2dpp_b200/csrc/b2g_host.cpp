@@ -12,6 +12,7 @@
 // Compiled with g++ -O2 -ffp-contract=off (no FMA contraction), never -ffast-math.
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -272,6 +273,7 @@ inline float IntBits(int v) { float f; memcpy(&f, &v, 4); return f; }
 // One world flattened into world-major field arrays of capacity-sized rows.
 struct FlatWorld {
     std::vector<std::vector<uint32_t>> f;  // per field id, capacity * components words
+    int fixtures = 0, proxies = 0, shapeWords = 0, chainVerts = 0;  // slots used
 };
 
 struct Caps {
@@ -485,6 +487,11 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
     put(out.f[B2GPU_F_INV_DT0], 0, 0.0f);
     put(out.f[B2GPU_F_BODY_COUNT], 0, nb);
     put(out.f[B2GPU_F_PROXY_COUNT], 0, proxyCount);
+    put(out.f[B2GPU_F_FIXTURE_COUNT], 0, nf);
+    put(out.f[B2GPU_F_SHAPE_WORD_COUNT], 0, shapeWordsUsed);
+    put(out.f[B2GPU_F_CHAIN_VERT_COUNT], 0, chainUsed);
+    put(out.f[B2GPU_F_NEW_FIXTURE], 0, 1);  // CreateFixture raised e_newFixture
+    out.fixtures = nf; out.proxies = proxyCount; out.shapeWords = shapeWordsUsed; out.chainVerts = chainUsed;
 
     // ---- b2World::CreateJoint calls (b2World.cpp:211-270); the joint constructors copy the def
     // (b2RevoluteJoint.cpp:47-64, b2PrismaticJoint.cpp:100-125, b2DistanceJoint.cpp:51-62) ----
@@ -539,6 +546,7 @@ const int kBuildFields[] = {
     B2GPU_F_BODY_DAMP, B2GPU_F_BODY_FLAGS, B2GPU_F_FIXTURE_INFO, B2GPU_F_FIXTURE_SHAPE, B2GPU_F_FIXTURE_MAT,
     B2GPU_F_FIXTURE_FILTER, B2GPU_F_PROXY_FAT, B2GPU_F_PROXY_INFO, B2GPU_F_SHAPE_WORDS, B2GPU_F_CHAIN_VERTS,
     B2GPU_F_JOINT_COUNT, B2GPU_F_JOINT_I, B2GPU_F_JOINT_F0, B2GPU_F_JOINT_F1, B2GPU_F_JOINT_F2, B2GPU_F_JOINT_IMPULSE,
+    B2GPU_F_FIXTURE_COUNT, B2GPU_F_SHAPE_WORD_COUNT, B2GPU_F_CHAIN_VERT_COUNT, B2GPU_F_PROXY_FREE_COUNT, B2GPU_F_NEW_FIXTURE,
     B2GPU_F_PROXY_MOVED,
 };
 
@@ -627,6 +635,71 @@ int b2gpu_batch_build_worlds(b2gpu_batch* batch, const b2g_scene* scenes, int32_
             if (rc != B2GPU_OK) return rc;
         }
     }
+    return B2GPU_OK;
+}
+
+// Spawn record (32-bit words), consumed by k_spawn (b2g_step.cu):
+//   header   world, fixtures, proxies, shapeWords, chainVerts
+//   body     xf[4] sweep[4] sweep0[4] vel[4] mass[4] damp[4] flags
+//   fixture  info (body field = 0), shape offset (relative), friction, restitution, filter[2]        x fixtures
+//   proxy    fat AABB[4], fixture (relative) | child << 16                                          x proxies
+//   shape table words (chain entries hold a relative first vertex), chain vertices xy
+int b2gpu_batch_create_bodies(b2gpu_batch* batch, const b2gpu_spawn* spawns, int32_t count, const b2g_fixture_def* fixtures,
+                              const float* vertices, int32_t* bodyIndices) {
+    if (!batch || count < 0 || (count > 0 && (!spawns || !bodyIndices))) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    if (count == 0) return B2GPU_OK;
+    std::vector<std::pair<int, int>> shapes(B2GPU_F_COUNT);
+    for (int id = 0; id < B2GPU_F_COUNT; ++id) {
+        int rc = b2gpu_batch_field_shape(batch, id, &shapes[id].first, &shapes[id].second);
+        if (rc != B2GPU_OK) return rc;
+    }
+    Caps cap;
+    cap.NB = shapes[B2GPU_F_BODY_XF].first; cap.NF = shapes[B2GPU_F_FIXTURE_INFO].first; cap.NP = shapes[B2GPU_F_PROXY_FAT].first;
+    cap.NC = shapes[B2GPU_F_CONTACT_A].first; cap.NS = shapes[B2GPU_F_SHAPE_WORDS].first; cap.NV = shapes[B2GPU_F_CHAIN_VERTS].first;
+    cap.NE = shapes[B2GPU_F_EVENT_A].first;
+    // spawns of one world keep their order: stable sort by world, results mapped back
+    std::vector<int> order(count);
+    for (int i = 0; i < count; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return spawns[a].world < spawns[b].world; });
+    std::vector<uint32_t> words;
+    std::vector<int64_t> offsets(count + 1);
+    std::string err;
+    for (int n = 0; n < count; ++n) {
+        const b2gpu_spawn& sp = spawns[order[n]];
+        if (sp.fixtureCount < 0 || (sp.fixtureCount > 0 && !fixtures)) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "spawn without fixtures array");
+        std::vector<b2g_fixture_def> fds(fixtures + (sp.fixtureCount ? sp.firstFixture : 0), fixtures + (sp.fixtureCount ? sp.firstFixture + sp.fixtureCount : 0));
+        for (b2g_fixture_def& fd : fds) fd.body = 0;
+        b2g_scene mini;
+        memset(&mini, 0, sizeof(mini));
+        mini.worldFlags = B2G_WORLD_DEFAULT_FLAGS;
+        mini.bodyCount = 1;
+        mini.fixtureCount = (int)fds.size();
+        mini.bodies = &sp.body;
+        mini.fixtures = fds.data();
+        mini.vertices = vertices;
+        FlatWorld fw;
+        int rc = Flatten(mini, cap, shapes, fw, err);
+        if (rc != B2GPU_OK) return b2gpu_host_set_error(rc, err.c_str());
+        offsets[n] = (int64_t)words.size();
+        auto push = [&](uint32_t v) { words.push_back(v); };
+        auto pushField = [&](int id, size_t first, size_t nwords) { for (size_t k = 0; k < nwords; ++k) push(fw.f[id][first + k]); };
+        push((uint32_t)sp.world); push((uint32_t)fw.fixtures); push((uint32_t)fw.proxies); push((uint32_t)fw.shapeWords); push((uint32_t)fw.chainVerts);
+        pushField(B2GPU_F_BODY_XF, 0, 4); pushField(B2GPU_F_BODY_SWEEP, 0, 4); pushField(B2GPU_F_BODY_SWEEP0, 0, 4);
+        pushField(B2GPU_F_BODY_VEL, 0, 4); pushField(B2GPU_F_BODY_MASS, 0, 4); pushField(B2GPU_F_BODY_DAMP, 0, 4);
+        pushField(B2GPU_F_BODY_FLAGS, 0, 1);
+        for (int f = 0; f < fw.fixtures; ++f) {
+            pushField(B2GPU_F_FIXTURE_INFO, f, 1); pushField(B2GPU_F_FIXTURE_SHAPE, f, 1);
+            pushField(B2GPU_F_FIXTURE_MAT, (size_t)f * 2, 2); pushField(B2GPU_F_FIXTURE_FILTER, (size_t)f * 2, 2);
+        }
+        for (int q = 0; q < fw.proxies; ++q) { pushField(B2GPU_F_PROXY_FAT, (size_t)q * 4, 4); pushField(B2GPU_F_PROXY_INFO, q, 1); }
+        pushField(B2GPU_F_SHAPE_WORDS, 0, fw.shapeWords);
+        pushField(B2GPU_F_CHAIN_VERTS, 0, (size_t)fw.chainVerts * 2);
+    }
+    offsets[count] = (int64_t)words.size();
+    std::vector<int32_t> sortedIdx(count);
+    int rc = b2gpu_batch_spawn_records(batch, words.data(), offsets.data(), count, sortedIdx.data());
+    if (rc != B2GPU_OK) return rc;
+    for (int n = 0; n < count; ++n) bodyIndices[order[n]] = sortedIdx[n];
     return B2GPU_OK;
 }
 

@@ -1552,7 +1552,10 @@ __global__ void __launch_bounds__(128) k_index_proxies(Arena A) {
 __global__ void __launch_bounds__(128) k_find_new_contacts(Arena A) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     int tile = w >> 5, lane = w & 31;
-    if (tile >= A.numTiles) return;
+    if (tile >= A.numTiles || w >= A.numWorlds) return;
+    const size_t ws = (size_t)tile * kTile + lane;
+    if (A.newFixture[ws] == 0) return;  // only worlds whose e_newFixture is set (freshly built, or a body was created)
+    A.newFixture[ws] = 0;
     UpdatePairsOrdered(&A, tile, lane);
 }
 

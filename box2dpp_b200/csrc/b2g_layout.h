@@ -77,6 +77,11 @@ struct Arena {
     int* eventCount;
     int* islandCount;    // last step (diagnostics)
     int* stepCount;
+    int* fixtureCount;   // fixture slots in use
+    int* shapeWordCount; // shape-table words in use
+    int* chainVertCount;
+    int* proxyFreeCount; // freed proxy slots (LIFO, like b2DynamicTree's free list)
+    int* newFixture;     // b2World::e_newFixture
     int* pendingMoves;   // != 0: proxies were put into the move buffer between steps (b2Body::SetTransform)
     int* topoDirty;      // != 0: contact graph / touching / awake flags changed since the islands were built
 
@@ -101,6 +106,7 @@ struct Arena {
     float4* proxyFat;    // fat AABB lo.xy hi.xy (b2TreeNode::aabb)
     int* proxyInfo;      // fixture | child << 16
     int* proxyMoved;     // 1 = in the move buffer
+    int* proxyFree;      // [tile][NP][lane] stack of freed proxy slots
 
     // ---- shapes ----
     float* shapeWords;   // [tile][NS][lane]

@@ -128,6 +128,82 @@ __global__ void k_read_body_state(Arena A, float4* __restrict__ out) {
     o[1] = make_float4(v.x, v.y, v.z, sw.w);
 }
 
+// b2World::CreateBody + b2Body::CreateFixture after the first step, from records evaluated by the host layer
+// (b2g_host.cpp b2gpu_batch_create_bodies).  Records are grouped by world; the thread that owns a world's first record
+// applies that world's records in order.
+__global__ void k_spawn(Arena A, const uint32_t* __restrict__ words, const long long* __restrict__ offsets, int count,
+                        int* __restrict__ outIndex) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int w = (int)words[offsets[i]];
+    if (i > 0 && (int)words[offsets[i - 1]] == w) return;
+    const int tile = w >> 5, lane = w & 31;
+    const size_t ws = (size_t)tile * kTile + lane;
+    for (; i < count && (int)words[offsets[i]] == w; ++i) {
+        const uint32_t* r = words + offsets[i];
+        const int rf = (int)r[1], rp = (int)r[2], rs = (int)r[3], rv = (int)r[4];
+        const int nb = A.bodyCount[ws], nf = A.fixtureCount[ws], np = A.proxyCount[ws], ns = A.shapeWordCount[ws];
+        const int nv = A.chainVertCount[ws];
+        int nfree = A.proxyFreeCount[ws];
+        const int fresh = rp > nfree ? rp - nfree : 0;
+        if (nb + 1 > A.NB || nf + rf > A.NF || np + fresh > A.NP || ns + rs > A.NS || nv + rv > A.NV) {
+            A.status[ws] |= B2GPU_STATUS_SPAWN_OVERFLOW;
+            outIndex[i] = -1;
+            continue;
+        }
+        const uint32_t* p = r + 5;
+        auto f4 = [&](float4* base, int cap, int item) {
+            col(base, tile, cap, lane)[item] = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), __uint_as_float(p[3]));
+            p += 4;
+        };
+        const int b = nb;  // new highest index = head of m_bodyList
+        f4(A.bodyXf, A.NB, b); f4(A.bodySweep, A.NB, b); f4(A.bodySweep0, A.NB, b); f4(A.bodyVel, A.NB, b);
+        f4(A.bodyMass, A.NB, b); f4(A.bodyDamp, A.NB, b);
+        col(A.bodyForce, tile, A.NB, lane)[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        col(A.bodyFlags, tile, A.NB, lane)[b] = (int)*p++;
+        col(A.bodyIsland, tile, A.NB, lane)[b] = -1;
+        for (int f = 0; f < rf; ++f) {
+            const int info = (int)p[0], shapeOff = (int)p[1] + ns;
+            col(A.fixtureInfo, tile, A.NF, lane)[nf + f] = (info & ~0xffff) | b;
+            col(A.fixtureShape, tile, A.NF, lane)[nf + f] = shapeOff;
+            col(A.fixtureMat, tile, A.NF, lane)[nf + f] = make_float2(__uint_as_float(p[2]), __uint_as_float(p[3]));
+            col(A.fixtureFilter, tile, A.NF, lane)[nf + f] = make_int2((int)p[4], (int)p[5]);
+            p += 6;
+        }
+        Col<int> proxyFree = col(A.proxyFree, tile, A.NP, lane);
+        int npNow = np;
+        for (int q = 0; q < rp; ++q) {  // b2Fixture::CreateProxies -> b2DynamicTree::AllocateNode: most recently freed id first
+            const int slot = nfree > 0 ? proxyFree[--nfree] : npNow++;
+            col(A.proxyFat, tile, A.NP, lane)[slot] = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), __uint_as_float(p[3]));
+            const int info = (int)p[4];
+            col(A.proxyInfo, tile, A.NP, lane)[slot] = (nf + (info & 0xffff)) | (info & ~0xffff);
+            col(A.proxyMoved, tile, A.NP, lane)[slot] = 1;  // b2BroadPhase::CreateProxy buffers a move
+            p += 5;
+        }
+        float* sw = A.shapeWords + ((size_t)tile * A.NS + ns) * kTile + lane;
+        for (int k = 0; k < rs; ++k) sw[(size_t)k * kTile] = __uint_as_float(p[k]);
+        p += rs;
+        Col<float2> cv = col(A.chainVerts, tile, A.NV, lane);
+        for (int k = 0; k < rv; ++k) cv[nv + k] = make_float2(__uint_as_float(p[2 * k]), __uint_as_float(p[2 * k + 1]));
+        // chain entries of the shape table hold their first vertex index: rebase it
+        for (int f = 0; f < rf; ++f) {
+            const int fi = col(A.fixtureInfo, tile, A.NF, lane)[nf + f];
+            if (((fi >> 16) & 3) != B2G_SHAPE_CHAIN) continue;
+            float* e = A.shapeWords + ((size_t)tile * A.NS + col(A.fixtureShape, tile, A.NF, lane)[nf + f] + 1) * kTile + lane;
+            *e = __int_as_float(__float_as_int(*e) + nv);  // (two fixtures never share a chain entry: its first vertex is unique)
+        }
+        A.bodyCount[ws] = nb + 1;
+        A.fixtureCount[ws] = nf + rf;
+        A.proxyCount[ws] = npNow;
+        A.proxyFreeCount[ws] = nfree;
+        A.shapeWordCount[ws] = ns + rs;
+        A.chainVertCount[ws] = nv + rv;
+        A.newFixture[ws] = 1;
+        A.topoDirty[ws] = 1;
+        outIndex[i] = b;
+    }
+}
+
 // Compaction of the per-world event arenas: world w's events go to out[offsets[w] ...] (b2gpu_batch_read_events).
 __global__ void k_gather_events(Arena A, const long long* __restrict__ offsets, b2gpu_event* __restrict__ out, long long capacity) {
     const int w = blockIdx.x;  // one CTA per world, threads stride over its events
@@ -317,11 +393,22 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                     Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
                     Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
                     const int np = A.proxyCount[ws];
-                    for (int p = 0; p < np; ++p) {
-                        if ((fixtureInfo[proxyInfo[p] & 0xffff] & 0xffff) != b) continue;
-                        proxyFat[p] = make_float4(kMaxFloat, kMaxFloat, -kMaxFloat, -kMaxFloat);
-                        proxyMoved[p] = 0;
+                    // b2DynamicTree::FreeNode order = the body's fixture list (newest fixture first), children ascending:
+                    // the freed slots form a LIFO stack from which later CreateProxy calls take their ids
+                    Col<int> proxyFree = col(A.proxyFree, tile, A.NP, lane);
+                    int nfree = A.proxyFreeCount[ws];
+                    for (int fx = A.fixtureCount[ws] - 1; fx >= 0; --fx) {
+                        const int fi = fixtureInfo[fx];
+                        if ((fi & 0xffff) != b || (fi & (1 << 19))) continue;
+                        fixtureInfo[fx] = fi | (1 << 19);  // destroyed fixture
+                        for (int p = 0; p < np; ++p) {  // proxies of one fixture sit in ascending child order
+                            if ((proxyInfo[p] & 0xffff) != fx || proxyFat[p].x > proxyFat[p].z) continue;
+                            proxyFat[p] = make_float4(kMaxFloat, kMaxFloat, -kMaxFloat, -kMaxFloat);
+                            proxyMoved[p] = 0;
+                            proxyFree[nfree++] = p;
+                        }
                     }
+                    A.proxyFreeCount[ws] = nfree;
                 }
                 // 4. the body itself: a tombstone that is never a seed, never woken, never touched again
                 bodyFlags[b] = (bodyFlags[b] & kBodyTypeMask) | kBodyDestroyed;
@@ -526,6 +613,8 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(bodyCount, 1, int); ALLOC(proxyCount, 1, int); ALLOC(contactCount, 1, int);
     ALLOC(status, 1, int); ALLOC(eventCount, 1, int); ALLOC(islandCount, 1, int); ALLOC(stepCount, 1, int);
     ALLOC(topoDirty, 1, int); ALLOC(pendingMoves, 1, int);
+    ALLOC(fixtureCount, 1, int); ALLOC(shapeWordCount, 1, int); ALLOC(chainVertCount, 1, int); ALLOC(proxyFreeCount, 1, int);
+    ALLOC(newFixture, 1, int); ALLOC(proxyFree, A.NP, int);
     CUDA_TRY(cudaMemsetAsync(A.topoDirty, 1, (size_t)A.numTiles * kTile * sizeof(int), b->stream));
     ALLOC(bodyXf, A.NB, float4); ALLOC(bodySweep, A.NB, float4); ALLOC(bodySweep0, A.NB, float4);
     ALLOC(bodyVel, A.NB, float4); ALLOC(bodyForce, A.NB, float4); ALLOC(bodyMass, A.NB, float4);
@@ -603,6 +692,12 @@ int allocateArena(b2gpu_batch* b) {
     F(B2GPU_F_JOINT_F1, (void**)&A.jointF1, A.NJ, 4);
     F(B2GPU_F_JOINT_F2, (void**)&A.jointF2, A.NJ, 4);
     F(B2GPU_F_JOINT_IMPULSE, (void**)&A.jointImp, A.NJ, 4);
+    F(B2GPU_F_FIXTURE_COUNT, (void**)&A.fixtureCount, 1, 1);
+    F(B2GPU_F_SHAPE_WORD_COUNT, (void**)&A.shapeWordCount, 1, 1);
+    F(B2GPU_F_CHAIN_VERT_COUNT, (void**)&A.chainVertCount, 1, 1);
+    F(B2GPU_F_PROXY_FREE_COUNT, (void**)&A.proxyFreeCount, 1, 1);
+    F(B2GPU_F_PROXY_FREE, (void**)&A.proxyFree, A.NP, 1);
+    F(B2GPU_F_NEW_FIXTURE, (void**)&A.newFixture, 1, 1);
     return B2GPU_OK;
 }
 
@@ -1158,7 +1253,8 @@ const int kSnapshotFields[] = {
     B2GPU_F_FIXTURE_MAT, B2GPU_F_FIXTURE_FILTER, B2GPU_F_PROXY_FAT, B2GPU_F_PROXY_INFO, B2GPU_F_PROXY_MOVED, B2GPU_F_SHAPE_WORDS,
     B2GPU_F_CHAIN_VERTS, B2GPU_F_CONTACT_A, B2GPU_F_CONTACT_K, B2GPU_F_CONTACT_S, B2GPU_F_CONTACT_P0, B2GPU_F_CONTACT_P1,
     B2GPU_F_CONTACT_N, B2GPU_F_JOINT_COUNT, B2GPU_F_JOINT_I, B2GPU_F_JOINT_F0, B2GPU_F_JOINT_F1, B2GPU_F_JOINT_F2,
-    B2GPU_F_JOINT_IMPULSE,
+    B2GPU_F_JOINT_IMPULSE, B2GPU_F_FIXTURE_COUNT, B2GPU_F_SHAPE_WORD_COUNT, B2GPU_F_CHAIN_VERT_COUNT, B2GPU_F_PROXY_FREE_COUNT,
+    B2GPU_F_PROXY_FREE, B2GPU_F_NEW_FIXTURE,
 };
 struct SnapshotHeader {
     uint32_t magic, version;
@@ -1220,6 +1316,33 @@ int b2gpu_batch_snapshot_load(b2gpu_batch* b, const void* blob, int64_t size) {
     }
     b->needProxyIndex = true;
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_spawn_records(b2gpu_batch* b, const uint32_t* words, const int64_t* offsets, int32_t count, int32_t* bodyIndices) {
+    if (!b || count < 0 || (count > 0 && (!words || !offsets || !bodyIndices))) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    if (count == 0) return B2GPU_OK;
+    for (int32_t i = 0; i < count; ++i) {
+        const int w = (int)words[offsets[i]];
+        if (w < 0 || w >= b->desc.numWorlds) return fail(B2GPU_ERR_INVALID, "spawn %d names world %d outside the batch", i, w);
+        if (i > 0 && w < (int)words[offsets[i - 1]]) return fail(B2GPU_ERR_INVALID, "spawn records must be grouped by ascending world");
+    }
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    DevBuf dw, doff, dout;
+    int rc;
+    const size_t nwords = (size_t)offsets[count];
+    if ((rc = dw.alloc(nwords * 4)) != B2GPU_OK) return rc;
+    if ((rc = doff.alloc((size_t)(count + 1) * sizeof(int64_t))) != B2GPU_OK) return rc;
+    if ((rc = dout.alloc((size_t)count * sizeof(int32_t))) != B2GPU_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dw.p, words, nwords * 4, cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(doff.p, offsets, (size_t)(count + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    k_spawn<<<(unsigned)((count + 127) / 128), 128, 0, b->stream>>>(b->A, (const uint32_t*)dw.p, (const long long*)doff.p, count, (int*)dout.p);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(bodyIndices, dout.p, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    b->needInitialPairs = true;  // some world has e_newFixture set: the next Step starts with FindNewContacts
+    b->needProxyIndex = true;
     return B2GPU_OK;
 }
 

@@ -46,7 +46,8 @@ enum {
 enum { B2GPU_EVENT_BEGIN = 0, B2GPU_EVENT_END = 1, B2GPU_EVENT_PRESOLVE = 2, B2GPU_EVENT_POSTSOLVE = 3 };
 
 /* Per-world status bits (b2gpu_batch_download_field(B2GPU_F_STATUS)). */
-enum { B2GPU_STATUS_CONTACT_OVERFLOW = 1, B2GPU_STATUS_EVENT_OVERFLOW = 2, B2GPU_STATUS_BAD_COMMAND = 4 };
+enum { B2GPU_STATUS_CONTACT_OVERFLOW = 1, B2GPU_STATUS_EVENT_OVERFLOW = 2, B2GPU_STATUS_BAD_COMMAND = 4,
+       B2GPU_STATUS_SPAWN_OVERFLOW = 8 /* a body created after the first step did not fit the arenas */ };
 
 /* Between-step body edits: one record per call the reference's user would make on a b2Body
  * between two Steps.  Box2D/Dynamics/b2Body.h:738-833 (Apply*), :408-467 (SetLinearVelocity, SetAngularVelocity,
@@ -148,6 +149,12 @@ enum {
     B2GPU_F_JOINT_F2,           /* [W][NJ][4]  motorSpeed, localXAxisA.xy (normalised), 0 */
     B2GPU_F_JOINT_IMPULSE,      /* [W][NJ][4]  m_impulse.xyz, m_motorImpulse (warm-starting state);
                                                wheel: m_impulse, m_springImpulse, 0, m_motorImpulse */
+    B2GPU_F_FIXTURE_COUNT,      /* [W][1][1] int32  fixture slots in use (destroyed ones included) */
+    B2GPU_F_SHAPE_WORD_COUNT,   /* [W][1][1] int32  words of the shape table in use */
+    B2GPU_F_CHAIN_VERT_COUNT,   /* [W][1][1] int32 */
+    B2GPU_F_PROXY_FREE_COUNT,   /* [W][1][1] int32  freed proxy slots (b2DynamicTree's free list, LIFO) */
+    B2GPU_F_PROXY_FREE,         /* [W][NP][1] int32 */
+    B2GPU_F_NEW_FIXTURE,        /* [W][1][1] int32  b2World::e_newFixture: the next Step starts with FindNewContacts */
     B2GPU_F_COUNT
 };
 
@@ -281,6 +288,26 @@ int b2gpu_scene_capacities(const b2g_scene* scenes, int32_t sceneCount, b2gpu_ba
  * sceneCount == 1 with replicate > 1 builds `replicate` identical worlds. */
 int b2gpu_batch_build_worlds(b2gpu_batch* batch, const b2g_scene* scenes, int32_t sceneCount, int32_t firstWorld,
                              int32_t replicate);
+
+/* Replaces b2World::CreateBody + b2Body::CreateFixture calls made AFTER the first Step (b2World.cpp:98-122,
+ * b2Body.cpp:168-214): spawn i creates one body from spawns[i].body with the fixtures
+ * fixtures[firstFixture .. firstFixture + fixtureCount) (their `body` member is ignored; vertex indices refer to
+ * `vertices`).  The host layer evaluates shapes, mass data and fat AABBs like at build time; the device appends the
+ * body (new highest index = head of b2World::m_bodyList) and its fixtures, gives each proxy the most recently freed
+ * proxy slot (b2DynamicTree's LIFO free list, so proxy ids — the sort key of b2BroadPhase::UpdatePairs — are the
+ * reference's) or a fresh one, buffers the moves and raises e_newFixture.  Spawns of one world are applied in array
+ * order.  bodyIndices[i] = the new body's index, or -1 when the world's arenas are full
+ * (B2GPU_STATUS_SPAWN_OVERFLOW; raise the capacities in b2gpu_batch_desc before b2gpu_batch_create).  Synchronises. */
+typedef struct b2gpu_spawn {
+    int32_t world;
+    int32_t firstFixture, fixtureCount;
+    b2g_body_def body;
+} b2gpu_spawn;
+int b2gpu_batch_create_bodies(b2gpu_batch* batch, const b2gpu_spawn* spawns, int32_t count, const b2g_fixture_def* fixtures,
+                              const float* vertices, int32_t* bodyIndices);
+/* Device-layer primitive under it: applies pre-evaluated spawn records (layout: box2dpp_b200/csrc/b2g_host.cpp). */
+int b2gpu_batch_spawn_records(b2gpu_batch* batch, const uint32_t* words, const int64_t* offsets, int32_t count,
+                              int32_t* bodyIndices);
 
 /* Host-side shape math, exported for tests: b2PolygonShape::Set / SetAsBox / ComputeMass
  * (Box2D/Collision/Shapes/b2PolygonShape.cpp:32-245, 354-437).  out: 8 vertices, 8 normals, centroid, then

@@ -13,7 +13,12 @@
 //   * direct calls of the narrow-phase functions (b2CollidePolygons, ... Collision/b2Collision.h)
 //     and shape helpers (b2PolygonShape::Set / ComputeMass) for known-answer tests
 //   * an all-core CPU baseline: one world per thread slot, T threads (bench.py --impl reference)
+// The dumps need b2Fixture::m_proxies (the broad-phase proxy ids), which the library keeps private.
+#define private public
+#define protected public
 #include <Box2DRef/Box2D.h>
+#undef private
+#undef protected
 
 #include <pthread.h>
 #include <sched.h>
@@ -72,7 +77,8 @@ struct RefWorld {
     b2World* world;
     std::vector<b2Body*> bodies;      // creation order
     std::vector<b2Fixture*> fixtures; // creation order (nullptr once the body was destroyed)
-    std::vector<int> childCounts;     // proxies per fixture, kept for the dumps after destruction
+    std::vector<int> childCounts;     // proxies per fixture
+    int proxySlots = 0;               // high-water mark of proxy slots (see ref_world_get_proxies)
     Recorder recorder;
 };
 
@@ -89,6 +95,84 @@ void build_polygon(b2PolygonShape& poly, const b2g_fixture_def& fd, const float*
     }
 }
 
+// b2World::CreateBody from a body definition; the body's index (creation order) is its userData
+void add_body(RefWorld* rw, const b2g_body_def& d) {
+    b2BodyDef bd;
+    bd.type = (b2BodyType)d.type;
+    bd.position.Set(d.position[0], d.position[1]);
+    bd.angle = d.angle;
+    bd.linearVelocity.Set(d.linearVelocity[0], d.linearVelocity[1]);
+    bd.angularVelocity = d.angularVelocity;
+    bd.linearDamping = d.linearDamping;
+    bd.angularDamping = d.angularDamping;
+    bd.gravityScale = d.gravityScale;
+    bd.allowSleep = (d.flags & B2G_BD_ALLOW_SLEEP) != 0;
+    bd.awake = (d.flags & B2G_BD_AWAKE) != 0;
+    bd.fixedRotation = (d.flags & B2G_BD_FIXED_ROTATION) != 0;
+    bd.bullet = (d.flags & B2G_BD_BULLET) != 0;
+    bd.active = (d.flags & B2G_BD_ACTIVE) != 0;
+    bd.userData = (void*)(intptr_t)rw->bodies.size();
+    rw->bodies.push_back(rw->world->CreateBody(&bd));
+}
+
+// b2Body::CreateFixture from a fixture definition; the fixture's index (creation order) is its userData
+void add_fixture(RefWorld* rw, b2Body* body, const b2g_fixture_def& d, const float* v) {
+    b2FixtureDef fd;
+    fd.friction = d.friction;
+    fd.restitution = d.restitution;
+    fd.density = d.density;
+    fd.isSensor = d.isSensor != 0;
+    fd.filter.categoryBits = d.categoryBits;
+    fd.filter.maskBits = d.maskBits;
+    fd.filter.groupIndex = d.groupIndex;
+    fd.userData = (void*)(intptr_t)rw->fixtures.size();
+    b2Fixture* f = nullptr;
+    switch (d.shapeType) {
+        case B2G_SHAPE_CIRCLE: {
+            b2CircleShape sh;
+            sh.m_p.Set(d.p[0], d.p[1]);
+            sh.m_radius = d.radius;
+            fd.shape = &sh;
+            f = body->CreateFixture(&fd);
+        } break;
+        case B2G_SHAPE_EDGE: {
+            b2EdgeShape sh;
+            sh.Set(b2Vec2(v[2 * d.firstVertex], v[2 * d.firstVertex + 1]), b2Vec2(v[2 * d.firstVertex + 2], v[2 * d.firstVertex + 3]));
+            if (d.hasVertex0) { sh.m_vertex0.Set(d.vertex0[0], d.vertex0[1]); sh.m_hasVertex0 = true; }
+            if (d.hasVertex3) { sh.m_vertex3.Set(d.vertex3[0], d.vertex3[1]); sh.m_hasVertex3 = true; }
+            fd.shape = &sh;
+            f = body->CreateFixture(&fd);
+        } break;
+        case B2G_SHAPE_POLYGON: {
+            b2PolygonShape sh;
+            build_polygon(sh, d, v);
+            fd.shape = &sh;
+            f = body->CreateFixture(&fd);
+        } break;
+        case B2G_SHAPE_CHAIN: {
+            b2ChainShape sh;
+            std::vector<b2Vec2> pts(d.vertexCount);
+            for (int k = 0; k < d.vertexCount; ++k) pts[k].Set(v[2 * (d.firstVertex + k)], v[2 * (d.firstVertex + k) + 1]);
+            if (d.shapeKind == B2G_CHAIN_LOOP) {
+                sh.CreateLoop(pts.data(), d.vertexCount);
+            } else {
+                sh.CreateChain(pts.data(), d.vertexCount);
+                if (d.hasVertex0) sh.SetPrevVertex(b2Vec2(d.vertex0[0], d.vertex0[1]));
+                if (d.hasVertex3) sh.SetNextVertex(b2Vec2(d.vertex3[0], d.vertex3[1]));
+            }
+            fd.shape = &sh;
+            f = body->CreateFixture(&fd);
+        } break;
+    }
+    rw->fixtures.push_back(f);
+    rw->childCounts.push_back(f->GetShape()->GetChildCount());
+    for (int k = 0; k < f->m_proxyCount; ++k) {
+        const int id = f->m_proxies[k].proxyId;
+        const int slot = id == 0 ? 0 : (id + 1) / 2;
+        if (slot + 1 > rw->proxySlots) rw->proxySlots = slot + 1;
+    }
+}
+
 RefWorld* build_world(const b2g_scene* s) {
     RefWorld* rw = new RefWorld;
     rw->world = new b2World(b2Vec2(s->gravity[0], s->gravity[1]));
@@ -99,80 +183,8 @@ RefWorld* build_world(const b2g_scene* s) {
     w->SetAutoClearForces((s->worldFlags & B2G_WORLD_CLEAR_FORCES) != 0);
     w->SetContactListener(&rw->recorder);
 
-    for (int i = 0; i < s->bodyCount; ++i) {
-        const b2g_body_def& d = s->bodies[i];
-        b2BodyDef bd;
-        bd.type = (b2BodyType)d.type;
-        bd.position.Set(d.position[0], d.position[1]);
-        bd.angle = d.angle;
-        bd.linearVelocity.Set(d.linearVelocity[0], d.linearVelocity[1]);
-        bd.angularVelocity = d.angularVelocity;
-        bd.linearDamping = d.linearDamping;
-        bd.angularDamping = d.angularDamping;
-        bd.gravityScale = d.gravityScale;
-        bd.allowSleep = (d.flags & B2G_BD_ALLOW_SLEEP) != 0;
-        bd.awake = (d.flags & B2G_BD_AWAKE) != 0;
-        bd.fixedRotation = (d.flags & B2G_BD_FIXED_ROTATION) != 0;
-        bd.bullet = (d.flags & B2G_BD_BULLET) != 0;
-        bd.active = (d.flags & B2G_BD_ACTIVE) != 0;
-        bd.userData = (void*)(intptr_t)i;
-        rw->bodies.push_back(w->CreateBody(&bd));
-    }
-    for (int i = 0; i < s->fixtureCount; ++i) {
-        const b2g_fixture_def& d = s->fixtures[i];
-        b2FixtureDef fd;
-        fd.friction = d.friction;
-        fd.restitution = d.restitution;
-        fd.density = d.density;
-        fd.isSensor = d.isSensor != 0;
-        fd.filter.categoryBits = d.categoryBits;
-        fd.filter.maskBits = d.maskBits;
-        fd.filter.groupIndex = d.groupIndex;
-        fd.userData = (void*)(intptr_t)i;
-        b2Body* body = rw->bodies[d.body];
-        b2Fixture* f = nullptr;
-        const float* v = s->vertices;
-        switch (d.shapeType) {
-            case B2G_SHAPE_CIRCLE: {
-                b2CircleShape sh;
-                sh.m_p.Set(d.p[0], d.p[1]);
-                sh.m_radius = d.radius;
-                fd.shape = &sh;
-                f = body->CreateFixture(&fd);
-            } break;
-            case B2G_SHAPE_EDGE: {
-                b2EdgeShape sh;
-                sh.Set(b2Vec2(v[2 * d.firstVertex], v[2 * d.firstVertex + 1]),
-                       b2Vec2(v[2 * d.firstVertex + 2], v[2 * d.firstVertex + 3]));
-                if (d.hasVertex0) { sh.m_vertex0.Set(d.vertex0[0], d.vertex0[1]); sh.m_hasVertex0 = true; }
-                if (d.hasVertex3) { sh.m_vertex3.Set(d.vertex3[0], d.vertex3[1]); sh.m_hasVertex3 = true; }
-                fd.shape = &sh;
-                f = body->CreateFixture(&fd);
-            } break;
-            case B2G_SHAPE_POLYGON: {
-                b2PolygonShape sh;
-                build_polygon(sh, d, v);
-                fd.shape = &sh;
-                f = body->CreateFixture(&fd);
-            } break;
-            case B2G_SHAPE_CHAIN: {
-                b2ChainShape sh;
-                std::vector<b2Vec2> pts(d.vertexCount);
-                for (int k = 0; k < d.vertexCount; ++k) pts[k].Set(v[2 * (d.firstVertex + k)], v[2 * (d.firstVertex + k) + 1]);
-                if (d.shapeKind == B2G_CHAIN_LOOP) {
-                    sh.CreateLoop(pts.data(), d.vertexCount);
-                } else {
-                    sh.CreateChain(pts.data(), d.vertexCount);
-                    if (d.hasVertex0) sh.SetPrevVertex(b2Vec2(d.vertex0[0], d.vertex0[1]));
-                    if (d.hasVertex3) sh.SetNextVertex(b2Vec2(d.vertex3[0], d.vertex3[1]));
-                }
-                fd.shape = &sh;
-                f = body->CreateFixture(&fd);
-            } break;
-        }
-        rw->fixtures.push_back(f);
-        rw->childCounts.push_back(f->GetShape()->GetChildCount());
-    }
+    for (int i = 0; i < s->bodyCount; ++i) add_body(rw, s->bodies[i]);
+    for (int i = 0; i < s->fixtureCount; ++i) add_fixture(rw, rw->bodies[s->fixtures[i].body], s->fixtures[i], s->vertices);
     // b2World::CreateJoint in call order, from the same local-frame definitions the device path receives
     for (int i = 0; i < s->jointCount; ++i) {
         const b2g_joint_def& d = s->joints[i];
@@ -244,6 +256,15 @@ void ref_world_step(void* h, float dt, int velIters, int posIters) {
     RefWorld* rw = (RefWorld*)h;
     rw->recorder.events.clear();
     rw->world->Step(dt, velIters, posIters);
+}
+
+// b2World::CreateBody + b2Body::CreateFixture after the world has been stepped; returns the new body's index.
+int ref_world_create_body(void* h, const b2g_body_def* bd, const b2g_fixture_def* fds, int nf, const float* vertices) {
+    RefWorld* rw = (RefWorld*)h;
+    add_body(rw, *bd);
+    b2Body* body = rw->bodies.back();
+    for (int i = 0; i < nf; ++i) add_fixture(rw, body, fds[i], vertices);
+    return (int)rw->bodies.size() - 1;
 }
 
 // Between-step body edits, ops = B2GPU_CMD_* of include/b2gpu.h: the call a user of the reference makes on a b2Body.
@@ -403,30 +424,23 @@ int ref_world_get_contacts(void* h, int32_t* ints, float* floats, int cap) {
 
 // Fat AABBs per proxy: for each fixture (creation order), each child: 4 floats + proxyId.
 int ref_world_get_proxies(void* h, float* aabbs, int32_t* ids, int cap) {
+    // One row per proxy SLOT: slot k holds the proxy whose tree id is 0 (k = 0) or 2k - 1 (a leaf
+    // and its parent are allocated together, so leaf ids are the odd numbers; a destroyed proxy's id is reused by the
+    // next CreateProxy).  Rows of slots without a live proxy are zero with id -1.
     RefWorld* rw = (RefWorld*)h;
-    int n = 0;
     const b2BroadPhase& bp = rw->world->GetContactManager().m_broadPhase;
-    for (size_t fi = 0; fi < rw->fixtures.size(); ++fi) {
-        b2Fixture* f = rw->fixtures[fi];
-        int cc = f ? f->GetShape()->GetChildCount() : rw->childCounts[fi];
-        for (int k = 0; k < cc; ++k) {
-            if (!f) {  // proxy of a destroyed body: zeros
-                if (n < cap) { aabbs[4 * n] = aabbs[4 * n + 1] = aabbs[4 * n + 2] = aabbs[4 * n + 3] = 0.0f; ids[n] = -1; }
-                ++n;
-                continue;
-            }
-            // b2Fixture::m_proxies is private; the fat AABB is reachable through the proxy id,
-            // and ids are recoverable from GetAABB's owner only via friend access.  We use the
-            // public path: b2Fixture has no proxy-id getter in 2.3.2, so replicate the id rule
-            // (Appendix B.3 of SURVEY.md): k-th created proxy has id 0 (k = 0) or 2k-1.
-            int id = n == 0 ? 0 : 2 * n - 1;
-            if (n < cap) {
-                const b2AABB& a = bp.GetFatAABB(id);
-                aabbs[4 * n + 0] = a.lowerBound.x; aabbs[4 * n + 1] = a.lowerBound.y;
-                aabbs[4 * n + 2] = a.upperBound.x; aabbs[4 * n + 3] = a.upperBound.y;
-                ids[n] = id;
-            }
-            ++n;
+    int n = rw->proxySlots;
+    for (int i = 0; i < n && i < cap; ++i) { aabbs[4 * i] = aabbs[4 * i + 1] = aabbs[4 * i + 2] = aabbs[4 * i + 3] = 0.0f; ids[i] = -1; }
+    for (b2Fixture* f : rw->fixtures) {
+        if (!f) continue;
+        for (int k = 0; k < f->m_proxyCount; ++k) {
+            const int id = f->m_proxies[k].proxyId;
+            const int slot = id == 0 ? 0 : (id + 1) / 2;
+            if (slot >= cap) continue;
+            const b2AABB& a = bp.GetFatAABB(id);
+            aabbs[4 * slot + 0] = a.lowerBound.x; aabbs[4 * slot + 1] = a.lowerBound.y;
+            aabbs[4 * slot + 2] = a.upperBound.x; aabbs[4 * slot + 3] = a.upperBound.y;
+            ids[slot] = id;
         }
     }
     return n;

@@ -59,6 +59,9 @@ def lib(kind="ref"):
         L.ref_world_get_proxies.restype = C.c_int
         L.ref_world_get_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_world_get_events.restype = C.c_int
+        if kind == "ref":
+            L.ref_world_create_body.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.ref_world_create_body.restype = C.c_int
         L.ref_world_body_command.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
         L.ref_world_body_command.restype = None
         L.ref_polygon_build.argtypes = [C.POINTER(FixtureDef), C.c_void_p, C.c_void_p]
@@ -123,6 +126,13 @@ class RefWorld:
         if not self.L.ref_world_raycast_closest(self.h, _p(a), _p(b), _p(oi), _p(of)):
             return None
         return int(oi[0]), int(oi[1]), of[0], of[1:3].copy(), of[3:5].copy()
+
+    def create_body(self, body_def, fixture_defs, vertices):
+        """b2World::CreateBody + CreateFixture after stepping (live reference only); returns the body index."""
+        from box2dpp_b200.scene import FixtureDef
+        fds = (FixtureDef * max(len(fixture_defs), 1))(*fixture_defs)
+        v = np.ascontiguousarray(vertices if len(vertices) else [0.0, 0.0], np.float32)
+        return self.L.ref_world_create_body(self.h, C.byref(body_def), fds, len(fixture_defs), _p(v))
 
     def bodies(self) -> np.ndarray:
         """[nb,16] float32: xf.p(2) q.s q.c | c(2) a | v(2) w | awake mass I localCenter(2) pad."""

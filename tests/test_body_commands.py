@@ -157,3 +157,76 @@ def test_destroy_body_matches_reference(oracles):
     batch.body_commands(np.array([(w, dead, B.CMD_SET_AWAKE, 1, (0, 0), (0, 0))], dtype=B.BODY_COMMAND_DTYPE))
     assert batch.status()[w] == 4
     batch.close()
+
+
+def _spawn_def(rng, kind):
+    """(BodyDef, [FixtureDef], vertices) of one body to create mid-run, built through the Scene helpers."""
+    tmp = S.Scene()
+    b = tmp.create_body(S.DYNAMIC_BODY, (rng.uniform(-6.0, 6.0), rng.uniform(6.0, 11.0)), angle=rng.uniform(-1.0, 1.0),
+                        linear_velocity=(rng.uniform(-2.0, 2.0), rng.uniform(-3.0, 0.0)), angular_velocity=rng.uniform(-2.0, 2.0),
+                        flags=S.BD_DEFAULT | (S.BD_BULLET if kind == 3 else 0))
+    if kind == 0:
+        tmp.create_circle(b, rng.uniform(0.2, 0.5), density=1.0, restitution=0.1)
+    elif kind == 1:
+        tmp.create_box(b, rng.uniform(0.2, 0.5), rng.uniform(0.2, 0.5), density=2.0, friction=0.4)
+    elif kind == 2:  # two fixtures: a convex polygon and a sensor halo
+        n = 5
+        r = rng.uniform(0.3, 0.6)
+        tmp.create_polygon(b, [(float(np.float32(r * np.cos(2 * np.pi * j / n))), float(np.float32(r * np.sin(2 * np.pi * j / n)))) for j in range(n)], density=1.0)
+        tmp.create_circle(b, 1.0, sensor=True)
+    else:
+        tmp.create_box(b, 0.15, 0.15, density=6.0)
+    return tmp.bodies[0], list(tmp.fixtures), list(tmp.vertices)
+
+
+@pytest.mark.gpu
+def test_create_and_destroy_bodies_match_reference(oracles):
+    """b2World::CreateBody / CreateFixture and DestroyBody between steps (b2gpu_batch_create_bodies, B2GPU_CMD_DESTROY_BODY):
+    body indices, reused proxy ids (= pair order), e_newFixture's FindNewContacts at the next Step, mass data of the new
+    bodies — everything stays bit-identical to the reference."""
+    if not oracles.available("ref"):
+        pytest.skip("checked against the live reference")
+    scenes = [S.pyramid(4), S.mixed(2, bodies=10), S.jointed(1), S.hello_world(), S.pyramid(3, flags=NOCCD, jitter_seed=2),
+              S.sensors(1, bodies=6)] * 6  # 36 worlds
+    refs = [oracles.RefWorld(s, record_events=True) for s in scenes]
+    batch = B.WorldBatch(scenes, event_mask=B.EVENT_ALL, headroom=(24, 40, 40, 800, 0))
+    rng = S.LCG(4242)
+    alive = [list(range(s.body_count)) for s in scenes]
+    created = 0
+    for step in range(240):
+        if step % 7 == 3:
+            spawns, destroys = [], []
+            for w, r in enumerate(refs):
+                u = rng.next_u()
+                if u < 0.45:  # create one or two bodies
+                    for _ in range(1 + int(rng.next_u() * 2) % 2):
+                        bd, fds, verts = _spawn_def(rng, int(rng.next_u() * 4) % 4)
+                        idx = r.create_body(bd, fds, verts)
+                        spawns.append((w, bd, fds, verts, idx))
+                elif u < 0.75 and len(alive[w]) > 2:  # destroy a dynamic body (possibly one that was created mid-run)
+                    pick = alive[w][1 + int(rng.next_u() * (len(alive[w]) - 1)) % (len(alive[w]) - 1)]
+                    alive[w].remove(pick)
+                    r.command(pick, B.CMD_DESTROY_BODY)
+                    destroys.append((w, pick, B.CMD_DESTROY_BODY, 0, (0, 0), (0, 0)))
+            if destroys:
+                batch.body_commands(np.array(destroys, dtype=B.BODY_COMMAND_DTYPE))
+            if spawns:
+                got = batch.create_bodies([(w, bd, fds, verts) for (w, bd, fds, verts, _) in spawns])
+                assert got.tolist() == [idx for (*_, idx) in spawns]
+                for (w, *_, idx) in spawns:
+                    alive[w].append(idx)
+                created += len(spawns)
+            for w, r in enumerate(refs):
+                compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} after edits at step {step}")
+        for r in refs:
+            r.step(1 / 60, 8, 3)
+        batch.step(1 / 60, 8, 3)
+        for w, r in enumerate(refs):
+            compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} step {step}")
+    assert created > 150 and (batch.status() == 0).all()
+    # a world without headroom reports the overflow instead of corrupting its arenas
+    small = B.WorldBatch([S.hello_world()])
+    bd, fds, verts = _spawn_def(S.LCG(1), 1)
+    assert small.create_bodies([(0, bd, fds, verts)]).tolist() == [-1] and small.status()[0] == 8
+    small.close()
+    batch.close()
