@@ -438,6 +438,10 @@ public:
 
     // Per-world capacity overrides for the device arenas (0 = derived from the scenes); call before the first Step.
     void SetCapacities(int32_t maxContacts, int32_t maxEvents) { m_maxContacts = maxContacts; m_maxEvents = maxEvents; }
+    // Room per world for bodies created after the first Step (b2World::CreateBody on a running world); before the first Step.
+    void SetSpawnHeadroom(int32_t bodies, int32_t fixtures, int32_t proxies, int32_t shapeWords, int32_t chainVertices) {
+        m_headroom[0] = bodies; m_headroom[1] = fixtures; m_headroom[2] = proxies; m_headroom[3] = shapeWords; m_headroom[4] = chainVertices;
+    }
     void SetContactListener(b2ContactListener* listener) {
         if (m_handle && listener && !m_eventMask) throw std::runtime_error("SetContactListener must precede the first Step");
         m_listener = listener;
@@ -504,6 +508,10 @@ private:
         m_eventMask = m_listener ? 15 : 0;
         desc.eventMask = m_eventMask;
         Check(b2gpu_scene_capacities(scenes.data(), desc.numWorlds, &desc));
+        desc.maxBodies += m_headroom[0]; desc.maxFixtures += m_headroom[1]; desc.maxProxies += m_headroom[2];
+        desc.maxShapeWords += m_headroom[3]; desc.maxChainVerts += m_headroom[4];
+        if (m_headroom[2] > 0 && m_maxContacts == 0) desc.maxContacts += 4 * m_headroom[2];
+        if (desc.eventMask && m_maxEvents == 0 && desc.maxEvents < 3 * desc.maxContacts) desc.maxEvents = 3 * desc.maxContacts;
         Check(b2gpu_batch_create(&desc, &m_handle));
         int rc = b2gpu_batch_build_worlds(m_handle, scenes.data(), desc.numWorlds, 0, 1);
         if (rc != B2GPU_OK) {
@@ -516,10 +524,24 @@ private:
         m_maxEventsBuilt = desc.maxEvents;
     }
     void Queue(const b2Body* b, int32_t op, bool wake, float vx, float vy, float px, float py);
-    void Flush() {  // queued body edits -> device, in call order per world
+    void Flush() {  // queued body edits and bodies created on the running worlds -> device, in call order
+        FlushCommands();
+        FlushSpawns();
+    }
+    void FlushCommands() {
         if (m_commands.empty()) return;
         Check(b2gpu_batch_body_commands(m_handle, m_commands.data(), (int64_t)m_commands.size()));
         m_commands.clear();
+        m_stateValid = false;
+    }
+    void FlushSpawns() {  // b2World::CreateBody / b2Body::CreateFixture calls made after the first Step
+        if (m_spawns.empty()) return;
+        std::vector<int32_t> idx(m_spawns.size());
+        Check(b2gpu_batch_create_bodies(m_handle, m_spawns.data(), (int32_t)m_spawns.size(), m_spawnFixtures.data(),
+                                        m_spawnVertices.data(), idx.data()));
+        for (size_t i = 0; i < m_spawns.size(); ++i)
+            if (idx[i] != m_spawnBodies[i]->GetIndex()) throw std::runtime_error("b2gpu: a world's arenas are full (SetSpawnHeadroom)");
+        m_spawns.clear(); m_spawnFixtures.clear(); m_spawnVertices.clear(); m_spawnBodies.clear();
         m_stateValid = false;
     }
     void Refresh() {  // lazy readback of body state after a Step
@@ -571,6 +593,13 @@ private:
     bool m_stateValid = false;
     std::vector<float> m_xf, m_sweep, m_vel;
     std::vector<b2gpu_body_command> m_commands;
+    int32_t m_headroom[5] = {0, 0, 0, 0, 0};
+    // bodies created after the first Step, not yet on the device (only commands OR spawns are pending at any time, so
+    // that the device sees creations and edits in call order)
+    std::vector<b2gpu_spawn> m_spawns;
+    std::vector<b2g_fixture_def> m_spawnFixtures;
+    std::vector<float> m_spawnVertices;
+    std::vector<b2Body*> m_spawnBodies;
     std::vector<int64_t> m_eventOffsets;
     std::vector<b2gpu_event> m_events;
     std::vector<int32_t> m_bodyFlags;
@@ -596,7 +625,7 @@ inline bool b2World::IsLocked() const { return m_batch->IsBuilt(); }
 inline int32_t b2World::GetBodyCount() const { return (int32_t)(m_owned ? m_owned->World(0) : *this).m_bodies.size(); }
 inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
     b2World& w = B2_SELF;
-    if (w.m_batch->IsBuilt()) return nullptr;  // like a locked world (b2World.cpp:100-104)
+    const bool running = w.m_batch->IsBuilt();  // the world has been stepped: the body goes to the device at the next flush
     b2g_body_def d;
     std::memset(&d, 0, sizeof(d));
     d.type = (int32_t)def->type;
@@ -617,6 +646,17 @@ inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
     b->m_type = def->type;
     b->m_userData = def->userData;
     w.m_bodies.push_back(std::move(b));
+    if (running) {
+        b2WorldBatch* B = w.m_batch;
+        B->FlushCommands();  // edits made before this creation come first
+        b2gpu_spawn sp;
+        std::memset(&sp, 0, sizeof(sp));
+        sp.world = w.m_index;
+        sp.firstFixture = (int32_t)B->m_spawnFixtures.size();
+        sp.body = d;
+        B->m_spawns.push_back(sp);
+        B->m_spawnBodies.push_back(w.m_bodies.back().get());
+    }
     return w.m_bodies.back().get();
 }
 inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
@@ -691,7 +731,12 @@ inline int32_t b2World::GetContactCount() const {
 
 inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
     b2World& w = *m_world;
-    if (w.m_batch->IsBuilt() || !def->shape) return nullptr;
+    if (!def->shape) return nullptr;
+    b2WorldBatch* B = w.m_batch;
+    const bool running = B->IsBuilt();
+    // on a running world fixtures can only be given to the body created last (before anything else was queued):
+    // b2gpu_batch_create_bodies takes a body with its fixtures in one record
+    if (running && (B->m_spawnBodies.empty() || B->m_spawnBodies.back() != this)) return nullptr;
     b2g_fixture_def fd;
     std::memset(&fd, 0, sizeof(fd));
     fd.body = m_index;
@@ -702,8 +747,14 @@ inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
     fd.categoryBits = def->filter.categoryBits;
     fd.maskBits = def->filter.maskBits;
     fd.groupIndex = def->filter.groupIndex;
-    def->shape->Describe(fd, w.m_vertices);
-    w.m_fixtureDefs.push_back(fd);
+    if (running) {
+        def->shape->Describe(fd, B->m_spawnVertices);
+        B->m_spawnFixtures.push_back(fd);
+        B->m_spawns.back().fixtureCount += 1;
+    } else {
+        def->shape->Describe(fd, w.m_vertices);
+        w.m_fixtureDefs.push_back(fd);
+    }
     std::unique_ptr<b2Fixture> f(new b2Fixture);
     f->m_body = this;
     f->m_userData = def->userData;
@@ -818,6 +869,7 @@ inline void b2DistanceJointDef::Initialize(b2Body* b1, b2Body* b2, const b2Vec<f
 
 inline void b2WorldBatch::Queue(const b2Body* b, int32_t op, bool wake, float vx, float vy, float px, float py) {
     Build();
+    FlushSpawns();  // a body created earlier must exist before an edit that follows it
     b2gpu_body_command c;
     c.world = b->m_world->m_index;
     c.body = b->m_index;

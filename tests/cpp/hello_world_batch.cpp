@@ -55,7 +55,6 @@ static int hello() {
         std::printf("%08x %08x %08x %08x %08x %08x\n", bits(position[b2VecX]), bits(position[b2VecY]), bits(angle),
                     bits(v[b2VecX]), bits(v[b2VecY]), bits(body->GetAngularVelocity()));
     }
-    if (world.CreateBody(&bodyDef) != nullptr) return 2;  // a stepped world is frozen, like a locked b2World
     return world.GetBodyCount() == 2 && world.GetProxyCount() == 2 ? 0 : 3;
 }
 
@@ -222,10 +221,73 @@ static int joints(int steps) {
     return 0;
 }
 
+// Bodies created and destroyed on a running world through the reference's API (a game server spawning and despawning):
+// b2World::CreateBody / b2Body::CreateFixture after Steps, b2World::DestroyBody, and again CreateBody (proxy ids reused).
+static int spawn(int steps) {
+    b2WorldBatch worlds(b2Vec<float, 2>{{0.0f, -10.0f}}, 2);
+    worlds.SetSpawnHeadroom(8, 8, 8, 200, 0);
+    std::vector<std::vector<b2Body*>> bodies(2);
+    for (int w = 0; w < 2; ++w) {
+        b2BodyDef gd;
+        b2Body* ground = worlds[w].CreateBody(&gd);
+        b2PolygonShape gs;
+        gs.SetAsBox(20.0f, 1.0f, b2Vec<float, 2>{{0.0f, -1.0f}}, 0.0f);
+        ground->CreateFixture(&gs, 0.0f);
+        bodies[w].push_back(ground);
+        b2BodyDef bd;
+        bd.type = b2BodyType::DYNAMIC_BODY;
+        bd.position = b2Vec<float, 2>{{0.0f, 2.0f + w}};
+        b2Body* box = worlds[w].CreateBody(&bd);
+        b2PolygonShape bs;
+        bs.SetAsBox(0.5f, 0.5f);
+        box->CreateFixture(&bs, 1.0f);
+        bodies[w].push_back(box);
+    }
+    for (int s = 0; s < steps; ++s) {
+        for (int w = 0; w < 2; ++w) {
+            if (s % 20 == 10 && bodies[w].size() < 8) {  // spawn: alternately a box and a ball, above the pile
+                b2BodyDef bd;
+                bd.type = b2BodyType::DYNAMIC_BODY;
+                bd.position = b2Vec<float, 2>{{0.3f * (s / 20) - 0.4f * w, 5.0f}};
+                bd.angle = 0.1f * (s / 20);
+                b2Body* nb = worlds[w].CreateBody(&bd);
+                if ((s / 20) % 2 == 0) {
+                    b2PolygonShape bs;
+                    bs.SetAsBox(0.4f, 0.3f);
+                    b2FixtureDef fd;
+                    fd.shape = &bs; fd.density = 2.0f; fd.friction = 0.5f;
+                    nb->CreateFixture(&fd);
+                } else {
+                    b2CircleShape cs;
+                    cs.SetRadius(0.35f);
+                    nb->CreateFixture(&cs, 1.5f);
+                }
+                nb->ApplyLinearImpulse(b2Vec<float, 2>{{0.5f, 0.0f}}, b2Vec<float, 2>{{bd.position[0], 5.1f}}, true);
+                bodies[w].push_back(nb);
+            }
+            if (s == 55 + 20 * w) {  // despawn the first box; its proxy id goes to the next spawned body
+                worlds[w].DestroyBody(bodies[w][1]);
+                bodies[w][1] = nullptr;
+            }
+        }
+        worlds.Step(1.0f / 60.0f, 8, 3);
+    }
+    if (worlds.GetStatus() != 0) return 4;
+    for (int w = 0; w < 2; ++w)
+        for (size_t i = 0; i < bodies[w].size(); ++i) {
+            b2Body* b = bodies[w][i];
+            if (!b) { std::printf("%d %zu dead\n", w, i); continue; }
+            b2Vec<float, 2> p = b->GetPosition();
+            std::printf("%d %zu %08x %08x %08x\n", w, i, bits(p[0]), bits(p[1]), bits(b->GetAngle()));
+        }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     try {
         if (argc >= 2 && std::strcmp(argv[1], "batch") == 0)
             return batch(argc > 2 ? std::atoi(argv[2]) : 3, argc > 3 ? std::atoi(argv[3]) : 4, argc > 4 ? std::atoi(argv[4]) : 120);
+        if (argc >= 2 && std::strcmp(argv[1], "spawn") == 0) return spawn(argc > 2 ? std::atoi(argv[2]) : 160);
         if (argc >= 2 && std::strcmp(argv[1], "joints") == 0) return joints(argc > 2 ? std::atoi(argv[2]) : 200);
         if (argc >= 2 && std::strcmp(argv[1], "edits") == 0)
             return edits(argc > 2 ? std::atoi(argv[2]) : 3, argc > 3 ? std::atoi(argv[3]) : 150);

@@ -164,3 +164,52 @@ def test_joints_through_cpp_api(exe, oracles):
     for i, b in enumerate((cart, pole, bob)):
         want = [int(np.float32(v).view(np.uint32)) for v in (rb[b, 0], rb[b, 1], rb[b, 6])]
         assert got[i] == want, f"body {b}: {got[i]} vs {want}"
+
+
+@pytest.mark.gpu
+def test_spawn_and_despawn_through_cpp_api(exe, oracles):
+    """b2World::CreateBody / b2Body::CreateFixture / b2World::DestroyBody on running worlds through the C++ mirror
+    (reference defaults): every surviving body's state equals the reference's after 160 steps."""
+    if not oracles.available("ref"):
+        pytest.skip("checked against the live reference")
+    from box2dpp_b200 import batch as B
+    steps = 160
+    r = subprocess.run([exe, "spawn", str(steps)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = {}
+    for line in r.stdout.strip().splitlines():
+        f = line.split()
+        got[(int(f[0]), int(f[1]))] = None if f[2] == "dead" else [int(x, 16) for x in f[2:5]]
+    f32 = lambda x: float(np.float32(x))  # noqa: E731
+    for w in range(2):
+        s = S.Scene()
+        g = s.create_body(S.STATIC_BODY)
+        s.create_box(g, 20.0, 1.0, center=(0.0, -1.0), angle=0.0)
+        b = s.create_body(S.DYNAMIC_BODY, (0.0, 2.0 + w))
+        s.create_box(b, 0.5, 0.5, density=1.0)
+        ref = oracles.RefWorld(s)
+        count = 2
+        for st in range(steps):
+            if st % 20 == 10 and count < 8:
+                k = st // 20
+                tmp = S.Scene()
+                px = f32(f32(0.3) * np.float32(k) - f32(0.4) * np.float32(w))
+                nb = tmp.create_body(S.DYNAMIC_BODY, (px, 5.0), angle=f32(f32(0.1) * np.float32(k)))
+                if k % 2 == 0:
+                    tmp.create_box(nb, 0.4, 0.3, density=2.0, friction=0.5)
+                else:
+                    tmp.create_circle(nb, 0.35, density=1.5)
+                idx = ref.create_body(tmp.bodies[0], list(tmp.fixtures), list(tmp.vertices))
+                ref.command(idx, B.CMD_APPLY_LINEAR_IMPULSE, 1, (0.5, 0.0), (px, f32(5.1)))
+                count += 1
+            if st == 55 + 20 * w:
+                ref.command(1, B.CMD_DESTROY_BODY)
+            ref.step(1.0 / 60.0, 8, 3)
+        rb = ref.bodies()
+        assert rb.shape[0] == count
+        for i in range(count):
+            if rb[i, 15] == 1.0:
+                assert got[(w, i)] is None
+                continue
+            want = [int(np.float32(v).view(np.uint32)) for v in (rb[i, 0], rb[i, 1], rb[i, 6])]
+            assert got[(w, i)] == want, f"world {w} body {i}: {got[(w, i)]} vs {want}"
