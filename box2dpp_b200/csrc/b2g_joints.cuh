@@ -1,4 +1,4 @@
-// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel and weld joints.
+// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel, weld, rope and friction joints.
 //
 // Reference (vanilla twin Regression/box2d-ref/Box2DRef/Dynamics/Joints; the fork's files are
 // Box2D/Dynamics/Joints/b2RevoluteJoint.cpp, b2PrismaticJoint.cpp, b2DistanceJoint.cpp, same line structure):
@@ -198,6 +198,56 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
         c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
         c.jTmp[t + 1] = make_float4(u.x, u.y, mass, gamma);
         c.jTmp[t + 2] = make_float4(bias, 0.0f, 0.0f, 0.0f);
+    } else if (type == B2G_JOINT_ROPE) {  // b2RopeJoint.cpp:59-133; f1.x = maxLength
+        Vec2 u = cB + rB - cA - rA;
+        const float length = Length(u);
+        c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
+        if (length > kLinearSlop) {
+            u = Div(1.0f, length) * u;
+        } else {  // degenerate rope: no constraint this step (the reference returns before touching the velocities)
+            c.jTmp[t + 1] = make_float4(0.0f, 0.0f, 0.0f, length);
+            imp.x = 0.0f;
+            c.jImp[j] = imp;
+            return;
+        }
+        const float crA = Cross(rA, u), crB = Cross(rB, u);
+        const float invMass = mA + iA * crA * crA + mB + iB * crB * crB;
+        const float mass = invMass != 0.0f ? Div(1.0f, invMass) : 0.0f;
+        if (warmStarting) {
+            imp.x *= dtRatio;
+            const Vec2 P = imp.x * u;
+            vA = vA - mA * P;
+            wA -= iA * Cross(rA, P);
+            vB = vB + mB * P;
+            wB += iB * Cross(rB, P);
+        } else {
+            imp.x = 0.0f;
+        }
+        c.jTmp[t + 1] = make_float4(u.x, u.y, mass, length);
+    } else if (type == B2G_JOINT_FRICTION) {  // b2FrictionJoint.cpp:63-128; f1 = maxForce, maxTorque; jImp = linear.xy, angular
+        const float k11 = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+        const float k12 = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+        const float k22 = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+        // b2Mat22::GetInverse (b2Math.h:226-238) with a = ex.x, b = ey.x, c = ex.y, d = ey.y
+        float det = k11 * k22 - k12 * k12;
+        if (det != 0.0f) det = Div(1.0f, det);
+        const float lmxx = det * k22, lmyx = -det * k12, lmxy = -det * k12, lmyy = det * k11;  // ex.x, ey.x, ex.y, ey.y
+        float angularMass = iA + iB;
+        if (angularMass > 0.0f) angularMass = Div(1.0f, angularMass);
+        if (warmStarting) {
+            imp.x *= dtRatio; imp.y *= dtRatio;
+            imp.z *= dtRatio;
+            const Vec2 P = V2(imp.x, imp.y);
+            vA = vA - mA * P;
+            wA -= iA * (Cross(rA, P) + imp.z);
+            vB = vB + mB * P;
+            wB += iB * (Cross(rB, P) + imp.z);
+        } else {
+            imp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
+        c.jTmp[t + 1] = make_float4(lmxx, lmyx, lmxy, lmyy);
+        c.jTmp[t + 2] = make_float4(angularMass, 0.0f, 0.0f, 0.0f);
     } else if (type == B2G_JOINT_WHEEL) {  // b2WheelJoint.cpp:79-199
         // jImp: m_impulse, m_springImpulse, -, m_motorImpulse.  f1: frequencyHz, dampingRatio, -, maxMotorTorque
         const Vec2 d = cB + rB - cA - rA;
@@ -466,6 +516,56 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
         wA -= iA * Cross(rA, P);
         vB = vB + mB * P;
         wB += iB * Cross(rB, P);
+    } else if (type == B2G_JOINT_ROPE) {  // b2RopeJoint.cpp:135-169
+        const float4 f1 = c.jF1[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1];
+        const Vec2 rA = V2(t0.x, t0.y), rB = V2(t0.z, t0.w), u = V2(t1.x, t1.y);
+        const Vec2 vpA = vA + Cross(wA, rA);
+        const Vec2 vpB = vB + Cross(wB, rB);
+        const float C = t1.w - f1.x;
+        float Cdot = Dot(u, vpB - vpA);
+        if (C < 0.0f) Cdot += Div(1.0f, h) * C;  // predictive constraint: data.step.inv_dt * C
+        float impulse = -t1.z * Cdot;
+        const float oldImpulse = imp.x;
+        imp.x = Min(0.0f, imp.x + impulse);
+        impulse = imp.x - oldImpulse;
+        const Vec2 P = impulse * u;
+        vA = vA - mA * P;
+        wA -= iA * Cross(rA, P);
+        vB = vB + mB * P;
+        wB += iB * Cross(rB, P);
+    } else if (type == B2G_JOINT_FRICTION) {  // b2FrictionJoint.cpp:130-186
+        const float4 f1 = c.jF1[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2];
+        const Vec2 rA = V2(t0.x, t0.y), rB = V2(t0.z, t0.w);
+        {  // angular friction
+            const float Cdot = wB - wA;
+            float impulse = -t2.x * Cdot;
+            const float oldImpulse = imp.z;
+            const float maxImpulse = h * f1.y;
+            imp.z = Clamp(imp.z + impulse, -maxImpulse, maxImpulse);
+            impulse = imp.z - oldImpulse;
+            wA -= iA * impulse;
+            wB += iB * impulse;
+        }
+        {  // linear friction
+            const Vec2 Cdot = vB + Cross(wB, rB) - vA - Cross(wA, rA);
+            Vec2 impulse = -V2(t1.x * Cdot.x + t1.y * Cdot.y, t1.z * Cdot.x + t1.w * Cdot.y);  // -b2Mul(m_linearMass, Cdot)
+            const Vec2 oldImpulse = V2(imp.x, imp.y);
+            Vec2 li = oldImpulse + impulse;
+            const float maxImpulse = h * f1.x;
+            if (Dot(li, li) > maxImpulse * maxImpulse) {
+                Normalize(li);
+                li = maxImpulse * li;  // b2Vec2::operator*=(float): x *= a
+            }
+            imp.x = li.x;
+            imp.y = li.y;
+            impulse = li - oldImpulse;
+            vA = vA - mA * impulse;
+            wA -= iA * Cross(rA, impulse);
+            vB = vB + mB * impulse;
+            wB += iB * Cross(rB, impulse);
+        }
     } else if (type == B2G_JOINT_WHEEL) {  // b2WheelJoint.cpp:201-261
         const float4 f1 = c.jF1[j], f2 = c.jF2[j];
         const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2], t3 = c.jTmp[t + 3];
@@ -674,6 +774,23 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
         cB = cB + mB * P;
         aB += iB * Cross(rB, P);
         okay = Abs(C) < kLinearSlop;
+    } else if (type == B2G_JOINT_ROPE) {  // b2RopeJoint.cpp:171-206
+        const float mass = c.jTmp[(size_t)j * kJointTmp + 1].z;
+        const Rot qA = MakeRot(aA), qB = MakeRot(aB);
+        const Vec2 rA = Mul(qA, lA), rB = Mul(qB, lB);
+        Vec2 u = cB + rB - cA - rA;
+        const float length = Normalize(u);
+        float C = length - f1.x;
+        C = Clamp(C, 0.0f, kMaxLinearCorrection);
+        const float impulse = -mass * C;
+        const Vec2 P = impulse * u;
+        cA = cA - mA * P;
+        aA -= iA * Cross(rA, P);
+        cB = cB + mB * P;
+        aB += iB * Cross(rB, P);
+        okay = length - f1.x < kLinearSlop;
+    } else if (type == B2G_JOINT_FRICTION) {  // b2FrictionJoint.cpp:188-193: no position correction
+        return true;
     } else if (type == B2G_JOINT_WHEEL) {  // b2WheelJoint.cpp:263-312
         const float4 f2 = c.jF2[j];
         const float4 t1 = c.jTmp[(size_t)j * kJointTmp + 1];

@@ -264,6 +264,17 @@ struct b2WeldJointDef : public b2JointDef {
     b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}};
     float referenceAngle = 0.0f, frequencyHz = 0.0f, dampingRatio = 0.0f;
 };
+struct b2RopeJointDef : public b2JointDef {  // Dynamics/Joints/b2RopeJoint.h:28-52
+    b2RopeJointDef() { type = b2JointType::ROPE_JOINT; }
+    b2Vec<float, 2> localAnchorA{{-1.0f, 0.0f}}, localAnchorB{{1.0f, 0.0f}};
+    float maxLength = 0.0f;
+};
+struct b2FrictionJointDef : public b2JointDef {  // Dynamics/Joints/b2FrictionJoint.h:27-56
+    b2FrictionJointDef() { type = b2JointType::FRICTION_JOINT; }
+    void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec<float, 2>& anchor);
+    b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}};
+    float maxForce = 0.0f, maxTorque = 0.0f;
+};
 class b2Joint {
 public:
     b2JointType GetType() const { return m_type; }
@@ -374,7 +385,7 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
-    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel and weld joints; nullptr for the
+    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel, weld, rope and friction joints; nullptr for the
     // joint types outside the device path and once the world is locked (after the first Step)
     b2Joint* CreateJoint(const b2JointDef* def);
     // b2World::DestroyBody (b2World.cpp:124-203): queued like the b2Body edits; the body's joints, contacts and proxies go
@@ -693,6 +704,16 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
         set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB); set2(d.localAxisA, r->localAxisA);
         d.enableMotor = r->enableMotor; d.maxMotor = r->maxMotorTorque; d.motorSpeed = r->motorSpeed;
         d.frequencyHz = r->frequencyHz; d.dampingRatio = r->dampingRatio;
+    } else if (def->type == b2JointType::ROPE_JOINT) {
+        const b2RopeJointDef* r = static_cast<const b2RopeJointDef*>(def);
+        d.type = B2G_JOINT_ROPE;
+        set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB);
+        d.length = r->maxLength;
+    } else if (def->type == b2JointType::FRICTION_JOINT) {
+        const b2FrictionJointDef* r = static_cast<const b2FrictionJointDef*>(def);
+        d.type = B2G_JOINT_FRICTION;
+        set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB);
+        d.length = r->maxForce; d.maxMotor = r->maxTorque;
     } else if (def->type == b2JointType::WELD_JOINT) {
         const b2WeldJointDef* r = static_cast<const b2WeldJointDef*>(def);
         d.type = B2G_JOINT_WELD;
@@ -852,6 +873,11 @@ inline void b2WheelJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<floa
     localAnchorA = bodyA->GetLocalPoint(anchor);
     localAnchorB = bodyB->GetLocalPoint(anchor);
     localAxisA = bodyA->GetLocalVector(axis);
+}
+inline void b2FrictionJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& anchor) {
+    bodyA = bA; bodyB = bB;
+    localAnchorA = bodyA->GetLocalPoint(anchor);
+    localAnchorB = bodyB->GetLocalPoint(anchor);
 }
 inline void b2WeldJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& anchor) {
     bodyA = bA; bodyB = bB;

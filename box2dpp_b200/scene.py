@@ -63,7 +63,7 @@ class FixtureDef(C.Structure):
     ]
 
 
-JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WHEEL, JOINT_WELD = 1, 2, 3, 7, 8
+JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WHEEL, JOINT_WELD, JOINT_FRICTION, JOINT_ROPE = 1, 2, 3, 7, 8, 9, 10
 
 
 class JointDef(C.Structure):
@@ -185,6 +185,22 @@ class Scene:
         jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor)
         jd.referenceAngle = float(F32(self.bodies[body_b].angle) - F32(self.bodies[body_a].angle))
         jd.frequencyHz, jd.dampingRatio = frequency_hz, damping_ratio
+        return len(self.joints) - 1
+
+    def create_rope_joint(self, body_a, body_b, anchor_a, anchor_b, max_length, collide_connected=False) -> int:
+        """b2RopeJointDef (b2RopeJoint.h:28-52): local anchors from world points, maxLength."""
+        jd = self._joint(JOINT_ROPE, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor_a)
+        jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor_b)
+        jd.length = max_length
+        return len(self.joints) - 1
+
+    def create_friction_joint(self, body_a, body_b, anchor, max_force, max_torque, collide_connected=False) -> int:
+        """b2FrictionJointDef::Initialize(bodyA, bodyB, anchor) (b2FrictionJoint.cpp:36-42) + maxForce / maxTorque."""
+        jd = self._joint(JOINT_FRICTION, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor)
+        jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor)
+        jd.length, jd.maxMotor = max_force, max_torque
         return len(self.joints) - 1
 
     def create_distance_joint(self, body_a, body_b, anchor_a, anchor_b, frequency_hz=0.0, damping_ratio=0.0,
@@ -551,7 +567,8 @@ def jointed(seed: int, flags=WORLD_DEFAULT) -> Scene:
 def vehicles(seed: int, flags=WORLD_DEFAULT) -> Scene:
     """Wheel and weld joints: a car (chassis + two wheels on b2WheelJoint springs, the rear one
     motorised) driving over bumpy chain terrain towards a cantilever of planks held by weld joints (rigid and soft),
-    plus a welded compound that tumbles down.  All randomness from LCG(seed)."""
+    plus a welded compound that tumbles down, a weight on a rope joint and a puck slowed by a friction joint.
+    All randomness from LCG(seed)."""
     rng = LCG(seed)
     s = Scene((0.0, -10.0), flags)
     g = s.create_body(STATIC_BODY, (0.0, 0.0))
@@ -580,6 +597,13 @@ def vehicles(seed: int, flags=WORLD_DEFAULT) -> Scene:
     b = s.create_body(DYNAMIC_BODY, (2.9, 6.0))
     s.create_circle(b, 0.35, density=1.0)
     s.create_weld_joint(a, b, (2.6, 6.0))
+    # ---- a weight on a rope (slack at first, then taut) and a puck held by a friction joint against the ground ----
+    wgt = s.create_body(DYNAMIC_BODY, (-26.0 + rng.uniform(0.0, 0.5), 9.0))
+    s.create_box(wgt, 0.3, 0.3, density=4.0)
+    s.create_rope_joint(g, wgt, (-27.0, 12.0), (float(F32(s.bodies[wgt].position[0])), 9.0), max_length=4.5)
+    puck = s.create_body(DYNAMIC_BODY, (-24.0, 3.0), linear_velocity=(rng.uniform(3.0, 6.0), 2.0), angular_velocity=5.0, gravity_scale=0.0)
+    s.create_circle(puck, 0.3, density=1.0)
+    s.create_friction_joint(g, puck, (-24.0, 3.0), max_force=rng.uniform(1.0, 3.0), max_torque=0.4)
     c2 = s.create_body(DYNAMIC_BODY, (2.0, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)
     s.create_box(c2, 0.3, 0.3, density=1.0)
     d2 = s.create_body(DYNAMIC_BODY, (2.6, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)

@@ -145,7 +145,8 @@ enum {
     B2GPU_F_JOINT_F1,           /* [W][NJ][4]  revolute / prismatic: referenceAngle, lower, upper, maxMotorTorque|Force;
                                                distance: length, frequencyHz, dampingRatio, 0;
                                                wheel: frequencyHz, dampingRatio, 0, maxMotorTorque;
-                                               weld: referenceAngle, frequencyHz, dampingRatio, 0 */
+                                               weld: referenceAngle, frequencyHz, dampingRatio, 0;
+                                               rope: maxLength; friction: maxForce, maxTorque */
     B2GPU_F_JOINT_F2,           /* [W][NJ][4]  motorSpeed, localXAxisA.xy (normalised), 0 */
     B2GPU_F_JOINT_IMPULSE,      /* [W][NJ][4]  m_impulse.xyz, m_motorImpulse (warm-starting state);
                                                wheel: m_impulse, m_springImpulse, 0, m_motorImpulse */

@@ -218,6 +218,20 @@ RefWorld* build_world(const b2g_scene* s) {
             jd.enableMotor = d.enableMotor != 0; jd.maxMotorTorque = d.maxMotor; jd.motorSpeed = d.motorSpeed;
             jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
             w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_ROPE) {
+            b2RopeJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.maxLength = d.length;
+            w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_FRICTION) {
+            b2FrictionJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.maxForce = d.length; jd.maxTorque = d.maxMotor;
+            w->CreateJoint(&jd);
         } else if (d.type == B2G_JOINT_WELD) {
             b2WeldJointDef jd;
             jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
