@@ -503,8 +503,9 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
     for (int j = 0; j < nj; ++j) {
         const b2g_joint_def& d = s.joints[j];
         if (d.type != B2G_JOINT_REVOLUTE && d.type != B2G_JOINT_PRISMATIC && d.type != B2G_JOINT_DISTANCE &&
-            d.type != B2G_JOINT_WHEEL && d.type != B2G_JOINT_WELD && d.type != B2G_JOINT_ROPE && d.type != B2G_JOINT_FRICTION) {
-            err = "joint type outside the device path (revolute, prismatic, distance, wheel, weld, rope and friction joints are built)";
+            d.type != B2G_JOINT_WHEEL && d.type != B2G_JOINT_WELD && d.type != B2G_JOINT_ROPE && d.type != B2G_JOINT_FRICTION &&
+            d.type != B2G_JOINT_MOTOR) {
+            err = "joint type outside the device path (revolute, prismatic, distance, wheel, weld, rope, friction and motor joints are built)";
             return B2GPU_ERR_UNSUPPORTED;
         }
         if (d.bodyA < 0 || d.bodyA >= nb || d.bodyB < 0 || d.bodyB >= nb || d.bodyA == d.bodyB) {
@@ -526,6 +527,8 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
             put(F1, o, d.length); put(F1, o + 1, 0.0f); put(F1, o + 2, 0.0f); put(F1, o + 3, 0.0f);
         } else if (d.type == B2G_JOINT_FRICTION) {
             put(F1, o, d.length); put(F1, o + 1, d.maxMotor); put(F1, o + 2, 0.0f); put(F1, o + 3, 0.0f);
+        } else if (d.type == B2G_JOINT_MOTOR) {
+            put(F1, o, d.length); put(F1, o + 1, d.maxMotor); put(F1, o + 2, d.referenceAngle); put(F1, o + 3, d.frequencyHz);
         } else if (d.type == B2G_JOINT_WHEEL) {
             put(F1, o, d.frequencyHz); put(F1, o + 1, d.dampingRatio); put(F1, o + 2, 0.0f); put(F1, o + 3, d.maxMotor);
         } else if (d.type == B2G_JOINT_WELD) {

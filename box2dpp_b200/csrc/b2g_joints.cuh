@@ -1,4 +1,4 @@
-// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel, weld, rope and friction joints.
+// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel, weld, rope, friction and motor joints.
 //
 // Reference (vanilla twin Regression/box2d-ref/Box2DRef/Dynamics/Joints; the fork's files are
 // Box2D/Dynamics/Joints/b2RevoluteJoint.cpp, b2PrismaticJoint.cpp, b2DistanceJoint.cpp, same line structure):
@@ -198,6 +198,32 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
         c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
         c.jTmp[t + 1] = make_float4(u.x, u.y, mass, gamma);
         c.jTmp[t + 2] = make_float4(bias, 0.0f, 0.0f, 0.0f);
+    } else if (type == B2G_JOINT_MOTOR) {  // b2MotorJoint.cpp:61-133; f0.xy = linearOffset, f1 = maxForce, maxTorque, angularOffset, correctionFactor
+        const Vec2 mrA = Mul(qA, -V2(msA.z, msA.w)), mrB = Mul(qB, -V2(msB.z, msB.w));
+        const float k11 = mA + mB + iA * mrA.y * mrA.y + iB * mrB.y * mrB.y;
+        const float k12 = -iA * mrA.x * mrA.y - iB * mrB.x * mrB.y;
+        const float k22 = mA + mB + iA * mrA.x * mrA.x + iB * mrB.x * mrB.x;
+        float det = k11 * k22 - k12 * k12;
+        if (det != 0.0f) det = Div(1.0f, det);
+        const float lmxx = det * k22, lmyx = -det * k12, lmxy = -det * k12, lmyy = det * k11;
+        float angularMass = iA + iB;
+        if (angularMass > 0.0f) angularMass = Div(1.0f, angularMass);
+        const Vec2 linearError = cB + mrB - cA - mrA - Mul(qA, V2(f0.x, f0.y));
+        const float angularError = aB - aA - f1.z;
+        if (warmStarting) {
+            imp.x *= dtRatio; imp.y *= dtRatio;
+            imp.z *= dtRatio;
+            const Vec2 P = V2(imp.x, imp.y);
+            vA = vA - mA * P;
+            wA -= iA * (Cross(mrA, P) + imp.z);
+            vB = vB + mB * P;
+            wB += iB * (Cross(mrB, P) + imp.z);
+        } else {
+            imp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        c.jTmp[t + 0] = make_float4(mrA.x, mrA.y, mrB.x, mrB.y);
+        c.jTmp[t + 1] = make_float4(lmxx, lmyx, lmxy, lmyy);
+        c.jTmp[t + 2] = make_float4(angularMass, linearError.x, linearError.y, angularError);
     } else if (type == B2G_JOINT_ROPE) {  // b2RopeJoint.cpp:59-133; f1.x = maxLength
         Vec2 u = cB + rB - cA - rA;
         const float length = Length(u);
@@ -516,6 +542,39 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
         wA -= iA * Cross(rA, P);
         vB = vB + mB * P;
         wB += iB * Cross(rB, P);
+    } else if (type == B2G_JOINT_MOTOR) {  // b2MotorJoint.cpp:135-193
+        const float4 f1 = c.jF1[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2];
+        const Vec2 rA = V2(t0.x, t0.y), rB = V2(t0.z, t0.w);
+        const float inv_h = Div(1.0f, h);
+        {  // angular constraint
+            const float Cdot = wB - wA + inv_h * f1.w * t2.w;
+            float impulse = -t2.x * Cdot;
+            const float oldImpulse = imp.z;
+            const float maxImpulse = h * f1.y;
+            imp.z = Clamp(imp.z + impulse, -maxImpulse, maxImpulse);
+            impulse = imp.z - oldImpulse;
+            wA -= iA * impulse;
+            wB += iB * impulse;
+        }
+        {  // linear constraint
+            const Vec2 Cdot = vB + Cross(wB, rB) - vA - Cross(wA, rA) + (inv_h * f1.w) * V2(t2.y, t2.z);
+            Vec2 impulse = -V2(t1.x * Cdot.x + t1.y * Cdot.y, t1.z * Cdot.x + t1.w * Cdot.y);
+            const Vec2 oldImpulse = V2(imp.x, imp.y);
+            Vec2 li = oldImpulse + impulse;
+            const float maxImpulse = h * f1.x;
+            if (Dot(li, li) > maxImpulse * maxImpulse) {
+                Normalize(li);
+                li = maxImpulse * li;
+            }
+            imp.x = li.x;
+            imp.y = li.y;
+            impulse = li - oldImpulse;
+            vA = vA - mA * impulse;
+            wA -= iA * Cross(rA, impulse);
+            vB = vB + mB * impulse;
+            wB += iB * Cross(rB, impulse);
+        }
     } else if (type == B2G_JOINT_ROPE) {  // b2RopeJoint.cpp:135-169
         const float4 f1 = c.jF1[j];
         const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1];
@@ -789,8 +848,8 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
         cB = cB + mB * P;
         aB += iB * Cross(rB, P);
         okay = length - f1.x < kLinearSlop;
-    } else if (type == B2G_JOINT_FRICTION) {  // b2FrictionJoint.cpp:188-193: no position correction
-        return true;
+    } else if (type == B2G_JOINT_FRICTION || type == B2G_JOINT_MOTOR) {  // b2FrictionJoint.cpp:188-193, b2MotorJoint.cpp:195-200
+        return true;  // no position correction
     } else if (type == B2G_JOINT_WHEEL) {  // b2WheelJoint.cpp:263-312
         const float4 f2 = c.jF2[j];
         const float4 t1 = c.jTmp[(size_t)j * kJointTmp + 1];

@@ -275,6 +275,12 @@ struct b2FrictionJointDef : public b2JointDef {  // Dynamics/Joints/b2FrictionJo
     b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}};
     float maxForce = 0.0f, maxTorque = 0.0f;
 };
+struct b2MotorJointDef : public b2JointDef {  // Dynamics/Joints/b2MotorJoint.h:27-57
+    b2MotorJointDef() { type = b2JointType::MOTOR_JOINT; }
+    void Initialize(b2Body* bodyA, b2Body* bodyB);
+    b2Vec<float, 2> linearOffset{{0.0f, 0.0f}};
+    float angularOffset = 0.0f, maxForce = 1.0f, maxTorque = 1.0f, correctionFactor = 0.3f;
+};
 class b2Joint {
 public:
     b2JointType GetType() const { return m_type; }
@@ -385,7 +391,7 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
-    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel, weld, rope and friction joints; nullptr for the
+    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel, weld, rope, friction and motor joints; nullptr for the
     // joint types outside the device path and once the world is locked (after the first Step)
     b2Joint* CreateJoint(const b2JointDef* def);
     // b2World::DestroyBody (b2World.cpp:124-203): queued like the b2Body edits; the body's joints, contacts and proxies go
@@ -704,6 +710,12 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
         set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB); set2(d.localAxisA, r->localAxisA);
         d.enableMotor = r->enableMotor; d.maxMotor = r->maxMotorTorque; d.motorSpeed = r->motorSpeed;
         d.frequencyHz = r->frequencyHz; d.dampingRatio = r->dampingRatio;
+    } else if (def->type == b2JointType::MOTOR_JOINT) {
+        const b2MotorJointDef* r = static_cast<const b2MotorJointDef*>(def);
+        d.type = B2G_JOINT_MOTOR;
+        set2(d.localAnchorA, r->linearOffset);
+        d.referenceAngle = r->angularOffset;
+        d.length = r->maxForce; d.maxMotor = r->maxTorque; d.frequencyHz = r->correctionFactor;
     } else if (def->type == b2JointType::ROPE_JOINT) {
         const b2RopeJointDef* r = static_cast<const b2RopeJointDef*>(def);
         d.type = B2G_JOINT_ROPE;
@@ -791,6 +803,11 @@ inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
 }
 inline const b2Vec<float, 2>& b2Body::GetPosition() const {
     b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt()) {  // scene still open (joint defs' Initialize())
+        const b2g_body_def& d = m_world->m_bodyDefs[m_index];
+        m_tmp[0] = {{d.position[0], d.position[1]}};
+        return m_tmp[0];
+    }
     B->Refresh();
     const float* x = &B->m_xf[B->Slot(this) * 4];
     m_tmp[0] = {{x[0], x[1]}};
@@ -873,6 +890,11 @@ inline void b2WheelJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<floa
     localAnchorA = bodyA->GetLocalPoint(anchor);
     localAnchorB = bodyB->GetLocalPoint(anchor);
     localAxisA = bodyA->GetLocalVector(axis);
+}
+inline void b2MotorJointDef::Initialize(b2Body* bA, b2Body* bB) {
+    bodyA = bA; bodyB = bB;
+    linearOffset = bodyA->GetLocalPoint(bodyB->GetPosition());
+    angularOffset = bodyB->GetAngle() - bodyA->GetAngle();
 }
 inline void b2FrictionJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& anchor) {
     bodyA = bA; bodyB = bB;

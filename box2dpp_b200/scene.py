@@ -63,7 +63,7 @@ class FixtureDef(C.Structure):
     ]
 
 
-JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WHEEL, JOINT_WELD, JOINT_FRICTION, JOINT_ROPE = 1, 2, 3, 7, 8, 9, 10
+JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WHEEL, JOINT_WELD, JOINT_FRICTION, JOINT_ROPE, JOINT_MOTOR = 1, 2, 3, 7, 8, 9, 10, 11
 
 
 class JointDef(C.Structure):
@@ -201,6 +201,19 @@ class Scene:
         jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor)
         jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor)
         jd.length, jd.maxMotor = max_force, max_torque
+        return len(self.joints) - 1
+
+    def create_motor_joint(self, body_a, body_b, linear_offset=None, angular_offset=None, max_force=1.0, max_torque=1.0,
+                           correction_factor=0.3, collide_connected=False) -> int:
+        """b2MotorJointDef::Initialize(bodyA, bodyB) (b2MotorJoint.cpp:36-45) unless offsets are given."""
+        jd = self._joint(JOINT_MOTOR, body_a, body_b, collide_connected)
+        if linear_offset is None:
+            linear_offset = self._local(body_a, self.bodies[body_b].position)
+        if angular_offset is None:
+            angular_offset = float(F32(self.bodies[body_b].angle) - F32(self.bodies[body_a].angle))
+        jd.localAnchorA[0], jd.localAnchorA[1] = linear_offset
+        jd.referenceAngle = angular_offset
+        jd.length, jd.maxMotor, jd.frequencyHz = max_force, max_torque, correction_factor
         return len(self.joints) - 1
 
     def create_distance_joint(self, body_a, body_b, anchor_a, anchor_b, frequency_hz=0.0, damping_ratio=0.0,
@@ -604,6 +617,11 @@ def vehicles(seed: int, flags=WORLD_DEFAULT) -> Scene:
     puck = s.create_body(DYNAMIC_BODY, (-24.0, 3.0), linear_velocity=(rng.uniform(3.0, 6.0), 2.0), angular_velocity=5.0, gravity_scale=0.0)
     s.create_circle(puck, 0.3, density=1.0)
     s.create_friction_joint(g, puck, (-24.0, 3.0), max_force=rng.uniform(1.0, 3.0), max_torque=0.4)
+    # ---- a platform driven towards an offset from the ground by a motor joint ----
+    plat = s.create_body(DYNAMIC_BODY, (-32.0, 6.0), gravity_scale=0.0)
+    s.create_box(plat, 1.0, 0.2, density=2.0)
+    s.create_motor_joint(g, plat, linear_offset=(-30.0 + rng.uniform(-1.0, 1.0), 8.0), angular_offset=0.5, max_force=200.0,
+                         max_torque=100.0, correction_factor=0.3)
     c2 = s.create_body(DYNAMIC_BODY, (2.0, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)
     s.create_box(c2, 0.3, 0.3, density=1.0)
     d2 = s.create_body(DYNAMIC_BODY, (2.6, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)

@@ -98,7 +98,7 @@ typedef struct b2g_fixture_def {
 
 /* Joint types: the values of b2JointType (Box2D/Dynamics/Joints/b2Joint.h:31-45). */
 enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3, B2G_JOINT_WHEEL = 7, B2G_JOINT_WELD = 8,
-       B2G_JOINT_FRICTION = 9, B2G_JOINT_ROPE = 10 };
+       B2G_JOINT_FRICTION = 9, B2G_JOINT_ROPE = 10, B2G_JOINT_MOTOR = 11 };
 
 /* The arguments of b2World::CreateJoint: the members of b2RevoluteJointDef (b2RevoluteJoint.h:35-86),
  * b2PrismaticJointDef (b2PrismaticJoint.h:33-87), b2DistanceJointDef (b2DistanceJoint.h:32-67), b2WheelJointDef
@@ -115,7 +115,9 @@ typedef struct b2g_joint_def {
     float lower, upper;       /* revolute: lowerAngle / upperAngle; prismatic: lowerTranslation / upperTranslation */
     float maxMotor;           /* revolute, wheel: maxMotorTorque; prismatic: maxMotorForce; friction: maxTorque */
     float motorSpeed;
-    float length;             /* distance: length; rope: maxLength; friction: maxForce */
+    float length;             /* distance: length; rope: maxLength; friction, motor: maxForce */
+                              /* motor: localAnchorA = linearOffset, referenceAngle = angularOffset, maxMotor = maxTorque,
+                                 frequencyHz = correctionFactor */
     float frequencyHz, dampingRatio; /* distance, wheel, weld */
 } b2g_joint_def;
 

@@ -225,6 +225,13 @@ RefWorld* build_world(const b2g_scene* s) {
             jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
             jd.maxLength = d.length;
             w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_MOTOR) {
+            b2MotorJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.linearOffset.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.angularOffset = d.referenceAngle;
+            jd.maxForce = d.length; jd.maxTorque = d.maxMotor; jd.correctionFactor = d.frequencyHz;
+            w->CreateJoint(&jd);
         } else if (d.type == B2G_JOINT_FRICTION) {
             b2FrictionJointDef jd;
             jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
