@@ -20,9 +20,10 @@ tail -c 600 gpurun_out/${TAG}_bench_ref.json
 # The two ncu passes run the batch as ONE world group (B2GPU_GROUPS=1) so that a launch is the whole batch, like the
 # per-kernel CUDA-event times of bench.py's roofline block.
 # launch list: every kernel with its device time (cold cache, serialised: compare shares); the skip count passes the
-# world-building uploads (~250 launches) and the 90 pre-roll steps (8 launches each)
-B2GPU_GROUPS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1100 -c 40 --csv \
-    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 12 --warmup 3 --worlds-per-gpu $WORLDS --no-cpu-baseline --e2e-steps 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1
+# world-building uploads (~300 launches) and 290 pre-roll steps (8 launches each), so the list shows the same settled
+# regime as the end of bench.py's default timed region (where its per-kernel CUDA-event times are taken)
+B2GPU_GROUPS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2700 -c 40 --csv \
+    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 12 --warmup 3 --preroll 290 --worlds-per-gpu $WORLDS --no-cpu-baseline --e2e-steps 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -3 gpurun_out/${TAG}_launches.csv
 # full capture of one kernel (a launch on the settled pyramid, well after the pre-roll)
 B2GPU_GROUPS=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:^${KERNEL}\$ -s 95 -c 1 -f \
