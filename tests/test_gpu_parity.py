@@ -260,6 +260,42 @@ def test_snapshot_restore_continues_bit_identically():
     fresh.close()
 
 
+def test_edge_cases_empty_world_zero_dt_and_overflow(oracles):
+    """Edge cases: a world without bodies and one with only a static body next to normal worlds (ragged batch); a step with
+    dt = 0 (b2World::Step then only runs Collide, b2World.cpp:926-944) matches the oracle; a contact arena that is too
+    small reports B2GPU_STATUS_CONTACT_OVERFLOW instead of corrupting memory; an event arena likewise."""
+    Ref = _ref_cls(oracles)
+    empty = S.Scene()
+    lonely = S.Scene()
+    lonely.create_box(lonely.create_body(S.STATIC_BODY), 5.0, 1.0)
+    scenes = [empty, S.pyramid(4, flags=NOCCD), lonely, S.hello_world(NOCCD)]
+    batch = WorldBatch(scenes, event_mask=EVENT_ALL)
+    refs = [Ref(s, record_events=True) for s in scenes[1:]]
+    for step in range(50):
+        dt = 0.0 if step in (7, 8, 30) else 1.0 / 60.0
+        batch.step(dt, 8, 3)
+        for r in refs:
+            r.step(dt, 8, 3)
+        for w, r in enumerate(refs, start=1):
+            compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} step {step}")
+    assert batch.bodies(0).shape[0] == 0 and batch.contacts(0)[0].shape[0] == 0
+    assert (batch.status() == 0).all()
+    batch.close()
+    # contact arena with room for 8 contacts only: a 5-row pyramid needs ~40
+    small = WorldBatch([S.pyramid(5, flags=NOCCD), S.hello_world(NOCCD)], max_contacts=8)
+    small.step_n(1.0 / 60.0, 8, 3, 30)
+    st = small.status()
+    assert st[0] & 1 and st[1] == 0, st
+    assert int(small.field(B.F_CONTACT_COUNT)[0, 0, 0]) <= 8
+    small.close()
+    few = WorldBatch([S.pyramid(5, flags=NOCCD)], event_mask=EVENT_ALL, max_events=4)
+    few.step_n(1.0 / 60.0, 8, 3, 40)
+    assert few.status()[0] & 2
+    offsets, ev = few.read_events()
+    assert ev.shape[0] <= 4
+    few.close()
+
+
 def test_replicated_worlds_identical(oracles):
     sc = S.pyramid(10, flags=NOCCD)
     batch = WorldBatch(sc, replicate=70)
