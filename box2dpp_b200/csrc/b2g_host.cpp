@@ -504,8 +504,8 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
         const b2g_joint_def& d = s.joints[j];
         if (d.type != B2G_JOINT_REVOLUTE && d.type != B2G_JOINT_PRISMATIC && d.type != B2G_JOINT_DISTANCE &&
             d.type != B2G_JOINT_WHEEL && d.type != B2G_JOINT_WELD && d.type != B2G_JOINT_ROPE && d.type != B2G_JOINT_FRICTION &&
-            d.type != B2G_JOINT_MOTOR) {
-            err = "joint type outside the device path (revolute, prismatic, distance, wheel, weld, rope, friction and motor joints are built)";
+            d.type != B2G_JOINT_MOTOR && d.type != B2G_JOINT_PULLEY) {
+            err = "joint type outside the device path (revolute, prismatic, distance, wheel, weld, rope, friction, motor and pulley joints are built)";
             return B2GPU_ERR_UNSUPPORTED;
         }
         if (d.bodyA < 0 || d.bodyA >= nb || d.bodyB < 0 || d.bodyB >= nb || d.bodyA == d.bodyB) {
@@ -527,6 +527,8 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
             put(F1, o, d.length); put(F1, o + 1, 0.0f); put(F1, o + 2, 0.0f); put(F1, o + 3, 0.0f);
         } else if (d.type == B2G_JOINT_FRICTION) {
             put(F1, o, d.length); put(F1, o + 1, d.maxMotor); put(F1, o + 2, 0.0f); put(F1, o + 3, 0.0f);
+        } else if (d.type == B2G_JOINT_PULLEY) {
+            put(F1, o, d.localAxisA[0]); put(F1, o + 1, d.localAxisA[1]); put(F1, o + 2, d.lower); put(F1, o + 3, d.upper);
         } else if (d.type == B2G_JOINT_MOTOR) {
             put(F1, o, d.length); put(F1, o + 1, d.maxMotor); put(F1, o + 2, d.referenceAngle); put(F1, o + 3, d.frequencyHz);
         } else if (d.type == B2G_JOINT_WHEEL) {
@@ -539,7 +541,11 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
         Vec2 axis = V2(d.localAxisA[0], d.localAxisA[1]);
         if (d.type == B2G_JOINT_PRISMATIC) Normalize(axis);  // m_localXAxisA.Normalize()
         auto& F2 = out.f[B2GPU_F_JOINT_F2];
-        put(F2, o, d.motorSpeed); put(F2, o + 1, axis.x); put(F2, o + 2, axis.y); put(F2, o + 3, 0.0f);
+        if (d.type == B2G_JOINT_PULLEY) {  // ratio, m_constant = lengthA + ratio * lengthB (b2PulleyJoint.cpp:76)
+            put(F2, o, d.motorSpeed); put(F2, o + 1, d.length + d.motorSpeed * d.maxMotor); put(F2, o + 2, 0.0f); put(F2, o + 3, 0.0f);
+        } else {
+            put(F2, o, d.motorSpeed); put(F2, o + 1, axis.x); put(F2, o + 2, axis.y); put(F2, o + 3, 0.0f);
+        }
     }
     put(out.f[B2GPU_F_JOINT_COUNT], 0, nj);
     return B2GPU_OK;

@@ -1,4 +1,4 @@
-// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel, weld, rope, friction and motor joints.
+// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel, weld, rope, friction, motor and pulley joints.
 //
 // Reference (vanilla twin Regression/box2d-ref/Box2DRef/Dynamics/Joints; the fork's files are
 // Box2D/Dynamics/Joints/b2RevoluteJoint.cpp, b2PrismaticJoint.cpp, b2DistanceJoint.cpp, same line structure):
@@ -198,6 +198,31 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
         c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
         c.jTmp[t + 1] = make_float4(u.x, u.y, mass, gamma);
         c.jTmp[t + 2] = make_float4(bias, 0.0f, 0.0f, 0.0f);
+    } else if (type == B2G_JOINT_PULLEY) {  // b2PulleyJoint.cpp:82-164; f1 = groundAnchorA.xy, groundAnchorB.xy; f2 = ratio, constant
+        Vec2 uA = cA + rA - V2(f1.x, f1.y);
+        Vec2 uB = cB + rB - V2(f1.z, f1.w);
+        const float lengthA = Length(uA), lengthB = Length(uB);
+        if (lengthA > 10.0f * kLinearSlop) uA = Div(1.0f, lengthA) * uA; else uA = V2(0.0f, 0.0f);
+        if (lengthB > 10.0f * kLinearSlop) uB = Div(1.0f, lengthB) * uB; else uB = V2(0.0f, 0.0f);
+        const float ruA = Cross(rA, uA), ruB = Cross(rB, uB);
+        const float pmA = mA + iA * ruA * ruA;
+        const float pmB = mB + iB * ruB * ruB;
+        float mass = pmA + f2.x * f2.x * pmB;
+        if (mass > 0.0f) mass = Div(1.0f, mass);
+        if (warmStarting) {
+            imp.x *= dtRatio;
+            const Vec2 PA = -(imp.x) * uA;
+            const Vec2 PB = (-f2.x * imp.x) * uB;
+            vA = vA + mA * PA;
+            wA += iA * Cross(rA, PA);
+            vB = vB + mB * PB;
+            wB += iB * Cross(rB, PB);
+        } else {
+            imp.x = 0.0f;
+        }
+        c.jTmp[t + 0] = make_float4(rA.x, rA.y, rB.x, rB.y);
+        c.jTmp[t + 1] = make_float4(uA.x, uA.y, uB.x, uB.y);
+        c.jTmp[t + 2] = make_float4(mass, 0.0f, 0.0f, 0.0f);
     } else if (type == B2G_JOINT_MOTOR) {  // b2MotorJoint.cpp:61-133; f0.xy = linearOffset, f1 = maxForce, maxTorque, angularOffset, correctionFactor
         const Vec2 mrA = Mul(qA, -V2(msA.z, msA.w)), mrB = Mul(qB, -V2(msB.z, msB.w));
         const float k11 = mA + mB + iA * mrA.y * mrA.y + iB * mrB.y * mrB.y;
@@ -542,6 +567,21 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
         wA -= iA * Cross(rA, P);
         vB = vB + mB * P;
         wB += iB * Cross(rB, P);
+    } else if (type == B2G_JOINT_PULLEY) {  // b2PulleyJoint.cpp:166-193
+        const float4 f2 = c.jF2[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2];
+        const Vec2 rA = V2(t0.x, t0.y), rB = V2(t0.z, t0.w), uA = V2(t1.x, t1.y), uB = V2(t1.z, t1.w);
+        const Vec2 vpA = vA + Cross(wA, rA);
+        const Vec2 vpB = vB + Cross(wB, rB);
+        const float Cdot = -Dot(uA, vpA) - f2.x * Dot(uB, vpB);
+        const float impulse = -t2.x * Cdot;
+        imp.x += impulse;
+        const Vec2 PA = -impulse * uA;
+        const Vec2 PB = (-f2.x * impulse) * uB;
+        vA = vA + mA * PA;
+        wA += iA * Cross(rA, PA);
+        vB = vB + mB * PB;
+        wB += iB * Cross(rB, PB);
     } else if (type == B2G_JOINT_MOTOR) {  // b2MotorJoint.cpp:135-193
         const float4 f1 = c.jF1[j];
         const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2];
@@ -833,6 +873,30 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
         cB = cB + mB * P;
         aB += iB * Cross(rB, P);
         okay = Abs(C) < kLinearSlop;
+    } else if (type == B2G_JOINT_PULLEY) {  // b2PulleyJoint.cpp:195-264
+        const float4 f2 = c.jF2[j];
+        const Rot qA = MakeRot(aA), qB = MakeRot(aB);
+        const Vec2 rA = Mul(qA, lA), rB = Mul(qB, lB);
+        Vec2 uA = cA + rA - V2(f1.x, f1.y);
+        Vec2 uB = cB + rB - V2(f1.z, f1.w);
+        const float lengthA = Length(uA), lengthB = Length(uB);
+        if (lengthA > 10.0f * kLinearSlop) uA = Div(1.0f, lengthA) * uA; else uA = V2(0.0f, 0.0f);
+        if (lengthB > 10.0f * kLinearSlop) uB = Div(1.0f, lengthB) * uB; else uB = V2(0.0f, 0.0f);
+        const float ruA = Cross(rA, uA), ruB = Cross(rB, uB);
+        const float pmA = mA + iA * ruA * ruA;
+        const float pmB = mB + iB * ruB * ruB;
+        float mass = pmA + f2.x * f2.x * pmB;
+        if (mass > 0.0f) mass = Div(1.0f, mass);
+        const float C = f2.y - lengthA - f2.x * lengthB;
+        const float linearError = Abs(C);
+        const float impulse = -mass * C;
+        const Vec2 PA = -impulse * uA;
+        const Vec2 PB = (-f2.x * impulse) * uB;
+        cA = cA + mA * PA;
+        aA += iA * Cross(rA, PA);
+        cB = cB + mB * PB;
+        aB += iB * Cross(rB, PB);
+        okay = linearError < kLinearSlop;
     } else if (type == B2G_JOINT_ROPE) {  // b2RopeJoint.cpp:171-206
         const float mass = c.jTmp[(size_t)j * kJointTmp + 1].z;
         const Rot qA = MakeRot(aA), qB = MakeRot(aB);

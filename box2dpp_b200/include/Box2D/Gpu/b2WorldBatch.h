@@ -275,6 +275,13 @@ struct b2FrictionJointDef : public b2JointDef {  // Dynamics/Joints/b2FrictionJo
     b2Vec<float, 2> localAnchorA{{0.0f, 0.0f}}, localAnchorB{{0.0f, 0.0f}};
     float maxForce = 0.0f, maxTorque = 0.0f;
 };
+struct b2PulleyJointDef : public b2JointDef {  // Dynamics/Joints/b2PulleyJoint.h:29-72
+    b2PulleyJointDef() { type = b2JointType::PULLEY_JOINT; collideConnected = true; }
+    void Initialize(b2Body* bodyA, b2Body* bodyB, const b2Vec<float, 2>& groundAnchorA, const b2Vec<float, 2>& groundAnchorB,
+                    const b2Vec<float, 2>& anchorA, const b2Vec<float, 2>& anchorB, float ratio);
+    b2Vec<float, 2> groundAnchorA{{-1.0f, 1.0f}}, groundAnchorB{{1.0f, 1.0f}}, localAnchorA{{-1.0f, 0.0f}}, localAnchorB{{1.0f, 0.0f}};
+    float lengthA = 0.0f, lengthB = 0.0f, ratio = 1.0f;
+};
 struct b2MotorJointDef : public b2JointDef {  // Dynamics/Joints/b2MotorJoint.h:27-57
     b2MotorJointDef() { type = b2JointType::MOTOR_JOINT; }
     void Initialize(b2Body* bodyA, b2Body* bodyB);
@@ -391,7 +398,7 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
-    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel, weld, rope, friction and motor joints; nullptr for the
+    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel, weld, rope, friction, motor and pulley joints; nullptr for the
     // joint types outside the device path and once the world is locked (after the first Step)
     b2Joint* CreateJoint(const b2JointDef* def);
     // b2World::DestroyBody (b2World.cpp:124-203): queued like the b2Body edits; the body's joints, contacts and proxies go
@@ -710,6 +717,12 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
         set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB); set2(d.localAxisA, r->localAxisA);
         d.enableMotor = r->enableMotor; d.maxMotor = r->maxMotorTorque; d.motorSpeed = r->motorSpeed;
         d.frequencyHz = r->frequencyHz; d.dampingRatio = r->dampingRatio;
+    } else if (def->type == b2JointType::PULLEY_JOINT) {
+        const b2PulleyJointDef* r = static_cast<const b2PulleyJointDef*>(def);
+        d.type = B2G_JOINT_PULLEY;
+        set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB); set2(d.localAxisA, r->groundAnchorA);
+        d.lower = r->groundAnchorB[0]; d.upper = r->groundAnchorB[1];
+        d.length = r->lengthA; d.maxMotor = r->lengthB; d.motorSpeed = r->ratio;
     } else if (def->type == b2JointType::MOTOR_JOINT) {
         const b2MotorJointDef* r = static_cast<const b2MotorJointDef*>(def);
         d.type = B2G_JOINT_MOTOR;
@@ -890,6 +903,18 @@ inline void b2WheelJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<floa
     localAnchorA = bodyA->GetLocalPoint(anchor);
     localAnchorB = bodyB->GetLocalPoint(anchor);
     localAxisA = bodyA->GetLocalVector(axis);
+}
+inline void b2PulleyJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& groundA, const b2Vec<float, 2>& groundB,
+                                         const b2Vec<float, 2>& anchorA, const b2Vec<float, 2>& anchorB, float r) {
+    bodyA = bA; bodyB = bB;
+    groundAnchorA = groundA; groundAnchorB = groundB;
+    localAnchorA = bodyA->GetLocalPoint(anchorA);
+    localAnchorB = bodyB->GetLocalPoint(anchorB);
+    const float ax = anchorA[0] - groundA[0], ay = anchorA[1] - groundA[1];
+    lengthA = std::sqrt(ax * ax + ay * ay);
+    const float bx = anchorB[0] - groundB[0], by = anchorB[1] - groundB[1];
+    lengthB = std::sqrt(bx * bx + by * by);
+    ratio = r;
 }
 inline void b2MotorJointDef::Initialize(b2Body* bA, b2Body* bB) {
     bodyA = bA; bodyB = bB;

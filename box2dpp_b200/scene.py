@@ -64,6 +64,7 @@ class FixtureDef(C.Structure):
 
 
 JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WHEEL, JOINT_WELD, JOINT_FRICTION, JOINT_ROPE, JOINT_MOTOR = 1, 2, 3, 7, 8, 9, 10, 11
+JOINT_PULLEY = 4
 
 
 class JointDef(C.Structure):
@@ -214,6 +215,22 @@ class Scene:
         jd.localAnchorA[0], jd.localAnchorA[1] = linear_offset
         jd.referenceAngle = angular_offset
         jd.length, jd.maxMotor, jd.frequencyHz = max_force, max_torque, correction_factor
+        return len(self.joints) - 1
+
+    def create_pulley_joint(self, body_a, body_b, ground_a, ground_b, anchor_a, anchor_b, ratio=1.0, collide_connected=True) -> int:
+        """b2PulleyJointDef::Initialize(bodyA, bodyB, groundA, groundB, anchorA, anchorB, ratio) (b2PulleyJoint.cpp:37-56);
+        collideConnected defaults to true like b2PulleyJointDef's constructor."""
+        jd = self._joint(JOINT_PULLEY, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = self._local(body_a, anchor_a)
+        jd.localAnchorB[0], jd.localAnchorB[1] = self._local(body_b, anchor_b)
+        jd.localAxisA[0], jd.localAxisA[1] = ground_a
+        jd.lower, jd.upper = ground_b
+
+        def dist(p, q):
+            dx, dy = F32(F32(p[0]) - F32(q[0])), F32(F32(p[1]) - F32(q[1]))
+            return float(np.sqrt(F32(dx * dx) + F32(dy * dy), dtype=F32))
+
+        jd.length, jd.maxMotor, jd.motorSpeed = dist(anchor_a, ground_a), dist(anchor_b, ground_b), ratio
         return len(self.joints) - 1
 
     def create_distance_joint(self, body_a, body_b, anchor_a, anchor_b, frequency_hz=0.0, damping_ratio=0.0,
@@ -622,6 +639,12 @@ def vehicles(seed: int, flags=WORLD_DEFAULT) -> Scene:
     s.create_box(plat, 1.0, 0.2, density=2.0)
     s.create_motor_joint(g, plat, linear_offset=(-30.0 + rng.uniform(-1.0, 1.0), 8.0), angular_offset=0.5, max_force=200.0,
                          max_torque=100.0, correction_factor=0.3)
+    # ---- two weights over a pulley (Testbed "Pulleys"), ratio 1.5 ----
+    pa = s.create_body(DYNAMIC_BODY, (-36.0, 5.0))
+    s.create_box(pa, 0.5, 0.8, density=5.0)
+    pb = s.create_body(DYNAMIC_BODY, (-34.0, 5.0 + rng.uniform(0.0, 0.5)))
+    s.create_box(pb, 0.5, 0.8, density=5.0)
+    s.create_pulley_joint(pa, pb, (-36.0, 11.0), (-34.0, 11.0), (-36.0, 5.8), (-34.0, float(F32(s.bodies[pb].position[1]) + F32(0.8))), ratio=1.5)
     c2 = s.create_body(DYNAMIC_BODY, (2.0, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)
     s.create_box(c2, 0.3, 0.3, density=1.0)
     d2 = s.create_body(DYNAMIC_BODY, (2.6, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)

@@ -97,7 +97,7 @@ typedef struct b2g_fixture_def {
 } b2g_fixture_def;
 
 /* Joint types: the values of b2JointType (Box2D/Dynamics/Joints/b2Joint.h:31-45). */
-enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3, B2G_JOINT_WHEEL = 7, B2G_JOINT_WELD = 8,
+enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3, B2G_JOINT_PULLEY = 4, B2G_JOINT_WHEEL = 7, B2G_JOINT_WELD = 8,
        B2G_JOINT_FRICTION = 9, B2G_JOINT_ROPE = 10, B2G_JOINT_MOTOR = 11 };
 
 /* The arguments of b2World::CreateJoint: the members of b2RevoluteJointDef (b2RevoluteJoint.h:35-86),
@@ -116,6 +116,8 @@ typedef struct b2g_joint_def {
     float maxMotor;           /* revolute, wheel: maxMotorTorque; prismatic: maxMotorForce; friction: maxTorque */
     float motorSpeed;
     float length;             /* distance: length; rope: maxLength; friction, motor: maxForce */
+                              /* pulley: localAxisA = groundAnchorA, (lower, upper) = groundAnchorB, length = lengthA,
+                                 maxMotor = lengthB, motorSpeed = ratio */
                               /* motor: localAnchorA = linearOffset, referenceAngle = angularOffset, maxMotor = maxTorque,
                                  frequencyHz = correctionFactor */
     float frequencyHz, dampingRatio; /* distance, wheel, weld */

@@ -225,6 +225,15 @@ RefWorld* build_world(const b2g_scene* s) {
             jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
             jd.maxLength = d.length;
             w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_PULLEY) {
+            b2PulleyJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.groundAnchorA.Set(d.localAxisA[0], d.localAxisA[1]);
+            jd.groundAnchorB.Set(d.lower, d.upper);
+            jd.lengthA = d.length; jd.lengthB = d.maxMotor; jd.ratio = d.motorSpeed;
+            w->CreateJoint(&jd);
         } else if (d.type == B2G_JOINT_MOTOR) {
             b2MotorJointDef jd;
             jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
