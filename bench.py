@@ -252,6 +252,7 @@ def main():
     except Exception:
         forces = np.zeros((W, batch.max_bodies, 3), np.float32)
         out = np.empty((W, batch.max_bodies, 4), np.float32)
+    # (a) the three separate calls, everything on the batch's stream: copy in, step, copy out
     for _ in range(3):
         batch.apply_forces(forces); batch.step(DT, 8, 3); batch.read_transforms(out)
     barrier()
@@ -261,10 +262,22 @@ def main():
         batch.step(DT, 8, 3)
         batch.read_transforms(out)  # synchronises: the caller holds this step's transforms
     t3 = time.perf_counter()
+    sep_s = max_over_ranks(t3 - t2)
+    # (b) the fused call (b2gpu_batch_step_io): same work and bytes, each world group's copies under the other groups'
+    # kernels; synchronises every step as well.  This is the call a per-step caller makes, so it is the e2e figure.
+    for _ in range(3):
+        batch.step_io(forces, DT, 8, 3, out)
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.step_io(forces, DT, 8, 3, out)
+    t3 = time.perf_counter()
     e2e_s = max_over_ranks(t3 - t2)
     e2e = {"value": total_worlds * e2e_steps / e2e_s, "unit": "world-steps/s",
            "h2d_bytes_per_step": int(forces.nbytes) * world_size, "d2h_bytes_per_step": int(out.nbytes) * world_size,
-           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "call": "b2gpu_batch_step_io",
+           "separate_calls": {"value": total_worlds * e2e_steps / sep_s, "ms_per_step": 1e3 * sep_s / e2e_steps,
+                              "call": "b2gpu_batch_apply_forces + b2gpu_batch_step + b2gpu_batch_read_transforms"}}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

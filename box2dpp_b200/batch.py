@@ -39,7 +39,7 @@ EVENT_ALL = 15
 EXPORTED_SYMBOLS = [
     "b2gpu_batch_create", "b2gpu_batch_destroy", "b2gpu_batch_upload_field", "b2gpu_batch_download_field",
     "b2gpu_batch_field_shape", "b2gpu_batch_step", "b2gpu_batch_step_n", "b2gpu_batch_sync",
-    "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_last_step_ms",
+    "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_step_io", "b2gpu_batch_last_step_ms",
     "b2gpu_batch_profile_steps", "b2gpu_batch_profile_kernels", "b2gpu_batch_kernel_name", "b2gpu_batch_launch_count", "b2gpu_last_error", "b2gpu_scene_capacities",
     "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build", "b2gpu_host_sincosf", "b2gpu_sincosf",
     "b2gpu_collide_pairs",
@@ -97,6 +97,7 @@ def lib():
         L.b2gpu_batch_sync.argtypes = [vp]
         L.b2gpu_batch_apply_forces.argtypes = [vp, vp]
         L.b2gpu_batch_read_transforms.argtypes = [vp, vp]
+        L.b2gpu_batch_step_io.argtypes = [vp, vp, C.c_float, i32, i32, vp]
         L.b2gpu_batch_body_commands.argtypes = [vp, vp, C.c_int64]
         L.b2gpu_batch_read_body_state.argtypes = [vp, vp]
         L.b2gpu_batch_query_aabb.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
@@ -247,6 +248,21 @@ class WorldBatch:
         f = np.ascontiguousarray(forces, np.float32)
         assert f.size == self.num_worlds * self.max_bodies * 3
         _check(lib().b2gpu_batch_apply_forces(self.h, f.ctypes.data_as(C.c_void_p)))
+
+    def step_io(self, forces: np.ndarray | None, dt: float, vel_iters: int, pos_iters: int,
+                out: np.ndarray | None = None) -> np.ndarray:
+        """b2gpu_batch_step_io: apply_forces + step + read_transforms in one call, the host copies of each world
+        group overlapped with the other groups' kernels.  Returns the transforms [W, maxBodies, 4]."""
+        fptr = None
+        if forces is not None:
+            f = np.ascontiguousarray(forces, np.float32)
+            assert f.size == self.num_worlds * self.max_bodies * 3
+            fptr = f.ctypes.data_as(C.c_void_p)
+        if out is None:
+            out = np.empty((self.num_worlds, self.max_bodies, 4), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.num_worlds * self.max_bodies * 4
+        _check(lib().b2gpu_batch_step_io(self.h, fptr, dt, vel_iters, pos_iters, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def body_commands(self, commands: np.ndarray):
         """b2gpu_batch_body_commands: `commands` is a BODY_COMMAND_DTYPE array (any world order)."""

@@ -72,10 +72,12 @@ __global__ void k_interleave(uint32_t* __restrict__ arena, const uint32_t* __res
 
 // b2Body::ApplyForceToCenter / ApplyTorque for every body (Box2D/Dynamics/b2Body.h:738-790):
 // wake on a non-zero force, then accumulate if awake.
-__global__ void k_apply_forces(Arena A, const float* __restrict__ forces) {
+// Covers tiles [A.tile0, A.tile0 + tileCount): the whole batch, or one world group's share (b2gpu_batch_step_io).
+__global__ void k_apply_forces(Arena A, const float* __restrict__ forces, int tileCount) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // lane-fastest: (tile, body, lane)
-    size_t total = (size_t)A.numTiles * A.NB * kTile;
+    size_t total = (size_t)tileCount * A.NB * kTile;
     if (idx >= total) return;
+    idx += (size_t)A.tile0 * A.NB * kTile;
     int lane = (int)(idx & 31);
     size_t r = idx >> 5;
     int body = (int)(r % A.NB);
@@ -97,10 +99,11 @@ __global__ void k_apply_forces(Arena A, const float* __restrict__ forces) {
 }
 
 // b2Body::GetTransform for every body, world-major output
-__global__ void k_read_transforms(Arena A, float4* __restrict__ out) {
+__global__ void k_read_transforms(Arena A, float4* __restrict__ out, int tileCount) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)A.numTiles * A.NB * kTile;
+    size_t total = (size_t)tileCount * A.NB * kTile;
     if (idx >= total) return;
+    idx += (size_t)A.tile0 * A.NB * kTile;
     int lane = (int)(idx & 31);
     size_t r = idx >> 5;
     int body = (int)(r % A.NB);
@@ -851,7 +854,30 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
 // warps per SM, while the parallel kernels need registers and issue slots but no shared memory: the groups are
 // software-pipelined so that one group's part 1 runs while the other groups are in parts 0 / 2 — group g's part 1 of
 // a step waits for group g-1's part 1 of the same step (group 0: for the last group's part 1 of the previous step).
-int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks, int count, bool traceGroups = false) {
+//
+// Per-step host I/O (io != nullptr, b2gpu_batch_step_io): every group copies ITS worlds' forces in before its chain and
+// its worlds' transforms out after it, on its own stream, so one group's PCIe transfers run under the other groups'
+// kernels instead of in front of and behind the whole batch's step.
+struct StepIo {
+    const float* forces;   // host, [world][maxBodies][3] or null
+    float* transforms;     // host, [world][maxBodies][4] or null
+    float* devForces;      // device staging, same shapes
+    float4* devTransforms;
+    int groups;            // world groups for this call (>= b->groups)
+};
+
+// Streams and events of groups [0, G) (created on first use: b2gpu_batch_step_io may use more groups than the step).
+int ensureGroupStreams(b2gpu_batch* b, int G) {
+    for (int g = 0; g < G && g < b2gpu_batch::kMaxGroups; ++g) {
+        if (g > 0 && !b->groupStream[g]) CUDA_TRY(cudaStreamCreateWithFlags(&b->groupStream[g], cudaStreamNonBlocking));
+        if (g > 0 && !b->evJoin[g]) CUDA_TRY(cudaEventCreateWithFlags(&b->evJoin[g], cudaEventDisableTiming));
+        if (!b->evSeq[g]) CUDA_TRY(cudaEventCreateWithFlags(&b->evSeq[g], cudaEventDisableTiming));
+    }
+    return B2GPU_OK;
+}
+
+int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks, int count, bool traceGroups = false,
+                 const StepIo* io = nullptr) {
     cudaStream_t st = b->stream;
     if (b->needInitialPairs) {  // if (m_flags & e_newFixture) FindNewContacts()
         const int threads = b->blockSize;
@@ -868,6 +894,7 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
     const int perStep = dt > 0.0f ? stepKernelCount(b) : 1;
     const int nkTrace = stepKernelCount(b) + 1;  // traceGroups: marks is [group][step][nk + 1]
     int G = ((marks && !traceGroups) || b->groups < 1) ? 1 : b->groups;
+    if (io) G = io->groups;
     if (G > b->A.numTiles) G = b->A.numTiles > 0 ? b->A.numTiles : 1;
     const int per = (b->A.numTiles + G - 1) / G;
     if (G > 1) {  // fork: every group stream waits for what is already queued on the batch's stream
@@ -883,6 +910,18 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
             cudaStream_t gs = g == 0 ? st : b->groupStream[g];
             cudaEvent_t* mk = marks ? marks + (traceGroups ? ((size_t)g * count + i) * nkTrace : 0) : nullptr;
             int m = 0;
+            // this group's worlds and their slice of the host buffers
+            const int w0 = t0 * kTile;
+            const int w1 = (t0 + n) * kTile < b->desc.numWorlds ? (t0 + n) * kTile : b->desc.numWorlds;
+            const size_t ioItems = (size_t)n * b->A.NB * kTile;
+            Arena Ag = b->A;
+            Ag.tile0 = t0;
+            if (io && io->forces && w1 > w0) {
+                const size_t off = (size_t)w0 * b->A.NB * 3, len = (size_t)(w1 - w0) * b->A.NB * 3;
+                cudaMemcpyAsync(io->devForces + off, io->forces + off, len * sizeof(float), cudaMemcpyHostToDevice, gs);
+                k_apply_forces<<<(unsigned)((ioItems + 255) / 256), 256, 0, gs>>>(Ag, io->devForces, n);
+                b->launches++;
+            }
             enqueuePart(b, 0, dt, velIters, posIters, mk, &m, gs, t0, n);
             if (pipeline) {
                 const int prev = g == 0 ? G - 1 : g - 1;
@@ -891,6 +930,13 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
             enqueuePart(b, 1, dt, velIters, posIters, mk, &m, gs, t0, n);
             if (pipeline) cudaEventRecord(b->evSeq[g], gs);
             enqueuePart(b, 2, dt, velIters, posIters, mk, &m, gs, t0, n);
+            if (io && io->transforms && w1 > w0) {
+                const size_t off = (size_t)w0 * b->A.NB * 4, len = (size_t)(w1 - w0) * b->A.NB * 4;
+                k_read_transforms<<<(unsigned)((ioItems + 255) / 256), 256, 0, gs>>>(Ag, io->devTransforms, n);
+                b->launches++;
+                cudaMemcpyAsync(io->transforms + off, (const float*)io->devTransforms + off, len * sizeof(float),
+                                cudaMemcpyDeviceToHost, gs);
+            }
         }
     }
     for (int g = 1; g < G; ++g) {  // join
@@ -1207,7 +1253,7 @@ int b2gpu_batch_apply_forces(b2gpu_batch* b, const float* forces) {
     size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 3 * sizeof(float);
     CUDA_TRY(cudaMemcpyAsync(b->ioDev, forces, bytes, cudaMemcpyHostToDevice, b->stream));
     size_t total = (size_t)b->A.numTiles * b->A.NB * kTile;
-    k_apply_forces<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, b->ioDev);
+    k_apply_forces<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, b->ioDev, b->A.numTiles);
     b->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2GPU_OK;
@@ -1219,12 +1265,39 @@ int b2gpu_batch_read_transforms(b2gpu_batch* b, float* out) {
     int rc = ensureIo(b);
     if (rc != B2GPU_OK) return rc;
     size_t total = (size_t)b->A.numTiles * b->A.NB * kTile;
-    k_read_transforms<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, (float4*)b->ioDev);
+    k_read_transforms<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, (float4*)b->ioDev, b->A.numTiles);
     b->launches++;
     CUDA_TRY(cudaGetLastError());
     size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
     CUDA_TRY(cudaMemcpyAsync(out, b->ioDev, bytes, cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
+// One b2World::Step of every world with its per-step host I/O fused in (see StepIo).
+int b2gpu_batch_step_io(b2gpu_batch* b, const float* forces, float dt, int32_t velIters, int32_t posIters, float* transforms) {
+    if (!b) return fail(B2GPU_ERR_INVALID, "null batch");
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    const size_t perBody = (size_t)b->desc.numWorlds * b->A.NB * sizeof(float);
+    int rc = ensureIo(b, perBody * 8);  // forces (3 floats, padded to 4) and transforms (4 floats) side by side
+    if (rc != B2GPU_OK) return rc;
+    StepIo io;
+    io.forces = forces;
+    io.transforms = transforms;
+    io.devForces = b->ioDev;
+    io.devTransforms = reinterpret_cast<float4*>(b->ioDev + (size_t)b->desc.numWorlds * b->A.NB * 4);
+    // eight groups: the exposed transfers are the first group's copy in and the last group's copy out, an eighth of the
+    // batch's each (16,384 pyramid worlds, ms per step for 2 / 4 / 8 groups: 6.81 / 6.46 / 6.28; separate calls 8.60)
+    io.groups = b2gpu_batch::kMaxGroups;
+    if (const char* env = getenv("B2GPU_IO_GROUPS")) {
+        const int g = atoi(env);
+        if (g >= 1 && g <= b2gpu_batch::kMaxGroups) io.groups = g;
+    }
+    rc = ensureGroupStreams(b, io.groups);
+    if (rc != B2GPU_OK) return rc;
+    rc = enqueueSteps(b, dt, velIters, posIters, nullptr, 1, false, &io);
+    if (rc != B2GPU_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(b->stream));  // joined: the caller holds this step's transforms
     return B2GPU_OK;
 }
 

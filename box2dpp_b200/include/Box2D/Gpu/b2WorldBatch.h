@@ -479,6 +479,18 @@ public:
         m_stateValid = false;
         if (m_listener) DispatchEvents();
     }
+    // Step with the dense per-step I/O of an RL / game-server loop fused in (b2gpu_batch_step_io): forces
+    // [world][GetMaxBodies()][3] = fx, fy, torque (ApplyForceToCenter / ApplyTorque; may be null) are applied, every
+    // world steps, transforms [world][GetMaxBodies()][4] = p.x, p.y, q.s, q.c (may be null) are read back; the host
+    // copies of one world group overlap the kernels of the others (pinned buffers).
+    void StepIO(const float* forces, float timeStep, int32_t velocityIterations, int32_t positionIterations, float* transforms) {
+        Build();
+        Flush();
+        Check(b2gpu_batch_step_io(m_handle, forces, timeStep, velocityIterations, positionIterations, transforms));
+        m_stateValid = false;
+        if (m_listener) DispatchEvents();
+    }
+    int32_t GetMaxBodies() { Build(); return m_maxBodies; }
     // `steps` steps replayed from a CUDA graph (no listener dispatch in between).
     void StepN(float timeStep, int32_t velocityIterations, int32_t positionIterations, int32_t steps) {
         Build();

@@ -191,6 +191,16 @@ int b2gpu_batch_sync(b2gpu_batch* batch);
 int b2gpu_batch_apply_forces(b2gpu_batch* batch, const float* forces);
 int b2gpu_batch_read_transforms(b2gpu_batch* batch, float* out);
 
+/* One step with its per-step I/O fused in: apply_forces(forces) + b2World::Step(dt, velIters, posIters)
+ * (Box2D/Dynamics/b2World.cpp:888-954) + read_transforms(transforms) for every world, the loop body of a caller that
+ * reads observations and writes controls every step.  Same results as the three separate calls (bit-identical);
+ * the difference is scheduling: the batch is cut into world groups, each group copies its own slice of `forces`
+ * in and of `transforms` out on its own stream, so the PCIe transfers of one group run under the kernels of the
+ * others.  Either pointer may be null (that side is skipped); pinned host buffers are needed for the overlap.
+ * Synchronises: on return `transforms` holds this step's result. */
+int b2gpu_batch_step_io(b2gpu_batch* batch, const float* forces, float dt, int32_t velIters, int32_t posIters,
+                        float* transforms);
+
 /* Applies `count` body commands between two steps.  Commands of one world are applied in array order (the order
  * the reference's user would have made the calls in); different worlds are independent and run in parallel.
  * The array may be in any world order (it is grouped by world on the host, stably).  A command naming a body

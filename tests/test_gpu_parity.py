@@ -367,6 +367,43 @@ def test_worlds_match_golden_hashes(name):
     batch.close()
 
 
+def test_step_io_equals_separate_calls():
+    """b2gpu_batch_step_io (per-group copies on the groups' streams) == apply_forces + step + read_transforms,
+    bit-for-bit, with a ragged last tile and more tiles than groups, and for every group count."""
+    W = 150  # 5 tiles, the last one with 22 worlds
+    sb = S.pyramid_batch(W, 6, flags=NOCCD & ~S.WORLD_ALLOW_SLEEP, first_seed=3, jittered=True)
+    rng = np.random.default_rng(5)
+    a = WorldBatch(sb)
+    forces = np.zeros((W, a.max_bodies, 3), np.float32)
+    seq = []
+    for k in range(30):
+        f = forces.copy()
+        f[:, 1:, :] = rng.uniform(-40.0, 40.0, size=f[:, 1:, :].shape).astype(np.float32) * (rng.random((W, a.max_bodies - 1, 1)) < 0.3)
+        seq.append(f)
+    ref_out = []
+    for f in seq:
+        a.apply_forces(f)
+        a.step(1.0 / 60.0, 8, 3)
+        ref_out.append(a.read_transforms().copy())
+    a.close()
+    for groups in ("1", "3", None, "8"):
+        if groups is None:
+            os.environ.pop("B2GPU_IO_GROUPS", None)
+        else:
+            os.environ["B2GPU_IO_GROUPS"] = groups
+        try:
+            b = WorldBatch(sb)
+            out = np.empty((W, b.max_bodies, 4), np.float32)
+            for k, f in enumerate(seq):
+                b.step_io(f, 1.0 / 60.0, 8, 3, out)
+                assert (out.view(np.uint32) == ref_out[k].view(np.uint32)).all(), f"step {k}, io groups {groups}"
+            # either side may be skipped
+            b.step_io(None, 1.0 / 60.0, 8, 3, out)
+            b.close()
+        finally:
+            os.environ.pop("B2GPU_IO_GROUPS", None)
+
+
 def test_full_size_batch_properties(oracles):
     """BASELINE configs[2] at full size: 16,384 pyramid-20 worlds on one B200.  Size-independent properties:
     (a) identical worlds stay bit-identical to each other and to the oracle's single world;
