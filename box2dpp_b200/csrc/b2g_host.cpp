@@ -504,15 +504,75 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
         const b2g_joint_def& d = s.joints[j];
         if (d.type != B2G_JOINT_REVOLUTE && d.type != B2G_JOINT_PRISMATIC && d.type != B2G_JOINT_DISTANCE &&
             d.type != B2G_JOINT_WHEEL && d.type != B2G_JOINT_WELD && d.type != B2G_JOINT_ROPE && d.type != B2G_JOINT_FRICTION &&
-            d.type != B2G_JOINT_MOTOR && d.type != B2G_JOINT_PULLEY) {
-            err = "joint type outside the device path (revolute, prismatic, distance, wheel, weld, rope, friction, motor and pulley joints are built)";
+            d.type != B2G_JOINT_MOTOR && d.type != B2G_JOINT_PULLEY && d.type != B2G_JOINT_MOUSE && d.type != B2G_JOINT_GEAR) {
+            err = "unknown joint type (b2JointType values 1-11 are built)";
             return B2GPU_ERR_UNSUPPORTED;
+        }
+        const size_t o = (size_t)j * 4;
+        if (d.type == B2G_JOINT_GEAR) {
+            // b2GearJoint::b2GearJoint (b2GearJoint.cpp:47-133): bodies, anchors, axes and reference angles are copied
+            // from joint1 / joint2 (revolute or prismatic, created earlier), the constant from the bodies' poses now.
+            const int j1 = d.enableLimit, j2 = d.enableMotor;
+            if (j1 < 0 || j1 >= j || j2 < 0 || j2 >= j) { err = "gear joint: joint1 / joint2 must be joints created before it"; return B2GPU_ERR_INVALID; }
+            int bodyOf[4];  // A, B, C, D
+            float side[2][6] = {{0.0f}};
+            int sideType[2];
+            float coordinate[2];
+            for (int k = 0; k < 2; ++k) {
+                const b2g_joint_def& g = s.joints[k == 0 ? j1 : j2];
+                if (g.type != B2G_JOINT_REVOLUTE && g.type != B2G_JOINT_PRISMATIC) { err = "gear joint: joint1 / joint2 must be revolute or prismatic"; return B2GPU_ERR_INVALID; }
+                if (g.bodyA < 0 || g.bodyA >= nb || g.bodyB < 0 || g.bodyB >= nb) { err = "joint references a body that does not exist"; return B2GPU_ERR_INVALID; }
+                sideType[k] = g.type;
+                const HBody& ground = bodies[g.bodyA];  // m_bodyC / m_bodyD = joint->GetBodyA()
+                const HBody& moving = bodies[g.bodyB];  // m_bodyA / m_bodyB = joint->GetBodyB()
+                bodyOf[2 + k] = g.bodyA;
+                bodyOf[k] = g.bodyB;
+                if (g.type == B2G_JOINT_REVOLUTE) {
+                    side[k][0] = g.referenceAngle;
+                    coordinate[k] = moving.a - ground.a - g.referenceAngle;
+                } else {
+                    Vec2 axis = V2(g.localAxisA[0], g.localAxisA[1]);
+                    Normalize(axis);  // the prismatic joint's m_localXAxisA
+                    const Vec2 pG = V2(g.localAnchorA[0], g.localAnchorA[1]), lM = V2(g.localAnchorB[0], g.localAnchorB[1]);
+                    const Vec2 pM = MulT(ground.xf.q, Mul(moving.xf.q, lM) + (moving.xf.p - ground.xf.p));
+                    coordinate[k] = Dot(pM - pG, axis);
+                    side[k][0] = pG.x; side[k][1] = pG.y; side[k][2] = lM.x; side[k][3] = lM.y; side[k][4] = axis.x; side[k][5] = axis.y;
+                }
+            }
+            if (bodyOf[0] == bodyOf[1]) { err = "gear joint connects a body to itself"; return B2GPU_ERR_INVALID; }
+            const float ratio = d.motorSpeed;
+            const float constant = coordinate[0] + ratio * coordinate[1];
+            put(out.f[B2GPU_F_JOINT_I], o, d.type | ((d.collideConnected ? 1 : 0) << 8) | (sideType[0] << 11) | (sideType[1] << 13));
+            put(out.f[B2GPU_F_JOINT_I], o + 1, bodyOf[0] | (bodyOf[1] << 16));
+            put(out.f[B2GPU_F_JOINT_I], o + 2, 0);
+            put(out.f[B2GPU_F_JOINT_I], o + 3, bodyOf[2] | (bodyOf[3] << 16));
+            for (int k = 0; k < 4; ++k) put(out.f[B2GPU_F_JOINT_F0], o + k, side[0][k]);
+            put(out.f[B2GPU_F_JOINT_F1], o, side[0][4]); put(out.f[B2GPU_F_JOINT_F1], o + 1, side[0][5]);
+            put(out.f[B2GPU_F_JOINT_F1], o + 2, ratio); put(out.f[B2GPU_F_JOINT_F1], o + 3, constant);
+            for (int k = 0; k < 4; ++k) put(out.f[B2GPU_F_JOINT_F2], o + k, side[1][k]);
+            // the last two constants ride in the unused half of the impulse record (x = m_impulse)
+            put(out.f[B2GPU_F_JOINT_IMPULSE], o, 0.0f); put(out.f[B2GPU_F_JOINT_IMPULSE], o + 1, 0.0f);
+            put(out.f[B2GPU_F_JOINT_IMPULSE], o + 2, side[1][4]); put(out.f[B2GPU_F_JOINT_IMPULSE], o + 3, side[1][5]);
+            continue;
         }
         if (d.bodyA < 0 || d.bodyA >= nb || d.bodyB < 0 || d.bodyB >= nb || d.bodyA == d.bodyB) {
             err = "joint references a body that does not exist (or connects a body to itself)";
             return B2GPU_ERR_INVALID;
         }
-        const size_t o = (size_t)j * 4;
+        if (d.type == B2G_JOINT_MOUSE) {
+            // b2MouseJoint::b2MouseJoint (b2MouseJoint.cpp:33-52): m_localAnchorB = b2MulT(bodyB's transform, target);
+            // b2Body::GetMass() of body B is read by InitVelocityConstraints (:113) — carried in the record
+            const Vec2 target = V2(d.localAnchorA[0], d.localAnchorA[1]);
+            const Vec2 lB = MulT(bodies[d.bodyB].xf, target);
+            put(out.f[B2GPU_F_JOINT_I], o, d.type | ((d.collideConnected ? 1 : 0) << 8));
+            put(out.f[B2GPU_F_JOINT_I], o + 1, d.bodyA | (d.bodyB << 16));
+            put(out.f[B2GPU_F_JOINT_I], o + 2, 0); put(out.f[B2GPU_F_JOINT_I], o + 3, 0);
+            put(out.f[B2GPU_F_JOINT_F0], o, target.x); put(out.f[B2GPU_F_JOINT_F0], o + 1, target.y);
+            put(out.f[B2GPU_F_JOINT_F0], o + 2, lB.x); put(out.f[B2GPU_F_JOINT_F0], o + 3, lB.y);
+            put(out.f[B2GPU_F_JOINT_F1], o, d.length); put(out.f[B2GPU_F_JOINT_F1], o + 1, d.frequencyHz);
+            put(out.f[B2GPU_F_JOINT_F1], o + 2, d.dampingRatio); put(out.f[B2GPU_F_JOINT_F1], o + 3, bodies[d.bodyB].mass);
+            continue;
+        }
         auto& JI = out.f[B2GPU_F_JOINT_I];
         put(JI, o, d.type | ((d.collideConnected ? 1 : 0) << 8) | ((d.enableLimit ? 1 : 0) << 9) | ((d.enableMotor ? 1 : 0) << 10));
         put(JI, o + 1, d.bodyA | (d.bodyB << 16));

@@ -1,4 +1,4 @@
-// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel, weld, rope, friction, motor and pulley joints.
+// b2g_joints.cuh — joints in the island solver: revolute, prismatic, distance, wheel, weld, rope, friction, motor, pulley, mouse and gear joints (all 11 of b2JointType).
 //
 // Reference (vanilla twin Regression/box2d-ref/Box2DRef/Dynamics/Joints; the fork's files are
 // Box2D/Dynamics/Joints/b2RevoluteJoint.cpp, b2PrismaticJoint.cpp, b2DistanceJoint.cpp, same line structure):
@@ -92,6 +92,15 @@ __device__ __forceinline__ JointCols MakeJointCols(const Arena& A, int tile, int
     return c;
 }
 
+
+// ---- gear joint (b2GearJoint.cpp): four bodies.  Record: jI.x bits 11-12 / 13-14 = type of joint1 / joint2, jI.y = A | B << 16,
+// jI.w = C | D << 16 (A, C = joint1's bodyB, bodyA; B, D = joint2's).  Per side six constants: revolute (referenceAngle, -),
+// prismatic (localAnchor on C / D .xy, localAnchor on A / B .xy, localAxis .xy).  Side 1 = jF0.xyzw + jF1.xy, side 2 =
+// jF2.xyzw + jImp.zw; jF1.z = ratio, jF1.w = m_constant; jImp.x = m_impulse.
+struct GearJacobian {
+    Vec2 JvAC, JvBD;
+    float JwA, JwB, JwC, JwD, mass;
+};
 // ---- InitVelocityConstraints ---------------------------------------------------------------------------------
 __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float h, float dtRatio, bool warmStarting) {
     const JointCols& c = *cp;
@@ -113,7 +122,101 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
     float4 imp = c.jImp[j];
     const size_t t = (size_t)j * kJointTmp;
 
-    if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:66-176
+    if (type == B2G_JOINT_GEAR) {  // b2GearJoint.cpp:135-248
+        const int bC = ji.w & 0xffff, bD = (ji.w >> 16) & 0xffff;
+        const int typeA = (ji.x >> 11) & 3, typeB = (ji.x >> 13) & 3;
+        const float4 msC = c.bodyMass[bC], msD = c.bodyMass[bD];
+        const float mC = msC.x, iC = msC.y, mD = msD.x, iD = msD.y;
+        const float aC = c.bodySweep[bC].z, aD = c.bodySweep[bD].z;
+        float4 velC = c.bodyVel[bC], velD = c.bodyVel[bD];
+        Vec2 vC = V2(velC.x, velC.y), vD = V2(velD.x, velD.y);
+        float wC = velC.z, wD = velD.z;
+        const Rot qC = MakeRot(aC), qD = MakeRot(aD);
+        const float ratio = f1.z;
+        GearJacobian g;
+        g.mass = 0.0f;
+        if (typeA == B2G_JOINT_REVOLUTE) {
+            g.JvAC = V2(0.0f, 0.0f);
+            g.JwA = 1.0f;
+            g.JwC = 1.0f;
+            g.mass += iA + iC;
+        } else {
+            const Vec2 u = Mul(qC, V2(f1.x, f1.y));
+            const Vec2 rC = Mul(qC, V2(f0.x, f0.y) - V2(msC.z, msC.w));
+            const Vec2 gA = Mul(qA, V2(f0.z, f0.w) - V2(msA.z, msA.w));
+            g.JvAC = u;
+            g.JwC = Cross(rC, u);
+            g.JwA = Cross(gA, u);
+            g.mass += mC + mA + iC * g.JwC * g.JwC + iA * g.JwA * g.JwA;
+        }
+        if (typeB == B2G_JOINT_REVOLUTE) {
+            g.JvBD = V2(0.0f, 0.0f);
+            g.JwB = ratio;
+            g.JwD = ratio;
+            g.mass += ratio * ratio * (iB + iD);
+        } else {
+            const Vec2 u = Mul(qD, V2(imp.z, imp.w));
+            const Vec2 rD = Mul(qD, V2(f2.x, f2.y) - V2(msD.z, msD.w));
+            const Vec2 gB = Mul(qB, V2(f2.z, f2.w) - V2(msB.z, msB.w));
+            g.JvBD = ratio * u;
+            g.JwD = ratio * Cross(rD, u);
+            g.JwB = ratio * Cross(gB, u);
+            g.mass += ratio * ratio * (mD + mB) + iD * g.JwD * g.JwD + iB * g.JwB * g.JwB;
+        }
+        g.mass = g.mass > 0.0f ? Div(1.0f, g.mass) : 0.0f;
+        if (warmStarting) {  // (no dtRatio scaling in the reference)
+            vA = vA + (mA * imp.x) * g.JvAC;
+            wA += iA * imp.x * g.JwA;
+            vB = vB + (mB * imp.x) * g.JvBD;
+            wB += iB * imp.x * g.JwB;
+            vC = vC - (mC * imp.x) * g.JvAC;
+            wC -= iC * imp.x * g.JwC;
+            vD = vD - (mD * imp.x) * g.JvBD;
+            wD -= iD * imp.x * g.JwD;
+        } else {
+            imp.x = 0.0f;
+        }
+        c.jTmp[t + 0] = make_float4(g.JvAC.x, g.JvAC.y, g.JvBD.x, g.JvBD.y);
+        c.jTmp[t + 1] = make_float4(g.JwA, g.JwB, g.JwC, g.JwD);
+        c.jTmp[t + 2] = make_float4(g.mass, 0.0f, 0.0f, 0.0f);
+        c.jImp[j] = imp;
+        // stores in the reference's order A, B, C, D (C and D may be the same body: the later store wins)
+        c.bodyVel[bA] = make_float4(vA.x, vA.y, wA, 0.0f);
+        c.bodyVel[bB] = make_float4(vB.x, vB.y, wB, 0.0f);
+        c.bodyVel[bC] = make_float4(vC.x, vC.y, wC, 0.0f);
+        c.bodyVel[bD] = make_float4(vD.x, vD.y, wD, 0.0f);
+        return;
+    }
+    if (type == B2G_JOINT_MOUSE) {  // b2MouseJoint.cpp:96-160; f0 = target.xy, localAnchorB.xy; f1 = maxForce, frequencyHz, dampingRatio, mass of B
+        const float mass = f1.w;
+        const float omega = 2.0f * kPi * f1.y;
+        const float d = 2.0f * mass * f1.z * omega;
+        const float k = mass * (omega * omega);
+        float gamma = h * (d + h * k);
+        if (gamma != 0.0f) gamma = Div(1.0f, gamma);
+        const float beta = h * k * gamma;
+        const float kxx = mB + iB * rB.y * rB.y + gamma;  // K.ex.x
+        const float kxy = -iB * rB.x * rB.y;              // K.ex.y = K.ey.x
+        const float kyy = mB + iB * rB.x * rB.x + gamma;  // K.ey.y
+        float det = kxx * kyy - kxy * kxy;                // b2Mat22::GetInverse (b2Math.h:226-238)
+        if (det != 0.0f) det = Div(1.0f, det);
+        const float mxx = det * kyy, myx = -det * kxy, mxy = -det * kxy, myy = det * kxx;  // ex.x, ey.x, ex.y, ey.y
+        Vec2 C = cB + rB - V2(f0.x, f0.y);
+        C.x *= beta;
+        C.y *= beta;
+        wB *= 0.98f;
+        if (warmStarting) {
+            imp.x *= dtRatio; imp.y *= dtRatio;
+            const Vec2 P = V2(imp.x, imp.y);
+            vB = vB + mB * P;
+            wB += iB * Cross(rB, P);
+        } else {
+            imp.x = 0.0f; imp.y = 0.0f;
+        }
+        c.jTmp[t + 0] = make_float4(rB.x, rB.y, C.x, C.y);
+        c.jTmp[t + 1] = make_float4(mxx, myx, mxy, myy);
+        c.jTmp[t + 2] = make_float4(gamma, 0.0f, 0.0f, 0.0f);
+    } else if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:66-176
         const bool fixedRotation = (iA + iB == 0.0f);
         Mat33 M;
         M.ex.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
@@ -485,7 +588,55 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
     const size_t t = (size_t)j * kJointTmp;
     const int limitState = ji.z;
 
-    if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:178-277
+    if (type == B2G_JOINT_GEAR) {  // b2GearJoint.cpp:250-285
+        const int bC = ji.w & 0xffff, bD = (ji.w >> 16) & 0xffff;
+        const float4 msC = c.bodyMass[bC], msD = c.bodyMass[bD];
+        const float mC = msC.x, iC = msC.y, mD = msD.x, iD = msD.y;
+        float4 velC = c.bodyVel[bC], velD = c.bodyVel[bD];
+        Vec2 vC = V2(velC.x, velC.y), vD = V2(velD.x, velD.y);
+        float wC = velC.z, wD = velD.z;
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2];
+        const Vec2 JvAC = V2(t0.x, t0.y), JvBD = V2(t0.z, t0.w);
+        const float JwA = t1.x, JwB = t1.y, JwC = t1.z, JwD = t1.w;
+        float Cdot = Dot(JvAC, vA - vC) + Dot(JvBD, vB - vD);
+        Cdot += (JwA * wA - JwC * wC) + (JwB * wB - JwD * wD);
+        const float impulse = -t2.x * Cdot;
+        imp.x += impulse;
+        vA = vA + (mA * impulse) * JvAC;
+        wA += iA * impulse * JwA;
+        vB = vB + (mB * impulse) * JvBD;
+        wB += iB * impulse * JwB;
+        vC = vC - (mC * impulse) * JvAC;
+        wC -= iC * impulse * JwC;
+        vD = vD - (mD * impulse) * JvBD;
+        wD -= iD * impulse * JwD;
+        c.jImp[j] = imp;
+        c.bodyVel[bA] = make_float4(vA.x, vA.y, wA, 0.0f);
+        c.bodyVel[bB] = make_float4(vB.x, vB.y, wB, 0.0f);
+        c.bodyVel[bC] = make_float4(vC.x, vC.y, wC, 0.0f);
+        c.bodyVel[bD] = make_float4(vD.x, vD.y, wD, 0.0f);
+        return;
+    }
+    if (type == B2G_JOINT_MOUSE) {  // b2MouseJoint.cpp:162-186
+        const float4 f1 = c.jF1[j];
+        const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2];
+        const Vec2 rB = V2(t0.x, t0.y), C = V2(t0.z, t0.w);
+        const Vec2 Cdot = vB + Cross(wB, rB);
+        const Vec2 rhs = -(Cdot + C + t2.x * V2(imp.x, imp.y));
+        Vec2 impulse = V2(t1.x * rhs.x + t1.y * rhs.y, t1.z * rhs.x + t1.w * rhs.y);  // b2Mul(m_mass, rhs)
+        const Vec2 oldImpulse = V2(imp.x, imp.y);
+        imp.x += impulse.x;
+        imp.y += impulse.y;
+        const float maxImpulse = h * f1.x;
+        if (LengthSquared(V2(imp.x, imp.y)) > maxImpulse * maxImpulse) {
+            const float scale = Div(maxImpulse, Length(V2(imp.x, imp.y)));
+            imp.x *= scale;
+            imp.y *= scale;
+        }
+        impulse = V2(imp.x, imp.y) - oldImpulse;
+        vB = vB + mB * impulse;
+        wB += iB * Cross(rB, impulse);
+    } else if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:178-277
         const float4 f1 = c.jF1[j], f2 = c.jF2[j];
         const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2], t3 = c.jTmp[t + 3];
         const Vec2 rA = V2(t0.x, t0.y), rB = V2(t0.z, t0.w);
@@ -816,6 +967,78 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
     const int limitState = ji.z;
     bool okay;
 
+    if (type == B2G_JOINT_MOUSE) return true;  // b2MouseJoint.cpp:188-192
+    if (type == B2G_JOINT_GEAR) {  // b2GearJoint.cpp:287-383
+        const int bC = ji.w & 0xffff, bD = (ji.w >> 16) & 0xffff;
+        const int typeA = (ji.x >> 11) & 3, typeB = (ji.x >> 13) & 3;
+        const float4 f2 = c.jF2[j], imp = c.jImp[j];
+        const float4 msC = c.bodyMass[bC], msD = c.bodyMass[bD];
+        const float mC = msC.x, iC = msC.y, mD = msD.x, iD = msD.y;
+        float4 swC = c.bodySweep[bC], swD = c.bodySweep[bD];
+        Vec2 cC = V2(swC.x, swC.y), cD = V2(swD.x, swD.y);
+        float aC = swC.z, aD = swD.z;
+        const Rot qA = MakeRot(aA), qB = MakeRot(aB), qC = MakeRot(aC), qD = MakeRot(aD);
+        const float ratio = f1.z, constant = f1.w;
+        const float linearError = 0.0f;
+        float coordinateA, coordinateB;
+        Vec2 JvAC, JvBD;
+        float JwA, JwB, JwC, JwD;
+        float mass = 0.0f;
+        if (typeA == B2G_JOINT_REVOLUTE) {
+            JvAC = V2(0.0f, 0.0f);
+            JwA = 1.0f;
+            JwC = 1.0f;
+            mass += iA + iC;
+            coordinateA = aA - aC - f0.x;
+        } else {
+            const Vec2 axisC = V2(f1.x, f1.y);
+            const Vec2 u = Mul(qC, axisC);
+            const Vec2 rC = Mul(qC, V2(f0.x, f0.y) - V2(msC.z, msC.w));
+            const Vec2 rA = Mul(qA, V2(f0.z, f0.w) - V2(msA.z, msA.w));
+            JvAC = u;
+            JwC = Cross(rC, u);
+            JwA = Cross(rA, u);
+            mass += mC + mA + iC * JwC * JwC + iA * JwA * JwA;
+            const Vec2 pC = V2(f0.x, f0.y) - V2(msC.z, msC.w);
+            const Vec2 pA = MulT(qC, rA + (cA - cC));
+            coordinateA = Dot(pA - pC, axisC);
+        }
+        if (typeB == B2G_JOINT_REVOLUTE) {
+            JvBD = V2(0.0f, 0.0f);
+            JwB = ratio;
+            JwD = ratio;
+            mass += ratio * ratio * (iB + iD);
+            coordinateB = aB - aD - f2.x;
+        } else {
+            const Vec2 axisD = V2(imp.z, imp.w);
+            const Vec2 u = Mul(qD, axisD);
+            const Vec2 rD = Mul(qD, V2(f2.x, f2.y) - V2(msD.z, msD.w));
+            const Vec2 rB = Mul(qB, V2(f2.z, f2.w) - V2(msB.z, msB.w));
+            JvBD = ratio * u;
+            JwD = ratio * Cross(rD, u);
+            JwB = ratio * Cross(rB, u);
+            mass += ratio * ratio * (mD + mB) + iD * JwD * JwD + iB * JwB * JwB;
+            const Vec2 pD = V2(f2.x, f2.y) - V2(msD.z, msD.w);
+            const Vec2 pB = MulT(qD, rB + (cB - cD));
+            coordinateB = Dot(pB - pD, axisD);
+        }
+        const float C = (coordinateA + ratio * coordinateB) - constant;
+        float impulse = 0.0f;
+        if (mass > 0.0f) impulse = Div(-C, mass);
+        cA = cA + (mA * impulse) * JvAC;
+        aA += iA * impulse * JwA;
+        cB = cB + (mB * impulse) * JvBD;
+        aB += iB * impulse * JwB;
+        cC = cC - (mC * impulse) * JvAC;
+        aC -= iC * impulse * JwC;
+        cD = cD - (mD * impulse) * JvBD;
+        aD -= iD * impulse * JwD;
+        c.bodySweep[bA] = make_float4(cA.x, cA.y, aA, swA.w);
+        c.bodySweep[bB] = make_float4(cB.x, cB.y, aB, swB.w);
+        c.bodySweep[bC] = make_float4(cC.x, cC.y, aC, swC.w);
+        c.bodySweep[bD] = make_float4(cD.x, cD.y, aD, swD.w);
+        return linearError < kLinearSlop;
+    }
     if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:279-371
         float angularError = 0.0f, positionError = 0.0f;
         const bool fixedRotation = (iA + iB == 0.0f);

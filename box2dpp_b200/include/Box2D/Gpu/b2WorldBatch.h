@@ -282,6 +282,18 @@ struct b2PulleyJointDef : public b2JointDef {  // Dynamics/Joints/b2PulleyJoint.
     b2Vec<float, 2> groundAnchorA{{-1.0f, 1.0f}}, groundAnchorB{{1.0f, 1.0f}}, localAnchorA{{-1.0f, 0.0f}}, localAnchorB{{1.0f, 0.0f}};
     float lengthA = 0.0f, lengthB = 0.0f, ratio = 1.0f;
 };
+struct b2MouseJointDef : public b2JointDef {  // Dynamics/Joints/b2MouseJoint.h:29-55
+    b2MouseJointDef() { type = b2JointType::MOUSE_JOINT; }
+    b2Vec<float, 2> target{{0.0f, 0.0f}};
+    float maxForce = 0.0f, frequencyHz = 5.0f, dampingRatio = 0.7f;
+};
+class b2Joint;
+struct b2GearJointDef : public b2JointDef {  // Dynamics/Joints/b2GearJoint.h:27-47
+    b2GearJointDef() { type = b2JointType::GEAR_JOINT; }
+    b2Joint* joint1 = nullptr;  // revolute or prismatic
+    b2Joint* joint2 = nullptr;
+    float ratio = 1.0f;
+};
 struct b2MotorJointDef : public b2JointDef {  // Dynamics/Joints/b2MotorJoint.h:27-57
     b2MotorJointDef() { type = b2JointType::MOTOR_JOINT; }
     void Initialize(b2Body* bodyA, b2Body* bodyB);
@@ -398,8 +410,7 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
-    // b2World::CreateJoint (b2World.cpp:211-270) for revolute, prismatic, distance, wheel, weld, rope, friction, motor and pulley joints; nullptr for the
-    // joint types outside the device path and once the world is locked (after the first Step)
+    // b2World::CreateJoint (b2World.cpp:211-270) for all eleven joint types; nullptr once the world is locked (after the first Step)
     b2Joint* CreateJoint(const b2JointDef* def);
     // b2World::DestroyBody (b2World.cpp:124-203): queued like the b2Body edits; the body's joints, contacts and proxies go
     // with it on the device.  The b2Body object stays allocated (its index is reserved) but must not be used again.
@@ -735,6 +746,19 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
         set2(d.localAnchorA, r->localAnchorA); set2(d.localAnchorB, r->localAnchorB); set2(d.localAxisA, r->groundAnchorA);
         d.lower = r->groundAnchorB[0]; d.upper = r->groundAnchorB[1];
         d.length = r->lengthA; d.maxMotor = r->lengthB; d.motorSpeed = r->ratio;
+    } else if (def->type == b2JointType::MOUSE_JOINT) {
+        const b2MouseJointDef* r = static_cast<const b2MouseJointDef*>(def);
+        d.type = B2G_JOINT_MOUSE;
+        set2(d.localAnchorA, r->target);
+        d.length = r->maxForce; d.frequencyHz = r->frequencyHz; d.dampingRatio = r->dampingRatio;
+    } else if (def->type == b2JointType::GEAR_JOINT) {
+        const b2GearJointDef* r = static_cast<const b2GearJointDef*>(def);
+        if (!r->joint1 || !r->joint2) return nullptr;
+        d.type = B2G_JOINT_GEAR;
+        d.enableLimit = r->joint1->GetIndex(); d.enableMotor = r->joint2->GetIndex();
+        d.motorSpeed = r->ratio;
+        // b2GearJoint.cpp:59-60, 92-93: the gear's bodies are the second bodies of joint1 / joint2
+        d.bodyA = r->joint1->GetBodyB()->GetIndex(); d.bodyB = r->joint2->GetBodyB()->GetIndex();
     } else if (def->type == b2JointType::MOTOR_JOINT) {
         const b2MotorJointDef* r = static_cast<const b2MotorJointDef*>(def);
         d.type = B2G_JOINT_MOTOR;
@@ -763,8 +787,8 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
     w.m_jointDefs.push_back(d);
     std::unique_ptr<b2Joint> j(new b2Joint);
     j->m_type = def->type;
-    j->m_bodyA = def->bodyA;
-    j->m_bodyB = def->bodyB;
+    j->m_bodyA = w.m_bodies[d.bodyA].get();
+    j->m_bodyB = w.m_bodies[d.bodyB].get();
     j->m_userData = def->userData;
     j->m_index = (int32_t)w.m_joints.size();
     w.m_joints.push_back(std::move(j));

@@ -64,7 +64,7 @@ class FixtureDef(C.Structure):
 
 
 JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_DISTANCE, JOINT_WHEEL, JOINT_WELD, JOINT_FRICTION, JOINT_ROPE, JOINT_MOTOR = 1, 2, 3, 7, 8, 9, 10, 11
-JOINT_PULLEY = 4
+JOINT_PULLEY, JOINT_MOUSE, JOINT_GEAR = 4, 5, 6
 
 
 class JointDef(C.Structure):
@@ -215,6 +215,23 @@ class Scene:
         jd.localAnchorA[0], jd.localAnchorA[1] = linear_offset
         jd.referenceAngle = angular_offset
         jd.length, jd.maxMotor, jd.frequencyHz = max_force, max_torque, correction_factor
+        return len(self.joints) - 1
+
+    def create_mouse_joint(self, body_a, body_b, target, max_force, frequency_hz=5.0, damping_ratio=0.7, collide_connected=False) -> int:
+        """b2MouseJointDef (b2MouseJoint.h:29-55): drags the point of body_b that is at `target` now towards `target`
+        (a soft constraint with a force cap); body_a is unused by the solver (the Testbed passes the ground)."""
+        jd = self._joint(JOINT_MOUSE, body_a, body_b, collide_connected)
+        jd.localAnchorA[0], jd.localAnchorA[1] = target
+        jd.length, jd.frequencyHz, jd.dampingRatio = max_force, frequency_hz, damping_ratio
+        return len(self.joints) - 1
+
+    def create_gear_joint(self, joint1, joint2, ratio=1.0, collide_connected=False) -> int:
+        """b2GearJointDef (b2GearJoint.h:27-47): joint1 / joint2 are indices of revolute or prismatic joints created
+        earlier; coordinate1 + ratio * coordinate2 stays constant.  bodyA / bodyB = the joints' second bodies
+        (b2GearJoint.cpp:59-60, 92-93)."""
+        a, b = self.joints[joint1].bodyB, self.joints[joint2].bodyB
+        jd = self._joint(JOINT_GEAR, a, b, collide_connected)
+        jd.enableLimit, jd.enableMotor, jd.motorSpeed = joint1, joint2, ratio
         return len(self.joints) - 1
 
     def create_pulley_joint(self, body_a, body_b, ground_a, ground_b, anchor_a, anchor_b, ratio=1.0, collide_connected=True) -> int:
@@ -645,6 +662,23 @@ def vehicles(seed: int, flags=WORLD_DEFAULT) -> Scene:
     pb = s.create_body(DYNAMIC_BODY, (-34.0, 5.0 + rng.uniform(0.0, 0.5)))
     s.create_box(pb, 0.5, 0.8, density=5.0)
     s.create_pulley_joint(pa, pb, (-36.0, 11.0), (-34.0, 11.0), (-36.0, 5.8), (-34.0, float(F32(s.bodies[pb].position[1]) + F32(0.8))), ratio=1.5)
+    # ---- gears (Testbed "Gears"): two wheels on ground pivots and a plank on a vertical slide, coupled by two gear joints ----
+    r1, r2 = 0.5, 1.0
+    w1 = s.create_body(DYNAMIC_BODY, (-44.0, 12.0), angular_velocity=rng.uniform(1.0, 3.0))
+    s.create_circle(w1, r1, density=5.0)
+    jw1 = s.create_revolute_joint(g, w1, (-44.0, 12.0))
+    w2 = s.create_body(DYNAMIC_BODY, (-42.5, 12.0))
+    s.create_circle(w2, r2, density=5.0)
+    jw2 = s.create_revolute_joint(g, w2, (-42.5, 12.0))
+    plank = s.create_body(DYNAMIC_BODY, (-41.0, 12.0 + rng.uniform(-0.2, 0.2)))
+    s.create_box(plank, 0.5, 2.5, density=5.0)
+    jpl = s.create_prismatic_joint(g, plank, (-41.0, 12.0), (0.0, 1.0), lower=-5.0, upper=5.0, enable_limit=True)
+    s.create_gear_joint(jw1, jw2, ratio=r2 / r1)
+    s.create_gear_joint(jw2, jpl, ratio=-1.0 / r2)
+    # ---- a crate dragged by a mouse joint towards the point where it was grabbed ----
+    crate = s.create_body(DYNAMIC_BODY, (-48.0, 9.0), linear_velocity=(rng.uniform(2.0, 5.0), 3.0), angular_velocity=2.0)
+    s.create_box(crate, 0.5, 0.5, density=1.0)
+    s.create_mouse_joint(g, crate, (-47.7, 9.3), max_force=1000.0 * 1.0)
     c2 = s.create_body(DYNAMIC_BODY, (2.0, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)
     s.create_box(c2, 0.3, 0.3, density=1.0)
     d2 = s.create_body(DYNAMIC_BODY, (2.6, 8.0), flags=BD_DEFAULT | BD_FIXED_ROTATION)

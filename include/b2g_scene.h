@@ -97,8 +97,8 @@ typedef struct b2g_fixture_def {
 } b2g_fixture_def;
 
 /* Joint types: the values of b2JointType (Box2D/Dynamics/Joints/b2Joint.h:31-45). */
-enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3, B2G_JOINT_PULLEY = 4, B2G_JOINT_WHEEL = 7, B2G_JOINT_WELD = 8,
-       B2G_JOINT_FRICTION = 9, B2G_JOINT_ROPE = 10, B2G_JOINT_MOTOR = 11 };
+enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3, B2G_JOINT_PULLEY = 4, B2G_JOINT_MOUSE = 5, B2G_JOINT_GEAR = 6,
+       B2G_JOINT_WHEEL = 7, B2G_JOINT_WELD = 8, B2G_JOINT_FRICTION = 9, B2G_JOINT_ROPE = 10, B2G_JOINT_MOTOR = 11 };
 
 /* The arguments of b2World::CreateJoint: the members of b2RevoluteJointDef (b2RevoluteJoint.h:35-86),
  * b2PrismaticJointDef (b2PrismaticJoint.h:33-87), b2DistanceJointDef (b2DistanceJoint.h:32-67), b2WheelJointDef
@@ -120,7 +120,12 @@ typedef struct b2g_joint_def {
                                  maxMotor = lengthB, motorSpeed = ratio */
                               /* motor: localAnchorA = linearOffset, referenceAngle = angularOffset, maxMotor = maxTorque,
                                  frequencyHz = correctionFactor */
-    float frequencyHz, dampingRatio; /* distance, wheel, weld */
+                              /* mouse (b2MouseJointDef, b2MouseJoint.h:29-55): localAnchorA = target (world point),
+                                 length = maxForce, frequencyHz, dampingRatio; bodyA is unused by the solver */
+                              /* gear (b2GearJointDef, b2GearJoint.h:27-47): enableLimit = index of joint1, enableMotor =
+                                 index of joint2 in joints[] (revolute or prismatic, created earlier), motorSpeed = ratio;
+                                 the bodies come from those joints, as in b2GearJoint's constructor */
+    float frequencyHz, dampingRatio; /* distance, wheel, weld, mouse */
 } b2g_joint_def;
 
 typedef struct b2g_scene {

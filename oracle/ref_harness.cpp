@@ -190,7 +190,27 @@ RefWorld* build_world(const b2g_scene* s) {
         const b2g_joint_def& d = s->joints[i];
         b2Body* bA = rw->bodies[d.bodyA];
         b2Body* bB = rw->bodies[d.bodyB];
-        if (d.type == B2G_JOINT_REVOLUTE) {
+        if (d.type == B2G_JOINT_MOUSE) {
+            b2MouseJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.target.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.maxForce = d.length; jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
+            w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_GEAR) {
+            // joints[k] of the scene = the k-th CreateJoint call; m_jointList is head-inserted (newest first)
+            auto jointAt = [&](int k) {
+                b2Joint* j = w->GetJointList();
+                for (int n = w->GetJointCount() - 1 - k; n > 0 && j; --n) j = j->GetNext();
+                return j;
+            };
+            b2GearJointDef jd;
+            jd.joint1 = jointAt(d.enableLimit);
+            jd.joint2 = jointAt(d.enableMotor);
+            jd.bodyA = jd.joint1->GetBodyB(); jd.bodyB = jd.joint2->GetBodyB();  // what the Testbed passes; the constructor overrides them
+            jd.collideConnected = d.collideConnected != 0;
+            jd.ratio = d.motorSpeed;
+            w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_REVOLUTE) {
             b2RevoluteJointDef jd;
             jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
             jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);

@@ -192,7 +192,8 @@ static int joints(int steps) {
     pj.Initialize(ground, cart, b2Vec<float, 2>{{0.0f, 3.0f}}, b2Vec<float, 2>{{1.0f, 0.0f}});
     pj.lowerTranslation = -3.0f; pj.upperTranslation = 3.0f; pj.enableLimit = true;
     pj.maxMotorForce = 60.0f; pj.motorSpeed = 2.5f; pj.enableMotor = true;
-    if (!world.CreateJoint(&pj)) return 5;
+    b2Joint* slide = world.CreateJoint(&pj);
+    if (!slide) return 5;
     bd.position = b2Vec<float, 2>{{0.0f, 4.0f}};
     bd.angle = 0.2f;
     b2Body* pole = world.CreateBody(&bd);
@@ -212,8 +213,33 @@ static int joints(int steps) {
     dj.Initialize(ground, bob, b2Vec<float, 2>{{6.0f, 8.0f}}, b2Vec<float, 2>{{8.0f, 6.0f}});
     dj.frequencyHz = 3.0f; dj.dampingRatio = 0.2f;
     if (!world.CreateJoint(&dj)) return 5;
+    // a flywheel on a ground pivot geared to the cart's slide (b2GearJointDef), and a crate held by a mouse joint
+    bd.position = b2Vec<float, 2>{{-6.0f, 5.0f}};
+    b2Body* wheel = world.CreateBody(&bd);
+    b2CircleShape ws;
+    ws.SetRadius(0.5f);
+    wheel->CreateFixture(&ws, 3.0f);
+    b2RevoluteJointDef wj;
+    wj.Initialize(ground, wheel, b2Vec<float, 2>{{-6.0f, 5.0f}});
+    b2Joint* wheelJoint = world.CreateJoint(&wj);
+    if (!wheelJoint) return 5;
+    b2GearJointDef gj;
+    gj.bodyA = wheel; gj.bodyB = cart;
+    gj.joint1 = wheelJoint; gj.joint2 = slide;
+    gj.ratio = -2.0f;
+    if (!world.CreateJoint(&gj)) return 5;
+    bd.position = b2Vec<float, 2>{{12.0f, 4.0f}};
+    b2Body* crate = world.CreateBody(&bd);
+    b2PolygonShape crs;
+    crs.SetAsBox(0.4f, 0.4f);
+    crate->CreateFixture(&crs, 1.0f);
+    b2MouseJointDef mj;
+    mj.bodyA = ground; mj.bodyB = crate;
+    mj.target = b2Vec<float, 2>{{12.2f, 4.3f}};
+    mj.maxForce = 500.0f;
+    if (!world.CreateJoint(&mj)) return 5;
     for (int s = 0; s < steps; ++s) world.Step(1.0f / 60.0f, 8, 3);
-    b2Body* all[3] = {cart, pole, bob};
+    b2Body* all[5] = {cart, pole, bob, wheel, crate};
     for (b2Body* b : all) {
         b2Vec<float, 2> p = b->GetPosition();
         std::printf("%08x %08x %08x\n", bits(p[0]), bits(p[1]), bits(b->GetAngle()));

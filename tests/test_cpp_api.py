@@ -149,19 +149,26 @@ def test_joints_through_cpp_api(exe, oracles):
     s.create_edge(g, (-40.0, 0.0), (40.0, 0.0))
     cart = s.create_body(S.DYNAMIC_BODY, (0.0, 3.0))
     s.create_box(cart, 0.6, 0.25, density=2.0)
-    s.create_prismatic_joint(g, cart, (0.0, 3.0), (1.0, 0.0), lower=-3.0, upper=3.0, enable_limit=True,
-                             max_motor_force=60.0, motor_speed=2.5, enable_motor=True)
+    slide = s.create_prismatic_joint(g, cart, (0.0, 3.0), (1.0, 0.0), lower=-3.0, upper=3.0, enable_limit=True,
+                                     max_motor_force=60.0, motor_speed=2.5, enable_motor=True)
     pole = s.create_body(S.DYNAMIC_BODY, (0.0, 4.0), angle=0.2)
     s.create_box(pole, 0.08, 1.0, density=1.0)
     s.create_revolute_joint(cart, pole, (0.0, 3.0))
     bob = s.create_body(S.DYNAMIC_BODY, (8.0, 6.0))
     s.create_circle(bob, 0.35, density=2.0)
     s.create_distance_joint(g, bob, (6.0, 8.0), (8.0, 6.0), frequency_hz=3.0, damping_ratio=0.2)
+    wheel = s.create_body(S.DYNAMIC_BODY, (-6.0, 5.0))
+    s.create_circle(wheel, 0.5, density=3.0)
+    wheel_joint = s.create_revolute_joint(g, wheel, (-6.0, 5.0))
+    s.create_gear_joint(wheel_joint, slide, ratio=-2.0)
+    crate = s.create_body(S.DYNAMIC_BODY, (12.0, 4.0))
+    s.create_box(crate, 0.4, 0.4, density=1.0)
+    s.create_mouse_joint(g, crate, (12.2, 4.3), max_force=500.0)
     ref = oracles.RefWorld(s)
     for _ in range(200):
         ref.step(1.0 / 60.0, 8, 3)
     rb = ref.bodies()
-    for i, b in enumerate((cart, pole, bob)):
+    for i, b in enumerate((cart, pole, bob, wheel, crate)):
         want = [int(np.float32(v).view(np.uint32)) for v in (rb[b, 0], rb[b, 1], rb[b, 6])]
         assert got[i] == want, f"body {b}: {got[i]} vs {want}"
 
