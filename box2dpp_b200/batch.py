@@ -65,7 +65,8 @@ _lib = None
 BODY_COMMAND_DTYPE = np.dtype([("world", "<i4"), ("body", "<i4"), ("op", "<i4"), ("wake", "<i4"),
                                ("v", "<f4", 2), ("p", "<f4", 2)])
 (CMD_APPLY_FORCE, CMD_APPLY_FORCE_TO_CENTER, CMD_APPLY_TORQUE, CMD_APPLY_LINEAR_IMPULSE, CMD_APPLY_ANGULAR_IMPULSE,
- CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE, CMD_DESTROY_BODY) = range(10)
+ CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE, CMD_DESTROY_BODY,
+ CMD_MOUSE_SET_TARGET) = range(11)
 
 
 AABB_QUERY_DTYPE = np.dtype([("world", "<i4"), ("lower", "<f4", 2), ("upper", "<f4", 2)])       # b2gpu_aabb_query

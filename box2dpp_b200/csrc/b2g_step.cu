@@ -320,6 +320,23 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                 v.z = c.v[0];
                 bodyVel[b] = v;
             } break;
+            case B2GPU_CMD_MOUSE_SET_TARGET: {  // b2MouseJoint::SetTarget — Dynamics/Joints/b2MouseJoint.cpp:54-61
+                int found = -1;
+                if (A.hasJoints) {
+                    Col<int4> jI = col(A.jointI, tile, A.NJ, lane);
+                    for (int j = A.jointCount[ws] - 1; j >= 0 && found < 0; --j) {  // the body's joint list is newest first
+                        const int4 ji = jI[j];
+                        if ((ji.x & 0xff) == B2G_JOINT_MOUSE && ((ji.y >> 16) & 0xffff) == b) found = j;
+                    }
+                }
+                if (found < 0) { A.status[ws] |= B2GPU_STATUS_BAD_COMMAND; break; }
+                if ((f & kBodyAwake) == 0) wake();
+                Col<float4> jF0 = col(A.jointF0, tile, A.NJ, lane);
+                float4 t = jF0[found];
+                t.x = c.v[0];
+                t.y = c.v[1];
+                jF0[found] = t;
+            } break;
             case B2GPU_CMD_DESTROY_BODY: {  // b2World::DestroyBody — Dynamics/b2World.cpp:124-203
                 A.topoDirty[ws] = 1;
                 // 1. the attached joints, in the body's joint-list order (newest first): b2World::DestroyJoint wakes

@@ -307,6 +307,9 @@ public:
     b2Body* GetBodyB() const { return m_bodyB; }
     void* GetUserData() const { return m_userData; }
     int32_t GetIndex() const { return m_index; }  // creation order within the world
+    // b2MouseJoint::SetTarget (Dynamics/Joints/b2MouseJoint.cpp:54-61); ignored for the other joint types.  Queued like
+    // the b2Body edits and applied before the next Step.
+    void SetTarget(const b2Vec<float, 2>& target);
 
 private:
     friend class b2World;
@@ -394,6 +397,8 @@ public:
 private:
     friend class b2World;
     friend class b2WorldBatch;
+    friend class b2Joint;
+    void SetMouseTarget(const b2Vec<float, 2>& target);  // b2Joint::SetTarget of the mouse joint attached to this body
     b2World* m_world = nullptr;
     int32_t m_index = 0;
     b2BodyType m_type = b2BodyType::STATIC_BODY;
@@ -986,6 +991,12 @@ inline void b2WorldBatch::Queue(const b2Body* b, int32_t op, bool wake, float vx
     c.wake = wake ? 1 : 0;
     c.v[0] = vx; c.v[1] = vy; c.p[0] = px; c.p[1] = py;
     m_commands.push_back(c);
+}
+inline void b2Body::SetMouseTarget(const b2Vec<float, 2>& target) {
+    m_world->m_batch->Queue(this, B2GPU_CMD_MOUSE_SET_TARGET, true, target[0], target[1], 0.0f, 0.0f);
+}
+inline void b2Joint::SetTarget(const b2Vec<float, 2>& target) {
+    if (m_type == b2JointType::MOUSE_JOINT && m_bodyB) m_bodyB->SetMouseTarget(target);
 }
 inline void b2Body::ApplyForce(const b2Vec<float, 2>& force, const b2Vec<float, 2>& point, bool wake) {
     m_world->m_batch->Queue(this, B2GPU_CMD_APPLY_FORCE, wake, force[0], force[1], point[0], point[1]);

@@ -65,6 +65,9 @@ enum {
     B2GPU_CMD_DESTROY_BODY = 9,          /*                                   b2World::DestroyBody(body), b2World.cpp:124-203:
                                             its joints, contacts (EndContact events, wake-ups) and proxies go with it;
                                             the body index stays reserved (later commands on it are BAD_COMMAND) */
+    B2GPU_CMD_MOUSE_SET_TARGET = 10,     /* v = target                        b2MouseJoint::SetTarget(target) (b2MouseJoint.cpp:54-61) on the
+                                            mouse joint whose bodyB is `body` (the newest one if it has several): wakes the
+                                            body; BAD_COMMAND if the body carries no mouse joint */
     B2GPU_CMD_COUNT
 };
 typedef struct b2gpu_body_command {

@@ -330,6 +330,15 @@ void ref_world_body_command(void* h, int body, int op, int wake, float vx, float
         rw->bodies[body] = nullptr;
         return;
     }
+    if (op == 10) {  // b2MouseJoint::SetTarget on the newest mouse joint whose bodyB is this body
+        for (b2JointEdge* je = b->GetJointList(); je; je = je->next) {
+            if (je->joint->GetType() == e_mouseJoint && je->joint->GetBodyB() == b) {
+                static_cast<b2MouseJoint*>(je->joint)->SetTarget(b2Vec2(vx, vy));
+                break;
+            }
+        }
+        return;
+    }
     switch (op) {
         case 0: b->ApplyForce(b2Vec2(vx, vy), b2Vec2(px, py), wake != 0); break;
         case 1: b->ApplyForceToCenter(b2Vec2(vx, vy), wake != 0); break;

@@ -115,6 +115,54 @@ def test_bad_command_sets_status():
 
 
 @pytest.mark.gpu
+def test_mouse_joint_set_target_matches_reference(oracles):
+    """b2MouseJoint::SetTarget between steps (B2GPU_CMD_MOUSE_SET_TARGET): a crate on the ground dragged along a path by a
+    mouse joint, parked for a while, then dragged again; bit-identical to the reference."""
+    if not oracles.available("ref"):
+        pytest.skip("checked against the live reference")
+    scenes = []
+    for w in range(6):
+        s = S.Scene()
+        g = s.create_body(S.STATIC_BODY)
+        s.create_box(g, 30.0, 1.0, center=(0.0, -1.0), angle=0.0)
+        crate = s.create_body(S.DYNAMIC_BODY, (0.5 * w, 0.5))
+        s.create_box(crate, 0.5, 0.5, density=1.0, friction=0.4)
+        other = s.create_body(S.DYNAMIC_BODY, (0.5 * w + 2.0, 0.5))
+        s.create_box(other, 0.5, 0.5, density=2.0)
+        s.create_mouse_joint(g, crate, (0.5 * w + 0.2, 0.7), max_force=200.0 + 50.0 * w)
+        scenes.append(s)
+    refs = [oracles.RefWorld(s) for s in scenes]
+    batch = B.WorldBatch(scenes)
+    for step in range(420):
+        rows = []
+        if step < 120 or step >= 330:
+            if step % 3 == 0:
+                for w, r in enumerate(refs):
+                    t = np.float32(step) * np.float32(0.05)
+                    target = (float(np.float32(0.5 * w) + np.float32(3.0) * np.sin(t)), float(np.float32(1.5) + np.cos(t)))
+                    r.command(1, B.CMD_MOUSE_SET_TARGET, 1, target)
+                    rows.append((w, 1, B.CMD_MOUSE_SET_TARGET, 1, target, (0, 0)))
+        if step == 120:  # park it near the ground for 200 steps
+            for w, r in enumerate(refs):
+                target = (0.5 * w + 1.0, 0.45)
+                r.command(1, B.CMD_MOUSE_SET_TARGET, 1, target)
+                rows.append((w, 1, B.CMD_MOUSE_SET_TARGET, 1, target, (0, 0)))
+        if rows:
+            batch.body_commands(np.array(rows, dtype=B.BODY_COMMAND_DTYPE))
+        for r in refs:
+            r.step(1.0 / 60.0, 8, 3)
+        batch.step(1.0 / 60.0, 8, 3)
+        if step % 30 == 29 or step == 329:
+            for w, r in enumerate(refs):
+                compare_world(r, batch.bodies(w), batch.contacts(w), what=f"world {w} step {step}")
+    assert (batch.status() == 0).all()
+    # a body without a mouse joint: BAD_COMMAND
+    batch.body_commands(np.array([(2, 2, B.CMD_MOUSE_SET_TARGET, 1, (0, 0), (0, 0))], dtype=B.BODY_COMMAND_DTYPE))
+    assert batch.status()[2] == 4
+    batch.close()
+
+
+@pytest.mark.gpu
 def test_destroy_body_matches_reference(oracles):
     """b2World::DestroyBody between steps (B2GPU_CMD_DESTROY_BODY): the body's joints, contacts (EndContact events, wake-ups
     of the neighbours) and proxies go with it; everything that remains stays bit-identical to the reference."""
