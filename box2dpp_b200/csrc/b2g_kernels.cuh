@@ -1569,8 +1569,14 @@ __global__ void __launch_bounds__(128) k_find_new_contacts(Arena A) {
 //   E  warp 0: b2ContactManager::AddPair for the remaining candidates in sorted order.
 // Worlds whose move buffer or candidate list overflows the shared-memory lists take UpdatePairsOrdered instead.
 constexpr int kPairWarps = 8;
-constexpr int kMaxMoved = 64;     // per world, else overflow path
-constexpr int kMaxCand = 256;     // per world, else overflow path
+#ifndef B2G_MAX_MOVED
+#define B2G_MAX_MOVED 64
+#endif
+#ifndef B2G_MAX_CAND
+#define B2G_MAX_CAND 256
+#endif
+constexpr int kMaxMoved = B2G_MAX_MOVED;     // per world, else overflow path
+constexpr int kMaxCand = B2G_MAX_CAND;       // per world, else overflow path
 
 __global__ void __launch_bounds__(kPairWarps * 32, 4) k_sync_pairs(Arena A, float dt) {
     __shared__ uint16_t sMoved[kMaxMoved][kTile];

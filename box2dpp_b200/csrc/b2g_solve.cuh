@@ -29,7 +29,10 @@ namespace b2g {
 constexpr int kVelRec = 7;      // float4 per velocity record
 constexpr int kPosRec = 5;      // float4 per position record
 constexpr int kRecStages = 6;   // TMA ring depth of the position kernel (records in flight per tile)
-constexpr int kVelStages = 7;   // TMA ring depth of the velocity kernel
+#ifndef B2G_VEL_STAGES
+#define B2G_VEL_STAGES 7
+#endif
+constexpr int kVelStages = B2G_VEL_STAGES;   // TMA ring depth of the velocity kernel
 constexpr int kImpStages = 8;   // cp.async ring depth for accumulated impulses
 constexpr int kStageBytes = kVelRec * 16 * kTile;  // 3584
 constexpr int kPrepWarps = 8;

@@ -588,6 +588,13 @@ struct b2gpu_batch {
     cudaGraphExec_t graphExecChunk = nullptr;  // kGraphChunk steps (several groups only)
     float graphDt = 0.0f;
     int graphVel = 0, graphPos = 0;
+    // graph of one b2gpu_batch_step_io call (kernels and the groups' host copies), keyed by the host pointers too
+    cudaGraphExec_t graphExecIo = nullptr;
+    const float* ioGraphForces = nullptr;
+    float* ioGraphTransforms = nullptr;
+    float ioGraphDt = 0.0f;
+    int ioGraphVel = 0, ioGraphPos = 0, ioGraphGroups = 0;
+    int64_t ioGraphLaunches = 0;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     float lastStepMs = 0.0f;
     // per-step I/O staging
@@ -774,7 +781,12 @@ int configureKernels(b2gpu_batch* b) {
     // k_islands: as many worlds per CTA as keep two or more CTAs resident per SM (the DFS is latency bound)
     const size_t perWorld = IslandSmemPerWorld(desc->maxBodies, desc->maxContacts, desc->maxJoints > 0 ? desc->maxJoints : 0);
     int L = 32;
-    while (L > 1 && perWorld * L > (size_t)100 * 1024) L >>= 1;
+    size_t islandBudget = (size_t)100 * 1024;
+    if (const char* env = getenv("B2GPU_ISLAND_KB")) {  // experiments: shared memory per k_islands CTA
+        const int kb = atoi(env);
+        if (kb >= 1 && kb <= 200) islandBudget = (size_t)kb * 1024;
+    }
+    while (L > 1 && perWorld * L > islandBudget) L >>= 1;
     if (perWorld * L > (size_t)maxSmem - 1024)
         return fail(B2GPU_ERR_CAPACITY, "a world with %d bodies / %d contacts exceeds the island kernel's shared memory",
                     desc->maxBodies, desc->maxContacts);
@@ -1050,6 +1062,7 @@ int b2gpu_batch_destroy(b2gpu_batch* b) {
     if (b->cmdDev) cudaFree(b->cmdDev);
     if (b->graphExec) cudaGraphExecDestroy(b->graphExec);
     if (b->graphExecChunk) cudaGraphExecDestroy(b->graphExecChunk);
+    if (b->graphExecIo) cudaGraphExecDestroy(b->graphExecIo);
     for (int g = 1; g < b2gpu_batch::kMaxGroups; ++g) {
         if (b->groupStream[g]) { cudaStreamSynchronize(b->groupStream[g]); cudaStreamDestroy(b->groupStream[g]); }
         if (b->evJoin[g]) cudaEventDestroy(b->evJoin[g]);
@@ -1074,6 +1087,7 @@ int b2gpu_batch_upload_field(b2gpu_batch* b, int32_t field, const void* host, in
         for (int32_t i = 0; i < worldCount; ++i)
             if (flags[i] & B2G_WORLD_CONTINUOUS) { b->anyContinuous = true; break; }
         if (b->anyContinuous) {  // the captured steps have no k_toi: capture again
+            if (b->graphExecIo) { cudaGraphExecDestroy(b->graphExecIo); b->graphExecIo = nullptr; }
             if (b->graphExec) { cudaGraphExecDestroy(b->graphExec); b->graphExec = nullptr; }
             if (b->graphExecChunk) { cudaGraphExecDestroy(b->graphExecChunk); b->graphExecChunk = nullptr; }
         }
@@ -1254,6 +1268,7 @@ int64_t b2gpu_batch_launch_count(b2gpu_batch* b) { return b ? b->launches : 0; }
 static int ensureIo(b2gpu_batch* b, size_t need = 0) {
     if (need == 0) need = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
     if (b->ioBytes < need) {
+        if (b->graphExecIo) { cudaGraphExecDestroy(b->graphExecIo); b->graphExecIo = nullptr; }  // it holds the old pointer
         if (b->ioDev) cudaFree(b->ioDev);
         b->ioDev = nullptr;
         CUDA_TRY(cudaMalloc((void**)&b->ioDev, need));
@@ -1312,8 +1327,41 @@ int b2gpu_batch_step_io(b2gpu_batch* b, const float* forces, float dt, int32_t v
     }
     rc = ensureGroupStreams(b, io.groups);
     if (rc != B2GPU_OK) return rc;
-    rc = enqueueSteps(b, dt, velIters, posIters, nullptr, 1, false, &io);
-    if (rc != B2GPU_OK) return rc;
+    // A caller's loop passes the same pinned buffers every step: the whole call (copies included) is then one graph
+    // launch instead of ~100 stream operations.  Pageable buffers cannot be captured; they take the direct path.
+    auto pinned = [](const void* p) {
+        if (!p) return true;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool graphable = !b->needInitialPairs && !b->needProxyIndex && pinned(forces) && pinned(transforms) && !getenv("B2GPU_IO_NO_GRAPH");
+    if (graphable) {
+        const bool same = b->graphExecIo && b->ioGraphForces == forces && b->ioGraphTransforms == transforms && b->ioGraphDt == dt &&
+                          b->ioGraphVel == velIters && b->ioGraphPos == posIters && b->ioGraphGroups == io.groups;
+        if (!same) {
+            if (b->graphExecIo) { cudaGraphExecDestroy(b->graphExecIo); b->graphExecIo = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+            const int64_t before = b->launches;
+            rc = enqueueSteps(b, dt, velIters, posIters, nullptr, 1, false, &io);
+            b->ioGraphLaunches = b->launches - before;
+            b->launches = before;
+            cudaError_t e = cudaStreamEndCapture(b->stream, &graph);
+            if (rc != B2GPU_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "step_io graph capture failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&b->graphExecIo, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { b->graphExecIo = nullptr; return fail(B2GPU_ERR_CUDA, "step_io graph instantiate failed: %s", cudaGetErrorString(e)); }
+            b->ioGraphForces = forces; b->ioGraphTransforms = transforms; b->ioGraphDt = dt;
+            b->ioGraphVel = velIters; b->ioGraphPos = posIters; b->ioGraphGroups = io.groups;
+        }
+        CUDA_TRY(cudaGraphLaunch(b->graphExecIo, b->stream));
+        b->launches += b->ioGraphLaunches;
+    } else {
+        rc = enqueueSteps(b, dt, velIters, posIters, nullptr, 1, false, &io);
+        if (rc != B2GPU_OK) return rc;
+    }
     CUDA_TRY(cudaStreamSynchronize(b->stream));  // joined: the caller holds this step's transforms
     return B2GPU_OK;
 }

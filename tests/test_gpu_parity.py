@@ -374,6 +374,7 @@ def test_step_io_equals_separate_calls():
     sb = S.pyramid_batch(W, 6, flags=NOCCD & ~S.WORLD_ALLOW_SLEEP, first_seed=3, jittered=True)
     rng = np.random.default_rng(5)
     a = WorldBatch(sb)
+    a_max_bodies = a.max_bodies
     forces = np.zeros((W, a.max_bodies, 3), np.float32)
     seq = []
     for k in range(30):
@@ -400,6 +401,16 @@ def test_step_io_equals_separate_calls():
             # either side may be skipped
             b.step_io(None, 1.0 / 60.0, 8, 3, out)
             b.close()
+            if groups is None:  # pinned buffers: the call is replayed from a captured graph (same pointers every step)
+                import torch
+                fp = torch.zeros((W, a_max_bodies, 3), dtype=torch.float32).pin_memory()
+                op = torch.empty((W, a_max_bodies, 4), dtype=torch.float32).pin_memory()
+                b = WorldBatch(sb)
+                for k, f in enumerate(seq):
+                    fp.numpy()[:] = f
+                    b.step_io(fp.numpy(), 1.0 / 60.0, 8, 3, op.numpy())
+                    assert (op.numpy().view(np.uint32) == ref_out[k].view(np.uint32)).all(), f"step {k}, graph path"
+                b.close()
         finally:
             os.environ.pop("B2GPU_IO_GROUPS", None)
 
