@@ -26,7 +26,7 @@ scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     u = dict(zip(hdr, units))
-    name = d["Kernel Name"].split("(")[0]
+    name = d["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0]
     rd = float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]]
     wr = float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]]
     out[name] = {"source": f"profiles/{tag}_{name}_full_raw.csv (ncu --set full --clock-control none)", "worlds": worlds,
