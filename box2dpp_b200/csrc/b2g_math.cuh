@@ -186,8 +186,14 @@ B2G_HD double ReduceLarge(uint32_t xi, int* np) {
 }
 }  // namespace detail
 
-// sin and cos of a float, each bit-identical to glibc's sinf / cosf.
-B2G_HD void SinCos(float y, float* sp, float* cp) {
+// sin and cos of a float, each bit-identical to glibc's sinf / cosf: every range of the argument.  Kept out of line on
+// the device (the large-argument reduction is long and rarely runs); SinCos below handles |y| < pi/4 inline.
+#ifdef __CUDACC__
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+void SinCosGeneral(float y, float* sp, float* cp) {
     const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10,
                  c4 = 0x1.99343027bf8c3p-16;
     const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
@@ -245,6 +251,36 @@ B2G_HD void SinCos(float y, float* sp, float* cp) {
         *sp = cosPoly;
         *cp = sinPoly;
     }
+}
+
+// sinf / cosf as above.  |y| < pi/4 (every resting or slowly turning body) runs inline and branch-free: it is the
+// general path with n = 0, sign = +1 and the plain polynomial table (x * 1.0 is exact, so `xs` is `x`), and the
+// |y| < 2^-12 shortcut (sin = y, cos = 1) becomes a select.
+B2G_HD void SinCos(float y, float* sp, float* cp) {
+    const uint32_t top = (AsUint(y) >> 20) & 0x7ff;
+    if (top < ((0x3f490fdbu >> 20) & 0x7ff)) {
+        const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10,
+                     c4 = 0x1.99343027bf8c3p-16;
+        const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+        const double x = (double)y;
+        const double x2 = b2g_dmul(x, x);
+        const double x3 = b2g_dmul(x, x2);
+        const double sA = b2g_fma(x2, s3, s2);
+        const double x7 = b2g_dmul(x3, x2);
+        const double sB = b2g_fma(x3, s1, x);
+        const float sinPoly = (float)b2g_fma(x7, sA, sB);
+        const double x4 = b2g_dmul(x2, x2);
+        const double cA = b2g_fma(x2, c4, c3);
+        const double cB = b2g_fma(x2, c1, c0);
+        const double x6 = b2g_dmul(x4, x2);
+        const double cC = b2g_fma(x4, c2, cB);
+        const float cosPoly = (float)b2g_fma(x6, cA, cC);
+        const bool tiny = top < ((0x39800000u >> 20) & 0x7ff);  // |y| < 2^-12
+        *sp = tiny ? y : sinPoly;
+        *cp = tiny ? 1.0f : cosPoly;
+        return;
+    }
+    SinCosGeneral(y, sp, cp);
 }
 
 B2G_HD Rot MakeRot(float angle) {

@@ -917,19 +917,22 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
                             Normalize(normal);
                             point = 0.5f * (pointA + pointB);
                             separation = Dot(pointB - pointA, normal) - radiusA - radiusB;
-                        } else if (mtype == kManifoldFaceA) {
-                            normal = Mul(xfA.q, localNormal);
-                            Vec2 planePoint = Mul(xfA, localPoint);
-                            Vec2 clipPoint = Mul(xfB, lp);
-                            separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
-                            point = clipPoint;
                         } else {
-                            normal = Mul(xfB.q, localNormal);
-                            Vec2 planePoint = Mul(xfB, localPoint);
-                            Vec2 clipPoint = Mul(xfA, lp);
+                            // e_faceA / e_faceB (b2ContactSolver.cpp:642-664) are the same arithmetic with the bodies'
+                            // roles swapped: selected, not branched on — lane = world, so one warp holds both kinds
+                            const bool faceA = mtype == kManifoldFaceA;
+                            Xf xfR, xfI;  // the reference face's body, the incident one
+                            xfR.q.s = faceA ? xfA.q.s : xfB.q.s; xfR.q.c = faceA ? xfA.q.c : xfB.q.c;
+                            xfR.p.x = faceA ? xfA.p.x : xfB.p.x; xfR.p.y = faceA ? xfA.p.y : xfB.p.y;
+                            xfI.q.s = faceA ? xfB.q.s : xfA.q.s; xfI.q.c = faceA ? xfB.q.c : xfA.q.c;
+                            xfI.p.x = faceA ? xfB.p.x : xfA.p.x; xfI.p.y = faceA ? xfB.p.y : xfA.p.y;
+                            normal = Mul(xfR.q, localNormal);
+                            Vec2 planePoint = Mul(xfR, localPoint);
+                            Vec2 clipPoint = Mul(xfI, lp);
                             separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
                             point = clipPoint;
-                            normal = -normal;
+                            normal.x = faceA ? normal.x : -normal.x;
+                            normal.y = faceA ? normal.y : -normal.y;
                         }
                         Vec2 rA = point - cAp;
                         Vec2 rB = point - cBp;
