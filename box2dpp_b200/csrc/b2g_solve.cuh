@@ -810,7 +810,6 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
     }
 
     const uint32_t bodyBytes = (uint32_t)A.NB * 3 * kTile * 4;
-    float* sPos = reinterpret_cast<float*>(smem) + lane;
     unsigned char* stages = smem + ((bodyBytes + 127) & ~127u);
     uint32_t* sDone = reinterpret_cast<uint32_t*>(stages + kRecStages * kPosStageBytes) + lane;  // word wd at sDone[wd * 32]
     uint64_t* full = reinterpret_cast<uint64_t*>(stages + kRecStages * kPosStageBytes + (size_t)doneWords * kTile * 4);
@@ -866,16 +865,22 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
     }
     while (!MbarTryWait(bodyBar, 0)) {}
 
-    int s = 0, use = 0;
+    // Loop invariants pinned in registers and every ring / body-table access on 32-bit shared-window addresses, as in
+    // k_solve_velocity: the chain is bound by the instructions the lone consumer warp has to issue per contact.
+    const BodyTable T{Keep(SmemAddr(smem) + (uint32_t)lane * 4)};
+    const uint32_t stage0 = Keep(SmemAddr(stages) + (uint32_t)lane * 16);
+    const uint32_t stageEnd = Keep(stage0 + (uint32_t)depth * kPosStageBytes);
+    const uint32_t full0 = Keep(SmemAddr(full)), empty0 = Keep(SmemAddr(empty));
+    const int nK = Keep(n), nMaxK = Keep(nMax);
+    uint32_t st = stage0, stFull = full0, stEmpty = empty0, parity = 0;
     for (int pass = 0; pass < posIters; ++pass) {
         int isl = 0;
         int islEnd = islands > 0 ? iContactEnd[0] : 0;
         float minSeparation = 0.0f;
         bool islDone = islands > 0 ? ((sDone[0] & 1u) != 0) : true;
-        for (int i = 0; i < nMax; ++i) {
-            const float4* rec = reinterpret_cast<const float4*>(stages + (size_t)s * kPosStageBytes) + lane;
-            while (!MbarTryWait(&full[s], (uint32_t)use & 1u)) {}
-            if (i < n) {
+        for (int i = 0; i < nMaxK; ++i) {
+            while (!MbarTryWaitA(stFull, parity)) {}
+            if (i < nK) {
                 while (i >= islEnd) {  // entering the next island: close the previous one
                     if (!islDone && minSeparation >= -3.0f * kLinearSlop) {
                         sDone[(isl >> 5) * kTile] |= 1u << (isl & 31);
@@ -887,8 +892,8 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
                     islDone = (sDone[(isl >> 5) * kTile] >> (isl & 31) & 1u) != 0;
                 }
                 if (!islDone) {
-                    const float4 r0 = rec[0 * kTile], r1 = rec[1 * kTile], r2 = rec[2 * kTile], r3 = rec[3 * kTile],
-                                 r4 = rec[4 * kTile];
+                    const float4 r0 = LdsF4(st), r1 = LdsF4(st + 512), r2 = LdsF4(st + 1024), r3 = LdsF4(st + 1536),
+                                 r4 = LdsF4(st + 2048);
                     const int packed = __float_as_int(r4.z);
                     const int bodyA = packed & 0x7fff, bodyB = (packed >> 15) & 0x7fff;
                     const int pointCount = (packed >> 30) & 3;
@@ -897,12 +902,11 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
                     const float mA = r2.x, iA = r2.y, mB = r2.z, iB = r2.w;
                     const Vec2 localCenterA = V2(r3.x, r3.y), localCenterB = V2(r3.z, r3.w);
                     const Vec2 localNormal = V2(r0.x, r0.y), localPoint = V2(r0.z, r0.w);
-                    float* pA = sPos + (size_t)bodyA * 3 * kTile;
-                    float* pB = sPos + (size_t)bodyB * 3 * kTile;
-                    Vec2 cAp = V2(pA[0], pA[kTile]), cBp = V2(pB[0], pB[kTile]);
-                    float aA = pA[2 * kTile], aB = pB[2 * kTile];
-                    for (int j = 0; j < pointCount; ++j) {
-                        const Vec2 lp = j == 0 ? V2(r1.x, r1.y) : V2(r1.z, r1.w);
+                    const uint32_t pA = T.at(bodyA), pB = T.at(bodyB);
+                    Vec2 cAp = V2(LdsF(pA), LdsF(pA + 128)), cBp = V2(LdsF(pB), LdsF(pB + 128));
+                    float aA = LdsF(pA + 256), aB = LdsF(pB + 256);
+                    // one manifold point (b2ContactSolver.cpp:687-734)
+                    auto solvePoint = [&](const Vec2 lp) {
                         Xf xfA, xfB;
                         xfA.q = MakeRot(aA);
                         xfB.q = MakeRot(aB);
@@ -947,13 +951,18 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
                         aA -= iA * Cross(rA, P);
                         cBp = cBp + mB * P;
                         aB += iB * Cross(rB, P);
-                    }
-                    pA[0] = cAp.x; pA[kTile] = cAp.y; pA[2 * kTile] = aA;
-                    pB[0] = cBp.x; pB[kTile] = cBp.y; pB[2 * kTile] = aB;
+                    };
+                    if (pointCount > 0) solvePoint(V2(r1.x, r1.y));
+                    if (pointCount > 1) solvePoint(V2(r1.z, r1.w));
+                    StsF(pA, cAp.x); StsF(pA + 128, cAp.y); StsF(pA + 256, aA);
+                    StsF(pB, cBp.x); StsF(pB + 128, cBp.y); StsF(pB + 256, aB);
                 }
             }
-            MbarArrive(&empty[s]);
-            if (++s == depth) { s = 0; ++use; }
+            MbarArriveA(stEmpty);
+            st += kPosStageBytes;
+            stFull += 8;
+            stEmpty += 8;
+            if (st == stageEnd) { st = stage0; stFull = full0; stEmpty = empty0; parity ^= 1u; }
         }
         if (n > 0 && !islDone && minSeparation >= -3.0f * kLinearSlop) {  // close the last island of this pass
             sDone[(isl >> 5) * kTile] |= 1u << (isl & 31);
