@@ -28,7 +28,10 @@ namespace b2g {
 
 constexpr int kVelRec = 7;      // float4 per velocity record
 constexpr int kPosRec = 5;      // float4 per position record
-constexpr int kRecStages = 6;   // TMA ring depth of the position kernel (records in flight per tile)
+#ifndef B2G_REC_STAGES
+#define B2G_REC_STAGES 6
+#endif
+constexpr int kRecStages = B2G_REC_STAGES;   // TMA ring depth of the position kernel (records in flight per tile)
 #ifndef B2G_VEL_STAGES
 #define B2G_VEL_STAGES 7
 #endif
