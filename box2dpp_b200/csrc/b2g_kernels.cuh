@@ -52,13 +52,15 @@ __device__ __forceinline__ Xf LoadXf(const Col<float4>& c, int i) {
 struct DevPoly {
     const float* w;  // word 0 of the shape for this lane; word k at w[k * 32]
     int n;
-    __device__ __forceinline__ DevPoly(const float* base) : w(base) { n = __float_as_int(base[0]); }
+    // the shape table is immutable while a step kernel runs (written at build / spawn time only): read-only path
+    __device__ __forceinline__ float ld(int k) const { return __ldg(w + k); }
+    __device__ __forceinline__ DevPoly(const float* base) : w(base) { n = __float_as_int(__ldg(base)); }
     __device__ __forceinline__ int count() const { return n; }
-    __device__ __forceinline__ float radius() const { return w[1 * kTile]; }
-    __device__ __forceinline__ Vec2 centroid() const { return V2(w[2 * kTile], w[3 * kTile]); }
-    __device__ __forceinline__ Vec2 vert(int i) const { return V2(w[(4 + 2 * i) * kTile], w[(5 + 2 * i) * kTile]); }
+    __device__ __forceinline__ float radius() const { return ld(1 * kTile); }
+    __device__ __forceinline__ Vec2 centroid() const { return V2(ld(2 * kTile), ld(3 * kTile)); }
+    __device__ __forceinline__ Vec2 vert(int i) const { return V2(ld((4 + 2 * i) * kTile), ld((5 + 2 * i) * kTile)); }
     __device__ __forceinline__ Vec2 normal(int i) const {
-        return V2(w[(4 + 2 * n + 2 * i) * kTile], w[(5 + 2 * n + 2 * i) * kTile]);
+        return V2(ld((4 + 2 * n + 2 * i) * kTile), ld((5 + 2 * n + 2 * i) * kTile));
     }
 };
 __device__ __forceinline__ CircleData LoadCircle(const float* w) {
