@@ -55,20 +55,30 @@ struct ClipVertex {
     uint32_t key;
 };
 
-// b2ClipSegmentToLine
+// b2ClipSegmentToLine.  The reference appends to vOut[numOut++]; here the two output slots are selected with the same
+// predicates (both inputs kept leaves no room for the crossing point: d0, d1 <= 0 makes d0 * d1 >= 0), so the arrays are
+// indexed statically and stay in registers instead of local memory.
 B2G_HD int ClipSegmentToLine(ClipVertex vOut[2], const ClipVertex vIn[2], Vec2 normal, float offset, int vertexIndexA) {
-    int numOut = 0;
-    float distance0 = Dot(normal, vIn[0].v) - offset;
-    float distance1 = Dot(normal, vIn[1].v) - offset;
-    if (distance0 <= 0.0f) vOut[numOut++] = vIn[0];
-    if (distance1 <= 0.0f) vOut[numOut++] = vIn[1];
-    if (distance0 * distance1 < 0.0f) {
+    const float distance0 = Dot(normal, vIn[0].v) - offset;
+    const float distance1 = Dot(normal, vIn[1].v) - offset;
+    const bool keep0 = distance0 <= 0.0f, keep1 = distance1 <= 0.0f;
+    const bool cross = distance0 * distance1 < 0.0f;
+    ClipVertex x = vIn[1];  // the crossing point, evaluated only when it exists (as the reference does)
+    if (cross) {
         float interp = Div(distance0, distance0 - distance1);
-        vOut[numOut].v = vIn[0].v + interp * (vIn[1].v - vIn[0].v);
-        vOut[numOut].key = MakeKey(vertexIndexA, (vIn[0].key >> 8) & 0xff, kFeatureVertex, kFeatureFace);
-        ++numOut;
+        x.v = vIn[0].v + interp * (vIn[1].v - vIn[0].v);
+        x.key = MakeKey(vertexIndexA, (vIn[0].key >> 8) & 0xff, kFeatureVertex, kFeatureFace);
     }
-    return numOut;
+    // slot 0: the first of (in0 if kept, in1 if kept, crossing point); slot 1: the next one
+    const ClipVertex in0 = vIn[0], in1 = vIn[1];
+    vOut[0].v.x = keep0 ? in0.v.x : (keep1 ? in1.v.x : x.v.x);
+    vOut[0].v.y = keep0 ? in0.v.y : (keep1 ? in1.v.y : x.v.y);
+    vOut[0].key = keep0 ? in0.key : (keep1 ? in1.key : x.key);
+    const bool both = keep0 && keep1;
+    vOut[1].v.x = both ? in1.v.x : x.v.x;
+    vOut[1].v.y = both ? in1.v.y : x.v.y;
+    vOut[1].key = both ? in1.key : x.key;
+    return (keep0 ? 1 : 0) + (keep1 ? 1 : 0) + (cross ? 1 : 0);
 }
 
 // b2FindMaxSeparation
