@@ -102,8 +102,10 @@ enum { B2G_JOINT_REVOLUTE = 1, B2G_JOINT_PRISMATIC = 2, B2G_JOINT_DISTANCE = 3, 
 
 /* The arguments of b2World::CreateJoint: the members of b2RevoluteJointDef (b2RevoluteJoint.h:35-86),
  * b2PrismaticJointDef (b2PrismaticJoint.h:33-87), b2DistanceJointDef (b2DistanceJoint.h:32-67), b2WheelJointDef
- * (b2WheelJoint.h:33-73) and b2WeldJointDef (b2WeldJoint.h:30-62), already in the
- * bodies' local frames (what the defs' Initialize() helpers compute). */
+ * (b2WheelJoint.h:33-73), b2WeldJointDef (b2WeldJoint.h:30-62), b2RopeJointDef, b2FrictionJointDef, b2MotorJointDef,
+ * b2PulleyJointDef, b2MouseJointDef and b2GearJointDef (all eleven b2JointType values), already in the bodies' local
+ * frames (what the defs' Initialize() helpers compute).  One record serves every type; the comments on the fields say
+ * which def member each type keeps where. */
 typedef struct b2g_joint_def {
     int32_t type;             /* B2G_JOINT_* */
     int32_t bodyA, bodyB;     /* indices into bodies[] */
