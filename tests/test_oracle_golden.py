@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import golden_cases as G
+from box2dpp_b200 import scene as S
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -134,3 +135,33 @@ def test_port_equals_reference_every_float(oracles):
             p.step(1.0 / 60.0, 8, 3)
             if step % 3 == 0:
                 compare_world(r, p.bodies(), p.contacts(), p.proxies()[0], p.events(), what=f"scene {si} step {step}")
+
+
+def test_reference_gear_and_mouse_joints_behave(oracles):
+    """Semantic check of the oracle harness for the two joint types added last (gear, mouse): the gear constraint
+    coordinate1 + ratio * coordinate2 stays at its initial value (b2GearJoint.cpp:287-383) and the mouse joint holds
+    its crate near the target — i.e. the scene builder and ref_harness.cpp wire the defs the way the Testbed does."""
+    if not oracles.available("ref"):
+        pytest.skip("needs the live reference (oracle/_ref)")
+    s = S.Scene()
+    g = s.create_body(S.STATIC_BODY)
+    s.create_box(g, 30.0, 1.0, center=(0.0, -1.0), angle=0.0)
+    w1 = s.create_body(S.DYNAMIC_BODY, (-4.0, 6.0), angular_velocity=3.0)
+    s.create_circle(w1, 0.5, density=5.0)
+    j1 = s.create_revolute_joint(g, w1, (-4.0, 6.0))
+    w2 = s.create_body(S.DYNAMIC_BODY, (-2.5, 6.0))
+    s.create_circle(w2, 1.0, density=5.0)
+    j2 = s.create_revolute_joint(g, w2, (-2.5, 6.0))
+    ratio = 2.0
+    s.create_gear_joint(j1, j2, ratio=ratio)
+    crate = s.create_body(S.DYNAMIC_BODY, (5.0, 4.0))
+    s.create_box(crate, 0.4, 0.4, density=1.0)
+    s.create_mouse_joint(g, crate, (5.0, 4.0), max_force=1000.0)
+    ref = oracles.RefWorld(s)
+    for _ in range(120):
+        ref.step(1.0 / 60.0, 8, 3)
+    b = ref.bodies()
+    a1, a2 = float(b[w1, 6]), float(b[w2, 6])
+    assert abs(a1) > 0.5, "the driven wheel should have turned"
+    assert abs(a1 + ratio * a2) < 0.05, (a1, a2)
+    assert abs(float(b[crate, 0]) - 5.0) < 0.1 and abs(float(b[crate, 1]) - 4.0) < 0.3, b[crate, :2]
