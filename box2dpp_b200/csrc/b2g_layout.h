@@ -149,6 +149,7 @@ struct Arena {
     float* solveVel;     // [tile][NB][3][lane]  b2Velocity table (v.x, v.y, w): TMA source / sink of the velocity kernel
     float* solvePos;     // [tile][NB][3][lane]  b2Position table (c.x, c.y, a)
     int* solveCount;     // [tile][lane]         island contacts of this step (all islands)
+    int* solveFlags;     // [tile][lane]         bit 0: some island contact has an e_circles manifold
     int* islandSolved;   // [tile][ceil(NB/32)][lane]  bit per island: position solver converged
 
     // ---- continuous collision (b2World::SolveTOI) ----

@@ -283,6 +283,33 @@ B2G_HD void SinCos(float y, float* sp, float* cp) {
     SinCosGeneral(y, sp, cp);
 }
 
+// The |y| < pi/4 arithmetic of SinCos without the range test (InSinCosFastRange is the caller's business): the sequential
+// solver evaluates it unconditionally and redoes the contact through SinCos when an angle was out of range.
+B2G_HD bool InSinCosFastRange(float y) { return ((AsUint(y) >> 20) & 0x7ff) < ((0x3f490fdbu >> 20) & 0x7ff); }
+B2G_HD Rot MakeRotFastRange(float y) {
+    const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10,
+                 c4 = 0x1.99343027bf8c3p-16;
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double x = (double)y;
+    const double x2 = b2g_dmul(x, x);
+    const double x3 = b2g_dmul(x, x2);
+    const double sA = b2g_fma(x2, s3, s2);
+    const double x7 = b2g_dmul(x3, x2);
+    const double sB = b2g_fma(x3, s1, x);
+    const float sinPoly = (float)b2g_fma(x7, sA, sB);
+    const double x4 = b2g_dmul(x2, x2);
+    const double cA = b2g_fma(x2, c4, c3);
+    const double cB = b2g_fma(x2, c1, c0);
+    const double x6 = b2g_dmul(x4, x2);
+    const double cC = b2g_fma(x4, c2, cB);
+    const float cosPoly = (float)b2g_fma(x6, cA, cC);
+    const bool tiny = ((AsUint(y) >> 20) & 0x7ff) < ((0x39800000u >> 20) & 0x7ff);  // |y| < 2^-12
+    Rot q;
+    q.s = tiny ? y : sinPoly;
+    q.c = tiny ? 1.0f : cosPoly;
+    return q;
+}
+
 B2G_HD Rot MakeRot(float angle) {
     Rot q;
     SinCos(angle, &q.s, &q.c);

@@ -22,6 +22,8 @@
 // every rounding — is exactly the reference's.
 #pragma once
 
+#include <type_traits>
+
 #include "b2g_kernels.cuh"
 
 namespace b2g {
@@ -29,13 +31,21 @@ namespace b2g {
 constexpr int kVelRec = 7;      // float4 per velocity record
 constexpr int kPosRec = 5;      // float4 per position record
 #ifndef B2G_REC_STAGES
-#define B2G_REC_STAGES 6
+#define B2G_REC_STAGES 8
 #endif
 constexpr int kRecStages = B2G_REC_STAGES;   // TMA ring depth of the position kernel (records in flight per tile)
 #ifndef B2G_VEL_STAGES
-#define B2G_VEL_STAGES 7
+#define B2G_VEL_STAGES 8
 #endif
 constexpr int kVelStages = B2G_VEL_STAGES;   // TMA ring depth of the velocity kernel
+#ifndef B2G_VEL_PREFETCH
+#define B2G_VEL_PREFETCH 24
+#endif
+constexpr int kVelPrefetch = B2G_VEL_PREFETCH;  // records pulled into L2 ahead of the velocity ring (0 = off)
+#ifndef B2G_POS_PREFETCH
+#define B2G_POS_PREFETCH 16
+#endif
+constexpr int kPosPrefetch = B2G_POS_PREFETCH;
 constexpr int kImpStages = 8;   // cp.async ring depth for accumulated impulses
 constexpr int kStageBytes = kVelRec * 16 * kTile;  // 3584
 constexpr int kPrepWarps = 8;
@@ -69,6 +79,10 @@ __device__ __forceinline__ void TmaStore1D(void* dst, const void* src, uint32_t 
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(SmemAddr(src)), "r"(bytes)
                  : "memory");
 }
+// global -> L2 bulk prefetch (no destination: the later TMA load of the same bytes finds them in L2)
+__device__ __forceinline__ void TmaPrefetchL2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void TmaStoreCommitAndWait() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -87,8 +101,11 @@ __device__ __forceinline__ void CpAsyncWait() {
 __device__ __forceinline__ int PackBodies(int bodyA, int bodyB, int pointCount) { return bodyA | (bodyB << 15) | (pointCount << 30); }
 
 // Shared-memory budget of the sequential kernels for a world capacity of NB bodies.
+// The tile's body table in shared memory: NB rows of 3 floats x 32 lanes, plus one scratch row that lanes without a
+// contact at the current index work on.
+__host__ __device__ inline size_t SolveTableBytes(int NB) { return ((size_t)(NB + 1) * 3 * kTile * 4 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t SolveSmemBytes(int NB) {
-    size_t body = ((size_t)NB * 3 * kTile * 4 + 127) & ~(size_t)127;
+    size_t body = SolveTableBytes(NB);
     size_t done = (size_t)((NB + 31) / 32) * kTile * 4;
     size_t vel = (size_t)kVelStages * (kVelRec + 1) * 16 * kTile + 256;                // ring + barriers
     size_t pos = (size_t)kRecStages * kPosRec * 16 * kTile + done + 256;
@@ -122,6 +139,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32, B2G_PREP_MIN_BLOCKS) k_solve_
     Col<float4> bodyMass = col(A.bodyMass, tile, A.NB, lane);
     Col<float4> bodyDamp = col(A.bodyDamp, tile, A.NB, lane);
     float* sv = A.solveVel + (size_t)tile * A.NB * 3 * kTile + lane;  // [body][3][lane]
+    if (warp == 0) A.solveFlags[ws] = 0;  // set again below, behind the barrier
 
     // ---- integrate velocities of island bodies; every body's velocity goes into the solver table ----
     const int nbMax = __reduce_max_sync(0xffffffffu, nb);
@@ -169,8 +187,11 @@ __global__ void __launch_bounds__(kPrepWarps * 32, B2G_PREP_MIN_BLOCKS) k_solve_
     const int n = islands > 0 ? iContactEnd[islands - 1] : 0;
     const int nMax = __reduce_max_sync(0xffffffffu, n);
     if (warp == 0) A.solveCount[ws] = n;
+    int isl = 0, islEnd = islands > 0 ? iContactEnd[0] : 0;  // island of contact i (i only grows)
+    bool circles = false;
     for (int i = warp; i < nMax; i += kPrepWarps) {
         if (i >= n) continue;
+        while (i >= islEnd) islEnd = iContactEnd[++isl];
         const int k = iContacts[i];
         const int4 a = cA[k];
         const int bodyA = a.y & 0xffff, bodyB = (a.y >> 16) & 0xffff;
@@ -309,8 +330,12 @@ __global__ void __launch_bounds__(kPrepWarps * 32, B2G_PREP_MIN_BLOCKS) k_solve_
         pr[1 * kTile] = make_float4(p0.x, p0.y, p1.x, p1.y);
         pr[2 * kTile] = make_float4(mA, iA, mB, iB);
         pr[3 * kTile] = make_float4(msA.z, msA.w, msB.z, msB.w);
-        pr[4 * kTile] = make_float4(radiusA, radiusB, __int_as_float(PackBodies(bodyA, bodyB, pointCount)), __int_as_float(mtype));
+        // manifold type | last contact of its island << 2 | island << 8
+        pr[4 * kTile] = make_float4(radiusA, radiusB, __int_as_float(PackBodies(bodyA, bodyB, pointCount)),
+                                    __int_as_float(mtype | (i == islEnd - 1 ? 4 : 0) | (isl << 8)));
+        circles |= mtype == kManifoldCircles;
     }
+    if (circles) atomicOr(&A.solveFlags[ws], 1);  // k_solve_position picks its e_circles-capable variant
 }
 
 // =================================================================================================
@@ -355,6 +380,12 @@ __device__ __forceinline__ float LdsF(uint32_t a) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint32_t LdsU(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void StsU(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void StsF(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
 __device__ __forceinline__ void StsF4(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
@@ -395,144 +426,180 @@ struct BodyTable {
     __device__ __forceinline__ uint32_t at(int b) const { return base + (uint32_t)b * (3 * kTile * 4); }
 };
 
+// One velocity record in registers, with the shared-memory addresses of its two bodies' table rows.
 struct VelRecord {
     float4 q0, q1, q2, q3, q4, q5, q6, imp;
+    uint32_t pA, pB;  // table rows (a lane without a contact at this index points both at its scratch row)
+    int points;       // manifold points of this lane's contact (0: no contact at this index, nothing to solve)
 };
-__device__ __forceinline__ VelRecord LoadVelRecord(uint32_t st) {  // st: shared address of this lane's float4 0
-    VelRecord r;
+// The six floats of a contact's two b2Velocity entries.
+struct BodyVals {
+    float ax, ay, aw, bx, by, bw;
+};
+__device__ __forceinline__ void IssueVelRecord(VelRecord& r, uint32_t st) {
     r.q0 = LdsF4(st + 0 * 512); r.q1 = LdsF4(st + 1 * 512); r.q2 = LdsF4(st + 2 * 512); r.q3 = LdsF4(st + 3 * 512);
     r.q4 = LdsF4(st + 4 * 512); r.q5 = LdsF4(st + 5 * 512); r.q6 = LdsF4(st + 6 * 512); r.imp = LdsF4(st + 7 * 512);
-    return r;
+}
+__device__ __forceinline__ void TouchF4(float4& v) { asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)); }
+// Decode the record issued by IssueVelRecord (this is the first use of the loaded registers, i.e. where the loads
+// are waited for: it is placed a whole contact solve after IssueVelRecord).
+__device__ __forceinline__ void FinishVelRecord(VelRecord& r, bool active, BodyTable T, uint32_t scratch) {
+    TouchF4(r.q0); TouchF4(r.q1); TouchF4(r.q2); TouchF4(r.q3); TouchF4(r.q4); TouchF4(r.q5); TouchF4(r.q6); TouchF4(r.imp);
+    const int packed = __float_as_int(r.q0.w);
+    r.pA = active ? T.at(packed & 0x7fff) : scratch;
+    r.pB = active ? T.at((packed >> 15) & 0x7fff) : scratch;
+    const int pointCount = (packed >> 30) & 3;
+    r.points = active ? (pointCount > 1 ? 2 : pointCount) : 0;
+}
+__device__ __forceinline__ BodyVals LoadBodyVals(uint32_t pA, uint32_t pB) {
+    BodyVals b;
+    b.ax = LdsF(pA); b.ay = LdsF(pA + 128); b.aw = LdsF(pA + 256);
+    b.bx = LdsF(pB); b.by = LdsF(pB + 128); b.bw = LdsF(pB + 256);
+    return b;
+}
+__device__ __forceinline__ void StoreBodyVals(uint32_t pA, uint32_t pB, const BodyVals& b) {
+    StsF(pA, b.ax); StsF(pA + 128, b.ay); StsF(pA + 256, b.aw);
+    StsF(pB, b.bx); StsF(pB + 128, b.by); StsF(pB + 256, b.bw);
+}
+// Store-to-load forwarding by hand: `loaded` was read from the table BEFORE `cur` (the values the previous contact
+// left for its bodies, rows curA / curB) was stored, so rows the two contacts share are taken from `cur` instead.
+__device__ __forceinline__ BodyVals ForwardBodyVals(const BodyVals& loaded, const BodyVals& cur, uint32_t pA, uint32_t pB,
+                                                    uint32_t curA, uint32_t curB) {
+    const bool aa = pA == curA, ab = pA == curB, ba = pB == curA, bb = pB == curB;
+    BodyVals o;
+    o.ax = aa ? cur.ax : (ab ? cur.bx : loaded.ax);
+    o.ay = aa ? cur.ay : (ab ? cur.by : loaded.ay);
+    o.aw = aa ? cur.aw : (ab ? cur.bw : loaded.aw);
+    o.bx = ba ? cur.ax : (bb ? cur.bx : loaded.bx);
+    o.by = ba ? cur.ay : (bb ? cur.by : loaded.by);
+    o.bw = ba ? cur.aw : (bb ? cur.bw : loaded.bw);
+    return o;
 }
 
-// WarmStart of one contact (b2ContactSolver.cpp:240-278)
-__device__ __forceinline__ void WarmStartContact(const VelRecord& r, BodyTable T) {
-    const int packed = __float_as_int(r.q0.w);
-    const int bodyA = packed & 0x7fff, bodyB = (packed >> 15) & 0x7fff;
-    const int pointCount = (packed >> 30) & 3;
+// WarmStart of one contact (b2ContactSolver.cpp:240-278) on body values held in registers
+__device__ __forceinline__ void WarmStartContact(const VelRecord& r, BodyVals& bv) {
+    const int points = r.points;
     const float mA = r.q1.x, iA = r.q1.y, mB = r.q1.z, iB = r.q1.w;
-    const uint32_t pA = T.at(bodyA), pB = T.at(bodyB);
-    Vec2 vA = V2(LdsF(pA), LdsF(pA + 128)), vB = V2(LdsF(pB), LdsF(pB + 128));
-    float wA = LdsF(pA + 256), wB = LdsF(pB + 256);
+    Vec2 vA = V2(bv.ax, bv.ay), vB = V2(bv.bx, bv.by);
+    float wA = bv.aw, wB = bv.bw;
     const Vec2 normal = V2(r.q0.x, r.q0.y);
     const Vec2 tangent = Cross(normal, 1.0f);
-    {
+    if (points > 0) {
         Vec2 P = r.imp.x * normal + r.imp.y * tangent;
         wA -= iA * Cross(V2(r.q2.x, r.q2.y), P);
         vA = vA - mA * P;
         wB += iB * Cross(V2(r.q2.z, r.q2.w), P);
         vB = vB + mB * P;
     }
-    if (pointCount > 1) {
+    if (points > 1) {
         Vec2 P = r.imp.z * normal + r.imp.w * tangent;
         wA -= iA * Cross(V2(r.q4.x, r.q4.y), P);
         vA = vA - mA * P;
         wB += iB * Cross(V2(r.q4.z, r.q4.w), P);
         vB = vB + mB * P;
     }
-    StsF(pA, vA.x); StsF(pA + 128, vA.y); StsF(pA + 256, wA);
-    StsF(pB, vB.x); StsF(pB + 128, vB.y); StsF(pB + 256, wB);
+    bv.ax = vA.x; bv.ay = vA.y; bv.aw = wA;
+    bv.bx = vB.x; bv.by = vB.y; bv.bw = wB;
 }
 
-// SolveVelocityConstraints for one contact (b2ContactSolver.cpp:280-597); returns the updated impulses
-__device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, BodyTable T) {
-    const float4 q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3;
+// One point's friction constraint (b2ContactSolver.cpp:305-333; tangentSpeed is 0: b2Contact::SetTangentSpeed is
+// not exposed)
+__device__ __forceinline__ void SolveTangent(Vec2& vA, float& wA, Vec2& vB, float& wB, Vec2 rA, Vec2 rB, Vec2 tangent,
+                                             float tangentMass, float friction, float normalImpulse, float& tangentImpulse,
+                                             float mA, float iA, float mB, float iB) {
+    Vec2 dv = vB + Cross(wB, rB) - vA - Cross(wA, rA);
+    float vt = Dot(dv, tangent) - 0.0f;
+    float lambda = tangentMass * (-vt);
+    float maxFriction = friction * normalImpulse;
+    float newImpulse = Clamp(tangentImpulse + lambda, -maxFriction, maxFriction);
+    lambda = newImpulse - tangentImpulse;
+    tangentImpulse = newImpulse;
+    Vec2 P = lambda * tangent;
+    vA = vA - mA * P;
+    wA -= iA * Cross(rA, P);
+    vB = vB + mB * P;
+    wB += iB * Cross(rB, P);
+}
+
+// SolveVelocityConstraints for one contact (b2ContactSolver.cpp:280-597), straight-line for every point count: the
+// friction constraint of point 0 is common; then the one-point normal constraint and (friction of point 1 + block
+// solver) are both evaluated — they are independent, the one-point arithmetic fills issue slots the two-point chain
+// leaves empty — and the result of the contact's own point count is selected.  The reference tries the block
+// solver's four cases in order and takes the first feasible one; here all four are evaluated and the same one is
+// selected.  `points` == 0 (no contact for this lane at this index): any result will do, it goes to the scratch row.
+__device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, BodyVals& bv) {
+    const float4 q0 = r.q0, q1 = r.q1, q2 = r.q2, q3 = r.q3, q4 = r.q4, q5 = r.q5, q6 = r.q6;
     float4 imp = r.imp;
-    const int packed = __float_as_int(q0.w);
-    const int bodyA = packed & 0x7fff, bodyB = (packed >> 15) & 0x7fff;
-    const int pointCount = (packed >> 30) & 3;
     const float mA = q1.x, iA = q1.y, mB = q1.z, iB = q1.w;
-    const uint32_t pA = T.at(bodyA), pB = T.at(bodyB);
-    Vec2 vA = V2(LdsF(pA), LdsF(pA + 128)), vB = V2(LdsF(pB), LdsF(pB + 128));
-    float wA = LdsF(pA + 256), wB = LdsF(pB + 256);
+    Vec2 vA = V2(bv.ax, bv.ay), vB = V2(bv.bx, bv.by);
+    float wA = bv.aw, wB = bv.bw;
     const Vec2 normal = V2(q0.x, q0.y);
     const Vec2 tangent = Cross(normal, 1.0f);
     const Vec2 rA0 = V2(q2.x, q2.y), rB0 = V2(q2.z, q2.w);
+    const Vec2 rA1 = V2(q4.x, q4.y), rB1 = V2(q4.z, q4.w);
     const float friction = q0.z;
-    {  // tangent constraint of point 0 (tangentSpeed is 0: b2Contact::SetTangentSpeed is not exposed)
-        Vec2 dv = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
-        float vt = Dot(dv, tangent) - 0.0f;
-        float lambda = q3.y * (-vt);
-        float maxFriction = friction * imp.x;
-        float newImpulse = Clamp(imp.y + lambda, -maxFriction, maxFriction);
-        lambda = newImpulse - imp.y;
-        imp.y = newImpulse;
-        Vec2 P = lambda * tangent;
-        vA = vA - mA * P;
-        wA -= iA * Cross(rA0, P);
-        vB = vB + mB * P;
-        wB += iB * Cross(rB0, P);
-    }
-    if (pointCount == 1) {
+    SolveTangent(vA, wA, vB, wB, rA0, rB0, tangent, q3.y, friction, imp.x, imp.y, mA, iA, mB, iB);
+    // ---- one point: normal constraint (b2ContactSolver.cpp:336-371) ----
+    Vec2 vA1 = vA, vB1 = vB;
+    float wA1 = wA, wB1 = wB, impX1;
+    {
         Vec2 dv = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
         float vn = Dot(dv, normal);
         float lambda = -q3.x * (vn - q3.z);
         float newImpulse = Max(imp.x + lambda, 0.0f);
         lambda = newImpulse - imp.x;
-        imp.x = newImpulse;
+        impX1 = newImpulse;
         Vec2 P = lambda * normal;
-        vA = vA - mA * P;
-        wA -= iA * Cross(rA0, P);
-        vB = vB + mB * P;
-        wB += iB * Cross(rB0, P);
-    } else {
-        const float4 q4 = r.q4, q5 = r.q5, q6 = r.q6;
-        const Vec2 rA1 = V2(q4.x, q4.y), rB1 = V2(q4.z, q4.w);
-        {  // tangent constraint of point 1
-            Vec2 dv = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
-            float vt = Dot(dv, tangent) - 0.0f;
-            float lambda = q5.y * (-vt);
-            float maxFriction = friction * imp.z;
-            float newImpulse = Clamp(imp.w + lambda, -maxFriction, maxFriction);
-            lambda = newImpulse - imp.w;
-            imp.w = newImpulse;
-            Vec2 P = lambda * tangent;
-            vA = vA - mA * P;
-            wA -= iA * Cross(rA1, P);
-            vB = vB + mB * P;
-            wB += iB * Cross(rB1, P);
-        }
-        // block solver (b2ContactSolver.cpp:388-589).  The reference tries four cases in order and takes the
-        // first feasible one; here all four are evaluated branch-free and the same one is selected.
-        const float k11 = q5.z, k12 = q5.w, k22 = q6.x;
-        const float nmxx = q6.y, nmxy = q6.z, nmyy = q6.w;  // normalMass = K^-1 (symmetric)
-        const Vec2 a = V2(imp.x, imp.z);
-        Vec2 dv1 = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
-        Vec2 dv2 = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
-        float vn1 = Dot(dv1, normal);
-        float vn2 = Dot(dv2, normal);
-        Vec2 b;
-        b.x = vn1 - q3.z;
-        b.y = vn2 - q3.w;
-        b.x -= k11 * a.x + k12 * a.y;
-        b.y -= k12 * a.x + k22 * a.y;
-        const float x1 = -(nmxx * b.x + nmxy * b.y);  // case 1: x = -normalMass * b
-        const float y1 = -(nmxy * b.x + nmyy * b.y);
-        const bool ok1 = x1 >= 0.0f && y1 >= 0.0f;
-        const float x2 = -q3.x * b.x;                  // case 2: x2 = 0
-        const bool ok2 = x2 >= 0.0f && (k12 * x2 + b.y) >= 0.0f;
-        const float y3 = -q5.x * b.y;                  // case 3: x1 = 0
-        const bool ok3 = y3 >= 0.0f && (k12 * y3 + b.x) >= 0.0f;
-        const bool ok4 = b.x >= 0.0f && b.y >= 0.0f;   // case 4: both 0
-        const bool solved = ok1 || ok2 || ok3 || ok4;
-        Vec2 x;
-        x.x = ok1 ? x1 : (ok2 ? x2 : 0.0f);
-        x.y = ok1 ? y1 : ((!ok2 && ok3) ? y3 : 0.0f);
-        Vec2 d = x - a;
-        Vec2 P1 = d.x * normal;
-        Vec2 P2 = d.y * normal;
-        Vec2 nvA = vA - mA * (P1 + P2);
-        float nwA = wA - iA * (Cross(rA0, P1) + Cross(rA1, P2));
-        Vec2 nvB = vB + mB * (P1 + P2);
-        float nwB = wB + iB * (Cross(rB0, P1) + Cross(rB1, P2));
-        if (solved) {
-            vA = nvA; wA = nwA; vB = nvB; wB = nwB;
-            imp.x = x.x;
-            imp.z = x.y;
-        }
+        vA1 = vA1 - mA * P;
+        wA1 -= iA * Cross(rA0, P);
+        vB1 = vB1 + mB * P;
+        wB1 += iB * Cross(rB0, P);
     }
-    StsF(pA, vA.x); StsF(pA + 128, vA.y); StsF(pA + 256, wA);
-    StsF(pB, vB.x); StsF(pB + 128, vB.y); StsF(pB + 256, wB);
+    // ---- two points: friction of point 1, then the block solver (b2ContactSolver.cpp:388-589) ----
+    SolveTangent(vA, wA, vB, wB, rA1, rB1, tangent, q5.y, friction, imp.z, imp.w, mA, iA, mB, iB);
+    const float k11 = q5.z, k12 = q5.w, k22 = q6.x;
+    const float nmxx = q6.y, nmxy = q6.z, nmyy = q6.w;  // normalMass = K^-1 (symmetric)
+    const Vec2 a = V2(imp.x, imp.z);
+    Vec2 dv1 = vB + Cross(wB, rB0) - vA - Cross(wA, rA0);
+    Vec2 dv2 = vB + Cross(wB, rB1) - vA - Cross(wA, rA1);
+    float vn1 = Dot(dv1, normal);
+    float vn2 = Dot(dv2, normal);
+    Vec2 b;
+    b.x = vn1 - q3.z;
+    b.y = vn2 - q3.w;
+    b.x -= k11 * a.x + k12 * a.y;
+    b.y -= k12 * a.x + k22 * a.y;
+    const float x1 = -(nmxx * b.x + nmxy * b.y);  // case 1: x = -normalMass * b
+    const float y1 = -(nmxy * b.x + nmyy * b.y);
+    const bool ok1 = x1 >= 0.0f && y1 >= 0.0f;
+    const float x2 = -q3.x * b.x;                  // case 2: x2 = 0
+    const bool ok2 = x2 >= 0.0f && (k12 * x2 + b.y) >= 0.0f;
+    const float y3 = -q5.x * b.y;                  // case 3: x1 = 0
+    const bool ok3 = y3 >= 0.0f && (k12 * y3 + b.x) >= 0.0f;
+    const bool ok4 = b.x >= 0.0f && b.y >= 0.0f;   // case 4: both 0
+    const bool solved = ok1 || ok2 || ok3 || ok4;
+    Vec2 x;
+    x.x = ok1 ? x1 : (ok2 ? x2 : 0.0f);
+    x.y = ok1 ? y1 : ((!ok2 && ok3) ? y3 : 0.0f);
+    Vec2 d = x - a;
+    Vec2 P1 = d.x * normal;
+    Vec2 P2 = d.y * normal;
+    Vec2 nvA = vA - mA * (P1 + P2);
+    float nwA = wA - iA * (Cross(rA0, P1) + Cross(rA1, P2));
+    Vec2 nvB = vB + mB * (P1 + P2);
+    float nwB = wB + iB * (Cross(rB0, P1) + Cross(rB1, P2));
+    // ---- select: one point | two points solved | two points, no feasible case (velocities and impulses stay) ----
+    const bool onePoint = r.points == 1;
+    const bool take = solved && !onePoint;
+    bv.ax = onePoint ? vA1.x : (take ? nvA.x : vA.x);
+    bv.ay = onePoint ? vA1.y : (take ? nvA.y : vA.y);
+    bv.aw = onePoint ? wA1 : (take ? nwA : wA);
+    bv.bx = onePoint ? vB1.x : (take ? nvB.x : vB.x);
+    bv.by = onePoint ? vB1.y : (take ? nvB.y : vB.y);
+    bv.bw = onePoint ? wB1 : (take ? nwB : wB);
+    imp.x = onePoint ? impX1 : (take ? x.x : imp.x);
+    imp.z = onePoint ? r.imp.z : (take ? x.y : imp.z);
+    imp.w = onePoint ? r.imp.w : imp.w;
     return imp;
 }
 
@@ -551,10 +618,12 @@ __global__ void __launch_bounds__(96) k_solve_velocity(Arena A, int velIters) {
     // values in the ring stage, and the producer lane that fetched them (cp.async) writes them back to global
     // memory when the stage is recycled and fetches them again for the next pass — store and re-fetch of one
     // contact are issued by the same thread, in that order, as long as the ring holds fewer than nMax records.
-    const int depth = nMax - 1 < 1 ? 1 : (nMax - 1 < kVelStages ? nMax - 1 : kVelStages);
+    // The depth is a power of two (stage of record k = k & (depth - 1)).
+    int depth = 1;
+    while (depth * 2 <= nMax - 1 && depth * 2 <= kVelStages) depth *= 2;
 
     const uint32_t bodyBytes = (uint32_t)A.NB * 3 * kTile * 4;
-    unsigned char* stages = smem + ((bodyBytes + 127) & ~127u);
+    unsigned char* stages = smem + SolveTableBytes(A.NB);
     uint64_t* full = reinterpret_cast<uint64_t*>(stages + kVelStages * kVelStageBytes);
     uint64_t* empty = full + kVelStages;
     uint64_t* bodyBar = empty + kVelStages;
@@ -575,14 +644,14 @@ __global__ void __launch_bounds__(96) k_solve_velocity(Arena A, int velIters) {
     if (warp == 2) {
         // ================= watcher: waits for every record in order and publishes the count =================
         // (mbarrier.try_wait returns a predicate that must be consumed at once, ~50-90 cycles; the consumer
-        // polls this word with an ordinary load instead, whose latency it overlaps with the solve)
+        // polls this word with an ordinary load instead, and only when its cached copy runs out)
         if (lane != 0) return;
         const uint32_t ready = SmemAddr(&sReady);
         int s = 0;
         uint32_t phase = 0;
         for (int r = 0; r < total; ++r) {
             while (!MbarTryWait(&full[s], phase)) {}
-            StsRelease(ready, (uint32_t)r + 1u);
+            StsRelease(ready, r + 1 < total ? (uint32_t)r + 1u : 0x7fffffffu);  // after the last one: "everything"
             if (++s == depth) { s = 0; phase ^= 1u; }
         }
         return;
@@ -598,6 +667,20 @@ __global__ void __launch_bounds__(96) k_solve_velocity(Arena A, int velIters) {
         int i = 0, s = 0;
         int wi = 0, wpass = 0;  // record that previously occupied stage s (write-back cursor)
         uint32_t phase = 1;     // parity of the consumer's release that frees stage s for its next use
+        // The ring holds what shared memory leaves room for (a few records per tile), far less than HBM latency x
+        // bandwidth needs in flight; so the records are pulled into L2 kVelPrefetch records ahead of the ring's own loads,
+        // which then complete with L2 latency.
+        int pi = 0;  // record index of the next prefetch, pf records issued so far
+        int pf = 0;
+        auto prefetch = [&]() {
+            if (lane == 0 && pf < total) {
+                TmaPrefetchL2(src + (size_t)pi * (kVelRec * 16 * kTile), kVelRec * 16 * kTile);
+                TmaPrefetchL2(gImp - lane + (size_t)pi * kTile, 16 * kTile);
+            }
+            ++pf;
+            if (++pi == nMax) pi = 0;
+        };
+        for (int k = 0; k < kVelPrefetch; ++k) prefetch();
         for (int seq = 0; seq < total + depth; ++seq) {
             float4* st = reinterpret_cast<float4*>(stages + (size_t)s * kVelStageBytes) + lane;
             if (seq >= depth) {  // stage s holds record seq - depth: wait for the consumer, write its impulses back
@@ -607,6 +690,7 @@ __global__ void __launch_bounds__(96) k_solve_velocity(Arena A, int velIters) {
                 if (++wi == nMax) { wi = 0; ++wpass; }
             }
             if (seq < total) {
+                prefetch();
                 if (lane == 0) {
                     MbarExpectTx(&full[s], kVelRec * 16 * kTile);
                     TmaLoad1D(st, src + (size_t)i * (kVelRec * 16 * kTile), kVelRec * 16 * kTile, &full[s]);
@@ -621,67 +705,98 @@ __global__ void __launch_bounds__(96) k_solve_velocity(Arena A, int velIters) {
     }
 
     // ================= consumer =================
+    // One world's chain is ~velIters * n dependent contact solves, so everything that is not the solve's own arithmetic
+    // is kept off it:
+    //  * three records live in registers (being solved / next / being fetched).  A record's shared-memory loads are
+    //    issued at the top of a step and first looked at at the end of it, a whole solve later;
+    //  * the body values of the NEXT contact are read from the table at the top of the step too; rows both contacts
+    //    touch are forwarded from registers at the end (ForwardBodyVals) instead of going through a store and a reload;
+    //  * lanes without a contact at the current index solve a scratch row instead of branching around the solve, and
+    //    the solve itself is straight-line for every point count (SolveVelocityContact): a step is one basic block;
+    //  * the count of landed records is cached; the shared word is read once per three steps, and only if needed.
     while (!MbarTryWait(bodyBar, 0)) {}
     // Loop invariants are pinned in registers (Keep): left alone, the compiler re-derives them from %tid / %ctaid /
     // the shared-window base inside the loop, which costs more than the solve's own address arithmetic.
     const BodyTable T{Keep(SmemAddr(smem) + (uint32_t)lane * 4)};
+    const uint32_t scratch = Keep(T.at(A.NB));  // row NB of the table: this lane's scratch row
     const uint32_t stage0 = Keep(SmemAddr(stages) + (uint32_t)lane * 16);
     const uint32_t empty0 = Keep(SmemAddr(empty));
     const uint32_t ready = Keep(SmemAddr(&sReady));
-    const uint32_t stageEnd = Keep(stage0 + (uint32_t)depth * kVelStageBytes);
+    const uint32_t mask = Keep((uint32_t)depth - 1u);
     const int warmRecords = Keep(anyWarm ? nMax : 0);
     const int nK = Keep(n), nMaxK = Keep(nMax), totalK = Keep(total);
-    if (depth >= 3) {
-        // Two records of look-ahead in registers: the record solved in an iteration was loaded one iteration
-        // earlier, so neither the ring's barrier nor the LDS latency sits on the solver's dependency chain.
-        uint32_t ldStage = stage0, stStage = stage0, stEmpty = empty0;
-        int i = 0, seq = 0;
-        auto load = [&](VelRecord& r) {
-            r = LoadVelRecord(ldStage);
-            ldStage += kVelStageBytes;
-            if (ldStage == stageEnd) ldStage = stage0;
+
+    if (depth >= 4) {
+        int iLoad = 0, seq = 0;  // seq: record being solved; records up to seq + 1 are in registers
+        uint32_t landed = 0;
+        auto waitLanded = [&](uint32_t need) {
+            while (landed < need) landed = LdsAcquire(ready);
         };
-        // one solver step on the record held in `r`, then refill `r` with the record two ahead
-        auto step = [&](VelRecord& r) {
-            uint32_t landed = LdsAcquire(ready);  // polled now, needed after the solve
-            if (i < nK) {
-                if (seq < warmRecords) {
-                    if (warm) WarmStartContact(r, T);
-                } else {
-                    StsF4(stStage + 7 * 512, SolveVelocityContact(r, T));
-                }
+        auto stageOf = [&](int k) { return stage0 + (((uint32_t)k & mask) << 12); };  // kVelStageBytes == 4096
+        auto emptyOf = [&](int k) { return empty0 + (((uint32_t)k & mask) << 3); };
+        auto finish = [&](VelRecord& r, int k) {  // record k (issued earlier) becomes usable
+            FinishVelRecord(r, k < totalK && iLoad < nK, T, scratch);
+            if (++iLoad == nMaxK) iLoad = 0;
+        };
+        // One chain step: `cur` (record seq) is solved on `bv`; meanwhile `fill` receives record seq + 2 (past the last
+        // record: a stale stage, read and ignored) and the body values of `nxt` are read.
+        auto step = [&](VelRecord& cur, const VelRecord& nxt, VelRecord& fill, BodyVals& bv, auto warmPass) {
+            constexpr bool WARM = decltype(warmPass)::value;
+            IssueVelRecord(fill, stageOf(seq + 2));
+            const BodyVals nextLoaded = LoadBodyVals(nxt.pA, nxt.pB);  // before this contact's stores: ForwardBodyVals
+            if (WARM) {
+                if (warm) WarmStartContact(cur, bv);
+            } else {
+                const float4 imp = SolveVelocityContact(cur, bv);
+                StsF4(stageOf(seq) + 7 * 512, imp);
             }
-            MbarArriveA(stEmpty);  // hands the stage (and the updated impulses in it) back to the producer
-            stStage += kVelStageBytes;
-            stEmpty += 8;
-            if (stStage == stageEnd) { stStage = stage0; stEmpty = empty0; }
-            if (seq + 2 < totalK) {
-                while (landed < (uint32_t)seq + 3u) landed = LdsAcquire(ready);
-                load(r);
-            }
-            if (++i == nMaxK) i = 0;
+            StoreBodyVals(cur.pA, cur.pB, bv);
+            MbarArriveA(emptyOf(seq));  // hands the stage (and the updated impulses in it) back to the producer
+            bv = ForwardBodyVals(nextLoaded, bv, nxt.pA, nxt.pB, cur.pA, cur.pB);
+            finish(fill, seq + 2);
             ++seq;
         };
-        VelRecord r0, r1;
-        while (LdsAcquire(ready) < 2u) {}
-        load(r0);
-        load(r1);
-        while (seq < totalK) {
-            step(r0);
-            if (seq < totalK) step(r1);
+        VelRecord r0, r1, r2;
+        waitLanded(3u);  // depth >= 4 implies total >= 5
+        IssueVelRecord(r0, stageOf(0));
+        finish(r0, 0);
+        IssueVelRecord(r1, stageOf(1));
+        finish(r1, 1);
+        BodyVals bv = LoadBodyVals(r0.pA, r0.pB);
+        // warm-start pass, and whatever does not fill a group of three: one step at a time, registers rotated by moves
+        auto single = [&](auto warmPass) {
+            step(r0, r1, r2, bv, warmPass);
+            r0 = r1;
+            r1 = r2;
+            waitLanded((uint32_t)seq + 3u);  // the record the next step fetches
+        };
+        while (seq < warmRecords) single(std::true_type());
+        if (depth >= 8) {
+            while (seq + 3 <= totalK) {
+                if (landed < (uint32_t)seq + 5u) waitLanded((uint32_t)seq + 5u);  // the three records this group fetches
+                step(r0, r1, r2, bv, std::false_type());
+                step(r1, r2, r0, bv, std::false_type());
+                step(r2, r0, r1, bv, std::false_type());
+            }
+            waitLanded((uint32_t)seq + 3u);
         }
+        while (seq < totalK) single(std::false_type());
     } else {
         int i = 0, cs = 0;
         for (int seq = 0; seq < total; ++seq) {
             const uint32_t st = stage0 + cs * kVelStageBytes;
             while (LdsAcquire(ready) < (uint32_t)seq + 1u) {}
             if (i < n) {
-                const VelRecord r = LoadVelRecord(st);
+                VelRecord r;
+                IssueVelRecord(r, st);
+                FinishVelRecord(r, true, T, scratch);
+                BodyVals bv = LoadBodyVals(r.pA, r.pB);
                 if (seq < warmRecords) {
-                    if (warm) WarmStartContact(r, T);
+                    if (warm) WarmStartContact(r, bv);
                 } else {
-                    StsF4(st + 7 * 512, SolveVelocityContact(r, T));
+                    StsF4(st + 7 * 512, SolveVelocityContact(r, bv));
                 }
+                StoreBodyVals(r.pA, r.pB, bv);
             }
             MbarArriveA(empty0 + cs * 8);
             if (++i == nMax) i = 0;
@@ -790,13 +905,123 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_solve_integrate(Arena A, fl
 // b2ContactSolver.cpp:614-744); each island stops as soon as one of its passes ends with
 // minSeparation >= -3 * b2_linearSlop.  Warp 0 (consumer) solves out of shared memory, lane 0 of warp 1
 // (producer) streams the position records of one pass through a TMA + mbarrier ring and then waits for the
-// consumer's verdict on whether another pass is needed.
+// consumer's verdict on whether another pass is needed, lane 0 of warp 2 (watcher) publishes how many records
+// have landed.  The consumer is built like k_solve_velocity's: three records in registers, the next contact's
+// body values fetched during the solve and forwarded, lanes without work on a scratch row, a step is
+// straight-line code.
 // =================================================================================================
 constexpr int kPosStageBytes = kPosRec * 16 * kTile;  // 2560
 
-__global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
+struct PosRecord {
+    float4 r0, r1, r2, r3, r4;
+    uint32_t pA, pB;  // table rows of the two bodies
+    int info;         // manifold type | last contact of its island << 2 | has a contact << 3 | two points << 4 | island << 8
+};
+__device__ __forceinline__ void IssuePosRecord(PosRecord& r, uint32_t st) {
+    r.r0 = LdsF4(st); r.r1 = LdsF4(st + 512); r.r2 = LdsF4(st + 1024); r.r3 = LdsF4(st + 1536); r.r4 = LdsF4(st + 2048);
+}
+__device__ __forceinline__ void FinishPosRecord(PosRecord& r, bool active, BodyTable T) {
+    TouchF4(r.r0); TouchF4(r.r1); TouchF4(r.r2); TouchF4(r.r3); TouchF4(r.r4);
+    const int packed = __float_as_int(r.r4.z);
+    r.pA = T.at(packed & 0x7fff);
+    r.pB = T.at((packed >> 15) & 0x7fff);
+    const int pointCount = (packed >> 30) & 3;
+    const int word = __float_as_int(r.r4.w);
+    r.info = active && pointCount > 0 ? ((word & ~0x18) | 8 | (pointCount > 1 ? 16 : 0)) : 0;
+}
+
+// One manifold point of SolvePositionConstraints (b2ContactSolver.cpp:687-734; b2PositionSolverManifold :614-664).
+// e_faceA / e_faceB are the same arithmetic with the bodies' roles swapped: selected, not branched on (lane = world,
+// a warp holds both kinds); CIRCLES adds the e_circles arithmetic beside it, again selected.
+// FASTROT: sinf / cosf by the |angle| < pi/4 arithmetic only; `slow` is set when that was not valid for one of the two
+// angles (the caller then redoes the contact with FASTROT = false).
+template <bool CIRCLES, bool FASTROT>
+__device__ __forceinline__ float SolvePositionPoint(const PosRecord& r, Vec2 lp, Vec2& cAp, float& aA, Vec2& cBp, float& aB,
+                                                    bool& slow) {
+    const int mtype = r.info & 3;
+    const float mA = r.r2.x, iA = r.r2.y, mB = r.r2.z, iB = r.r2.w;
+    const Vec2 localCenterA = V2(r.r3.x, r.r3.y), localCenterB = V2(r.r3.z, r.r3.w);
+    const Vec2 localNormal = V2(r.r0.x, r.r0.y), localPoint = V2(r.r0.z, r.r0.w);
+    const float radiusA = r.r4.x, radiusB = r.r4.y;
+    Xf xfA, xfB;
+    if (FASTROT) {
+        slow = slow || !InSinCosFastRange(aA) || !InSinCosFastRange(aB);
+        xfA.q = MakeRotFastRange(aA);
+        xfB.q = MakeRotFastRange(aB);
+    } else {
+        xfA.q = MakeRot(aA);
+        xfB.q = MakeRot(aB);
+    }
+    xfA.p = cAp - Mul(xfA.q, localCenterA);
+    xfB.p = cBp - Mul(xfB.q, localCenterB);
+    const bool faceA = mtype == kManifoldFaceA;
+    Xf xfR, xfI;  // the reference face's body, the incident one
+    xfR.q.s = faceA ? xfA.q.s : xfB.q.s; xfR.q.c = faceA ? xfA.q.c : xfB.q.c;
+    xfR.p.x = faceA ? xfA.p.x : xfB.p.x; xfR.p.y = faceA ? xfA.p.y : xfB.p.y;
+    xfI.q.s = faceA ? xfB.q.s : xfA.q.s; xfI.q.c = faceA ? xfB.q.c : xfA.q.c;
+    xfI.p.x = faceA ? xfB.p.x : xfA.p.x; xfI.p.y = faceA ? xfB.p.y : xfA.p.y;
+    Vec2 normal = Mul(xfR.q, localNormal);
+    const Vec2 planePoint = Mul(xfR, localPoint);
+    const Vec2 clipPoint = Mul(xfI, lp);
+    float separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+    Vec2 point = clipPoint;
+    normal.x = faceA ? normal.x : -normal.x;
+    normal.y = faceA ? normal.y : -normal.y;
+    if (CIRCLES) {
+        const Vec2 pointA = Mul(xfA, localPoint);
+        const Vec2 pointB = Mul(xfB, lp);
+        Vec2 n = pointB - pointA;
+        Normalize(n);
+        const float sep = Dot(pointB - pointA, n) - radiusA - radiusB;
+        const Vec2 mid = 0.5f * (pointA + pointB);
+        const bool circ = mtype == kManifoldCircles;
+        normal.x = circ ? n.x : normal.x; normal.y = circ ? n.y : normal.y;
+        point.x = circ ? mid.x : point.x; point.y = circ ? mid.y : point.y;
+        separation = circ ? sep : separation;
+    }
+    const Vec2 rA = point - cAp;
+    const Vec2 rB = point - cBp;
+    const float C = Clamp(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+    const float rnA = Cross(rA, normal);
+    const float rnB = Cross(rB, normal);
+    const float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    const float quotient = Div(-C, K);  // unconditionally: a select below, not a branch around the division
+    const float impulse = K > 0.0f ? quotient : 0.0f;
+    const Vec2 P = impulse * normal;
+    cAp = cAp - mA * P;
+    aA -= iA * Cross(rA, P);
+    cBp = cBp + mB * P;
+    aB += iB * Cross(rB, P);
+    return separation;
+}
+
+// A whole contact through the full-range sinf / cosf and every manifold type: out of line, for the rare contact one of
+// whose bodies is turned further than pi/4.  Returns the bodies' new positions and min(separation) over its points.
+struct PosContactResult {
+    BodyVals bv;
+    float minSeparation;
+};
+__device__ __noinline__ PosContactResult SolvePositionContactAnyAngle(float4 r0, float4 r1, float4 r2, float4 r3, float4 r4,
+                                                                         int info, BodyVals bv) {
+    PosRecord r;
+    r.r0 = r0; r.r1 = r1; r.r2 = r2; r.r3 = r3; r.r4 = r4;
+    r.pA = r.pB = 0;
+    r.info = info;
+    Vec2 cAp = V2(bv.ax, bv.ay), cBp = V2(bv.bx, bv.by);
+    float aA = bv.aw, aB = bv.bw;
+    bool slow = false;
+    PosContactResult o;
+    o.minSeparation = SolvePositionPoint<true, false>(r, V2(r1.x, r1.y), cAp, aA, cBp, aB, slow);
+    if (info & 16) o.minSeparation = Min(o.minSeparation, SolvePositionPoint<true, false>(r, V2(r1.z, r1.w), cAp, aA, cBp, aB, slow));
+    o.bv.ax = cAp.x; o.bv.ay = cAp.y; o.bv.aw = aA;
+    o.bv.bx = cBp.x; o.bv.by = cBp.y; o.bv.bw = aB;
+    return o;
+}
+
+__global__ void __launch_bounds__(96) k_solve_position(Arena A, int posIters) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int sContinue;
+    __shared__ uint32_t sReady;  // records that have landed in the ring, over all passes (published by the watcher)
     const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const int n = A.solveCount[ws];
@@ -811,16 +1036,18 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
             for (int wd = 0; wd < doneWords; ++wd) gDone[(size_t)wd * kTile] = posIters > 0 ? -1 : 0;
         return;
     }
+    const bool anyCircles = __any_sync(0xffffffffu, (A.solveFlags[ws] & 1) != 0);
 
     const uint32_t bodyBytes = (uint32_t)A.NB * 3 * kTile * 4;
-    unsigned char* stages = smem + ((bodyBytes + 127) & ~127u);
+    unsigned char* stages = smem + SolveTableBytes(A.NB);
     uint32_t* sDone = reinterpret_cast<uint32_t*>(stages + kRecStages * kPosStageBytes) + lane;  // word wd at sDone[wd * 32]
     uint64_t* full = reinterpret_cast<uint64_t*>(stages + kRecStages * kPosStageBytes + (size_t)doneWords * kTile * 4);
     uint64_t* empty = full + kRecStages;
     uint64_t* bodyBar = empty + kRecStages;
     uint64_t* passBar = bodyBar + 1;
     float* gPos = A.solvePos + (size_t)tile * A.NB * 3 * kTile;
-    const int depth = nMax < kRecStages ? nMax : kRecStages;
+    int depth = 1;  // a power of two: stage of record k = k & (depth - 1), k counted over all passes
+    while (depth * 2 <= nMax && depth * 2 <= kRecStages) depth *= 2;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kRecStages; ++s) {
@@ -829,6 +1056,7 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
         }
         MbarInit(bodyBar, 1);
         MbarInit(passBar, 32);
+        sReady = 0;
         FenceBarrierInit();
     }
     __syncthreads();
@@ -839,13 +1067,30 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
         MbarExpectTx(bodyBar, bodyBytes);
         TmaLoad1D(smem, gPos, bodyBytes, bodyBar);
         const unsigned char* src = reinterpret_cast<const unsigned char*>(A.posRec + (size_t)tile * A.NC * kPosRec * kTile);
-        int s = 0, use = 0;
+        int k = 0;  // records issued so far
         for (int pass = 0; pass < posIters; ++pass) {
-            for (int i = 0; i < nMax; ++i) {
+            for (int i = 0; i < kPosPrefetch && i < nMax; ++i) TmaPrefetchL2(src + (size_t)i * kPosStageBytes, kPosStageBytes);
+            for (int i = 0; i < nMax; ++i, ++k) {
+                if (i + kPosPrefetch < nMax) TmaPrefetchL2(src + (size_t)(i + kPosPrefetch) * kPosStageBytes, kPosStageBytes);
+                const int s = k & (depth - 1), use = k / depth;
                 if (use > 0) while (!MbarTryWait(&empty[s], (uint32_t)(use - 1) & 1u)) {}
                 MbarExpectTx(&full[s], kPosStageBytes);
                 TmaLoad1D(stages + (size_t)s * kPosStageBytes, src + (size_t)i * kPosStageBytes, kPosStageBytes, &full[s]);
-                if (++s == depth) { s = 0; ++use; }
+            }
+            while (!MbarTryWait(passBar, (uint32_t)pass & 1u)) {}
+            if (*(volatile int*)&sContinue == 0) break;
+        }
+        return;
+    }
+    if (warp == 2) {
+        // ================= watcher (one lane): counts landed records =================
+        if (lane != 0) return;
+        const uint32_t ready = SmemAddr(&sReady);
+        int k = 0;
+        for (int pass = 0; pass < posIters; ++pass) {
+            for (int i = 0; i < nMax; ++i, ++k) {
+                while (!MbarTryWait(&full[k & (depth - 1)], (uint32_t)(k / depth) & 1u)) {}
+                StsRelease(ready, (uint32_t)k + 1u);
             }
             while (!MbarTryWait(passBar, (uint32_t)pass & 1u)) {}
             if (*(volatile int*)&sContinue == 0) break;
@@ -871,112 +1116,144 @@ __global__ void __launch_bounds__(64) k_solve_position(Arena A, int posIters) {
     // Loop invariants pinned in registers and every ring / body-table access on 32-bit shared-window addresses, as in
     // k_solve_velocity: the chain is bound by the instructions the lone consumer warp has to issue per contact.
     const BodyTable T{Keep(SmemAddr(smem) + (uint32_t)lane * 4)};
+    const uint32_t scratch = Keep(T.at(A.NB));
     const uint32_t stage0 = Keep(SmemAddr(stages) + (uint32_t)lane * 16);
-    const uint32_t stageEnd = Keep(stage0 + (uint32_t)depth * kPosStageBytes);
-    const uint32_t full0 = Keep(SmemAddr(full)), empty0 = Keep(SmemAddr(empty));
+    const uint32_t empty0 = Keep(SmemAddr(empty));
+    const uint32_t ready = Keep(SmemAddr(&sReady));
+    const uint32_t done0 = Keep(SmemAddr(sDone));
+    const uint32_t mask = Keep((uint32_t)depth - 1u);
     const int nK = Keep(n), nMaxK = Keep(nMax);
-    uint32_t st = stage0, stFull = full0, stEmpty = empty0, parity = 0;
-    for (int pass = 0; pass < posIters; ++pass) {
-        int isl = 0;
-        int islEnd = islands > 0 ? iContactEnd[0] : 0;
-        float minSeparation = 0.0f;
-        bool islDone = islands > 0 ? ((sDone[0] & 1u) != 0) : true;
-        for (int i = 0; i < nMaxK; ++i) {
-            while (!MbarTryWaitA(stFull, parity)) {}
-            if (i < nK) {
-                while (i >= islEnd) {  // entering the next island: close the previous one
-                    if (!islDone && minSeparation >= -3.0f * kLinearSlop) {
-                        sDone[(isl >> 5) * kTile] |= 1u << (isl & 31);
+    StsF(scratch, 0.0f); StsF(scratch + 128, 0.0f); StsF(scratch + 256, 0.0f);  // angle 0: the fast sinf / cosf path
+
+    auto runPasses = [&](auto circlesTag) {
+        constexpr bool CIRCLES = decltype(circlesTag)::value;
+        uint32_t landed = 0;
+        int base = 0;  // ring index of this pass's record 0
+        auto waitLanded = [&](uint32_t need) {
+            while (landed < need) landed = LdsAcquire(ready);
+        };
+        auto stageOf = [&](int k) { return stage0 + ((uint32_t)k & mask) * kPosStageBytes; };
+        auto emptyOf = [&](int k) { return empty0 + (((uint32_t)k & mask) << 3); };
+        auto doneBit = [&](int info) {  // converged bit of the island a record belongs to
+            const uint32_t isl = (uint32_t)info >> 8;
+            return ((LdsU(done0 + (isl >> 5) * (kTile * 4)) >> (isl & 31)) & 1u) != 0;
+        };
+        for (int pass = 0; pass < posIters; ++pass) {
+            int i = 0;  // record being solved; records up to i + 1 are in registers
+            float minSeparation = 0.0f;
+            auto finish = [&](PosRecord& r, int k) { FinishPosRecord(r, k < nK, T); };
+            // One chain step: `cur` (record i of the pass) is solved on `bv` if `solve`; `fill` receives record i + 2 (past
+            // the pass's last record: a stale stage, read and ignored) and the body values of `nxt` are read.
+            auto step = [&](PosRecord& cur, const PosRecord& nxt, PosRecord& fill, BodyVals& bv, uint32_t& curA, uint32_t& curB,
+                            bool& solve) {
+                IssuePosRecord(fill, stageOf(base + i + 2));
+                // a contact is solved if its island has not converged in an earlier pass
+                const bool solveNext = (nxt.info & 8) != 0 && !doneBit(nxt.info);
+                const uint32_t nxtA = solveNext ? nxt.pA : scratch, nxtB = solveNext ? nxt.pB : scratch;
+                const BodyVals nextLoaded = LoadBodyVals(nxtA, nxtB);  // before this contact's stores: ForwardBodyVals
+                {
+                    const bool two = (cur.info & 16) != 0;
+                    Vec2 cAp = V2(bv.ax, bv.ay), cBp = V2(bv.bx, bv.by);
+                    float aA = bv.aw, aB = bv.bw;
+                    bool slow = false;
+                    const float s0 = SolvePositionPoint<CIRCLES, true>(cur, V2(cur.r1.x, cur.r1.y), cAp, aA, cBp, aB, slow);
+                    Vec2 cAp2 = cAp, cBp2 = cBp;
+                    float aA2 = aA, aB2 = aB;
+                    const float s1 = SolvePositionPoint<CIRCLES, true>(cur, V2(cur.r1.z, cur.r1.w), cAp2, aA2, cBp2, aB2, slow);
+                    BodyVals nb;
+                    nb.ax = two ? cAp2.x : cAp.x; nb.ay = two ? cAp2.y : cAp.y; nb.aw = two ? aA2 : aA;
+                    nb.bx = two ? cBp2.x : cBp.x; nb.by = two ? cBp2.y : cBp.y; nb.bw = two ? aB2 : aB;
+                    float sep = two ? Min(s0, s1) : s0;  // Min(Min(m, s0), s1) == Min(m, Min(s0, s1)): no NaN reaches here unless the world is lost
+                    if (slow && solve) {  // a body turned further than pi/4: the same again with the full-range sinf / cosf
+                        const PosContactResult o = SolvePositionContactAnyAngle(cur.r0, cur.r1, cur.r2, cur.r3, cur.r4, cur.info, bv);
+                        nb = o.bv;
+                        sep = o.minSeparation;
+                    }
+                    minSeparation = solve ? Min(minSeparation, sep) : minSeparation;
+                    // not solved: the scratch row keeps its zeros
+                    bv.ax = solve ? nb.ax : bv.ax; bv.ay = solve ? nb.ay : bv.ay; bv.aw = solve ? nb.aw : bv.aw;
+                    bv.bx = solve ? nb.bx : bv.bx; bv.by = solve ? nb.by : bv.by; bv.bw = solve ? nb.bw : bv.bw;
+                }
+                StoreBodyVals(curA, curB, bv);
+                if (i < nMaxK) MbarArriveA(emptyOf(base + i));
+                bv = ForwardBodyVals(nextLoaded, bv, nxtA, nxtB, curA, curB);
+                if ((cur.info & 12) == 12) {  // last contact of its island: close the island
+                    if (solve && minSeparation >= -3.0f * kLinearSlop) {
+                        const uint32_t isl = (uint32_t)cur.info >> 8;
+                        const uint32_t wd = done0 + (isl >> 5) * (kTile * 4);
+                        StsU(wd, LdsU(wd) | (1u << (isl & 31)));
                         --pending;
                     }
-                    ++isl;
-                    islEnd = iContactEnd[isl];
                     minSeparation = 0.0f;
-                    islDone = (sDone[(isl >> 5) * kTile] >> (isl & 31) & 1u) != 0;
                 }
-                if (!islDone) {
-                    const float4 r0 = LdsF4(st), r1 = LdsF4(st + 512), r2 = LdsF4(st + 1024), r3 = LdsF4(st + 1536),
-                                 r4 = LdsF4(st + 2048);
-                    const int packed = __float_as_int(r4.z);
-                    const int bodyA = packed & 0x7fff, bodyB = (packed >> 15) & 0x7fff;
-                    const int pointCount = (packed >> 30) & 3;
-                    const int mtype = __float_as_int(r4.w);
-                    const float radiusA = r4.x, radiusB = r4.y;
-                    const float mA = r2.x, iA = r2.y, mB = r2.z, iB = r2.w;
-                    const Vec2 localCenterA = V2(r3.x, r3.y), localCenterB = V2(r3.z, r3.w);
-                    const Vec2 localNormal = V2(r0.x, r0.y), localPoint = V2(r0.z, r0.w);
-                    const uint32_t pA = T.at(bodyA), pB = T.at(bodyB);
-                    Vec2 cAp = V2(LdsF(pA), LdsF(pA + 128)), cBp = V2(LdsF(pB), LdsF(pB + 128));
-                    float aA = LdsF(pA + 256), aB = LdsF(pB + 256);
-                    // one manifold point (b2ContactSolver.cpp:687-734)
-                    auto solvePoint = [&](const Vec2 lp) {
-                        Xf xfA, xfB;
-                        xfA.q = MakeRot(aA);
-                        xfB.q = MakeRot(aB);
-                        xfA.p = cAp - Mul(xfA.q, localCenterA);
-                        xfB.p = cBp - Mul(xfB.q, localCenterB);
-                        Vec2 normal, point;
-                        float separation;
-                        if (mtype == kManifoldCircles) {
-                            Vec2 pointA = Mul(xfA, localPoint);
-                            Vec2 pointB = Mul(xfB, lp);
-                            normal = pointB - pointA;
-                            Normalize(normal);
-                            point = 0.5f * (pointA + pointB);
-                            separation = Dot(pointB - pointA, normal) - radiusA - radiusB;
-                        } else {
-                            // e_faceA / e_faceB (b2ContactSolver.cpp:642-664) are the same arithmetic with the bodies'
-                            // roles swapped: selected, not branched on — lane = world, so one warp holds both kinds
-                            const bool faceA = mtype == kManifoldFaceA;
-                            Xf xfR, xfI;  // the reference face's body, the incident one
-                            xfR.q.s = faceA ? xfA.q.s : xfB.q.s; xfR.q.c = faceA ? xfA.q.c : xfB.q.c;
-                            xfR.p.x = faceA ? xfA.p.x : xfB.p.x; xfR.p.y = faceA ? xfA.p.y : xfB.p.y;
-                            xfI.q.s = faceA ? xfB.q.s : xfA.q.s; xfI.q.c = faceA ? xfB.q.c : xfA.q.c;
-                            xfI.p.x = faceA ? xfB.p.x : xfA.p.x; xfI.p.y = faceA ? xfB.p.y : xfA.p.y;
-                            normal = Mul(xfR.q, localNormal);
-                            Vec2 planePoint = Mul(xfR, localPoint);
-                            Vec2 clipPoint = Mul(xfI, lp);
-                            separation = Dot(clipPoint - planePoint, normal) - radiusA - radiusB;
-                            point = clipPoint;
-                            normal.x = faceA ? normal.x : -normal.x;
-                            normal.y = faceA ? normal.y : -normal.y;
+                curA = nxtA;
+                curB = nxtB;
+                solve = solveNext;
+                finish(fill, i + 2);
+                ++i;
+            };
+            if (depth < 8) {
+                // a handful of contacts per world: one record at a time, nothing overlapped
+                for (; i < nMaxK; ++i) {
+                    waitLanded((uint32_t)(base + i) + 1u);
+                    PosRecord r;
+                    IssuePosRecord(r, stageOf(base + i));
+                    finish(r, i);
+                    const bool solve = (r.info & 8) != 0 && !doneBit(r.info);
+                    if (solve) {
+                        BodyVals bv = LoadBodyVals(r.pA, r.pB);
+                        Vec2 cAp = V2(bv.ax, bv.ay), cBp = V2(bv.bx, bv.by);
+                        float aA = bv.aw, aB = bv.bw;
+                        bool slow = false;
+                        minSeparation = Min(minSeparation, SolvePositionPoint<true, false>(r, V2(r.r1.x, r.r1.y), cAp, aA, cBp, aB, slow));
+                        if (r.info & 16)
+                            minSeparation = Min(minSeparation, SolvePositionPoint<true, false>(r, V2(r.r1.z, r.r1.w), cAp, aA, cBp, aB, slow));
+                        bv.ax = cAp.x; bv.ay = cAp.y; bv.aw = aA;
+                        bv.bx = cBp.x; bv.by = cBp.y; bv.bw = aB;
+                        StoreBodyVals(r.pA, r.pB, bv);
+                    }
+                    MbarArriveA(emptyOf(base + i));
+                    if ((r.info & 12) == 12) {
+                        if (solve && minSeparation >= -3.0f * kLinearSlop) {
+                            const uint32_t isl = (uint32_t)r.info >> 8;
+                            const uint32_t wd = done0 + (isl >> 5) * (kTile * 4);
+                            StsU(wd, LdsU(wd) | (1u << (isl & 31)));
+                            --pending;
                         }
-                        Vec2 rA = point - cAp;
-                        Vec2 rB = point - cBp;
-                        minSeparation = Min(minSeparation, separation);
-                        float C = Clamp(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
-                        float rnA = Cross(rA, normal);
-                        float rnB = Cross(rB, normal);
-                        float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-                        float impulse = K > 0.0f ? Div(-C, K) : 0.0f;
-                        Vec2 P = impulse * normal;
-                        cAp = cAp - mA * P;
-                        aA -= iA * Cross(rA, P);
-                        cBp = cBp + mB * P;
-                        aB += iB * Cross(rB, P);
-                    };
-                    if (pointCount > 0) solvePoint(V2(r1.x, r1.y));
-                    if (pointCount > 1) solvePoint(V2(r1.z, r1.w));
-                    StsF(pA, cAp.x); StsF(pA + 128, cAp.y); StsF(pA + 256, aA);
-                    StsF(pB, cBp.x); StsF(pB + 128, cBp.y); StsF(pB + 256, aB);
+                        minSeparation = 0.0f;
+                    }
                 }
+            } else {
+            PosRecord r0, r1, r2;
+            waitLanded((uint32_t)base + 2u);
+            IssuePosRecord(r0, stageOf(base));
+            finish(r0, 0);
+            IssuePosRecord(r1, stageOf(base + 1));
+            finish(r1, 1);
+            bool solve = (r0.info & 8) != 0 && !doneBit(r0.info);
+            uint32_t curA = solve ? r0.pA : scratch, curB = solve ? r0.pB : scratch;
+            BodyVals bv = LoadBodyVals(curA, curB);
+            const int limit = base + nMaxK;  // records of this pass end here
+            auto needFor = [&](int k) { return (uint32_t)(k < limit ? k : limit); };
+            // groups of three steps; the steps past the pass's last record have nothing to solve (and release no stage)
+            while (i < nMaxK) {
+                const uint32_t need = needFor(base + i + 5);  // the three records this group fetches
+                if (landed < need) waitLanded(need);
+                step(r0, r1, r2, bv, curA, curB, solve);
+                step(r1, r2, r0, bv, curA, curB, solve);
+                step(r2, r0, r1, bv, curA, curB, solve);
             }
-            MbarArriveA(stEmpty);
-            st += kPosStageBytes;
-            stFull += 8;
-            stEmpty += 8;
-            if (st == stageEnd) { st = stage0; stFull = full0; stEmpty = empty0; parity ^= 1u; }
+            }
+            base += nMaxK;
+            const bool more = pass + 1 < posIters && !__all_sync(0xffffffffu, pending == 0);
+            if (lane == 0) *(volatile int*)&sContinue = more ? 1 : 0;
+            __syncwarp();
+            MbarArrive(passBar);
+            if (!more) break;
         }
-        if (n > 0 && !islDone && minSeparation >= -3.0f * kLinearSlop) {  // close the last island of this pass
-            sDone[(isl >> 5) * kTile] |= 1u << (isl & 31);
-            --pending;
-        }
-        const bool more = pass + 1 < posIters && !__all_sync(0xffffffffu, pending == 0);
-        if (lane == 0) *(volatile int*)&sContinue = more ? 1 : 0;
-        __syncwarp();
-        MbarArrive(passBar);
-        if (!more) break;
-    }
+    };
+    if (anyCircles) runPasses(std::true_type());
+    else runPasses(std::false_type());
     for (int wd = 0; wd < doneWords; ++wd) gDone[(size_t)wd * kTile] = (int)sDone[wd * kTile];
     FenceProxyAsync();
     __syncwarp();

@@ -661,7 +661,7 @@ int allocateArena(b2gpu_batch* b) {
         ALLOC(velRec, (size_t)A.NC * kVelRec, float4); ALLOC(posRec, (size_t)A.NC * kPosRec, float4);
         ALLOC(impRec, A.NC, float4);
         ALLOC(solveVel, (size_t)A.NB * 3, float); ALLOC(solvePos, (size_t)A.NB * 3, float);
-        ALLOC(solveCount, 1, int); ALLOC(islandSolved, (A.NB + 31) / 32, int);
+        ALLOC(solveCount, 1, int); ALLOC(solveFlags, 1, int); ALLOC(islandSolved, (A.NB + 31) / 32, int);
     } else {
         ALLOC(vc, (size_t)A.NC * kVcStride, float4);
     }
@@ -853,7 +853,7 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
             mark();
             k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
             mark();
-            k_solve_position<<<tiles, 64, b->solveSmem, st>>>(A, posIters);
+            k_solve_position<<<tiles, 96, b->solveSmem, st>>>(A, posIters);
             mark();
         } else {
             k_solve<<<blocks, threads, 0, st>>>(A, dt, velIters, posIters);
@@ -977,6 +977,14 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
     if (e != cudaSuccess) return fail(B2GPU_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return B2GPU_OK;
 }
+// Captured graphs bake in the kernel chain (k_toi / k_toi_events only when some world steps continuously), the world
+// groups and the step_io staging pointers: whatever changes one of those drops every graph, they are re-captured on use.
+void invalidateGraphs(b2gpu_batch* b) {
+    if (b->graphExecIo) { cudaGraphExecDestroy(b->graphExecIo); b->graphExecIo = nullptr; }
+    if (b->graphExec) { cudaGraphExecDestroy(b->graphExec); b->graphExec = nullptr; }
+    if (b->graphExecChunk) { cudaGraphExecDestroy(b->graphExecChunk); b->graphExecChunk = nullptr; }
+}
+
 int enqueueStep(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent_t* marks) {
     return enqueueSteps(b, dt, velIters, posIters, marks, 1);
 }
@@ -1087,9 +1095,7 @@ int b2gpu_batch_upload_field(b2gpu_batch* b, int32_t field, const void* host, in
         for (int32_t i = 0; i < worldCount; ++i)
             if (flags[i] & B2G_WORLD_CONTINUOUS) { b->anyContinuous = true; break; }
         if (b->anyContinuous) {  // the captured steps have no k_toi: capture again
-            if (b->graphExecIo) { cudaGraphExecDestroy(b->graphExecIo); b->graphExecIo = nullptr; }
-            if (b->graphExec) { cudaGraphExecDestroy(b->graphExec); b->graphExec = nullptr; }
-            if (b->graphExecChunk) { cudaGraphExecDestroy(b->graphExecChunk); b->graphExecChunk = nullptr; }
+            invalidateGraphs(b);
         }
     }
     // any host edit may change what the islands depend on: rebuild them on the next step
@@ -1449,8 +1455,7 @@ int b2gpu_batch_snapshot_load(b2gpu_batch* b, const void* blob, int64_t size) {
     b->needInitialPairs = h.needInitialPairs != 0;
     if ((h.anyContinuous != 0) != b->anyContinuous) {
         b->anyContinuous = h.anyContinuous != 0;
-        if (b->graphExec) { cudaGraphExecDestroy(b->graphExec); b->graphExec = nullptr; }
-        if (b->graphExecChunk) { cudaGraphExecDestroy(b->graphExecChunk); b->graphExecChunk = nullptr; }
+        invalidateGraphs(b);
     }
     b->needProxyIndex = true;
     CUDA_TRY(cudaStreamSynchronize(b->stream));

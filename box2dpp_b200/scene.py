@@ -545,6 +545,48 @@ def sensors(seed: int, flags=WORLD_DEFAULT, bodies=14) -> Scene:
     return s
 
 
+def filtered(seed: int, flags=WORLD_DEFAULT, bodies=36) -> Scene:
+    """Collision filtering and per-body dynamics parameters that every other scene leaves at their defaults
+    (SURVEY.md §8 a21, a13): b2Filter categoryBits / maskBits / groupIndex — positive groups (always collide), negative
+    groups (never collide) and one-sided masks, the rule of b2ContactFilter::ShouldCollide (b2WorldCallbacks.cpp:26-39)
+    — and linearDamping / angularDamping (b2Island.cpp:217-218), gravityScale outside {0, 1}, fixedRotation bodies in
+    contact.  Boxes, circles and polygons dropped in a heap onto a box ground with two static ledges that only some
+    categories can stand on.  All randomness from LCG(seed)."""
+    rng = LCG(seed)
+    s = Scene((0.0, -10.0), flags)
+    g = s.create_body(STATIC_BODY, (0.0, 0.0))
+    s.create_box(g, 30.0, 1.0, center=(0.0, -1.0), angle=0.0, category=0x0010)                 # everyone lands here
+    s.create_box(g, 4.0, 0.25, center=(-6.0, 3.0), angle=0.0, category=0x0002, mask=0x0004)    # ledge for category 4 only
+    s.create_box(g, 4.0, 0.25, center=(6.0, 3.5), angle=0.1, category=0x0008, mask=0xFFFF, group=-3)  # not for group -3
+    cats = [0x0001, 0x0002, 0x0004, 0x0008]
+    for k in range(bodies):
+        px = float(F32(-11.0 + 2.0 * (k % 12)) + F32(rng.uniform(0.0, 0.8)))
+        py = float(F32(5.0 + 1.6 * (k // 12)) + F32(rng.uniform(0.0, 0.8)))
+        bflags = BD_DEFAULT | (BD_FIXED_ROTATION if k % 5 == 0 else 0)
+        b = s.create_body(DYNAMIC_BODY, (px, py), angle=rng.uniform(-0.6, 0.6), angular_velocity=rng.uniform(-2.0, 2.0),
+                          linear_damping=(0.0, 0.3, 1.5)[k % 3], angular_damping=(0.0, 0.8)[k % 2],
+                          gravity_scale=(1.0, 0.35, 2.5, -0.15, 1.0)[k % 5], flags=bflags)
+        cat = cats[int(rng.next_u() * 4) % 4]
+        u = rng.next_u()
+        mask = 0xFFFF if u < 0.4 else (0xFFFF & ~cats[int(rng.next_u() * 4) % 4] if u < 0.8 else (cat | 0x0010))
+        v = rng.next_u()
+        group = 0 if v < 0.5 else (2 if v < 0.65 else (-3 if v < 0.85 else -7))
+        kw = dict(density=1.0, friction=0.4, restitution=(0.0, 0.3)[k % 2], category=cat, mask=mask, group=group)
+        if k % 3 == 0:
+            s.create_circle(b, rng.uniform(0.3, 0.55), **kw)
+        elif k % 3 == 1:
+            s.create_box(b, rng.uniform(0.3, 0.6), rng.uniform(0.25, 0.5), **kw)
+        else:
+            n = 3 + int(rng.next_u() * 4) % 4
+            r = rng.uniform(0.35, 0.6)
+            poly = []
+            for j in range(n):
+                ang = (j + 0.7 * rng.next_u()) * (2.0 * np.pi / n)
+                poly.append((float(F32(r * np.cos(ang))), float(F32(r * np.sin(ang)))))
+            s.create_polygon(b, poly, **kw)
+    return s
+
+
 def jointed(seed: int, flags=WORLD_DEFAULT) -> Scene:
     """Joint scene: every mechanism the device path solves, in one world so that islands mix joints
     and contacts —

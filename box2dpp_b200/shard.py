@@ -19,6 +19,8 @@ def shard_range(total_worlds: int, world_size: int, rank: int) -> tuple[int, int
 
 def owner_of(world: int, total_worlds: int, world_size: int) -> int:
     """Rank that owns `world` under shard_range."""
+    if world_size <= 0 or not 0 <= world < total_worlds:
+        raise ValueError("bad shard arguments")
     base, extra = divmod(total_worlds, world_size)
     split = extra * (base + 1)
     if world < split:

@@ -185,6 +185,10 @@ WORLD_CASES = {
     "jointed_seed2_default_noccd": (lambda: S.jointed(2, flags=NOCCD), 400, 6, 2),
     "vehicles_seed1_default": (lambda: S.vehicles(1), 400, 8, 3),
     "vehicles_seed2_default_noccd": (lambda: S.vehicles(2, flags=NOCCD), 400, 6, 2),
+    # b2Filter category / mask / group rules, linear and angular damping, gravityScale, fixedRotation (round 2)
+    "filtered_seed1_noccd": (lambda: S.filtered(1, flags=NOCCD), 300, 8, 3),
+    "filtered_seed4_noccd_nosleep_62": (lambda: S.filtered(4, flags=NOCCD & ~S.WORLD_ALLOW_SLEEP), 300, 6, 2),
+    "filtered_seed2_default": (lambda: S.filtered(2), 300, 8, 3),
 }
 # scenes the C restatement can run (continuous physics off); the device path runs every case
 NOCCD_CASES = [k for k in WORLD_CASES if "default" not in k and "_ccd_" not in k]
