@@ -96,27 +96,79 @@ def build_scenes(workload, count, first_seed, flags, jittered=True):
     return scenes, scenes.__getitem__
 
 
-def cpu_reference_run(steps, warmup, threads=None, worlds_per_thread=16, workload="pyramid", flags=None):
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# measured on this pool's GPU hosts (16 cores): ~47 k pyramid / ~310 k mixed / ~600 k jointed world-steps/s; only used
+# to size the CPU sample so that one timed block lasts about a second
+CPU_RATE_GUESS = {"pyramid": 3000.0, "mixed": 20000.0, "jointed": 40000.0}  # world-steps/s per thread
+
+
+def cpu_reference_run(steps, warmup, threads=None, worlds_per_thread=None, workload="pyramid", flags=None, repeats=3):
     """The reference's own b2World::Step (vanilla Box2D compiled from /root/reference into oracle/_ref),
-    one world per thread slot on every host core.  Falls back to nothing: if oracle/_ref is absent the
-    C port is NOT a fair stand-in for speed, so we say so."""
+    one world per thread slot on every host core.  The sample is sized so that a timed block of `steps` steps lasts
+    >= ~1 s (a 0.1 s block read 76 k - 92 k on the same box in round 1), the block is timed `repeats` times back to
+    back and the median is the value; the spread is reported beside it.  If oracle/_ref is absent the C port is NOT a
+    fair stand-in for speed, so we say so."""
     from box2dpp_b200 import scene as S
     from oracle import worlds  # TEST INFRASTRUCTURE: used only as the CPU baseline / reference arm
     threads = threads or os.cpu_count()
+    if worlds_per_thread is None:
+        worlds_per_thread = int(min(512, max(16, -(-1.2 * CPU_RATE_GUESS[workload] // max(steps, 1)))))
     n = threads * worlds_per_thread
     flags = flags_throughput() if flags is None else flags
     _, get = build_scenes(workload, n, 0, flags)
     scenes = [get(i) for i in range(n)]
     if not worlds.available("ref"):
         return None
-    sec, _ = worlds.bench_run(scenes, worlds_per_thread, threads, steps, warmup, DT, 8, 3)
+    secs = worlds.bench_run_repeats(scenes, worlds_per_thread, threads, steps, warmup, DT, 8, 3, repeats)
+    med = sorted(secs)[len(secs) // 2]
     what = {"pyramid": f"jittered pyramid-{ROWS}", "mixed": "mixed-shape (chain terrain, circles, polygons)",
             "jointed": "jointed (bridge, cart-pole, walker, pendulums)"}[workload]
-    return {"value": n * steps / sec, "unit": "world-steps/s", "cores": threads, "kind": "reference",
+    return {"value": n * steps / med, "unit": "world-steps/s", "cores": threads, "kind": "reference",
+            "cpu": cpu_model(),
             "sample": f"{threads} threads x {worlds_per_thread} {what} worlds, {warmup} warm-up + "
-                      f"{steps} timed steps, 8/3 iterations, sleeping {'on' if flags & S.WORLD_ALLOW_SLEEP else 'off'}, "
+                      f"{repeats} x {steps} timed steps (median), 8/3 iterations, sleeping {'on' if flags & S.WORLD_ALLOW_SLEEP else 'off'}, "
                       f"TOI {'on' if flags & S.WORLD_CONTINUOUS else 'off'}, vanilla Box2D 2.3.2 -O2",
-            "seconds": sec, "worlds": n}
+            "repeat_values": [n * steps / x for x in secs],
+            "spread": (max(secs) - min(secs)) / med,
+            "seconds": med, "worlds": n}
+
+
+def pin_to_gpu_numa(gpu_index):
+    """Bind this process to the CPUs of the NUMA node its GPU hangs off (before any pinned buffer is allocated, so that
+    first touch puts the staging memory next to the GPU's root port).  Returns what it did, for the JSON line."""
+    info = {"gpu": gpu_index, "node": None, "cpus": None}
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={gpu_index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("0000") and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]  # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["node"] = node
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["cpus"] = f"{min(use)}-{max(use)} ({len(use)} of {len(allowed)} allowed)"
+        else:
+            info["cpus"] = f"unchanged: {len(allowed)} allowed CPUs, {'all local' if use == allowed else 'none local'}"
+    except Exception as exc:  # a container without sysfs PCI nodes: leave the affinity alone
+        info["error"] = str(exc)[:80]
+    return info
 
 
 def main():
@@ -180,7 +232,7 @@ def main():
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "body_steps_per_s": r["value"] * nbody,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu", "repeat_values", "spread")},
                 "e2e": {"value": r["value"], "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -188,6 +240,7 @@ def main():
 
     from box2dpp_b200.batch import F_CONTACT_COUNT, F_ISLAND_CONTACT_END, F_ISLAND_COUNT, WorldBatch
 
+    numa = pin_to_gpu_numa(local_rank)
     dist = None
     if world_size > 1:
         import torch
@@ -242,16 +295,20 @@ def main():
     kms = {k: v / prof_steps for k, v in batch.profile_kernels(DT, 8, 3, prof_steps).items()}
 
     # ---- end to end through the C ABI with host buffers: forces H2D, step, transforms D2H, every step ----
-    import ctypes
     e2e_steps = args.e2e_steps or max(10, min(args.steps, 100))
+    # What crosses the bus every step: a force (fx, fy, torque) for every non-static body going in, the pose (x, y, angle)
+    # of every non-static body coming out (b2gpu_batch_io_select): not the static ground / terrain, three floats per pose.
+    scene0 = sb.scene(0) if hasattr(sb, "scene") else sb[0]
+    io_bodies = [i for i, bd in enumerate(scene0.bodies) if bd.type != S.STATIC_BODY]
+    batch.io_select(force_bodies=io_bodies, pose_bodies=io_bodies, xya=True)
     try:
         import torch
-        forces_t = torch.zeros((W, batch.max_bodies, 3), dtype=torch.float32).pin_memory()
-        out_t = torch.empty((W, batch.max_bodies, 4), dtype=torch.float32).pin_memory()
+        forces_t = torch.zeros((W, len(io_bodies), 3), dtype=torch.float32).pin_memory()
+        out_t = torch.empty((W, len(io_bodies), 3), dtype=torch.float32).pin_memory()
         forces, out = forces_t.numpy(), out_t.numpy()
     except Exception:
-        forces = np.zeros((W, batch.max_bodies, 3), np.float32)
-        out = np.empty((W, batch.max_bodies, 4), np.float32)
+        forces = np.zeros((W, len(io_bodies), 3), np.float32)
+        out = np.empty((W, len(io_bodies), 3), np.float32)
     # (a) the three separate calls, everything on the batch's stream: copy in, step, copy out
     for _ in range(3):
         batch.apply_forces(forces); batch.step(DT, 8, 3); batch.read_transforms(out)
@@ -283,6 +340,8 @@ def main():
     e2e = {"value": total_worlds * e2e_steps / e2e_s, "unit": "world-steps/s",
            "h2d_bytes_per_step": int(forces.nbytes) * world_size, "d2h_bytes_per_step": int(out.nbytes) * world_size,
            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "call": "b2gpu_batch_step_io",
+           "io": f"forces in and poses (x, y, angle) out for the {len(io_bodies)} non-static bodies of every world "
+                 f"(b2gpu_batch_io_select), pinned host buffers", "numa": numa,
            "device_resident_ms_per_step_same_regime": same_regime_ms,
            "separate_calls": {"value": total_worlds * e2e_steps / sep_s, "ms_per_step": 1e3 * sep_s / e2e_steps,
                               "call": "b2gpu_batch_apply_forces + b2gpu_batch_step + b2gpu_batch_read_transforms"}}
@@ -353,9 +412,9 @@ def main():
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_reference_run(200, preroll + 10, workload=args.workload, flags=flags)
+            cpu = cpu_reference_run(100, preroll + 10, workload=args.workload, flags=flags, worlds_per_thread=32, repeats=3)
             if cpu:
-                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu", "spread")}
         except Exception as exc:  # the baseline is a report, never a dependency of the GPU number
             cpu = {"error": str(exc)}
     batch.close()

@@ -39,7 +39,7 @@ EVENT_ALL = 15
 EXPORTED_SYMBOLS = [
     "b2gpu_batch_create", "b2gpu_batch_destroy", "b2gpu_batch_upload_field", "b2gpu_batch_download_field",
     "b2gpu_batch_field_shape", "b2gpu_batch_step", "b2gpu_batch_step_n", "b2gpu_batch_sync",
-    "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_step_io", "b2gpu_batch_last_step_ms",
+    "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_step_io", "b2gpu_batch_io_select", "b2gpu_batch_last_step_ms",
     "b2gpu_batch_profile_steps", "b2gpu_batch_profile_kernels", "b2gpu_batch_kernel_name", "b2gpu_batch_launch_count", "b2gpu_last_error", "b2gpu_scene_capacities",
     "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build", "b2gpu_host_sincosf", "b2gpu_sincosf",
     "b2gpu_collide_pairs",
@@ -99,6 +99,7 @@ def lib():
         L.b2gpu_batch_apply_forces.argtypes = [vp, vp]
         L.b2gpu_batch_read_transforms.argtypes = [vp, vp]
         L.b2gpu_batch_step_io.argtypes = [vp, vp, C.c_float, i32, i32, vp]
+        L.b2gpu_batch_io_select.argtypes = [vp, vp, i32, vp, i32, i32]
         L.b2gpu_batch_body_commands.argtypes = [vp, vp, C.c_int64]
         L.b2gpu_batch_read_body_state.argtypes = [vp, vp]
         L.b2gpu_batch_query_aabb.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
@@ -184,6 +185,8 @@ class WorldBatch:
         _check(L.b2gpu_batch_build_worlds(self.h, arr, n_scenes, 0, replicate))
         self.max_bodies = d.maxBodies
         self._pinned = {}
+        self.io_force_count = self.io_pose_count = d.maxBodies  # b2gpu_batch_io_select
+        self.io_pose_floats = 4
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
@@ -245,23 +248,40 @@ class WorldBatch:
         _check(lib().b2gpu_batch_upload_field(self.h, fid, v.ctypes.data_as(C.c_void_p), first, v.shape[0]))
 
     # ---- per-step I/O ----
+    def io_select(self, force_bodies=None, pose_bodies=None, xya=False):
+        """b2gpu_batch_io_select: the bodies (index lists, the same in every world; None = every body slot, [] = none)
+        whose forces go in / whose poses come out, and the pose format (xya: p.x p.y angle instead of p.x p.y q.s q.c)."""
+        def arg(ids):
+            if ids is None:
+                return None, -1
+            a = np.ascontiguousarray(ids, np.int32)
+            return a, a.shape[0]
+        fa, fn = arg(force_bodies)
+        pa, pn = arg(pose_bodies)
+        _check(lib().b2gpu_batch_io_select(self.h, fa.ctypes.data_as(C.c_void_p) if fa is not None else None, fn,
+                                           pa.ctypes.data_as(C.c_void_p) if pa is not None else None, pn, 1 if xya else 0))
+        self.io_force_count = self.max_bodies if fn < 0 else fn
+        self.io_pose_count = self.max_bodies if pn < 0 else pn
+        self.io_pose_floats = 3 if xya else 4
+
     def apply_forces(self, forces: np.ndarray):
         f = np.ascontiguousarray(forces, np.float32)
-        assert f.size == self.num_worlds * self.max_bodies * 3
+        assert f.size == self.num_worlds * self.io_force_count * 3
         _check(lib().b2gpu_batch_apply_forces(self.h, f.ctypes.data_as(C.c_void_p)))
 
     def step_io(self, forces: np.ndarray | None, dt: float, vel_iters: int, pos_iters: int,
                 out: np.ndarray | None = None) -> np.ndarray:
         """b2gpu_batch_step_io: apply_forces + step + read_transforms in one call, the host copies of each world
-        group overlapped with the other groups' kernels.  Returns the transforms [W, maxBodies, 4]."""
+        group overlapped with the other groups' kernels.  Returns the transforms [W, bodies, 4] (or what io_select chose)."""
         fptr = None
         if forces is not None:
             f = np.ascontiguousarray(forces, np.float32)
-            assert f.size == self.num_worlds * self.max_bodies * 3
+            assert f.size == self.num_worlds * self.io_force_count * 3
             fptr = f.ctypes.data_as(C.c_void_p)
         if out is None:
-            out = np.empty((self.num_worlds, self.max_bodies, 4), np.float32)
-        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.num_worlds * self.max_bodies * 4
+            out = np.empty((self.num_worlds, self.io_pose_count, self.io_pose_floats), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous
+        assert out.size == self.num_worlds * self.io_pose_count * self.io_pose_floats
         _check(lib().b2gpu_batch_step_io(self.h, fptr, dt, vel_iters, pos_iters, out.ctypes.data_as(C.c_void_p)))
         return out
 
@@ -295,7 +315,8 @@ class WorldBatch:
 
     def read_transforms(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:
-            out = np.empty((self.num_worlds, self.max_bodies, 4), np.float32)
+            out = np.empty((self.num_worlds, self.io_pose_count, self.io_pose_floats), np.float32)
+        assert out.size == self.num_worlds * self.io_pose_count * self.io_pose_floats
         _check(lib().b2gpu_batch_read_transforms(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
 

@@ -625,10 +625,67 @@ const int kBuildFields[] = {
 
 }  // namespace
 
+// Checks a scene description at the C ABI boundary: every index the host layer is going to follow must be in range,
+// every shape must have the vertices its class needs (b2EdgeShape 2, b2PolygonShape::Set 3..8, b2ChainShape::CreateChain
+// >= 2, CreateLoop >= 3).  Returns B2GPU_OK or sets the error message.
+static int ValidateFixtures(const b2g_fixture_def* fixtures, int fixtureCount, int bodyCount, const float* vertices, int vertexCount,
+                            const char* what) {
+    char msg[160];
+    if (fixtureCount < 0 || bodyCount < 0 || vertexCount < 0 || (fixtureCount > 0 && !fixtures)) {
+        snprintf(msg, sizeof(msg), "%s: negative count or null fixture array", what);
+        return b2gpu_host_set_error(B2GPU_ERR_INVALID, msg);
+    }
+    for (int i = 0; i < fixtureCount; ++i) {
+        const b2g_fixture_def& d = fixtures[i];
+        int need = 0, least = 0;
+        switch (d.shapeType) {
+            case B2G_SHAPE_CIRCLE: break;
+            case B2G_SHAPE_EDGE: need = 2; break;
+            case B2G_SHAPE_POLYGON:
+                if (d.shapeKind == B2G_POLY_SET) { need = d.vertexCount; least = 3; }
+                break;
+            case B2G_SHAPE_CHAIN: need = d.vertexCount; least = d.shapeKind == B2G_CHAIN_LOOP ? 3 : 2; break;
+            default:
+                snprintf(msg, sizeof(msg), "%s: fixture %d has unknown shape type %d", what, i, d.shapeType);
+                return b2gpu_host_set_error(B2GPU_ERR_INVALID, msg);
+        }
+        if (d.body < 0 || d.body >= bodyCount) {
+            snprintf(msg, sizeof(msg), "%s: fixture %d names body %d of %d", what, i, d.body, bodyCount);
+            return b2gpu_host_set_error(B2GPU_ERR_INVALID, msg);
+        }
+        if (need < least || (d.shapeType == B2G_SHAPE_POLYGON && need > kMaxPolygonVertices)) {
+            snprintf(msg, sizeof(msg), "%s: fixture %d has %d vertices (its shape class needs %d..)", what, i, need, least);
+            return b2gpu_host_set_error(B2GPU_ERR_INVALID, msg);
+        }
+        if (need > 0 && (!vertices || d.firstVertex < 0 || (long long)d.firstVertex + need > (long long)vertexCount)) {
+            snprintf(msg, sizeof(msg), "%s: fixture %d reads vertices [%d, %d) of %d", what, i, d.firstVertex, d.firstVertex + need,
+                     vertexCount);
+            return b2gpu_host_set_error(B2GPU_ERR_INVALID, msg);
+        }
+    }
+    return B2GPU_OK;
+}
+static int ValidateScene(const b2g_scene& s, int index) {
+    char what[48];
+    snprintf(what, sizeof(what), "scene %d", index);
+    if (s.bodyCount < 0 || (s.bodyCount > 0 && !s.bodies) || s.jointCount < 0 || (s.jointCount > 0 && !s.joints))
+        return b2gpu_host_set_error(B2GPU_ERR_INVALID, "scene: negative count or null body / joint array");
+    int rc = ValidateFixtures(s.fixtures, s.fixtureCount, s.bodyCount, s.vertices, s.vertexCount, what);
+    if (rc != B2GPU_OK) return rc;
+    for (int j = 0; j < s.jointCount; ++j)
+        if (s.joints[j].bodyA < 0 || s.joints[j].bodyA >= s.bodyCount || s.joints[j].bodyB < 0 || s.joints[j].bodyB >= s.bodyCount)
+            return b2gpu_host_set_error(B2GPU_ERR_INVALID, "scene: a joint names a body that does not exist");
+    return B2GPU_OK;
+}
+
 extern "C" {
 
 int b2gpu_scene_capacities(const b2g_scene* scenes, int32_t sceneCount, b2gpu_batch_desc* desc) {
     if (!scenes || !desc || sceneCount <= 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < sceneCount; ++i) {
+        int rc = ValidateScene(scenes[i], i);
+        if (rc != B2GPU_OK) return rc;
+    }
     int NB = 1, NF = 1, NP = 1, NS = 4, NV = 1;
     for (int i = 0; i < sceneCount; ++i) {
         int nb, nf, np, ns, nv;
@@ -662,6 +719,10 @@ int b2gpu_scene_capacities(const b2g_scene* scenes, int32_t sceneCount, b2gpu_ba
 int b2gpu_batch_build_worlds(b2gpu_batch* batch, const b2g_scene* scenes, int32_t sceneCount, int32_t firstWorld,
                              int32_t replicate) {
     if (!batch || !scenes || sceneCount <= 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < sceneCount; ++i) {
+        int rc = ValidateScene(scenes[i], i);
+        if (rc != B2GPU_OK) return rc;
+    }
     if (replicate < 1) replicate = 1;
     if (replicate > 1 && sceneCount != 1) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "replicate needs exactly one scene");
     std::vector<std::pair<int, int>> shapes(B2GPU_F_COUNT);
@@ -790,6 +851,34 @@ int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, f
     MassData md = ComputeMass(sh, fd->density);
     out[34] = md.mass; out[35] = md.center.x; out[36] = md.center.y; out[37] = md.I;
     return sh.count;
+}
+
+int b2gpu_host_body_mass_data(const b2g_scene* scene, int32_t body, float* out) {
+    if (!scene || !out || body < 0 || body >= scene->bodyCount) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    int rc = ValidateFixtures(scene->fixtures, scene->fixtureCount, scene->bodyCount, scene->vertices, scene->vertexCount, "scene");
+    if (rc != B2GPU_OK) return rc;
+    // b2Body::ResetMassData (b2Body.cpp:283-352), the loop of Flatten above for one body
+    const b2g_body_def& bd = scene->bodies[body];
+    float mass = 0.0f, I = 0.0f;
+    Vec2 localCenter = V2(0.0f, 0.0f);
+    if (bd.type == B2G_DYNAMIC_BODY) {
+        for (int f = scene->fixtureCount - 1; f >= 0; --f) {  // fixture list is head-inserted: newest first
+            const b2g_fixture_def& fd = scene->fixtures[f];
+            if (fd.body != body || fd.density == 0.0f) continue;
+            HostShape sh;
+            BuildShape(sh, fd, scene->vertices);
+            MassData md = ComputeMass(sh, fd.density);
+            mass += md.mass;
+            localCenter = localCenter + md.mass * md.center;
+            I += md.I;
+        }
+        if (mass > 0.0f) localCenter = (1.0f / mass) * localCenter;
+        else mass = 1.0f;
+        if (I > 0.0f && (bd.flags & B2G_BD_FIXED_ROTATION) == 0) I -= mass * Dot(localCenter, localCenter);
+        else I = 0.0f;
+    }
+    out[0] = mass; out[1] = I; out[2] = localCenter.x; out[3] = localCenter.y;
+    return B2GPU_OK;
 }
 
 int b2gpu_host_sincosf(const float* x, float* s, float* c, int64_t n) {

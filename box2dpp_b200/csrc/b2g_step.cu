@@ -73,20 +73,22 @@ __global__ void k_interleave(uint32_t* __restrict__ arena, const uint32_t* __res
 // b2Body::ApplyForceToCenter / ApplyTorque for every body (Box2D/Dynamics/b2Body.h:738-790):
 // wake on a non-zero force, then accumulate if awake.
 // Covers tiles [A.tile0, A.tile0 + tileCount): the whole batch, or one world group's share (b2gpu_batch_step_io).
-__global__ void k_apply_forces(Arena A, const float* __restrict__ forces, int tileCount) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // lane-fastest: (tile, body, lane)
-    size_t total = (size_t)tileCount * A.NB * kTile;
+// `sel` (device, nSel body indices, the same in every world) picks the bodies that take part; null = every body slot.
+__global__ void k_apply_forces(Arena A, const float* __restrict__ forces, int tileCount, const int* __restrict__ sel, int nSel) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // lane-fastest: (tile, selected body, lane)
+    size_t total = (size_t)tileCount * nSel * kTile;
     if (idx >= total) return;
-    idx += (size_t)A.tile0 * A.NB * kTile;
     int lane = (int)(idx & 31);
     size_t r = idx >> 5;
-    int body = (int)(r % A.NB);
-    int tile = (int)(r / A.NB);
+    int k = (int)(r % nSel);
+    int tile = A.tile0 + (int)(r / nSel);
+    int body = sel ? sel[k] : k;
     int w = tile * kTile + lane;
     if (w >= A.numWorlds || body >= A.bodyCount[(size_t)tile * kTile + lane]) return;
-    const float* f = forces + ((size_t)w * A.NB + body) * 3;
+    const float* f = forces + ((size_t)w * nSel + k) * 3;
     float fx = f[0], fy = f[1], tq = f[2];
     if (fx == 0.0f && fy == 0.0f && tq == 0.0f) return;
+    idx = ((size_t)tile * A.NB + body) * kTile + lane;
     int flags = A.bodyFlags[idx];
     if ((flags & kBodyTypeMask) != B2G_DYNAMIC_BODY || (flags & kBodyDestroyed)) return;
     if ((flags & kBodyAwake) == 0) {
@@ -98,19 +100,27 @@ __global__ void k_apply_forces(Arena A, const float* __restrict__ forces, int ti
     A.bodyForce[idx] = make_float4(cur.x + fx, cur.y + fy, cur.z + tq, 0.0f);
 }
 
-// b2Body::GetTransform for every body, world-major output
-__global__ void k_read_transforms(Arena A, float4* __restrict__ out, int tileCount) {
+// b2Body::GetTransform (format B2GPU_POSE_XF: p.x p.y q.s q.c) or GetPosition + GetAngle (B2GPU_POSE_XYA: p.x p.y angle)
+// of the selected bodies, world-major output
+__global__ void k_read_transforms(Arena A, float* __restrict__ out, int tileCount, const int* __restrict__ sel, int nSel, int format) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)tileCount * A.NB * kTile;
+    size_t total = (size_t)tileCount * nSel * kTile;
     if (idx >= total) return;
-    idx += (size_t)A.tile0 * A.NB * kTile;
     int lane = (int)(idx & 31);
     size_t r = idx >> 5;
-    int body = (int)(r % A.NB);
-    int tile = (int)(r / A.NB);
+    int k = (int)(r % nSel);
+    int tile = A.tile0 + (int)(r / nSel);
+    int body = sel ? sel[k] : k;
     int w = tile * kTile + lane;
     if (w >= A.numWorlds) return;
-    out[(size_t)w * A.NB + body] = A.bodyXf[idx];
+    idx = ((size_t)tile * A.NB + body) * kTile + lane;
+    const float4 xf = A.bodyXf[idx];
+    if (format == B2GPU_POSE_XYA) {
+        float* o = out + ((size_t)w * nSel + k) * 3;
+        o[0] = xf.x; o[1] = xf.y; o[2] = A.bodySweep[idx].z;
+    } else {
+        reinterpret_cast<float4*>(out)[(size_t)w * nSel + k] = xf;
+    }
 }
 
 // b2Body state for every body, world-major output: p.x p.y angle awake | v.x v.y omega sleepTime
@@ -600,6 +610,11 @@ struct b2gpu_batch {
     // per-step I/O staging
     float* ioDev = nullptr;
     size_t ioBytes = 0;
+    // b2gpu_batch_io_select: the bodies (device index lists; null = every body slot) and the format of the dense I/O
+    int* ioForceSel = nullptr;
+    int* ioPoseSel = nullptr;
+    int ioForceCount = 0, ioPoseCount = 0;  // entries per world (NB while nothing is selected)
+    int ioPoseFormat = B2GPU_POSE_XF;
     b2gpu_body_command* cmdDev = nullptr;
     size_t cmdBytes = 0;
 };
@@ -849,11 +864,11 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
         return;
     } else if (part == 1) {
         if (b->tileSolver) {
-            k_solve_velocity<<<tiles, 96, b->solveSmem, st>>>(A, velIters);
+            k_solve_velocity<<<tiles, 128, b->solveSmem, st>>>(A, velIters);
             mark();
             k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
             mark();
-            k_solve_position<<<tiles, 96, b->solveSmem, st>>>(A, posIters);
+            k_solve_position<<<tiles, 128, b->solveSmem, st>>>(A, posIters);
             mark();
         } else {
             k_solve<<<blocks, threads, 0, st>>>(A, dt, velIters, posIters);
@@ -888,10 +903,10 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
 // its worlds' transforms out after it, on its own stream, so one group's PCIe transfers run under the other groups'
 // kernels instead of in front of and behind the whole batch's step.
 struct StepIo {
-    const float* forces;   // host, [world][maxBodies][3] or null
-    float* transforms;     // host, [world][maxBodies][4] or null
+    const float* forces;   // host, [world][ioForceCount][3] or null
+    float* transforms;     // host, [world][ioPoseCount][3 or 4] or null
     float* devForces;      // device staging, same shapes
-    float4* devTransforms;
+    float* devTransforms;
     int groups;            // world groups for this call (>= b->groups)
 };
 
@@ -942,13 +957,14 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
             // this group's worlds and their slice of the host buffers
             const int w0 = t0 * kTile;
             const int w1 = (t0 + n) * kTile < b->desc.numWorlds ? (t0 + n) * kTile : b->desc.numWorlds;
-            const size_t ioItems = (size_t)n * b->A.NB * kTile;
+            const int nF = b->ioForceCount, nP = b->ioPoseCount, poseFloats = b->ioPoseFormat == B2GPU_POSE_XYA ? 3 : 4;
             Arena Ag = b->A;
             Ag.tile0 = t0;
-            if (io && io->forces && w1 > w0) {
-                const size_t off = (size_t)w0 * b->A.NB * 3, len = (size_t)(w1 - w0) * b->A.NB * 3;
+            if (io && io->forces && w1 > w0 && nF > 0) {
+                const size_t off = (size_t)w0 * nF * 3, len = (size_t)(w1 - w0) * nF * 3;
+                const size_t items = (size_t)n * nF * kTile;
                 cudaMemcpyAsync(io->devForces + off, io->forces + off, len * sizeof(float), cudaMemcpyHostToDevice, gs);
-                k_apply_forces<<<(unsigned)((ioItems + 255) / 256), 256, 0, gs>>>(Ag, io->devForces, n);
+                k_apply_forces<<<(unsigned)((items + 255) / 256), 256, 0, gs>>>(Ag, io->devForces, n, b->ioForceSel, nF);
                 b->launches++;
             }
             enqueuePart(b, 0, dt, velIters, posIters, mk, &m, gs, t0, n);
@@ -959,12 +975,13 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
             enqueuePart(b, 1, dt, velIters, posIters, mk, &m, gs, t0, n);
             if (pipeline) cudaEventRecord(b->evSeq[g], gs);
             enqueuePart(b, 2, dt, velIters, posIters, mk, &m, gs, t0, n);
-            if (io && io->transforms && w1 > w0) {
-                const size_t off = (size_t)w0 * b->A.NB * 4, len = (size_t)(w1 - w0) * b->A.NB * 4;
-                k_read_transforms<<<(unsigned)((ioItems + 255) / 256), 256, 0, gs>>>(Ag, io->devTransforms, n);
+            if (io && io->transforms && w1 > w0 && nP > 0) {
+                const size_t off = (size_t)w0 * nP * poseFloats, len = (size_t)(w1 - w0) * nP * poseFloats;
+                const size_t items = (size_t)n * nP * kTile;
+                k_read_transforms<<<(unsigned)((items + 255) / 256), 256, 0, gs>>>(Ag, io->devTransforms, n, b->ioPoseSel, nP,
+                                                                                 b->ioPoseFormat);
                 b->launches++;
-                cudaMemcpyAsync(io->transforms + off, (const float*)io->devTransforms + off, len * sizeof(float),
-                                cudaMemcpyDeviceToHost, gs);
+                cudaMemcpyAsync(io->transforms + off, io->devTransforms + off, len * sizeof(float), cudaMemcpyDeviceToHost, gs);
             }
         }
     }
@@ -1023,6 +1040,15 @@ int b2gpu_batch_create(const b2gpu_batch_desc* desc, b2gpu_batch** out) {
         return fail(B2GPU_ERR_INVALID, "capacities must be positive");
     if (desc->maxBodies > 65535 || desc->maxFixtures > 65535 || desc->maxProxies > 65535)
         return fail(B2GPU_ERR_CAPACITY, "bodies, fixtures and proxies per world are limited to 65535");
+    if (desc->maxJoints < 0 || desc->maxEvents < 0 || desc->maxChainVerts < 0)
+        return fail(B2GPU_ERR_INVALID, "maxJoints, maxEvents and maxChainVerts must not be negative");
+    {   // the arenas index with size_t, but the per-world capacities multiply: refuse what cannot be a real request
+        const double perWorld = 200.0 * desc->maxBodies + 48.0 * desc->maxFixtures + 40.0 * desc->maxProxies +
+                                600.0 * desc->maxContacts + 4.0 * desc->maxShapeWords + 8.0 * desc->maxChainVerts +
+                                32.0 * desc->maxEvents + 200.0 * desc->maxJoints;
+        if (perWorld * (double)desc->numWorlds > 1.0e12)
+            return fail(B2GPU_ERR_CAPACITY, "numWorlds x capacities asks for more than 1 TB of device memory");
+    }
     if (desc->blockSize != 0 && (desc->blockSize % 32 != 0 || desc->blockSize > 128))
         return fail(B2GPU_ERR_INVALID, "blockSize must be 32, 64, 96 or 128");
     CUDA_TRY(cudaSetDevice(desc->device));
@@ -1037,6 +1063,7 @@ int b2gpu_batch_create(const b2gpu_batch_desc* desc, b2gpu_batch** out) {
     e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete b; return fail(B2GPU_ERR_CUDA, "stream create failed: %s", cudaGetErrorString(e)); }
     int rc = allocateArena(b);
+    b->ioForceCount = b->ioPoseCount = b->A.NB;  // dense I/O covers every body slot until b2gpu_batch_io_select says otherwise
     if (rc == B2GPU_OK) {
         e = cudaEventCreate(&b->evStart);
         if (e == cudaSuccess) e = cudaEventCreate(&b->evStop);
@@ -1067,6 +1094,8 @@ int b2gpu_batch_destroy(b2gpu_batch* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (void* p : b->allocations) cudaFree(p);
     if (b->ioDev) cudaFree(b->ioDev);
+    if (b->ioForceSel) cudaFree(b->ioForceSel);
+    if (b->ioPoseSel) cudaFree(b->ioPoseSel);
     if (b->cmdDev) cudaFree(b->cmdDev);
     if (b->graphExec) cudaGraphExecDestroy(b->graphExec);
     if (b->graphExecChunk) cudaGraphExecDestroy(b->graphExecChunk);
@@ -1283,15 +1312,48 @@ static int ensureIo(b2gpu_batch* b, size_t need = 0) {
     return B2GPU_OK;
 }
 
+int b2gpu_batch_io_select(b2gpu_batch* b, const int32_t* forceBodies, int32_t forceCount, const int32_t* poseBodies,
+                          int32_t poseCount, int32_t poseFormat) {
+    if (!b) return fail(B2GPU_ERR_INVALID, "null batch");
+    if (poseFormat != B2GPU_POSE_XF && poseFormat != B2GPU_POSE_XYA) return fail(B2GPU_ERR_INVALID, "unknown pose format %d", poseFormat);
+    if (forceCount < -1 || poseCount < -1 || (forceCount > 0 && !forceBodies) || (poseCount > 0 && !poseBodies))
+        return fail(B2GPU_ERR_INVALID, "bad body selection");
+    for (int i = 0; i < forceCount; ++i)
+        if (forceBodies[i] < 0 || forceBodies[i] >= b->A.NB) return fail(B2GPU_ERR_INVALID, "force body %d out of range", forceBodies[i]);
+    for (int i = 0; i < poseCount; ++i)
+        if (poseBodies[i] < 0 || poseBodies[i] >= b->A.NB) return fail(B2GPU_ERR_INVALID, "pose body %d out of range", poseBodies[i]);
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));  // nothing in flight uses the old lists
+    auto set = [&](int** dev, int* count, const int32_t* host, int n) -> int {
+        if (*dev) { cudaFree(*dev); *dev = nullptr; }
+        if (n < 0) { *count = b->A.NB; return B2GPU_OK; }  // every body slot
+        *count = n;
+        if (n == 0) return B2GPU_OK;
+        CUDA_TRY(cudaMalloc((void**)dev, (size_t)n * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(*dev, host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        return B2GPU_OK;
+    };
+    int rc = set(&b->ioForceSel, &b->ioForceCount, forceBodies, forceCount);
+    if (rc != B2GPU_OK) return rc;
+    rc = set(&b->ioPoseSel, &b->ioPoseCount, poseBodies, poseCount);
+    if (rc != B2GPU_OK) return rc;
+    b->ioPoseFormat = poseFormat;
+    invalidateGraphs(b);  // the step_io graph holds the old lists and sizes
+    return B2GPU_OK;
+}
+
 int b2gpu_batch_apply_forces(b2gpu_batch* b, const float* forces) {
     if (!b || !forces) return fail(B2GPU_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(b->desc.device));
-    int rc = ensureIo(b);
+    if (b->ioForceCount == 0) return B2GPU_OK;
+    size_t bytes = (size_t)b->desc.numWorlds * b->ioForceCount * 3 * sizeof(float);
+    int rc = ensureIo(b, bytes);
     if (rc != B2GPU_OK) return rc;
-    size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 3 * sizeof(float);
     CUDA_TRY(cudaMemcpyAsync(b->ioDev, forces, bytes, cudaMemcpyHostToDevice, b->stream));
-    size_t total = (size_t)b->A.numTiles * b->A.NB * kTile;
-    k_apply_forces<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, b->ioDev, b->A.numTiles);
+    size_t total = (size_t)b->A.numTiles * b->ioForceCount * kTile;
+    Arena A = b->A;
+    A.tile0 = 0;
+    k_apply_forces<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(A, b->ioDev, b->A.numTiles, b->ioForceSel, b->ioForceCount);
     b->launches++;
     CUDA_TRY(cudaGetLastError());
     return B2GPU_OK;
@@ -1300,13 +1362,18 @@ int b2gpu_batch_apply_forces(b2gpu_batch* b, const float* forces) {
 int b2gpu_batch_read_transforms(b2gpu_batch* b, float* out) {
     if (!b || !out) return fail(B2GPU_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(b->desc.device));
-    int rc = ensureIo(b);
+    if (b->ioPoseCount == 0) return B2GPU_OK;
+    const int poseFloats = b->ioPoseFormat == B2GPU_POSE_XYA ? 3 : 4;
+    size_t bytes = (size_t)b->desc.numWorlds * b->ioPoseCount * poseFloats * sizeof(float);
+    int rc = ensureIo(b, bytes);
     if (rc != B2GPU_OK) return rc;
-    size_t total = (size_t)b->A.numTiles * b->A.NB * kTile;
-    k_read_transforms<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(b->A, (float4*)b->ioDev, b->A.numTiles);
+    size_t total = (size_t)b->A.numTiles * b->ioPoseCount * kTile;
+    Arena A = b->A;
+    A.tile0 = 0;
+    k_read_transforms<<<(unsigned)((total + 255) / 256), 256, 0, b->stream>>>(A, b->ioDev, b->A.numTiles, b->ioPoseSel, b->ioPoseCount,
+                                                                             b->ioPoseFormat);
     b->launches++;
     CUDA_TRY(cudaGetLastError());
-    size_t bytes = (size_t)b->desc.numWorlds * b->A.NB * 4 * sizeof(float);
     CUDA_TRY(cudaMemcpyAsync(out, b->ioDev, bytes, cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     return B2GPU_OK;
@@ -1316,14 +1383,16 @@ int b2gpu_batch_read_transforms(b2gpu_batch* b, float* out) {
 int b2gpu_batch_step_io(b2gpu_batch* b, const float* forces, float dt, int32_t velIters, int32_t posIters, float* transforms) {
     if (!b) return fail(B2GPU_ERR_INVALID, "null batch");
     CUDA_TRY(cudaSetDevice(b->desc.device));
-    const size_t perBody = (size_t)b->desc.numWorlds * b->A.NB * sizeof(float);
-    int rc = ensureIo(b, perBody * 8);  // forces (3 floats, padded to 4) and transforms (4 floats) side by side
+    // device staging: forces first, transforms behind them (16-byte aligned for the float4 stores of B2GPU_POSE_XF)
+    const size_t forceFloats = ((size_t)b->desc.numWorlds * b->ioForceCount * 3 + 3) & ~(size_t)3;
+    const size_t poseFloats = (size_t)b->desc.numWorlds * b->ioPoseCount * 4;
+    int rc = ensureIo(b, (forceFloats + poseFloats) * sizeof(float));
     if (rc != B2GPU_OK) return rc;
     StepIo io;
     io.forces = forces;
     io.transforms = transforms;
     io.devForces = b->ioDev;
-    io.devTransforms = reinterpret_cast<float4*>(b->ioDev + (size_t)b->desc.numWorlds * b->A.NB * 4);
+    io.devTransforms = b->ioDev + forceFloats;
     // eight groups: the exposed transfers are the first group's copy in and the last group's copy out, an eighth of the
     // batch's each (16,384 pyramid worlds, ms per step for 2 / 4 / 8 groups: 6.81 / 6.46 / 6.28; separate calls 8.60)
     io.groups = b2gpu_batch::kMaxGroups;

@@ -30,6 +30,7 @@
 #define B2_WORLD_BATCH_H
 
 #include <array>
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -399,6 +400,19 @@ private:
     friend class b2WorldBatch;
     friend class b2Joint;
     void SetMouseTarget(const b2Vec<float, 2>& target);  // b2Joint::SetTarget of the mouse joint attached to this body
+    // While the scene is still being recorded (no Step yet) edits are queued and getters are answered on the host from
+    // this shadow of the body's definition, so a `body->SetLinearVelocity(..)` or `jd.Initialize(a, b, a->GetWorldCenter())`
+    // right after CreateBody neither creates the device batch nor freezes the scene.
+    struct Shadow {
+        float p[2] = {0.0f, 0.0f}, angle = 0.0f, v[2] = {0.0f, 0.0f}, w = 0.0f;
+        bool awake = true;
+        bool exact = true;      // false after an edit whose effect needs the device (impulses): getters then build the batch
+        bool destroyed = false;
+        int32_t fixtures = 0;       // fixtures given to this body so far
+        int32_t massFixtures = -1;  // fixture count the cached local centre was computed for
+        float localCenter[2] = {0.0f, 0.0f};
+    };
+    mutable Shadow m_shadow;
     b2World* m_world = nullptr;
     int32_t m_index = 0;
     b2BodyType m_type = b2BodyType::STATIC_BODY;
@@ -415,7 +429,7 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
-    // b2World::CreateJoint (b2World.cpp:211-270) for all eleven joint types; nullptr once the world is locked (after the first Step)
+    // b2World::CreateJoint (b2World.cpp:211-270) for all eleven joint types; throws once the batch is built (first Step)
     b2Joint* CreateJoint(const b2JointDef* def);
     // b2World::DestroyBody (b2World.cpp:124-203): queued like the b2Body edits; the body's joints, contacts and proxies go
     // with it on the device.  The b2Body object stays allocated (its index is reserved) but must not be used again.
@@ -506,7 +520,16 @@ public:
         m_stateValid = false;
         if (m_listener) DispatchEvents();
     }
-    int32_t GetMaxBodies() { Build(); return m_maxBodies; }
+    int32_t GetMaxBodies() { BuildEarly(); return m_maxBodies; }
+    // Which bodies StepIO carries and how (b2gpu_batch_io_select): `forceBodies` / `poseBodies` are creation indices
+    // (b2Body::GetIndex(), the same in every world; an empty vector = none, nullptr = every body slot); xya = true reads
+    // GetPosition + GetAngle (3 floats per body) instead of GetTransform (4).
+    void SelectIO(const std::vector<int32_t>* forceBodies, const std::vector<int32_t>* poseBodies, bool xya) {
+        BuildEarly();
+        Check(b2gpu_batch_io_select(m_handle, forceBodies ? forceBodies->data() : nullptr, forceBodies ? (int32_t)forceBodies->size() : -1,
+                                    poseBodies ? poseBodies->data() : nullptr, poseBodies ? (int32_t)poseBodies->size() : -1,
+                                    xya ? B2GPU_POSE_XYA : B2GPU_POSE_XF));
+    }
     // `steps` steps replayed from a CUDA graph (no listener dispatch in between).
     void StepN(float timeStep, int32_t velocityIterations, int32_t positionIterations, int32_t steps) {
         Build();
@@ -519,7 +542,7 @@ public:
     b2gpu_batch* GetHandle() const { return m_handle; }
     // OR of B2GPU_STATUS_* over all worlds (arena overflow is reported, never silent)
     int32_t GetStatus() {
-        Build();
+        BuildEarly();
         std::vector<int32_t> st(m_worlds.size());
         Check(b2gpu_batch_download_field(m_handle, B2GPU_F_STATUS, st.data(), 0, (int32_t)st.size()));
         int32_t acc = 0;
@@ -532,6 +555,23 @@ private:
     friend class b2Body;
     static void Check(int rc) {
         if (rc != B2GPU_OK) throw std::runtime_error(std::string("b2gpu: ") + b2gpu_last_error());
+    }
+    // Built before the first Step (an edit or getter that needs the device while the scene was open): the spawn arenas get
+    // default headroom so that CreateBody keeps working on the now running worlds.
+    void BuildEarly() {
+        if (m_handle) return;
+        if (m_headroom[0] == 0 && m_headroom[1] == 0 && m_headroom[2] == 0) {
+            int32_t nb = 0, nf = 0, np = 0, nv = 0;
+            for (auto& w : m_worlds) {
+                nb = std::max(nb, (int32_t)w->m_bodyDefs.size());
+                nf = std::max(nf, (int32_t)w->m_fixtureDefs.size());
+                np = std::max(np, w->m_proxyCount);
+                nv = std::max(nv, (int32_t)(w->m_vertices.size() / 2));
+            }
+            m_headroom[0] = nb / 2 + 16; m_headroom[1] = nf / 2 + 16; m_headroom[2] = np / 2 + 16;
+            m_headroom[3] = 64 * (nf / 2 + 16); m_headroom[4] = nv / 2 + 64;
+        }
+        Build();
     }
     void Build() {
         if (m_handle) return;
@@ -646,6 +686,7 @@ private:
     std::vector<float> m_xf, m_sweep, m_vel;
     std::vector<b2gpu_body_command> m_commands;
     int32_t m_headroom[5] = {0, 0, 0, 0, 0};
+    bool m_destroyedWhileOpen = false;  // DestroyBody before the first Step (see b2World::CreateBody)
     // bodies created after the first Step, not yet on the device (only commands OR spawns are pending at any time, so
     // that the device sees creations and edits in call order)
     std::vector<b2gpu_spawn> m_spawns;
@@ -677,6 +718,9 @@ inline bool b2World::IsLocked() const { return m_batch->IsBuilt(); }
 inline int32_t b2World::GetBodyCount() const { return (int32_t)(m_owned ? m_owned->World(0) : *this).m_bodies.size(); }
 inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
     b2World& w = B2_SELF;
+    // A body was destroyed while the scene was still open: what is created after it must see the freed proxy ids
+    // (b2DynamicTree's LIFO free list), so the batch is built now and this body takes the running-world path.
+    if (!w.m_batch->IsBuilt() && w.m_batch->m_destroyedWhileOpen) w.m_batch->BuildEarly();
     const bool running = w.m_batch->IsBuilt();  // the world has been stepped: the body goes to the device at the next flush
     b2g_body_def d;
     std::memset(&d, 0, sizeof(d));
@@ -697,6 +741,9 @@ inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
     b->m_index = (int32_t)w.m_bodies.size();
     b->m_type = def->type;
     b->m_userData = def->userData;
+    b->m_shadow.p[0] = d.position[0]; b->m_shadow.p[1] = d.position[1]; b->m_shadow.angle = d.angle;
+    b->m_shadow.v[0] = d.linearVelocity[0]; b->m_shadow.v[1] = d.linearVelocity[1]; b->m_shadow.w = d.angularVelocity;
+    b->m_shadow.awake = def->awake;
     w.m_bodies.push_back(std::move(b));
     if (running) {
         b2WorldBatch* B = w.m_batch;
@@ -713,7 +760,10 @@ inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
 }
 inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
     b2World& w = B2_SELF;
-    if (w.m_batch->IsBuilt() || !def->bodyA || !def->bodyB) return nullptr;
+    if (!def->bodyA || !def->bodyB) return nullptr;
+    if (w.m_batch->IsBuilt())
+        throw std::runtime_error("b2World::CreateJoint on a running world is not supported: create joints before the first Step "
+                                 "(or before the first call that reads device state)");
     b2g_joint_def d;
     std::memset(&d, 0, sizeof(d));
     d.bodyA = def->bodyA->GetIndex();
@@ -809,7 +859,7 @@ inline int32_t b2World::GetProxyCount() const { return (m_owned ? m_owned->World
 inline int32_t b2World::GetContactCount() const {
     b2WorldBatch* batch = m_batch;
     const b2World& w = m_owned ? m_owned->World(0) : *this;
-    batch->Build();
+    if (!batch->IsBuilt()) return 0;  // contacts are created by the first Step (b2World::Step -> FindNewContacts)
     int32_t n = 0;
     b2WorldBatch::Check(b2gpu_batch_download_field(batch->m_handle, B2GPU_F_CONTACT_COUNT, &n, w.m_index, 1));
     return n;
@@ -852,14 +902,15 @@ inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
     int children = 1;
     if (fd.shapeType == B2G_SHAPE_CHAIN) children = fd.shapeKind == B2G_CHAIN_LOOP ? fd.vertexCount : fd.vertexCount - 1;
     w.m_proxyCount += children;
+    m_shadow.fixtures += 1;
+    if (def->density > 0.0f && m_shadow.w != 0.0f) m_shadow.exact = false;  // ResetMassData moves the velocity (b2Body.cpp:350)
     w.m_fixtures.push_back(std::move(f));
     return w.m_fixtures.back().get();
 }
 inline const b2Vec<float, 2>& b2Body::GetPosition() const {
     b2WorldBatch* B = m_world->m_batch;
     if (!B->IsBuilt()) {  // scene still open (joint defs' Initialize())
-        const b2g_body_def& d = m_world->m_bodyDefs[m_index];
-        m_tmp[0] = {{d.position[0], d.position[1]}};
+        m_tmp[0] = {{m_shadow.p[0], m_shadow.p[1]}};
         return m_tmp[0];
     }
     B->Refresh();
@@ -869,12 +920,31 @@ inline const b2Vec<float, 2>& b2Body::GetPosition() const {
 }
 inline float b2Body::GetAngle() const {
     b2WorldBatch* B = m_world->m_batch;
-    if (!B->IsBuilt()) return m_world->m_bodyDefs[m_index].angle;  // scene still open (joint defs' Initialize())
+    if (!B->IsBuilt()) return m_shadow.angle;  // scene still open (joint defs' Initialize())
     B->Refresh();
     return B->m_sweep[B->Slot(this) * 4 + 2];
 }
 inline const b2Vec<float, 2>& b2Body::GetWorldCenter() const {
     b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt()) {  // scene still open: position + R(angle) * localCenter, the centre from the fixtures recorded so far
+        b2World& w = *m_world;
+        if (m_shadow.massFixtures != (int32_t)w.m_fixtureDefs.size()) {
+            b2g_scene sc;
+            std::memset(&sc, 0, sizeof(sc));
+            sc.bodyCount = (int32_t)w.m_bodyDefs.size(); sc.bodies = w.m_bodyDefs.data();
+            sc.fixtureCount = (int32_t)w.m_fixtureDefs.size(); sc.fixtures = w.m_fixtureDefs.data();
+            sc.vertexCount = (int32_t)(w.m_vertices.size() / 2); sc.vertices = w.m_vertices.data();
+            float md[4];
+            b2WorldBatch::Check(b2gpu_host_body_mass_data(&sc, m_index, md));
+            m_shadow.localCenter[0] = md[2]; m_shadow.localCenter[1] = md[3];
+            m_shadow.massFixtures = sc.fixtureCount;
+        }
+        float sn, cs;
+        b2WorldBatch::Check(b2gpu_host_sincosf(&m_shadow.angle, &sn, &cs, 1));  // b2Rot::Set as the library evaluates it
+        const float lx = m_shadow.localCenter[0], ly = m_shadow.localCenter[1];
+        m_tmp[1] = {{(cs * lx - sn * ly) + m_shadow.p[0], (sn * lx + cs * ly) + m_shadow.p[1]}};
+        return m_tmp[1];
+    }
     B->Refresh();
     const float* s = &B->m_sweep[B->Slot(this) * 4];
     m_tmp[1] = {{s[0], s[1]}};
@@ -882,6 +952,11 @@ inline const b2Vec<float, 2>& b2Body::GetWorldCenter() const {
 }
 inline const b2Vec<float, 2>& b2Body::GetLinearVelocity() const {
     b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt() && m_shadow.exact) {
+        m_tmp[2] = {{m_shadow.v[0], m_shadow.v[1]}};
+        return m_tmp[2];
+    }
+    if (!B->IsBuilt()) B->BuildEarly();
     B->Refresh();
     const float* v = &B->m_vel[B->Slot(this) * 4];
     m_tmp[2] = {{v[0], v[1]}};
@@ -889,11 +964,14 @@ inline const b2Vec<float, 2>& b2Body::GetLinearVelocity() const {
 }
 inline float b2Body::GetAngularVelocity() const {
     b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt() && m_shadow.exact) return m_shadow.w;
+    if (!B->IsBuilt()) B->BuildEarly();
     B->Refresh();
     return B->m_vel[B->Slot(this) * 4 + 2];
 }
 inline bool b2Body::IsAwake() const {
     b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt()) return m_shadow.awake;
     B->Refresh();
     return (B->m_bodyFlags[B->Slot(this)] & 8) != 0;
 }
@@ -902,8 +980,7 @@ inline b2Vec<float, 2> b2Body::GetLocalPoint(const b2Vec<float, 2>& p) const {
     float px, py, qs, qc;
     b2WorldBatch* B = m_world->m_batch;
     if (!B->IsBuilt()) {
-        const b2g_body_def& d = m_world->m_bodyDefs[m_index];
-        px = d.position[0]; py = d.position[1]; qs = std::sin(d.angle); qc = std::cos(d.angle);
+        px = m_shadow.p[0]; py = m_shadow.p[1]; qs = std::sin(m_shadow.angle); qc = std::cos(m_shadow.angle);
     } else {
         B->Refresh();
         const float* x = &B->m_xf[B->Slot(this) * 4];
@@ -916,8 +993,7 @@ inline b2Vec<float, 2> b2Body::GetLocalVector(const b2Vec<float, 2>& v) const {
     float qs, qc;
     b2WorldBatch* B = m_world->m_batch;
     if (!B->IsBuilt()) {
-        const b2g_body_def& d = m_world->m_bodyDefs[m_index];
-        qs = std::sin(d.angle); qc = std::cos(d.angle);
+        qs = std::sin(m_shadow.angle); qc = std::cos(m_shadow.angle);
     } else {
         B->Refresh();
         const float* x = &B->m_xf[B->Slot(this) * 4];
@@ -982,15 +1058,77 @@ inline void b2DistanceJointDef::Initialize(b2Body* b1, b2Body* b2, const b2Vec<f
 }
 
 inline void b2WorldBatch::Queue(const b2Body* b, int32_t op, bool wake, float vx, float vy, float px, float py) {
-    Build();
-    FlushSpawns();  // a body created earlier must exist before an edit that follows it
+    if (m_handle) FlushSpawns();  // a body created earlier must exist before an edit that follows it
     b2gpu_body_command c;
     c.world = b->m_world->m_index;
     c.body = b->m_index;
     c.op = op;
     c.wake = wake ? 1 : 0;
     c.v[0] = vx; c.v[1] = vy; c.p[0] = px; c.p[1] = py;
-    m_commands.push_back(c);
+    if (m_handle) {
+        m_commands.push_back(c);
+        return;
+    }
+    // Scene still open.  A body without fixtures has no proxies and no mass data yet, so a velocity / transform / awake
+    // setter is exactly a change of its definition (and b2Body::ResetMassData of the fixtures that follow adjusts the
+    // velocity as the reference does, b2Body.cpp:350).  Everything else is queued and applied by the device, in call
+    // order, right after the batch is built.  (Not reproduced: a fixture added to a body AFTER a setter that itself
+    // followed an earlier fixture of that body.)
+    b2g_body_def& def = b->m_world->m_bodyDefs[b->m_index];
+    const bool bare = b->m_shadow.fixtures == 0;
+    bool folded = false;
+    if (bare && b->m_type != b2BodyType::STATIC_BODY && op == B2GPU_CMD_SET_LINEAR_VELOCITY) {
+        def.linearVelocity[0] = vx; def.linearVelocity[1] = vy;
+        if (vx * vx + vy * vy > 0.0f) def.flags |= B2G_BD_AWAKE;
+        folded = true;
+    } else if (bare && b->m_type != b2BodyType::STATIC_BODY && op == B2GPU_CMD_SET_ANGULAR_VELOCITY) {
+        def.angularVelocity = vx;
+        if (vx * vx > 0.0f) def.flags |= B2G_BD_AWAKE;
+        folded = true;
+    } else if (bare && op == B2GPU_CMD_SET_TRANSFORM) {
+        def.position[0] = vx; def.position[1] = vy; def.angle = px;
+        folded = true;
+    } else if (bare && op == B2GPU_CMD_SET_AWAKE) {
+        if (wake) def.flags |= B2G_BD_AWAKE;
+        else { def.flags &= ~B2G_BD_AWAKE; def.linearVelocity[0] = def.linearVelocity[1] = def.angularVelocity = 0.0f; }
+        folded = true;
+    } else if ((op == B2GPU_CMD_SET_LINEAR_VELOCITY || op == B2GPU_CMD_SET_ANGULAR_VELOCITY) && b->m_type == b2BodyType::STATIC_BODY) {
+        folded = true;  // b2Body::SetLinearVelocity on a static body does nothing
+    }
+    if (!folded) m_commands.push_back(c);
+    // keep the host shadow in step (b2Body.h:408-467, 634-653; b2Body.cpp:418-440)
+    b2Body::Shadow& s = b->m_shadow;
+    const bool isStatic = b->m_type == b2BodyType::STATIC_BODY;
+    switch (op) {
+        case B2GPU_CMD_SET_LINEAR_VELOCITY:
+            if (isStatic) break;
+            if (vx * vx + vy * vy > 0.0f) s.awake = true;
+            s.v[0] = vx; s.v[1] = vy;
+            break;
+        case B2GPU_CMD_SET_ANGULAR_VELOCITY:
+            if (isStatic) break;
+            if (vx * vx > 0.0f) s.awake = true;
+            s.w = vx;
+            break;
+        case B2GPU_CMD_SET_TRANSFORM:
+            s.p[0] = vx; s.p[1] = vy; s.angle = px;
+            break;
+        case B2GPU_CMD_SET_AWAKE:
+            if (wake) s.awake = true;
+            else { s.awake = false; s.v[0] = s.v[1] = s.w = 0.0f; }
+            break;
+        case B2GPU_CMD_DESTROY_BODY:
+            s.destroyed = true;
+            m_destroyedWhileOpen = true;
+            break;
+        case B2GPU_CMD_APPLY_LINEAR_IMPULSE:
+        case B2GPU_CMD_APPLY_ANGULAR_IMPULSE:
+            s.exact = false;  // the new velocity needs the body's mass data: velocity getters build the batch
+            break;
+        default:  // forces, torques, the mouse target: no getter of the mirror shows them before the step
+            if (wake && !isStatic) s.awake = true;
+            break;
+    }
 }
 inline void b2Body::SetMouseTarget(const b2Vec<float, 2>& target) {
     m_world->m_batch->Queue(this, B2GPU_CMD_MOUSE_SET_TARGET, true, target[0], target[1], 0.0f, 0.0f);

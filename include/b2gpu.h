@@ -204,6 +204,19 @@ int b2gpu_batch_read_transforms(b2gpu_batch* batch, float* out);
 int b2gpu_batch_step_io(b2gpu_batch* batch, const float* forces, float dt, int32_t velIters, int32_t posIters,
                         float* transforms);
 
+/* Which bodies the dense per-step I/O above carries, and in which format — so that only what the caller controls and
+ * observes crosses the bus (e.g. not the static ground, three floats per pose instead of four).
+ *   forceBodies[forceCount]: body indices, the same in every world; `forces` of apply_forces / step_io then is
+ *       forces[(world * forceCount + k) * 3] for body forceBodies[k].  forceCount -1: every body slot (the default), 0: none.
+ *   poseBodies[poseCount]: likewise for `out` / `transforms`: out[(world * poseCount + k) * F].
+ *   poseFormat: B2GPU_POSE_XF   p.x p.y q.s q.c (b2Body::GetTransform, F = 4, the default)
+ *               B2GPU_POSE_XYA  p.x p.y angle   (b2Body::GetPosition + GetAngle, F = 3; Box2D/Dynamics/b2Body.h:500-533)
+ * Takes effect for the following calls; synchronises the batch's stream. */
+#define B2GPU_POSE_XF 0
+#define B2GPU_POSE_XYA 1
+int b2gpu_batch_io_select(b2gpu_batch* batch, const int32_t* forceBodies, int32_t forceCount, const int32_t* poseBodies,
+                          int32_t poseCount, int32_t poseFormat);
+
 /* Applies `count` body commands between two steps.  Commands of one world are applied in array order (the order
  * the reference's user would have made the calls in); different worlds are independent and run in parallel.
  * The array may be in any world order (it is grouped by world on the host, stably).  A command naming a body
@@ -327,6 +340,12 @@ int b2gpu_batch_spawn_records(b2gpu_batch* batch, const uint32_t* words, const i
  * (Box2D/Collision/Shapes/b2PolygonShape.cpp:32-245, 354-437).  out: 8 vertices, 8 normals, centroid, then
  * mass, center.xy, I (38 floats); returns the vertex count. */
 int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, float* out);
+
+/* b2Body::GetMass / GetInertia-about-the-centre / GetLocalCenter of one body of a scene description, i.e.
+ * b2Body::ResetMassData (Box2D/Dynamics/b2Body.cpp:283-352) over the fixtures recorded so far.  out: mass, I, center.x,
+ * center.y (static and kinematic bodies: zeros).  Host code, no device: the C++ mirror answers b2Body::GetWorldCenter
+ * with it while a scene is still being recorded. */
+int b2gpu_host_body_mass_data(const b2g_scene* scene, int32_t body, float* out);
 
 /* b2Rot::Set(angle) (Box2D/Common/b2Math.h:302-311) as the host layer evaluates it: the library's own
  * sinf / cosf, bit-identical to the libm the reference links (tests/test_sincos.py).  Host code, no device. */

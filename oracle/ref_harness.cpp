@@ -706,4 +706,60 @@ double ref_bench_run(const b2g_scene* scenes, int sceneCount, int worldsPerThrea
     return worst;
 }
 
+// The same with the timed region repeated: `repeats` back-to-back blocks of `steps` steps, all threads released together
+// at the start of each block; seconds[r] = the slowest thread's time for block r.  (bench.py --impl reference reports the
+// median and the spread, so that a ratio against it carries its own error bar.)
+double ref_bench_run_repeats(const b2g_scene* scenes, int sceneCount, int worldsPerThread, int threads, int steps,
+                             int warmupSteps, float dt, int velIters, int posIters, int repeats, double* seconds) {
+    {
+        RefWorld* rw = build_world(&scenes[0]);
+        rw->world->Step(dt, velIters, posIters);
+        delete rw->world;
+        delete rw;
+    }
+    if (repeats < 1) repeats = 1;
+    std::atomic<int> arrived(0), released(0);
+    std::vector<double> elapsed((size_t)threads * repeats, 0.0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) {
+        pool.emplace_back([&, t]() {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            CPU_SET(t % (int)std::thread::hardware_concurrency(), &set);
+            pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+            std::vector<RefWorld*> worlds;
+            for (int k = 0; k < worldsPerThread; ++k)
+                worlds.push_back(build_world(&scenes[(t * worldsPerThread + k) % sceneCount]));
+            for (int s = 0; s < warmupSteps; ++s)
+                for (RefWorld* rw : worlds) rw->world->Step(dt, velIters, posIters);
+            for (int r = 0; r < repeats; ++r) {
+                arrived.fetch_add(1);
+                while (released.load() <= r) std::this_thread::yield();
+                auto t0 = std::chrono::steady_clock::now();
+                for (int s = 0; s < steps; ++s)
+                    for (RefWorld* rw : worlds) rw->world->Step(dt, velIters, posIters);
+                auto t1 = std::chrono::steady_clock::now();
+                elapsed[(size_t)t * repeats + r] = std::chrono::duration<double>(t1 - t0).count();
+            }
+            for (RefWorld* rw : worlds) {
+                delete rw->world;
+                delete rw;
+            }
+        });
+    }
+    for (int r = 0; r < repeats; ++r) {
+        while (arrived.load() < threads * (r + 1)) std::this_thread::yield();
+        released.store(r + 1);
+    }
+    for (auto& th : pool) th.join();
+    double best = 0.0;
+    for (int r = 0; r < repeats; ++r) {
+        double worst = 0.0;
+        for (int t = 0; t < threads; ++t) worst = elapsed[(size_t)t * repeats + r] > worst ? elapsed[(size_t)t * repeats + r] : worst;
+        if (seconds) seconds[r] = worst;
+        if (r == 0 || worst < best) best = worst;
+    }
+    return best;
+}
+
 }  // extern "C"

@@ -78,6 +78,9 @@ def lib(kind="ref"):
             L.ref_bench_run.restype = C.c_double
             L.ref_bench_run.argtypes = [C.POINTER(CScene), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                         C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+            L.ref_bench_run_repeats.restype = C.c_double
+            L.ref_bench_run_repeats.argtypes = [C.POINTER(CScene), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                                C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         _libs[kind] = L
     return _libs[kind]
 
@@ -226,6 +229,15 @@ def bench_run(scenes, worlds_per_thread, threads, steps, warmup, dt, vel_iters, 
     sec = lib().ref_bench_run(arr, len(scenes), worlds_per_thread, threads, steps, warmup, dt, vel_iters,
                               pos_iters, C.byref(chk))
     return sec, chk.value
+
+
+def bench_run_repeats(scenes, worlds_per_thread, threads, steps, warmup, dt, vel_iters, pos_iters, repeats=3):
+    """All-core CPU baseline, the timed block of `steps` steps repeated: returns the list of seconds per block."""
+    arr = scene_array(scenes)
+    sec = (C.c_double * repeats)()
+    lib().ref_bench_run_repeats(arr, len(scenes), worlds_per_thread, threads, steps, warmup, dt, vel_iters, pos_iters,
+                                repeats, sec)
+    return list(sec)
 
 
 # ---- hashes of SURVEY.md Appendix D -------------------------------------------------------------

@@ -29,6 +29,37 @@ def exe():
     return EXE
 
 
+@pytest.fixture(scope="module")
+def edits_exe():
+    lib = os.path.join(ROOT, "box2dpp_b200")
+    if not os.path.exists(os.path.join(lib, "libb2gpu.so")):
+        pytest.skip("libb2gpu.so not built")
+    out = os.path.join(ROOT, "tests", "cpp", "scene_open_edits")
+    cmd = ["g++", "-std=c++14", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "box2dpp_b200", "include"), os.path.join(ROOT, "tests", "cpp", "scene_open_edits.cpp"),
+           "-o", out, "-L" + lib, "-lb2gpu", "-Wl,-rpath," + lib]
+    subprocess.check_call(cmd)
+    return out
+
+
+def test_edits_and_getters_before_the_first_step_do_not_freeze_the_scene(edits_exe):
+    """b2Body setters / getters right after CreateBody and joint defs initialised from GetWorldCenter() (the reference's
+    usual construction patterns) are served on the host: no device batch, the scene stays open.  Needs no GPU."""
+    r = subprocess.run([edits_exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "no device batch created" in r.stdout
+
+
+@pytest.mark.gpu
+def test_setters_before_the_first_step_equal_the_definition(edits_exe):
+    """SetLinearVelocity / SetAngularVelocity after CreateBody == the same values in the b2BodyDef, bit for bit after 60 steps;
+    CreateJoint on the running world throws instead of returning nullptr."""
+    r = subprocess.run([edits_exe, "step"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = r.stdout.strip().splitlines()
+    assert len(rows) == 2 and rows[0] == rows[1], rows
+
+
 def _has_gpu():
     try:
         import torch

@@ -442,6 +442,40 @@ def test_step_io_equals_separate_calls():
             os.environ.pop("B2GPU_IO_GROUPS", None)
 
 
+def test_step_io_with_selected_bodies_and_poses():
+    """b2gpu_batch_io_select: forces for a subset of the bodies and (x, y, angle) poses of the dynamic ones only give the
+    same worlds as the dense calls with zeros elsewhere, and the poses are the transforms' positions + the sweeps' angles."""
+    scenes = [S.pyramid(5, flags=NOCCD, jitter_seed=w) for w in range(70)]
+    dense, lean = WorldBatch(scenes), WorldBatch(scenes)
+    nb = dense.max_bodies
+    pushed = [1, 4, 9, nb - 1]
+    dynamic = list(range(1, nb))  # body 0 is the static ground
+    lean.io_select(force_bodies=pushed, pose_bodies=dynamic, xya=True)
+    rs = np.random.RandomState(5)
+    for step in range(40):
+        f_lean = rs.uniform(-40.0, 40.0, (len(scenes), len(pushed), 3)).astype(np.float32)
+        if step % 3 == 0:
+            f_lean[rs.randint(0, len(scenes), 20)] = 0.0  # worlds without any force this step
+        f_dense = np.zeros((len(scenes), nb, 3), np.float32)
+        f_dense[:, pushed, :] = f_lean
+        xf = dense.step_io(f_dense, 1.0 / 60.0, 8, 3)
+        pose = lean.step_io(f_lean, 1.0 / 60.0, 8, 3)
+        assert pose.shape == (len(scenes), nb - 1, 3)
+        assert (pose[:, :, :2].view(np.uint32) == xf[:, 1:, :2].view(np.uint32)).all(), f"step {step}: positions"
+        if step % 10 == 9:
+            for w in (0, 33, 69):
+                assert (dense.bodies(w).view(np.uint32) == lean.bodies(w).view(np.uint32)).all(), f"step {step} world {w}"
+                assert (pose[w, :, 2].view(np.uint32) == lean.bodies(w)[1:, 6].view(np.uint32)).all(), f"step {step}: angles"
+    # the separate calls honour the selection too
+    lean.apply_forces(np.zeros((len(scenes), len(pushed), 3), np.float32))
+    assert lean.read_transforms().shape == (len(scenes), nb - 1, 3)
+    # back to every body, four floats
+    lean.io_select()
+    assert lean.step_io(None, 1.0 / 60.0, 8, 3).shape == (len(scenes), nb, 4)
+    dense.close()
+    lean.close()
+
+
 def test_full_size_batch_properties(oracles):
     """BASELINE configs[2] at full size: 16,384 pyramid-20 worlds on one B200.  Size-independent properties:
     (a) identical worlds stay bit-identical to each other and to the oracle's single world;

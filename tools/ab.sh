@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for V in "$@"; do
   LIB=box2dpp_b200/libb2gpu_${V}.so
   [ "$V" = "base" ] && LIB=box2dpp_b200/libb2gpu.so
-  B2GPU_LIB=$LIB python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 5 > gpurun_out/${TAG}_${V}.json 2> gpurun_out/${TAG}_${V}.err
+  B2GPU_LIB=$LIB timeout 150 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 5 > gpurun_out/${TAG}_${V}.json 2> gpurun_out/${TAG}_${V}.err
   python - "$V" gpurun_out/${TAG}_${V}.json <<'PY'
 import json,sys
 try:
