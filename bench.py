@@ -240,7 +240,11 @@ def main():
 
     from box2dpp_b200.batch import F_CONTACT_COUNT, F_ISLAND_CONTACT_END, F_ISLAND_COUNT, WorldBatch
 
-    numa = pin_to_gpu_numa(local_rank)
+    # nvidia-smi counts physical GPUs; under CUDA_VISIBLE_DEVICES (tools/sweep_multi.py runs several jobs side by side on
+    # disjoint GPU sets) CUDA device `local_rank` is another one
+    visible = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+    smi_index = int(visible[local_rank]) if local_rank < len(visible) else local_rank
+    numa = pin_to_gpu_numa(smi_index)
     dist = None
     if world_size > 1:
         import torch
@@ -268,7 +272,7 @@ def main():
     batch.step_n(DT, 8, 3, preroll)
     batch.sync()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(smi_index)
     sampler.start()
     batch.step_n(DT, 8, 3, warmup)
     batch.sync()

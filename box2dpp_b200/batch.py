@@ -99,7 +99,8 @@ def lib():
         L.b2gpu_batch_apply_forces.argtypes = [vp, vp]
         L.b2gpu_batch_read_transforms.argtypes = [vp, vp]
         L.b2gpu_batch_step_io.argtypes = [vp, vp, C.c_float, i32, i32, vp]
-        L.b2gpu_batch_io_select.argtypes = [vp, vp, i32, vp, i32, i32]
+        if hasattr(L, "b2gpu_batch_io_select"):  # absent from older diagnostic builds (B2GPU_LIB)
+            L.b2gpu_batch_io_select.argtypes = [vp, vp, i32, vp, i32, i32]
         L.b2gpu_batch_body_commands.argtypes = [vp, vp, C.c_int64]
         L.b2gpu_batch_read_body_state.argtypes = [vp, vp]
         L.b2gpu_batch_query_aabb.argtypes = [vp, vp, C.c_int64, i32, vp, vp]

@@ -39,14 +39,36 @@ constexpr int kRecStages = B2G_REC_STAGES;   // TMA ring depth of the position k
 #endif
 constexpr int kVelStages = B2G_VEL_STAGES;   // TMA ring depth of the velocity kernel
 #ifndef B2G_VEL_PREFETCH
-#define B2G_VEL_PREFETCH 24
+#define B2G_VEL_PREFETCH 0
 #endif
-constexpr int kVelPipelineMin = 32;              // island contacts per world from which the velocity kernel pipelines
-constexpr int kVelPrefetch = B2G_VEL_PREFETCH;  // records pulled into L2 ahead of the velocity ring (0 = off)
+#ifndef B2G_VEL_PIPELINE_MIN
+#define B2G_VEL_PIPELINE_MIN 32
+#endif
+constexpr int kVelPipelineMin = B2G_VEL_PIPELINE_MIN;              // island contacts per world from which the velocity kernel pipelines
+// Records pulled into L2 ahead of the rings' own loads (cp.async.bulk.prefetch.L2).  OFF: it bought nothing once the ring
+// released its stages early (velocity kernel 1.796 ms without, 1.786 ms with, profiles/r2h_*), and with it compiled in two
+// runs of the same 16,384-world batch disagreed in a few whole tiles per 120 steps when two world groups ran side by side
+// (tools/diag_determinism.py; never without it).  Kept as a build knob for that experiment only.
+constexpr int kVelPrefetch = B2G_VEL_PREFETCH;
 #ifndef B2G_POS_PREFETCH
-#define B2G_POS_PREFETCH 16
+#define B2G_POS_PREFETCH 0
 #endif
 constexpr int kPosPrefetch = B2G_POS_PREFETCH;
+#ifndef B2G_POS_FORCE_SIMPLE
+#define B2G_POS_FORCE_SIMPLE 0
+#endif
+// A/B knob: give a ring stage back to the producer as soon as its record has been LOADED (1) instead of once it has
+// been SOLVED (0, default).  Early release is not safe here: mbarrier.arrive is not held back by shared-memory loads that
+// are still in flight, and nothing else is either when the loaded registers are first used a whole solve later.  With
+// another kernel hammering the same SM's load / store unit (two world groups side by side) a record's loads now and then
+// came back after the producer had refilled the stage: runs of 8 lanes (one 128-byte wavefront of a float4 row) holding
+// the record eight places further on, i.e. two runs of one batch differing in a few tiles per thousand steps
+// (tools/diag_determinism.py, profiles/r2_determinism.md).  Released after the solve, every loaded register has been
+// consumed by the arithmetic whose results the preceding st.shared wrote, so the loads have returned by construction;
+// the two stages of look-ahead this gives up cost nothing measurable (velocity kernel 1.733 -> 1.744 ms).
+#ifndef B2G_EARLY_RELEASE
+#define B2G_EARLY_RELEASE 0
+#endif
 constexpr int kImpStages = 8;   // cp.async ring depth for accumulated impulses
 constexpr int kStageBytes = kVelRec * 16 * kTile;  // 3584
 constexpr int kPrepWarps = 8;
@@ -105,7 +127,7 @@ __device__ __forceinline__ void CpAsyncWait() {
 // and slot % 4 is the scheduler; so the SAME warp index in both CTAs never shares a scheduler, while warp w of one and
 // w - 1 of the other do.  (The three-warp CTAs of round 1 had their consumers on one scheduler: 2.38 ms instead of
 // 1.78 ms for the velocity kernel.)  Hence: four warps, fixed roles, consumer = warp 0 everywhere.
-enum SeqRole { kRoleConsumer = 0, kRoleIdle = 1, kRoleProducer = 2, kRoleWatcher = 3 };
+enum SeqRole { kRoleConsumer = 0, kRoleIdle = 1, kRoleProducer = 2, kRoleIdle2 = 3 };
 __device__ __forceinline__ int SequentialRole(int warp) { return warp; }
 
 __device__ __forceinline__ int PackBodies(int bodyA, int bodyB, int pointCount) { return bodyA | (bodyB << 15) | (pointCount << 30); }
@@ -359,7 +381,7 @@ constexpr int kVelStageBytes = (kVelRec + 1) * 16 * kTile;  // record + impulses
 
 __device__ __forceinline__ uint32_t MbarTryWait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    // suspend-time hint: the producer / watcher warps sleep in hardware until the phase completes instead of
+    // suspend-time hint: the producer warp sleeps in hardware until the phase completes instead of
     // spinning next to the consumer warp
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok)
@@ -416,13 +438,26 @@ __device__ __forceinline__ uint32_t Keep(uint32_t v) { asm volatile("" : "+r"(v)
 __device__ __forceinline__ int Keep(int v) { asm volatile("" : "+r"(v)); return v; }
 template <class P>
 __device__ __forceinline__ P* Keep(P* v) { asm volatile("" : "+l"(v)); return v; }
-__device__ __forceinline__ uint32_t LdsAcquire(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
+// How the consumer learns that a ring stage has landed.  The stage is written by the ASYNC proxy (a TMA bulk copy, and in
+// the velocity kernel 32 cp.async's that arrive on the same mbarrier); only a thread that itself observes the mbarrier's
+// phase complete is guaranteed to see those bytes.  (Round 2's first build had a watcher lane observe the barriers and
+// publish a count in a shared word the consumer polled: two runs of one 16,384-world batch then disagreed in a few tiles
+// per thousand steps — the consumer now and then read a stage whose bytes were not all visible to it yet,
+// tools/diag_determinism.py.)  So every consumer lane tests the barrier itself, but off the chain: the NON-blocking test
+// for record k + 1 is issued while record k is being fetched, and its predicate is first looked at a whole contact solve
+// later, when the 50 - 90 cycles an mbarrier test takes have long passed; only if that test said "not yet" does the warp
+// fall into the blocking wait.  Stage s = k & (depth - 1) is reused every `depth` records and the look-ahead is shorter
+// than that, so the parity of record k's use, (k / depth) & 1, cannot alias an older phase.
+__device__ __forceinline__ uint32_t MbarTestA(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok;
 }
-__device__ __forceinline__ void StsRelease(uint32_t a, uint32_t v) {
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+__device__ __forceinline__ void MbarSpinA(uint32_t bar, uint32_t parity) {
+    while (!MbarTryWaitA(bar, parity)) {}
 }
 __device__ __forceinline__ void CpAsync16CgA(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -616,7 +651,6 @@ __device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, BodyV
 
 __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint32_t sReady;  // records whose data has landed in the ring (published by the watcher warp)
     const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const int n = A.solveCount[ws];
@@ -626,18 +660,18 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
     const int anyWarm = __any_sync(0xffffffffu, warm) ? 1 : 0;
     const int total = nMax * (velIters + anyWarm);
     // Two ring protocols.
-    //  * pipelined (nMax >= kVelPipelineMin, 8 stages): a stage is released as soon as the consumer has its record in
-    //    registers, two steps before the record is solved, so all 8 stages cover the latency of the ring's loads; the
-    //    consumer writes a contact's updated impulses straight to impRec, and the producer fetches them again for the
-    //    next pass a whole pass (>= kVelPipelineMin - 10 steps, and at least one release / acquire pair on an `empty`
-    //    barrier) later.
+    //  * pipelined (nMax >= kVelPipelineMin, 8 stages): a record is loaded into registers two steps before it is solved
+    //    and its stage is released once it HAS been solved (B2G_EARLY_RELEASE explains why not sooner); the consumer
+    //    writes a contact's updated impulses straight to impRec, and the producer fetches them again for the next pass
+    //    a whole pass (>= kVelPipelineMin - 8 steps, and at least one release / acquire pair on an `empty` barrier)
+    //    later.
     //  * small worlds: one record at a time; the updated impulses ride back in the ring stage and the producer lane that
     //    fetched them writes them to impRec when the stage is recycled — store and re-fetch of one contact are issued by
     //    the same thread, in that order.
     // The depth is a power of two (stage of record k = k & (depth - 1)).
     const bool pipelined = nMax >= kVelPipelineMin;
-    int depth = 1;
-    while (depth * 2 <= nMax - 1 && depth * 2 <= kVelStages) depth *= 2;
+    int depth = 1, depthLog = 0;
+    while (depth * 2 <= nMax - 1 && depth * 2 <= kVelStages) { depth *= 2; ++depthLog; }
 
     const uint32_t bodyBytes = (uint32_t)A.NB * 3 * kTile * 4;
     unsigned char* stages = smem + SolveTableBytes(A.NB);
@@ -653,28 +687,12 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
             MbarInit(&empty[s], 1);   // one consumer lane, on behalf of the (converged) warp
         }
         MbarInit(bodyBar, 1);
-        sReady = 0;
         FenceBarrierInit();
     }
     __syncthreads();
 
     const int role = SequentialRole(warp);
-    if (role == kRoleIdle) return;
-    if (role == kRoleWatcher) {
-        // ================= watcher: waits for every record in order and publishes the count =================
-        // (mbarrier.try_wait returns a predicate that must be consumed at once, ~50-90 cycles; the consumer
-        // polls this word with an ordinary load instead, and only when its cached copy runs out)
-        if (lane != 0) return;
-        const uint32_t ready = SmemAddr(&sReady);
-        int s = 0;
-        uint32_t phase = 0;
-        for (int r = 0; r < total; ++r) {
-            while (!MbarTryWait(&full[s], phase)) {}
-            StsRelease(ready, r + 1 < total ? (uint32_t)r + 1u : 0x7fffffffu);  // after the last one: "everything"
-            if (++s == depth) { s = 0; phase ^= 1u; }
-        }
-        return;
-    }
+    if (role != kRoleConsumer && role != kRoleProducer) return;
     if (role == kRoleProducer) {
         // ================= producer =================
         if (lane == 0) {
@@ -686,16 +704,11 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
         int i = 0, s = 0;
         int wi = 0, wpass = 0;  // record that previously occupied stage s (write-back cursor)
         uint32_t phase = 1;     // parity of the consumer's release that frees stage s for its next use
-        // The ring holds what shared memory leaves room for (a few records per tile), far less than HBM latency x
-        // bandwidth needs in flight; so the records are pulled into L2 kVelPrefetch records ahead of the ring's own loads,
-        // which then complete with L2 latency.
+        // (experiment, off by default: records pulled into L2 kVelPrefetch records ahead of the ring's own loads)
         int pi = 0;  // record index of the next prefetch, pf records issued so far
         int pf = 0;
         auto prefetch = [&]() {
-            if (lane == 0 && pf < total) {
-                TmaPrefetchL2(src + (size_t)pi * (kVelRec * 16 * kTile), kVelRec * 16 * kTile);
-                TmaPrefetchL2(gImp - lane + (size_t)pi * kTile, 16 * kTile);
-            }
+            if (lane == 0 && pf < total && kVelPrefetch > 0) TmaPrefetchL2(src + (size_t)pi * (kVelRec * 16 * kTile), kVelRec * 16 * kTile);
             ++pf;
             if (++pi == nMax) pi = 0;
         };
@@ -723,6 +736,8 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
             }
             if (++s == depth) { s = 0; phase ^= 1u; }
         }
+        // pipelined: the loop ends with the last records' impulse copies still in flight; a thread must not exit on them
+        asm volatile("cp.async.wait_all;" ::: "memory");
         return;
     }
 
@@ -735,7 +750,7 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
     //    touch are forwarded from registers at the end (ForwardBodyVals) instead of going through a store and a reload;
     //  * lanes without a contact at the current index solve a scratch row instead of branching around the solve, and
     //    the solve itself is straight-line for every point count (SolveVelocityContact): a step is one basic block;
-    //  * the count of landed records is cached; the shared word is only read when the cache runs out.
+    //  * whether the next record has landed is asked one step ahead (MbarTestA), so the answer costs the chain nothing.
     while (!MbarTryWait(bodyBar, 0)) {}
     // Loop invariants are pinned in registers (Keep): left alone, the compiler re-derives them from %tid / %ctaid /
     // the shared-window base inside the loop, which costs more than the solve's own address arithmetic.
@@ -743,33 +758,34 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
     const uint32_t scratch = Keep(T.at(A.NB));  // row NB of the table: this lane's scratch row
     const uint32_t stage0 = Keep(SmemAddr(stages) + (uint32_t)lane * 16);
     const uint32_t empty0 = Keep(SmemAddr(empty));
-    const uint32_t ready = Keep(SmemAddr(&sReady));
+    const uint32_t full0 = Keep(SmemAddr(full));
     const uint32_t mask = Keep((uint32_t)depth - 1u);
+    const uint32_t depthShift = Keep((uint32_t)depthLog);
     const int warmRecords = Keep(anyWarm ? nMax : 0);
     const int nK = Keep(n), nMaxK = Keep(nMax), totalK = Keep(total);
 
     if (pipelined) {
         int iLoad = 0, seq = 0;  // seq: record being solved; records up to seq + 1 are in registers
-        uint32_t landed = 0;
-        auto waitLanded = [&](uint32_t need) {
-            while (landed < need) landed = LdsAcquire(ready);
-        };
         auto stageOf = [&](int k) { return stage0 + (((uint32_t)k & mask) << 12); };  // kVelStageBytes == 4096
         auto emptyOf = [&](int k) { return empty0 + (((uint32_t)k & mask) << 3); };
-        // record k (issued earlier) becomes usable, and its stage goes back to the producer
+        auto fullOf = [&](int k) { return full0 + (((uint32_t)k & mask) << 3); };
+        auto parityOf = [&](int k) { return ((uint32_t)k >> depthShift) & 1u; };
+        uint32_t landedNext;  // the test of record seq + 2's barrier, issued a step ago
+        // record k (issued earlier) becomes usable
         auto finish = [&](VelRecord& r, int k) {
             FinishVelRecord(r, k < totalK && iLoad < nK, T, scratch);
             r.index = iLoad;
             if (++iLoad == nMaxK) iLoad = 0;
             __syncwarp();
-            if (k < totalK && lane == 0) MbarArriveA(emptyOf(k));
+            if (B2G_EARLY_RELEASE && k < totalK && lane == 0) MbarArriveA(emptyOf(k));
         };
         // One chain step: `cur` (record seq) is solved on `bv`; meanwhile `fill` receives record seq + 2 (past the last
         // record: a stale stage, read and ignored) and the body values of `nxt` are read.
         auto step = [&](VelRecord& cur, const VelRecord& nxt, VelRecord& fill, BodyVals& bv, auto warmPass) {
             constexpr bool WARM = decltype(warmPass)::value;
-            if (landed < (uint32_t)seq + 3u) waitLanded((uint32_t)seq + 3u);  // record seq + 2 (the watcher ends on "all")
+            if (!landedNext && seq + 2 < totalK) MbarSpinA(fullOf(seq + 2), parityOf(seq + 2));
             IssueVelRecord(fill, stageOf(seq + 2));
+            landedNext = MbarTestA(fullOf(seq + 3), parityOf(seq + 3));  // past the last record: an answer nobody uses
             const BodyVals nextLoaded = LoadBodyVals(nxt.pA, nxt.pB);  // before this contact's stores: ForwardBodyVals
             if (WARM) {
                 if (warm) WarmStartContact(cur, bv);
@@ -780,14 +796,18 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
             StoreBodyVals(cur.pA, cur.pB, bv);
             bv = ForwardBodyVals(nextLoaded, bv, nxt.pA, nxt.pB, cur.pA, cur.pB);
             finish(fill, seq + 2);
+            // record seq is solved and its results are stored: its stage goes back to the producer (see B2G_EARLY_RELEASE)
+            if (!B2G_EARLY_RELEASE && lane == 0) MbarArriveA(emptyOf(seq));
             ++seq;
         };
         VelRecord r0, r1, r2;
-        waitLanded(2u);
+        MbarSpinA(fullOf(0), parityOf(0));
         IssueVelRecord(r0, stageOf(0));
         finish(r0, 0);
+        MbarSpinA(fullOf(1), parityOf(1));
         IssueVelRecord(r1, stageOf(1));
         finish(r1, 1);
+        landedNext = MbarTestA(fullOf(2), parityOf(2));
         BodyVals bv = LoadBodyVals(r0.pA, r0.pB);
         // warm-start pass, and whatever does not fill a group of three: one step at a time, registers rotated by moves
         auto single = [&](auto warmPass) {
@@ -806,7 +826,7 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
         int i = 0, cs = 0;
         for (int seq = 0; seq < total; ++seq) {
             const uint32_t st = stage0 + cs * kVelStageBytes;
-            while (LdsAcquire(ready) < (uint32_t)seq + 1u) {}
+            MbarSpinA(full0 + cs * 8, ((uint32_t)seq >> depthShift) & 1u);
             if (i < n) {
                 VelRecord r;
                 IssueVelRecord(r, st);
@@ -927,8 +947,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_solve_integrate(Arena A, fl
 // b2ContactSolver.cpp:614-744); each island stops as soon as one of its passes ends with
 // minSeparation >= -3 * b2_linearSlop.  Warp 0 (consumer) solves out of shared memory, lane 0 of warp 1
 // (producer) streams the position records of one pass through a TMA + mbarrier ring and then waits for the
-// consumer's verdict on whether another pass is needed, lane 0 of warp 2 (watcher) publishes how many records
-// have landed.  The consumer is built like k_solve_velocity's: three records in registers, the next contact's
+// consumer's verdict on whether another pass is needed.  The consumer is built like k_solve_velocity's: three records in registers, the next contact's
 // body values fetched during the solve and forwarded, lanes without work on a scratch row, a step is
 // straight-line code.
 // =================================================================================================
@@ -1043,7 +1062,6 @@ __device__ __noinline__ PosContactResult SolvePositionContactAnyAngle(float4 r0,
 __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int sContinue;
-    __shared__ uint32_t sReady;  // records that have landed in the ring, over all passes (published by the watcher)
     const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const int n = A.solveCount[ws];
@@ -1068,8 +1086,8 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     uint64_t* bodyBar = empty + kRecStages;
     uint64_t* passBar = bodyBar + 1;
     float* gPos = A.solvePos + (size_t)tile * A.NB * 3 * kTile;
-    int depth = 1;  // a power of two: stage of record k = k & (depth - 1), k counted over all passes
-    while (depth * 2 <= nMax && depth * 2 <= kRecStages) depth *= 2;
+    int depth = 1, depthLog = 0;  // a power of two: stage of record k = k & (depth - 1), k counted over all passes
+    while (depth * 2 <= nMax && depth * 2 <= kRecStages) { depth *= 2; ++depthLog; }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kRecStages; ++s) {
@@ -1078,13 +1096,12 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
         }
         MbarInit(bodyBar, 1);
         MbarInit(passBar, 32);
-        sReady = 0;
         FenceBarrierInit();
     }
     __syncthreads();
 
     const int role = SequentialRole(warp);
-    if (role == kRoleIdle) return;
+    if (role != kRoleConsumer && role != kRoleProducer) return;
     if (role == kRoleProducer) {
         // ================= producer (one lane) =================
         if (lane != 0) return;
@@ -1093,28 +1110,13 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(A.posRec + (size_t)tile * A.NC * kPosRec * kTile);
         int k = 0;  // records issued so far
         for (int pass = 0; pass < posIters; ++pass) {
-            for (int i = 0; i < kPosPrefetch && i < nMax; ++i) TmaPrefetchL2(src + (size_t)i * kPosStageBytes, kPosStageBytes);
+            for (int i = 0; i < kPosPrefetch && i < nMax; ++i) TmaPrefetchL2(src + (size_t)i * kPosStageBytes, kPosStageBytes);  // off
             for (int i = 0; i < nMax; ++i, ++k) {
-                if (i + kPosPrefetch < nMax) TmaPrefetchL2(src + (size_t)(i + kPosPrefetch) * kPosStageBytes, kPosStageBytes);
+                if (kPosPrefetch > 0 && i + kPosPrefetch < nMax) TmaPrefetchL2(src + (size_t)(i + kPosPrefetch) * kPosStageBytes, kPosStageBytes);
                 const int s = k & (depth - 1), use = k / depth;
                 if (use > 0) while (!MbarTryWait(&empty[s], (uint32_t)(use - 1) & 1u)) {}
                 MbarExpectTx(&full[s], kPosStageBytes);
                 TmaLoad1D(stages + (size_t)s * kPosStageBytes, src + (size_t)i * kPosStageBytes, kPosStageBytes, &full[s]);
-            }
-            while (!MbarTryWait(passBar, (uint32_t)pass & 1u)) {}
-            if (*(volatile int*)&sContinue == 0) break;
-        }
-        return;
-    }
-    if (role == kRoleWatcher) {
-        // ================= watcher (one lane): counts landed records =================
-        if (lane != 0) return;
-        const uint32_t ready = SmemAddr(&sReady);
-        int k = 0;
-        for (int pass = 0; pass < posIters; ++pass) {
-            for (int i = 0; i < nMax; ++i, ++k) {
-                while (!MbarTryWait(&full[k & (depth - 1)], (uint32_t)(k / depth) & 1u)) {}
-                StsRelease(ready, (uint32_t)k + 1u);
             }
             while (!MbarTryWait(passBar, (uint32_t)pass & 1u)) {}
             if (*(volatile int*)&sContinue == 0) break;
@@ -1143,21 +1145,21 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     const uint32_t scratch = Keep(T.at(A.NB));
     const uint32_t stage0 = Keep(SmemAddr(stages) + (uint32_t)lane * 16);
     const uint32_t empty0 = Keep(SmemAddr(empty));
-    const uint32_t ready = Keep(SmemAddr(&sReady));
+    const uint32_t full0 = Keep(SmemAddr(full));
     const uint32_t done0 = Keep(SmemAddr(sDone));
     const uint32_t mask = Keep((uint32_t)depth - 1u);
+    const uint32_t depthShift = Keep((uint32_t)depthLog);
     const int nK = Keep(n), nMaxK = Keep(nMax);
     StsF(scratch, 0.0f); StsF(scratch + 128, 0.0f); StsF(scratch + 256, 0.0f);  // angle 0: the fast sinf / cosf path
 
     auto runPasses = [&](auto circlesTag) {
         constexpr bool CIRCLES = decltype(circlesTag)::value;
-        uint32_t landed = 0;
         int base = 0;  // ring index of this pass's record 0
-        auto waitLanded = [&](uint32_t need) {
-            while (landed < need) landed = LdsAcquire(ready);
-        };
         auto stageOf = [&](int k) { return stage0 + ((uint32_t)k & mask) * kPosStageBytes; };
         auto emptyOf = [&](int k) { return empty0 + (((uint32_t)k & mask) << 3); };
+        auto fullOf = [&](int k) { return full0 + (((uint32_t)k & mask) << 3); };
+        auto parityOf = [&](int k) { return ((uint32_t)k >> depthShift) & 1u; };
+        uint32_t landedNext = 0;  // the test of record i + 2's barrier, issued a step ago
         auto doneBit = [&](int info) {  // converged bit of the island a record belongs to
             const uint32_t isl = (uint32_t)info >> 8;
             return ((LdsU(done0 + (isl >> 5) * (kTile * 4)) >> (isl & 31)) & 1u) != 0;
@@ -1165,23 +1167,21 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
         for (int pass = 0; pass < posIters; ++pass) {
             int i = 0;  // record being solved; records up to i + 1 are in registers
             float minSeparation = 0.0f;
-            const int limit = base + nMaxK;  // records of this pass end here
-            auto needFor = [&](int k) { return (uint32_t)(k < limit ? k : limit); };
-            // record k of the pass (issued earlier) becomes usable, and its stage goes back to the producer
+            // record k of the pass (issued earlier) becomes usable
             auto finish = [&](PosRecord& r, int k) {
                 FinishPosRecord(r, k < nK, T);
                 __syncwarp();
-                if (k < nMaxK && lane == 0) MbarArriveA(emptyOf(base + k));
+                if (B2G_EARLY_RELEASE && k < nMaxK && lane == 0) MbarArriveA(emptyOf(base + k));
             };
             // One chain step: `cur` (record i of the pass) is solved on `bv` if `solve`; `fill` receives record i + 2 (past
             // the pass's last record: a stale stage, read and ignored) and the body values of `nxt` are read.
             auto step = [&](PosRecord& cur, const PosRecord& nxt, PosRecord& fill, BodyVals& bv, uint32_t& curA, uint32_t& curB,
                             bool& solve) {
-                {
-                    const uint32_t need = needFor(base + i + 3);  // record i + 2
-                    if (landed < need) waitLanded(need);
-                }
+                // record i + 2 (past the pass's last record there is nothing to wait for: the producer streams the next
+                // pass only after this one's verdict)
+                if (!landedNext && i + 2 < nMaxK) MbarSpinA(fullOf(base + i + 2), parityOf(base + i + 2));
                 IssuePosRecord(fill, stageOf(base + i + 2));
+                landedNext = MbarTestA(fullOf(base + i + 3), parityOf(base + i + 3));
                 // a contact is solved if its island has not converged in an earlier pass
                 const bool solveNext = (nxt.info & 8) != 0 && !doneBit(nxt.info);
                 const uint32_t nxtA = solveNext ? nxt.pA : scratch, nxtB = solveNext ? nxt.pB : scratch;
@@ -1224,12 +1224,14 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
                 curB = nxtB;
                 solve = solveNext;
                 finish(fill, i + 2);
+                // record i is solved and stored: its stage goes back (past the pass's last record there is none)
+                if (!B2G_EARLY_RELEASE && i < nMaxK && lane == 0) MbarArriveA(emptyOf(base + i));
                 ++i;
             };
-            if (depth < 8) {
+            if (depth < 8 || B2G_POS_FORCE_SIMPLE) {
                 // a handful of contacts per world: one record at a time, nothing overlapped
                 for (; i < nMaxK; ++i) {
-                    waitLanded((uint32_t)(base + i) + 1u);
+                    MbarSpinA(fullOf(base + i), parityOf(base + i));
                     PosRecord r;
                     IssuePosRecord(r, stageOf(base + i));
                     FinishPosRecord(r, i < nK, T);
@@ -1260,11 +1262,13 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
                 }
             } else {
             PosRecord r0, r1, r2;
-            waitLanded((uint32_t)base + 2u);
+            MbarSpinA(fullOf(base), parityOf(base));
             IssuePosRecord(r0, stageOf(base));
             finish(r0, 0);
+            MbarSpinA(fullOf(base + 1), parityOf(base + 1));
             IssuePosRecord(r1, stageOf(base + 1));
             finish(r1, 1);
+            landedNext = MbarTestA(fullOf(base + 2), parityOf(base + 2));
             bool solve = (r0.info & 8) != 0 && !doneBit(r0.info);
             uint32_t curA = solve ? r0.pA : scratch, curB = solve ? r0.pB : scratch;
             BodyVals bv = LoadBodyVals(curA, curB);
