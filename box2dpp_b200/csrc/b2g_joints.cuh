@@ -80,15 +80,44 @@ __device__ __forceinline__ Vec2 Mul22(const Mat33& A, Vec2 v) {
     return V2(A.ex.x * v.x + A.ey.x * v.y, A.ex.y * v.x + A.ey.y * v.y);
 }
 
+// Where a joint finds its bodies' b2Velocity / b2Position during the solve.  Generic solver (k_solve): the body arrays in
+// global memory are the working copies.  Tile solver (b2g_solve.cuh): the tile's table in shared memory, row b at
+// table + b * 384, components 128 bytes apart, this lane's column already added in (0 = not the table).
 struct JointCols {
     Col<int4> jI;
     Col<float4> jF0, jF1, jF2, jImp, jTmp;
     Col<float4> bodySweep, bodyVel, bodyMass;
+    uint32_t velTable, posTable;
+    static __device__ __forceinline__ float4 LoadRow(uint32_t a) {
+        float4 v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.x) : "r"(a));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.y) : "r"(a + 128));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v.z) : "r"(a + 256));
+        v.w = 0.0f;
+        return v;
+    }
+    static __device__ __forceinline__ void StoreRow(uint32_t a, float4 v) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v.x));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 128), "f"(v.y));
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 256), "f"(v.z));
+    }
+    __device__ __forceinline__ float4 vel(int b) const { return velTable ? LoadRow(velTable + (uint32_t)b * 384u) : bodyVel[b]; }
+    __device__ __forceinline__ void setVel(int b, float4 v) const {
+        if (velTable) StoreRow(velTable + (uint32_t)b * 384u, v);
+        else bodyVel[b] = v;
+    }
+    // m_sweep.c.xy, m_sweep.a (.w, the sleep time, is not the solver's: it stays where it is on the table path)
+    __device__ __forceinline__ float4 sweep(int b) const { return posTable ? LoadRow(posTable + (uint32_t)b * 384u) : bodySweep[b]; }
+    __device__ __forceinline__ void setSweep(int b, float4 v) const {
+        if (posTable) StoreRow(posTable + (uint32_t)b * 384u, v);
+        else bodySweep[b] = v;
+    }
 };
-__device__ __forceinline__ JointCols MakeJointCols(const Arena& A, int tile, int lane) {
+__device__ __forceinline__ JointCols MakeJointCols(const Arena& A, int tile, int lane, uint32_t velTable = 0, uint32_t posTable = 0) {
     JointCols c{col(A.jointI, tile, A.NJ, lane), col(A.jointF0, tile, A.NJ, lane), col(A.jointF1, tile, A.NJ, lane),
                 col(A.jointF2, tile, A.NJ, lane), col(A.jointImp, tile, A.NJ, lane), col(A.jointTmp, tile, A.NJ * kJointTmp, lane),
-                col(A.bodySweep, tile, A.NB, lane), col(A.bodyVel, tile, A.NB, lane), col(A.bodyMass, tile, A.NB, lane)};
+                col(A.bodySweep, tile, A.NB, lane), col(A.bodyVel, tile, A.NB, lane), col(A.bodyMass, tile, A.NB, lane),
+                velTable, posTable};
     return c;
 }
 
@@ -110,10 +139,10 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
     const float4 f0 = c.jF0[j], f1 = c.jF1[j], f2 = c.jF2[j];
     const float4 msA = c.bodyMass[bA], msB = c.bodyMass[bB];
     const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
-    const float4 swA = c.bodySweep[bA], swB = c.bodySweep[bB];
+    const float4 swA = c.sweep(bA), swB = c.sweep(bB);
     const Vec2 cA = V2(swA.x, swA.y), cB = V2(swB.x, swB.y);
     const float aA = swA.z, aB = swB.z;
-    float4 velA = c.bodyVel[bA], velB = c.bodyVel[bB];
+    float4 velA = c.vel(bA), velB = c.vel(bB);
     Vec2 vA = V2(velA.x, velA.y), vB = V2(velB.x, velB.y);
     float wA = velA.z, wB = velB.z;
     const Rot qA = MakeRot(aA), qB = MakeRot(aB);
@@ -127,8 +156,8 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
         const int typeA = (ji.x >> 11) & 3, typeB = (ji.x >> 13) & 3;
         const float4 msC = c.bodyMass[bC], msD = c.bodyMass[bD];
         const float mC = msC.x, iC = msC.y, mD = msD.x, iD = msD.y;
-        const float aC = c.bodySweep[bC].z, aD = c.bodySweep[bD].z;
-        float4 velC = c.bodyVel[bC], velD = c.bodyVel[bD];
+        const float aC = c.sweep(bC).z, aD = c.sweep(bD).z;
+        float4 velC = c.vel(bC), velD = c.vel(bD);
         Vec2 vC = V2(velC.x, velC.y), vD = V2(velD.x, velD.y);
         float wC = velC.z, wD = velD.z;
         const Rot qC = MakeRot(aC), qD = MakeRot(aD);
@@ -181,10 +210,10 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
         c.jTmp[t + 2] = make_float4(g.mass, 0.0f, 0.0f, 0.0f);
         c.jImp[j] = imp;
         // stores in the reference's order A, B, C, D (C and D may be the same body: the later store wins)
-        c.bodyVel[bA] = make_float4(vA.x, vA.y, wA, 0.0f);
-        c.bodyVel[bB] = make_float4(vB.x, vB.y, wB, 0.0f);
-        c.bodyVel[bC] = make_float4(vC.x, vC.y, wC, 0.0f);
-        c.bodyVel[bD] = make_float4(vD.x, vD.y, wD, 0.0f);
+        c.setVel(bA, make_float4(vA.x, vA.y, wA, 0.0f));
+        c.setVel(bB, make_float4(vB.x, vB.y, wB, 0.0f));
+        c.setVel(bC, make_float4(vC.x, vC.y, wC, 0.0f));
+        c.setVel(bD, make_float4(vD.x, vD.y, wD, 0.0f));
         return;
     }
     if (type == B2G_JOINT_MOUSE) {  // b2MouseJoint.cpp:96-160; f0 = target.xy, localAnchorB.xy; f1 = maxForce, frequencyHz, dampingRatio, mass of B
@@ -569,8 +598,8 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
         c.jTmp[t + 4] = make_float4(k13, k23, k33, 0.0f);
     }
     c.jImp[j] = imp;
-    c.bodyVel[bA] = make_float4(vA.x, vA.y, wA, 0.0f);
-    c.bodyVel[bB] = make_float4(vB.x, vB.y, wB, 0.0f);
+    c.setVel(bA, make_float4(vA.x, vA.y, wA, 0.0f));
+    c.setVel(bB, make_float4(vB.x, vB.y, wB, 0.0f));
 }
 
 // ---- SolveVelocityConstraints ----------------------------------------------------------------------------------
@@ -581,7 +610,7 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
     const int bA = ji.y & 0xffff, bB = (ji.y >> 16) & 0xffff;
     const float4 msA = c.bodyMass[bA], msB = c.bodyMass[bB];
     const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
-    float4 velA = c.bodyVel[bA], velB = c.bodyVel[bB];
+    float4 velA = c.vel(bA), velB = c.vel(bB);
     Vec2 vA = V2(velA.x, velA.y), vB = V2(velB.x, velB.y);
     float wA = velA.z, wB = velB.z;
     float4 imp = c.jImp[j];
@@ -592,7 +621,7 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
         const int bC = ji.w & 0xffff, bD = (ji.w >> 16) & 0xffff;
         const float4 msC = c.bodyMass[bC], msD = c.bodyMass[bD];
         const float mC = msC.x, iC = msC.y, mD = msD.x, iD = msD.y;
-        float4 velC = c.bodyVel[bC], velD = c.bodyVel[bD];
+        float4 velC = c.vel(bC), velD = c.vel(bD);
         Vec2 vC = V2(velC.x, velC.y), vD = V2(velD.x, velD.y);
         float wC = velC.z, wD = velD.z;
         const float4 t0 = c.jTmp[t + 0], t1 = c.jTmp[t + 1], t2 = c.jTmp[t + 2];
@@ -611,10 +640,10 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
         vD = vD - (mD * impulse) * JvBD;
         wD -= iD * impulse * JwD;
         c.jImp[j] = imp;
-        c.bodyVel[bA] = make_float4(vA.x, vA.y, wA, 0.0f);
-        c.bodyVel[bB] = make_float4(vB.x, vB.y, wB, 0.0f);
-        c.bodyVel[bC] = make_float4(vC.x, vC.y, wC, 0.0f);
-        c.bodyVel[bD] = make_float4(vD.x, vD.y, wD, 0.0f);
+        c.setVel(bA, make_float4(vA.x, vA.y, wA, 0.0f));
+        c.setVel(bB, make_float4(vB.x, vB.y, wB, 0.0f));
+        c.setVel(bC, make_float4(vC.x, vC.y, wC, 0.0f));
+        c.setVel(bD, make_float4(vD.x, vD.y, wD, 0.0f));
         return;
     }
     if (type == B2G_JOINT_MOUSE) {  // b2MouseJoint.cpp:162-186
@@ -947,8 +976,8 @@ __device__ __noinline__ void JointSolveVelocity(const JointCols* cp, int j, floa
         }
     }
     c.jImp[j] = imp;
-    c.bodyVel[bA] = make_float4(vA.x, vA.y, wA, 0.0f);
-    c.bodyVel[bB] = make_float4(vB.x, vB.y, wB, 0.0f);
+    c.setVel(bA, make_float4(vA.x, vA.y, wA, 0.0f));
+    c.setVel(bB, make_float4(vB.x, vB.y, wB, 0.0f));
 }
 
 // ---- SolvePositionConstraints; returns the joint's "okay" -------------------------------------------------------------
@@ -960,7 +989,7 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
     const float4 f0 = c.jF0[j], f1 = c.jF1[j];
     const float4 msA = c.bodyMass[bA], msB = c.bodyMass[bB];
     const float mA = msA.x, iA = msA.y, mB = msB.x, iB = msB.y;
-    float4 swA = c.bodySweep[bA], swB = c.bodySweep[bB];
+    float4 swA = c.sweep(bA), swB = c.sweep(bB);
     Vec2 cA = V2(swA.x, swA.y), cB = V2(swB.x, swB.y);
     float aA = swA.z, aB = swB.z;
     const Vec2 lA = V2(f0.x, f0.y) - V2(msA.z, msA.w), lB = V2(f0.z, f0.w) - V2(msB.z, msB.w);
@@ -974,7 +1003,7 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
         const float4 f2 = c.jF2[j], imp = c.jImp[j];
         const float4 msC = c.bodyMass[bC], msD = c.bodyMass[bD];
         const float mC = msC.x, iC = msC.y, mD = msD.x, iD = msD.y;
-        float4 swC = c.bodySweep[bC], swD = c.bodySweep[bD];
+        float4 swC = c.sweep(bC), swD = c.sweep(bD);
         Vec2 cC = V2(swC.x, swC.y), cD = V2(swD.x, swD.y);
         float aC = swC.z, aD = swD.z;
         const Rot qA = MakeRot(aA), qB = MakeRot(aB), qC = MakeRot(aC), qD = MakeRot(aD);
@@ -1033,10 +1062,10 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
         aC -= iC * impulse * JwC;
         cD = cD - (mD * impulse) * JvBD;
         aD -= iD * impulse * JwD;
-        c.bodySweep[bA] = make_float4(cA.x, cA.y, aA, swA.w);
-        c.bodySweep[bB] = make_float4(cB.x, cB.y, aB, swB.w);
-        c.bodySweep[bC] = make_float4(cC.x, cC.y, aC, swC.w);
-        c.bodySweep[bD] = make_float4(cD.x, cD.y, aD, swD.w);
+        c.setSweep(bA, make_float4(cA.x, cA.y, aA, swA.w));
+        c.setSweep(bB, make_float4(cB.x, cB.y, aB, swB.w));
+        c.setSweep(bC, make_float4(cC.x, cC.y, aC, swC.w));
+        c.setSweep(bD, make_float4(cD.x, cD.y, aD, swD.w));
         return linearError < kLinearSlop;
     }
     if (type == B2G_JOINT_REVOLUTE) {  // b2RevoluteJoint.cpp:279-371
@@ -1262,7 +1291,7 @@ __device__ __noinline__ bool JointSolvePosition(const JointCols* cp, int j) {
         aB += iB * LB;
         okay = linearError <= kLinearSlop && angularError <= kAngularSlop;
     }
-    c.bodySweep[bA] = make_float4(cA.x, cA.y, aA, swA.w);
-    c.bodySweep[bB] = make_float4(cB.x, cB.y, aB, swB.w);
+    c.setSweep(bA, make_float4(cA.x, cA.y, aA, swA.w));
+    c.setSweep(bB, make_float4(cB.x, cB.y, aB, swB.w));
     return okay;
 }

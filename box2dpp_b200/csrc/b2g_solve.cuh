@@ -138,7 +138,7 @@ __device__ __forceinline__ int PackBodies(int bodyA, int bodyB, int pointCount) 
 __host__ __device__ inline size_t SolveTableBytes(int NB) { return ((size_t)(NB + 1) * 3 * kTile * 4 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t SolveSmemBytes(int NB) {
     size_t body = SolveTableBytes(NB);
-    size_t done = (size_t)((NB + 31) / 32) * kTile * 4;
+    size_t done = 2 * (size_t)((NB + 31) / 32) * kTile * 4;  // "converged" and "contacts fine this pass" bit per island
     size_t vel = (size_t)kVelStages * (kVelRec + 1) * 16 * kTile + 256;                // ring + barriers
     size_t pos = (size_t)kRecStages * kPosRec * 16 * kTile + done + 256;
     return body + (vel > pos ? vel : pos);
@@ -649,13 +649,22 @@ __device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, BodyV
     return imp;
 }
 
-__global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
+__global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters, float h) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t ws = (size_t)tile * kTile + lane;
     const int n = A.solveCount[ws];
     const int nMax = __reduce_max_sync(0xffffffffu, n);
-    if (nMax == 0) return;  // no touching contact in the whole tile: velocities stay as integrated
+    // joints of this world's islands, in island order (k_islands): b2Island::Solve initialises them after the contacts'
+    // warm start and solves them in front of the contacts in every velocity iteration (b2Island.cpp:252-269).  Islands
+    // only share static bodies, so "every island's joints, then every island's contacts" is the same arithmetic.
+    int nJoints = 0;
+    if (A.hasJoints) {
+        const int islands = A.islandCount[ws];
+        if (islands > 0 && A.jointCount[ws] > 0) nJoints = col(A.islandJointEnd, tile, A.NB, lane)[islands - 1];
+    }
+    const bool anyJoints = A.hasJoints && __any_sync(0xffffffffu, nJoints > 0);
+    if (nMax == 0 && !anyJoints) return;  // nothing to solve in the whole tile: velocities stay as integrated
     const bool warm = (A.worldFlags[ws] & B2G_WORLD_WARM_STARTING) != 0;
     const int anyWarm = __any_sync(0xffffffffu, warm) ? 1 : 0;
     const int total = nMax * (velIters + anyWarm);
@@ -669,7 +678,9 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
     //    fetched them writes them to impRec when the stage is recycled — store and re-fetch of one contact are issued by
     //    the same thread, in that order.
     // The depth is a power of two (stage of record k = k & (depth - 1)).
-    const bool pipelined = nMax >= kVelPipelineMin;
+    // A tile with joints takes the one-record path: the joints run between two passes on the table in shared memory,
+    // and the pipelined consumer carries the next contact's body values in registers across pass boundaries.
+    const bool pipelined = nMax >= kVelPipelineMin && !anyJoints;
     int depth = 1, depthLog = 0;
     while (depth * 2 <= nMax - 1 && depth * 2 <= kVelStages) { depth *= 2; ++depthLog; }
 
@@ -823,8 +834,23 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
         }
         while (seq < totalK) single(std::false_type());
     } else {
+        const JointCols jc = MakeJointCols(A, tile, lane, T.base, 0);
+        Col<int> iJoints = col(A.islandJoints, tile, A.NJ, lane);
+        const float dtRatio = A.invDt0[ws] * h;
+        auto jointsInit = [&]() {
+            for (int j = 0; j < nJoints; ++j) JointInitVelocity(&jc, iJoints[j], h, dtRatio, warm);
+            __syncwarp();
+        };
+        auto jointsSolve = [&]() {
+            for (int j = 0; j < nJoints; ++j) JointSolveVelocity(&jc, iJoints[j], h);
+            __syncwarp();
+        };
         int i = 0, cs = 0;
         for (int seq = 0; seq < total; ++seq) {
+            if (anyJoints && i == 0 && seq >= warmRecords) {  // a velocity iteration starts
+                if (seq == warmRecords) jointsInit();
+                jointsSolve();
+            }
             const uint32_t st = stage0 + cs * kVelStageBytes;
             MbarSpinA(full0 + cs * 8, ((uint32_t)seq >> depthShift) & 1u);
             if (i < n) {
@@ -843,6 +869,10 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters) {
             if (lane == 0) MbarArriveA(empty0 + cs * 8);
             if (++i == nMax) i = 0;
             if (++cs == depth) cs = 0;
+        }
+        if (anyJoints && (nMax == 0 || velIters == 0)) {  // no contact pass to hang the joints on
+            jointsInit();
+            for (int it = 0; it < velIters; ++it) jointsSolve();
         }
     }
     // velocities back to the solver table in global memory
@@ -1070,7 +1100,15 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     const int doneWords = (A.NB + 31) / 32;
     int* gDone = A.islandSolved + (size_t)tile * doneWords * kTile + lane;  // bit per island: position solver converged
     Col<int> iContactEnd = col(A.islandContactEnd, tile, A.NB, lane);
-    if (nMax == 0 || posIters <= 0) {
+    // Joints (b2Island.cpp:316-320): every position iteration of an island solves its contacts, then its joints, and the
+    // island has converged once both say so.  A world with joints therefore gets its islands' verdicts after the joints
+    // have run, behind the tile's contact pass (islands only share static bodies: the order across islands is free).
+    Col<int> iJointEnd = col(A.islandJointEnd, tile, A.NB, lane);
+    Col<int> iJoints = col(A.islandJoints, tile, A.NJ, lane);
+    int nJoints = 0;
+    if (A.hasJoints && islands > 0 && A.jointCount[ws] > 0) nJoints = iJointEnd[islands - 1];
+    const bool anyJoints = A.hasJoints && __any_sync(0xffffffffu, nJoints > 0);
+    if ((nMax == 0 && !anyJoints) || posIters <= 0) {
         // islands without contacts converge in the first pass (minSeparation == 0); no pass, no convergence
         if (warp == 0)
             for (int wd = 0; wd < doneWords; ++wd) gDone[(size_t)wd * kTile] = posIters > 0 ? -1 : 0;
@@ -1081,7 +1119,7 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     const uint32_t bodyBytes = (uint32_t)A.NB * 3 * kTile * 4;
     unsigned char* stages = smem + SolveTableBytes(A.NB);
     uint32_t* sDone = reinterpret_cast<uint32_t*>(stages + kRecStages * kPosStageBytes) + lane;  // word wd at sDone[wd * 32]
-    uint64_t* full = reinterpret_cast<uint64_t*>(stages + kRecStages * kPosStageBytes + (size_t)doneWords * kTile * 4);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + kRecStages * kPosStageBytes + (size_t)2 * doneWords * kTile * 4);
     uint64_t* empty = full + kRecStages;
     uint64_t* bodyBar = empty + kRecStages;
     uint64_t* passBar = bodyBar + 1;
@@ -1125,16 +1163,19 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     }
 
     // ================= consumer =================
-    for (int wd = 0; wd < doneWords; ++wd) sDone[wd * kTile] = 0u;
-    // islands that own at least one contact and have not converged yet
+    for (int wd = 0; wd < 2 * doneWords; ++wd) sDone[wd * kTile] = 0u;  // words doneWords..: "contacts fine this pass"
+    // islands that own at least one contact (or joint) and have not converged yet
+    const bool deferred = nJoints > 0;  // this world's islands get their verdict after the joints
     int pending = 0;
     {
-        int prev = 0;
+        int prev = 0, prevJ = 0;
         for (int isl = 0; isl < islands; ++isl) {
             int e = iContactEnd[isl];
-            if (e > prev) ++pending;
-            else sDone[(isl >> 5) * kTile] |= 1u << (isl & 31);  // no contacts: minSeparation = 0 -> solved
+            const int ej = deferred ? iJointEnd[isl] : 0;
+            if (e > prev || ej > prevJ) ++pending;
+            else sDone[(isl >> 5) * kTile] |= 1u << (isl & 31);  // nothing to solve: minSeparation = 0 -> solved
             prev = e;
+            prevJ = ej;
         }
     }
     while (!MbarTryWait(bodyBar, 0)) {}
@@ -1147,6 +1188,7 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     const uint32_t empty0 = Keep(SmemAddr(empty));
     const uint32_t full0 = Keep(SmemAddr(full));
     const uint32_t done0 = Keep(SmemAddr(sDone));
+    const uint32_t ok0 = Keep(SmemAddr(sDone + doneWords * kTile));
     const uint32_t mask = Keep((uint32_t)depth - 1u);
     const uint32_t depthShift = Keep((uint32_t)depthLog);
     const int nK = Keep(n), nMaxK = Keep(nMax);
@@ -1214,9 +1256,9 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
                 if ((cur.info & 12) == 12) {  // last contact of its island: close the island
                     if (solve && minSeparation >= -3.0f * kLinearSlop) {
                         const uint32_t isl = (uint32_t)cur.info >> 8;
-                        const uint32_t wd = done0 + (isl >> 5) * (kTile * 4);
+                        const uint32_t wd = (deferred ? ok0 : done0) + (isl >> 5) * (kTile * 4);
                         StsU(wd, LdsU(wd) | (1u << (isl & 31)));
-                        --pending;
+                        if (!deferred) --pending;
                     }
                     minSeparation = 0.0f;
                 }
@@ -1253,9 +1295,9 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
                     if ((r.info & 12) == 12) {
                         if (solve && minSeparation >= -3.0f * kLinearSlop) {
                             const uint32_t isl = (uint32_t)r.info >> 8;
-                            const uint32_t wd = done0 + (isl >> 5) * (kTile * 4);
+                            const uint32_t wd = (deferred ? ok0 : done0) + (isl >> 5) * (kTile * 4);
                             StsU(wd, LdsU(wd) | (1u << (isl & 31)));
-                            --pending;
+                            if (!deferred) --pending;
                         }
                         minSeparation = 0.0f;
                     }
@@ -1280,6 +1322,34 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
             }
             }
             base += nMaxK;
+            if (anyJoints) {
+                __syncwarp();
+                if (deferred) {
+                    const JointCols jc = MakeJointCols(A, tile, lane, 0, T.base);
+                    int j0 = 0, c0 = 0;
+                    for (int isl = 0; isl < islands; ++isl) {
+                        const int j1 = iJointEnd[isl], c1 = iContactEnd[isl];
+                        const uint32_t dw = done0 + ((uint32_t)isl >> 5) * (kTile * 4), ow = ok0 + ((uint32_t)isl >> 5) * (kTile * 4);
+                        const uint32_t bit = 1u << (isl & 31);
+                        if ((LdsU(dw) & bit) == 0) {
+                            bool jointsOkay = true;
+                            for (int j = j0; j < j1; ++j) {
+                                const bool jointOkay = JointSolvePosition(&jc, iJoints[j]);
+                                jointsOkay = jointsOkay && jointOkay;
+                            }
+                            const bool contactsOkay = c1 == c0 || (LdsU(ow) & bit) != 0;
+                            if (contactsOkay && jointsOkay) {
+                                StsU(dw, LdsU(dw) | bit);
+                                --pending;
+                            }
+                            StsU(ow, LdsU(ow) & ~bit);
+                        }
+                        j0 = j1;
+                        c0 = c1;
+                    }
+                }
+                __syncwarp();
+            }
             const bool more = pass + 1 < posIters && !__all_sync(0xffffffffu, pending == 0);
             if (lane == 0) *(volatile int*)&sContinue = more ? 1 : 0;
             __syncwarp();

@@ -785,7 +785,7 @@ int configureKernels(b2gpu_batch* b) {
     // Solver path: the tile path keeps the b2Velocity / b2Position table of 32 worlds in shared memory.
     b->solveSmem = SolveSmemBytes(desc->maxBodies);
     // joints are solved by the generic kernel only (b2g_joints.cuh)
-    b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0 && desc->maxJoints <= 0;
+    b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0;
     b->collideSmemOk = (size_t)desc->maxContacts * kTile <= (size_t)maxSmem - 2048;
     if (b->collideSmemOk)
         CUDA_TRY(cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, desc->maxContacts * kTile));
@@ -864,7 +864,7 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
         return;
     } else if (part == 1) {
         if (b->tileSolver) {
-            k_solve_velocity<<<tiles, 128, b->solveSmem, st>>>(A, velIters);
+            k_solve_velocity<<<tiles, 128, b->solveSmem, st>>>(A, velIters, dt);
             mark();
             k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
             mark();

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("out")
     ap.add_argument("--gpus", type=int, default=8)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--cells", default="", help="explicit plan: workload:total_worlds:gpus[:alone],... (replaces the default one)")
     a = ap.parse_args()
     out_dir = os.path.dirname(os.path.abspath(a.out))
     G = a.gpus
@@ -63,6 +64,14 @@ def main():
                 continue
             shared.append({"name": f"pyramid_{t}on{n}", "workload": "pyramid", "wpg": wpg, "n": n,
                            "steps": 20 if wpg <= 65536 else 10, "e2e": 3})
+    if a.cells:
+        alone, shared, skipped = [], [], []
+        for c in a.cells.split(","):
+            f = c.split(":")
+            wl, t, n = f[0], int(f[1]), int(f[2])
+            job = {"name": f"{wl}_{t}on{n}", "workload": wl, "wpg": t // n, "n": n, "steps": 20 if t // n <= 65536 else 10,
+                   "e2e": 20 if len(f) > 3 else 3}
+            (alone if len(f) > 3 else shared).append(job)
     results = open(a.out, "a")
     for s in skipped:
         results.write(json.dumps({"skipped": s}) + "\n")
