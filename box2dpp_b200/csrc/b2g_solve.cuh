@@ -649,6 +649,8 @@ __device__ __forceinline__ float4 SolveVelocityContact(const VelRecord& r, BodyV
     return imp;
 }
 
+// JOINTS: the batch has joints (a separate instantiation, so that the joint-free kernel's code is what it was).
+template <bool JOINTS>
 __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters, float h) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tile = A.tile0 + blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -659,11 +661,11 @@ __global__ void __launch_bounds__(128) k_solve_velocity(Arena A, int velIters, f
     // warm start and solves them in front of the contacts in every velocity iteration (b2Island.cpp:252-269).  Islands
     // only share static bodies, so "every island's joints, then every island's contacts" is the same arithmetic.
     int nJoints = 0;
-    if (A.hasJoints) {
+    if (JOINTS) {
         const int islands = A.islandCount[ws];
         if (islands > 0 && A.jointCount[ws] > 0) nJoints = col(A.islandJointEnd, tile, A.NB, lane)[islands - 1];
     }
-    const bool anyJoints = A.hasJoints && __any_sync(0xffffffffu, nJoints > 0);
+    const bool anyJoints = JOINTS && __any_sync(0xffffffffu, nJoints > 0);
     if (nMax == 0 && !anyJoints) return;  // nothing to solve in the whole tile: velocities stay as integrated
     const bool warm = (A.worldFlags[ws] & B2G_WORLD_WARM_STARTING) != 0;
     const int anyWarm = __any_sync(0xffffffffu, warm) ? 1 : 0;
@@ -1089,6 +1091,7 @@ __device__ __noinline__ PosContactResult SolvePositionContactAnyAngle(float4 r0,
     return o;
 }
 
+template <bool JOINTS>
 __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int sContinue;
@@ -1106,8 +1109,8 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     Col<int> iJointEnd = col(A.islandJointEnd, tile, A.NB, lane);
     Col<int> iJoints = col(A.islandJoints, tile, A.NJ, lane);
     int nJoints = 0;
-    if (A.hasJoints && islands > 0 && A.jointCount[ws] > 0) nJoints = iJointEnd[islands - 1];
-    const bool anyJoints = A.hasJoints && __any_sync(0xffffffffu, nJoints > 0);
+    if (JOINTS && islands > 0 && A.jointCount[ws] > 0) nJoints = iJointEnd[islands - 1];
+    const bool anyJoints = JOINTS && __any_sync(0xffffffffu, nJoints > 0);
     if ((nMax == 0 && !anyJoints) || posIters <= 0) {
         // islands without contacts converge in the first pass (minSeparation == 0); no pass, no convergence
         if (warp == 0)
@@ -1163,9 +1166,9 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     }
 
     // ================= consumer =================
-    for (int wd = 0; wd < 2 * doneWords; ++wd) sDone[wd * kTile] = 0u;  // words doneWords..: "contacts fine this pass"
+    for (int wd = 0; wd < (JOINTS ? 2 : 1) * doneWords; ++wd) sDone[wd * kTile] = 0u;  // words doneWords..: "contacts fine this pass"
     // islands that own at least one contact (or joint) and have not converged yet
-    const bool deferred = nJoints > 0;  // this world's islands get their verdict after the joints
+    const bool deferred = JOINTS && nJoints > 0;  // this world's islands get their verdict after the joints
     int pending = 0;
     {
         int prev = 0, prevJ = 0;
@@ -1188,7 +1191,7 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     const uint32_t empty0 = Keep(SmemAddr(empty));
     const uint32_t full0 = Keep(SmemAddr(full));
     const uint32_t done0 = Keep(SmemAddr(sDone));
-    const uint32_t ok0 = Keep(SmemAddr(sDone + doneWords * kTile));
+    const uint32_t ok0 = JOINTS ? Keep(SmemAddr(sDone + doneWords * kTile)) : 0u;
     const uint32_t mask = Keep((uint32_t)depth - 1u);
     const uint32_t depthShift = Keep((uint32_t)depthLog);
     const int nK = Keep(n), nMaxK = Keep(nMax);

@@ -784,14 +784,15 @@ int configureKernels(b2gpu_batch* b) {
     CUDA_TRY(cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->device));
     // Solver path: the tile path keeps the b2Velocity / b2Position table of 32 worlds in shared memory.
     b->solveSmem = SolveSmemBytes(desc->maxBodies);
-    // joints are solved by the generic kernel only (b2g_joints.cuh)
     b->tileSolver = b->solveSmem <= (size_t)maxSmem && desc->maxBodies < 32768 && (desc->reserved & 1) == 0;
     b->collideSmemOk = (size_t)desc->maxContacts * kTile <= (size_t)maxSmem - 2048;
     if (b->collideSmemOk)
         CUDA_TRY(cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, desc->maxContacts * kTile));
     if (b->tileSolver) {
-        CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
-        CUDA_TRY(cudaFuncSetAttribute(k_solve_position, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_solve_velocity<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_solve_position<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_solve_position<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->solveSmem));
     }
     // k_islands: as many worlds per CTA as keep two or more CTAs resident per SM (the DFS is latency bound)
     const size_t perWorld = IslandSmemPerWorld(desc->maxBodies, desc->maxContacts, desc->maxJoints > 0 ? desc->maxJoints : 0);
@@ -864,11 +865,13 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
         return;
     } else if (part == 1) {
         if (b->tileSolver) {
-            k_solve_velocity<<<tiles, 128, b->solveSmem, st>>>(A, velIters, dt);
+            if (A.hasJoints) k_solve_velocity<true><<<tiles, 128, b->solveSmem, st>>>(A, velIters, dt);
+            else k_solve_velocity<false><<<tiles, 128, b->solveSmem, st>>>(A, velIters, dt);
             mark();
             k_solve_integrate<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
             mark();
-            k_solve_position<<<tiles, 128, b->solveSmem, st>>>(A, posIters);
+            if (A.hasJoints) k_solve_position<true><<<tiles, 128, b->solveSmem, st>>>(A, posIters);
+            else k_solve_position<false><<<tiles, 128, b->solveSmem, st>>>(A, posIters);
             mark();
         } else {
             k_solve<<<blocks, threads, 0, st>>>(A, dt, velIters, posIters);

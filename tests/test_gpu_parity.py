@@ -192,6 +192,14 @@ def test_joints_no_warm_starting_and_62(oracles):
     run_parity(oracles, scenes, 300, 6, 2, check_every=3)
 
 
+def test_joints_generic_solver(oracles):
+    # the same joint code on the body arrays in global memory (k_solve): the path of batches whose body table does not
+    # fit shared memory
+    _need_ref(oracles)
+    scenes = [S.jointed(2), S.vehicles(3, flags=NOCCD), S.jointed(5, flags=NOCCD)]
+    run_parity(oracles, scenes, 240, 8, 3, check_every=2, generic_solver=True)
+
+
 def test_binned_and_lane_mapped_narrow_phase_agree():
     # k_collide's type-binned evaluation (worlds that mix shape types) against the lane-per-world evaluation
     scenes = [S.mixed(s) for s in range(20)] + [S.sensors(s) for s in range(8)] + [S.vehicles(s) for s in range(6)] + \
