@@ -25,13 +25,13 @@ LIB_PATH = os.environ.get("B2GPU_LIB") or os.path.join(_HERE, "libb2gpu.so")
  F_PROXY_INFO, F_PROXY_MOVED, F_SHAPE_WORDS, F_CHAIN_VERTS, F_CONTACT_A, F_CONTACT_K, F_CONTACT_S, F_CONTACT_P0,
  F_CONTACT_P1, F_CONTACT_N, F_EVENT_A, F_EVENT_B, F_ISLAND_CONTACTS, F_ISLAND_CONTACT_END, F_JOINT_COUNT, F_JOINT_I,
  F_JOINT_F0, F_JOINT_F1, F_JOINT_F2, F_JOINT_IMPULSE, F_FIXTURE_COUNT, F_SHAPE_WORD_COUNT, F_CHAIN_VERT_COUNT,
- F_PROXY_FREE_COUNT, F_PROXY_FREE, F_NEW_FIXTURE, F_COUNT) = range(50)
+ F_PROXY_FREE_COUNT, F_PROXY_FREE, F_NEW_FIXTURE, F_JOINT_SEQ, F_FIXTURE_MASS, F_COUNT) = range(52)
 
 INT_FIELDS = {F_WORLD_FLAGS, F_BODY_COUNT, F_PROXY_COUNT, F_CONTACT_COUNT, F_STATUS, F_EVENT_COUNT, F_ISLAND_COUNT,
               F_STEP_COUNT, F_BODY_FLAGS, F_FIXTURE_INFO, F_FIXTURE_SHAPE, F_FIXTURE_FILTER, F_PROXY_INFO,
               F_PROXY_MOVED, F_CONTACT_A, F_CONTACT_K, F_CONTACT_S, F_EVENT_A, F_ISLAND_CONTACTS,
               F_ISLAND_CONTACT_END, F_JOINT_COUNT, F_JOINT_I, F_FIXTURE_COUNT, F_SHAPE_WORD_COUNT, F_CHAIN_VERT_COUNT,
-              F_PROXY_FREE_COUNT, F_PROXY_FREE, F_NEW_FIXTURE}
+              F_PROXY_FREE_COUNT, F_PROXY_FREE, F_NEW_FIXTURE, F_JOINT_SEQ}
 
 EVENT_BEGIN, EVENT_END, EVENT_PRESOLVE, EVENT_POSTSOLVE = 0, 1, 2, 3
 EVENT_ALL = 15
@@ -42,7 +42,8 @@ EXPORTED_SYMBOLS = [
     "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_step_io", "b2gpu_batch_io_select", "b2gpu_batch_last_step_ms",
     "b2gpu_batch_profile_steps", "b2gpu_batch_profile_kernels", "b2gpu_batch_kernel_name", "b2gpu_batch_launch_count", "b2gpu_last_error", "b2gpu_scene_capacities",
     "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build", "b2gpu_host_sincosf", "b2gpu_sincosf",
-    "b2gpu_collide_pairs",
+    "b2gpu_collide_pairs", "b2gpu_batch_create_bodies", "b2gpu_batch_create_fixtures", "b2gpu_batch_create_joints",
+    "b2gpu_batch_joint_records", "b2gpu_batch_spawn_records", "b2gpu_batch_body_commands",
 ]
 
 COLLIDE_POLYGONS, COLLIDE_CIRCLES, COLLIDE_POLYGON_CIRCLE, COLLIDE_EDGE_CIRCLE, COLLIDE_EDGE_POLYGON = range(5)
@@ -66,7 +67,17 @@ BODY_COMMAND_DTYPE = np.dtype([("world", "<i4"), ("body", "<i4"), ("op", "<i4"),
                                ("v", "<f4", 2), ("p", "<f4", 2)])
 (CMD_APPLY_FORCE, CMD_APPLY_FORCE_TO_CENTER, CMD_APPLY_TORQUE, CMD_APPLY_LINEAR_IMPULSE, CMD_APPLY_ANGULAR_IMPULSE,
  CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE, CMD_DESTROY_BODY,
- CMD_MOUSE_SET_TARGET) = range(11)
+ CMD_MOUSE_SET_TARGET, CMD_SET_FILTER, CMD_DESTROY_JOINT, CMD_SET_TYPE, CMD_SET_ACTIVE, CMD_SET_MASS_DATA,
+ CMD_RESET_MASS_DATA, CMD_DESTROY_FIXTURE) = range(18)
+
+
+def put_filter(commands: np.ndarray, i: int, category_bits=1, mask_bits=0xffff, group_index=0):
+    """Fills the v field of the CMD_SET_FILTER command commands[i]: two int32 BIT PATTERNS in the float slots (written through an
+    integer view: a float assignment could quieten a NaN pattern)."""
+    bits = commands["v"].view(np.uint32)
+    bits[i, 0] = (category_bits & 0xffff) | ((mask_bits & 0xffff) << 16)
+    bits[i, 1] = np.array([group_index], np.int32).view(np.uint32)[0]
+
 
 
 AABB_QUERY_DTYPE = np.dtype([("world", "<i4"), ("lower", "<f4", 2), ("upper", "<f4", 2)])       # b2gpu_aabb_query
@@ -111,6 +122,8 @@ def lib():
         L.b2gpu_batch_snapshot_save.argtypes = [vp, vp, C.c_int64]
         L.b2gpu_batch_snapshot_load.argtypes = [vp, vp, C.c_int64]
         L.b2gpu_batch_create_bodies.argtypes = [vp, vp, i32, vp, vp, vp]
+        L.b2gpu_batch_create_fixtures.argtypes = [vp, vp, i32, vp, vp, vp]
+        L.b2gpu_batch_create_joints.argtypes = [vp, vp, vp, i32, vp]
         L.b2gpu_batch_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_steps.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
         L.b2gpu_batch_profile_kernels.argtypes = [vp, C.c_float, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
@@ -156,7 +169,7 @@ class WorldBatch:
     """A batch of independent worlds on one GPU."""
 
     def __init__(self, scenes, replicate=1, device=0, max_contacts=0, max_events=0, event_mask=0, block_size=0,
-                 generic_solver=False, always_rebuild_islands=False, binned_collide=None, headroom=None):
+                 generic_solver=False, always_rebuild_islands=False, binned_collide=None, headroom=None, joint_headroom=0):
         if isinstance(scenes, Scene):
             scenes = [scenes]
         if isinstance(scenes, SceneBatch):
@@ -178,6 +191,7 @@ class WorldBatch:
             d.maxContacts += 4 * headroom[2]
             if d.eventMask:
                 d.maxEvents = max(d.maxEvents, 3 * d.maxContacts)
+        d.maxJoints += joint_headroom  # room for b2World::CreateJoint on the running worlds
         if binned_collide is not None:  # default: decided by b2gpu_scene_capacities (worlds that mix shape types)
             d.reserved = (d.reserved | 4) if binned_collide else (d.reserved & ~4)
         self.desc = d
@@ -420,6 +434,42 @@ class WorldBatch:
         cv = np.ascontiguousarray(verts if verts else [0.0, 0.0], np.float32)
         out = np.zeros(max(n, 1), np.int32)
         _check(lib().b2gpu_batch_create_bodies(self.h, arr, n, cf, cv.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out[:n]
+
+    def create_fixtures(self, attach):
+        """b2gpu_batch_create_fixtures: attach = [(world, body, [FixtureDef, ...], vertices xy list)] — b2Body::CreateFixture on
+        bodies that exist.  Returns the index of each entry's first new fixture (-1: arenas full / no such body)."""
+        from .scene import FixtureDef
+
+        class Attach(C.Structure):
+            _fields_ = [("world", C.c_int32), ("body", C.c_int32), ("firstFixture", C.c_int32), ("fixtureCount", C.c_int32)]
+
+        n = len(attach)
+        arr = (Attach * max(n, 1))()
+        fds, verts = [], []
+        for i, (world, body, fixtures, v) in enumerate(attach):
+            arr[i].world, arr[i].body, arr[i].firstFixture, arr[i].fixtureCount = world, body, len(fds), len(fixtures)
+            base = len(verts) // 2
+            for f in fixtures:
+                g = FixtureDef.from_buffer_copy(bytes(f))
+                g.firstVertex += base
+                fds.append(g)
+            verts.extend(float(x) for x in v)
+        cf = (FixtureDef * max(len(fds), 1))(*fds)
+        cv = np.ascontiguousarray(verts if verts else [0.0, 0.0], np.float32)
+        out = np.zeros(max(n, 1), np.int32)
+        _check(lib().b2gpu_batch_create_fixtures(self.h, arr, n, cf, cv.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out[:n]
+
+    def create_joints(self, joints):
+        """b2gpu_batch_create_joints: joints = [(world, JointDef)] — b2World::CreateJoint on running worlds.  Returns joint ids."""
+        from .scene import JointDef
+
+        n = len(joints)
+        worlds = np.ascontiguousarray([w for w, _ in joints] or [0], np.int32)
+        defs = (JointDef * max(n, 1))(*[JointDef.from_buffer_copy(bytes(d)) for _, d in joints])
+        out = np.zeros(max(n, 1), np.int32)
+        _check(lib().b2gpu_batch_create_joints(self.h, worlds.ctypes.data_as(C.c_void_p), defs, n, out.ctypes.data_as(C.c_void_p)))
         return out[:n]
 
     def snapshot(self) -> np.ndarray:

@@ -271,6 +271,36 @@ int BuildShape(HostShape& sh, const b2g_fixture_def& d, const float* V) {
 inline float IntBits(int v) { float f; memcpy(&f, &v, 4); return f; }
 
 // One world flattened into world-major field arrays of capacity-sized rows.
+// The constructor of every joint class that only copies its def (b2RevoluteJoint.cpp:47-64, b2PrismaticJoint.cpp:100-125,
+// b2DistanceJoint.cpp:51-62, b2WheelJoint.cpp:44-72, b2WeldJoint.cpp:52-66, b2RopeJoint.cpp:39-52, b2FrictionJoint.cpp:46-61,
+// b2MotorJoint.cpp:46-62, b2PulleyJoint.cpp:59-83) as the device's joint columns: I[4], F0[4], F1[4], F2[4] (bit patterns).
+// Gear and mouse joints read body state when they are built and are laid out by their own code in Flatten.
+static void PlainJointColumns(const b2g_joint_def& d, uint32_t cols[16]) {
+    auto fb = [](float v) { uint32_t u; memcpy(&u, &v, 4); return u; };
+    cols[0] = (uint32_t)(d.type | ((d.collideConnected ? 1 : 0) << 8) | ((d.enableLimit ? 1 : 0) << 9) | ((d.enableMotor ? 1 : 0) << 10));
+    cols[1] = (uint32_t)(d.bodyA | (d.bodyB << 16));
+    cols[2] = 0;  // m_limitState = e_inactiveLimit
+    cols[3] = 0;
+    cols[4] = fb(d.localAnchorA[0]); cols[5] = fb(d.localAnchorA[1]); cols[6] = fb(d.localAnchorB[0]); cols[7] = fb(d.localAnchorB[1]);
+    float f1[4], f2[4];
+    if (d.type == B2G_JOINT_DISTANCE) { f1[0] = d.length; f1[1] = d.frequencyHz; f1[2] = d.dampingRatio; f1[3] = 0.0f; }
+    else if (d.type == B2G_JOINT_ROPE) { f1[0] = d.length; f1[1] = 0.0f; f1[2] = 0.0f; f1[3] = 0.0f; }
+    else if (d.type == B2G_JOINT_FRICTION) { f1[0] = d.length; f1[1] = d.maxMotor; f1[2] = 0.0f; f1[3] = 0.0f; }
+    else if (d.type == B2G_JOINT_PULLEY) { f1[0] = d.localAxisA[0]; f1[1] = d.localAxisA[1]; f1[2] = d.lower; f1[3] = d.upper; }
+    else if (d.type == B2G_JOINT_MOTOR) { f1[0] = d.length; f1[1] = d.maxMotor; f1[2] = d.referenceAngle; f1[3] = d.frequencyHz; }
+    else if (d.type == B2G_JOINT_WHEEL) { f1[0] = d.frequencyHz; f1[1] = d.dampingRatio; f1[2] = 0.0f; f1[3] = d.maxMotor; }
+    else if (d.type == B2G_JOINT_WELD) { f1[0] = d.referenceAngle; f1[1] = d.frequencyHz; f1[2] = d.dampingRatio; f1[3] = 0.0f; }
+    else { f1[0] = d.referenceAngle; f1[1] = d.lower; f1[2] = d.upper; f1[3] = d.maxMotor; }
+    Vec2 axis = V2(d.localAxisA[0], d.localAxisA[1]);
+    if (d.type == B2G_JOINT_PRISMATIC) Normalize(axis);  // m_localXAxisA.Normalize()
+    if (d.type == B2G_JOINT_PULLEY) {  // ratio, m_constant = lengthA + ratio * lengthB (b2PulleyJoint.cpp:76)
+        f2[0] = d.motorSpeed; f2[1] = d.length + d.motorSpeed * d.maxMotor; f2[2] = 0.0f; f2[3] = 0.0f;
+    } else {
+        f2[0] = d.motorSpeed; f2[1] = axis.x; f2[2] = axis.y; f2[3] = 0.0f;
+    }
+    for (int k = 0; k < 4; ++k) { cols[8 + k] = fb(f1[k]); cols[12 + k] = fb(f2[k]); }
+}
+
 struct FlatWorld {
     std::vector<std::vector<uint32_t>> f;  // per field id, capacity * components words
     int fixtures = 0, proxies = 0, shapeWords = 0, chainVerts = 0;  // slots used
@@ -402,7 +432,12 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
             shapeWordsUsed += (int)words.size();
             shapeDedup[words] = offset;
         }
-        put(out.f[B2GPU_F_FIXTURE_INFO], i, d.body | (sh.type << 16) | ((d.isSensor ? 1 : 0) << 18));
+        put(out.f[B2GPU_F_FIXTURE_INFO], i, d.body | (sh.type << 16) | ((d.isSensor ? 1 : 0) << 18) | (d.density > 0.0f ? kFixtureHasDensity : 0));
+        {   // b2Fixture::GetMassData, kept for b2Body::ResetMassData on the device (SetType, DestroyFixture, CreateFixture)
+            MassData md = ComputeMass(sh, d.density);
+            put(out.f[B2GPU_F_FIXTURE_MASS], (size_t)i * 4, md.mass); put(out.f[B2GPU_F_FIXTURE_MASS], (size_t)i * 4 + 1, md.center.x);
+            put(out.f[B2GPU_F_FIXTURE_MASS], (size_t)i * 4 + 2, md.center.y); put(out.f[B2GPU_F_FIXTURE_MASS], (size_t)i * 4 + 3, md.I);
+        }
         put(out.f[B2GPU_F_FIXTURE_SHAPE], i, offset);
         put(out.f[B2GPU_F_FIXTURE_MAT], (size_t)i * 2, d.friction);
         put(out.f[B2GPU_F_FIXTURE_MAT], (size_t)i * 2 + 1, d.restitution);
@@ -542,7 +577,7 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
             if (bodyOf[0] == bodyOf[1]) { err = "gear joint connects a body to itself"; return B2GPU_ERR_INVALID; }
             const float ratio = d.motorSpeed;
             const float constant = coordinate[0] + ratio * coordinate[1];
-            put(out.f[B2GPU_F_JOINT_I], o, d.type | ((d.collideConnected ? 1 : 0) << 8) | (sideType[0] << 11) | (sideType[1] << 13));
+            put(out.f[B2GPU_F_JOINT_I], o, d.type | ((d.collideConnected ? 1 : 0) << 8) | (sideType[0] << 11) | (sideType[1] << 13) | (j << 16));
             put(out.f[B2GPU_F_JOINT_I], o + 1, bodyOf[0] | (bodyOf[1] << 16));
             put(out.f[B2GPU_F_JOINT_I], o + 2, 0);
             put(out.f[B2GPU_F_JOINT_I], o + 3, bodyOf[2] | (bodyOf[3] << 16));
@@ -564,7 +599,7 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
             // b2Body::GetMass() of body B is read by InitVelocityConstraints (:113) — carried in the record
             const Vec2 target = V2(d.localAnchorA[0], d.localAnchorA[1]);
             const Vec2 lB = MulT(bodies[d.bodyB].xf, target);
-            put(out.f[B2GPU_F_JOINT_I], o, d.type | ((d.collideConnected ? 1 : 0) << 8));
+            put(out.f[B2GPU_F_JOINT_I], o, d.type | ((d.collideConnected ? 1 : 0) << 8) | (j << 16));
             put(out.f[B2GPU_F_JOINT_I], o + 1, d.bodyA | (d.bodyB << 16));
             put(out.f[B2GPU_F_JOINT_I], o + 2, 0); put(out.f[B2GPU_F_JOINT_I], o + 3, 0);
             put(out.f[B2GPU_F_JOINT_F0], o, target.x); put(out.f[B2GPU_F_JOINT_F0], o + 1, target.y);
@@ -573,40 +608,17 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
             put(out.f[B2GPU_F_JOINT_F1], o + 2, d.dampingRatio); put(out.f[B2GPU_F_JOINT_F1], o + 3, bodies[d.bodyB].mass);
             continue;
         }
-        auto& JI = out.f[B2GPU_F_JOINT_I];
-        put(JI, o, d.type | ((d.collideConnected ? 1 : 0) << 8) | ((d.enableLimit ? 1 : 0) << 9) | ((d.enableMotor ? 1 : 0) << 10));
-        put(JI, o + 1, d.bodyA | (d.bodyB << 16));
-        put(JI, o + 2, 0);  // m_limitState = e_inactiveLimit
-        put(JI, o + 3, 0);
-        auto& F0 = out.f[B2GPU_F_JOINT_F0];
-        put(F0, o, d.localAnchorA[0]); put(F0, o + 1, d.localAnchorA[1]); put(F0, o + 2, d.localAnchorB[0]); put(F0, o + 3, d.localAnchorB[1]);
-        auto& F1 = out.f[B2GPU_F_JOINT_F1];
-        if (d.type == B2G_JOINT_DISTANCE) {
-            put(F1, o, d.length); put(F1, o + 1, d.frequencyHz); put(F1, o + 2, d.dampingRatio); put(F1, o + 3, 0.0f);
-        } else if (d.type == B2G_JOINT_ROPE) {
-            put(F1, o, d.length); put(F1, o + 1, 0.0f); put(F1, o + 2, 0.0f); put(F1, o + 3, 0.0f);
-        } else if (d.type == B2G_JOINT_FRICTION) {
-            put(F1, o, d.length); put(F1, o + 1, d.maxMotor); put(F1, o + 2, 0.0f); put(F1, o + 3, 0.0f);
-        } else if (d.type == B2G_JOINT_PULLEY) {
-            put(F1, o, d.localAxisA[0]); put(F1, o + 1, d.localAxisA[1]); put(F1, o + 2, d.lower); put(F1, o + 3, d.upper);
-        } else if (d.type == B2G_JOINT_MOTOR) {
-            put(F1, o, d.length); put(F1, o + 1, d.maxMotor); put(F1, o + 2, d.referenceAngle); put(F1, o + 3, d.frequencyHz);
-        } else if (d.type == B2G_JOINT_WHEEL) {
-            put(F1, o, d.frequencyHz); put(F1, o + 1, d.dampingRatio); put(F1, o + 2, 0.0f); put(F1, o + 3, d.maxMotor);
-        } else if (d.type == B2G_JOINT_WELD) {
-            put(F1, o, d.referenceAngle); put(F1, o + 1, d.frequencyHz); put(F1, o + 2, d.dampingRatio); put(F1, o + 3, 0.0f);
-        } else {
-            put(F1, o, d.referenceAngle); put(F1, o + 1, d.lower); put(F1, o + 2, d.upper); put(F1, o + 3, d.maxMotor);
-        }
-        Vec2 axis = V2(d.localAxisA[0], d.localAxisA[1]);
-        if (d.type == B2G_JOINT_PRISMATIC) Normalize(axis);  // m_localXAxisA.Normalize()
-        auto& F2 = out.f[B2GPU_F_JOINT_F2];
-        if (d.type == B2G_JOINT_PULLEY) {  // ratio, m_constant = lengthA + ratio * lengthB (b2PulleyJoint.cpp:76)
-            put(F2, o, d.motorSpeed); put(F2, o + 1, d.length + d.motorSpeed * d.maxMotor); put(F2, o + 2, 0.0f); put(F2, o + 3, 0.0f);
-        } else {
-            put(F2, o, d.motorSpeed); put(F2, o + 1, axis.x); put(F2, o + 2, axis.y); put(F2, o + 3, 0.0f);
+        uint32_t cols[16];
+        PlainJointColumns(d, cols);
+        put(out.f[B2GPU_F_JOINT_I], o, (int)cols[0] | (j << 16));  // the joint's id = its creation number in the world
+        for (int k = 1; k < 4; ++k) out.f[B2GPU_F_JOINT_I][o + k] = cols[k];
+        for (int k = 0; k < 4; ++k) {
+            out.f[B2GPU_F_JOINT_F0][o + k] = cols[4 + k];
+            out.f[B2GPU_F_JOINT_F1][o + k] = cols[8 + k];
+            out.f[B2GPU_F_JOINT_F2][o + k] = cols[12 + k];
         }
     }
+    put(out.f[B2GPU_F_JOINT_SEQ], 0, nj);
     put(out.f[B2GPU_F_JOINT_COUNT], 0, nj);
     return B2GPU_OK;
 }
@@ -620,6 +632,7 @@ const int kBuildFields[] = {
     B2GPU_F_FIXTURE_FILTER, B2GPU_F_PROXY_FAT, B2GPU_F_PROXY_INFO, B2GPU_F_SHAPE_WORDS, B2GPU_F_CHAIN_VERTS,
     B2GPU_F_JOINT_COUNT, B2GPU_F_JOINT_I, B2GPU_F_JOINT_F0, B2GPU_F_JOINT_F1, B2GPU_F_JOINT_F2, B2GPU_F_JOINT_IMPULSE,
     B2GPU_F_FIXTURE_COUNT, B2GPU_F_SHAPE_WORD_COUNT, B2GPU_F_CHAIN_VERT_COUNT, B2GPU_F_PROXY_FREE_COUNT, B2GPU_F_NEW_FIXTURE,
+    B2GPU_F_JOINT_SEQ, B2GPU_F_FIXTURE_MASS,
     B2GPU_F_PROXY_MOVED,
 };
 
@@ -773,13 +786,14 @@ int b2gpu_batch_build_worlds(b2gpu_batch* batch, const b2g_scene* scenes, int32_
 }
 
 // Spawn record (32-bit words), consumed by k_spawn (b2g_step.cu):
-//   header   world, fixtures, proxies, shapeWords, chainVerts
+//   header   world, fixtures, proxies, shapeWords, chainVerts, target body (-1 = create a new body; else b2Body::CreateFixture
+//            on that existing body: the body part is ignored and the proxies are made on the device under its transform)
 //   body     xf[4] sweep[4] sweep0[4] vel[4] mass[4] damp[4] flags
-//   fixture  info (body field = 0), shape offset (relative), friction, restitution, filter[2]        x fixtures
+//   fixture  info (body field = 0), shape offset (relative), friction, restitution, filter[2], mass data[4]   x fixtures
 //   proxy    fat AABB[4], fixture (relative) | child << 16                                          x proxies
 //   shape table words (chain entries hold a relative first vertex), chain vertices xy
-int b2gpu_batch_create_bodies(b2gpu_batch* batch, const b2gpu_spawn* spawns, int32_t count, const b2g_fixture_def* fixtures,
-                              const float* vertices, int32_t* bodyIndices) {
+static int SpawnOrAttach(b2gpu_batch* batch, const b2gpu_spawn* spawns, const int32_t* targets, int32_t count,
+                         const b2g_fixture_def* fixtures, const float* vertices, int32_t* bodyIndices) {
     if (!batch || count < 0 || (count > 0 && (!spawns || !bodyIndices))) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
     if (count == 0) return B2GPU_OK;
     std::vector<std::pair<int, int>> shapes(B2GPU_F_COUNT);
@@ -818,12 +832,14 @@ int b2gpu_batch_create_bodies(b2gpu_batch* batch, const b2gpu_spawn* spawns, int
         auto push = [&](uint32_t v) { words.push_back(v); };
         auto pushField = [&](int id, size_t first, size_t nwords) { for (size_t k = 0; k < nwords; ++k) push(fw.f[id][first + k]); };
         push((uint32_t)sp.world); push((uint32_t)fw.fixtures); push((uint32_t)fw.proxies); push((uint32_t)fw.shapeWords); push((uint32_t)fw.chainVerts);
+        push((uint32_t)(targets ? targets[order[n]] : -1));
         pushField(B2GPU_F_BODY_XF, 0, 4); pushField(B2GPU_F_BODY_SWEEP, 0, 4); pushField(B2GPU_F_BODY_SWEEP0, 0, 4);
         pushField(B2GPU_F_BODY_VEL, 0, 4); pushField(B2GPU_F_BODY_MASS, 0, 4); pushField(B2GPU_F_BODY_DAMP, 0, 4);
         pushField(B2GPU_F_BODY_FLAGS, 0, 1);
         for (int f = 0; f < fw.fixtures; ++f) {
             pushField(B2GPU_F_FIXTURE_INFO, f, 1); pushField(B2GPU_F_FIXTURE_SHAPE, f, 1);
             pushField(B2GPU_F_FIXTURE_MAT, (size_t)f * 2, 2); pushField(B2GPU_F_FIXTURE_FILTER, (size_t)f * 2, 2);
+            pushField(B2GPU_F_FIXTURE_MASS, (size_t)f * 4, 4);
         }
         for (int q = 0; q < fw.proxies; ++q) { pushField(B2GPU_F_PROXY_FAT, (size_t)q * 4, 4); pushField(B2GPU_F_PROXY_INFO, q, 1); }
         pushField(B2GPU_F_SHAPE_WORDS, 0, fw.shapeWords);
@@ -834,6 +850,59 @@ int b2gpu_batch_create_bodies(b2gpu_batch* batch, const b2gpu_spawn* spawns, int
     int rc = b2gpu_batch_spawn_records(batch, words.data(), offsets.data(), count, sortedIdx.data());
     if (rc != B2GPU_OK) return rc;
     for (int n = 0; n < count; ++n) bodyIndices[order[n]] = sortedIdx[n];
+    return B2GPU_OK;
+}
+
+int b2gpu_batch_create_bodies(b2gpu_batch* batch, const b2gpu_spawn* spawns, int32_t count, const b2g_fixture_def* fixtures,
+                              const float* vertices, int32_t* bodyIndices) {
+    return SpawnOrAttach(batch, spawns, nullptr, count, fixtures, vertices, bodyIndices);
+}
+
+// b2Body::CreateFixture on bodies that exist already: the same records as a spawn, aimed at an existing body.
+int b2gpu_batch_create_fixtures(b2gpu_batch* batch, const b2gpu_attach* attach, int32_t count, const b2g_fixture_def* fixtures,
+                                const float* vertices, int32_t* fixtureIndices) {
+    if (!batch || count < 0 || (count > 0 && (!attach || !fixtureIndices))) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    std::vector<b2gpu_spawn> spawns((size_t)count);
+    std::vector<int32_t> targets((size_t)count);
+    for (int i = 0; i < count; ++i) {
+        if (attach[i].body < 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "create_fixtures: negative body index");
+        memset(&spawns[i], 0, sizeof(b2gpu_spawn));
+        spawns[i].world = attach[i].world;
+        spawns[i].firstFixture = attach[i].firstFixture;
+        spawns[i].fixtureCount = attach[i].fixtureCount;
+        spawns[i].body.type = B2G_DYNAMIC_BODY;  // a stand-in: shapes and mass data do not depend on the body
+        spawns[i].body.flags = B2G_BD_ACTIVE | B2G_BD_AWAKE;
+        spawns[i].body.gravityScale = 1.0f;
+        targets[i] = attach[i].body;
+    }
+    return SpawnOrAttach(batch, spawns.data(), targets.data(), count, fixtures, vertices, fixtureIndices);
+}
+
+// b2World::CreateJoint on running worlds: the def's columns, grouped by world, applied by k_create_joints.
+int b2gpu_batch_create_joints(b2gpu_batch* batch, const int32_t* worlds, const b2g_joint_def* defs, int32_t count, int32_t* jointIds) {
+    if (!batch || count < 0 || (count > 0 && (!worlds || !defs || !jointIds))) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    if (count == 0) return B2GPU_OK;
+    std::vector<int> order(count);
+    for (int i = 0; i < count; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return worlds[a] < worlds[b]; });
+    std::vector<uint32_t> words((size_t)count * 21);
+    for (int n = 0; n < count; ++n) {
+        const b2g_joint_def& d = defs[order[n]];
+        if (d.type == B2G_JOINT_GEAR || d.type == B2G_JOINT_MOUSE)
+            return b2gpu_host_set_error(B2GPU_ERR_UNSUPPORTED, "gear and mouse joints read body state when they are constructed: create them with the scene");
+        if (d.type < B2G_JOINT_REVOLUTE || d.type > B2G_JOINT_MOTOR)
+            return b2gpu_host_set_error(B2GPU_ERR_UNSUPPORTED, "unknown joint type");
+        if (d.bodyA < 0 || d.bodyB < 0 || d.bodyA > 0xffff || d.bodyB > 0xffff || d.bodyA == d.bodyB)
+            return b2gpu_host_set_error(B2GPU_ERR_INVALID, "joint references a body that does not exist (or connects a body to itself)");
+        uint32_t* r = &words[(size_t)n * 21];
+        r[0] = (uint32_t)worlds[order[n]];
+        PlainJointColumns(d, r + 1);
+        for (int k = 17; k < 21; ++k) r[k] = 0;  // accumulated impulses start at zero
+    }
+    std::vector<int32_t> sorted(count);
+    int rc = b2gpu_batch_joint_records(batch, words.data(), count, sorted.data());
+    if (rc != B2GPU_OK) return rc;
+    for (int n = 0; n < count; ++n) jointIds[order[n]] = sorted[n];
     return B2GPU_OK;
 }
 

@@ -303,9 +303,44 @@ __device__ __forceinline__ int UpdateOne(const Arena& A, int tile, int lane, int
            (m.pointCount << kResCountShift) | (pointCountOld << kResOldCountShift);
 }
 
-__device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, int k) {
+// b2ContactFilter::ShouldCollide — Dynamics/b2WorldCallbacks.cpp:26-39
+__device__ __forceinline__ bool FilterShouldCollide(int2 fa, int2 fb) {
+    int groupA = fa.y, groupB = fb.y;
+    if (groupA == groupB && groupA != 0) return groupA > 0;
+    int catA = fa.x & 0xffff, maskA = (fa.x >> 16) & 0xffff;
+    int catB = fb.x & 0xffff, maskB = (fb.x >> 16) & 0xffff;
+    return (maskA & catB) != 0 && (catA & maskB) != 0;
+}
+
+// b2Body::ShouldCollide (b2Body.cpp:395-416): at least one dynamic body, and no joint between the two bodies that has
+// collideConnected == false
+__device__ __forceinline__ bool BodiesShouldCollide(const Arena& A, int tile, int lane, int bodyA, int bodyB) {
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    if ((bodyFlags[bodyA] & kBodyTypeMask) != B2G_DYNAMIC_BODY && (bodyFlags[bodyB] & kBodyTypeMask) != B2G_DYNAMIC_BODY) return false;
+    if (A.hasJoints) {
+        Col<int4> jI = col(A.jointI, tile, A.NJ, lane);
+        const int nj = A.jointCount[(size_t)tile * kTile + lane];
+        const int ab = bodyA | (bodyB << 16), ba = bodyB | (bodyA << 16);
+        for (int j = 0; j < nj; ++j) {
+            const int4 ji = jI[j];
+            if ((ji.y == ab || ji.y == ba) && (ji.x & (1 << 8)) == 0) return false;
+        }
+    }
+    return true;
+}
+
+// The e_filterFlag branch of b2ContactManager::Collide (b2ContactManager.cpp:124-146) for a flagged contact: false = the
+// contact is to be destroyed.  (Kept out of line: contacts are flagged by a handful of between-step edits only.)
+__device__ __noinline__ bool RefilterKeeps(const Arena* Ap, int tile, int lane, int4 a) {
+    const Arena& A = *Ap;
+    if (!BodiesShouldCollide(A, tile, lane, (a.y >> 16) & 0xffff, a.y & 0xffff)) return false;  // bodyB->ShouldCollide(bodyA)
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    Col<int2> fixtureFilter = col(A.fixtureFilter, tile, A.NF, lane);
+    return FilterShouldCollide(fixtureFilter[proxyInfo[a.x & 0xffff] & 0xffff], fixtureFilter[proxyInfo[(a.x >> 16) & 0xffff] & 0xffff]);
+}
+
+__device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, int k, const int4 a0) {
     Col<int4> cA = col(A.contactA, tile, A.NC, lane);
-    const int4 a0 = cA[k];
     const int proxyA = a0.x & 0xffff, proxyB = (a0.x >> 16) & 0xffff;
     Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
     if (!FatOverlap(proxyFat[proxyA], proxyFat[proxyB])) {
@@ -316,6 +351,22 @@ __device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, in
         return kResDead | ((a0.z & kContactTouching) ? kResWasTouching : 0) | (pointCountOld << kResOldCountShift);
     }
     return UpdateOne(A, tile, lane, k, a0);
+}
+
+// A contact flagged for filtering is looked at before anything else, awake or not (b2ContactManager.cpp:124-146).
+// Returns true when it is to be destroyed: marked dead like a contact whose fat AABBs parted, `res` says so to the
+// list-order pass.  Otherwise the flag is cleared and the contact goes on as usual.
+__device__ __forceinline__ bool RefilterOne(const Arena& A, int tile, int lane, int k, int4& a0, int& res) {
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    if (!RefilterKeeps(&A, tile, lane, a0)) {
+        a0.z |= kContactDead;
+        cA[k] = a0;
+        res = kResDead | ((a0.z & kContactTouching) ? kResWasTouching : 0) | (((a0.w >> 8) & 3) << kResOldCountShift);
+        return true;
+    }
+    a0.z &= ~kContactFilter;
+    cA[k] = a0;
+    return false;
 }
 
 constexpr int kCollideWarps = 8;
@@ -379,14 +430,16 @@ __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_
         Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
         for (int k = warp; k < nMax; k += kCollideWarps) {
             if (k >= n) continue;
-            const int4 a0 = cA[k];
+            int4 a0 = cA[k];
             const int bfA = bodyFlags[a0.y & 0xffff], bfB = bodyFlags[(a0.y >> 16) & 0xffff];
             const bool activeA = (bfA & kBodyAwake) && (bfA & kBodyTypeMask) != B2G_STATIC_BODY;
             const bool activeB = (bfB & kBodyAwake) && (bfB & kBodyTypeMask) != B2G_STATIC_BODY;
             int res = 0;
-            if (activeA || activeB) {
+            if ((a0.z & kContactFilter) && RefilterOne(A, tile, lane, k, a0, res)) {
+                summary |= 3;
+            } else if (activeA || activeB) {
                 if (!FatOverlap(proxyFat[a0.x & 0xffff], proxyFat[(a0.x >> 16) & 0xffff])) {
-                    res = CollideOne(A, tile, lane, k);  // the destroy branch
+                    res = CollideOne(A, tile, lane, k, a0);  // the destroy branch
                     summary |= 3;
                 } else {
                     const int cls = CollideClass(a0);
@@ -426,13 +479,16 @@ __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_
 #endif
     for (int k = warp; k < nMax; k += kCollideWarps) {
         if (k >= n) continue;
-        const int bodies = cA[k].y;
+        int4 a0 = cA[k];
+        const int bodies = a0.y;
         const int bfA = bodyFlags[bodies & 0xffff], bfB = bodyFlags[(bodies >> 16) & 0xffff];
         const bool activeA = (bfA & kBodyAwake) && (bfA & kBodyTypeMask) != B2G_STATIC_BODY;
         const bool activeB = (bfB & kBodyAwake) && (bfB & kBodyTypeMask) != B2G_STATIC_BODY;
         int res = 0;
-        if (activeA || activeB) {
-            res = CollideOne(A, tile, lane, k);
+        if ((a0.z & kContactFilter) && RefilterOne(A, tile, lane, k, a0, res)) {
+            summary |= 3;
+        } else if (activeA || activeB) {
+            res = CollideOne(A, tile, lane, k, a0);
             const bool changed = ((res & kResWasTouching) != 0) != ((res & kResTouching) != 0);
             if ((res & kResDead) || changed) summary |= 3;
             if (A.eventMask) summary |= 1;
@@ -465,7 +521,7 @@ __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_
             const bool activeA = (bfA & kBodyAwake) && (bfA & kBodyTypeMask) != B2G_STATIC_BODY;
             const bool activeB = (bfB & kBodyAwake) && (bfB & kBodyTypeMask) != B2G_STATIC_BODY;
             if (!activeA && !activeB) continue;
-            res = CollideOne(A, tile, lane, k);
+            res = CollideOne(A, tile, lane, k, a);
             A.topoDirty[ws] = 1;
         }
         const int pointCount = (res >> kResCountShift) & 3, pointCountOld = (res >> kResOldCountShift) & 3;
@@ -1350,15 +1406,6 @@ __global__ void __launch_bounds__(128) k_solve(Arena A, float h, int velIters, i
 // =================================================================================================
 // k_sync_pairs
 // =================================================================================================
-// b2ContactFilter::ShouldCollide — Dynamics/b2WorldCallbacks.cpp:26-39
-__device__ __forceinline__ bool FilterShouldCollide(int2 fa, int2 fb) {
-    int groupA = fa.y, groupB = fb.y;
-    if (groupA == groupB && groupA != 0) return groupA > 0;
-    int catA = fa.x & 0xffff, maskA = (fa.x >> 16) & 0xffff;
-    int catB = fb.x & 0xffff, maskB = (fb.x >> 16) & 0xffff;
-    return (maskA & catB) != 0 && (catA & maskB) != 0;
-}
-
 // b2Contact::s_registers (b2Contact.cpp:42-76): 0 = no contact class, 1 = primary, 2 = swapped
 __device__ __forceinline__ int ContactRegister(int t1, int t2) {
     if (t2 == B2G_SHAPE_CIRCLE) return 1;                                   // circle/edge/polygon/chain vs circle
@@ -1413,16 +1460,8 @@ __device__ __noinline__ void AddPair(PairCtx& c, int proxyA, int proxyB, bool kn
     int bfA = c.bodyFlags[bodyA], bfB = c.bodyFlags[bodyB];
     // b2Body::ShouldCollide (b2Body.cpp:395-416): at least one dynamic body, and no joint between the two bodies that
     // has collideConnected == false
-    if ((bfA & kBodyTypeMask) != B2G_DYNAMIC_BODY && (bfB & kBodyTypeMask) != B2G_DYNAMIC_BODY) return;
-    if (c.A.hasJoints) {
-        Col<int4> jI = col(c.A.jointI, c.tile, c.A.NJ, c.lane);
-        const int nj = c.A.jointCount[c.ws];
-        const int ab = bodyA | (bodyB << 16), ba = bodyB | (bodyA << 16);
-        for (int j = 0; j < nj; ++j) {
-            const int4 ji = jI[j];
-            if ((ji.y == ab || ji.y == ba) && (ji.x & (1 << 8)) == 0) return;
-        }
-    }
+    (void)bfA; (void)bfB;
+    if (!BodiesShouldCollide(c.A, c.tile, c.lane, bodyA, bodyB)) return;
     if (!FilterShouldCollide(c.fixtureFilter[fixtureA], c.fixtureFilter[fixtureB])) return;
     int tA = (fiA >> 16) & 3, tB = (fiB >> 16) & 3;
     int reg = ContactRegister(tA, tB);
@@ -1476,6 +1515,7 @@ __device__ __forceinline__ bool SynchronizeProxy(const Arena& A, int tile, int l
     Vec2 lo = Min(lo1, lo2), hi = Max(hi1, hi2);
     Vec2 displacement = xf2.p - xf1.p;
     float4 fat = proxyFat[p];
+    if (fat.x > fat.z) return false;  // a freed proxy slot (destroyed fixture, deactivated body): it stays out of the broad phase
     // b2AABB::Contains
     bool contains = fat.x <= lo.x && fat.y <= lo.y && hi.x <= fat.z && hi.y <= fat.w;
     if (contains) return false;

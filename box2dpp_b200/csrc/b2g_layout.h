@@ -37,6 +37,8 @@ enum : int {
     kBodyActive = 1 << 7,
     kBodyToiIsland = 1 << 8,  // e_islandFlag as b2World::SolveTOI uses it (kBodyIsland keeps the discrete islands)
     kBodyToiMoved = 1 << 9,   // displaced by the current TOI sub-step (temporary)
+    kFixtureHasDensity = 1 << 20, // fixtureInfo: m_density > 0 (b2Body::ResetMassData skips the others)
+    kFixtureDestroyed = 1 << 19, // fixtureInfo: b2Body::DestroyFixture / DestroyBody removed the fixture (the slot is never reused)
     kBodyDestroyed = 1 << 10, // b2World::DestroyBody was called: the slot is a tombstone (never awake, never active)
 };
 // contact flag bits (Box2D/Dynamics/Contacts/b2Contact.h:155-174)
@@ -101,6 +103,7 @@ struct Arena {
     int* fixtureShape;   // word offset into shapeWords
     float2* fixtureMat;  // friction, restitution
     int2* fixtureFilter; // categoryBits | maskBits << 16, groupIndex
+    float4* fixtureMass; // b2Fixture::GetMassData: mass, center.xy, I (mass 0 = density 0: b2Body::ResetMassData skips it)
 
     // ---- proxies [tile][NP][lane] (creation order == ascending tree id) ----
     float4* proxyFat;    // fat AABB lo.xy hi.xy (b2TreeNode::aabb)
@@ -123,6 +126,7 @@ struct Arena {
 
     // ---- joints [tile][NJ][lane], creation order (b2World::m_jointList is that array walked backwards) ----
     int* jointCount;     // [tile][lane]
+    int* jointSeq;       // [tile][lane] joints created so far = the next joint id (the id rides in jointI.x bits 16-31)
     int4* jointI;        // type | collideConnected << 8 | enableLimit << 9 | enableMotor << 10, bodyA | bodyB << 16, m_limitState, 0
     float4* jointF0;     // localAnchorA.xy, localAnchorB.xy
     float4* jointF1;     // referenceAngle, lower, upper, maxMotorTorque|Force   (distance: length, frequencyHz, dampingRatio)

@@ -141,6 +141,289 @@ __global__ void k_read_body_state(Arena A, float4* __restrict__ out) {
     o[1] = make_float4(v.x, v.y, v.z, sw.w);
 }
 
+// ---- building blocks of the between-step edits (k_body_commands, k_attach_fixtures, k_create_joints) ----
+
+// b2Contact::FlagForFiltering on every contact between two bodies (b2World.cpp:255-263, 342-358)
+__device__ __noinline__ void FlagContactsBetween(const Arena& A, int tile, int lane, int bodyA, int bodyB) {
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+    const int nc = A.contactCount[(size_t)tile * kTile + lane];
+    const int ab = bodyA | (bodyB << 16), ba = bodyB | (bodyA << 16);
+    for (int k = 0; k < nc; ++k) {
+        int4 a = cA[k];
+        if (a.y != ab && a.y != ba) continue;
+        a.z |= kContactFilter;
+        cA[k] = a;
+    }
+}
+
+// b2ContactManager::Destroy (EndContact if touching, b2ContactManager.cpp:45-105) + b2Contact::Destroy (wake both bodies if
+// the manifold had points, b2Contact.cpp:103-122) for the contacts of body b — only those of fixture `fixture` when it
+// is >= 0 — in the body's contact-list order (newest first); then a stable erase keeps every list's order.
+__device__ __noinline__ void DestroyContactsOf(const Arena& A, int tile, int lane, int b, int fixture) {
+    const size_t ws = (size_t)tile * kTile + lane;
+    Col<int4> cA = col(A.contactA, tile, A.NC, lane), cK = col(A.contactK, tile, A.NC, lane);
+    Col<int2> cS = col(A.contactS, tile, A.NC, lane);
+    Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane), cP1 = col(A.contactP1, tile, A.NC, lane);
+    Col<float4> cN = col(A.contactN, tile, A.NC, lane);
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane);
+    EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws], A.NE, A.eventMask};
+    const int nc = A.contactCount[ws];
+    bool any = false;
+    for (int k = nc - 1; k >= 0; --k) {
+        int4 a = cA[k];
+        const int kA = a.y & 0xffff, kB = (a.y >> 16) & 0xffff;
+        if (kA != b && kB != b) continue;
+        const int pa = proxyInfo[a.x & 0xffff], pb = proxyInfo[(a.x >> 16) & 0xffff];
+        if (fixture >= 0 && (pa & 0xffff) != fixture && (pb & 0xffff) != fixture) continue;
+        any = true;
+        const int pointCount = (a.w >> 8) & 0xff;
+        if (a.z & kContactTouching)
+            ev.push(kEventEnd, pa & 0xffff, (pa >> 16) & 0xffff, pb & 0xffff, (pb >> 16) & 0xffff, pointCount, make_float4(0, 0, 0, 0));
+        if (pointCount > 0 && (a.z & kContactSensor) == 0) {
+            WakeBody(bodyFlags, bodySweep, kA);
+            WakeBody(bodyFlags, bodySweep, kB);
+        }
+        a.z |= kContactDead;
+        cA[k] = a;
+    }
+    if (!any) return;
+    A.topoDirty[ws] = 1;
+    int wpos = 0;
+    for (int k = 0; k < nc; ++k) {
+        const int4 a = cA[k];
+        if (a.z & kContactDead) continue;
+        if (wpos != k) { cA[wpos] = a; cK[wpos] = cK[k]; cS[wpos] = cS[k]; cP0[wpos] = cP0[k]; cP1[wpos] = cP1[k]; cN[wpos] = cN[k]; }
+        ++wpos;
+    }
+    A.contactCount[ws] = wpos;
+}
+
+// b2Fixture::DestroyProxies (b2Fixture.cpp:141-152): an empty fat AABB never overlaps anything, the proxy leaves the move
+// buffer (b2BroadPhase::UnBufferMove) and its slot goes onto the LIFO free stack (b2DynamicTree::FreeNode), children ascending.
+__device__ __noinline__ void DestroyFixtureProxies(const Arena& A, int tile, int lane, int fx) {
+    const size_t ws = (size_t)tile * kTile + lane;
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
+    Col<int> proxyFree = col(A.proxyFree, tile, A.NP, lane);
+    const int np = A.proxyCount[ws];
+    int nfree = A.proxyFreeCount[ws];
+    // the proxies of one fixture were allocated in ascending child order, but (after slot reuse) not in ascending slots
+    int children = 0;
+    for (int p = 0; p < np; ++p)
+        if ((proxyInfo[p] & 0xffff) == fx && proxyFat[p].x <= proxyFat[p].z) ++children;
+    for (int child = 0, left = children; left > 0 && child < 65536; ++child) {
+        for (int p = 0; p < np; ++p) {
+            const int pi = proxyInfo[p];
+            if ((pi & 0xffff) != fx || ((pi >> 16) & 0xffff) != child || proxyFat[p].x > proxyFat[p].z) continue;
+            proxyFat[p] = make_float4(kMaxFloat, kMaxFloat, -kMaxFloat, -kMaxFloat);
+            proxyMoved[p] = 0;
+            proxyFree[nfree++] = p;
+            --left;
+            break;
+        }
+    }
+    A.proxyFreeCount[ws] = nfree;
+}
+
+// b2Fixture::CreateProxies (b2Fixture.cpp:122-139): per child the shape's AABB under xf, fattened by b2_aabbExtension
+// (b2DynamicTree::CreateProxy), the most recently freed proxy id or a fresh one, a buffered move.
+__device__ __noinline__ void CreateFixtureProxies(const Arena& A, int tile, int lane, int fx, Xf xf) {
+    const size_t ws = (size_t)tile * kTile + lane;
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
+    Col<int> proxyFree = col(A.proxyFree, tile, A.NP, lane);
+    Col<float2> chainVerts = col(A.chainVerts, tile, A.NV, lane);
+    const int fi = col(A.fixtureInfo, tile, A.NF, lane)[fx];
+    const int shapeType = (fi >> 16) & 3;
+    const float* sw = A.shapeWords + ((size_t)tile * A.NS + col(A.fixtureShape, tile, A.NF, lane)[fx]) * kTile + lane;
+    // b2Shape::GetChildCount: a chain has count - 1 children (its table entry holds the vertex count), everything else one
+    const int children = shapeType == B2G_SHAPE_CHAIN ? __float_as_int(sw[2 * kTile]) - 1 : 1;
+    int np = A.proxyCount[ws], nfree = A.proxyFreeCount[ws];
+    for (int child = 0; child < children; ++child) {
+        if (nfree == 0 && np >= A.NP) { A.status[ws] |= B2GPU_STATUS_SPAWN_OVERFLOW; break; }
+        const int slot = nfree > 0 ? proxyFree[--nfree] : np++;
+        Vec2 lo, hi;
+        ShapeAABB(sw, shapeType, chainVerts, child, xf, &lo, &hi);
+        const Vec2 r = V2(kAabbExtension, kAabbExtension);
+        lo = lo - r;
+        hi = hi + r;
+        proxyFat[slot] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        proxyInfo[slot] = fx | (child << 16);
+        proxyMoved[slot] = 1;
+    }
+    A.proxyCount[ws] = np;
+    A.proxyFreeCount[ws] = nfree;
+    A.pendingMoves[ws] = 1;
+}
+
+// b2BroadPhase::TouchProxy = BufferMove for every proxy of a fixture
+__device__ __noinline__ void TouchFixtureProxies(const Arena& A, int tile, int lane, int fx) {
+    const size_t ws = (size_t)tile * kTile + lane;
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
+    Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
+    const int np = A.proxyCount[ws];
+    for (int p = 0; p < np; ++p) {
+        if ((proxyInfo[p] & 0xffff) != fx || proxyFat[p].x > proxyFat[p].z) continue;
+        proxyMoved[p] = 1;
+        A.pendingMoves[ws] = 1;
+    }
+}
+
+// b2Body::SynchronizeFixtures (b2Body.cpp:442-453) outside a step
+__device__ __noinline__ void SynchronizeBodyFixtures(const Arena& A, int tile, int lane, int b) {
+    const size_t ws = (size_t)tile * kTile + lane;
+    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+    Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+    const int np = A.proxyCount[ws];
+    for (int p = 0; p < np; ++p) {
+        const int pi = proxyInfo[p];
+        const int fi = fixtureInfo[pi & 0xffff];
+        if ((fi & 0xffff) != b || (fi & kFixtureDestroyed)) continue;
+        if (SynchronizeProxy(A, tile, lane, p, pi & 0xffff, (pi >> 16) & 0xffff, fi, b)) A.pendingMoves[ws] = 1;
+    }
+}
+
+// The tail both b2Body::ResetMassData and SetMassData share: the centre of mass moves, the velocity follows it
+__device__ __forceinline__ void MoveCenterOfMass(const Arena& A, int tile, int lane, int b, float invMass, float invI, Vec2 localCenter) {
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane), bodySweep0 = col(A.bodySweep0, tile, A.NB, lane);
+    Col<float4> bodyVel = col(A.bodyVel, tile, A.NB, lane);
+    const Xf xf = LoadXf(col(A.bodyXf, tile, A.NB, lane), b);
+    col(A.bodyMass, tile, A.NB, lane)[b] = make_float4(invMass, invI, localCenter.x, localCenter.y);
+    float4 sw = bodySweep[b];
+    const Vec2 oldCenter = V2(sw.x, sw.y);
+    const Vec2 c = Mul(xf, localCenter);
+    sw.x = c.x; sw.y = c.y;
+    bodySweep[b] = sw;
+    float4 s0 = bodySweep0[b];
+    s0.x = c.x; s0.y = c.y;
+    bodySweep0[b] = s0;
+    float4 v = bodyVel[b];
+    const Vec2 lv = V2(v.x, v.y) + Cross(v.z, c - oldCenter);
+    v.x = lv.x; v.y = lv.y;
+    bodyVel[b] = v;
+}
+
+// b2Body::ResetMassData — Dynamics/b2Body.cpp:283-352: the fixtures' mass data summed in fixture-list order (newest first)
+__device__ __noinline__ void ResetMassData(const Arena& A, int tile, int lane, int b) {
+    const size_t ws = (size_t)tile * kTile + lane;
+    Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane), bodySweep0 = col(A.bodySweep0, tile, A.NB, lane);
+    const int f = col(A.bodyFlags, tile, A.NB, lane)[b];
+    const int type = f & kBodyTypeMask;
+    if (type == B2G_STATIC_BODY || type == B2G_KINEMATIC_BODY) {
+        const float4 xf = col(A.bodyXf, tile, A.NB, lane)[b];
+        col(A.bodyMass, tile, A.NB, lane)[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 sw = bodySweep[b];
+        sw.x = xf.x; sw.y = xf.y;
+        bodySweep[b] = sw;
+        bodySweep0[b] = make_float4(xf.x, xf.y, sw.z, bodySweep0[b].w);
+        return;
+    }
+    Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+    Col<float4> fixtureMass = col(A.fixtureMass, tile, A.NF, lane);
+    float mass = 0.0f, I = 0.0f;
+    Vec2 localCenter = V2(0.0f, 0.0f);
+    for (int fx = A.fixtureCount[ws] - 1; fx >= 0; --fx) {
+        const int fi = fixtureInfo[fx];
+        if ((fi & 0xffff) != b || (fi & kFixtureDestroyed)) continue;
+        const float4 md = fixtureMass[fx];
+        if ((fi & kFixtureHasDensity) == 0) continue;  // if (f->m_density == 0.0f) continue;
+        mass += md.x;
+        localCenter = localCenter + md.x * V2(md.y, md.z);
+        I += md.w;
+    }
+    float invMass, invI;
+    if (mass > 0.0f) {
+        invMass = Div(1.0f, mass);
+        localCenter = invMass * localCenter;
+    } else {
+        mass = 1.0f;
+        invMass = 1.0f;
+    }
+    if (I > 0.0f && (f & kBodyFixedRotation) == 0) {
+        I -= mass * Dot(localCenter, localCenter);
+        invI = Div(1.0f, I);
+    } else {
+        invI = 0.0f;
+    }
+    MoveCenterOfMass(A, tile, lane, b, invMass, invI, localCenter);
+}
+
+// b2Body::CreateFixture on an existing body (b2Body.cpp:168-214), one call per fixture of the record, in record order: the
+// fixture becomes the head of the body's fixture list, gets its proxies under the body's CURRENT transform if the body is
+// active, the mass data is reset if it has density, e_newFixture is raised.  Record layout: k_spawn.
+__device__ __noinline__ void AttachFixtures(const Arena& A, int tile, int lane, int b, const uint32_t* r, int rf, int rs, int rv) {
+    const size_t ws = (size_t)tile * kTile + lane;
+    const int rp = (int)r[2];
+    const int nf = A.fixtureCount[ws], ns = A.shapeWordCount[ws], nv = A.chainVertCount[ws];
+    const uint32_t* p = r + 6 + 25;                       // the body part of the record is not used
+    const uint32_t* shapeWords = p + (size_t)rf * 10 + (size_t)rp * 5;
+    float* sw = A.shapeWords + ((size_t)tile * A.NS + ns) * kTile + lane;
+    for (int k = 0; k < rs; ++k) sw[(size_t)k * kTile] = __uint_as_float(shapeWords[k]);
+    Col<float2> cv = col(A.chainVerts, tile, A.NV, lane);
+    for (int k = 0; k < rv; ++k) cv[nv + k] = make_float2(__uint_as_float(shapeWords[rs + 2 * k]), __uint_as_float(shapeWords[rs + 2 * k + 1]));
+    A.shapeWordCount[ws] = ns + rs;
+    A.chainVertCount[ws] = nv + rv;
+    const int bf = col(A.bodyFlags, tile, A.NB, lane)[b];
+    const Xf xf = LoadXf(col(A.bodyXf, tile, A.NB, lane), b);
+    for (int f = 0; f < rf; ++f, p += 10) {
+        const int info = (int)p[0], shapeOff = (int)p[1] + ns, fx = nf + f;
+        col(A.fixtureInfo, tile, A.NF, lane)[fx] = (info & ~0xffff) | b;
+        col(A.fixtureShape, tile, A.NF, lane)[fx] = shapeOff;
+        col(A.fixtureMat, tile, A.NF, lane)[fx] = make_float2(__uint_as_float(p[2]), __uint_as_float(p[3]));
+        col(A.fixtureFilter, tile, A.NF, lane)[fx] = make_int2((int)p[4], (int)p[5]);
+        col(A.fixtureMass, tile, A.NF, lane)[fx] = make_float4(__uint_as_float(p[6]), __uint_as_float(p[7]), __uint_as_float(p[8]), __uint_as_float(p[9]));
+        if (((info >> 16) & 3) == B2G_SHAPE_CHAIN) {  // the table entry holds its first vertex relative to the record
+            float* e = A.shapeWords + ((size_t)tile * A.NS + shapeOff + 1) * kTile + lane;
+            *e = __int_as_float(__float_as_int(*e) + nv);
+        }
+        A.fixtureCount[ws] = fx + 1;
+        if (bf & kBodyActive) CreateFixtureProxies(A, tile, lane, fx, xf);
+        if (info & kFixtureHasDensity) ResetMassData(A, tile, lane, b);
+    }
+    A.newFixture[ws] = 1;
+    A.topoDirty[ws] = 1;
+}
+
+// b2World::CreateJoint on a running world (b2World.cpp:205-265).  21 words per record: world, then the joint's five
+// 4-word columns (the id bits of word 1 are filled in here).  Records are grouped by world, applied in order.
+__global__ void k_create_joints(Arena A, const uint32_t* __restrict__ words, int count, int* __restrict__ outId) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int w = (int)words[(size_t)i * 21];
+    if (i > 0 && (int)words[(size_t)(i - 1) * 21] == w) return;
+    const int tile = w >> 5, lane = w & 31;
+    const size_t ws = (size_t)tile * kTile + lane;
+    Col<int> bodyFlags = col(A.bodyFlags, tile, A.NB, lane);
+    for (; i < count && (int)words[(size_t)i * 21] == w; ++i) {
+        const uint32_t* r = words + (size_t)i * 21 + 1;
+        const int nj = A.jointCount[ws], nb = A.bodyCount[ws];
+        const int bA = (int)(r[1] & 0xffff), bB = (int)(r[1] >> 16);
+        if (!A.hasJoints || nj >= A.NJ) { A.status[ws] |= B2GPU_STATUS_SPAWN_OVERFLOW; outId[i] = -1; continue; }
+        if (bA >= nb || bB >= nb || bA == bB || (bodyFlags[bA] & kBodyDestroyed) || (bodyFlags[bB] & kBodyDestroyed)) {
+            A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
+            outId[i] = -1;
+            continue;
+        }
+        const int id = A.jointSeq[ws];
+        auto f4 = [&](float4* base, int k) {
+            col(base, tile, A.NJ, lane)[nj] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+        };
+        col(A.jointI, tile, A.NJ, lane)[nj] = make_int4((int)((r[0] & 0xffff) | ((uint32_t)id << 16)), (int)r[1], (int)r[2], (int)r[3]);
+        f4(A.jointF0, 1); f4(A.jointF1, 2); f4(A.jointF2, 3); f4(A.jointImp, 4);
+        A.jointCount[ws] = nj + 1;
+        A.jointSeq[ws] = id + 1;
+        A.topoDirty[ws] = 1;
+        // if the joint prevents collisions, then flag any contacts for filtering (b2World.cpp:255-263)
+        if ((r[0] & (1u << 8)) == 0) FlagContactsBetween(A, tile, lane, bA, bB);
+        outId[i] = id;
+    }
+}
+
 // b2World::CreateBody + b2Body::CreateFixture after the first step, from records evaluated by the host layer
 // (b2g_host.cpp b2gpu_batch_create_bodies).  Records are grouped by world; the thread that owns a world's first record
 // applies that world's records in order.
@@ -155,16 +438,27 @@ __global__ void k_spawn(Arena A, const uint32_t* __restrict__ words, const long 
     for (; i < count && (int)words[offsets[i]] == w; ++i) {
         const uint32_t* r = words + offsets[i];
         const int rf = (int)r[1], rp = (int)r[2], rs = (int)r[3], rv = (int)r[4];
+        const int target = (int)r[5];  // -1: a new body; else b2Body::CreateFixture on this existing body
         const int nb = A.bodyCount[ws], nf = A.fixtureCount[ws], np = A.proxyCount[ws], ns = A.shapeWordCount[ws];
         const int nv = A.chainVertCount[ws];
         int nfree = A.proxyFreeCount[ws];
         const int fresh = rp > nfree ? rp - nfree : 0;
-        if (nb + 1 > A.NB || nf + rf > A.NF || np + fresh > A.NP || ns + rs > A.NS || nv + rv > A.NV) {
+        if (nb + (target < 0 ? 1 : 0) > A.NB || nf + rf > A.NF || np + fresh > A.NP || ns + rs > A.NS || nv + rv > A.NV) {
             A.status[ws] |= B2GPU_STATUS_SPAWN_OVERFLOW;
             outIndex[i] = -1;
             continue;
         }
-        const uint32_t* p = r + 5;
+        if (target >= 0) {
+            if (target >= nb || (col(A.bodyFlags, tile, A.NB, lane)[target] & kBodyDestroyed)) {
+                A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
+                outIndex[i] = -1;
+                continue;
+            }
+            AttachFixtures(A, tile, lane, target, r, rf, rs, rv);
+            outIndex[i] = nf;  // index of the first new fixture
+            continue;
+        }
+        const uint32_t* p = r + 6;
         auto f4 = [&](float4* base, int cap, int item) {
             col(base, tile, cap, lane)[item] = make_float4(__uint_as_float(p[0]), __uint_as_float(p[1]), __uint_as_float(p[2]), __uint_as_float(p[3]));
             p += 4;
@@ -181,7 +475,9 @@ __global__ void k_spawn(Arena A, const uint32_t* __restrict__ words, const long 
             col(A.fixtureShape, tile, A.NF, lane)[nf + f] = shapeOff;
             col(A.fixtureMat, tile, A.NF, lane)[nf + f] = make_float2(__uint_as_float(p[2]), __uint_as_float(p[3]));
             col(A.fixtureFilter, tile, A.NF, lane)[nf + f] = make_int2((int)p[4], (int)p[5]);
-            p += 6;
+            col(A.fixtureMass, tile, A.NF, lane)[nf + f] =
+                make_float4(__uint_as_float(p[6]), __uint_as_float(p[7]), __uint_as_float(p[8]), __uint_as_float(p[9]));
+            p += 10;
         }
         Col<int> proxyFree = col(A.proxyFree, tile, A.NP, lane);
         int npNow = np;
@@ -241,6 +537,7 @@ __global__ void k_gather_events(Arena A, const long long* __restrict__ offsets, 
     }
 }
 
+
 // Between-step body edits (include/b2gpu.h B2GPU_CMD_*).  The command array is grouped by world; the thread that
 // owns the first command of a world applies that world's commands in order, exactly as the reference's user
 // would have made the calls (Box2D/Dynamics/b2Body.h:738-833, 408-467, 634-653; b2Body.cpp:418-440).
@@ -261,6 +558,25 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
     const int nb = A.bodyCount[ws];
     for (; i < count && cmds[i].world == w; ++i) {
         const b2gpu_body_command c = cmds[i];
+        if (c.op == B2GPU_CMD_DESTROY_JOINT) {  // b2World::DestroyJoint — Dynamics/b2World.cpp:267-360
+            int found = -1;
+            Col<int4> jI = col(A.jointI, tile, A.NJ, lane);
+            const int nj = A.hasJoints ? A.jointCount[ws] : 0;
+            for (int j = 0; j < nj && found < 0; ++j)
+                if (((jI[j].x >> 16) & 0xffff) == c.wake) found = j;
+            if (found < 0) { A.status[ws] |= B2GPU_STATUS_BAD_COMMAND; continue; }
+            const int4 ji = jI[found];
+            const int jA = ji.y & 0xffff, jB = (ji.y >> 16) & 0xffff;
+            if (WakeBody(bodyFlags, bodySweep, jA)) A.topoDirty[ws] = 1;  // bodyA->SetAwake(true); bodyB->SetAwake(true)
+            if (WakeBody(bodyFlags, bodySweep, jB)) A.topoDirty[ws] = 1;
+            Col<float4> jF0 = col(A.jointF0, tile, A.NJ, lane), jF1 = col(A.jointF1, tile, A.NJ, lane);
+            Col<float4> jF2 = col(A.jointF2, tile, A.NJ, lane), jImp = col(A.jointImp, tile, A.NJ, lane);
+            for (int j = found; j + 1 < nj; ++j) { jI[j] = jI[j + 1]; jF0[j] = jF0[j + 1]; jF1[j] = jF1[j + 1]; jF2[j] = jF2[j + 1]; jImp[j] = jImp[j + 1]; }
+            A.jointCount[ws] = nj - 1;
+            A.topoDirty[ws] = 1;
+            if ((ji.x & (1 << 8)) == 0) FlagContactsBetween(A, tile, lane, jA, jB);  // collideConnected == false: the pair may collide now
+            continue;
+        }
         if (c.body < 0 || c.body >= nb || c.op < 0 || c.op >= B2GPU_CMD_COUNT) {
             A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
             continue;
@@ -376,74 +692,110 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                         A.jointCount[ws] = wpos;
                     }
                 }
-                // 2. the attached contacts, in the body's contact-list order (newest first):
-                //    b2ContactManager::Destroy (EndContact if touching) + b2Contact::Destroy (wake if it had points)
+                // 2. the attached contacts, in the body's contact-list order (newest first)
+                DestroyContactsOf(A, tile, lane, b, -1);
+                // 3. the fixtures' proxies leave the broad phase (b2Fixture::DestroyProxies), fixture list order = newest first
                 {
-                    Col<int4> cA = col(A.contactA, tile, A.NC, lane), cK = col(A.contactK, tile, A.NC, lane);
-                    Col<int2> cS = col(A.contactS, tile, A.NC, lane);
-                    Col<float4> cP0 = col(A.contactP0, tile, A.NC, lane), cP1 = col(A.contactP1, tile, A.NC, lane);
-                    Col<float4> cN = col(A.contactN, tile, A.NC, lane);
-                    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
-                    EventSink ev{col(A.eventA, tile, A.NE, lane), col(A.eventB, tile, A.NE, lane), &A.eventCount[ws], &A.status[ws],
-                                 A.NE, A.eventMask};
-                    const int nc = A.contactCount[ws];
-                    bool any = false;
-                    for (int k = nc - 1; k >= 0; --k) {
-                        const int4 a = cA[k];
-                        const int kA = a.y & 0xffff, kB = (a.y >> 16) & 0xffff;
-                        if (kA != b && kB != b) continue;
-                        any = true;
-                        const int pointCount = (a.w >> 8) & 0xff;
-                        if (a.z & kContactTouching) {
-                            const int pa = proxyInfo[a.x & 0xffff], pb = proxyInfo[(a.x >> 16) & 0xffff];
-                            ev.push(kEventEnd, pa & 0xffff, (pa >> 16) & 0xffff, pb & 0xffff, (pb >> 16) & 0xffff, pointCount,
-                                    make_float4(0, 0, 0, 0));
-                        }
-                        if (pointCount > 0 && (a.z & kContactSensor) == 0) {
-                            WakeBody(bodyFlags, bodySweep, kA);
-                            WakeBody(bodyFlags, bodySweep, kB);
-                        }
-                    }
-                    if (any) {
-                        int wpos = 0;
-                        for (int k = 0; k < nc; ++k) {
-                            const int4 a = cA[k];
-                            if ((a.y & 0xffff) == b || ((a.y >> 16) & 0xffff) == b) continue;
-                            if (wpos != k) { cA[wpos] = a; cK[wpos] = cK[k]; cS[wpos] = cS[k]; cP0[wpos] = cP0[k]; cP1[wpos] = cP1[k]; cN[wpos] = cN[k]; }
-                            ++wpos;
-                        }
-                        A.contactCount[ws] = wpos;
-                    }
-                }
-                // 3. the fixtures' proxies leave the broad phase (b2Fixture::DestroyProxies): an empty fat AABB never
-                //    overlaps anything, and the proxy leaves the move buffer (b2BroadPhase::UnBufferMove)
-                {
-                    Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
                     Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
-                    Col<float4> proxyFat = col(A.proxyFat, tile, A.NP, lane);
-                    Col<int> proxyMoved = col(A.proxyMoved, tile, A.NP, lane);
-                    const int np = A.proxyCount[ws];
-                    // b2DynamicTree::FreeNode order = the body's fixture list (newest fixture first), children ascending:
-                    // the freed slots form a LIFO stack from which later CreateProxy calls take their ids
-                    Col<int> proxyFree = col(A.proxyFree, tile, A.NP, lane);
-                    int nfree = A.proxyFreeCount[ws];
                     for (int fx = A.fixtureCount[ws] - 1; fx >= 0; --fx) {
                         const int fi = fixtureInfo[fx];
-                        if ((fi & 0xffff) != b || (fi & (1 << 19))) continue;
-                        fixtureInfo[fx] = fi | (1 << 19);  // destroyed fixture
-                        for (int p = 0; p < np; ++p) {  // proxies of one fixture sit in ascending child order
-                            if ((proxyInfo[p] & 0xffff) != fx || proxyFat[p].x > proxyFat[p].z) continue;
-                            proxyFat[p] = make_float4(kMaxFloat, kMaxFloat, -kMaxFloat, -kMaxFloat);
-                            proxyMoved[p] = 0;
-                            proxyFree[nfree++] = p;
-                        }
+                        if ((fi & 0xffff) != b || (fi & kFixtureDestroyed)) continue;
+                        fixtureInfo[fx] = fi | kFixtureDestroyed;
+                        DestroyFixtureProxies(A, tile, lane, fx);
                     }
-                    A.proxyFreeCount[ws] = nfree;
                 }
                 // 4. the body itself: a tombstone that is never a seed, never woken, never touched again
                 bodyFlags[b] = (bodyFlags[b] & kBodyTypeMask) | kBodyDestroyed;
                 bodyVel[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 bodyForce[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            } break;
+            case B2GPU_CMD_SET_FILTER: {  // b2Fixture::SetFilterData + Refilter — Dynamics/b2Fixture.cpp:185-215
+                const int fx = c.wake;
+                Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+                if (fx < 0 || fx >= A.fixtureCount[ws] || (fixtureInfo[fx] & 0xffff) != b || (fixtureInfo[fx] & kFixtureDestroyed)) {
+                    A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
+                    break;
+                }
+                col(A.fixtureFilter, tile, A.NF, lane)[fx] = make_int2(__float_as_int(c.v[0]), __float_as_int(c.v[1]));
+                // flag the fixture's contacts for filtering
+                Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+                Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+                const int nc = A.contactCount[ws];
+                for (int k = 0; k < nc; ++k) {
+                    int4 a = cA[k];
+                    if ((proxyInfo[a.x & 0xffff] & 0xffff) != fx && (proxyInfo[(a.x >> 16) & 0xffff] & 0xffff) != fx) continue;
+                    a.z |= kContactFilter;
+                    cA[k] = a;
+                }
+                if (f & kBodyActive) TouchFixtureProxies(A, tile, lane, fx);  // an inactive body's fixtures have no proxies
+            } break;
+            case B2GPU_CMD_SET_TYPE: {  // b2Body::SetType — Dynamics/b2Body.cpp:115-166
+                const int newType = c.wake;
+                if (newType < B2G_STATIC_BODY || newType > B2G_DYNAMIC_BODY) { A.status[ws] |= B2GPU_STATUS_BAD_COMMAND; break; }
+                if (newType == type) break;
+                f = (f & ~kBodyTypeMask) | newType;
+                bodyFlags[b] = f;
+                A.topoDirty[ws] = 1;
+                ResetMassData(A, tile, lane, b);
+                if (newType == B2G_STATIC_BODY) {
+                    bodyVel[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    const float4 sw = bodySweep[b];
+                    bodySweep0[b] = make_float4(sw.x, sw.y, sw.z, 0.0f);
+                    if (f & kBodyActive) SynchronizeBodyFixtures(A, tile, lane, b);
+                }
+                wake();
+                bodyForce[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                DestroyContactsOf(A, tile, lane, b, -1);
+                if (f & kBodyActive) {  // touch the proxies so that new contacts will be created (when appropriate)
+                    Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+                    for (int fx = A.fixtureCount[ws] - 1; fx >= 0; --fx)
+                        if ((fixtureInfo[fx] & 0xffff) == b && (fixtureInfo[fx] & kFixtureDestroyed) == 0) TouchFixtureProxies(A, tile, lane, fx);
+                }
+            } break;
+            case B2GPU_CMD_SET_ACTIVE: {  // b2Body::SetActive — Dynamics/b2Body.cpp:455-510
+                const bool flag = c.wake != 0;
+                if (flag == ((f & kBodyActive) != 0)) break;
+                Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+                A.topoDirty[ws] = 1;
+                if (flag) {
+                    bodyFlags[b] = f | kBodyActive;
+                    const Xf xf = LoadXf(bodyXf, b);
+                    for (int fx = A.fixtureCount[ws] - 1; fx >= 0; --fx)  // m_fixtureList: newest first
+                        if ((fixtureInfo[fx] & 0xffff) == b && (fixtureInfo[fx] & kFixtureDestroyed) == 0) CreateFixtureProxies(A, tile, lane, fx, xf);
+                } else {
+                    bodyFlags[b] = f & ~kBodyActive;
+                    for (int fx = A.fixtureCount[ws] - 1; fx >= 0; --fx)
+                        if ((fixtureInfo[fx] & 0xffff) == b && (fixtureInfo[fx] & kFixtureDestroyed) == 0) DestroyFixtureProxies(A, tile, lane, fx);
+                    DestroyContactsOf(A, tile, lane, b, -1);
+                }
+            } break;
+            case B2GPU_CMD_SET_MASS_DATA: {  // b2Body::SetMassData — Dynamics/b2Body.cpp:354-394
+                if (type != B2G_DYNAMIC_BODY) break;
+                float mass = c.v[0];
+                if (mass <= 0.0f) mass = 1.0f;
+                const float invMass = Div(1.0f, mass);
+                float invI = 0.0f;
+                const Vec2 center = V2(c.p[0], c.p[1]);
+                if (c.v[1] > 0.0f && (f & kBodyFixedRotation) == 0) {
+                    const float I = c.v[1] - mass * Dot(center, center);
+                    invI = Div(1.0f, I);
+                }
+                MoveCenterOfMass(A, tile, lane, b, invMass, invI, center);
+            } break;
+            case B2GPU_CMD_RESET_MASS_DATA: {
+                ResetMassData(A, tile, lane, b);
+            } break;
+            case B2GPU_CMD_DESTROY_FIXTURE: {  // b2Body::DestroyFixture — Dynamics/b2Body.cpp:216-281
+                const int fx = c.wake;
+                Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+                if (fx < 0 || fx >= A.fixtureCount[ws] || (fixtureInfo[fx] & 0xffff) != b || (fixtureInfo[fx] & kFixtureDestroyed)) {
+                    A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
+                    break;
+                }
+                DestroyContactsOf(A, tile, lane, b, fx);
+                if (f & kBodyActive) DestroyFixtureProxies(A, tile, lane, fx);
+                fixtureInfo[fx] |= kFixtureDestroyed;
+                ResetMassData(A, tile, lane, b);
             } break;
             case B2GPU_CMD_SET_AWAKE: {
                 if (c.wake) {
@@ -488,6 +840,7 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                     Vec2 lo = Min(lo1, lo1), hi = Max(hi1, hi1);
                     const Vec2 displacement = xf.p - xf.p;
                     const float4 fat = proxyFat[p];
+                    if (fat.x > fat.z) continue;  // freed slot
                     if (fat.x <= lo.x && fat.y <= lo.y && hi.x <= fat.z && hi.y <= fat.w) continue;
                     const Vec2 r = V2(kAabbExtension, kAabbExtension);
                     lo = lo - r;
@@ -662,7 +1015,7 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(bodyVel, A.NB, float4); ALLOC(bodyForce, A.NB, float4); ALLOC(bodyMass, A.NB, float4);
     ALLOC(bodyDamp, A.NB, float4); ALLOC(bodyFlags, A.NB, int); ALLOC(bodyIsland, A.NB, int);
     ALLOC(fixtureInfo, A.NF, int); ALLOC(fixtureShape, A.NF, int); ALLOC(fixtureMat, A.NF, float2);
-    ALLOC(fixtureFilter, A.NF, int2);
+    ALLOC(fixtureFilter, A.NF, int2); ALLOC(fixtureMass, A.NF, float4);
     ALLOC(proxyFat, A.NP, float4); ALLOC(proxyInfo, A.NP, int); ALLOC(proxyMoved, A.NP, int);
     ALLOC(shapeWords, A.NS, float); ALLOC(chainVerts, A.NV, float2);
     ALLOC(contactA, A.NC, int4); ALLOC(contactK, A.NC, int4); ALLOC(contactS, A.NC, int2);
@@ -685,7 +1038,7 @@ int allocateArena(b2gpu_batch* b) {
     ALLOC(bodyProxyStart, A.NB + 1, int); ALLOC(bodyProxyList, A.NP, int); ALLOC(toiBodies, kToiBodyCap, int); ALLOC(toiContacts, kMaxToiContacts, int);
     ALLOC(toiVc, (size_t)kMaxToiContacts * kVcStride, float4);
     ALLOC(eventA, A.NE, int4); ALLOC(eventB, A.NE, float4);
-    ALLOC(jointCount, 1, int); ALLOC(jointI, A.NJ, int4); ALLOC(jointF0, A.NJ, float4); ALLOC(jointF1, A.NJ, float4);
+    ALLOC(jointCount, 1, int); ALLOC(jointSeq, 1, int); ALLOC(jointI, A.NJ, int4); ALLOC(jointF0, A.NJ, float4); ALLOC(jointF1, A.NJ, float4);
     ALLOC(jointF2, A.NJ, float4); ALLOC(jointImp, A.NJ, float4); ALLOC(jointTmp, (size_t)A.NJ * kJointTmp, float4);
     ALLOC(islandJoints, A.NJ, int); ALLOC(islandJointEnd, A.NB, int);
 
@@ -740,6 +1093,8 @@ int allocateArena(b2gpu_batch* b) {
     F(B2GPU_F_PROXY_FREE_COUNT, (void**)&A.proxyFreeCount, 1, 1);
     F(B2GPU_F_PROXY_FREE, (void**)&A.proxyFree, A.NP, 1);
     F(B2GPU_F_NEW_FIXTURE, (void**)&A.newFixture, 1, 1);
+    F(B2GPU_F_JOINT_SEQ, (void**)&A.jointSeq, 1, 1);
+    F(B2GPU_F_FIXTURE_MASS, (void**)&A.fixtureMass, A.NF, 4);
     return B2GPU_OK;
 }
 
@@ -1561,6 +1916,28 @@ int b2gpu_batch_spawn_records(b2gpu_batch* b, const uint32_t* words, const int64
     return B2GPU_OK;
 }
 
+int b2gpu_batch_joint_records(b2gpu_batch* b, const uint32_t* words, int32_t count, int32_t* jointIds) {
+    if (!b || count < 0 || (count > 0 && (!words || !jointIds))) return fail(B2GPU_ERR_INVALID, "bad arguments");
+    if (count == 0) return B2GPU_OK;
+    for (int32_t i = 0; i < count; ++i) {
+        const int w = (int)words[(size_t)i * 21];
+        if (w < 0 || w >= b->desc.numWorlds) return fail(B2GPU_ERR_INVALID, "joint %d names world %d outside the batch", i, w);
+        if (i > 0 && w < (int)words[(size_t)(i - 1) * 21]) return fail(B2GPU_ERR_INVALID, "joint records must be grouped by ascending world");
+    }
+    CUDA_TRY(cudaSetDevice(b->desc.device));
+    DevBuf dw, dout;
+    int rc;
+    if ((rc = dw.alloc((size_t)count * 21 * 4)) != B2GPU_OK) return rc;
+    if ((rc = dout.alloc((size_t)count * sizeof(int32_t))) != B2GPU_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dw.p, words, (size_t)count * 21 * 4, cudaMemcpyHostToDevice, b->stream));
+    k_create_joints<<<(unsigned)((count + 127) / 128), 128, 0, b->stream>>>(b->A, (const uint32_t*)dw.p, count, (int*)dout.p);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(jointIds, dout.p, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return B2GPU_OK;
+}
+
 int b2gpu_batch_read_events(b2gpu_batch* b, int64_t* offsets, b2gpu_event* events, int64_t capacity) {
     if (!b || !offsets || capacity < 0) return fail(B2GPU_ERR_INVALID, "bad arguments");
     CUDA_TRY(cudaSetDevice(b->desc.device));
@@ -1619,6 +1996,11 @@ int b2gpu_batch_body_commands(b2gpu_batch* b, const b2gpu_body_command* commands
     CUDA_TRY(cudaGetLastError());
     // the host array (or its grouped copy) may die when we return
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    for (int64_t i = 0; i < count; ++i)  // proxies came or went: the body -> proxies index is rebuilt before the next step
+        if (commands[i].op == B2GPU_CMD_DESTROY_BODY || commands[i].op == B2GPU_CMD_SET_ACTIVE || commands[i].op == B2GPU_CMD_DESTROY_FIXTURE) {
+            b->needProxyIndex = true;
+            break;
+        }
     return B2GPU_OK;
 }
 

@@ -68,6 +68,26 @@ enum {
     B2GPU_CMD_MOUSE_SET_TARGET = 10,     /* v = target                        b2MouseJoint::SetTarget(target) (b2MouseJoint.cpp:54-61) on the
                                             mouse joint whose bodyB is `body` (the newest one if it has several): wakes the
                                             body; BAD_COMMAND if the body carries no mouse joint */
+    /* ---- edits that change what collides (all of them leave the rest to the next Step, like the reference) ---- */
+    B2GPU_CMD_SET_FILTER = 11,           /* wake = fixture index, v[0] / v[1] = the BIT PATTERNS of two int32: categoryBits |
+                                            maskBits << 16, groupIndex   b2Fixture::SetFilterData + Refilter (b2Fixture.cpp:185-215):
+                                            the fixture's contacts are flagged for filtering (b2ContactManager::Collide re-asks
+                                            ShouldCollide at the next Step and destroys those that fail, :124-146), its proxies are
+                                            touched (b2BroadPhase::TouchProxy) so that new pairs can form */
+    B2GPU_CMD_DESTROY_JOINT = 12,        /* wake = joint id (creation order in its world, as returned by b2gpu_batch_create_joints;
+                                            scene joints are 0 .. jointCount-1), body ignored   b2World::DestroyJoint (b2World.cpp:267-360):
+                                            wakes both bodies; if the joint had collideConnected == false the contacts between its
+                                            two bodies are flagged for filtering */
+    B2GPU_CMD_SET_TYPE = 13,             /* wake = b2BodyType          b2Body::SetType (b2Body.cpp:115-166): mass data reset, a body
+                                            turned static is stopped and its proxies re-synchronised, the body wakes, forces are
+                                            cleared, its contacts are destroyed (no EndContact there, like the reference: :150-157
+                                            calls b2ContactManager::Destroy, which does report it), its proxies are touched */
+    B2GPU_CMD_SET_ACTIVE = 14,           /* wake = flag                b2Body::SetActive (b2Body.cpp:455-510): proxies created /
+                                            destroyed, contacts destroyed on deactivation */
+    B2GPU_CMD_SET_MASS_DATA = 15,        /* v[0] = mass, v[1] = I (about the local origin), p = center   b2Body::SetMassData (:354-394) */
+    B2GPU_CMD_RESET_MASS_DATA = 16,      /*                             b2Body::ResetMassData (:283-352) */
+    B2GPU_CMD_DESTROY_FIXTURE = 17,      /* wake = fixture index       b2Body::DestroyFixture (:216-281): its contacts are destroyed
+                                            (EndContact events), its proxies leave the broad phase, the mass data is reset */
     B2GPU_CMD_COUNT
 };
 typedef struct b2gpu_body_command {
@@ -159,6 +179,8 @@ enum {
     B2GPU_F_PROXY_FREE_COUNT,   /* [W][1][1] int32  freed proxy slots (b2DynamicTree's free list, LIFO) */
     B2GPU_F_PROXY_FREE,         /* [W][NP][1] int32 */
     B2GPU_F_NEW_FIXTURE,        /* [W][1][1] int32  b2World::e_newFixture: the next Step starts with FindNewContacts */
+    B2GPU_F_JOINT_SEQ,          /* [W][1][1] int32  joints created so far = the next joint id (ids ride in JOINT_I.x bits 16-31) */
+    B2GPU_F_FIXTURE_MASS,       /* [W][NF][4]  b2Fixture::GetMassData: mass, center.xy, I (what b2Body::ResetMassData sums) */
     B2GPU_F_COUNT
 };
 
@@ -335,6 +357,31 @@ int b2gpu_batch_create_bodies(b2gpu_batch* batch, const b2gpu_spawn* spawns, int
 /* Device-layer primitive under it: applies pre-evaluated spawn records (layout: box2dpp_b200/csrc/b2g_host.cpp). */
 int b2gpu_batch_spawn_records(b2gpu_batch* batch, const uint32_t* words, const int64_t* offsets, int32_t count,
                               int32_t* bodyIndices);
+
+/* Replaces b2Body::CreateFixture on a body that exists already (b2Body.cpp:168-214): attach[i] adds the fixtures
+ * fixtures[firstFixture .. firstFixture + fixtureCount) to body `body` of world `world`, one CreateFixture call each, in
+ * order: head of the body's fixture list, proxies under the body's current transform if it is active, mass data reset
+ * if the fixture has density, e_newFixture raised (the next Step starts with FindNewContacts).  fixtureIndices[i] = index
+ * of the first new fixture (the handle B2GPU_CMD_DESTROY_FIXTURE / SET_FILTER take), or -1 when an arena is full
+ * (B2GPU_STATUS_SPAWN_OVERFLOW) or the body does not exist (B2GPU_STATUS_BAD_COMMAND).  Synchronises. */
+typedef struct b2gpu_attach {
+    int32_t world, body;
+    int32_t firstFixture, fixtureCount;
+} b2gpu_attach;
+int b2gpu_batch_create_fixtures(b2gpu_batch* batch, const b2gpu_attach* attach, int32_t count, const b2g_fixture_def* fixtures,
+                                const float* vertices, int32_t* fixtureIndices);
+
+/* Replaces b2World::CreateJoint calls made on a running world (b2World.cpp:205-265): joint i is created in world
+ * worlds[i] from defs[i] (the def after Initialize(), as in b2g_scene).  The joint becomes the head of the world's and
+ * of both bodies' joint lists; if collideConnected is false the contacts between its two bodies are flagged for
+ * filtering, so the next Step destroys them (:255-263).  Joints of one world are created in array order.
+ * jointIds[i] = the joint's id (the handle B2GPU_CMD_DESTROY_JOINT takes), or -1 when the world's joint arena is full
+ * (B2GPU_STATUS_SPAWN_OVERFLOW) — size it with b2gpu_batch_desc.maxJoints.  Gear and mouse joints read body state when
+ * they are constructed and can only be created with the scene (B2GPU_ERR_UNSUPPORTED here).  Synchronises. */
+int b2gpu_batch_create_joints(b2gpu_batch* batch, const int32_t* worlds, const b2g_joint_def* defs, int32_t count,
+                              int32_t* jointIds);
+/* Device-layer primitive under it: 21 words per joint (world, then the five 4-word joint columns). */
+int b2gpu_batch_joint_records(b2gpu_batch* batch, const uint32_t* words, int32_t count, int32_t* jointIds);
 
 /* Host-side shape math, exported for tests: b2PolygonShape::Set / SetAsBox / ComputeMass
  * (Box2D/Collision/Shapes/b2PolygonShape.cpp:32-245, 354-437).  out: 8 vertices, 8 normals, centroid, then

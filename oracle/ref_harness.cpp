@@ -78,6 +78,7 @@ struct RefWorld {
     std::vector<b2Body*> bodies;      // creation order
     std::vector<b2Fixture*> fixtures; // creation order (nullptr once the body was destroyed)
     std::vector<int> childCounts;     // proxies per fixture
+    std::vector<b2Joint*> joints;     // creation order = joint ids (nullptr once destroyed, alone or with one of its bodies)
     int proxySlots = 0;               // high-water mark of proxy slots (see ref_world_get_proxies)
     Recorder recorder;
 };
@@ -113,6 +114,14 @@ void add_body(RefWorld* rw, const b2g_body_def& d) {
     bd.active = (d.flags & B2G_BD_ACTIVE) != 0;
     bd.userData = (void*)(intptr_t)rw->bodies.size();
     rw->bodies.push_back(rw->world->CreateBody(&bd));
+}
+
+void note_proxy_slots(RefWorld* rw, b2Fixture* f) {
+    for (int k = 0; k < f->m_proxyCount; ++k) {
+        const int id = f->m_proxies[k].proxyId;
+        const int slot = id == 0 ? 0 : (id + 1) / 2;
+        if (slot + 1 > rw->proxySlots) rw->proxySlots = slot + 1;
+    }
 }
 
 // b2Body::CreateFixture from a fixture definition; the fixture's index (creation order) is its userData
@@ -166,11 +175,108 @@ void add_fixture(RefWorld* rw, b2Body* body, const b2g_fixture_def& d, const flo
     }
     rw->fixtures.push_back(f);
     rw->childCounts.push_back(f->GetShape()->GetChildCount());
-    for (int k = 0; k < f->m_proxyCount; ++k) {
-        const int id = f->m_proxies[k].proxyId;
-        const int slot = id == 0 ? 0 : (id + 1) / 2;
-        if (slot + 1 > rw->proxySlots) rw->proxySlots = slot + 1;
+    note_proxy_slots(rw, f);
+}
+
+// b2World::CreateJoint from a joint definition; the joint's id is its place in rw->joints (creation order)
+b2Joint* add_joint(RefWorld* rw, const b2g_joint_def& d) {
+    b2World* w = rw->world;
+    b2Joint* made = nullptr;
+    {
+        b2Body* bA = rw->bodies[d.bodyA];
+        b2Body* bB = rw->bodies[d.bodyB];
+        if (d.type == B2G_JOINT_MOUSE) {
+            b2MouseJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.target.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.maxForce = d.length; jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_GEAR) {
+            auto jointAt = [&](int k) { return rw->joints[k]; };  // joints[k] of the scene = the k-th CreateJoint call
+            b2GearJointDef jd;
+            jd.joint1 = jointAt(d.enableLimit);
+            jd.joint2 = jointAt(d.enableMotor);
+            jd.bodyA = jd.joint1->GetBodyB(); jd.bodyB = jd.joint2->GetBodyB();  // what the Testbed passes; the constructor overrides them
+            jd.collideConnected = d.collideConnected != 0;
+            jd.ratio = d.motorSpeed;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_REVOLUTE) {
+            b2RevoluteJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.referenceAngle = d.referenceAngle;
+            jd.enableLimit = d.enableLimit != 0; jd.lowerAngle = d.lower; jd.upperAngle = d.upper;
+            jd.enableMotor = d.enableMotor != 0; jd.maxMotorTorque = d.maxMotor; jd.motorSpeed = d.motorSpeed;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_PRISMATIC) {
+            b2PrismaticJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.localAxisA.Set(d.localAxisA[0], d.localAxisA[1]);
+            jd.referenceAngle = d.referenceAngle;
+            jd.enableLimit = d.enableLimit != 0; jd.lowerTranslation = d.lower; jd.upperTranslation = d.upper;
+            jd.enableMotor = d.enableMotor != 0; jd.maxMotorForce = d.maxMotor; jd.motorSpeed = d.motorSpeed;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_WHEEL) {
+            b2WheelJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.localAxisA.Set(d.localAxisA[0], d.localAxisA[1]);
+            jd.enableMotor = d.enableMotor != 0; jd.maxMotorTorque = d.maxMotor; jd.motorSpeed = d.motorSpeed;
+            jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_ROPE) {
+            b2RopeJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.maxLength = d.length;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_PULLEY) {
+            b2PulleyJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.groundAnchorA.Set(d.localAxisA[0], d.localAxisA[1]);
+            jd.groundAnchorB.Set(d.lower, d.upper);
+            jd.lengthA = d.length; jd.lengthB = d.maxMotor; jd.ratio = d.motorSpeed;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_MOTOR) {
+            b2MotorJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.linearOffset.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.angularOffset = d.referenceAngle;
+            jd.maxForce = d.length; jd.maxTorque = d.maxMotor; jd.correctionFactor = d.frequencyHz;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_FRICTION) {
+            b2FrictionJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.maxForce = d.length; jd.maxTorque = d.maxMotor;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_WELD) {
+            b2WeldJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.referenceAngle = d.referenceAngle;
+            jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
+            made = w->CreateJoint(&jd);
+        } else if (d.type == B2G_JOINT_DISTANCE) {
+            b2DistanceJointDef jd;
+            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
+            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
+            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
+            jd.length = d.length; jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
+            made = w->CreateJoint(&jd);
+        }
     }
+    rw->joints.push_back(made);
+    return made;
 }
 
 RefWorld* build_world(const b2g_scene* s) {
@@ -186,105 +292,7 @@ RefWorld* build_world(const b2g_scene* s) {
     for (int i = 0; i < s->bodyCount; ++i) add_body(rw, s->bodies[i]);
     for (int i = 0; i < s->fixtureCount; ++i) add_fixture(rw, rw->bodies[s->fixtures[i].body], s->fixtures[i], s->vertices);
     // b2World::CreateJoint in call order, from the same local-frame definitions the device path receives
-    for (int i = 0; i < s->jointCount; ++i) {
-        const b2g_joint_def& d = s->joints[i];
-        b2Body* bA = rw->bodies[d.bodyA];
-        b2Body* bB = rw->bodies[d.bodyB];
-        if (d.type == B2G_JOINT_MOUSE) {
-            b2MouseJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.target.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.maxForce = d.length; jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_GEAR) {
-            // joints[k] of the scene = the k-th CreateJoint call; m_jointList is head-inserted (newest first)
-            auto jointAt = [&](int k) {
-                b2Joint* j = w->GetJointList();
-                for (int n = w->GetJointCount() - 1 - k; n > 0 && j; --n) j = j->GetNext();
-                return j;
-            };
-            b2GearJointDef jd;
-            jd.joint1 = jointAt(d.enableLimit);
-            jd.joint2 = jointAt(d.enableMotor);
-            jd.bodyA = jd.joint1->GetBodyB(); jd.bodyB = jd.joint2->GetBodyB();  // what the Testbed passes; the constructor overrides them
-            jd.collideConnected = d.collideConnected != 0;
-            jd.ratio = d.motorSpeed;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_REVOLUTE) {
-            b2RevoluteJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
-            jd.referenceAngle = d.referenceAngle;
-            jd.enableLimit = d.enableLimit != 0; jd.lowerAngle = d.lower; jd.upperAngle = d.upper;
-            jd.enableMotor = d.enableMotor != 0; jd.maxMotorTorque = d.maxMotor; jd.motorSpeed = d.motorSpeed;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_PRISMATIC) {
-            b2PrismaticJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
-            jd.localAxisA.Set(d.localAxisA[0], d.localAxisA[1]);
-            jd.referenceAngle = d.referenceAngle;
-            jd.enableLimit = d.enableLimit != 0; jd.lowerTranslation = d.lower; jd.upperTranslation = d.upper;
-            jd.enableMotor = d.enableMotor != 0; jd.maxMotorForce = d.maxMotor; jd.motorSpeed = d.motorSpeed;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_WHEEL) {
-            b2WheelJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
-            jd.localAxisA.Set(d.localAxisA[0], d.localAxisA[1]);
-            jd.enableMotor = d.enableMotor != 0; jd.maxMotorTorque = d.maxMotor; jd.motorSpeed = d.motorSpeed;
-            jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_ROPE) {
-            b2RopeJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
-            jd.maxLength = d.length;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_PULLEY) {
-            b2PulleyJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
-            jd.groundAnchorA.Set(d.localAxisA[0], d.localAxisA[1]);
-            jd.groundAnchorB.Set(d.lower, d.upper);
-            jd.lengthA = d.length; jd.lengthB = d.maxMotor; jd.ratio = d.motorSpeed;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_MOTOR) {
-            b2MotorJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.linearOffset.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.angularOffset = d.referenceAngle;
-            jd.maxForce = d.length; jd.maxTorque = d.maxMotor; jd.correctionFactor = d.frequencyHz;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_FRICTION) {
-            b2FrictionJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
-            jd.maxForce = d.length; jd.maxTorque = d.maxMotor;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_WELD) {
-            b2WeldJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
-            jd.referenceAngle = d.referenceAngle;
-            jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
-            w->CreateJoint(&jd);
-        } else if (d.type == B2G_JOINT_DISTANCE) {
-            b2DistanceJointDef jd;
-            jd.bodyA = bA; jd.bodyB = bB; jd.collideConnected = d.collideConnected != 0;
-            jd.localAnchorA.Set(d.localAnchorA[0], d.localAnchorA[1]);
-            jd.localAnchorB.Set(d.localAnchorB[0], d.localAnchorB[1]);
-            jd.length = d.length; jd.frequencyHz = d.frequencyHz; jd.dampingRatio = d.dampingRatio;
-            w->CreateJoint(&jd);
-        }
-    }
+    for (int i = 0; i < s->jointCount; ++i) add_joint(rw, s->joints[i]);
     return rw;
 }
 
@@ -317,15 +325,74 @@ int ref_world_create_body(void* h, const b2g_body_def* bd, const b2g_fixture_def
     return (int)rw->bodies.size() - 1;
 }
 
+// b2Fixture::SetFilterData (the B2GPU_CMD_SET_FILTER payload as plain integers)
+void ref_world_set_filter(void* h, int fixture, int categoryBits, int maskBits, int groupIndex) {
+    RefWorld* rw = (RefWorld*)h;
+    if (fixture < 0 || fixture >= (int)rw->fixtures.size() || !rw->fixtures[fixture]) return;
+    b2Filter f;
+    f.categoryBits = (uint16)categoryBits; f.maskBits = (uint16)maskBits; f.groupIndex = (int16)groupIndex;
+    rw->fixtures[fixture]->SetFilterData(f);
+}
+
+// b2World::CreateJoint on a stepped world; returns the joint id.
+int ref_world_create_joint(void* h, const b2g_joint_def* d) {
+    RefWorld* rw = (RefWorld*)h;
+    if (d->bodyA < 0 || d->bodyA >= (int)rw->bodies.size() || d->bodyB < 0 || d->bodyB >= (int)rw->bodies.size()) return -1;
+    if (!rw->bodies[d->bodyA] || !rw->bodies[d->bodyB]) return -1;
+    add_joint(rw, *d);
+    return (int)rw->joints.size() - 1;
+}
+
+// b2Body::CreateFixture on an existing body of a stepped world; returns the fixture index.
+int ref_world_create_fixture(void* h, int body, const b2g_fixture_def* fd, const float* vertices) {
+    RefWorld* rw = (RefWorld*)h;
+    if (body < 0 || body >= (int)rw->bodies.size() || !rw->bodies[body]) return -1;
+    add_fixture(rw, rw->bodies[body], *fd, vertices);
+    return (int)rw->fixtures.size() - 1;
+}
+
 // Between-step body edits, ops = B2GPU_CMD_* of include/b2gpu.h: the call a user of the reference makes on a b2Body.
 void ref_world_body_command(void* h, int body, int op, int wake, float vx, float vy, float px, float py) {
     RefWorld* rw = (RefWorld*)h;
+    if (op == 12) {  // b2World::DestroyJoint(joint id)
+        if (wake < 0 || wake >= (int)rw->joints.size() || !rw->joints[wake]) return;
+        rw->world->DestroyJoint(rw->joints[wake]);
+        rw->joints[wake] = nullptr;
+        return;
+    }
     if (body < 0 || body >= (int)rw->bodies.size()) return;
     b2Body* b = rw->bodies[body];
     if (!b) return;  // destroyed earlier
-    if (op == 9) {   // b2World::DestroyBody: the body's fixtures go with it; the indices stay reserved
+    if (op >= 11) {
+        switch (op) {
+            case 11: {  // b2Fixture::SetFilterData: the two ints travel as float bit patterns
+                if (wake < 0 || wake >= (int)rw->fixtures.size() || !rw->fixtures[wake]) return;
+                int32_t bits, group;
+                memcpy(&bits, &vx, 4); memcpy(&group, &vy, 4);
+                b2Filter f;
+                f.categoryBits = (uint16)(bits & 0xffff); f.maskBits = (uint16)((bits >> 16) & 0xffff); f.groupIndex = (int16)group;
+                rw->fixtures[wake]->SetFilterData(f);
+            } break;
+            case 13: b->SetType((b2BodyType)wake); break;
+            case 14: {
+                b->SetActive(wake != 0);
+                for (b2Fixture* f : rw->fixtures) if (f && f->GetBody() == b) note_proxy_slots(rw, f);
+            } break;
+            case 15: { b2MassData md; md.mass = vx; md.I = vy; md.center.Set(px, py); b->SetMassData(&md); } break;
+            case 16: b->ResetMassData(); break;
+            case 17: {
+                if (wake < 0 || wake >= (int)rw->fixtures.size() || !rw->fixtures[wake] || rw->fixtures[wake]->GetBody() != b) return;
+                b->DestroyFixture(rw->fixtures[wake]);
+                rw->fixtures[wake] = nullptr;
+            } break;
+        }
+        return;
+    }
+    if (op == 9) {   // b2World::DestroyBody: the body's fixtures and joints go with it; the indices stay reserved
         for (size_t i = 0; i < rw->fixtures.size(); ++i)
             if (rw->fixtures[i] && rw->fixtures[i]->GetBody() == b) rw->fixtures[i] = nullptr;
+        for (size_t i = 0; i < rw->joints.size(); ++i)
+            if (rw->joints[i] && (rw->joints[i]->GetBodyA() == b || rw->joints[i]->GetBodyB() == b)) rw->joints[i] = nullptr;
         rw->world->DestroyBody(b);
         rw->bodies[body] = nullptr;
         return;

@@ -62,6 +62,12 @@ def lib(kind="ref"):
         if kind == "ref":
             L.ref_world_create_body.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
             L.ref_world_create_body.restype = C.c_int
+            L.ref_world_set_filter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+            L.ref_world_set_filter.restype = None
+            L.ref_world_create_joint.argtypes = [C.c_void_p, C.c_void_p]
+            L.ref_world_create_joint.restype = C.c_int
+            L.ref_world_create_fixture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            L.ref_world_create_fixture.restype = C.c_int
         L.ref_world_body_command.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
         L.ref_world_body_command.restype = None
         L.ref_polygon_build.argtypes = [C.POINTER(FixtureDef), C.c_void_p, C.c_void_p]
@@ -136,6 +142,19 @@ class RefWorld:
         fds = (FixtureDef * max(len(fixture_defs), 1))(*fixture_defs)
         v = np.ascontiguousarray(vertices if len(vertices) else [0.0, 0.0], np.float32)
         return self.L.ref_world_create_body(self.h, C.byref(body_def), fds, len(fixture_defs), _p(v))
+
+    def set_filter(self, fixture, category_bits, mask_bits, group_index):
+        """b2Fixture::SetFilterData (live reference only)."""
+        self.L.ref_world_set_filter(self.h, fixture, category_bits, mask_bits, group_index)
+
+    def create_joint(self, joint_def):
+        """b2World::CreateJoint after stepping (live reference only); returns the joint id (creation order)."""
+        return self.L.ref_world_create_joint(self.h, C.byref(joint_def))
+
+    def create_fixture(self, body, fixture_def, vertices):
+        """b2Body::CreateFixture on an existing body after stepping (live reference only); returns the fixture index."""
+        v = np.ascontiguousarray(vertices if len(vertices) else [0.0, 0.0], np.float32)
+        return self.L.ref_world_create_fixture(self.h, body, C.byref(fixture_def), _p(v))
 
     def bodies(self) -> np.ndarray:
         """[nb,16] float32: xf.p(2) q.s q.c | c(2) a | v(2) w | awake mass I localCenter(2) pad."""

@@ -278,3 +278,141 @@ def test_create_and_destroy_bodies_match_reference(oracles):
     assert small.create_bodies([(0, bd, fds, verts)]).tolist() == [-1] and small.status()[0] == 8
     small.close()
     batch.close()
+
+
+def _edit_fixture(rng, kind):
+    """[FixtureDef], vertices of one fixture to attach to an existing body."""
+    tmp = S.Scene()
+    b = tmp.create_body(S.DYNAMIC_BODY, (0.0, 0.0))
+    if kind == 0:
+        tmp.create_circle(b, rng.uniform(0.15, 0.4), density=rng.uniform(0.5, 2.0), restitution=0.2)
+    elif kind == 1:
+        tmp.create_box(b, rng.uniform(0.15, 0.4), rng.uniform(0.15, 0.4), density=1.5, friction=0.5)
+    elif kind == 2:
+        tmp.create_circle(b, rng.uniform(0.5, 0.9), sensor=True)  # no density: the mass data stays
+    else:
+        n = 4
+        r = rng.uniform(0.25, 0.5)
+        tmp.create_polygon(b, [(float(np.float32(r * np.cos(2 * np.pi * j / n + 0.3))), float(np.float32(r * np.sin(2 * np.pi * j / n + 0.3)))) for j in range(n)], density=1.0)
+    return list(tmp.fixtures), list(tmp.vertices)
+
+
+def _edit_joint(rng, body_a, body_b):
+    jd = S.JointDef()
+    kind = int(rng.next_u() * 6) % 6
+    jd.bodyA, jd.bodyB = body_a, body_b
+    jd.collideConnected = 1 if rng.next_u() < 0.4 else 0
+    jd.localAnchorA[0], jd.localAnchorA[1] = float(np.float32(rng.uniform(-0.2, 0.2))), float(np.float32(rng.uniform(-0.2, 0.2)))
+    jd.localAnchorB[0], jd.localAnchorB[1] = float(np.float32(rng.uniform(-0.2, 0.2))), float(np.float32(rng.uniform(-0.2, 0.2)))
+    if kind == 0:
+        jd.type, jd.length, jd.frequencyHz, jd.dampingRatio = S.JOINT_DISTANCE, float(np.float32(rng.uniform(1.0, 4.0))), 3.0, 0.6
+    elif kind == 1:
+        jd.type, jd.length = S.JOINT_ROPE, float(np.float32(rng.uniform(2.0, 6.0)))
+    elif kind == 2:
+        jd.type, jd.length, jd.maxMotor = S.JOINT_FRICTION, 5.0, 2.0
+    elif kind == 3:
+        jd.type, jd.frequencyHz, jd.dampingRatio = S.JOINT_WELD, 2.0, 0.7
+    elif kind == 4:
+        jd.type, jd.lower, jd.upper, jd.enableLimit = S.JOINT_REVOLUTE, -0.5, 0.5, 1
+    else:
+        jd.type, jd.length = S.JOINT_DISTANCE, float(np.float32(rng.uniform(1.5, 3.0)))
+    return jd
+
+
+@pytest.mark.gpu
+def test_world_edits_match_reference(oracles):
+    """The rest of §8f-2 against the live reference, random edits between steps, every float and contact compared after
+    the edits and after every step: b2Fixture::SetFilterData (contacts flagged, b2ContactManager::Collide's e_filterFlag
+    branch), b2World::CreateJoint / DestroyJoint on running worlds (collideConnected flags the pair's contacts),
+    b2Body::SetType, SetActive, SetMassData, ResetMassData, DestroyFixture and CreateFixture on existing bodies."""
+    if not oracles.available("ref"):
+        pytest.skip("checked against the live reference")
+    base = [S.pyramid(4), S.mixed(2, bodies=10), S.jointed(1), S.filtered(16), S.hello_world(), S.jointed(4, flags=NOCCD),
+            S.pyramid(3, flags=NOCCD, jitter_seed=2), S.sensors(1, bodies=6)]
+    scenes = base * 4  # 32 worlds
+    refs = [oracles.RefWorld(s, record_events=True) for s in scenes]
+    batch = B.WorldBatch(scenes, event_mask=B.EVENT_ALL, headroom=(0, 60, 90, 1500, 0), joint_headroom=24)
+    rng = S.LCG(977)
+    bodies = [list(range(s.body_count)) for s in scenes]
+    fixtures = [{i: int(f.body) for i, f in enumerate(s.fixtures)} for s in scenes]          # live fixture -> body
+    joints = [set(range(len(s.joints))) for s in scenes]
+    types = [[int(b.type) for b in s.bodies] for s in scenes]
+    counts = {}
+    pick = lambda seq: seq[int(rng.next_u() * len(seq)) % len(seq)]  # noqa: E731
+    for step in range(260):
+        if step % 5 == 2:
+            cmds, attach, new_joints, filters = [], [], [], {}
+            for w, r in enumerate(refs):
+                for _ in range(1 + int(rng.next_u() * 2) % 2):
+                    u = rng.next_u()
+                    body = pick(bodies[w])
+                    if u < 0.16 and fixtures[w]:
+                        fx = pick(sorted(fixtures[w]))
+                        filters[len(cmds)] = (1 << (int(rng.next_u() * 4) % 4), 0xffff if rng.next_u() < 0.5 else int(rng.next_u() * 16) % 16,
+                                              int(rng.next_u() * 5) % 5 - 2)
+                        cmds.append((w, fixtures[w][fx], B.CMD_SET_FILTER, fx, (0.0, 0.0), (0.0, 0.0)))
+                    elif u < 0.28:
+                        t = int(rng.next_u() * 3) % 3
+                        if body == 0 and rng.next_u() < 0.8:
+                            continue  # the ground mostly stays what it is
+                        cmds.append((w, body, B.CMD_SET_TYPE, t, (0.0, 0.0), (0.0, 0.0)))
+                        types[w][body] = t
+                    elif u < 0.40:
+                        cmds.append((w, body, B.CMD_SET_ACTIVE, 1 if rng.next_u() < 0.6 else 0, (0.0, 0.0), (0.0, 0.0)))
+                    elif u < 0.50:
+                        m = float(np.float32(rng.uniform(0.5, 5.0)))
+                        cmds.append((w, body, B.CMD_SET_MASS_DATA, 0, (m, float(np.float32(rng.uniform(0.5, 3.0)))),
+                                     (float(np.float32(rng.uniform(-0.1, 0.1))), float(np.float32(rng.uniform(-0.1, 0.1))))))
+                    elif u < 0.56:
+                        cmds.append((w, body, B.CMD_RESET_MASS_DATA, 0, (0.0, 0.0), (0.0, 0.0)))
+                    elif u < 0.66 and fixtures[w]:
+                        fx = pick(sorted(fixtures[w]))
+                        cmds.append((w, fixtures[w].pop(fx), B.CMD_DESTROY_FIXTURE, fx, (0.0, 0.0), (0.0, 0.0)))
+                    elif u < 0.80:
+                        fds, verts = _edit_fixture(rng, int(rng.next_u() * 4) % 4)
+                        attach.append((w, body, fds, verts))
+                    elif u < 0.92 and len(bodies[w]) > 1:
+                        other = pick([b for b in bodies[w] if b != body])
+                        new_joints.append((w, _edit_joint(rng, body, other)))
+                    elif joints[w]:
+                        j = pick(sorted(joints[w]))
+                        joints[w].discard(j)
+                        cmds.append((w, 0, B.CMD_DESTROY_JOINT, j, (0.0, 0.0), (0.0, 0.0)))
+            # the reference takes the calls in the order the device applies them: commands, then fixtures, then joints
+            for i, (w, body, op, wake, v, p) in enumerate(cmds):
+                if op == B.CMD_SET_FILTER:
+                    refs[w].set_filter(wake, *filters[i])
+                else:
+                    refs[w].command(body, op, wake, v, p)
+                counts[op] = counts.get(op, 0) + 1
+            if cmds:
+                arr = np.array(cmds, dtype=B.BODY_COMMAND_DTYPE)
+                for i, f in filters.items():
+                    B.put_filter(arr, i, *f)
+                batch.body_commands(arr)
+            if attach:
+                want = [refs[w].create_fixture(body, fds[0], verts) for (w, body, fds, verts) in attach]
+                got = batch.create_fixtures(attach)
+                assert got.tolist() == want
+                for (w, body, *_), fx in zip(attach, want):
+                    fixtures[w][fx] = body
+                counts["fixture"] = counts.get("fixture", 0) + len(attach)
+            if new_joints:
+                want = [refs[w].create_joint(jd) for (w, jd) in new_joints]
+                got = batch.create_joints(new_joints)
+                assert got.tolist() == want
+                for (w, _), j in zip(new_joints, want):
+                    joints[w].add(j)
+                counts["joint"] = counts.get("joint", 0) + len(new_joints)
+            for w, r in enumerate(refs):
+                compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} after edits at step {step}")
+        for r in refs:
+            r.step(1 / 60, 8, 3)
+        batch.step(1 / 60, 8, 3)
+        for w, r in enumerate(refs):
+            compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} step {step}")
+    assert (batch.status() == 0).all(), batch.status()
+    assert all(counts.get(k, 0) > 20 for k in (B.CMD_SET_FILTER, B.CMD_SET_TYPE, B.CMD_SET_ACTIVE, B.CMD_SET_MASS_DATA,
+                                               B.CMD_DESTROY_FIXTURE, "fixture", "joint")), counts
+    assert counts.get(B.CMD_DESTROY_JOINT, 0) > 10, counts
+    batch.close()
