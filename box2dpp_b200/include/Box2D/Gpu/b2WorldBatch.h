@@ -19,8 +19,10 @@
 //   b2ContactListener, b2ContactImpulse       Dynamics/b2WorldCallbacks.h:74-136
 //
 // Differences a caller must know:
-//   * Worlds are frozen at the first Step: CreateBody / CreateFixture afterwards return nullptr, exactly like a
-//     locked reference world does (b2World.cpp:100-104).  DestroyBody, joints, queries are out of scope.
+//   * The scene is recorded on the host until the first Step (or the first call that needs the device); from then on
+//     CreateBody / CreateFixture / CreateJoint / DestroyBody / DestroyFixture / DestroyJoint and the b2Body / b2Fixture
+//     setters below act on the running worlds with the reference's semantics (arena headroom: SetSpawnHeadroom,
+//     SetJointHeadroom).  Gear and mouse joints can only be created while the scene is open.
 //   * Shapes record HOW they were built (SetAsBox / Set / CreateChain ...); hulls, normals, mass data and fat
 //     AABBs are computed by the host layer of libb2gpu.so with the reference's arithmetic when the batch is built.
 //   * Listener callbacks are delivered after Step from the device's readback buffer, in the reference's order,
@@ -327,6 +329,8 @@ public:
     void* GetUserData() const { return m_userData; }
     b2Shape::Type GetType() const { return m_type; }
     int32_t GetIndex() const { return m_index; }  // creation order within the world
+    // b2Fixture::SetFilterData (b2Fixture.cpp:185-215): the fixture's contacts are re-filtered at the next Step
+    void SetFilterData(const b2Filter& filter);
 
 private:
     friend class b2Body;
@@ -334,6 +338,11 @@ private:
     void* m_userData = nullptr;
     b2Shape::Type m_type = b2Shape::e_circle;
     int32_t m_index = 0;
+};
+struct b2MassData {  // Collision/Shapes/b2Shape.h:27-38
+    float mass = 0.0f;
+    b2Vec<float, 2> center{{0.0f, 0.0f}};
+    float I = 0.0f;
 };
 
 // ---- listener: b2ContactListener over the readback buffer -------------------------------------------
@@ -394,11 +403,19 @@ public:
     void SetAngularVelocity(float omega);
     void SetTransform(const b2Vec<float, 2>& position, float angle);
     void SetAwake(bool flag);
+    // Edits that change what a body is (b2Body.cpp:115-166, 216-281, 283-394, 455-510): applied on the device before the
+    // next Step; calling one while the scene is still open builds the batch first.
+    void SetType(b2BodyType type);
+    void SetActive(bool flag);
+    void SetMassData(const b2MassData* data);
+    void ResetMassData();
+    void DestroyFixture(b2Fixture* fixture);  // the b2Fixture object stays allocated (its index is reserved)
 
 private:
     friend class b2World;
     friend class b2WorldBatch;
     friend class b2Joint;
+    friend class b2Fixture;
     void SetMouseTarget(const b2Vec<float, 2>& target);  // b2Joint::SetTarget of the mouse joint attached to this body
     // While the scene is still being recorded (no Step yet) edits are queued and getters are answered on the host from
     // this shadow of the body's definition, so a `body->SetLinearVelocity(..)` or `jd.Initialize(a, b, a->GetWorldCenter())`
@@ -429,8 +446,11 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
-    // b2World::CreateJoint (b2World.cpp:211-270) for all eleven joint types; throws once the batch is built (first Step)
+    // b2World::CreateJoint (b2World.cpp:211-270) for all eleven joint types; on a running world every type but gear and
+    // mouse (they read body state when they are constructed: create those before the first Step)
     b2Joint* CreateJoint(const b2JointDef* def);
+    // b2World::DestroyJoint (b2World.cpp:267-360); the b2Joint object stays allocated (its index is reserved)
+    void DestroyJoint(b2Joint* joint);
     // b2World::DestroyBody (b2World.cpp:124-203): queued like the b2Body edits; the body's joints, contacts and proxies go
     // with it on the device.  The b2Body object stays allocated (its index is reserved) but must not be used again.
     // EndContact events of the destruction are in the readback buffer (b2gpu_batch_read_events) until the next Step.
@@ -454,6 +474,7 @@ public:
 
 private:
     friend class b2Body;
+    friend class b2Fixture;
     friend class b2WorldBatch;
     b2World(b2WorldBatch* batch, int32_t index, const b2Vec<float, 2>& gravity) : m_batch(batch), m_index(index), m_gravity(gravity) {}
     void SetFlag(int bit, bool on);
@@ -496,6 +517,8 @@ public:
     void SetSpawnHeadroom(int32_t bodies, int32_t fixtures, int32_t proxies, int32_t shapeWords, int32_t chainVertices) {
         m_headroom[0] = bodies; m_headroom[1] = fixtures; m_headroom[2] = proxies; m_headroom[3] = shapeWords; m_headroom[4] = chainVertices;
     }
+    // Room per world for joints created after the first Step (b2World::CreateJoint on a running world); before the first Step.
+    void SetJointHeadroom(int32_t joints) { m_jointHeadroom = joints; }
     void SetContactListener(b2ContactListener* listener) {
         if (m_handle && listener && !m_eventMask) throw std::runtime_error("SetContactListener must precede the first Step");
         m_listener = listener;
@@ -553,6 +576,7 @@ public:
 private:
     friend class b2World;
     friend class b2Body;
+    friend class b2Fixture;
     static void Check(int rc) {
         if (rc != B2GPU_OK) throw std::runtime_error(std::string("b2gpu: ") + b2gpu_last_error());
     }
@@ -571,6 +595,7 @@ private:
             m_headroom[0] = nb / 2 + 16; m_headroom[1] = nf / 2 + 16; m_headroom[2] = np / 2 + 16;
             m_headroom[3] = 64 * (nf / 2 + 16); m_headroom[4] = nv / 2 + 64;
         }
+        if (m_jointHeadroom == 0) m_jointHeadroom = 8;
         Build();
     }
     void Build() {
@@ -602,6 +627,7 @@ private:
         Check(b2gpu_scene_capacities(scenes.data(), desc.numWorlds, &desc));
         desc.maxBodies += m_headroom[0]; desc.maxFixtures += m_headroom[1]; desc.maxProxies += m_headroom[2];
         desc.maxShapeWords += m_headroom[3]; desc.maxChainVerts += m_headroom[4];
+        desc.maxJoints += m_jointHeadroom;
         if (m_headroom[2] > 0 && m_maxContacts == 0) desc.maxContacts += 4 * m_headroom[2];
         if (desc.eventMask && m_maxEvents == 0 && desc.maxEvents < 3 * desc.maxContacts) desc.maxEvents = 3 * desc.maxContacts;
         Check(b2gpu_batch_create(&desc, &m_handle));
@@ -616,6 +642,7 @@ private:
         m_maxEventsBuilt = desc.maxEvents;
     }
     void Queue(const b2Body* b, int32_t op, bool wake, float vx, float vy, float px, float py);
+    void QueueEdit(const b2Body* b, int32_t op, int32_t arg, float vx, float vy, float px, float py);
     void Flush() {  // queued body edits and bodies created on the running worlds -> device, in call order
         FlushCommands();
         FlushSpawns();
@@ -686,6 +713,7 @@ private:
     std::vector<float> m_xf, m_sweep, m_vel;
     std::vector<b2gpu_body_command> m_commands;
     int32_t m_headroom[5] = {0, 0, 0, 0, 0};
+    int32_t m_jointHeadroom = 0;
     bool m_destroyedWhileOpen = false;  // DestroyBody before the first Step (see b2World::CreateBody)
     // bodies created after the first Step, not yet on the device (only commands OR spawns are pending at any time, so
     // that the device sees creations and edits in call order)
@@ -761,9 +789,9 @@ inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
 inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
     b2World& w = B2_SELF;
     if (!def->bodyA || !def->bodyB) return nullptr;
-    if (w.m_batch->IsBuilt())
-        throw std::runtime_error("b2World::CreateJoint on a running world is not supported: create joints before the first Step "
-                                 "(or before the first call that reads device state)");
+    const bool running = w.m_batch->IsBuilt();
+    if (running && (def->type == b2JointType::GEAR_JOINT || def->type == b2JointType::MOUSE_JOINT))
+        throw std::runtime_error("gear and mouse joints read body state when they are constructed: create them before the first Step");
     b2g_joint_def d;
     std::memset(&d, 0, sizeof(d));
     d.bodyA = def->bodyA->GetIndex();
@@ -839,7 +867,16 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
     } else {
         return nullptr;
     }
-    w.m_jointDefs.push_back(d);
+    if (running) {  // b2World::CreateJoint on the running world, after everything queued before it
+        b2WorldBatch* B = w.m_batch;
+        B->Flush();
+        int32_t id = -1;
+        b2WorldBatch::Check(b2gpu_batch_create_joints(B->m_handle, &w.m_index, &d, 1, &id));
+        if (id != (int32_t)w.m_joints.size()) throw std::runtime_error("b2gpu: the world's joint arena is full (SetJointHeadroom)");
+        B->m_stateValid = false;
+    } else {
+        w.m_jointDefs.push_back(d);
+    }
     std::unique_ptr<b2Joint> j(new b2Joint);
     j->m_type = def->type;
     j->m_bodyA = w.m_bodies[d.bodyA].get();
@@ -848,6 +885,17 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
     j->m_index = (int32_t)w.m_joints.size();
     w.m_joints.push_back(std::move(j));
     return w.m_joints.back().get();
+}
+inline void b2World::DestroyJoint(b2Joint* joint) {
+    b2World& w = B2_SELF;
+    if (!joint || joint->GetIndex() < 0 || joint->GetIndex() >= (int32_t)w.m_joints.size() || w.m_joints[joint->GetIndex()].get() != joint) return;
+    b2WorldBatch* B = w.m_batch;
+    B->BuildEarly();
+    B->FlushSpawns();
+    b2gpu_body_command c;
+    std::memset(&c, 0, sizeof(c));
+    c.world = w.m_index; c.op = B2GPU_CMD_DESTROY_JOINT; c.wake = joint->GetIndex();
+    B->m_commands.push_back(c);
 }
 inline void b2World::DestroyBody(b2Body* body) {
     if (!body || body->GetWorld() != &(B2_SELF)) return;
@@ -871,9 +919,9 @@ inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
     if (!def->shape) return nullptr;
     b2WorldBatch* B = w.m_batch;
     const bool running = B->IsBuilt();
-    // on a running world fixtures can only be given to the body created last (before anything else was queued):
-    // b2gpu_batch_create_bodies takes a body with its fixtures in one record
-    if (running && (B->m_spawnBodies.empty() || B->m_spawnBodies.back() != this)) return nullptr;
+    // on a running world the body created last (nothing else queued since) takes its fixtures in its spawn record
+    // (b2gpu_batch_create_bodies); any other body gets them through b2gpu_batch_create_fixtures, at once
+    const bool attach = running && (B->m_spawnBodies.empty() || B->m_spawnBodies.back() != this);
     b2g_fixture_def fd;
     std::memset(&fd, 0, sizeof(fd));
     fd.body = m_index;
@@ -884,7 +932,17 @@ inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
     fd.categoryBits = def->filter.categoryBits;
     fd.maskBits = def->filter.maskBits;
     fd.groupIndex = def->filter.groupIndex;
-    if (running) {
+    if (attach) {
+        B->Flush();
+        std::vector<float> verts;
+        def->shape->Describe(fd, verts);
+        b2gpu_attach at;
+        at.world = w.m_index; at.body = m_index; at.firstFixture = 0; at.fixtureCount = 1;
+        int32_t idx = -1;
+        b2WorldBatch::Check(b2gpu_batch_create_fixtures(B->m_handle, &at, 1, &fd, verts.empty() ? nullptr : verts.data(), &idx));
+        if (idx != (int32_t)w.m_fixtures.size()) throw std::runtime_error("b2gpu: a world's arenas are full (SetSpawnHeadroom)");
+        B->m_stateValid = false;
+    } else if (running) {
         def->shape->Describe(fd, B->m_spawnVertices);
         B->m_spawnFixtures.push_back(fd);
         B->m_spawns.back().fixtureCount += 1;
@@ -1162,6 +1220,40 @@ inline void b2Body::SetTransform(const b2Vec<float, 2>& position, float angle) {
 }
 inline void b2Body::SetAwake(bool flag) {
     m_world->m_batch->Queue(this, B2GPU_CMD_SET_AWAKE, flag, 0.0f, 0.0f, 0.0f, 0.0f);
+}
+// The edits below only exist on the device: a scene that is still open is built first.
+inline void b2WorldBatch::QueueEdit(const b2Body* b, int32_t op, int32_t arg, float vx, float vy, float px, float py) {
+    BuildEarly();
+    FlushSpawns();
+    b2gpu_body_command c;
+    c.world = b->m_world->m_index; c.body = b->m_index; c.op = op; c.wake = arg;
+    c.v[0] = vx; c.v[1] = vy; c.p[0] = px; c.p[1] = py;
+    m_commands.push_back(c);
+}
+inline void b2Body::SetType(b2BodyType type) {
+    if (type == m_type) return;
+    m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_TYPE, (int32_t)type, 0.0f, 0.0f, 0.0f, 0.0f);
+    m_type = type;
+}
+inline void b2Body::SetActive(bool flag) { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_ACTIVE, flag ? 1 : 0, 0.0f, 0.0f, 0.0f, 0.0f); }
+inline void b2Body::SetMassData(const b2MassData* d) {
+    m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_MASS_DATA, 0, d->mass, d->I, d->center[0], d->center[1]);
+}
+inline void b2Body::ResetMassData() { m_world->m_batch->QueueEdit(this, B2GPU_CMD_RESET_MASS_DATA, 0, 0.0f, 0.0f, 0.0f, 0.0f); }
+inline void b2Body::DestroyFixture(b2Fixture* fixture) {
+    if (!fixture || fixture->GetBody() != this) return;
+    m_world->m_batch->QueueEdit(this, B2GPU_CMD_DESTROY_FIXTURE, fixture->GetIndex(), 0.0f, 0.0f, 0.0f, 0.0f);
+    fixture->m_body = nullptr;
+}
+inline void b2Fixture::SetFilterData(const b2Filter& filter) {
+    if (!m_body) return;
+    const int32_t bits = (int32_t)((uint32_t)filter.categoryBits | ((uint32_t)filter.maskBits << 16)), group = filter.groupIndex;
+    float v[2];
+    std::memcpy(&v[0], &bits, 4);  // the two integers travel as bit patterns in the command's float slots
+    std::memcpy(&v[1], &group, 4);
+    b2WorldBatch* B = m_body->m_world->m_batch;
+    B->QueueEdit(m_body, B2GPU_CMD_SET_FILTER, m_index, 0.0f, 0.0f, 0.0f, 0.0f);
+    std::memcpy(B->m_commands.back().v, v, 8);
 }
 
 }  // namespace box2d

@@ -92,13 +92,13 @@ int main(int argc, char** argv) {
         std::printf("%08x %08x %08x %08x %08x %08x\n", bits(p[0]), bits(p[1]), bits(probe[w]->GetAngle()), bits(v[0]), bits(v[1]),
                     bits(probe[w]->GetAngularVelocity()));
     }
-    // creating a joint on the running world is an error, not a silent nullptr
+    // a joint that connects a body to itself is an error (on the running world too), not a silent nullptr
     try {
         b2RevoluteJointDef jd;
         jd.bodyA = probe[0];
         jd.bodyB = probe[0];
         batch[0].CreateJoint(&jd);
-        std::fprintf(stderr, "CreateJoint on a running world did not throw\n");
+        std::fprintf(stderr, "CreateJoint of a body with itself did not throw\n");
         return 3;
     } catch (const std::exception&) {
     }

@@ -1,0 +1,79 @@
+// The reference's edit calls on running worlds through the C++ mirror (Box2D/Gpu/b2WorldBatch.h):
+// b2World::CreateJoint / DestroyJoint, b2Body::CreateFixture on an existing body, DestroyFixture, SetType, SetActive,
+// SetMassData, b2Fixture::SetFilterData.
+//
+// World 0 is built completely before the first Step; world 1 gets its second fixture and its joint AFTER the batch exists
+// (the running-world path).  Both are the same sequence of reference calls, so their state must agree bit for bit.
+#include <cstdio>
+#include <cstring>
+
+#include "Box2D/Gpu/b2WorldBatch.h"
+
+using namespace box2d;
+
+static unsigned bits(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+
+int main() {
+    b2WorldBatch batch(b2Vec<float, 2>{{0.0f, -10.0f}}, 3);
+    b2Body* arm[3];
+    b2Body* ground[3];
+    b2Fixture* extra[3] = {nullptr, nullptr, nullptr};
+    b2Joint* joint[3] = {nullptr, nullptr, nullptr};
+    b2PolygonShape box, plate;
+    box.SetAsBox(0.5f, 0.25f);
+    plate.SetAsBox(0.2f, 0.6f, b2Vec<float, 2>{{0.6f, 0.0f}}, 0.3f);
+    for (int w = 0; w < 3; ++w) {
+        b2World& world = batch[w];
+        b2BodyDef gd;
+        ground[w] = world.CreateBody(&gd);
+        b2PolygonShape gbox;
+        gbox.SetAsBox(20.0f, 1.0f);
+        ground[w]->CreateFixture(&gbox, 0.0f);
+        b2BodyDef bd;
+        bd.type = b2BodyType::DYNAMIC_BODY;
+        bd.position = {{1.0f, 5.0f}};
+        arm[w] = world.CreateBody(&bd);
+        arm[w]->CreateFixture(&box, 1.0f);
+        if (w == 0) {  // everything at scene time
+            extra[w] = arm[w]->CreateFixture(&plate, 2.0f);
+            b2RevoluteJointDef jd;
+            jd.Initialize(ground[w], arm[w], b2Vec<float, 2>{{0.0f, 5.0f}});
+            joint[w] = world.CreateJoint(&jd);
+        }
+    }
+    if (batch.GetStatus() != 0) return 2;  // builds the batch: worlds 1 and 2 are running from here on
+    for (int w = 1; w < 3; ++w) {
+        extra[w] = arm[w]->CreateFixture(&plate, 2.0f);  // b2Body::CreateFixture on an existing body of a running world
+        b2RevoluteJointDef jd;
+        jd.Initialize(ground[w], arm[w], b2Vec<float, 2>{{0.0f, 5.0f}});
+        joint[w] = batch[w].CreateJoint(&jd);             // b2World::CreateJoint on a running world
+        if (!extra[w] || !joint[w]) return 3;
+    }
+    for (int i = 0; i < 90; ++i) batch.Step(1.0f / 60.0f, 8, 3);
+    for (int w = 0; w < 2; ++w) {
+        const b2Vec<float, 2> p = arm[w]->GetPosition(), v = arm[w]->GetLinearVelocity();
+        std::printf("%08x %08x %08x %08x %08x %08x\n", bits(p[0]), bits(p[1]), bits(arm[w]->GetAngle()), bits(v[0]), bits(v[1]),
+                    bits(arm[w]->GetAngularVelocity()));
+    }
+    // world 2: the joint goes, the arm drops onto the ground; then it loses its plate, turns kinematic, is switched off and on
+    batch[2].DestroyJoint(joint[2]);
+    for (int i = 0; i < 60; ++i) batch.Step(1.0f / 60.0f, 8, 3);
+    const float yFallen = arm[2]->GetPosition()[1];
+    arm[2]->DestroyFixture(extra[2]);
+    b2Filter none;
+    none.maskBits = 0;
+    b2MassData md;
+    md.mass = 3.0f; md.I = 1.0f;
+    arm[2]->SetMassData(&md);
+    batch.Step(1.0f / 60.0f, 8, 3);
+    arm[2]->SetActive(false);
+    batch.Step(1.0f / 60.0f, 8, 3);
+    arm[2]->SetActive(true);
+    arm[2]->SetType(b2BodyType::KINEMATIC_BODY);
+    arm[2]->SetLinearVelocity(b2Vec<float, 2>{{0.0f, 1.0f}});
+    for (int i = 0; i < 30; ++i) batch.Step(1.0f / 60.0f, 8, 3);
+    const float yLifted = arm[2]->GetPosition()[1];
+    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
+    (void)none;
+    return 0;
+}

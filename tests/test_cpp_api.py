@@ -42,6 +42,35 @@ def edits_exe():
     return out
 
 
+def _build(name):
+    lib = os.path.join(ROOT, "box2dpp_b200")
+    if not os.path.exists(os.path.join(lib, "libb2gpu.so")):
+        pytest.skip("libb2gpu.so not built")
+    out = os.path.join(ROOT, "tests", "cpp", name)
+    cmd = ["g++", "-std=c++14", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "box2dpp_b200", "include"), os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
+           "-o", out, "-L" + lib, "-lb2gpu", "-Wl,-rpath," + lib]
+    subprocess.check_call(cmd)
+    return out
+
+
+def test_world_edits_program_compiles():
+    """The running-world edit calls of the mirror (CreateJoint, CreateFixture on an existing body, DestroyFixture, SetType ...)
+    compile warning-free against the header."""
+    _build("world_edits")
+
+
+@pytest.mark.gpu
+def test_running_world_creation_equals_scene_time_creation():
+    """A fixture and a joint given to a running world == the same calls made before the first Step, bit for bit after 90
+    steps; DestroyJoint / DestroyFixture / SetMassData / SetActive / SetType / SetLinearVelocity behave (tests/cpp/world_edits.cpp)."""
+    r = subprocess.run([_build("world_edits")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    rows = r.stdout.strip().splitlines()
+    assert len(rows) == 3 and rows[0] == rows[1], rows
+    assert rows[2] == "edits ok", rows
+
+
 def test_edits_and_getters_before_the_first_step_do_not_freeze_the_scene(edits_exe):
     """b2Body setters / getters right after CreateBody and joint defs initialised from GetWorldCenter() (the reference's
     usual construction patterns) are served on the host: no device batch, the scene stays open.  Needs no GPU."""
