@@ -88,10 +88,12 @@ B2G_HD float FindMaxSeparation(int* edgeIndex, const P1& poly1, Xf xf1, const P2
     Xf xf = MulT(xf2, xf1);
     int bestIndex = 0;
     float maxSeparation = -kMaxFloat;
+#pragma unroll
     for (int i = 0; i < count1; ++i) {
         Vec2 n = Mul(xf.q, poly1.normal(i));
         Vec2 v1 = Mul(xf, poly1.vert(i));
         float si = kMaxFloat;
+#pragma unroll
         for (int j = 0; j < count2; ++j) {
             float sij = Dot(n, poly2.vert(j) - v1);
             if (sij < si) si = sij;
@@ -112,6 +114,7 @@ B2G_HD void FindIncidentEdge(ClipVertex c[2], const P1& poly1, Xf xf1, int edge1
     int count2 = poly2.count();
     int index = 0;
     float minDot = kMaxFloat;
+#pragma unroll
     for (int i = 0; i < count2; ++i) {
         float dot = Dot(normal1, poly2.normal(i));
         if (dot < minDot) {

@@ -63,6 +63,19 @@ struct DevPoly {
         return V2(ld((4 + 2 * n + 2 * i) * kTile), ld((5 + 2 * n + 2 * i) * kTile));
     }
 };
+// The same table entry with a vertex count known at compile time: the loops of the SAT and of the clipping unroll, every
+// vertex / normal load gets a constant offset, and the whole address arithmetic of the inner loops disappears.
+template <int N>
+struct DevPolyN {
+    const float* w;
+    __device__ __forceinline__ float ld(int k) const { return __ldg(w + k); }
+    __device__ __forceinline__ explicit DevPolyN(const float* base) : w(base) {}
+    __device__ __forceinline__ constexpr int count() const { return N; }
+    __device__ __forceinline__ float radius() const { return ld(1 * kTile); }
+    __device__ __forceinline__ Vec2 centroid() const { return V2(ld(2 * kTile), ld(3 * kTile)); }
+    __device__ __forceinline__ Vec2 vert(int i) const { return V2(ld((4 + 2 * i) * kTile), ld((5 + 2 * i) * kTile)); }
+    __device__ __forceinline__ Vec2 normal(int i) const { return V2(ld((4 + 2 * N + 2 * i) * kTile), ld((5 + 2 * N + 2 * i) * kTile)); }
+};
 __device__ __forceinline__ CircleData LoadCircle(const float* w) {
     CircleData c;
     c.radius = w[0];
@@ -213,6 +226,11 @@ __device__ __forceinline__ void EvaluateContact(const Arena& A, int tile, int la
     const float* wB = A.shapeWords + ((size_t)tile * A.NS + shapeOffB) * kTile + lane;
     int tA = shapeTypes & 3, tB = (shapeTypes >> 2) & 3;
     if (tA == B2G_SHAPE_POLYGON && tB == B2G_SHAPE_POLYGON) {
+#ifndef B2G_NO_BOX_FAST_PATH
+        // quadrilaterals against quadrilaterals (every SetAsBox pair): the same functions with the counts as constants
+        if (__float_as_int(__ldg(wA)) == 4 && __float_as_int(__ldg(wB)) == 4) CollidePolygons(m, DevPolyN<4>(wA), xfA, DevPolyN<4>(wB), xfB);
+        else
+#endif
         CollidePolygons(m, DevPoly(wA), xfA, DevPoly(wB), xfB);
     } else if (tA == B2G_SHAPE_CIRCLE && tB == B2G_SHAPE_CIRCLE) {
         CollideCircles(m, LoadCircle(wA), xfA, LoadCircle(wB), xfB);
