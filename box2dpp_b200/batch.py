@@ -136,6 +136,7 @@ def lib():
         L.b2gpu_batch_build_worlds.argtypes = [vp, C.POINTER(CScene), i32, i32, i32]
         L.b2gpu_host_polygon_build.argtypes = [C.POINTER(FixtureDef), vp, vp]
         L.b2gpu_host_sincosf.argtypes = [vp, vp, vp, C.c_int64]
+        L.b2gpu_host_sincosf_wide.argtypes = [vp, vp, vp, C.c_int64]
         L.b2gpu_sincosf.argtypes = [i32, vp, vp, vp, C.c_int64]
         L.b2gpu_collide_pairs.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp]
         _lib = L

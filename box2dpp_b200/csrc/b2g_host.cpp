@@ -950,6 +950,21 @@ int b2gpu_host_body_mass_data(const b2g_scene* scene, int32_t body, float* out) 
     return B2GPU_OK;
 }
 
+// The branch-free |x| < 120 arithmetic the position solver runs inline (b2g_math.cuh MakeRotWideRange), exposed for the
+// bit-parity test against libm; arguments outside that range take SinCos like the solver's fallback does.
+int b2gpu_host_sincosf_wide(const float* x, float* s, float* c, int64_t n) {
+    if (!x || !s || !c || n < 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    for (int64_t i = 0; i < n; ++i) {
+        if (InSinCosWideRange(x[i])) {
+            const Rot q = MakeRotWideRange(x[i]);
+            s[i] = q.s; c[i] = q.c;
+        } else {
+            SinCos(x[i], &s[i], &c[i]);
+        }
+    }
+    return B2GPU_OK;
+}
+
 int b2gpu_host_sincosf(const float* x, float* s, float* c, int64_t n) {
     if (!x || !s || !c || n < 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
     for (int64_t i = 0; i < n; ++i) SinCos(x[i], &s[i], &c[i]);

@@ -310,6 +310,47 @@ B2G_HD Rot MakeRotFastRange(float y) {
     return q;
 }
 
+// The same for |y| < 120 (the range glibc reduces with one multiply and one fused multiply-add, SinCosGeneral's second
+// branch), still branch-free: quadrant n = round(y * 2/pi), reduced argument x - n * pi/2, the two polynomials on it, then
+// sign and swap by quadrant.  Negating every coefficient of the cosine polynomial (glibc's second table) negates its value
+// exactly, and the sine polynomial is odd in its argument, so the signs are applied to the results.  Bodies that have
+// turned further than pi/4 (anything that rolls or tumbles) stay on the sequential solver's straight-line path with it.
+B2G_HD bool InSinCosWideRange(float y) { return ((AsUint(y) >> 20) & 0x7ff) < ((0x42f00000u >> 20) & 0x7ff); }
+B2G_HD Rot MakeRotWideRange(float y) {
+    const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10,
+                 c4 = 0x1.99343027bf8c3p-16;
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    const uint32_t top = (AsUint(y) >> 20) & 0x7ff;
+    const bool reduce = top >= ((0x3f490fdbu >> 20) & 0x7ff);  // |y| >= pi/4
+    const double x0 = (double)y;
+    const double r = b2g_dmul(x0, hpi_inv);
+    const int nr = ((int32_t)r + 0x800000) >> 24;
+    const int n = reduce ? nr : 0;
+    const double xr = b2g_fma(-(double)nr, hpi, x0);
+    const double x = reduce ? xr : x0;
+    const double x2 = b2g_dmul(x, x);
+    const double x3 = b2g_dmul(x, x2);
+    const double sA = b2g_fma(x2, s3, s2);
+    const double x7 = b2g_dmul(x3, x2);
+    const double sB = b2g_fma(x3, s1, x);
+    float sinPoly = (float)b2g_fma(x7, sA, sB);
+    const double x4 = b2g_dmul(x2, x2);
+    const double cA = b2g_fma(x2, c4, c3);
+    const double cB = b2g_fma(x2, c1, c0);
+    const double x6 = b2g_dmul(x4, x2);
+    const double cC = b2g_fma(x4, c2, cB);
+    float cosPoly = (float)b2g_fma(x6, cA, cC);
+    const int q = n & 3;
+    sinPoly = (q == 1 || q == 2) ? -sinPoly : sinPoly;  // sign[n & 3] multiplies the odd polynomial's argument
+    cosPoly = (n & 2) ? -cosPoly : cosPoly;             // the negated coefficient table
+    const bool tiny = top < ((0x39800000u >> 20) & 0x7ff);  // |y| < 2^-12
+    Rot o;
+    o.s = tiny ? y : ((n & 1) ? cosPoly : sinPoly);
+    o.c = tiny ? 1.0f : ((n & 1) ? sinPoly : cosPoly);
+    return o;
+}
+
 B2G_HD Rot MakeRot(float angle) {
     Rot q;
     SinCos(angle, &q.s, &q.c);

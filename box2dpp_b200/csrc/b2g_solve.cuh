@@ -1006,9 +1006,11 @@ __device__ __forceinline__ void FinishPosRecord(PosRecord& r, bool active, BodyT
 // One manifold point of SolvePositionConstraints (b2ContactSolver.cpp:687-734; b2PositionSolverManifold :614-664).
 // e_faceA / e_faceB are the same arithmetic with the bodies' roles swapped: selected, not branched on (lane = world,
 // a warp holds both kinds); CIRCLES adds the e_circles arithmetic beside it, again selected.
-// FASTROT: sinf / cosf by the |angle| < pi/4 arithmetic only; `slow` is set when that was not valid for one of the two
-// angles (the caller then redoes the contact with FASTROT = false).
-template <bool CIRCLES, bool FASTROT>
+// ROT: how sinf / cosf are evaluated.  kRotNarrow: the |angle| < pi/4 arithmetic only; kRotWide: the |angle| < 120
+// arithmetic (quadrant reduction, still branch-free: tiles with bodies that roll or tumble); `slow` is set when that was
+// not valid for one of the two angles (the caller then redoes the contact with kRotAny, the full function).
+enum : int { kRotAny = 0, kRotNarrow = 1, kRotWide = 2 };
+template <bool CIRCLES, int ROT>
 __device__ __forceinline__ float SolvePositionPoint(const PosRecord& r, Vec2 lp, Vec2& cAp, float& aA, Vec2& cBp, float& aB,
                                                     bool& slow) {
     const int mtype = r.info & 3;
@@ -1017,10 +1019,14 @@ __device__ __forceinline__ float SolvePositionPoint(const PosRecord& r, Vec2 lp,
     const Vec2 localNormal = V2(r.r0.x, r.r0.y), localPoint = V2(r.r0.z, r.r0.w);
     const float radiusA = r.r4.x, radiusB = r.r4.y;
     Xf xfA, xfB;
-    if (FASTROT) {
+    if (ROT == kRotNarrow) {
         slow = slow || !InSinCosFastRange(aA) || !InSinCosFastRange(aB);
         xfA.q = MakeRotFastRange(aA);
         xfB.q = MakeRotFastRange(aB);
+    } else if (ROT == kRotWide) {
+        slow = slow || !InSinCosWideRange(aA) || !InSinCosWideRange(aB);
+        xfA.q = MakeRotWideRange(aA);
+        xfB.q = MakeRotWideRange(aB);
     } else {
         xfA.q = MakeRot(aA);
         xfB.q = MakeRot(aB);
@@ -1084,8 +1090,8 @@ __device__ __noinline__ PosContactResult SolvePositionContactAnyAngle(float4 r0,
     float aA = bv.aw, aB = bv.bw;
     bool slow = false;
     PosContactResult o;
-    o.minSeparation = SolvePositionPoint<true, false>(r, V2(r1.x, r1.y), cAp, aA, cBp, aB, slow);
-    if (info & 16) o.minSeparation = Min(o.minSeparation, SolvePositionPoint<true, false>(r, V2(r1.z, r1.w), cAp, aA, cBp, aB, slow));
+    o.minSeparation = SolvePositionPoint<true, kRotAny>(r, V2(r1.x, r1.y), cAp, aA, cBp, aB, slow);
+    if (info & 16) o.minSeparation = Min(o.minSeparation, SolvePositionPoint<true, kRotAny>(r, V2(r1.z, r1.w), cAp, aA, cBp, aB, slow));
     o.bv.ax = cAp.x; o.bv.ay = cAp.y; o.bv.aw = aA;
     o.bv.bx = cBp.x; o.bv.by = cBp.y; o.bv.bw = aB;
     return o;
@@ -1197,8 +1203,9 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
     const int nK = Keep(n), nMaxK = Keep(nMax);
     StsF(scratch, 0.0f); StsF(scratch + 128, 0.0f); StsF(scratch + 256, 0.0f);  // angle 0: the fast sinf / cosf path
 
-    auto runPasses = [&](auto circlesTag) {
+    auto runPasses = [&](auto circlesTag, auto rotTag) {
         constexpr bool CIRCLES = decltype(circlesTag)::value;
+        constexpr int ROT = decltype(rotTag)::value;
         int base = 0;  // ring index of this pass's record 0
         auto stageOf = [&](int k) { return stage0 + ((uint32_t)k & mask) * kPosStageBytes; };
         auto emptyOf = [&](int k) { return empty0 + (((uint32_t)k & mask) << 3); };
@@ -1236,10 +1243,10 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
                     Vec2 cAp = V2(bv.ax, bv.ay), cBp = V2(bv.bx, bv.by);
                     float aA = bv.aw, aB = bv.bw;
                     bool slow = false;
-                    const float s0 = SolvePositionPoint<CIRCLES, true>(cur, V2(cur.r1.x, cur.r1.y), cAp, aA, cBp, aB, slow);
+                    const float s0 = SolvePositionPoint<CIRCLES, ROT>(cur, V2(cur.r1.x, cur.r1.y), cAp, aA, cBp, aB, slow);
                     Vec2 cAp2 = cAp, cBp2 = cBp;
                     float aA2 = aA, aB2 = aB;
-                    const float s1 = SolvePositionPoint<CIRCLES, true>(cur, V2(cur.r1.z, cur.r1.w), cAp2, aA2, cBp2, aB2, slow);
+                    const float s1 = SolvePositionPoint<CIRCLES, ROT>(cur, V2(cur.r1.z, cur.r1.w), cAp2, aA2, cBp2, aB2, slow);
                     BodyVals nb;
                     nb.ax = two ? cAp2.x : cAp.x; nb.ay = two ? cAp2.y : cAp.y; nb.aw = two ? aA2 : aA;
                     nb.bx = two ? cBp2.x : cBp.x; nb.by = two ? cBp2.y : cBp.y; nb.bw = two ? aB2 : aB;
@@ -1286,9 +1293,9 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
                         Vec2 cAp = V2(bv.ax, bv.ay), cBp = V2(bv.bx, bv.by);
                         float aA = bv.aw, aB = bv.bw;
                         bool slow = false;
-                        minSeparation = Min(minSeparation, SolvePositionPoint<true, false>(r, V2(r.r1.x, r.r1.y), cAp, aA, cBp, aB, slow));
+                        minSeparation = Min(minSeparation, SolvePositionPoint<true, kRotAny>(r, V2(r.r1.x, r.r1.y), cAp, aA, cBp, aB, slow));
                         if (r.info & 16)
-                            minSeparation = Min(minSeparation, SolvePositionPoint<true, false>(r, V2(r.r1.z, r.r1.w), cAp, aA, cBp, aB, slow));
+                            minSeparation = Min(minSeparation, SolvePositionPoint<true, kRotAny>(r, V2(r.r1.z, r.r1.w), cAp, aA, cBp, aB, slow));
                         bv.ax = cAp.x; bv.ay = cAp.y; bv.aw = aA;
                         bv.bx = cBp.x; bv.by = cBp.y; bv.bw = aB;
                         StoreBodyVals(r.pA, r.pB, bv);
@@ -1360,8 +1367,20 @@ __global__ void __launch_bounds__(128) k_solve_position(Arena A, int posIters) {
             if (!more) break;
         }
     };
-    if (anyCircles) runPasses(std::true_type());
-    else runPasses(std::false_type());
+    // Which arithmetic the tile's steps evaluate: has any body of any of its worlds turned further than pi/4 (anything that
+    // rolls or tumbles)?  Then the wide-range sinf / cosf (and the e_circles arithmetic with it: one variant fewer).
+    bool turned = false;
+    {
+        const int nb = A.bodyCount[ws];
+        for (int b = 0; b < nb; ++b) turned |= !InSinCosFastRange(LdsF(T.at(b) + 256));
+    }
+#ifdef B2G_NO_WIDE_ROT  // A/B knob: turned bodies take the out-of-line full-range path, as before
+    turned = false;
+#endif
+    const bool anyTurned = __any_sync(0xffffffffu, turned);
+    if (anyTurned) runPasses(std::true_type(), std::integral_constant<int, kRotWide>());
+    else if (anyCircles) runPasses(std::true_type(), std::integral_constant<int, kRotNarrow>());
+    else runPasses(std::false_type(), std::integral_constant<int, kRotNarrow>());
     for (int wd = 0; wd < doneWords; ++wd) gDone[(size_t)wd * kTile] = (int)sDone[wd * kTile];
     FenceProxyAsync();
     __syncwarp();

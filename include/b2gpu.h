@@ -397,6 +397,9 @@ int b2gpu_host_body_mass_data(const b2g_scene* scene, int32_t body, float* out);
 /* b2Rot::Set(angle) (Box2D/Common/b2Math.h:302-311) as the host layer evaluates it: the library's own
  * sinf / cosf, bit-identical to the libm the reference links (tests/test_sincos.py).  Host code, no device. */
 int b2gpu_host_sincosf(const float* x, float* s, float* c, int64_t n);
+/* The same values through the branch-free |x| < 120 arithmetic the position solver evaluates inline (b2g_math.cuh
+ * MakeRotWideRange); exported for the bit-parity test. */
+int b2gpu_host_sincosf_wide(const float* x, float* s, float* c, int64_t n);
 
 /* ---- stateless device entry points (unit-level parity of the kernels' building blocks) -------------- */
 

@@ -34,6 +34,20 @@ def test_host_sincos_matches_libm_golden():
     assert _same(s, g["s"].view(np.float32)) and _same(c, g["c"].view(np.float32))
 
 
+def test_wide_range_inline_sincos_matches_libm_golden_and_general_path():
+    """MakeRotWideRange (|x| < 120, branch-free, what k_solve_position evaluates for turned bodies) == libm / SinCos."""
+    x = G.sincos_inputs()
+    g = np.load(os.path.join(GOLD, "sincos.npz"))
+    s, c = _call(B.lib().b2gpu_host_sincosf_wide, x)
+    assert _same(s, g["s"].view(np.float32)) and _same(c, g["c"].view(np.float32))
+    rs = np.random.RandomState(5)
+    y = np.concatenate([rs.uniform(-130, 130, 600000), rs.uniform(-1.0, 1.0, 100000), (np.arange(-160, 161) * (np.pi / 4)),
+                        np.nextafter(np.float32(np.arange(-150, 151) * (np.pi / 4)), np.float32(0))]).astype(np.float32)
+    s1, c1 = _call(B.lib().b2gpu_host_sincosf_wide, y)
+    s2, c2 = _call(B.lib().b2gpu_host_sincosf, y)
+    assert _same(s1, s2) and _same(c1, c2)
+
+
 def test_host_sincos_matches_live_libm(oracles):
     if not oracles.available("ref"):
         pytest.skip("oracle/_ref/libb2ref.so not present on this box")

@@ -26,6 +26,6 @@ B2GPU_GROUPS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control 
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 12 --warmup 3 --preroll 290 --worlds-per-gpu $WORLDS --no-cpu-baseline --e2e-steps 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -3 gpurun_out/${TAG}_launches.csv
 # full capture of one kernel (a launch on the settled pyramid, well after the pre-roll)
-B2GPU_GROUPS=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:^${KERNEL}\$ -s 95 -c 1 -f \
+B2GPU_GROUPS=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:^${KERNEL} -s 95 -c 1 -f \
     -o gpurun_out/${TAG}_${KERNEL} python bench.py --steps 6 --warmup 3 --worlds-per-gpu $WORLDS --no-cpu-baseline --e2e-steps 3 > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out/
