@@ -618,12 +618,13 @@ __host__ __device__ inline size_t IslandSmemPerWorld(int NB, int NC, int NJ) {
     return (size_t)NC * 9 + (size_t)NB * 5 + (NJ > 0 ? (size_t)((NJ + 1) & ~1) * 9 + (size_t)NB * 2 : 0);
 }
 
-// The grid is persistent (a few CTAs per SM, each walking groups of L worlds): in the steady state almost every
-// group's islands are still valid, and a CTA that only reads L dirty flags must not cost a launch slot with
-// tens of KB of shared memory.
-__global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L, int numGroups) {
+// One CTA per tile of 32 worlds.  In the steady state most worlds' islands are still valid, so the CTA first compacts the
+// tile's DIRTY worlds (ballot) and then walks them L at a time (L = what fits shared memory): a settled batch in which a
+// fifth of the worlds changed a touching flag runs one round per tile instead of a CTA per L worlds, dirty or not.
+__global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L, int numTiles) {
     extern __shared__ __align__(16) unsigned char ismem[];
-    __shared__ int sDirty[kTile];
+    __shared__ int sList[kTile];
+    __shared__ int sCount;
     const int t = threadIdx.x;
     const int NB = A.NB, NC = A.NC;
     // shared arrays, element (index, l) at [index * L + l]
@@ -642,27 +643,28 @@ __global__ void __launch_bounds__(kIslandThreads) k_islands(Arena A, int L, int 
     unsigned char* sJF = sBF + (size_t)NB * L;                         // [NJe][L]: joint already in an island
     (void)NJ;
 
-    for (int gi = blockIdx.x; gi < numGroups; gi += gridDim.x) {
-    const int g = A.tile0 * (kTile / L) + gi;  // group of L worlds (L divides 32)
-    const int w0 = g * L;                      // first world of the group
-    if (t < L) {
-        const int w = w0 + t;
+    if (blockIdx.x >= numTiles) return;
+    const int tile = A.tile0 + blockIdx.x;
+    if (t < kTile) {
+        const int w = tile * kTile + t;
         int d = 0;
         if (w < A.numWorlds) {
             d = A.topoDirty[w] | A.alwaysRebuildIslands;
             if (d) A.topoDirty[w] = 0;
         }
-        sDirty[t] = d;
+        const unsigned dirty = __ballot_sync(0xffffffffu, d != 0);
+        if (d) sList[__popc(dirty & ((1u << t) - 1u))] = t;
+        if (t == 0) sCount = __popc(dirty);
     }
-    const int anyDirty = __syncthreads_or(t < L ? sDirty[t] : 0);
-    if (!anyDirty) continue;
-
-    // ---- load the contact graph and the body flags of the dirty worlds ----
-    const int l = t % L;                 // world within the group
-    const int w = w0 + l;
-    const int tile = w >> 5, lane = w & 31;
+    __syncthreads();
+    const int dirtyCount = sCount;
+    for (int r0 = 0; r0 < dirtyCount; r0 += L) {
+    // ---- load the contact graph and the body flags of this round's worlds ----
+    const int l = t % L;                 // world within the round
+    const bool mine = r0 + l < dirtyCount;
+    const int lane = mine ? sList[r0 + l] : 0;
+    const int w = tile * kTile + lane;
     const size_t ws = (size_t)tile * kTile + lane;
-    const bool mine = w < A.numWorlds && sDirty[l] != 0;
     const int nb = mine ? A.bodyCount[ws] : 0;
     const int nc = mine ? A.contactCount[ws] : 0;
     Col<int4> cA = col(A.contactA, tile, NC, lane);

@@ -1204,12 +1204,7 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
         else k_collide<false><<<tiles, kCollideWarps * 32, 0, st>>>(A);
         mark();
         if (dt > 0.0f) {
-            const int islandGroups = (tileCount * kTile + b->islandLanes - 1) / b->islandLanes;
-            // one CTA per group: a persistent grid (CTAs walking several groups) was measured 2x slower, the hardware
-            // scheduler overlaps one CTA's graph load with another's DFS better than a loop with barriers does
-            const unsigned islandCtas = (unsigned)islandGroups;
-            k_islands<<<islandCtas, kIslandThreads, b->islandSmem, st>>>(
-                A, b->islandLanes, islandGroups);
+            k_islands<<<tiles, kIslandThreads, b->islandSmem, st>>>(A, b->islandLanes, tileCount);
             mark();
             if (b->tileSolver) {
                 k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
