@@ -1422,44 +1422,68 @@ __global__ void __launch_bounds__(kPrepWarps * 32) k_solve_finalize(Arena A, flo
     const bool allowSleep = live && (A.worldFlags[ws] & B2G_WORLD_ALLOW_SLEEP) != 0;
     if (!__any_sync(0xffffffffu, allowSleep)) return;
     __syncthreads();
-    if (warp != 0 || !allowSleep) return;
-    // ---- sleep (b2Island.cpp:345-382): islands one after another, bodies in island order ----
-    const int islands = A.islandCount[ws];
+    // ---- sleep (b2Island.cpp:345-382) ----
+    // Pass 1, all warps, entries of the island body lists strided over warps: every island body's sleep time is advanced
+    // or reset, and what it contributes to its island's minSleepTime goes to a per-entry scratch column (the velocity
+    // records are dead by now).  Pass 2, warp 0: per island the minimum over its entries — one coalesced stream of
+    // independent loads instead of a chain of dependent ones per body — and, rarely, the island goes to sleep.
+    const int islands = allowSleep ? A.islandCount[ws] : 0;
     Col<int> iBodies = col(A.islandBodies, tile, A.NB + A.NC, lane);
     Col<int> iBodyEnd = col(A.islandBodyEnd, tile, A.NB, lane);
-    const int doneWords = (A.NB + 31) / 32;
-    const int* gDone = A.islandSolved + (size_t)tile * doneWords * kTile + lane;
+    float* contribution = reinterpret_cast<float*>(A.velRec + (size_t)tile * A.NC * kVelRec * kTile) + lane;  // [entry][lane]
+    const int entries = islands > 0 ? iBodyEnd[islands - 1] : 0;
+    const int entriesMax = __reduce_max_sync(0xffffffffu, entries);
     const float linTolSqr = kLinearSleepTolerance * kLinearSleepTolerance;
     const float angTolSqr = kAngularSleepTolerance * kAngularSleepTolerance;
+    for (int i = warp; i < entriesMax; i += kPrepWarps) {
+        if (i >= entries) continue;
+        const int b = iBodies[i];
+        const int f = bodyFlags[b];
+        float c = -1.0f;  // a static body: no part in the minimum; pass 2 re-wakes it in island order
+        if ((f & kBodyTypeMask) != B2G_STATIC_BODY) {
+            const float4 vel = bodyVel[b];
+            float4 sw = bodySweep[b];
+            if ((f & kBodyAutoSleep) == 0 || vel.z * vel.z > angTolSqr || Dot(V2(vel.x, vel.y), V2(vel.x, vel.y)) > linTolSqr) {
+                sw.w = 0.0f;
+            } else {
+                sw.w += h;
+            }
+            bodySweep[b] = sw;
+            c = sw.w;
+        }
+        contribution[(size_t)i * kTile] = c;
+    }
+    __syncthreads();
+    if (warp != 0 || !allowSleep) return;
+    const int doneWords = (A.NB + 31) / 32;
+    const int* gDone = A.islandSolved + (size_t)tile * doneWords * kTile + lane;
     int b0 = 0;
     for (int isl = 0; isl < islands; ++isl) {
         const int b1 = iBodyEnd[isl];
         float minSleepTime = kMaxFloat;
-        for (int i = b0; i < b1; ++i) {
-            int b = iBodies[i];
-            int f = bodyFlags[b];
-            if ((f & kBodyTypeMask) == B2G_STATIC_BODY) {
+        auto take = [&](int i, float c) {
+            if (c < 0.0f) {
                 // b2World::Solve builds and solves islands alternately: this island's DFS re-woke a static body
                 // that an earlier island of the same step had put to sleep (b2World.cpp:441)
+                const int b = iBodies[i];
+                const int f = bodyFlags[b];
                 if ((f & kBodyAwake) == 0) bodyFlags[b] = f | kBodyAwake;
-                continue;
-            }
-            float4 vel = bodyVel[b];
-            float4 sw = bodySweep[b];
-            if ((f & kBodyAutoSleep) == 0 || vel.z * vel.z > angTolSqr || Dot(V2(vel.x, vel.y), V2(vel.x, vel.y)) > linTolSqr) {
-                sw.w = 0.0f;
-                minSleepTime = 0.0f;
             } else {
-                sw.w += h;
-                minSleepTime = Min(minSleepTime, sw.w);
+                minSleepTime = Min(minSleepTime, c);
             }
-            bodySweep[b] = sw;
+        };
+        int i = b0;
+        for (; i + 4 <= b1; i += 4) {
+            const float c0 = contribution[(size_t)i * kTile], c1 = contribution[(size_t)(i + 1) * kTile];
+            const float c2 = contribution[(size_t)(i + 2) * kTile], c3 = contribution[(size_t)(i + 3) * kTile];
+            take(i, c0); take(i + 1, c1); take(i + 2, c2); take(i + 3, c3);
         }
+        for (; i < b1; ++i) take(i, contribution[(size_t)i * kTile]);
         const bool positionSolved = (gDone[(size_t)(isl >> 5) * kTile] >> (isl & 31) & 1) != 0;
         if (minSleepTime >= kTimeToSleep && positionSolved) {
             A.topoDirty[ws] = 1;
-            for (int i = b0; i < b1; ++i) {  // b2Body::SetAwake(false), b2Body.h:644-652
-                int b = iBodies[i];
+            for (int k = b0; k < b1; ++k) {  // b2Body::SetAwake(false), b2Body.h:644-652
+                int b = iBodies[k];
                 bodyFlags[b] &= ~kBodyAwake;
                 float4 sw = bodySweep[b];
                 sw.w = 0.0f;
