@@ -1294,6 +1294,14 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
     if (io) G = io->groups;
     if (G > b->A.numTiles) G = b->A.numTiles > 0 ? b->A.numTiles : 1;
     const int per = (b->A.numTiles + G - 1) / G;
+    // experiment (B2GPU_GROUP0_TILES): with two groups, group 0 takes this many tiles (e.g. one full wave of resident tiles)
+    int first = per;
+    if (G == 2 && !io) {
+        if (const char* env = getenv("B2GPU_GROUP0_TILES")) {
+            const int v = atoi(env);
+            if (v > 0 && v < b->A.numTiles) first = v;
+        }
+    }
     if (G > 1) {  // fork: every group stream waits for what is already queued on the batch's stream
         cudaEventRecord(b->evFork, st);
         for (int g = 1; g < G; ++g) cudaStreamWaitEvent(b->groupStream[g], b->evFork, 0);
@@ -1301,8 +1309,9 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
     const bool pipeline = G > 1 && b->tileSolver && dt > 0.0f && b->pipelineGroups;
     for (int i = 0; i < count; ++i) {
         for (int g = 0; g < G; ++g) {
-            const int t0 = g * per;
-            const int n = b->A.numTiles - t0 < per ? b->A.numTiles - t0 : per;
+            const int t0 = (G == 2 && g == 1) ? first : g * per;
+            const int n = (G == 2 && !io) ? (g == 0 ? first : b->A.numTiles - first)
+                                          : (b->A.numTiles - t0 < per ? b->A.numTiles - t0 : per);
             if (n <= 0) break;
             cudaStream_t gs = g == 0 ? st : b->groupStream[g];
             cudaEvent_t* mk = marks ? marks + (traceGroups ? ((size_t)g * count + i) * nkTrace : 0) : nullptr;
