@@ -937,6 +937,12 @@ struct b2gpu_batch {
     bool needInitialPairs = true;  // b2World::e_newFixture
     bool needProxyIndex = true;    // the body -> proxies index has to be (re)built before the next step
     bool anyContinuous = false;    // some world has B2G_WORLD_CONTINUOUS: the step ends with k_toi
+    // Can a dynamic body of this batch be asleep?  (a world that allows sleeping, a body built or set asleep, a restored
+    // snapshot.)  While it cannot, the forces of b2gpu_batch_step_io wake nobody, so they may reach the device behind
+    // k_collide / k_islands (which do not read them) and their host copy hides under those kernels.
+    bool maySleep = false;
+    cudaStream_t copyStream[kMaxGroups] = {nullptr};
+    cudaEvent_t evCopy[kMaxGroups] = {nullptr};
     int blockSize = 32;
     bool tileSolver = false;       // b2g_solve.cuh path: the tile's body table fits in shared memory
     size_t solveSmem = 0;
@@ -1206,13 +1212,14 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
         if (dt > 0.0f) {
             k_islands<<<tiles, kIslandThreads, b->islandSmem, st>>>(A, b->islandLanes, tileCount);
             mark();
-            if (b->tileSolver) {
-                k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
-                mark();
-            }
         }
     } else if (dt <= 0.0f) {
         return;
+    } else if (part == 3) {  // the last kernel of part 0, on its own so that late forces can be slipped in front of it
+        if (b->tileSolver) {
+            k_solve_prepare<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
+            mark();
+        }
     } else if (part == 1) {
         if (b->tileSolver) {
             if (A.hasJoints) k_solve_velocity<true><<<tiles, 128, b->solveSmem, st>>>(A, velIters, dt);
@@ -1227,11 +1234,12 @@ void enqueuePart(b2gpu_batch* b, int part, float dt, int velIters, int posIters,
             k_solve<<<blocks, threads, 0, st>>>(A, dt, velIters, posIters);
             mark();
         }
-    } else {
+    } else if (part == 4) {  // the first kernel of part 2, on its own: the poses are final behind it unless k_toi follows
         if (b->tileSolver) {
             k_solve_finalize<<<tiles, kPrepWarps * 32, 0, st>>>(A, dt);
             mark();
         }
+    } else {
         k_sync_pairs<<<tiles, kPairWarps * 32, 0, st>>>(A, dt);
         mark();
         if (b->anyContinuous) {  // if (m_continuousPhysics && step.dt > 0) SolveTOI(step)
@@ -1269,6 +1277,8 @@ int ensureGroupStreams(b2gpu_batch* b, int G) {
         if (g > 0 && !b->groupStream[g]) CUDA_TRY(cudaStreamCreateWithFlags(&b->groupStream[g], cudaStreamNonBlocking));
         if (g > 0 && !b->evJoin[g]) CUDA_TRY(cudaEventCreateWithFlags(&b->evJoin[g], cudaEventDisableTiming));
         if (!b->evSeq[g]) CUDA_TRY(cudaEventCreateWithFlags(&b->evSeq[g], cudaEventDisableTiming));
+        if (!b->copyStream[g]) CUDA_TRY(cudaStreamCreateWithFlags(&b->copyStream[g], cudaStreamNonBlocking));
+        if (!b->evCopy[g]) CUDA_TRY(cudaEventCreateWithFlags(&b->evCopy[g], cudaEventDisableTiming));
     }
     return B2GPU_OK;
 }
@@ -1302,7 +1312,7 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
             if (v > 0 && v < b->A.numTiles) first = v;
         }
     }
-    if (G > 1) {  // fork: every group stream waits for what is already queued on the batch's stream
+    if (G > 1 || io) {  // fork: every group stream waits for what is already queued on the batch's stream
         cudaEventRecord(b->evFork, st);
         for (int g = 1; g < G; ++g) cudaStreamWaitEvent(b->groupStream[g], b->evFork, 0);
     }
@@ -1322,21 +1332,40 @@ int enqueueSteps(b2gpu_batch* b, float dt, int velIters, int posIters, cudaEvent
             const int nF = b->ioForceCount, nP = b->ioPoseCount, poseFloats = b->ioPoseFormat == B2GPU_POSE_XYA ? 3 : 4;
             Arena Ag = b->A;
             Ag.tile0 = t0;
-            if (io && io->forces && w1 > w0 && nF > 0) {
-                const size_t off = (size_t)w0 * nF * 3, len = (size_t)(w1 - w0) * nF * 3;
-                const size_t items = (size_t)n * nF * kTile;
-                cudaMemcpyAsync(io->devForces + off, io->forces + off, len * sizeof(float), cudaMemcpyHostToDevice, gs);
-                k_apply_forces<<<(unsigned)((items + 255) / 256), 256, 0, gs>>>(Ag, io->devForces, n, b->ioForceSel, nF);
+            const bool haveForces = io && io->forces && w1 > w0 && nF > 0;
+            // Forces only matter from the velocity integration on (k_solve_prepare / k_solve) — unless one wakes a sleeping
+            // body, which k_collide and k_islands would have to see.  No sleepers possible: the copy runs on its own stream
+            // under k_collide / k_islands and the forces are applied behind them.
+            const bool lateForces = haveForces && !b->maySleep && dt > 0.0f && b->copyStream[g] != nullptr;
+            const size_t fOff = (size_t)w0 * nF * 3, fLen = (size_t)(w1 - w0) * nF * 3;
+            const size_t fItems = (size_t)n * nF * kTile;
+            if (haveForces && !lateForces) {
+                cudaMemcpyAsync(io->devForces + fOff, io->forces + fOff, fLen * sizeof(float), cudaMemcpyHostToDevice, gs);
+                k_apply_forces<<<(unsigned)((fItems + 255) / 256), 256, 0, gs>>>(Ag, io->devForces, n, b->ioForceSel, nF);
                 b->launches++;
             }
+            if (lateForces) {
+                cudaStreamWaitEvent(b->copyStream[g], b->evFork, 0);  // not before what the batch's stream held at the fork
+                cudaMemcpyAsync(io->devForces + fOff, io->forces + fOff, fLen * sizeof(float), cudaMemcpyHostToDevice, b->copyStream[g]);
+                cudaEventRecord(b->evCopy[g], b->copyStream[g]);
+            }
             enqueuePart(b, 0, dt, velIters, posIters, mk, &m, gs, t0, n);
+            if (lateForces) {
+                cudaStreamWaitEvent(gs, b->evCopy[g], 0);
+                k_apply_forces<<<(unsigned)((fItems + 255) / 256), 256, 0, gs>>>(Ag, io->devForces, n, b->ioForceSel, nF);
+                b->launches++;
+            }
+            enqueuePart(b, 3, dt, velIters, posIters, mk, &m, gs, t0, n);
             if (pipeline) {
                 const int prev = g == 0 ? G - 1 : g - 1;
                 if (g > 0 || i > 0) cudaStreamWaitEvent(gs, b->evSeq[prev], 0);
             }
             enqueuePart(b, 1, dt, velIters, posIters, mk, &m, gs, t0, n);
             if (pipeline) cudaEventRecord(b->evSeq[g], gs);
+            enqueuePart(b, 4, dt, velIters, posIters, mk, &m, gs, t0, n);
             enqueuePart(b, 2, dt, velIters, posIters, mk, &m, gs, t0, n);
+            // (reading the poses out on the side stream right behind k_solve_finalize, under k_sync_pairs, was measured: no
+            // gain with 4 groups, a loss with more)
             if (io && io->transforms && w1 > w0 && nP > 0) {
                 const size_t off = (size_t)w0 * nP * poseFloats, len = (size_t)(w1 - w0) * nP * poseFloats;
                 const size_t items = (size_t)n * nP * kTile;
@@ -1459,6 +1488,10 @@ int b2gpu_batch_destroy(b2gpu_batch* b) {
     if (b->ioForceSel) cudaFree(b->ioForceSel);
     if (b->ioPoseSel) cudaFree(b->ioPoseSel);
     if (b->cmdDev) cudaFree(b->cmdDev);
+    for (int g = 0; g < b2gpu_batch::kMaxGroups; ++g) {
+        if (b->copyStream[g]) cudaStreamDestroy(b->copyStream[g]);
+        if (b->evCopy[g]) cudaEventDestroy(b->evCopy[g]);
+    }
     if (b->graphExec) cudaGraphExecDestroy(b->graphExec);
     if (b->graphExecChunk) cudaGraphExecDestroy(b->graphExecChunk);
     if (b->graphExecIo) cudaGraphExecDestroy(b->graphExecIo);
@@ -1488,6 +1521,16 @@ int b2gpu_batch_upload_field(b2gpu_batch* b, int32_t field, const void* host, in
         if (b->anyContinuous) {  // the captured steps have no k_toi: capture again
             invalidateGraphs(b);
         }
+    }
+    // can a dynamic body be asleep from now on?  (b2gpu_batch::maySleep: the graph of step_io bakes the answer in)
+    if (rc == B2GPU_OK && !b->maySleep && (field == B2GPU_F_WORLD_FLAGS || field == B2GPU_F_BODY_FLAGS)) {
+        const int32_t* v = static_cast<const int32_t*>(host);
+        const size_t nWords = (size_t)worldCount * b->fields[field].capacity;
+        for (size_t i = 0; i < nWords && !b->maySleep; ++i) {
+            if (field == B2GPU_F_WORLD_FLAGS) b->maySleep = (v[i] & B2G_WORLD_ALLOW_SLEEP) != 0;
+            else b->maySleep = (v[i] & kBodyTypeMask) == B2G_DYNAMIC_BODY && (v[i] & kBodyAwake) == 0 && (v[i] & kBodyDestroyed) == 0;
+        }
+        if (b->maySleep) invalidateGraphs(b);
     }
     // any host edit may change what the islands depend on: rebuild them on the next step
     if (rc == B2GPU_OK) cudaMemsetAsync(b->A.topoDirty, 1, (size_t)b->A.numTiles * kTile * sizeof(int), b->stream);
@@ -1757,7 +1800,7 @@ int b2gpu_batch_step_io(b2gpu_batch* b, const float* forces, float dt, int32_t v
     io.devTransforms = b->ioDev + forceFloats;
     // eight groups: the exposed transfers are the first group's copy in and the last group's copy out, an eighth of the
     // batch's each (16,384 pyramid worlds, ms per step for 2 / 4 / 8 groups: 6.81 / 6.46 / 6.28; separate calls 8.60)
-    io.groups = b2gpu_batch::kMaxGroups;
+    io.groups = 4;  // measured (tools/io_groups_r2b.sh, 16,384 pyramid worlds): 2 / 4 / 5 / 8 groups = 5.35 / 5.12 / 5.09 / 5.72 ms per step
     if (const char* env = getenv("B2GPU_IO_GROUPS")) {
         const int g = atoi(env);
         if (g >= 1 && g <= b2gpu_batch::kMaxGroups) io.groups = g;
@@ -1889,6 +1932,10 @@ int b2gpu_batch_snapshot_load(b2gpu_batch* b, const void* blob, int64_t size) {
         invalidateGraphs(b);
     }
     b->needProxyIndex = true;
+    if (!b->maySleep) {  // the restored state may hold sleepers: step_io goes back to forces-first
+        b->maySleep = true;
+        invalidateGraphs(b);
+    }
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     return B2GPU_OK;
 }
@@ -1917,6 +1964,14 @@ int b2gpu_batch_spawn_records(b2gpu_batch* b, const uint32_t* words, const int64
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     b->needInitialPairs = true;  // some world has e_newFixture set: the next Step starts with FindNewContacts
     b->needProxyIndex = true;
+    for (int32_t i = 0; i < count && !b->maySleep; ++i) {  // a body created asleep (b2BodyDef::awake == false)
+        const uint32_t* r = words + offsets[i];
+        const int flags = (int)r[6 + 24];
+        if ((int)r[5] < 0 && (flags & kBodyTypeMask) == B2G_DYNAMIC_BODY && (flags & kBodyAwake) == 0) {
+            b->maySleep = true;
+            invalidateGraphs(b);
+        }
+    }
     return B2GPU_OK;
 }
 
@@ -2000,6 +2055,11 @@ int b2gpu_batch_body_commands(b2gpu_batch* b, const b2gpu_body_command* commands
     CUDA_TRY(cudaGetLastError());
     // the host array (or its grouped copy) may die when we return
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    for (int64_t i = 0; i < count && !b->maySleep; ++i)
+        if (commands[i].op == B2GPU_CMD_SET_AWAKE && commands[i].wake == 0) {  // b2Body::SetAwake(false): a sleeper from now on
+            b->maySleep = true;
+            invalidateGraphs(b);
+        }
     for (int64_t i = 0; i < count; ++i)  // proxies came or went: the body -> proxies index is rebuilt before the next step
         if (commands[i].op == B2GPU_CMD_DESTROY_BODY || commands[i].op == B2GPU_CMD_SET_ACTIVE || commands[i].op == B2GPU_CMD_DESTROY_FIXTURE) {
             b->needProxyIndex = true;

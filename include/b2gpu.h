@@ -221,7 +221,10 @@ int b2gpu_batch_read_transforms(b2gpu_batch* batch, float* out);
  * reads observations and writes controls every step.  Same results as the three separate calls (bit-identical);
  * the difference is scheduling: the batch is cut into world groups, each group copies its own slice of `forces`
  * in and of `transforms` out on its own stream, so the PCIe transfers of one group run under the kernels of the
- * others.  Either pointer may be null (that side is skipped); pinned host buffers are needed for the overlap.
+ * others.  While no dynamic body of the batch can be asleep (no world allows sleeping, none was built or set asleep)
+ * a force cannot wake anybody, so a group's forces are copied on a side stream under its contact update and island
+ * build and applied just before the velocities are integrated — the first thing that reads them.  Either pointer may
+ * be null (that side is skipped); pinned host buffers are needed for the overlap.
  * Synchronises: on return `transforms` holds this step's result. */
 int b2gpu_batch_step_io(b2gpu_batch* batch, const float* forces, float dt, int32_t velIters, int32_t posIters,
                         float* transforms);

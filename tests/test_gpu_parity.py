@@ -450,6 +450,33 @@ def test_step_io_equals_separate_calls():
             os.environ.pop("B2GPU_IO_GROUPS", None)
 
 
+def test_step_io_forces_wake_sleepers_like_the_separate_calls():
+    """Worlds that do not allow sleeping let b2gpu_batch_step_io bring its forces in behind k_collide / k_islands (nobody can be
+    woken by them) — until a body is put to sleep by hand: from then on a force has to wake it BEFORE the step looks at the
+    contacts, as b2Body::ApplyForce before b2World::Step does.  step_io == apply_forces + step + read_transforms throughout."""
+    W = 96
+    sb = S.pyramid_batch(W, 5, flags=NOCCD & ~S.WORLD_ALLOW_SLEEP, first_seed=11, jittered=True)
+    a, b = WorldBatch(sb), WorldBatch(sb)
+    rng = np.random.default_rng(9)
+    nb = a.max_bodies
+    for k in range(90):
+        f = (rng.uniform(-30.0, 30.0, size=(W, nb, 3)) * (rng.random((W, nb, 1)) < 0.2)).astype(np.float32)
+        if k == 40:  # every settled box of the even worlds goes to sleep: b2Body::SetAwake(false)
+            cmds = np.array([(w, body, B.CMD_SET_AWAKE, 0, (0, 0), (0, 0)) for w in range(0, W, 2) for body in range(1, nb)],
+                            dtype=B.BODY_COMMAND_DTYPE)
+            a.body_commands(cmds)
+            b.body_commands(cmds)
+        a.apply_forces(f)
+        a.step(1.0 / 60.0, 8, 3)
+        want = a.read_transforms()
+        got = b.step_io(f, 1.0 / 60.0, 8, 3)
+        assert (got.view(np.uint32) == want.view(np.uint32)).all(), f"step {k}"
+    for w in (0, 1, 50, 95):
+        assert (a.bodies(w).view(np.uint32) == b.bodies(w).view(np.uint32)).all()
+    a.close()
+    b.close()
+
+
 def test_step_io_with_selected_bodies_and_poses():
     """b2gpu_batch_io_select: forces for a subset of the bodies and (x, y, angle) poses of the dynamic ones only give the
     same worlds as the dense calls with zeros elsewhere, and the poses are the transforms' positions + the sweeps' angles."""
