@@ -371,6 +371,8 @@ __device__ __forceinline__ int CollideOne(const Arena& A, int tile, int lane, in
     return UpdateOne(A, tile, lane, k, a0);
 }
 
+__device__ __forceinline__ void PrefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // A contact flagged for filtering is looked at before anything else, awake or not (b2ContactManager.cpp:124-146).
 // Returns true when it is to be destroyed: marked dead like a contact whose fat AABBs parted, `res` says so to the
 // list-order pass.  Otherwise the flag is cleared and the contact goes on as usual.
@@ -432,6 +434,11 @@ __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_
     __syncthreads();
 
     int summary = 0;  // 1: the list-order pass is needed, 2: island topology changed
+    // The walk is a chain of dependent loads per contact (its record -> body flags, fat AABBs -> transforms, manifold):
+    // the contact-indexed columns of this warp's NEXT contact are pulled towards the SM while this one is evaluated.
+    Col<int4> pfK = col(A.contactK, tile, A.NC, lane);
+    Col<float4> pfP0 = col(A.contactP0, tile, A.NC, lane), pfP1 = col(A.contactP1, tile, A.NC, lane);
+    Col<int2> pfS = col(A.contactS, tile, A.NC, lane);
 #ifndef B2G_NO_BINNED
     if (A.collideItems != nullptr) {
         // ---- type-binned evaluation (batches whose worlds mix shape types) ----
@@ -497,6 +504,12 @@ __global__ void __launch_bounds__(kCollideWarps * 32, B2G_COLLIDE_MIN_BLOCKS) k_
 #endif
     for (int k = warp; k < nMax; k += kCollideWarps) {
         if (k >= n) continue;
+#ifndef B2G_NO_COLLIDE_PREFETCH
+        if (k + kCollideWarps < n) {
+            const int kn = k + kCollideWarps;
+            PrefetchL2(&cA[kn]); PrefetchL2(&pfK[kn]); PrefetchL2(&pfP0[kn]); PrefetchL2(&pfP1[kn]); PrefetchL2(&pfS[kn]);
+        }
+#endif
         int4 a0 = cA[k];
         const int bodies = a0.y;
         const int bfA = bodyFlags[bodies & 0xffff], bfB = bodyFlags[(bodies >> 16) & 0xffff];
