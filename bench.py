@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--generic-solver", action="store_true", help="force the fallback solver kernel")
     ap.add_argument("--workload", default="pyramid", choices=["pyramid", "mixed", "jointed"],
                     help="pyramid = BASELINE configs[2] (the headline); mixed = configs[3] per-GPU share; "
-                         "jointed = bridge + cart-pole + walker + pendulums (joints: generic solver kernel)")
+                         "jointed = bridge + cart-pole + walker + pendulums (joints on the tile path)")
     ap.add_argument("--toi", action="store_true", help="continuous physics on (the reference's default) on both arms")
     ap.add_argument("--sleep", action="store_true", help="sleeping allowed (the reference's default) on both arms")
     ap.add_argument("--preroll", type=int, default=-1)
