@@ -513,7 +513,7 @@ int Flatten(const b2g_scene& s, const Caps& cap, const std::vector<std::pair<int
         auto& MS = out.f[B2GPU_F_BODY_MASS];
         put(MS, o, b.invMass); put(MS, o + 1, b.invI); put(MS, o + 2, b.localCenter.x); put(MS, o + 3, b.localCenter.y);
         auto& DP = out.f[B2GPU_F_BODY_DAMP];
-        put(DP, o, d.linearDamping); put(DP, o + 1, d.angularDamping); put(DP, o + 2, d.gravityScale); put(DP, o + 3, 0.0f);
+        put(DP, o, d.linearDamping); put(DP, o + 1, d.angularDamping); put(DP, o + 2, d.gravityScale); put(DP, o + 3, b.mass);
         put(out.f[B2GPU_F_BODY_FLAGS], i, b.flags);
     }
     put(out.f[B2GPU_F_GRAVITY], 0, s.gravity[0]);

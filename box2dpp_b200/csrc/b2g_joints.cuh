@@ -86,7 +86,7 @@ __device__ __forceinline__ Vec2 Mul22(const Mat33& A, Vec2 v) {
 struct JointCols {
     Col<int4> jI;
     Col<float4> jF0, jF1, jF2, jImp, jTmp;
-    Col<float4> bodySweep, bodyVel, bodyMass;
+    Col<float4> bodySweep, bodyVel, bodyMass, bodyDamp;  // bodyDamp.w = m_mass (b2Body::GetMass, read by the mouse joint)
     uint32_t velTable, posTable;
     static __device__ __forceinline__ float4 LoadRow(uint32_t a) {
         float4 v;
@@ -117,7 +117,7 @@ __device__ __forceinline__ JointCols MakeJointCols(const Arena& A, int tile, int
     JointCols c{col(A.jointI, tile, A.NJ, lane), col(A.jointF0, tile, A.NJ, lane), col(A.jointF1, tile, A.NJ, lane),
                 col(A.jointF2, tile, A.NJ, lane), col(A.jointImp, tile, A.NJ, lane), col(A.jointTmp, tile, A.NJ * kJointTmp, lane),
                 col(A.bodySweep, tile, A.NB, lane), col(A.bodyVel, tile, A.NB, lane), col(A.bodyMass, tile, A.NB, lane),
-                velTable, posTable};
+                col(A.bodyDamp, tile, A.NB, lane), velTable, posTable};
     return c;
 }
 
@@ -217,7 +217,7 @@ __device__ __noinline__ void JointInitVelocity(const JointCols* cp, int j, float
         return;
     }
     if (type == B2G_JOINT_MOUSE) {  // b2MouseJoint.cpp:96-160; f0 = target.xy, localAnchorB.xy; f1 = maxForce, frequencyHz, dampingRatio, mass of B
-        const float mass = f1.w;
+        const float mass = c.bodyDamp[bB].w;  // m_bodyB->GetMass() as it is now (b2Body::SetMassData / ResetMassData may have changed it)
         const float omega = 2.0f * kPi * f1.y;
         const float d = 2.0f * mass * f1.z * omega;
         const float k = mass * (omega * omega);

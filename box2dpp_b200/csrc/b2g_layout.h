@@ -94,7 +94,7 @@ struct Arena {
     float4* bodyVel;     // m_linearVelocity.xy, m_angularVelocity, (unused)
     float4* bodyForce;   // m_force.xy, m_torque, (unused)
     float4* bodyMass;    // m_invMass, m_invI, localCenter.xy
-    float4* bodyDamp;    // m_linearDamping, m_angularDamping, m_gravityScale, (unused)
+    float4* bodyDamp;    // m_linearDamping, m_angularDamping, m_gravityScale, m_mass (b2Body::GetMass)
     int* bodyFlags;      // type | kBody*
     int* bodyIsland;     // island id of this step (-1 = none)
 

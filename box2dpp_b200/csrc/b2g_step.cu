@@ -289,7 +289,9 @@ __device__ __noinline__ void SynchronizeBodyFixtures(const Arena& A, int tile, i
 }
 
 // The tail both b2Body::ResetMassData and SetMassData share: the centre of mass moves, the velocity follows it
-__device__ __forceinline__ void MoveCenterOfMass(const Arena& A, int tile, int lane, int b, float invMass, float invI, Vec2 localCenter) {
+__device__ __forceinline__ void MoveCenterOfMass(const Arena& A, int tile, int lane, int b, float mass, float invMass, float invI,
+                                                 Vec2 localCenter) {
+    col(A.bodyDamp, tile, A.NB, lane)[b].w = mass;  // m_mass
     Col<float4> bodySweep = col(A.bodySweep, tile, A.NB, lane), bodySweep0 = col(A.bodySweep0, tile, A.NB, lane);
     Col<float4> bodyVel = col(A.bodyVel, tile, A.NB, lane);
     const Xf xf = LoadXf(col(A.bodyXf, tile, A.NB, lane), b);
@@ -317,6 +319,7 @@ __device__ __noinline__ void ResetMassData(const Arena& A, int tile, int lane, i
     if (type == B2G_STATIC_BODY || type == B2G_KINEMATIC_BODY) {
         const float4 xf = col(A.bodyXf, tile, A.NB, lane)[b];
         col(A.bodyMass, tile, A.NB, lane)[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        col(A.bodyDamp, tile, A.NB, lane)[b].w = 0.0f;  // m_mass
         float4 sw = bodySweep[b];
         sw.x = xf.x; sw.y = xf.y;
         bodySweep[b] = sw;
@@ -350,7 +353,7 @@ __device__ __noinline__ void ResetMassData(const Arena& A, int tile, int lane, i
     } else {
         invI = 0.0f;
     }
-    MoveCenterOfMass(A, tile, lane, b, invMass, invI, localCenter);
+    MoveCenterOfMass(A, tile, lane, b, mass, invMass, invI, localCenter);
 }
 
 // b2Body::CreateFixture on an existing body (b2Body.cpp:168-214), one call per fixture of the record, in record order: the
@@ -780,7 +783,7 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                     const float I = c.v[1] - mass * Dot(center, center);
                     invI = Div(1.0f, I);
                 }
-                MoveCenterOfMass(A, tile, lane, b, invMass, invI, center);
+                MoveCenterOfMass(A, tile, lane, b, mass, invMass, invI, center);
             } break;
             case B2GPU_CMD_RESET_MASS_DATA: {
                 ResetMassData(A, tile, lane, b);

@@ -140,7 +140,7 @@ enum {
     B2GPU_F_BODY_VEL,           /* [W][NB][4]  m_linearVelocity.xy, m_angularVelocity, 0 */
     B2GPU_F_BODY_FORCE,         /* [W][NB][4]  m_force.xy, m_torque, 0 */
     B2GPU_F_BODY_MASS,          /* [W][NB][4]  m_invMass, m_invI, m_sweep.localCenter.xy */
-    B2GPU_F_BODY_DAMP,          /* [W][NB][4]  m_linearDamping, m_angularDamping, m_gravityScale, 0 */
+    B2GPU_F_BODY_DAMP,          /* [W][NB][4]  m_linearDamping, m_angularDamping, m_gravityScale, m_mass */
     B2GPU_F_BODY_FLAGS,         /* [W][NB][1] int32: type | island 4 | awake 8 | autoSleep 16 | bullet 32 | fixedRotation 64 | active 128 */
     B2GPU_F_FIXTURE_INFO,       /* [W][NF][1] int32: body | shapeType << 16 | isSensor << 18 */
     B2GPU_F_FIXTURE_SHAPE,      /* [W][NF][1] int32: word offset into the shape table */

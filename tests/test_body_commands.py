@@ -328,8 +328,8 @@ def test_world_edits_match_reference(oracles):
     if not oracles.available("ref"):
         pytest.skip("checked against the live reference")
     base = [S.pyramid(4), S.mixed(2, bodies=10), S.jointed(1), S.filtered(16), S.hello_world(), S.jointed(4, flags=NOCCD),
-            S.pyramid(3, flags=NOCCD, jitter_seed=2), S.sensors(1, bodies=6)]
-    scenes = base * 4  # 32 worlds
+            S.pyramid(3, flags=NOCCD, jitter_seed=2), S.sensors(1, bodies=6), S.vehicles(2, flags=NOCCD)]
+    scenes = base * 4  # 36 worlds (the vehicles scene brings every joint type, a mouse joint's m_bodyB->GetMass() included)
     refs = [oracles.RefWorld(s, record_events=True) for s in scenes]
     batch = B.WorldBatch(scenes, event_mask=B.EVENT_ALL, headroom=(0, 60, 90, 1500, 0), joint_headroom=24)
     rng = S.LCG(977)
