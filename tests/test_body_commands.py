@@ -336,6 +336,14 @@ def test_world_edits_match_reference(oracles):
     bodies = [list(range(s.body_count)) for s in scenes]
     fixtures = [{i: int(f.body) for i, f in enumerate(s.fixtures)} for s in scenes]          # live fixture -> body
     joints = [set(range(len(s.joints))) for s in scenes]
+    # The reference's contract for gear joints (b2GearJoint.h:53 "you have to manually destroy the gear joint if joint1 or
+    # joint2 is destroyed"; its solver reads bodyC / bodyD through their island index, which is stale when the ground is not
+    # in the island): the joints a gear was built from stay, and the gears' ground body stays active and static.
+    geared = [w for w, s in enumerate(scenes) if any(int(j.type) == S.JOINT_GEAR for j in s.joints)]
+    for w in geared:
+        for j in scenes[w].joints:
+            if int(j.type) == S.JOINT_GEAR:
+                joints[w] -= {int(j.enableLimit), int(j.enableMotor)}
     types = [[int(b.type) for b in s.bodies] for s in scenes]
     counts = {}
     pick = lambda seq: seq[int(rng.next_u() * len(seq)) % len(seq)]  # noqa: E731
@@ -346,6 +354,8 @@ def test_world_edits_match_reference(oracles):
                 for _ in range(1 + int(rng.next_u() * 2) % 2):
                     u = rng.next_u()
                     body = pick(bodies[w])
+                    if body == 0 and w in geared and 0.16 <= u < 0.40:
+                        continue
                     if u < 0.16 and fixtures[w]:
                         fx = pick(sorted(fixtures[w]))
                         filters[len(cmds)] = (1 << (int(rng.next_u() * 4) % 4), 0xffff if rng.next_u() < 0.5 else int(rng.next_u() * 16) % 16,
