@@ -165,3 +165,55 @@ def test_reference_gear_and_mouse_joints_behave(oracles):
     assert abs(a1) > 0.5, "the driven wheel should have turned"
     assert abs(a1 + ratio * a2) < 0.05, (a1, a2)
     assert abs(float(b[crate, 0]) - 5.0) < 0.1 and abs(float(b[crate, 1]) - 4.0) < 0.3, b[crate, :2]
+
+
+def test_reference_harness_edit_calls(oracles):
+    """The oracle harness's running-world edits (what the GPU parity tests replay against): each call reaches the reference's
+    own function and the harness's index bookkeeping (bodies, fixtures, joints by creation order) holds."""
+    if not oracles.available("ref"):
+        pytest.skip("oracle/_ref not built")
+    from box2dpp_b200 import batch as B
+    s = S.pyramid(3, flags=15 & ~4)
+    r = oracles.RefWorld(s, record_events=True)
+    for _ in range(60):
+        r.step(1 / 60, 8, 3)
+    n_contacts = r.contacts()[0].shape[0]
+    assert n_contacts > 0
+    top = s.body_count - 1
+    # b2Body::SetType(static): velocity cleared, contacts of the body destroyed
+    r.command(top, B.CMD_SET_TYPE, 0)
+    assert r.contacts()[0].shape[0] < n_contacts and (r.bodies()[top, 7:10] == 0).all()
+    r.command(top, B.CMD_SET_TYPE, 2)
+    # b2Body::SetMassData / ResetMassData: GetMass follows
+    r.command(1, B.CMD_SET_MASS_DATA, 0, (3.0, 2.0), (0.0, 0.0))
+    assert r.bodies()[1, 11] == np.float32(3.0)
+    r.command(1, B.CMD_RESET_MASS_DATA)
+    assert r.bodies()[1, 11] != np.float32(3.0)
+    # b2Body::CreateFixture on an existing body, then DestroyFixture: fixture indices keep counting, proxies come and go
+    tmp = S.Scene()
+    b = tmp.create_body(S.DYNAMIC_BODY, (0.0, 0.0))
+    tmp.create_circle(b, 0.3, density=1.0)
+    proxies = (r.proxies()[1] >= 0).sum()
+    fx = r.create_fixture(2, tmp.fixtures[0], tmp.vertices)
+    assert fx == len(s.fixtures) and (r.proxies()[1] >= 0).sum() == proxies + 1
+    r.command(2, B.CMD_DESTROY_FIXTURE, fx)
+    assert (r.proxies()[1] >= 0).sum() == proxies
+    # b2World::CreateJoint / DestroyJoint: ids by creation order
+    jd = S.JointDef()
+    jd.type, jd.bodyA, jd.bodyB, jd.length, jd.frequencyHz, jd.dampingRatio = S.JOINT_DISTANCE, 1, 2, 1.5, 3.0, 0.5
+    assert r.create_joint(jd) == 0 and r.create_joint(jd) == 1
+    r.command(0, B.CMD_DESTROY_JOINT, 0)
+    assert r.create_joint(jd) == 2
+    # b2Fixture::SetFilterData: a fixture that collides with nothing loses its contacts at the next Step
+    r.set_filter(1, 1, 0, 0)
+    before = r.contacts()[0]
+    r.step(1 / 60, 8, 3)
+    after = r.contacts()[0]
+    assert (before[:, [0, 2]] == 1).any() and not (after[:, [0, 2]] == 1).any()
+    # b2Body::SetActive(false): the body's proxies leave the broad phase
+    live = (r.proxies()[1] >= 0).sum()
+    r.command(3, B.CMD_SET_ACTIVE, 0)
+    assert (r.proxies()[1] >= 0).sum() == live - 1
+    for _ in range(30):
+        r.step(1 / 60, 8, 3)
+    assert np.isfinite(r.bodies()).all()
