@@ -68,7 +68,8 @@ BODY_COMMAND_DTYPE = np.dtype([("world", "<i4"), ("body", "<i4"), ("op", "<i4"),
 (CMD_APPLY_FORCE, CMD_APPLY_FORCE_TO_CENTER, CMD_APPLY_TORQUE, CMD_APPLY_LINEAR_IMPULSE, CMD_APPLY_ANGULAR_IMPULSE,
  CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE, CMD_DESTROY_BODY,
  CMD_MOUSE_SET_TARGET, CMD_SET_FILTER, CMD_DESTROY_JOINT, CMD_SET_TYPE, CMD_SET_ACTIVE, CMD_SET_MASS_DATA,
- CMD_RESET_MASS_DATA, CMD_DESTROY_FIXTURE) = range(18)
+ CMD_RESET_MASS_DATA, CMD_DESTROY_FIXTURE, CMD_SET_DAMPING, CMD_SET_GRAVITY_SCALE, CMD_SET_BULLET, CMD_SET_SLEEPING_ALLOWED,
+ CMD_SET_FIXED_ROTATION, CMD_SET_SENSOR, CMD_SET_MATERIAL) = range(25)
 
 
 def put_filter(commands: np.ndarray, i: int, category_bits=1, mask_bits=0xffff, group_index=0):

@@ -800,6 +800,72 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                 fixtureInfo[fx] |= kFixtureDestroyed;
                 ResetMassData(A, tile, lane, b);
             } break;
+            case B2GPU_CMD_SET_DAMPING: {
+                Col<float4> bodyDamp = col(A.bodyDamp, tile, A.NB, lane);
+                float4 d = bodyDamp[b];
+                d.x = c.v[0];
+                d.y = c.v[1];
+                bodyDamp[b] = d;
+            } break;
+            case B2GPU_CMD_SET_GRAVITY_SCALE: {
+                Col<float4> bodyDamp = col(A.bodyDamp, tile, A.NB, lane);
+                float4 d = bodyDamp[b];
+                d.z = c.v[0];
+                bodyDamp[b] = d;
+            } break;
+            case B2GPU_CMD_SET_BULLET: {
+                bodyFlags[b] = c.wake ? (f | kBodyBullet) : (f & ~kBodyBullet);
+            } break;
+            case B2GPU_CMD_SET_SLEEPING_ALLOWED: {  // b2Body.h:655-667
+                if (c.wake) {
+                    bodyFlags[b] = f | kBodyAutoSleep;
+                } else {
+                    bodyFlags[b] = f & ~kBodyAutoSleep;
+                    f &= ~kBodyAutoSleep;
+                    wake();
+                }
+            } break;
+            case B2GPU_CMD_SET_FIXED_ROTATION: {  // b2Body.cpp:512-534
+                const bool status = (f & kBodyFixedRotation) != 0, flag = c.wake != 0;
+                if (status == flag) break;
+                bodyFlags[b] = flag ? (f | kBodyFixedRotation) : (f & ~kBodyFixedRotation);
+                float4 v = bodyVel[b];
+                v.z = 0.0f;
+                bodyVel[b] = v;
+                ResetMassData(A, tile, lane, b);
+            } break;
+            case B2GPU_CMD_SET_SENSOR:
+            case B2GPU_CMD_SET_MATERIAL: {
+                const int fx = c.wake;
+                Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+                if (fx < 0 || fx >= A.fixtureCount[ws] || (fixtureInfo[fx] & 0xffff) != b || (fixtureInfo[fx] & kFixtureDestroyed)) {
+                    A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
+                    break;
+                }
+                if (c.op == B2GPU_CMD_SET_MATERIAL) {
+                    col(A.fixtureMat, tile, A.NF, lane)[fx] = make_float2(c.v[0], c.v[1]);
+                    break;
+                }
+                const int fi = fixtureInfo[fx];
+                const bool sensor = c.v[0] != 0.0f;
+                if (sensor == ((fi >> 18 & 1) != 0)) break;
+                wake();  // m_body->SetAwake(true)
+                fixtureInfo[fx] = sensor ? (fi | (1 << 18)) : (fi & ~(1 << 18));
+                // b2Contact::Update reads both fixtures' sensor flags every time (b2Contact.cpp:181-183): the cached bit of the
+                // fixture's contacts follows; island topology may change with it
+                Col<int4> cA = col(A.contactA, tile, A.NC, lane);
+                Col<int> proxyInfo = col(A.proxyInfo, tile, A.NP, lane);
+                const int nc = A.contactCount[ws];
+                for (int k = 0; k < nc; ++k) {
+                    int4 a = cA[k];
+                    const int fA = proxyInfo[a.x & 0xffff] & 0xffff, fB = proxyInfo[(a.x >> 16) & 0xffff] & 0xffff;
+                    if (fA != fx && fB != fx) continue;
+                    const bool s2 = ((fixtureInfo[fA] | fixtureInfo[fB]) >> 18 & 1) != 0;
+                    a.z = s2 ? (a.z | kContactSensor) : (a.z & ~kContactSensor);
+                    cA[k] = a;
+                }
+                A.topoDirty[ws] = 1;
+            } break;
             case B2GPU_CMD_SET_AWAKE: {
                 if (c.wake) {
                     wake();

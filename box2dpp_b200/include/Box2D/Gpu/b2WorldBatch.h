@@ -331,6 +331,10 @@ public:
     int32_t GetIndex() const { return m_index; }  // creation order within the world
     // b2Fixture::SetFilterData (b2Fixture.cpp:185-215): the fixture's contacts are re-filtered at the next Step
     void SetFilterData(const b2Filter& filter);
+    // b2Fixture::SetSensor (b2Fixture.cpp:222-229), SetFriction / SetRestitution (b2Fixture.h:330-345)
+    void SetSensor(bool sensor);
+    void SetFriction(float friction) { m_friction = friction; QueueMaterial(); }
+    void SetRestitution(float restitution) { m_restitution = restitution; QueueMaterial(); }
 
 private:
     friend class b2Body;
@@ -338,6 +342,8 @@ private:
     void* m_userData = nullptr;
     b2Shape::Type m_type = b2Shape::e_circle;
     int32_t m_index = 0;
+    void QueueMaterial();
+    float m_friction = 0.2f, m_restitution = 0.0f;  // host copies: the device command carries both
 };
 struct b2MassData {  // Collision/Shapes/b2Shape.h:27-38
     float mass = 0.0f;
@@ -410,6 +416,13 @@ public:
     void SetMassData(const b2MassData* data);
     void ResetMassData();
     void DestroyFixture(b2Fixture* fixture);  // the b2Fixture object stays allocated (its index is reserved)
+    // plain setters (b2Body.h:590-690, b2Body.cpp:512-534)
+    void SetLinearDamping(float damping) { m_linearDamping = damping; QueueDamping(); }
+    void SetAngularDamping(float damping) { m_angularDamping = damping; QueueDamping(); }
+    void SetGravityScale(float scale);
+    void SetBullet(bool flag);
+    void SetSleepingAllowed(bool flag);
+    void SetFixedRotation(bool flag);
 
 private:
     friend class b2World;
@@ -417,6 +430,8 @@ private:
     friend class b2Joint;
     friend class b2Fixture;
     void SetMouseTarget(const b2Vec<float, 2>& target);  // b2Joint::SetTarget of the mouse joint attached to this body
+    void QueueDamping();
+    float m_linearDamping = 0.0f, m_angularDamping = 0.0f;  // host copies: the device command carries both
     // While the scene is still being recorded (no Step yet) edits are queued and getters are answered on the host from
     // this shadow of the body's definition, so a `body->SetLinearVelocity(..)` or `jd.Initialize(a, b, a->GetWorldCenter())`
     // right after CreateBody neither creates the device batch nor freezes the scene.
@@ -769,6 +784,8 @@ inline b2Body* b2World::CreateBody(const b2BodyDef* def) {
     b->m_index = (int32_t)w.m_bodies.size();
     b->m_type = def->type;
     b->m_userData = def->userData;
+    b->m_linearDamping = def->linearDamping;
+    b->m_angularDamping = def->angularDamping;
     b->m_shadow.p[0] = d.position[0]; b->m_shadow.p[1] = d.position[1]; b->m_shadow.angle = d.angle;
     b->m_shadow.v[0] = d.linearVelocity[0]; b->m_shadow.v[1] = d.linearVelocity[1]; b->m_shadow.w = d.angularVelocity;
     b->m_shadow.awake = def->awake;
@@ -953,6 +970,8 @@ inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
     std::unique_ptr<b2Fixture> f(new b2Fixture);
     f->m_body = this;
     f->m_userData = def->userData;
+    f->m_friction = def->friction;
+    f->m_restitution = def->restitution;
     f->m_type = def->shape->GetType();
     f->m_index = (int32_t)w.m_fixtures.size();
     w.m_firstProxy.push_back(w.m_proxyCount);
@@ -1244,6 +1263,17 @@ inline void b2Body::DestroyFixture(b2Fixture* fixture) {
     if (!fixture || fixture->GetBody() != this) return;
     m_world->m_batch->QueueEdit(this, B2GPU_CMD_DESTROY_FIXTURE, fixture->GetIndex(), 0.0f, 0.0f, 0.0f, 0.0f);
     fixture->m_body = nullptr;
+}
+inline void b2Body::QueueDamping() { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_DAMPING, 0, m_linearDamping, m_angularDamping, 0.0f, 0.0f); }
+inline void b2Body::SetGravityScale(float scale) { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_GRAVITY_SCALE, 0, scale, 0.0f, 0.0f, 0.0f); }
+inline void b2Body::SetBullet(bool flag) { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_BULLET, flag ? 1 : 0, 0.0f, 0.0f, 0.0f, 0.0f); }
+inline void b2Body::SetSleepingAllowed(bool flag) { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_SLEEPING_ALLOWED, flag ? 1 : 0, 0.0f, 0.0f, 0.0f, 0.0f); }
+inline void b2Body::SetFixedRotation(bool flag) { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_FIXED_ROTATION, flag ? 1 : 0, 0.0f, 0.0f, 0.0f, 0.0f); }
+inline void b2Fixture::SetSensor(bool sensor) {
+    if (m_body) m_body->m_world->m_batch->QueueEdit(m_body, B2GPU_CMD_SET_SENSOR, m_index, sensor ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f);
+}
+inline void b2Fixture::QueueMaterial() {
+    if (m_body) m_body->m_world->m_batch->QueueEdit(m_body, B2GPU_CMD_SET_MATERIAL, m_index, m_friction, m_restitution, 0.0f, 0.0f);
 }
 inline void b2Fixture::SetFilterData(const b2Filter& filter) {
     if (!m_body) return;

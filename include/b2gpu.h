@@ -88,6 +88,16 @@ enum {
     B2GPU_CMD_RESET_MASS_DATA = 16,      /*                             b2Body::ResetMassData (:283-352) */
     B2GPU_CMD_DESTROY_FIXTURE = 17,      /* wake = fixture index       b2Body::DestroyFixture (:216-281): its contacts are destroyed
                                             (EndContact events), its proxies leave the broad phase, the mass data is reset */
+    /* ---- plain setters (b2Body.h:590-690, b2Body.cpp:512-534, b2Fixture.h:300-345, b2Fixture.cpp:217-224) ---- */
+    B2GPU_CMD_SET_DAMPING = 18,          /* v[0] = linear, v[1] = angular   b2Body::SetLinearDamping + SetAngularDamping */
+    B2GPU_CMD_SET_GRAVITY_SCALE = 19,    /* v[0] = scale                b2Body::SetGravityScale */
+    B2GPU_CMD_SET_BULLET = 20,           /* wake = flag                 b2Body::SetBullet */
+    B2GPU_CMD_SET_SLEEPING_ALLOWED = 21, /* wake = flag                 b2Body::SetSleepingAllowed (false also wakes the body) */
+    B2GPU_CMD_SET_FIXED_ROTATION = 22,   /* wake = flag                 b2Body::SetFixedRotation (angular velocity cleared, mass data reset) */
+    B2GPU_CMD_SET_SENSOR = 23,           /* wake = fixture index, v[0] != 0 = sensor   b2Fixture::SetSensor (wakes the body; the fixture's
+                                            contacts follow at their next Update, as the reference reads the flag there) */
+    B2GPU_CMD_SET_MATERIAL = 24,         /* wake = fixture index, v[0] = friction, v[1] = restitution   b2Fixture::SetFriction +
+                                            SetRestitution (existing contacts keep their mixed values, like the reference) */
     B2GPU_CMD_COUNT
 };
 typedef struct b2gpu_body_command {

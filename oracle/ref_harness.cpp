@@ -385,6 +385,17 @@ void ref_world_body_command(void* h, int body, int op, int wake, float vx, float
                 b->DestroyFixture(rw->fixtures[wake]);
                 rw->fixtures[wake] = nullptr;
             } break;
+            case 18: b->SetLinearDamping(vx); b->SetAngularDamping(vy); break;
+            case 19: b->SetGravityScale(vx); break;
+            case 20: b->SetBullet(wake != 0); break;
+            case 21: b->SetSleepingAllowed(wake != 0); break;
+            case 22: b->SetFixedRotation(wake != 0); break;
+            case 23:
+            case 24: {
+                if (wake < 0 || wake >= (int)rw->fixtures.size() || !rw->fixtures[wake] || rw->fixtures[wake]->GetBody() != b) return;
+                if (op == 23) rw->fixtures[wake]->SetSensor(vx != 0.0f);
+                else { rw->fixtures[wake]->SetFriction(vx); rw->fixtures[wake]->SetRestitution(vy); }
+            } break;
         }
         return;
     }

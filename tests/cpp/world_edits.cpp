@@ -65,6 +65,13 @@ int main() {
     b2MassData md;
     md.mass = 3.0f; md.I = 1.0f;
     arm[2]->SetMassData(&md);
+    arm[2]->SetLinearDamping(0.1f);
+    arm[2]->SetGravityScale(1.0f);
+    arm[2]->SetBullet(false);
+    arm[2]->SetSleepingAllowed(true);
+    arm[2]->SetFixedRotation(false);
+    extra[1]->SetSensor(false);
+    extra[1]->SetFriction(0.2f);
     batch.Step(1.0f / 60.0f, 8, 3);
     arm[2]->SetActive(false);
     batch.Step(1.0f / 60.0f, 8, 3);

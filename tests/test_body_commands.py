@@ -324,7 +324,9 @@ def test_world_edits_match_reference(oracles):
     """The rest of §8f-2 against the live reference, random edits between steps, every float and contact compared after
     the edits and after every step: b2Fixture::SetFilterData (contacts flagged, b2ContactManager::Collide's e_filterFlag
     branch), b2World::CreateJoint / DestroyJoint on running worlds (collideConnected flags the pair's contacts),
-    b2Body::SetType, SetActive, SetMassData, ResetMassData, DestroyFixture and CreateFixture on existing bodies."""
+    b2Body::SetType, SetActive, SetMassData, ResetMassData, DestroyFixture and CreateFixture on existing bodies, and the
+    plain setters (damping, gravity scale, bullet, sleeping allowed, fixed rotation, b2Fixture::SetSensor / SetFriction /
+    SetRestitution)."""
     if not oracles.available("ref"):
         pytest.skip("checked against the live reference")
     base = [S.pyramid(4), S.mixed(2, bodies=10), S.jointed(1), S.filtered(16), S.hello_world(), S.jointed(4, flags=NOCCD),
@@ -344,6 +346,8 @@ def test_world_edits_match_reference(oracles):
         for j in scenes[w].joints:
             if int(j.type) == S.JOINT_GEAR:
                 joints[w] -= {int(j.enableLimit), int(j.enableMotor)}
+    # (and a mouse joint's body stays dynamic: b2MouseJoint::InitVelocityConstraints asserts on a body without mass)
+    mouse_bodies = [{int(j.bodyB) for j in s.joints if int(j.type) == S.JOINT_MOUSE} for s in scenes]
     types = [[int(b.type) for b in s.bodies] for s in scenes]
     counts = {}
     pick = lambda seq: seq[int(rng.next_u() * len(seq)) % len(seq)]  # noqa: E731
@@ -363,7 +367,7 @@ def test_world_edits_match_reference(oracles):
                         cmds.append((w, fixtures[w][fx], B.CMD_SET_FILTER, fx, (0.0, 0.0), (0.0, 0.0)))
                     elif u < 0.28:
                         t = int(rng.next_u() * 3) % 3
-                        if body == 0 and rng.next_u() < 0.8:
+                        if (body == 0 and rng.next_u() < 0.8) or body in mouse_bodies[w]:
                             continue  # the ground mostly stays what it is
                         cmds.append((w, body, B.CMD_SET_TYPE, t, (0.0, 0.0), (0.0, 0.0)))
                         types[w][body] = t
@@ -381,9 +385,28 @@ def test_world_edits_match_reference(oracles):
                     elif u < 0.80:
                         fds, verts = _edit_fixture(rng, int(rng.next_u() * 4) % 4)
                         attach.append((w, body, fds, verts))
-                    elif u < 0.92 and len(bodies[w]) > 1:
+                    elif u < 0.86 and len(bodies[w]) > 1:
                         other = pick([b for b in bodies[w] if b != body])
                         new_joints.append((w, _edit_joint(rng, body, other)))
+                    elif u < 0.93:  # the plain setters
+                        k = int(rng.next_u() * 7) % 7
+                        f32 = lambda x: float(np.float32(x))  # noqa: E731
+                        if k == 0:
+                            cmds.append((w, body, B.CMD_SET_DAMPING, 0, (f32(rng.uniform(0.0, 0.5)), f32(rng.uniform(0.0, 0.5))), (0.0, 0.0)))
+                        elif k == 1:
+                            cmds.append((w, body, B.CMD_SET_GRAVITY_SCALE, 0, (f32(rng.uniform(-0.5, 2.0)), 0.0), (0.0, 0.0)))
+                        elif k == 2:
+                            cmds.append((w, body, B.CMD_SET_BULLET, 1 if rng.next_u() < 0.5 else 0, (0.0, 0.0), (0.0, 0.0)))
+                        elif k == 3:
+                            cmds.append((w, body, B.CMD_SET_SLEEPING_ALLOWED, 1 if rng.next_u() < 0.5 else 0, (0.0, 0.0), (0.0, 0.0)))
+                        elif k == 4:
+                            cmds.append((w, body, B.CMD_SET_FIXED_ROTATION, 1 if rng.next_u() < 0.5 else 0, (0.0, 0.0), (0.0, 0.0)))
+                        elif fixtures[w]:
+                            fx = pick(sorted(fixtures[w]))
+                            if k == 5:
+                                cmds.append((w, fixtures[w][fx], B.CMD_SET_SENSOR, fx, (1.0 if rng.next_u() < 0.4 else 0.0, 0.0), (0.0, 0.0)))
+                            else:
+                                cmds.append((w, fixtures[w][fx], B.CMD_SET_MATERIAL, fx, (f32(rng.uniform(0.0, 1.0)), f32(rng.uniform(0.0, 0.6))), (0.0, 0.0)))
                     elif joints[w]:
                         j = pick(sorted(joints[w]))
                         joints[w].discard(j)
@@ -424,5 +447,6 @@ def test_world_edits_match_reference(oracles):
     assert (batch.status() == 0).all(), batch.status()
     assert all(counts.get(k, 0) > 20 for k in (B.CMD_SET_FILTER, B.CMD_SET_TYPE, B.CMD_SET_ACTIVE, B.CMD_SET_MASS_DATA,
                                                B.CMD_DESTROY_FIXTURE, "fixture", "joint")), counts
-    assert counts.get(B.CMD_DESTROY_JOINT, 0) > 10, counts
+    assert counts.get(B.CMD_DESTROY_JOINT, 0) > 5, counts
+    assert sum(counts.get(k, 0) for k in range(B.CMD_SET_DAMPING, B.CMD_SET_MATERIAL + 1)) > 30, counts
     batch.close()
