@@ -906,6 +906,7 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
 inline void b2World::DestroyJoint(b2Joint* joint) {
     b2World& w = B2_SELF;
     if (!joint || joint->GetIndex() < 0 || joint->GetIndex() >= (int32_t)w.m_joints.size() || w.m_joints[joint->GetIndex()].get() != joint) return;
+    if (!joint->m_bodyA && !joint->m_bodyB) return;  // destroyed already
     b2WorldBatch* B = w.m_batch;
     B->BuildEarly();
     B->FlushSpawns();
@@ -913,6 +914,7 @@ inline void b2World::DestroyJoint(b2Joint* joint) {
     std::memset(&c, 0, sizeof(c));
     c.world = w.m_index; c.op = B2GPU_CMD_DESTROY_JOINT; c.wake = joint->GetIndex();
     B->m_commands.push_back(c);
+    joint->m_bodyA = joint->m_bodyB = nullptr;  // destroyed: a second DestroyJoint / SetTarget on it does nothing
 }
 inline void b2World::DestroyBody(b2Body* body) {
     if (!body || body->GetWorld() != &(B2_SELF)) return;
