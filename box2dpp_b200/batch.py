@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "b2gpu_batch_field_shape", "b2gpu_batch_step", "b2gpu_batch_step_n", "b2gpu_batch_sync",
     "b2gpu_batch_apply_forces", "b2gpu_batch_read_transforms", "b2gpu_batch_step_io", "b2gpu_batch_io_select", "b2gpu_batch_last_step_ms",
     "b2gpu_batch_profile_steps", "b2gpu_batch_profile_kernels", "b2gpu_batch_kernel_name", "b2gpu_batch_launch_count", "b2gpu_last_error", "b2gpu_scene_capacities",
-    "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build", "b2gpu_host_sincosf", "b2gpu_sincosf",
+    "b2gpu_batch_build_worlds", "b2gpu_host_polygon_build", "b2gpu_host_fixture_mass_data", "b2gpu_host_sincosf", "b2gpu_sincosf",
     "b2gpu_collide_pairs", "b2gpu_batch_create_bodies", "b2gpu_batch_create_fixtures", "b2gpu_batch_create_joints",
     "b2gpu_batch_joint_records", "b2gpu_batch_spawn_records", "b2gpu_batch_body_commands",
 ]
@@ -69,7 +69,7 @@ BODY_COMMAND_DTYPE = np.dtype([("world", "<i4"), ("body", "<i4"), ("op", "<i4"),
  CMD_SET_LINEAR_VELOCITY, CMD_SET_ANGULAR_VELOCITY, CMD_SET_TRANSFORM, CMD_SET_AWAKE, CMD_DESTROY_BODY,
  CMD_MOUSE_SET_TARGET, CMD_SET_FILTER, CMD_DESTROY_JOINT, CMD_SET_TYPE, CMD_SET_ACTIVE, CMD_SET_MASS_DATA,
  CMD_RESET_MASS_DATA, CMD_DESTROY_FIXTURE, CMD_SET_DAMPING, CMD_SET_GRAVITY_SCALE, CMD_SET_BULLET, CMD_SET_SLEEPING_ALLOWED,
- CMD_SET_FIXED_ROTATION, CMD_SET_SENSOR, CMD_SET_MATERIAL) = range(25)
+ CMD_SET_FIXED_ROTATION, CMD_SET_SENSOR, CMD_SET_MATERIAL, CMD_SET_DENSITY) = range(26)
 
 
 def put_filter(commands: np.ndarray, i: int, category_bits=1, mask_bits=0xffff, group_index=0):
@@ -136,6 +136,7 @@ def lib():
         L.b2gpu_scene_capacities.argtypes = [C.POINTER(CScene), i32, C.POINTER(BatchDesc)]
         L.b2gpu_batch_build_worlds.argtypes = [vp, C.POINTER(CScene), i32, i32, i32]
         L.b2gpu_host_polygon_build.argtypes = [C.POINTER(FixtureDef), vp, vp]
+        L.b2gpu_host_fixture_mass_data.argtypes = [C.POINTER(FixtureDef), vp, i32, vp]
         L.b2gpu_host_sincosf.argtypes = [vp, vp, vp, C.c_int64]
         L.b2gpu_host_sincosf_wide.argtypes = [vp, vp, vp, C.c_int64]
         L.b2gpu_sincosf.argtypes = [i32, vp, vp, vp, C.c_int64]
@@ -154,6 +155,18 @@ def host_polygon_build(fd: FixtureDef, verts):
     out = np.zeros(38, np.float32)
     n = lib().b2gpu_host_polygon_build(C.byref(fd), v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return n, out
+
+
+def host_fixture_mass_data(fd: FixtureDef, verts, density=None):
+    """b2gpu_host_fixture_mass_data: float32 [mass, I, center.x, center.y] of one fixture description (fd.firstVertex indexes
+    `verts`, the scene's vertex list) at `density` (default: fd.density) — the payload of CMD_SET_DENSITY."""
+    v = np.ascontiguousarray(verts if len(verts) else [0.0, 0.0], np.float32).reshape(-1)
+    one = FixtureDef.from_buffer_copy(fd)
+    if density is not None:
+        one.density = density
+    out = np.zeros(4, np.float32)
+    _check(lib().b2gpu_host_fixture_mass_data(C.byref(one), v.ctypes.data_as(C.c_void_p), len(v) // 2, out.ctypes.data_as(C.c_void_p)))
+    return out
 
 
 def collide_pairs(kind, shape_a, xf_a, shape_b, xf_b, device=0):

@@ -922,6 +922,19 @@ int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, f
     return sh.count;
 }
 
+int b2gpu_host_fixture_mass_data(const b2g_fixture_def* fd, const float* vertices, int32_t vertexCount, float* out) {
+    if (!fd || !out) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
+    b2g_fixture_def one = *fd;
+    one.body = 0;
+    int rc = ValidateFixtures(&one, 1, 1, vertices, vertexCount, "fixture");
+    if (rc != B2GPU_OK) return rc;
+    HostShape sh;
+    BuildShape(sh, one, vertices);
+    const MassData md = ComputeMass(sh, one.density);
+    out[0] = md.mass; out[1] = md.I; out[2] = md.center.x; out[3] = md.center.y;
+    return B2GPU_OK;
+}
+
 int b2gpu_host_body_mass_data(const b2g_scene* scene, int32_t body, float* out) {
     if (!scene || !out || body < 0 || body >= scene->bodyCount) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
     int rc = ValidateFixtures(scene->fixtures, scene->fixtureCount, scene->bodyCount, scene->vertices, scene->vertexCount, "scene");

@@ -834,6 +834,17 @@ __global__ void k_body_commands(Arena A, const b2gpu_body_command* __restrict__ 
                 bodyVel[b] = v;
                 ResetMassData(A, tile, lane, b);
             } break;
+            case B2GPU_CMD_SET_DENSITY: {  // b2Fixture::SetDensity (b2Fixture.h:313-317): the body's mass waits for ResetMassData
+                const int fx = c.wake;
+                Col<int> fixtureInfo = col(A.fixtureInfo, tile, A.NF, lane);
+                if (fx < 0 || fx >= A.fixtureCount[ws] || (fixtureInfo[fx] & 0xffff) != b || (fixtureInfo[fx] & kFixtureDestroyed)) {
+                    A.status[ws] |= B2GPU_STATUS_BAD_COMMAND;
+                    break;
+                }
+                col(A.fixtureMass, tile, A.NF, lane)[fx] = make_float4(c.v[0], c.p[0], c.p[1], c.v[1]);
+                const bool dense = c.v[0] != 0.0f || c.v[1] != 0.0f;
+                fixtureInfo[fx] = dense ? (fixtureInfo[fx] | kFixtureHasDensity) : (fixtureInfo[fx] & ~kFixtureHasDensity);
+            } break;
             case B2GPU_CMD_SET_SENSOR:
             case B2GPU_CMD_SET_MATERIAL: {
                 const int fx = c.wake;

@@ -335,6 +335,11 @@ public:
     void SetSensor(bool sensor);
     void SetFriction(float friction) { m_friction = friction; QueueMaterial(); }
     void SetRestitution(float restitution) { m_restitution = restitution; QueueMaterial(); }
+    // b2Fixture::SetDensity / GetDensity (b2Fixture.h:313-323): like the reference's, the body's mass only follows at the next
+    // b2Body::ResetMassData().  The fixture's b2MassData under the new density is computed on the host (b2Shape::ComputeMass,
+    // b2gpu_host_fixture_mass_data) and travels in the command.
+    void SetDensity(float density);
+    float GetDensity() const { return m_def.density; }
 
 private:
     friend class b2Body;
@@ -344,6 +349,8 @@ private:
     int32_t m_index = 0;
     void QueueMaterial();
     float m_friction = 0.2f, m_restitution = 0.0f;  // host copies: the device command carries both
+    b2g_fixture_def m_def;                          // the fixture as it was described, firstVertex = 0 into m_defVertices
+    std::vector<float> m_defVertices;
 };
 struct b2MassData {  // Collision/Shapes/b2Shape.h:27-38
     float mass = 0.0f;
@@ -388,6 +395,7 @@ public:
     const b2Vec<float, 2>& GetLinearVelocity() const;
     float GetAngularVelocity() const;
     bool IsAwake() const;
+    float GetMass() const;  // b2Body::GetMass (b2Body.h:530-533): m_mass as the last ResetMassData / SetMassData left it
     b2BodyType GetType() const { return m_type; }
     void* GetUserData() const { return m_userData; }
     b2World* GetWorld() const { return m_world; }
@@ -975,6 +983,8 @@ inline b2Fixture* b2Body::CreateFixture(const b2FixtureDef* def) {
     f->m_friction = def->friction;
     f->m_restitution = def->restitution;
     f->m_type = def->shape->GetType();
+    f->m_def = fd;
+    def->shape->Describe(f->m_def, f->m_defVertices);  // its own copy of the shape: SetDensity recomputes the mass data from it
     f->m_index = (int32_t)w.m_fixtures.size();
     w.m_firstProxy.push_back(w.m_proxyCount);
     // proxies: one per shape child (b2Fixture::CreateProxies, b2Fixture.cpp:124-139)
@@ -1047,6 +1057,24 @@ inline float b2Body::GetAngularVelocity() const {
     if (!B->IsBuilt()) B->BuildEarly();
     B->Refresh();
     return B->m_vel[B->Slot(this) * 4 + 2];
+}
+inline float b2Body::GetMass() const {
+    b2WorldBatch* B = m_world->m_batch;
+    b2World& w = *m_world;
+    if (!B->IsBuilt()) {  // scene still open: b2Body::ResetMassData over the fixtures recorded so far, on the host
+        b2g_scene sc;
+        std::memset(&sc, 0, sizeof(sc));
+        sc.bodyCount = (int32_t)w.m_bodyDefs.size(); sc.bodies = w.m_bodyDefs.data();
+        sc.fixtureCount = (int32_t)w.m_fixtureDefs.size(); sc.fixtures = w.m_fixtureDefs.data();
+        sc.vertexCount = (int32_t)(w.m_vertices.size() / 2); sc.vertices = w.m_vertices.data();
+        float md[4];
+        b2WorldBatch::Check(b2gpu_host_body_mass_data(&sc, m_index, md));
+        return md[0];
+    }
+    B->Flush();
+    std::vector<float> damp((size_t)B->m_maxBodies * 4);  // this world's B2GPU_F_BODY_DAMP rows: .w = m_mass
+    b2WorldBatch::Check(b2gpu_batch_download_field(B->m_handle, B2GPU_F_BODY_DAMP, damp.data(), w.m_index, 1));
+    return damp[(size_t)m_index * 4 + 3];
 }
 inline bool b2Body::IsAwake() const {
     b2WorldBatch* B = m_world->m_batch;
@@ -1273,6 +1301,14 @@ inline void b2Body::SetSleepingAllowed(bool flag) { m_world->m_batch->QueueEdit(
 inline void b2Body::SetFixedRotation(bool flag) { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_FIXED_ROTATION, flag ? 1 : 0, 0.0f, 0.0f, 0.0f, 0.0f); }
 inline void b2Fixture::SetSensor(bool sensor) {
     if (m_body) m_body->m_world->m_batch->QueueEdit(m_body, B2GPU_CMD_SET_SENSOR, m_index, sensor ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f);
+}
+inline void b2Fixture::SetDensity(float density) {
+    if (!m_body || !(density >= 0.0f)) return;  // b2Assert(b2IsValid(density) && density >= 0.0f)
+    m_def.density = density;
+    float md[4];
+    b2WorldBatch::Check(b2gpu_host_fixture_mass_data(&m_def, m_defVertices.empty() ? nullptr : m_defVertices.data(),
+                                                     (int32_t)(m_defVertices.size() / 2), md));
+    m_body->m_world->m_batch->QueueEdit(m_body, B2GPU_CMD_SET_DENSITY, m_index, md[0], md[1], md[2], md[3]);
 }
 inline void b2Fixture::QueueMaterial() {
     if (m_body) m_body->m_world->m_batch->QueueEdit(m_body, B2GPU_CMD_SET_MATERIAL, m_index, m_friction, m_restitution, 0.0f, 0.0f);

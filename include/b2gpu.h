@@ -98,6 +98,12 @@ enum {
                                             contacts follow at their next Update, as the reference reads the flag there) */
     B2GPU_CMD_SET_MATERIAL = 24,         /* wake = fixture index, v[0] = friction, v[1] = restitution   b2Fixture::SetFriction +
                                             SetRestitution (existing contacts keep their mixed values, like the reference) */
+    B2GPU_CMD_SET_DENSITY = 25,          /* wake = fixture index, v[0] = mass, v[1] = I, p = center: the fixture's b2MassData under
+                                            its NEW density (b2Shape::ComputeMass, b2gpu_host_fixture_mass_data computes it)
+                                            b2Fixture::SetDensity (b2Fixture.h:313-317): like the reference's call it does not
+                                            touch the body's mass, B2GPU_CMD_RESET_MASS_DATA does.  All-zero mass data = density 0
+                                            (b2Body::ResetMassData skips the fixture; for the massless edge / chain shapes the two
+                                            are the same arithmetic) */
     B2GPU_CMD_COUNT
 };
 typedef struct b2gpu_body_command {
@@ -400,6 +406,10 @@ int b2gpu_batch_joint_records(b2gpu_batch* batch, const uint32_t* words, int32_t
  * (Box2D/Collision/Shapes/b2PolygonShape.cpp:32-245, 354-437).  out: 8 vertices, 8 normals, centroid, then
  * mass, center.xy, I (38 floats); returns the vertex count. */
 int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, float* out);
+
+/* b2Fixture::GetMassData (Box2D/Dynamics/b2Fixture.h:347-350 -> b2Shape::ComputeMass at fd->density) of one fixture
+ * description, any shape type.  out: mass, I, center.x, center.y — the payload of B2GPU_CMD_SET_DENSITY.  Host code. */
+int b2gpu_host_fixture_mass_data(const b2g_fixture_def* fd, const float* vertices, int32_t vertexCount, float* out);
 
 /* b2Body::GetMass / GetInertia-about-the-centre / GetLocalCenter of one body of a scene description, i.e.
  * b2Body::ResetMassData (Box2D/Dynamics/b2Body.cpp:283-352) over the fixtures recorded so far.  out: mass, I, center.x,

@@ -334,6 +334,23 @@ void ref_world_set_filter(void* h, int fixture, int categoryBits, int maskBits, 
     rw->fixtures[fixture]->SetFilterData(f);
 }
 
+// b2Fixture::SetDensity (b2Fixture.h:313-317): the body's mass data waits for b2Body::ResetMassData (op 16)
+void ref_world_set_density(void* h, int fixture, float density) {
+    RefWorld* rw = (RefWorld*)h;
+    if (fixture < 0 || fixture >= (int)rw->fixtures.size() || !rw->fixtures[fixture]) return;
+    rw->fixtures[fixture]->SetDensity(density);
+}
+
+// b2Fixture::GetMassData: out = mass, I, center.x, center.y (the B2GPU_CMD_SET_DENSITY payload)
+int ref_world_fixture_mass_data(void* h, int fixture, float* out) {
+    RefWorld* rw = (RefWorld*)h;
+    if (fixture < 0 || fixture >= (int)rw->fixtures.size() || !rw->fixtures[fixture]) return -1;
+    b2MassData md;
+    rw->fixtures[fixture]->GetMassData(&md);
+    out[0] = md.mass; out[1] = md.I; out[2] = md.center.x; out[3] = md.center.y;
+    return 0;
+}
+
 // b2World::CreateJoint on a stepped world; returns the joint id.
 int ref_world_create_joint(void* h, const b2g_joint_def* d) {
     RefWorld* rw = (RefWorld*)h;

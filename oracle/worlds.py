@@ -64,6 +64,10 @@ def lib(kind="ref"):
             L.ref_world_create_body.restype = C.c_int
             L.ref_world_set_filter.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
             L.ref_world_set_filter.restype = None
+            L.ref_world_set_density.argtypes = [C.c_void_p, C.c_int, C.c_float]
+            L.ref_world_set_density.restype = None
+            L.ref_world_fixture_mass_data.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+            L.ref_world_fixture_mass_data.restype = C.c_int
             L.ref_world_create_joint.argtypes = [C.c_void_p, C.c_void_p]
             L.ref_world_create_joint.restype = C.c_int
             L.ref_world_create_fixture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -146,6 +150,17 @@ class RefWorld:
     def set_filter(self, fixture, category_bits, mask_bits, group_index):
         """b2Fixture::SetFilterData (live reference only)."""
         self.L.ref_world_set_filter(self.h, fixture, category_bits, mask_bits, group_index)
+
+    def set_density(self, fixture, density):
+        """b2Fixture::SetDensity (live reference only); the body's mass follows at the next ResetMassData."""
+        self.L.ref_world_set_density(self.h, fixture, density)
+
+    def fixture_mass_data(self, fixture):
+        """b2Fixture::GetMassData (live reference only): float32 [mass, I, center.x, center.y]."""
+        out = np.zeros(4, np.float32)
+        if self.L.ref_world_fixture_mass_data(self.h, fixture, _p(out)) != 0:
+            raise IndexError(fixture)
+        return out
 
     def create_joint(self, joint_def):
         """b2World::CreateJoint after stepping (live reference only); returns the joint id (creation order)."""

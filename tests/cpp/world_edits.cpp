@@ -55,6 +55,14 @@ int main() {
         std::printf("%08x %08x %08x %08x %08x %08x\n", bits(p[0]), bits(p[1]), bits(arm[w]->GetAngle()), bits(v[0]), bits(v[1]),
                     bits(arm[w]->GetAngularVelocity()));
     }
+    // world 1: b2Fixture::SetDensity only tells at the next ResetMassData (box 1.0 x 0.5 at density 1, plate 0.4 x 1.2 at 2 -> 4)
+    const float massBefore = arm[1]->GetMass();
+    extra[1]->SetDensity(4.0f);
+    const float massPending = arm[1]->GetMass();
+    arm[1]->ResetMassData();
+    const float massAfter = arm[1]->GetMass();
+    const bool densityOk = massBefore > 1.45f && massBefore < 1.47f && massPending == massBefore && massAfter > 2.41f && massAfter < 2.43f &&
+                           extra[1]->GetDensity() == 4.0f;
     // world 2: the joint goes, the arm drops onto the ground; then it loses its plate, turns kinematic, is switched off and on
     batch[2].DestroyJoint(joint[2]);
     for (int i = 0; i < 60; ++i) batch.Step(1.0f / 60.0f, 8, 3);
@@ -80,7 +88,8 @@ int main() {
     arm[2]->SetLinearVelocity(b2Vec<float, 2>{{0.0f, 1.0f}});
     for (int i = 0; i < 30; ++i) batch.Step(1.0f / 60.0f, 8, 3);
     const float yLifted = arm[2]->GetPosition()[1];
-    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
+    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && densityOk && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
+    if (!densityOk) std::printf("mass %g -> %g (pending) -> %g\n", massBefore, massPending, massAfter);
     (void)none;
     return 0;
 }

@@ -450,3 +450,63 @@ def test_world_edits_match_reference(oracles):
     assert counts.get(B.CMD_DESTROY_JOINT, 0) > 5, counts
     assert sum(counts.get(k, 0) for k in range(B.CMD_SET_DAMPING, B.CMD_SET_MATERIAL + 1)) > 30, counts
     batch.close()
+
+
+@pytest.mark.gpu
+def test_set_density_matches_reference(oracles):
+    """b2Fixture::SetDensity on running worlds (B2GPU_CMD_SET_DENSITY carries the fixture's mass data under the new density,
+    computed by the host layer): like the reference's call it changes nothing until b2Body::ResetMassData — sometimes issued
+    at once, sometimes steps later, sometimes as a side effect of another edit (SetType) — and from then on every float of the
+    world agrees with the live reference; b2Body::GetMass (B2GPU_F_BODY_DAMP .w) is compared as well."""
+    if not oracles.available("ref"):
+        pytest.skip("checked against the live reference")
+    scenes = [S.pyramid(4), S.mixed(3, bodies=10), S.hello_world(), S.sensors(1, bodies=6), S.pyramid(3, flags=NOCCD, jitter_seed=5),
+              S.mixed(11, flags=NOCCD, bodies=8)] * 2
+    refs = [oracles.RefWorld(s, record_events=True) for s in scenes]
+    batch = B.WorldBatch(scenes, event_mask=B.EVENT_ALL)
+    rng = S.LCG(4242)
+    f32 = lambda x: float(np.float32(x))  # noqa: E731
+    edits = resets = 0
+    mass_bad = []
+    for step in range(140):
+        if step % 4 == 1:
+            cmds = []
+            for w, (s, r) in enumerate(zip(scenes, refs)):
+                fx = int(rng.next_u() * len(s.fixtures)) % len(s.fixtures)
+                body = int(s.fixtures[fx].body)
+                density = 0.0 if rng.next_u() < 0.2 else f32(rng.uniform(0.2, 4.0))
+                md = B.host_fixture_mass_data(s.fixtures[fx], s.vertices, density)
+                r.set_density(fx, density)
+                assert r.fixture_mass_data(fx).view(np.uint32).tolist() == md.view(np.uint32).tolist()
+                cmds.append((w, body, B.CMD_SET_DENSITY, fx, (float(md[0]), float(md[1])), (float(md[2]), float(md[3]))))
+                edits += 1
+                u = rng.next_u()
+                if u < 0.6:
+                    other = int(rng.next_u() * s.body_count) % s.body_count  # any body: pending densities of earlier edits tell now
+                    for b in {body, other}:
+                        r.command(b, B.CMD_RESET_MASS_DATA)
+                        cmds.append((w, b, B.CMD_RESET_MASS_DATA, 0, (0.0, 0.0), (0.0, 0.0)))
+                        resets += 1
+                elif u < 0.7 and body != 0:  # SetType resets the mass data on its way
+                    for t in (S.KINEMATIC_BODY, S.DYNAMIC_BODY):
+                        r.command(body, B.CMD_SET_TYPE, t)
+                        cmds.append((w, body, B.CMD_SET_TYPE, t, (0.0, 0.0), (0.0, 0.0)))
+            batch.body_commands(np.array(cmds, dtype=B.BODY_COMMAND_DTYPE))
+        for r in refs:
+            r.step(1 / 60, 8, 3)
+        batch.step(1 / 60, 8, 3)
+        for w, r in enumerate(refs):
+            compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} step {step}")
+            if step % 4 == 1:
+                rb = r.bodies()
+                got = batch.field(B.F_BODY_DAMP, w, 1)[0, :rb.shape[0], 3]
+                if not same_bits(rb[:, 11], got):
+                    mass_bad.append((step, w, rb[:, 11].tolist(), got.tolist()))
+    assert (batch.status() == 0).all(), batch.status()
+    assert edits > 300 and resets > 200, (edits, resets)
+    assert not mass_bad, mass_bad[:2]
+    # a fixture index that is not the body's: refused like the other fixture commands
+    bad = np.array([(0, 1, B.CMD_SET_DENSITY, 0, (1.0, 1.0), (0.0, 0.0))], dtype=B.BODY_COMMAND_DTYPE)
+    batch.body_commands(bad)
+    assert batch.status()[0] & 4  # B2GPU_STATUS_BAD_COMMAND
+    batch.close()

@@ -198,6 +198,13 @@ def test_reference_harness_edit_calls(oracles):
     assert fx == len(s.fixtures) and (r.proxies()[1] >= 0).sum() == proxies + 1
     r.command(2, B.CMD_DESTROY_FIXTURE, fx)
     assert (r.proxies()[1] >= 0).sum() == proxies
+    # b2Fixture::SetDensity: GetMassData follows at once, the body's mass at the next ResetMassData
+    m_before = r.bodies()[3, 11]
+    fx3 = [i for i, f in enumerate(s.fixtures) if int(f.body) == 3][0]
+    r.set_density(fx3, 4.0)
+    assert r.bodies()[3, 11] == m_before and r.fixture_mass_data(fx3)[0] != m_before
+    r.command(3, B.CMD_RESET_MASS_DATA)
+    assert r.bodies()[3, 11] == r.fixture_mass_data(fx3)[0] != m_before
     # b2World::CreateJoint / DestroyJoint: ids by creation order
     jd = S.JointDef()
     jd.type, jd.bodyA, jd.bodyB, jd.length, jd.frequencyHz, jd.dampingRatio = S.JOINT_DISTANCE, 1, 2, 1.5, 3.0, 0.5
