@@ -878,32 +878,161 @@ int b2gpu_batch_create_fixtures(b2gpu_batch* batch, const b2gpu_attach* attach, 
     return SpawnOrAttach(batch, spawns.data(), targets.data(), count, fixtures, vertices, fixtureIndices);
 }
 
-// b2World::CreateJoint on running worlds: the def's columns, grouped by world, applied by k_create_joints.
+// The two joint classes whose constructors read the world (b2MouseJoint.cpp:33-52: body B's transform; b2GearJoint.cpp:47-133:
+// joint1 / joint2 and the poses of their four bodies): on a running world that state is on the device, so the world's rows
+// are read back and the constructor's arithmetic (the same lines as in Flatten above) is evaluated on them.
+namespace {
+struct LiveWorld {
+    int nb = 0, nj = 0;
+    std::vector<float> xf, sweep, damp, f0, f1, f2;
+    std::vector<int32_t> flags, ji;
+};
+int ReadLiveWorld(b2gpu_batch* batch, int world, bool joints, LiveWorld& lw) {
+    auto rows = [&](int field, auto& dst) -> int {
+        int32_t cap = 0, comps = 0;
+        int rc = b2gpu_batch_field_shape(batch, field, &cap, &comps);
+        if (rc != B2GPU_OK) return rc;
+        dst.assign((size_t)cap * comps + 4, 0);
+        return cap > 0 ? b2gpu_batch_download_field(batch, field, dst.data(), world, 1) : B2GPU_OK;
+    };
+    std::vector<int32_t> n;
+    int rc = rows(B2GPU_F_BODY_COUNT, n);
+    if (rc != B2GPU_OK) return rc;
+    lw.nb = n[0];
+    if ((rc = rows(B2GPU_F_BODY_XF, lw.xf)) != B2GPU_OK || (rc = rows(B2GPU_F_BODY_SWEEP, lw.sweep)) != B2GPU_OK ||
+        (rc = rows(B2GPU_F_BODY_DAMP, lw.damp)) != B2GPU_OK || (rc = rows(B2GPU_F_BODY_FLAGS, lw.flags)) != B2GPU_OK)
+        return rc;
+    if (!joints) return B2GPU_OK;
+    int32_t jointCap = 0;
+    if ((rc = b2gpu_batch_field_shape(batch, B2GPU_F_JOINT_I, &jointCap, nullptr)) != B2GPU_OK) return rc;
+    if (jointCap == 0) return B2GPU_OK;  // a batch without a joint arena: no joint1 / joint2 to be found
+    if ((rc = rows(B2GPU_F_JOINT_COUNT, n)) != B2GPU_OK) return rc;
+    lw.nj = n[0];
+    if ((rc = rows(B2GPU_F_JOINT_I, lw.ji)) != B2GPU_OK || (rc = rows(B2GPU_F_JOINT_F0, lw.f0)) != B2GPU_OK ||
+        (rc = rows(B2GPU_F_JOINT_F1, lw.f1)) != B2GPU_OK || (rc = rows(B2GPU_F_JOINT_F2, lw.f2)) != B2GPU_OK)
+        return rc;
+    return B2GPU_OK;
+}
+Xf LiveXf(const LiveWorld& lw, int b) {
+    Xf xf;
+    xf.p = V2(lw.xf[(size_t)b * 4], lw.xf[(size_t)b * 4 + 1]);
+    xf.q.s = lw.xf[(size_t)b * 4 + 2];
+    xf.q.c = lw.xf[(size_t)b * 4 + 3];
+    return xf;
+}
+bool LiveBody(const LiveWorld& lw, int b) { return b >= 0 && b < lw.nb && (lw.flags[b] & kBodyDestroyed) == 0; }
+
+int MouseRecord(const LiveWorld& lw, const b2g_joint_def& d, uint32_t* r) {
+    auto fb = [](float v) { uint32_t u; memcpy(&u, &v, 4); return u; };
+    if (!LiveBody(lw, d.bodyA) || !LiveBody(lw, d.bodyB) || d.bodyA == d.bodyB)
+        return b2gpu_host_set_error(B2GPU_ERR_INVALID, "joint references a body that does not exist (or connects a body to itself)");
+    const Vec2 target = V2(d.localAnchorA[0], d.localAnchorA[1]);
+    const Vec2 lB = MulT(LiveXf(lw, d.bodyB), target);  // m_localAnchorB = b2MulT(m_bodyB->GetTransform(), m_targetA)
+    r[0] = (uint32_t)(d.type | ((d.collideConnected ? 1 : 0) << 8));
+    r[1] = (uint32_t)(d.bodyA | (d.bodyB << 16));
+    r[2] = r[3] = 0;
+    r[4] = fb(target.x); r[5] = fb(target.y); r[6] = fb(lB.x); r[7] = fb(lB.y);
+    r[8] = fb(d.length); r[9] = fb(d.frequencyHz); r[10] = fb(d.dampingRatio); r[11] = fb(lw.damp[(size_t)d.bodyB * 4 + 3]);
+    for (int k = 12; k < 20; ++k) r[k] = 0;
+    return B2GPU_OK;
+}
+
+int GearRecord(const LiveWorld& lw, const b2g_joint_def& d, uint32_t* r) {
+    auto fb = [](float v) { uint32_t u; memcpy(&u, &v, 4); return u; };
+    int bodyOf[4];  // A, B, C, D
+    float side[2][6] = {{0.0f}};
+    int sideType[2];
+    float coordinate[2];
+    for (int k = 0; k < 2; ++k) {
+        const int id = k == 0 ? d.enableLimit : d.enableMotor;  // joint1 / joint2 by joint id
+        int row = -1;
+        for (int j = 0; j < lw.nj; ++j)
+            if (((lw.ji[(size_t)j * 4] >> 16) & 0xffff) == id) row = j;
+        if (id < 0 || row < 0) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "gear joint: joint1 / joint2 must be live joints of the world");
+        const int type = lw.ji[(size_t)row * 4] & 0xff;
+        if (type != B2G_JOINT_REVOLUTE && type != B2G_JOINT_PRISMATIC)
+            return b2gpu_host_set_error(B2GPU_ERR_INVALID, "gear joint: joint1 / joint2 must be revolute or prismatic");
+        const int g = lw.ji[(size_t)row * 4 + 1] & 0xffff, m = (lw.ji[(size_t)row * 4 + 1] >> 16) & 0xffff;
+        if (!LiveBody(lw, g) || !LiveBody(lw, m)) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "joint references a body that does not exist");
+        sideType[k] = type;
+        bodyOf[2 + k] = g;  // m_bodyC / m_bodyD = joint->GetBodyA()
+        bodyOf[k] = m;      // m_bodyA / m_bodyB = joint->GetBodyB()
+        const float* f0 = &lw.f0[(size_t)row * 4];
+        const float referenceAngle = lw.f1[(size_t)row * 4];
+        if (type == B2G_JOINT_REVOLUTE) {
+            side[k][0] = referenceAngle;
+            coordinate[k] = lw.sweep[(size_t)m * 4 + 2] - lw.sweep[(size_t)g * 4 + 2] - referenceAngle;
+        } else {
+            const Vec2 axis = V2(lw.f2[(size_t)row * 4 + 1], lw.f2[(size_t)row * 4 + 2]);  // m_localXAxisA, normalised when it was built
+            const Vec2 pG = V2(f0[0], f0[1]), lM = V2(f0[2], f0[3]);
+            const Xf ground = LiveXf(lw, g), moving = LiveXf(lw, m);
+            const Vec2 pM = MulT(ground.q, Mul(moving.q, lM) + (moving.p - ground.p));
+            coordinate[k] = Dot(pM - pG, axis);
+            side[k][0] = pG.x; side[k][1] = pG.y; side[k][2] = lM.x; side[k][3] = lM.y; side[k][4] = axis.x; side[k][5] = axis.y;
+        }
+    }
+    if (bodyOf[0] == bodyOf[1]) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "gear joint connects a body to itself");
+    const float ratio = d.motorSpeed;
+    const float constant = coordinate[0] + ratio * coordinate[1];
+    r[0] = (uint32_t)(d.type | ((d.collideConnected ? 1 : 0) << 8) | (sideType[0] << 11) | (sideType[1] << 13));
+    r[1] = (uint32_t)(bodyOf[0] | (bodyOf[1] << 16));
+    r[2] = 0;
+    r[3] = (uint32_t)(bodyOf[2] | (bodyOf[3] << 16));
+    for (int k = 0; k < 4; ++k) r[4 + k] = fb(side[0][k]);
+    r[8] = fb(side[0][4]); r[9] = fb(side[0][5]); r[10] = fb(ratio); r[11] = fb(constant);
+    for (int k = 0; k < 4; ++k) r[12 + k] = fb(side[1][k]);
+    r[16] = r[17] = 0;  // m_impulse
+    r[18] = fb(side[1][4]); r[19] = fb(side[1][5]);
+    return B2GPU_OK;
+}
+}  // namespace
+
+// b2World::CreateJoint on running worlds: the def's columns, grouped by world, applied by k_create_joints.  A gear or mouse
+// joint first sends what the call holds so far (its constructor has to see the joints and edits made before it).
 int b2gpu_batch_create_joints(b2gpu_batch* batch, const int32_t* worlds, const b2g_joint_def* defs, int32_t count, int32_t* jointIds) {
     if (!batch || count < 0 || (count > 0 && (!worlds || !defs || !jointIds))) return b2gpu_host_set_error(B2GPU_ERR_INVALID, "bad arguments");
     if (count == 0) return B2GPU_OK;
-    std::vector<int> order(count);
-    for (int i = 0; i < count; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return worlds[a] < worlds[b]; });
-    std::vector<uint32_t> words((size_t)count * 21);
-    for (int n = 0; n < count; ++n) {
-        const b2g_joint_def& d = defs[order[n]];
-        if (d.type == B2G_JOINT_GEAR || d.type == B2G_JOINT_MOUSE)
-            return b2gpu_host_set_error(B2GPU_ERR_UNSUPPORTED, "gear and mouse joints read body state when they are constructed: create them with the scene");
+    std::vector<int> pending;       // indices into defs, in call order
+    std::vector<uint32_t> records;  // 21 words each, parallel to `pending`
+    auto send = [&]() -> int {
+        const int n = (int)pending.size();
+        if (n == 0) return B2GPU_OK;
+        std::vector<int> order(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return worlds[pending[a]] < worlds[pending[b]]; });
+        std::vector<uint32_t> words((size_t)n * 21);
+        for (int i = 0; i < n; ++i) memcpy(&words[(size_t)i * 21], &records[(size_t)order[i] * 21], 21 * sizeof(uint32_t));
+        std::vector<int32_t> sorted(n);
+        int rc = b2gpu_batch_joint_records(batch, words.data(), n, sorted.data());
+        if (rc != B2GPU_OK) return rc;
+        for (int i = 0; i < n; ++i) jointIds[pending[order[i]]] = sorted[i];
+        pending.clear();
+        records.clear();
+        return B2GPU_OK;
+    };
+    for (int i = 0; i < count; ++i) {
+        const b2g_joint_def& d = defs[i];
         if (d.type < B2G_JOINT_REVOLUTE || d.type > B2G_JOINT_MOTOR)
             return b2gpu_host_set_error(B2GPU_ERR_UNSUPPORTED, "unknown joint type");
-        if (d.bodyA < 0 || d.bodyB < 0 || d.bodyA > 0xffff || d.bodyB > 0xffff || d.bodyA == d.bodyB)
-            return b2gpu_host_set_error(B2GPU_ERR_INVALID, "joint references a body that does not exist (or connects a body to itself)");
-        uint32_t* r = &words[(size_t)n * 21];
-        r[0] = (uint32_t)worlds[order[n]];
-        PlainJointColumns(d, r + 1);
-        for (int k = 17; k < 21; ++k) r[k] = 0;  // accumulated impulses start at zero
+        uint32_t r[21];
+        r[0] = (uint32_t)worlds[i];
+        if (d.type == B2G_JOINT_GEAR || d.type == B2G_JOINT_MOUSE) {
+            int rc = send();
+            if (rc != B2GPU_OK) return rc;
+            LiveWorld lw;
+            if ((rc = ReadLiveWorld(batch, worlds[i], d.type == B2G_JOINT_GEAR, lw)) != B2GPU_OK) return rc;
+            rc = d.type == B2G_JOINT_GEAR ? GearRecord(lw, d, r + 1) : MouseRecord(lw, d, r + 1);
+            if (rc != B2GPU_OK) return rc;
+        } else {
+            if (d.bodyA < 0 || d.bodyB < 0 || d.bodyA > 0xffff || d.bodyB > 0xffff || d.bodyA == d.bodyB)
+                return b2gpu_host_set_error(B2GPU_ERR_INVALID, "joint references a body that does not exist (or connects a body to itself)");
+            PlainJointColumns(d, r + 1);
+            for (int k = 17; k < 21; ++k) r[k] = 0;  // accumulated impulses start at zero
+        }
+        pending.push_back(i);
+        records.insert(records.end(), r, r + 21);
     }
-    std::vector<int32_t> sorted(count);
-    int rc = b2gpu_batch_joint_records(batch, words.data(), count, sorted.data());
-    if (rc != B2GPU_OK) return rc;
-    for (int n = 0; n < count; ++n) jointIds[order[n]] = sorted[n];
-    return B2GPU_OK;
+    return send();
 }
 
 int b2gpu_host_polygon_build(const b2g_fixture_def* fd, const float* vertices, float* out) {

@@ -469,8 +469,9 @@ public:
     b2World& operator=(const b2World&) = delete;
 
     b2Body* CreateBody(const b2BodyDef* def);
-    // b2World::CreateJoint (b2World.cpp:211-270) for all eleven joint types; on a running world every type but gear and
-    // mouse (they read body state when they are constructed: create those before the first Step)
+    // b2World::CreateJoint (b2World.cpp:211-270) for all eleven joint types, before the first Step or on the running world
+    // (gear and mouse joints read the world when they are constructed: b2gpu_batch_create_joints evaluates that on the
+    // world's current state)
     b2Joint* CreateJoint(const b2JointDef* def);
     // b2World::DestroyJoint (b2World.cpp:267-360); the b2Joint object stays allocated (its index is reserved)
     void DestroyJoint(b2Joint* joint);
@@ -815,8 +816,6 @@ inline b2Joint* b2World::CreateJoint(const b2JointDef* def) {
     b2World& w = B2_SELF;
     if (!def->bodyA || !def->bodyB) return nullptr;
     const bool running = w.m_batch->IsBuilt();
-    if (running && (def->type == b2JointType::GEAR_JOINT || def->type == b2JointType::MOUSE_JOINT))
-        throw std::runtime_error("gear and mouse joints read body state when they are constructed: create them before the first Step");
     b2g_joint_def d;
     std::memset(&d, 0, sizeof(d));
     d.bodyA = def->bodyA->GetIndex();

@@ -395,8 +395,11 @@ int b2gpu_batch_create_fixtures(b2gpu_batch* batch, const b2gpu_attach* attach, 
  * of both bodies' joint lists; if collideConnected is false the contacts between its two bodies are flagged for
  * filtering, so the next Step destroys them (:255-263).  Joints of one world are created in array order.
  * jointIds[i] = the joint's id (the handle B2GPU_CMD_DESTROY_JOINT takes), or -1 when the world's joint arena is full
- * (B2GPU_STATUS_SPAWN_OVERFLOW) — size it with b2gpu_batch_desc.maxJoints.  Gear and mouse joints read body state when
- * they are constructed and can only be created with the scene (B2GPU_ERR_UNSUPPORTED here).  Synchronises. */
+ * (B2GPU_STATUS_SPAWN_OVERFLOW) — size it with b2gpu_batch_desc.maxJoints.  Gear and mouse joints read the world when they
+ * are constructed (b2GearJoint.cpp:47-133: joint1 / joint2 — named by joint id in enableLimit / enableMotor, as in a scene —
+ * and their bodies' poses; b2MouseJoint.cpp:33-52: body B's transform): for them the call first applies the joints that
+ * precede them in `defs`, reads the world's body and joint rows back and evaluates the constructor on the host.  A bad def
+ * returns an error; joints that precede it in the call have been created by then.  Synchronises. */
 int b2gpu_batch_create_joints(b2gpu_batch* batch, const int32_t* worlds, const b2g_joint_def* defs, int32_t count,
                               int32_t* jointIds);
 /* Device-layer primitive under it: 21 words per joint (world, then the five 4-word joint columns). */

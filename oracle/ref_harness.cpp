@@ -356,6 +356,9 @@ int ref_world_create_joint(void* h, const b2g_joint_def* d) {
     RefWorld* rw = (RefWorld*)h;
     if (d->bodyA < 0 || d->bodyA >= (int)rw->bodies.size() || d->bodyB < 0 || d->bodyB >= (int)rw->bodies.size()) return -1;
     if (!rw->bodies[d->bodyA] || !rw->bodies[d->bodyB]) return -1;
+    if (d->type == B2G_JOINT_GEAR)  // joint1 / joint2 by joint id: they must still exist
+        for (int k : {d->enableLimit, d->enableMotor})
+            if (k < 0 || k >= (int)rw->joints.size() || !rw->joints[k]) return -1;
     add_joint(rw, *d);
     return (int)rw->joints.size() - 1;
 }

@@ -63,6 +63,21 @@ int main() {
     const float massAfter = arm[1]->GetMass();
     const bool densityOk = massBefore > 1.45f && massBefore < 1.47f && massPending == massBefore && massAfter > 2.41f && massAfter < 2.43f &&
                            extra[1]->GetDensity() == 4.0f;
+    // world 1: a mouse joint made on the running world (b2MouseJoint's constructor reads body B's transform) drags the arm,
+    // which swings about its pivot at (0, 5) with its origin 1 m away, to the top of that circle and holds it there
+    b2MouseJointDef mjd;
+    mjd.bodyA = ground[1];
+    mjd.bodyB = arm[1];
+    const b2Vec<float, 2> grab = arm[1]->GetPosition();
+    mjd.target = grab;
+    mjd.maxForce = 1000.0f * arm[1]->GetMass();
+    b2Joint* mouse = batch[1].CreateJoint(&mjd);
+    const b2Vec<float, 2> goal{{0.0f, 6.0f}};
+    if (mouse) mouse->SetTarget(goal);
+    arm[1]->SetAwake(true);
+    for (int i = 0; i < 45; ++i) batch.Step(1.0f / 60.0f, 8, 3);
+    const b2Vec<float, 2> held = arm[1]->GetPosition();
+    const bool mouseOk = mouse && grab[1] < 5.5f && held[1] > 5.95f && held[0] > -0.1f && held[0] < 0.1f;
     // world 2: the joint goes, the arm drops onto the ground; then it loses its plate, turns kinematic, is switched off and on
     batch[2].DestroyJoint(joint[2]);
     for (int i = 0; i < 60; ++i) batch.Step(1.0f / 60.0f, 8, 3);
@@ -88,7 +103,8 @@ int main() {
     arm[2]->SetLinearVelocity(b2Vec<float, 2>{{0.0f, 1.0f}});
     for (int i = 0; i < 30; ++i) batch.Step(1.0f / 60.0f, 8, 3);
     const float yLifted = arm[2]->GetPosition()[1];
-    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && densityOk && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
+    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && densityOk && mouseOk && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
+    if (!mouseOk) std::printf("mouse joint: grabbed at (%g, %g), now (%g, %g)\n", grab[0], grab[1], held[0], held[1]);
     if (!densityOk) std::printf("mass %g -> %g (pending) -> %g\n", massBefore, massPending, massAfter);
     (void)none;
     return 0;

@@ -510,3 +510,102 @@ def test_set_density_matches_reference(oracles):
     batch.body_commands(bad)
     assert batch.status()[0] & 4  # B2GPU_STATUS_BAD_COMMAND
     batch.close()
+
+
+def _late_mouse(ground, body, target, max_force, collide):
+    jd = S.JointDef()
+    jd.type, jd.bodyA, jd.bodyB, jd.collideConnected = S.JOINT_MOUSE, ground, body, collide
+    jd.localAnchorA[0], jd.localAnchorA[1] = float(np.float32(target[0])), float(np.float32(target[1]))
+    jd.length, jd.frequencyHz, jd.dampingRatio = max_force, 5.0, 0.7
+    return jd
+
+
+def _late_gear(joint1, joint2, ratio, body_a, body_b):
+    jd = S.JointDef()
+    jd.type, jd.bodyA, jd.bodyB = S.JOINT_GEAR, body_a, body_b
+    jd.enableLimit, jd.enableMotor, jd.motorSpeed = joint1, joint2, ratio
+    return jd
+
+
+@pytest.mark.gpu
+def test_gear_and_mouse_joints_on_running_worlds(oracles):
+    """b2World::CreateJoint of the two joint classes whose constructors read the world (b2GearJoint.cpp:47-133: joint1 / joint2
+    and their bodies' poses; b2MouseJoint.cpp:33-52: body B's transform) on worlds that have been stepping: the gears and the
+    mouse joint of the vehicles scene are created at step 20 instead of with the scene, together with a brand-new revolute
+    joint and a gear built on it in the same call; mouse joints grab boxes of running pyramids (collideConnected on and off);
+    b2MouseJoint::SetTarget keeps moving the targets; the late gear and its joint are destroyed again.  Every float of every
+    body and contact against the live reference, every step."""
+    if not oracles.available("ref"):
+        pytest.skip("checked against the live reference")
+    scenes, late = [], []
+    for seed in (1, 2, 3, 4, 5, 6):
+        s = S.vehicles(seed, flags=NOCCD if seed % 2 else S.WORLD_DEFAULT)
+        late.append([j for j in s.joints if int(j.type) in (S.JOINT_GEAR, S.JOINT_MOUSE)])
+        s.joints = [j for j in s.joints if int(j.type) not in (S.JOINT_GEAR, S.JOINT_MOUSE)]  # the gears' joint1 / joint2 precede them
+        scenes.append(s)
+    scenes += [S.pyramid(4), S.pyramid(3, flags=NOCCD, jitter_seed=3), S.pyramid(4, jitter_seed=8)]
+    refs = [oracles.RefWorld(s, record_events=True) for s in scenes]
+    batch = B.WorldBatch(scenes, event_mask=B.EVENT_ALL, joint_headroom=8)
+    rng = S.LCG(31337)
+    f32 = lambda x: float(np.float32(x))  # noqa: E731
+    mice = {}      # world -> body held by a mouse joint
+    late_ids = {}  # world -> (gear id, revolute id) of the pair created together
+    for step in range(130):
+        if step == 20:
+            new = []
+            for w, s in enumerate(scenes):
+                rb = refs[w].bodies()
+                if w < 6:
+                    n0 = len(s.joints)
+                    for jd in late[w]:
+                        if int(jd.type) == S.JOINT_MOUSE:  # grabbed where the crate is NOW
+                            b = int(jd.bodyB)
+                            jd = _late_mouse(int(jd.bodyA), b, (rb[b, 4] + 0.3, rb[b, 5] + 0.3), float(jd.length), 0)
+                            mice[w] = b
+                        new.append((w, jd))
+                    # a revolute joint between the ground and the motor joint's platform, and a gear between it and the first wheel pivot
+                    plat = [int(j.bodyB) for j in s.joints if int(j.type) == S.JOINT_MOTOR][0]
+                    pivot = [i for i, j in enumerate(s.joints) if int(j.type) == S.JOINT_REVOLUTE][0]
+                    rev = S.JointDef()
+                    rev.type, rev.bodyA, rev.bodyB = S.JOINT_REVOLUTE, 0, plat
+                    rev.localAnchorA[0], rev.localAnchorA[1] = f32(rb[plat, 4]), f32(rb[plat, 5])
+                    rev.referenceAngle = f32(rb[plat, 6])
+                    new.append((w, rev))
+                    rev_id = n0 + len(late[w])
+                    new.append((w, _late_gear(rev_id, pivot, 1.5, plat, int(s.joints[pivot].bodyB))))
+                    late_ids[w] = (rev_id + 1, rev_id)
+                else:
+                    b = s.body_count - 1 - (w - 6)
+                    new.append((w, _late_mouse(0, b, (rb[b, 4] + 0.2, rb[b, 5] + 0.4), 300.0, w % 2)))
+                    mice[w] = b
+            new = [x for x in new if x[0] >= 4] + [x for x in new if x[0] < 4]  # worlds out of order; each world's own order is kept
+            want = [refs[w].create_joint(jd) for (w, jd) in new]
+            got = batch.create_joints(new)
+            assert got.tolist() == want and min(want) >= 0, (got.tolist(), want)
+        if step > 20 and step % 9 == 0:
+            cmds = []
+            for w, b in sorted(mice.items()):
+                rb = refs[w].bodies()
+                t = (f32(rb[b, 4] + rng.uniform(-1.0, 1.0)), f32(rb[b, 5] + rng.uniform(-0.5, 1.5)))
+                refs[w].command(b, B.CMD_MOUSE_SET_TARGET, 1, t, (0.0, 0.0))
+                cmds.append((w, b, B.CMD_MOUSE_SET_TARGET, 1, t, (0.0, 0.0)))
+            batch.body_commands(np.array(cmds, dtype=B.BODY_COMMAND_DTYPE))
+        if step == 80:  # the gear first, then the joint it was built on (b2GearJoint.h:53)
+            cmds = []
+            for w, ids in sorted(late_ids.items()):
+                for j in ids:
+                    refs[w].command(0, B.CMD_DESTROY_JOINT, j)
+                    cmds.append((w, 0, B.CMD_DESTROY_JOINT, j, (0.0, 0.0), (0.0, 0.0)))
+            batch.body_commands(np.array(cmds, dtype=B.BODY_COMMAND_DTYPE))
+        for r in refs:
+            r.step(1 / 60, 8, 3)
+        batch.step(1 / 60, 8, 3)
+        for w, r in enumerate(refs):
+            compare_world(r, batch.bodies(w), batch.contacts(w), batch.proxies(w), batch.events(w), what=f"world {w} step {step}")
+    assert (batch.status() == 0).all(), batch.status()
+    # a gear on a joint that is gone, or that never was, is refused
+    with pytest.raises(B.B2GpuError):
+        batch.create_joints([(0, _late_gear(late_ids[0][1], 0, 1.0, 1, 2))])
+    with pytest.raises(B.B2GpuError):
+        batch.create_joints([(0, _late_gear(999, 0, 1.0, 1, 2))])
+    batch.close()
