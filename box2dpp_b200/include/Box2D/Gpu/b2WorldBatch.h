@@ -340,6 +340,15 @@ public:
     // b2gpu_host_fixture_mass_data) and travels in the command.
     void SetDensity(float density);
     float GetDensity() const { return m_def.density; }
+    // the getters beside them (b2Fixture.h:120-190): host copies of what the last setter / the definition said
+    float GetFriction() const { return m_friction; }
+    float GetRestitution() const { return m_restitution; }
+    bool IsSensor() const { return m_def.isSensor != 0; }
+    b2Filter GetFilterData() const {
+        b2Filter f;
+        f.categoryBits = (uint16_t)m_def.categoryBits; f.maskBits = (uint16_t)m_def.maskBits; f.groupIndex = (int16_t)m_def.groupIndex;
+        return f;
+    }
 
 private:
     friend class b2Body;
@@ -404,6 +413,20 @@ public:
     // body definition, which is what the joint defs' Initialize() helpers need
     b2Vec<float, 2> GetLocalPoint(const b2Vec<float, 2>& worldPoint) const;
     b2Vec<float, 2> GetLocalVector(const b2Vec<float, 2>& worldVector) const;
+    // b2Body::GetWorldPoint / GetWorldVector / GetLinearVelocityFromWorldPoint / FromLocalPoint (b2Body.h:557-587)
+    b2Vec<float, 2> GetWorldPoint(const b2Vec<float, 2>& localPoint) const;
+    b2Vec<float, 2> GetWorldVector(const b2Vec<float, 2>& localVector) const;
+    b2Vec<float, 2> GetLinearVelocityFromWorldPoint(const b2Vec<float, 2>& worldPoint) const;
+    b2Vec<float, 2> GetLinearVelocityFromLocalPoint(const b2Vec<float, 2>& localPoint) const {
+        return GetLinearVelocityFromWorldPoint(GetWorldPoint(localPoint));
+    }
+    // flag getters (b2Body.h:634-690): the device's flag word after the first Step, the definition before
+    bool IsBullet() const { return HasFlag(1 << 5, B2G_BD_BULLET); }
+    bool IsSleepingAllowed() const { return HasFlag(1 << 4, B2G_BD_ALLOW_SLEEP); }
+    bool IsFixedRotation() const { return HasFlag(1 << 6, B2G_BD_FIXED_ROTATION); }
+    bool IsActive() const { return HasFlag(1 << 7, B2G_BD_ACTIVE); }
+    float GetLinearDamping() const { return m_linearDamping; }
+    float GetAngularDamping() const { return m_angularDamping; }
     // Between-step edits (Dynamics/b2Body.h:738-833, 408-467, 634-653; b2Body.cpp:418-440).  Each call is queued as a
     // b2gpu_body_command in call order and applied on the device before the next Step / getter, with the
     // reference's semantics (type checks, wake rules, force only accumulates on awake bodies, SetTransform
@@ -438,6 +461,7 @@ private:
     friend class b2Joint;
     friend class b2Fixture;
     void SetMouseTarget(const b2Vec<float, 2>& target);  // b2Joint::SetTarget of the mouse joint attached to this body
+    bool HasFlag(int deviceBit, int defBit) const;
     void QueueDamping();
     float m_linearDamping = 0.0f, m_angularDamping = 0.0f;  // host copies: the device command carries both
     // While the scene is still being recorded (no Step yet) edits are queued and getters are answered on the host from
@@ -1107,6 +1131,29 @@ inline b2Vec<float, 2> b2Body::GetLocalVector(const b2Vec<float, 2>& v) const {
     }
     return b2Vec<float, 2>{{qc * v[0] + qs * v[1], -qs * v[0] + qc * v[1]}};  // b2MulT(q, v)
 }
+inline b2Vec<float, 2> b2Body::GetWorldPoint(const b2Vec<float, 2>& p) const {
+    const b2Vec<float, 2> x = GetLocalVector(b2Vec<float, 2>{{1.0f, 0.0f}});  // (q.c, -q.s)
+    const b2Vec<float, 2>& o = GetPosition();
+    const float qc = x[0], qs = -x[1];
+    return b2Vec<float, 2>{{(qc * p[0] - qs * p[1]) + o[0], (qs * p[0] + qc * p[1]) + o[1]}};  // b2Mul(xf, p)
+}
+inline b2Vec<float, 2> b2Body::GetWorldVector(const b2Vec<float, 2>& v) const {
+    const b2Vec<float, 2> x = GetLocalVector(b2Vec<float, 2>{{1.0f, 0.0f}});
+    const float qc = x[0], qs = -x[1];
+    return b2Vec<float, 2>{{qc * v[0] - qs * v[1], qs * v[0] + qc * v[1]}};  // b2Mul(q, v)
+}
+inline b2Vec<float, 2> b2Body::GetLinearVelocityFromWorldPoint(const b2Vec<float, 2>& wp) const {
+    const b2Vec<float, 2> c = GetWorldCenter(), v = GetLinearVelocity();
+    const float w = GetAngularVelocity();
+    const float dx = wp[0] - c[0], dy = wp[1] - c[1];
+    return b2Vec<float, 2>{{v[0] + (-w * dy), v[1] + w * dx}};  // m_linearVelocity + b2Cross(m_angularVelocity, worldPoint - m_sweep.c)
+}
+inline bool b2Body::HasFlag(int deviceBit, int defBit) const {
+    b2WorldBatch* B = m_world->m_batch;
+    if (!B->IsBuilt()) return (m_world->m_bodyDefs[(size_t)m_index].flags & defBit) != 0;
+    B->Refresh();
+    return (B->m_bodyFlags[B->Slot(this)] & deviceBit) != 0;
+}
 // The defs' Initialize() helpers (b2RevoluteJoint.cpp:38-45, b2PrismaticJoint.cpp:90-98, b2DistanceJoint.cpp:40-49)
 inline void b2RevoluteJointDef::Initialize(b2Body* bA, b2Body* bB, const b2Vec<float, 2>& anchor) {
     bodyA = bA; bodyB = bB;
@@ -1299,6 +1346,7 @@ inline void b2Body::SetBullet(bool flag) { m_world->m_batch->QueueEdit(this, B2G
 inline void b2Body::SetSleepingAllowed(bool flag) { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_SLEEPING_ALLOWED, flag ? 1 : 0, 0.0f, 0.0f, 0.0f, 0.0f); }
 inline void b2Body::SetFixedRotation(bool flag) { m_world->m_batch->QueueEdit(this, B2GPU_CMD_SET_FIXED_ROTATION, flag ? 1 : 0, 0.0f, 0.0f, 0.0f, 0.0f); }
 inline void b2Fixture::SetSensor(bool sensor) {
+    m_def.isSensor = sensor ? 1 : 0;
     if (m_body) m_body->m_world->m_batch->QueueEdit(m_body, B2GPU_CMD_SET_SENSOR, m_index, sensor ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f);
 }
 inline void b2Fixture::SetDensity(float density) {
@@ -1314,6 +1362,7 @@ inline void b2Fixture::QueueMaterial() {
 }
 inline void b2Fixture::SetFilterData(const b2Filter& filter) {
     if (!m_body) return;
+    m_def.categoryBits = filter.categoryBits; m_def.maskBits = filter.maskBits; m_def.groupIndex = filter.groupIndex;
     const int32_t bits = (int32_t)((uint32_t)filter.categoryBits | ((uint32_t)filter.maskBits << 16)), group = filter.groupIndex;
     float v[2];
     std::memcpy(&v[0], &bits, 4);  // the two integers travel as bit patterns in the command's float slots

@@ -56,6 +56,12 @@ int main(int argc, char** argv) {
         const b2Vec<float, 2> c = body->GetWorldCenter();
         REQUIRE(c[0] == 1.0f && c[1] == 4.0f);
         REQUIRE(body->GetPosition()[0] == 0.0f && body->GetPosition()[1] == 4.0f);
+        // the other getters of b2Body.h:530-690 are served from the definition as well
+        REQUIRE(body->GetMass() == 1.0f);  // 1.0 x 0.5 at density 2
+        REQUIRE(body->IsActive() && body->IsSleepingAllowed() && !body->IsBullet() && !body->IsFixedRotation());
+        const b2Vec<float, 2> wp = body->GetWorldPoint(b2Vec<float, 2>{{0.5f, -0.25f}}), wv = body->GetWorldVector(b2Vec<float, 2>{{0.0f, 2.0f}});
+        REQUIRE(wp[0] == 0.5f && wp[1] == 3.75f && wv[0] == 0.0f && wv[1] == 2.0f);
+        REQUIRE(!world.IsLocked());
 
         // a second body, and a joint whose def is initialised from the getters (b2RevoluteJointDef::Initialize)
         b2BodyDef bd2;
@@ -92,6 +98,18 @@ int main(int argc, char** argv) {
         std::printf("%08x %08x %08x %08x %08x %08x\n", bits(p[0]), bits(p[1]), bits(probe[w]->GetAngle()), bits(v[0]), bits(v[1]),
                     bits(probe[w]->GetAngularVelocity()));
     }
+    for (int w = 0; w < 2; ++w) {  // the same getters from the device: mass and flags as built, points through the body's transform
+        REQUIRE(probe[w]->GetMass() == 1.0f);
+        REQUIRE(probe[w]->IsActive() && probe[w]->IsSleepingAllowed() && !probe[w]->IsBullet() && !probe[w]->IsFixedRotation());
+        const b2Vec<float, 2> lp{{0.5f, -0.25f}};
+        const b2Vec<float, 2> back = probe[w]->GetLocalPoint(probe[w]->GetWorldPoint(lp));
+        REQUIRE(back[0] > lp[0] - 1e-5f && back[0] < lp[0] + 1e-5f && back[1] > lp[1] - 1e-5f && back[1] < lp[1] + 1e-5f);
+        const b2Vec<float, 2> c = probe[w]->GetWorldCenter(), v = probe[w]->GetLinearVelocity();
+        const b2Vec<float, 2> vc = probe[w]->GetLinearVelocityFromWorldPoint(c);
+        REQUIRE(vc[0] == v[0] && vc[1] == v[1]);
+    }
+    probe[0]->SetBullet(true);
+    REQUIRE(probe[0]->IsBullet() && !probe[1]->IsBullet());
     // a joint that connects a body to itself is an error (on the running world too), not a silent nullptr
     try {
         b2RevoluteJointDef jd;

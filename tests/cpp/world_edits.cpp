@@ -95,6 +95,9 @@ int main() {
     arm[2]->SetFixedRotation(false);
     extra[1]->SetSensor(false);
     extra[1]->SetFriction(0.2f);
+    extra[1]->SetFilterData(none);
+    const bool gettersOk = !extra[1]->IsSensor() && extra[1]->GetFriction() == 0.2f && extra[1]->GetRestitution() == 0.0f &&
+                           extra[1]->GetFilterData().maskBits == 0 && extra[1]->GetFilterData().categoryBits == 1;
     batch.Step(1.0f / 60.0f, 8, 3);
     arm[2]->SetActive(false);
     batch.Step(1.0f / 60.0f, 8, 3);
@@ -103,9 +106,8 @@ int main() {
     arm[2]->SetLinearVelocity(b2Vec<float, 2>{{0.0f, 1.0f}});
     for (int i = 0; i < 30; ++i) batch.Step(1.0f / 60.0f, 8, 3);
     const float yLifted = arm[2]->GetPosition()[1];
-    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && densityOk && mouseOk && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
+    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && densityOk && mouseOk && gettersOk && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
     if (!mouseOk) std::printf("mouse joint: grabbed at (%g, %g), now (%g, %g)\n", grab[0], grab[1], held[0], held[1]);
     if (!densityOk) std::printf("mass %g -> %g (pending) -> %g\n", massBefore, massPending, massAfter);
-    (void)none;
     return 0;
 }
