@@ -380,6 +380,21 @@ struct b2ContactEvent {  // what a b2Contact* tells a listener, by value
     int32_t childIndexA, childIndexB;
     int32_t pointCount;
 };
+// ---- queries: b2World::QueryAABB / RayCast over the batched device calls ----------------------------
+struct b2AABB {  // Collision/b2Collision.h:165-223
+    b2Vec<float, 2> lowerBound{{0.0f, 0.0f}};
+    b2Vec<float, 2> upperBound{{0.0f, 0.0f}};
+};
+class b2QueryCallback {  // Dynamics/b2WorldCallbacks.h:122-131
+public:
+    virtual ~b2QueryCallback() {}
+    virtual bool ReportFixture(b2Fixture* fixture) = 0;  // false ends the query
+};
+class b2RayCastCallback {  // Dynamics/b2WorldCallbacks.h:133-153
+public:
+    virtual ~b2RayCastCallback() {}
+    virtual float ReportFixture(b2Fixture* fixture, const b2Vec<float, 2>& point, const b2Vec<float, 2>& normal, float fraction) = 0;
+};
 class b2ContactListener {
 public:
     virtual ~b2ContactListener() {}
@@ -514,6 +529,14 @@ public:
     void SetAutoClearForces(bool flag) { SetFlag(B2G_WORLD_CLEAR_FORCES, flag); }
     bool GetAutoClearForces() const { return (m_flags & B2G_WORLD_CLEAR_FORCES) != 0; }
     b2Vec<float, 2> GetGravity() const { return m_gravity; }
+    // b2World::QueryAABB (b2World.cpp:965-972): ReportFixture once per proxy whose fat AABB overlaps `aabb` — the
+    // reference's set; the order is ascending proxy id where the reference reports in tree-traversal order.
+    void QueryAABB(b2QueryCallback* callback, const b2AABB& aabb);
+    // b2World::RayCast (b2World.cpp:1003-1020) for the closest-hit callback (the one that returns `fraction`): the nearest
+    // fixture along the ray is reported ONCE, with the reference's point / normal / fraction.  The reference also reports
+    // farther fixtures it meets on its way through the tree before the closest one clips the ray; a callback that collects
+    // every hit (returns 1) or skips fixtures (returns -1) needs those and is not served by this call.
+    void RayCast(b2RayCastCallback* callback, const b2Vec<float, 2>& point1, const b2Vec<float, 2>& point2);
     int32_t GetBodyCount() const;
     int32_t GetProxyCount() const;
     int32_t GetContactCount() const;
@@ -953,6 +976,40 @@ inline void b2World::DestroyBody(b2Body* body) {
 }
 inline void b2World::Step(float dt, int32_t vi, int32_t pi) { m_batch->Step(dt, vi, pi); }
 inline void b2World::SetContactListener(b2ContactListener* l) { m_batch->SetContactListener(l); }
+inline void b2World::QueryAABB(b2QueryCallback* callback, const b2AABB& aabb) {
+    b2World& w = B2_SELF;
+    b2WorldBatch* B = w.m_batch;
+    B->BuildEarly();
+    B->Flush();
+    b2gpu_aabb_query q;
+    q.world = w.m_index;
+    q.lower[0] = aabb.lowerBound[0]; q.lower[1] = aabb.lowerBound[1];
+    q.upper[0] = aabb.upperBound[0]; q.upper[1] = aabb.upperBound[1];
+    std::vector<int32_t> hits((size_t)std::max(w.m_proxyCount, 1));
+    int32_t count = 0;
+    b2WorldBatch::Check(b2gpu_batch_query_aabb(B->m_handle, &q, 1, (int32_t)hits.size(), &count, hits.data()));
+    count = std::min(count, (int32_t)hits.size());
+    for (int32_t i = 0; i < count; ++i) {
+        const int32_t fixture = hits[(size_t)i] & 0xffff;
+        if (fixture >= (int32_t)w.m_fixtures.size()) continue;
+        if (!callback->ReportFixture(w.m_fixtures[(size_t)fixture].get())) break;
+    }
+}
+inline void b2World::RayCast(b2RayCastCallback* callback, const b2Vec<float, 2>& p1, const b2Vec<float, 2>& p2) {
+    b2World& w = B2_SELF;
+    b2WorldBatch* B = w.m_batch;
+    B->BuildEarly();
+    B->Flush();
+    b2gpu_ray ray;
+    ray.world = w.m_index;
+    ray.p1[0] = p1[0]; ray.p1[1] = p1[1]; ray.p2[0] = p2[0]; ray.p2[1] = p2[1];
+    ray.maxFraction = 1.0f;
+    b2gpu_ray_hit hit;
+    b2WorldBatch::Check(b2gpu_batch_raycast_closest(B->m_handle, &ray, 1, &hit));
+    if (hit.fixture < 0 || hit.fixture >= (int32_t)w.m_fixtures.size()) return;
+    callback->ReportFixture(w.m_fixtures[(size_t)hit.fixture].get(), b2Vec<float, 2>{{hit.point[0], hit.point[1]}},
+                            b2Vec<float, 2>{{hit.normal[0], hit.normal[1]}}, hit.fraction);
+}
 inline int32_t b2World::GetProxyCount() const { return (m_owned ? m_owned->World(0) : *this).m_proxyCount; }
 inline int32_t b2World::GetContactCount() const {
     b2WorldBatch* batch = m_batch;

@@ -13,6 +13,26 @@ using namespace box2d;
 
 static unsigned bits(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 
+struct CountAll : b2QueryCallback {
+    int seen = 0, ofGround = 0;
+    b2Body* ground = nullptr;
+    bool stopAfterFirst = false;
+    bool ReportFixture(b2Fixture* f) override {
+        ++seen;
+        if (f->GetBody() == ground) ++ofGround;
+        return !stopAfterFirst;
+    }
+};
+struct Closest : b2RayCastCallback {
+    b2Fixture* fixture = nullptr;
+    b2Vec<float, 2> point{{0.0f, 0.0f}}, normal{{0.0f, 0.0f}};
+    float fraction = 1.0f;
+    float ReportFixture(b2Fixture* f, const b2Vec<float, 2>& p, const b2Vec<float, 2>& n, float fr) override {
+        fixture = f; point = p; normal = n; fraction = fr;
+        return fr;
+    }
+};
+
 int main() {
     b2WorldBatch batch(b2Vec<float, 2>{{0.0f, -10.0f}}, 3);
     b2Body* arm[3];
@@ -106,7 +126,24 @@ int main() {
     arm[2]->SetLinearVelocity(b2Vec<float, 2>{{0.0f, 1.0f}});
     for (int i = 0; i < 30; ++i) batch.Step(1.0f / 60.0f, 8, 3);
     const float yLifted = arm[2]->GetPosition()[1];
-    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && densityOk && mouseOk && gettersOk && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
+    // world 0 (ground box + the two-fixture arm on its pivot): b2World::QueryAABB over everything, then cut short; a ray
+    // dropped at x = 10 from y = 10 to y = -5 meets the top of the ground box (y = 1) at fraction 0.6
+    CountAll all, first;
+    all.ground = first.ground = ground[0];
+    first.stopAfterFirst = true;
+    b2AABB everything;
+    everything.lowerBound = {{-25.0f, -2.0f}};
+    everything.upperBound = {{25.0f, 12.0f}};
+    batch[0].QueryAABB(&all, everything);
+    batch[0].QueryAABB(&first, everything);
+    Closest ray;
+    batch[0].RayCast(&ray, b2Vec<float, 2>{{10.0f, 10.0f}}, b2Vec<float, 2>{{10.0f, -5.0f}});
+    const bool queriesOk = all.seen == 3 && all.ofGround == 1 && first.seen == 1 && ray.fixture && ray.fixture->GetBody() == ground[0] &&
+                           ray.fraction > 0.59999f && ray.fraction < 0.60001f && ray.normal[1] == 1.0f && ray.point[1] > 0.9999f &&
+                           ray.point[1] < 1.0001f;
+    if (!queriesOk) std::printf("queries: %d fixtures (%d of the ground), %d before the stop, ray fraction %g normal.y %g\n", all.seen,
+                                all.ofGround, first.seen, ray.fraction, ray.normal[1]);
+    std::printf("%s\n", (yFallen < 2.5f && yLifted > yFallen + 0.4f && densityOk && mouseOk && gettersOk && queriesOk && batch.GetStatus() == 0) ? "edits ok" : "edits FAILED");
     if (!mouseOk) std::printf("mouse joint: grabbed at (%g, %g), now (%g, %g)\n", grab[0], grab[1], held[0], held[1]);
     if (!densityOk) std::printf("mass %g -> %g (pending) -> %g\n", massBefore, massPending, massAfter);
     return 0;
