@@ -6,8 +6,8 @@
 // independent b2World objects that are built through the same calls and stepped together on one GPU by
 // b2gpu_batch_step (include/b2gpu.h), the replacement of b2World::Step (Box2D/Dynamics/b2World.cpp:888-954).
 // A b2World constructed on its own is a batch of one, so HelloWorld/HelloWorld.cpp:36-101 compiles against this
-// header unchanged apart from the include line and one call: world.SetContinuousPhysics(false) — the TOI
-// sub-stepper (b2World::SolveTOI) is not on the device path yet and the engine refuses to pretend otherwise.
+// header unchanged apart from the include line (continuous physics — b2World::SolveTOI — is on by default, like the
+// reference's; tests/cpp/hello_world_batch.cpp).
 //
 // Reference interfaces mirrored (paths under /root/reference/Box2D):
 //   b2Vec<T, N>, b2VecX / b2VecY              Common/b2Vec.h:17-72
@@ -17,12 +17,14 @@
 //                                             b2PolygonShape.h:48-60, b2ChainShape.h:48-61
 //   b2World                                   Dynamics/b2World.h:48-232
 //   b2ContactListener, b2ContactImpulse       Dynamics/b2WorldCallbacks.h:74-136
+//   b2QueryCallback, b2RayCastCallback        Dynamics/b2WorldCallbacks.h:122-153
+//   the eleven b2*JointDef, b2Joint           Dynamics/Joints/*.h
 //
 // Differences a caller must know:
 //   * The scene is recorded on the host until the first Step (or the first call that needs the device); from then on
 //     CreateBody / CreateFixture / CreateJoint / DestroyBody / DestroyFixture / DestroyJoint and the b2Body / b2Fixture
 //     setters below act on the running worlds with the reference's semantics (arena headroom: SetSpawnHeadroom,
-//     SetJointHeadroom).  Gear and mouse joints can only be created while the scene is open.
+//     SetJointHeadroom).
 //   * Shapes record HOW they were built (SetAsBox / Set / CreateChain ...); hulls, normals, mass data and fat
 //     AABBs are computed by the host layer of libb2gpu.so with the reference's arithmetic when the batch is built.
 //   * Listener callbacks are delivered after Step from the device's readback buffer, in the reference's order,
