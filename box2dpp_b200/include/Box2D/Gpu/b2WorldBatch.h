@@ -6,8 +6,8 @@
 // independent b2World objects that are built through the same calls and stepped together on one GPU by
 // b2gpu_batch_step (include/b2gpu.h), the replacement of b2World::Step (Box2D/Dynamics/b2World.cpp:888-954).
 // A b2World constructed on its own is a batch of one, so HelloWorld/HelloWorld.cpp:36-101 compiles against this
-// header unchanged apart from the include line (continuous physics — b2World::SolveTOI — is on by default, like the
-// reference's; tests/cpp/hello_world_batch.cpp).
+// header unchanged apart from the include line (tests/cpp/hello_world_batch.cpp; continuous physics — b2World::SolveTOI —
+// is on by default, like the reference's).
 //
 // Reference interfaces mirrored (paths under /root/reference/Box2D):
 //   b2Vec<T, N>, b2VecX / b2VecY              Common/b2Vec.h:17-72

@@ -1,7 +1,8 @@
 // HelloWorld/HelloWorld.cpp:30-107 of the reference, compiled against the B200 batch engine's mirror of the
 // reference API (box2dpp_b200/include/Box2D/Gpu/b2WorldBatch.h).  Differences from the reference file: the
-// include line, SetContinuousPhysics(false) (TOI is not on the device path), and the output format — bit
-// patterns instead of %4.2f so that the Python test can compare with the golden answers bit-for-bit.
+// include line, SetContinuousPhysics(false) (the golden answers this program is compared with were frozen with continuous
+// physics off; with it on — the default, like the reference's — the Python parity tests cover the same scene), and the
+// output format — bit patterns instead of %4.2f so that the Python test can compare with the golden answers bit-for-bit.
 //
 // Modes:  hello           the reference's main(): one b2World, 60 steps
 //         batch N ROWS    N pyramid worlds built through CreateBody / CreateFixture in a b2WorldBatch, with a
