@@ -36,7 +36,7 @@ enum {
     B2GPU_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product does not run on the CPU */
     B2GPU_ERR_CUDA = -2,        /* a CUDA runtime call failed */
     B2GPU_ERR_INVALID = -3,     /* bad argument */
-    B2GPU_ERR_UNSUPPORTED = -4, /* scene uses a feature outside the device path (sensors, TOI, joints) */
+    B2GPU_ERR_UNSUPPORTED = -4, /* a value outside what the device path builds (e.g. a joint type that is none of b2JointType 1-11) */
     B2GPU_ERR_CAPACITY = -5     /* a per-world capacity in the descriptor is too small */
 };
 
